@@ -1,0 +1,420 @@
+// gelato_b200.cu -- CUDA kernels (sm_100a) and the C ABI declared in
+// include/gelato_b200.h.
+//
+// Two fused kernels cover the whole NLP callback path:
+//   k_residuals : everything `objfunc` evaluates (Trajectory_Optimization.py:194-242)
+//   k_jacobian  : every x-dependent Jacobian value `sens` produces (:245-312)
+// Each is ONE launch per call; blocks take their role from a block table built
+// at plan creation (dynamics sections in chunks of nodes, aero rows, event
+// rows, linear rows).  blockIdx.y is the scenario index for batched solves.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see DESIGN.md H1;
+// gelato_selftest_unfused() verifies the flag at run time).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "plan_host.h"
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GB_THREADS)
+k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
+           double* __restrict__ vals_all) {
+  __shared__ BlockScratch sm;
+  const int scen = blockIdx.y;
+  const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
+  const double* x = x_all + (size_t)scen * P.n_vars;
+  double* vals = vals_all + (size_t)scen * P.n_vals;
+  jac_block_phase1(P, scen, bt, x, threadIdx.x, sm);
+  __syncthreads();
+  jac_block_phase2(P, scen, bt, x, vals, threadIdx.x, sm);
+}
+
+__global__ void __launch_bounds__(GB_THREADS)
+k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
+            double* __restrict__ g_all) {
+  __shared__ BlockScratch sm;
+  const int scen = blockIdx.y;
+  const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
+  const double* x = x_all + (size_t)scen * P.n_vars;
+  double* g = g_all + (size_t)scen * P.n_rows;
+  res_block_phase1(P, scen, bt, x, g, threadIdx.x, sm);
+  __syncthreads();
+  res_block_phase2(P, scen, bt, x, g, threadIdx.x, GB_THREADS, sm);
+}
+
+// probe: is a*b+c left unfused?  (1 + 2^-30)(1 - 2^-30) - 1 is 0 unfused, -2^-60 fused
+__global__ void k_unfused_probe(double a, double b, double c, double* out) { *out = a * b + c; }
+
+// FP64 issue-rate probes
+__global__ void k_fp64_fma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, b, c); a1 = __fma_rn(a1, b, c); a2 = __fma_rn(a2, b, c); a3 = __fma_rn(a3, b, c);
+    a4 = __fma_rn(a4, b, c); a5 = __fma_rn(a5, b, c); a6 = __fma_rn(a6, b, c); a7 = __fma_rn(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_fp64_muladd(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = __dadd_rn(__dmul_rn(a0, b), c); a1 = __dadd_rn(__dmul_rn(a1, b), c);
+    a2 = __dadd_rn(__dmul_rn(a2, b), c); a3 = __dadd_rn(__dmul_rn(a3, b), c);
+    a4 = __dadd_rn(__dmul_rn(a4, b), c); a5 = __dadd_rn(__dmul_rn(a5, b), c);
+    a6 = __dadd_rn(__dmul_rn(a6, b), c); a7 = __dadd_rn(__dmul_rn(a7, b), c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(GELATO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+struct GelatoPlan {
+  int device = 0;
+  PlanView view{};  // device pointers
+  std::vector<void*> owned;
+  int32_t* jac_blocks = nullptr;
+  int n_jac_blocks = 0;
+  int32_t* res_blocks = nullptr;
+  int n_res_blocks = 0;
+  double* vals_template = nullptr;       // [n_vals] (or [n_scen][n_vals])
+  long long vals_template_sstride = 0;
+  int n_scen_cfg = 1;
+  cudaStream_t stream = nullptr;
+  // staging for the host-buffer entry points
+  double *d_x = nullptr, *d_g = nullptr, *d_vals = nullptr;
+  double *h_x = nullptr, *h_out = nullptr;  // pinned
+  size_t cap_scen = 0;
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+template <typename T>
+static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
+  *dst = nullptr;
+  if (count == 0 || src == nullptr) return GELATO_OK;
+  void* d = nullptr;
+  CU(cudaMalloc(&d, count * sizeof(T)));
+  p->owned.push_back(d);
+  CU(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = static_cast<const T*>(d);
+  return GELATO_OK;
+}
+
+extern "C" {
+
+const char* gelato_last_error(void) { return g_err.c_str(); }
+
+int gelato_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
+  if (!d || !out) return fail(GELATO_ERR_ARG, "null argument");
+  if (d->n_sections <= 0 || d->n_nodes <= 0) return fail(GELATO_ERR_ARG, "empty problem");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GELATO_ERR_CUDA, "no CUDA device: the B200 kernels are the only evaluation path (no CPU fallback)");
+  CU(cudaSetDevice(device));
+  GelatoPlan* p = new GelatoPlan();
+  p->device = device;
+  PlanView& v = p->view;
+  planview_scalars(d, v);
+  const int S = v.S;
+  int rc;
+#define UP(field, src, count) if ((rc = upload(p, src, (size_t)(count), &v.field)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  UP(sec_i32, d->sec_i32, (size_t)S * GS_I32_COLS)
+  UP(sec_i64, d->sec_i64, (size_t)S * GS_I64_COLS)
+  UP(sec_f64, d->sec_f64, (size_t)S * GS_F64_COLS)
+  UP(d_pool, d->d_pool, d->d_pool_len)
+  UP(tau_pool, d->tau_pool, d->tau_pool_len)
+  UP(wind, d->wind, (size_t)d->n_wind * 3)
+  UP(ca, d->ca, (size_t)d->n_ca * 2)
+  UP(lin_i32, d->lin_i32, (size_t)d->n_lin * GL_I32_COLS)
+  UP(lin_f64, d->lin_f64, (size_t)d->n_lin * GL_F64_COLS)
+  UP(aero_i32, d->aero_i32, (size_t)d->n_aero * GA_I32_COLS)
+  UP(aero_i64, d->aero_i64, (size_t)d->n_aero * GA_I64_COLS)
+  UP(aero_f64, d->aero_f64, (size_t)d->n_aero * GA_F64_COLS)
+  UP(rc_aero, d->rc_aero, d->rc_aero ? (size_t)v.n_vars : 0)
+  UP(evt_i32, d->evt_i32, (size_t)d->n_evt * GE_I32_COLS)
+  UP(evt_i64, d->evt_i64, (size_t)d->n_evt * GE_I64_COLS)
+  UP(evt_f64, d->evt_f64, (size_t)d->n_evt * GE_F64_COLS)
+  const double* tmpl = nullptr;
+  if ((rc = upload(p, d->vals_template, (size_t)d->n_vals, &tmpl)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  p->vals_template = const_cast<double*>(tmpl);
+#undef UP
+
+  // block tables
+  std::vector<int32_t> jb, rb;
+  build_block_tables(d, jb, rb);
+  p->n_jac_blocks = (int)(jb.size() / BT_COLS);
+  p->n_res_blocks = (int)(rb.size() / BT_COLS);
+  const int32_t* tb = nullptr;
+  if ((rc = upload(p, jb.data(), jb.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  p->jac_blocks = const_cast<int32_t*>(tb);
+  if ((rc = upload(p, rb.data(), rb.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  p->res_blocks = const_cast<int32_t*>(tb);
+
+  CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&p->ev0));
+  CU(cudaEventCreate(&p->ev1));
+  *out = p;
+  return GELATO_OK;
+}
+
+int gelato_plan_set_scenarios(GelatoPlan* p, const GelatoScenarioDesc* sc) {
+  if (!p || !sc || sc->n_scen <= 0) return fail(GELATO_ERR_ARG, "bad scenario descriptor");
+  CU(cudaSetDevice(p->device));
+  PlanView& v = p->view;
+  int rc;
+  const double* dptr;
+  if (sc->sec_f64) {
+    if ((rc = upload(p, sc->sec_f64, (size_t)sc->n_scen * v.S * GS_F64_COLS, &dptr)) != GELATO_OK) return rc;
+    v.sec_f64 = dptr;
+    v.sec_f64_sstride = (long long)v.S * GS_F64_COLS;
+  }
+  if (sc->wind) {
+    if ((rc = upload(p, sc->wind, (size_t)sc->n_scen * v.n_wind * 3, &dptr)) != GELATO_OK) return rc;
+    v.wind = dptr;
+    v.wind_sstride = (long long)v.n_wind * 3;
+  }
+  if (sc->unit_mass) {
+    if ((rc = upload(p, sc->unit_mass, (size_t)sc->n_scen, &dptr)) != GELATO_OK) return rc;
+    v.unit_mass_scen = dptr;
+  }
+  if (sc->lin_const) {
+    if ((rc = upload(p, sc->lin_const, (size_t)sc->n_scen * v.n_lin, &dptr)) != GELATO_OK) return rc;
+    v.lin_const_scen = dptr;
+  }
+  if (sc->vals_template) {
+    if ((rc = upload(p, sc->vals_template, (size_t)sc->n_scen * v.n_vals, &dptr)) != GELATO_OK) return rc;
+    p->vals_template = const_cast<double*>(dptr);
+    p->vals_template_sstride = v.n_vals;
+  }
+  p->n_scen_cfg = sc->n_scen;
+  return GELATO_OK;
+}
+
+int gelato_plan_destroy(GelatoPlan* p) {
+  if (!p) return GELATO_OK;
+  cudaSetDevice(p->device);
+  for (void* d : p->owned) cudaFree(d);
+  if (p->d_x) cudaFree(p->d_x);
+  if (p->d_g) cudaFree(p->d_g);
+  if (p->d_vals) cudaFree(p->d_vals);
+  if (p->h_x) cudaFreeHost(p->h_x);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return GELATO_OK;
+}
+
+int32_t gelato_plan_n_vars(const GelatoPlan* p) { return p ? p->view.n_vars : 0; }
+int32_t gelato_plan_n_rows(const GelatoPlan* p) { return p ? p->view.n_rows : 0; }
+int64_t gelato_plan_n_vals(const GelatoPlan* p) { return p ? p->view.n_vals : 0; }
+int64_t gelato_plan_launch_count(const GelatoPlan* p) { return p ? p->launches : 0; }
+
+static int check_scen(GelatoPlan* p, int n_scen) {
+  if (!p) return fail(GELATO_ERR_ARG, "null plan");
+  if (n_scen <= 0) return fail(GELATO_ERR_ARG, "n_scen must be positive");
+  const bool per_scen = p->view.sec_f64_sstride || p->view.wind_sstride || p->view.unit_mass_scen ||
+                        p->view.lin_const_scen || p->vals_template_sstride;
+  if (per_scen && n_scen > p->n_scen_cfg)
+    return fail(GELATO_ERR_ARG, "n_scen exceeds the configured scenario blocks");
+  if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 (gridDim.y)");
+  return GELATO_OK;
+}
+
+int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev, int32_t n_scen, void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  dim3 grid(p->n_res_blocks, n_scen);
+  k_residuals<<<grid, GB_THREADS, 0, st>>>(p->view, p->res_blocks, x_dev, g_dev);
+  p->launches++;
+  CU(cudaGetLastError());
+  return GELATO_OK;
+}
+
+int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  // constants and D entries: device-to-device copy of the template, then the kernel
+  // overwrites every x-dependent slot
+  if (p->vals_template_sstride) {
+    CU(cudaMemcpyAsync(vals_dev, p->vals_template, (size_t)n_scen * p->view.n_vals * sizeof(double),
+                       cudaMemcpyDeviceToDevice, st));
+  } else {
+    for (int s = 0; s < n_scen; s++)
+      CU(cudaMemcpyAsync(vals_dev + (size_t)s * p->view.n_vals, p->vals_template,
+                         (size_t)p->view.n_vals * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  dim3 grid(p->n_jac_blocks, n_scen);
+  k_jacobian<<<grid, GB_THREADS, 0, st>>>(p->view, p->jac_blocks, x_dev, vals_dev);
+  p->launches++;
+  CU(cudaGetLastError());
+  return GELATO_OK;
+}
+
+static int ensure_staging(GelatoPlan* p, size_t n_scen) {
+  if (n_scen <= p->cap_scen) return GELATO_OK;
+  CU(cudaSetDevice(p->device));
+  if (p->d_x) cudaFree(p->d_x);
+  if (p->d_g) cudaFree(p->d_g);
+  if (p->d_vals) cudaFree(p->d_vals);
+  if (p->h_x) cudaFreeHost(p->h_x);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  p->d_x = p->d_g = p->d_vals = p->h_x = p->h_out = nullptr;
+  p->cap_scen = 0;
+  const PlanView& v = p->view;
+  const size_t nout = std::max<size_t>((size_t)v.n_rows, (size_t)v.n_vals);
+  CU(cudaMalloc(&p->d_x, n_scen * v.n_vars * sizeof(double)));
+  CU(cudaMalloc(&p->d_g, n_scen * v.n_rows * sizeof(double)));
+  CU(cudaMalloc(&p->d_vals, n_scen * (size_t)v.n_vals * sizeof(double)));
+  CU(cudaMallocHost(&p->h_x, n_scen * v.n_vars * sizeof(double)));
+  CU(cudaMallocHost(&p->h_out, n_scen * nout * sizeof(double)));
+  p->cap_scen = n_scen;
+  return GELATO_OK;
+}
+
+int gelato_eval_residuals(GelatoPlan* p, const double* x, double* g, int32_t n_scen) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!x || !g) return fail(GELATO_ERR_ARG, "null buffer");
+  if ((rc = ensure_staging(p, n_scen))) return rc;
+  const PlanView& v = p->view;
+  const size_t nx = (size_t)n_scen * v.n_vars, ng = (size_t)n_scen * v.n_rows;
+  memcpy(p->h_x, x, nx * sizeof(double));
+  CU(cudaMemcpyAsync(p->d_x, p->h_x, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  if ((rc = gelato_eval_residuals_dev(p, p->d_x, p->d_g, n_scen, p->stream))) return rc;
+  CU(cudaMemcpyAsync(p->h_out, p->d_g, ng * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  memcpy(g, p->h_out, ng * sizeof(double));
+  return GELATO_OK;
+}
+
+int gelato_eval_jacobian(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!x || !vals) return fail(GELATO_ERR_ARG, "null buffer");
+  if ((rc = ensure_staging(p, n_scen))) return rc;
+  const PlanView& v = p->view;
+  const size_t nx = (size_t)n_scen * v.n_vars, nv = (size_t)n_scen * (size_t)v.n_vals;
+  memcpy(p->h_x, x, nx * sizeof(double));
+  CU(cudaMemcpyAsync(p->d_x, p->h_x, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
+  CU(cudaMemcpyAsync(p->h_out, p->d_vals, nv * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  memcpy(vals, p->h_out, nv * sizeof(double));
+  return GELATO_OK;
+}
+
+int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
+                       float* avg_ms) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (reps <= 0 || !avg_ms) return fail(GELATO_ERR_ARG, "bad reps");
+  CU(cudaSetDevice(p->device));
+  if (which == 1) {  // template once; the timed region is the kernel alone
+    if ((rc = gelato_eval_jacobian_dev(p, x_dev, out_dev, n_scen, p->stream))) return rc;
+  }
+  CU(cudaStreamSynchronize(p->stream));
+  CU(cudaEventRecord(p->ev0, p->stream));
+  for (int i = 0; i < reps; i++) {
+    if (which == 0) {
+      dim3 grid(p->n_res_blocks, n_scen);
+      k_residuals<<<grid, GB_THREADS, 0, p->stream>>>(p->view, p->res_blocks, x_dev, out_dev);
+    } else {
+      dim3 grid(p->n_jac_blocks, n_scen);
+      k_jacobian<<<grid, GB_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, x_dev, out_dev);
+    }
+    p->launches++;
+  }
+  CU(cudaEventRecord(p->ev1, p->stream));
+  CU(cudaEventSynchronize(p->ev1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  *avg_ms = ms / reps;
+  return GELATO_OK;
+}
+
+int gelato_selftest_unfused(int device, int* ok) {
+  if (!ok) return fail(GELATO_ERR_ARG, "null");
+  CU(cudaSetDevice(device));
+  double* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double)));
+  k_unfused_probe<<<1, 1>>>(1.0 + 0x1p-30, 1.0 - 0x1p-30, -1.0, d);
+  double h = 1.0;
+  CU(cudaMemcpy(&h, d, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *ok = (h == 0.0);
+  return GELATO_OK;
+}
+
+int gelato_fp64_peak(int device, double* tflops_fma, double* tflops_nofma) {
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float ms;
+  for (int pass = 0; pass < 2; pass++) {
+    k_fp64_fma<<<blocks, threads>>>(d, iters);  // warm-up on pass 0
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(e0));
+    k_fp64_fma<<<blocks, threads>>>(d, iters);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (tflops_fma) *tflops_fma = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    k_fp64_muladd<<<blocks, threads>>>(d, iters);
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(e0));
+    k_fp64_muladd<<<blocks, threads>>>(d, iters);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (tflops_nofma) *tflops_nofma = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return GELATO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+/* physics.h -- the 3-DoF launch-vehicle physics leaves, written for one GPU
+ * thread per (node x perturbation column).
+ *
+ * Each function states which reference routine it replaces.  Values are
+ * bit-identical to the reference's formulas evaluated in IEEE binary64 with
+ * unfused multiply-add (the reference is built for baseline x86-64, no FMA:
+ * /root/reference/CMakeLists.txt:8,41), with the elementary functions taken
+ * from gmath.h.  Compile with nvcc -fmad=false.
+ *
+ * Unlike the reference, common sub-expressions are evaluated once per thread:
+ * one geodetic conversion for the altitude, one US-76 layer lookup shared by
+ * temperature / pressure / density / speed of sound, one sincos of the Earth
+ * rotation angle shared by every frame rotation
+ * (reference recomputes them: pybind_dynamics.cpp:42-68 calls ecef2geodetic
+ * twice, Air::us76_params five times, cos/sin(omega t) ~10 times).
+ *
+ * The header is host+device so the very same code can be stepped through by
+ * the host emulator in tests/emu (test harness only; the product library only
+ * ever launches it on the GPU).
+ */
+#ifndef GELATO_B200_PHYSICS_H_
+#define GELATO_B200_PHYSICS_H_
+
+#include "gmath.h"
+
+#define P_HD GM_HD
+
+#define P_PI 3.14159265358979323846
+#define P_MU 3.986004418e14
+#define P_OMEGA 7.2921151467e-5
+#define P_RA 6378137.0
+#define P_F (1.0 / 298.257223563)
+#define P_RB (P_RA * (1.0 - P_F))
+#define P_E2 ((P_RA * P_RA - P_RB * P_RB) / P_RA / P_RA)
+#define P_EP2 ((P_RA * P_RA - P_RB * P_RB) / P_RB / P_RB)
+
+struct Vec3 {
+  double x, y, z;
+};
+struct Quat {
+  double w, x, y, z;
+};
+
+P_HD Vec3 v3(double x, double y, double z) {
+  Vec3 r;
+  r.x = x; r.y = y; r.z = z;
+  return r;
+}
+P_HD Quat q4(double w, double x, double y, double z) {
+  Quat r;
+  r.w = w; r.x = x; r.y = y; r.z = z;
+  return r;
+}
+
+/* Eigen-style 3-vector reductions, order (a0 + a1) + a2 (see oracle_leaves.cpp) */
+P_HD double dot3(Vec3 a, Vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+P_HD double norm3(Vec3 a) { return gm_sqrt(dot3(a, a)); }
+P_HD Vec3 cross3(Vec3 a, Vec3 b) {
+  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+P_HD Vec3 sub3(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+P_HD Vec3 add3(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+P_HD Vec3 scale3(double s, Vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+P_HD Vec3 div3(Vec3 a, double s) { return v3(a.x / s, a.y / s, a.z / s); }
+P_HD Vec3 normalized3(Vec3 a) { /* Eigen normalized() */
+  double z = dot3(a, a);
+  if (z > 0.0) return div3(a, gm_sqrt(z));
+  return a;
+}
+
+/* wrapper_coordinate.hpp:50-57 quatmult */
+P_HD Quat quatmult(Quat q, Quat p) {
+  return q4(q.w * p.w - q.x * p.x - q.y * p.y - q.z * p.z,
+            q.w * p.x + q.x * p.w + q.y * p.z - q.z * p.y,
+            q.w * p.y - q.x * p.z + q.y * p.w + q.z * p.x,
+            q.w * p.z + q.x * p.y - q.y * p.x + q.z * p.w);
+}
+/* Eigen::Quaterniond operator* (Coordinate.cpp:104-106) */
+P_HD Quat eigen_quat_prod(Quat a, Quat b) {
+  return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z,
+            a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+            a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x);
+}
+P_HD Quat quatconj(Quat q) { return q4(q.w, -q.x, -q.y, -q.z); }
+/* wrapper_coordinate.hpp:70-78 quatrot */
+P_HD Vec3 quatrot(Quat q, Vec3 v) {
+  Quat vq = q4(0.0, v.x, v.y, v.z);
+  Quat r = quatmult(quatconj(q), quatmult(vq, q));
+  return v3(r.x, r.y, r.z);
+}
+
+/* ---- geodesy (Earth.cpp:49-61) ------------------------------------------ */
+struct Geodetic {
+  double lat, lon, alt; /* radians, radians, metres */
+};
+/* WANT: bit0 altitude, bit1 longitude (latitude is always produced) */
+template <int WANT>
+P_HD Geodetic ecef2geodetic(Vec3 r) {
+  Geodetic g;
+  double p = gm_sqrt(r.x * r.x + r.y * r.y);
+  double theta = gm_atan2(r.z * P_RA, p * P_RB);
+  double st, ct;
+  gm_sincos(theta, &st, &ct);
+  g.lat = gm_atan2(r.z + P_EP2 * P_RB * (st * st * st), p - P_E2 * P_RA * (ct * ct * ct));
+  g.lon = 0.0;
+  g.alt = 0.0;
+  if (WANT & 2) g.lon = gm_atan2(r.y, r.x);
+  if (WANT & 1) {
+    double sl, cl;
+    gm_sincos(g.lat, &sl, &cl);
+    double N = P_RA / gm_sqrt(1.0 - P_E2 * sl * sl);
+    g.alt = p / cl - N;
+  }
+  return g;
+}
+
+/* Coordinate.cpp:41-59 with cos/sin(omega t) supplied */
+P_HD Vec3 rot_ecef2eci(Vec3 a, double c, double s) { return v3(a.x * c - a.y * s, a.x * s + a.y * c, a.z); }
+P_HD Vec3 rot_eci2ecef(Vec3 a, double c, double s) { return v3(a.x * c + a.y * s, -a.x * s + a.y * c, a.z); }
+
+/* Coordinate.cpp:69-73 vel_eci2ecef */
+P_HD Vec3 vel_eci2ecef_cs(Vec3 vel, Vec3 pos, double c, double s) {
+  Vec3 w = v3(0.0, 0.0, P_OMEGA);
+  return rot_eci2ecef(sub3(vel, cross3(w, pos)), c, s);
+}
+/* Coordinate.cpp:61-67 vel_ecef2eci */
+P_HD Vec3 vel_ecef2eci_cs(Vec3 vel_ecef, Vec3 pos_ecef, double c, double s) {
+  Vec3 pos_eci = rot_ecef2eci(pos_ecef, c, s);
+  Vec3 vg = rot_ecef2eci(vel_ecef, c, s);
+  Vec3 w = v3(0.0, 0.0, P_OMEGA);
+  return add3(vg, cross3(w, pos_eci));
+}
+
+/* Coordinate.cpp:85-98 quat_ecef2ned from geodetic lat/lon */
+P_HD Quat quat_ecef2ned_ll(double lat, double lon) {
+  double s_hl, c_hl, s_hp, c_hp;
+  gm_sincos(lon / 2.0, &s_hl, &c_hl);
+  gm_sincos(lat / 2.0, &s_hp, &c_hp);
+  double r2 = gm_sqrt(2.0);
+  return q4(c_hl * (c_hp - s_hp) / r2, s_hl * (c_hp + s_hp) / r2, -c_hl * (c_hp + s_hp) / r2,
+            s_hl * (c_hp - s_hp) / r2);
+}
+
+/* Coordinate.cpp:104-110 quat_ned2eci(pos_eci, t); c,s = cos/sin(omega t) */
+P_HD Quat quat_ned2eci_cs(Vec3 pos_eci, double wt, double c, double s) {
+  double sh, ch;
+  gm_sincos(wt / 2.0, &sh, &ch);
+  Quat q_eci2ecef = q4(ch, 0.0, 0.0, sh);
+  Geodetic g = ecef2geodetic<2>(rot_eci2ecef(pos_eci, c, s));
+  Quat q = eigen_quat_prod(q_eci2ecef, quat_ecef2ned_ll(g.lat, g.lon));
+  return quatconj(q);
+}
+
+/* ---- gravity (gravity.cpp:11-57) ---------------------------------------- */
+P_HD Vec3 gravity_eci(Vec3 pos) {
+  const double a = 6378137.0, one_f = 298.257223563, mu = 3.986004418e14;
+  const double barC20 = -0.484165371736e-3;
+  const double f = 1.0 / one_f;
+  const double b = a * (1.0 - f);
+  double x = pos.x, y = pos.y, z = pos.z;
+  double r = gm_sqrt(x * x + y * y + z * z);
+  double irx, iry, irz;
+  if (r == 0.0) {
+    irx = iry = irz = 0.0;
+  } else {
+    irx = x / r;
+    iry = y / r;
+    irz = z / r;
+  }
+  double s5 = gm_sqrt(5.0);
+  double barP20 = s5 * (3.0 * irz * irz - 1.0) * 0.5;
+  double barP20d = s5 * 3.0 * irz;
+  if (r < b) r = b;
+  double g_ir = -mu / (r * r) * (1.0 + barC20 * (a / r) * (a / r) * (3.0 * barP20 + irz * barP20d));
+  double g_iz = mu / (r * r) * (a / r) * (a / r) * barC20 * barP20d;
+  return v3(g_ir * irx, g_ir * iry, g_ir * irz + g_iz);
+}
+
+/* ---- US Standard Atmosphere 1976 (Air.cpp:28-111) ------------------------ */
+struct AirState {
+  double T, P, rho, a;
+};
+
+P_HD double geopotential_altitude(double z) {
+  if (z < 86000.0) return 1.0 * (6356766.0 * z) / (6356766.0 + z);
+  return z;
+}
+
+P_HD void us76_layer(double h, double* Hb, double* Lmb, double* Tmb, double* Pb, double* R) {
+  /* last layer whose base is <= h; layer 0 when h is below every base (Air.cpp:56-60).
+   * Branch ladder instead of a table: no local-memory indexing on the GPU. */
+  const double Rstar = 8314.32;
+  double hb = 0.0, l = -0.0065, t = 288.15, p = 101325.0, m = 28.9644;
+  if (h >= 11000.0) { hb = 11000.0; l = 0.0; t = 216.65; p = 22632.0; }
+  if (h >= 20000.0) { hb = 20000.0; l = 0.001; t = 216.65; p = 5474.9; }
+  if (h >= 32000.0) { hb = 32000.0; l = 0.0028; t = 228.65; p = 868.02; }
+  if (h >= 47000.0) { hb = 47000.0; l = 0.0; t = 270.65; p = 110.91; }
+  if (h >= 51000.0) { hb = 51000.0; l = -0.0028; t = 270.65; p = 66.939; }
+  if (h >= 71000.0) { hb = 71000.0; l = -0.002; t = 214.65; p = 3.9564; }
+  if (h >= 86000.0) { hb = 86000.0; l = 0.0; t = 186.8673; p = 0.37338; m = 28.9522; }
+  if (h >= 91000.0) { hb = 91000.0; l = 0.0025; t = 186.8673; p = 0.15381; m = 28.89; }
+  if (h >= 110000.0) { hb = 110000.0; l = 0.012; t = 240.0; p = 7.1042e-3; m = 27.27; }
+  if (h >= 120000.0) { hb = 120000.0; l = 0.012; t = 360.0; p = 2.5382e-3; m = 26.20; }
+  *Hb = hb; *Lmb = l; *Tmb = t; *Pb = p; *R = Rstar / m;
+}
+
+/* WANT: bit0 pressure+density, bit1 speed of sound */
+template <int WANT>
+P_HD AirState us76(double h) {
+  const double g0 = 9.80665, r0 = 6356766.0;
+  double Hb, Lmb, Tmb, Pb, R;
+  us76_layer(h, &Hb, &Lmb, &Tmb, &Pb, &R);
+  AirState s;
+  if (h <= 91000.0) {
+    s.T = Tmb + Lmb * (h - Hb);
+  } else if (h <= 110000.0) {
+    const double Tc = 263.1905, A = -76.3232, a = -19942.9;
+    s.T = Tc + A * gm_sqrt(1.0 - (h - 91000.0) * (h - 91000.0) / a / a);
+  } else if (h <= 120000.0) {
+    s.T = Tmb + Lmb * (h - Hb);
+  } else {
+    const double Tinf = 1000.0;
+    double xi = (h - Hb) * (r0 + Hb) / (r0 + h);
+    s.T = Tinf - (Tinf - Tmb) * gm_exp(-0.01875e-3 * xi);
+  }
+  s.P = 0.0;
+  s.rho = 0.0;
+  s.a = 0.0;
+  if (WANT & 1) {
+    if (gm_fabs(Lmb) > 1.0e-6)
+      s.P = Pb * gm_pow((Tmb + Lmb * (h - Hb)) / Tmb, -g0 / Lmb / R);
+    else
+      s.P = Pb * gm_exp(g0 / R * (Hb - h) / Tmb);
+    s.rho = s.P / R / s.T;
+  }
+  if (WANT & 2) s.a = gm_sqrt(1.4 * R * s.T);
+  return s;
+}
+
+/* ---- table interpolation (wrapper_utils.hpp:51-87) ----------------------- */
+/* xp[i*stride], yp[i*stride]; lower_bound then idx-1 (x == xp[k] uses the interval
+ * below; x == xp[0] would read xp[-1] in the reference -- defined here as interval 0,
+ * like the oracle). */
+P_HD double interp_table(double x, const double* xp, const double* yp, int n, int stride) {
+  if (x < xp[0]) return yp[0];
+  if (x > xp[(n - 1) * stride]) return yp[(n - 1) * stride];
+  int lo = 0, cnt = n;
+  while (cnt > 0) {
+    int step = cnt >> 1;
+    int it = lo + step;
+    if (xp[it * stride] < x) {
+      lo = it + 1;
+      cnt -= step + 1;
+    } else {
+      cnt = step;
+    }
+  }
+  int idx = lo - 1;
+  if (idx < 0) idx = 0;
+  double x_lower = xp[idx * stride], x_upper = xp[(idx + 1) * stride];
+  double y_lower = yp[idx * stride], y_upper = yp[(idx + 1) * stride];
+  double alpha = (x - x_lower) / (x_upper - x_lower);
+  return y_lower + alpha * (y_upper - y_lower);
+}
+
+/* ---- air-relative velocity shared by dynamics and the aero constraints ---- */
+struct Tables {
+  const double* wind; /* [n_wind][3]: altitude, wind_n, wind_e */
+  int n_wind;
+  const double* ca; /* [n_ca][2]: mach, CA */
+  int n_ca;
+};
+
+struct AirRel {
+  Vec3 va;        /* air-relative velocity, ECI axes */
+  double alt_gp;  /* geopotential altitude */
+};
+
+/* pybind_dynamics.cpp:43-53 / wrapper_utils.hpp:93-101: pos/vel dimensional, t as
+ * the caller passes it (the dynamics pass NON-dimensional node times -- reference
+ * quirk A.5-1 -- the aero constraints pass seconds). */
+P_HD AirRel air_relative(Vec3 pos, Vec3 vel, double t, const Tables& tb) {
+  AirRel o;
+  Geodetic g = ecef2geodetic<1>(pos); /* ECI fed to ecef2geodetic: quirk A.5-2 */
+  o.alt_gp = geopotential_altitude(g.alt);
+  double wt = P_OMEGA * t;
+  double s, c;
+  gm_sincos(wt, &s, &c);
+  Vec3 vel_ecef = vel_eci2ecef_cs(vel, pos, c, s);
+  Vec3 wind_ned = v3(interp_table(o.alt_gp, tb.wind, tb.wind + 1, tb.n_wind, 3),
+                     interp_table(o.alt_gp, tb.wind, tb.wind + 2, tb.n_wind, 3), 0.0);
+  Vec3 wind_eci = quatrot(quat_ned2eci_cs(pos, wt, c, s), wind_ned);
+  o.va = sub3(rot_ecef2eci(vel_ecef, c, s), wind_eci);
+  return o;
+}
+
+/* ---- dynamics right-hand sides (pybind_dynamics.cpp:30-106) -------------- */
+struct SecParam {
+  double thrust, massflow, ref_area, nozzle_area;
+};
+struct Units {
+  double mass, pos, vel, u, t, dx;
+};
+
+/* dynamics_velocity: acceleration / unit_vel */
+P_HD Vec3 rhs_velocity_air(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, double t, const SecParam& sp,
+                           const Units& un, const Tables& tb) {
+  double mass = mass_e * un.mass;
+  Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
+  Vec3 vel = v3(vel_e.x * un.vel, vel_e.y * un.vel, vel_e.z * un.vel);
+  AirRel ar = air_relative(pos, vel, t, tb);
+  AirState as = us76<3>(ar.alt_gp);
+  double vn = norm3(ar.va);
+  double mach = vn / as.a;
+  double ca = interp_table(mach, tb.ca, tb.ca + 1, tb.n_ca, 2);
+  double k = 0.5 * as.rho * sp.ref_area * ca * vn;
+  Vec3 aero = v3(k * -ar.va.x, k * -ar.va.y, k * -ar.va.z);
+  double thrust = sp.thrust - sp.nozzle_area * as.P;
+  Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
+  Vec3 thr = scale3(thrust, tdir);
+  Vec3 g = gravity_eci(pos);
+  return v3(((thr.x + aero.x) / mass + g.x) / un.vel, ((thr.y + aero.y) / mass + g.y) / un.vel,
+            ((thr.z + aero.z) / mass + g.z) / un.vel);
+}
+
+/* dynamics_velocity_NoAir */
+P_HD Vec3 rhs_velocity_noair(double mass_e, Vec3 pos_e, Quat q, const SecParam& sp, const Units& un) {
+  double mass = mass_e * un.mass;
+  Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
+  Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
+  Vec3 thr = scale3(sp.thrust, tdir);
+  Vec3 g = gravity_eci(pos);
+  return v3((thr.x / mass + g.x) / un.vel, (thr.y / mass + g.y) / un.vel, (thr.z / mass + g.z) / un.vel);
+}
+
+/* dynamics_quaternion: 0.5 * q (x) (0, 0, u0, u1) * pi/180 */
+P_HD Quat rhs_quaternion(Quat q, double u0_e, double u1_e, double unit_u) {
+  double u0 = u0_e * unit_u, u1 = u1_e * unit_u;
+  Quat om = q4(0.0 * P_PI / 180.0, 0.0 * P_PI / 180.0, u0 * P_PI / 180.0, u1 * P_PI / 180.0);
+  Quat d = quatmult(q, om);
+  return q4(0.5 * d.w, 0.5 * d.x, 0.5 * d.y, 0.5 * d.z);
+}
+
+/* ---- aero constraint leaves (wrapper_utils.hpp:89-111,163-193) ----------- */
+/* kind: 0 angle of attack [rad], 1 dynamic pressure [Pa], 2 q*alpha [Pa rad].
+ * pos/vel dimensional, t in seconds. */
+P_HD double aero_quantity(int kind, Vec3 pos, Vec3 vel, Quat q, double t, const Tables& tb) {
+  AirRel ar = air_relative(pos, vel, t, tb);
+  double alpha = 0.0, dynp = 0.0;
+  if (kind != 1) {
+    Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
+    Vec3 a = div3(ar.va, norm3(ar.va)); /* normalize(): v / v.norm() */
+    Vec3 b = div3(tdir, norm3(tdir));
+    double c_alpha = dot3(a, b);
+    if (c_alpha > 1.0) alpha = 0.0;
+    else if (norm3(ar.va) < 1e-6) alpha = 0.0;
+    else alpha = gm_acos(c_alpha);
+  }
+  if (kind != 0) {
+    AirState as = us76<1>(ar.alt_gp);
+    dynp = 0.5 * as.rho * norm3(ar.va) * norm3(ar.va);
+  }
+  if (kind == 0) return alpha;
+  if (kind == 1) return dynp;
+  return dynp * alpha;
+}
+
+/* ---- event-point leaves --------------------------------------------------- */
+/* wrapper_coordinate.hpp:193-199 eci2geodetic -> (lat deg, lon deg, alt m) */
+P_HD Vec3 eci2geodetic_deg(Vec3 pos_eci, double t) {
+  double s, c;
+  gm_sincos(P_OMEGA * t, &s, &c);
+  Geodetic g = ecef2geodetic<3>(rot_eci2ecef(pos_eci, c, s));
+  return v3(g.lat * 180.0 / P_PI, g.lon * 180.0 / P_PI, g.alt);
+}
+
+/* iip.cpp:36-150 + pybind_IIP.cpp:34-51 (fill_na = true): (lat deg, lon deg, 0) or zeros */
+P_HD Vec3 iip_faa_deg(Vec3 posECEF, Vec3 velECEF) {
+  const Vec3 zero = v3(0.0 * (180.0 / P_PI), 0.0 * (180.0 / P_PI), 0.0);
+  double s0, c0;
+  gm_sincos(P_OMEGA * 0.0, &s0, &c0);
+  double r_k1 = P_RB;
+  Vec3 p0 = rot_ecef2eci(posECEF, c0, s0);
+  double r0 = norm3(p0);
+  if (r0 < r_k1) return zero;
+  Vec3 v0v = vel_ecef2eci_cs(velECEF, posECEF, c0, s0);
+  double v0 = norm3(v0v);
+  double eps_cos = (r0 * v0 * v0 / P_MU) - 1.0;
+  if (eps_cos >= 1.0) return zero;
+  double a_t = r0 / (1 - eps_cos);
+  double eps_sin = dot3(p0, v0v) / gm_sqrt(P_MU * a_t);
+  double eps2 = eps_cos * eps_cos + eps_sin * eps_sin;
+  if (gm_sqrt(eps2) <= 1.0 && a_t * (1 - gm_sqrt(eps2)) - P_RA >= 0.0) return zero;
+  double eps_k_cos = 0, eps_k_sin = 0, d_cos = 0, d_sin = 0;
+  double fs, gs, Ek = 0, Fk = 0, Gk = 0, r_k2 = 0, r_k1_tmp = 0;
+  for (int i = 0; i < 5; i++) {
+    eps_k_cos = (a_t - r_k1) / a_t;
+    if ((eps2 - eps_k_cos * eps_k_cos) < 0) return zero;
+    eps_k_sin = -gm_sqrt(eps2 - eps_k_cos * eps_k_cos);
+    d_cos = (eps_k_cos * eps_cos + eps_k_sin * eps_sin) / eps2;
+    d_sin = (eps_k_sin * eps_cos - eps_k_cos * eps_sin) / eps2;
+    fs = (d_cos - eps_cos) / (1 - eps_cos);
+    gs = (d_sin + eps_sin - eps_k_sin) * gm_sqrt(a_t * a_t * a_t / P_MU);
+    Ek = fs * p0.x + gs * v0v.x;
+    Fk = fs * p0.y + gs * v0v.y;
+    Gk = fs * p0.z + gs * v0v.z;
+    r_k2 = P_RA / gm_sqrt((P_E2 / (1 - P_E2)) * (Gk / r_k1) * (Gk / r_k1) + 1);
+    r_k1_tmp = r_k1;
+    r_k1 = r_k2;
+  }
+  if (gm_fabs(r_k1_tmp - r_k2) > 1.0) return zero;
+  double delta_eps = gm_atan2(d_sin, d_cos);
+  double time_sec = (delta_eps + eps_sin - eps_k_sin) * gm_sqrt(a_t * a_t * a_t / P_MU);
+  double phi_tmp = gm_asin(Gk / r_k2);
+  double phi = gm_atan2(gm_tan(phi_tmp), 1.0 - P_E2);
+  double lam = gm_atan2(Fk, Ek) - P_OMEGA * time_sec;
+  return v3(phi * (180.0 / P_PI), lam * (180.0 / P_PI), 0.0);
+}
+
+/* con_waypoint.py:214-218 iip_from_eci: dimensional pos/vel, t in seconds */
+P_HD Vec3 iip_from_eci_deg(Vec3 pos, Vec3 vel, double t) {
+  double s, c;
+  gm_sincos(P_OMEGA * t, &s, &c);
+  return iip_faa_deg(rot_eci2ecef(pos, c, s), vel_eci2ecef_cs(vel, pos, c, s));
+}
+
+/* con_waypoint.py:45-51 sin_elevation; p_ant = antenna ECEF position */
+P_HD double sin_elevation(Vec3 pos, double t, Vec3 p_ant) {
+  double s, c;
+  gm_sincos(P_OMEGA * t, &s, &c);
+  Vec3 d = sub3(rot_eci2ecef(pos, c, s), p_ant);
+  Vec3 dir = div3(d, norm3(d)); /* normalize(): dynamic vector v / v.norm() */
+  Geodetic g = ecef2geodetic<2>(p_ant);
+  Quat q_ned2ecef = quatconj(quat_ecef2ned_ll(g.lat, g.lon));
+  Vec3 vert = quatrot(q_ned2ecef, v3(0.0, 0.0, -1.0));
+  /* np.dot of two 3-vectors: BLAS ddot accumulates with fused multiply-add, ascending index
+   * (the same order the kernels use for D.X) */
+  return gm_fma(dir.z, vert.z, gm_fma(dir.y, vert.y, dir.x * vert.x));
+}
+
+/* terminal orbit (wrapper_coordinate.hpp:224-250) */
+P_HD double orbit_energy(Vec3 pos, Vec3 vel) {
+  double r = norm3(pos);
+  double v = norm3(vel);
+  return 0.5 * v * v - P_MU / r;
+}
+P_HD double angular_momentum(Vec3 pos, Vec3 vel) { return norm3(cross3(pos, vel)); }
+P_HD double inclination_rad(Vec3 pos, Vec3 vel) {
+  Vec3 h = cross3(pos, vel);
+  return gm_acos(h.z / norm3(h));
+}
+
+/* Coordinate.cpp:197-245 orbital_elements, only a and e (what the shipped
+ * user constraint reads: example/user_constraints.py:133-137) */
+P_HD void orbital_a_e(Vec3 pos, Vec3 vel, double* a_out, double* e_out) {
+  Vec3 nr = normalized3(pos);
+  Vec3 c = cross3(pos, vel);
+  Vec3 f = sub3(cross3(vel, c), scale3(P_MU, nr));
+  double p = dot3(c, c) / P_MU;
+  double e = norm3(f) / P_MU;
+  *a_out = p / (1.0 - e * e);
+  *e_out = e;
+}
+
+#endif /* GELATO_B200_PHYSICS_H_ */

@@ -1,0 +1,278 @@
+"""ctypes binding of libgelato_b200.so (the C ABI in include/gelato_b200.h).
+
+This is the thin layer that stands where the reference's five pybind11 modules
+stood (/root/reference/src/pybind_*.cpp): Python hands the engine a decision
+vector, the engine runs ONE fused CUDA kernel and hands back the whole residual
+vector or the whole Jacobian value vector.
+
+There is no CPU path: if the shared library is missing or no CUDA device is
+present, construction raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libgelato_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+_c_d = ctypes.c_double
+_pd = ctypes.POINTER(ctypes.c_double)
+_pi32 = ctypes.POINTER(ctypes.c_int32)
+_pi64 = ctypes.POINTER(ctypes.c_int64)
+_pu8 = ctypes.POINTER(ctypes.c_uint8)
+
+
+class GelatoError(RuntimeError):
+    pass
+
+
+class PlanDesc(ctypes.Structure):
+    """GelatoPlanDesc (include/gelato_b200.h)."""
+
+    _fields_ = [
+        ("n_sections", ctypes.c_int32), ("n_nodes", ctypes.c_int32), ("n_rows", ctypes.c_int32),
+        ("n_vals", ctypes.c_int64), ("payload_mode", ctypes.c_int32),
+        ("sec_i32", _pi32), ("sec_i64", _pi64), ("sec_f64", _pd),
+        ("d_pool", _pd), ("d_pool_len", ctypes.c_int64), ("tau_pool", _pd), ("tau_pool_len", ctypes.c_int64),
+        ("wind", _pd), ("n_wind", ctypes.c_int32), ("ca", _pd), ("n_ca", ctypes.c_int32),
+        ("unit_mass", _c_d), ("unit_pos", _c_d), ("unit_vel", _c_d), ("unit_u", _c_d), ("unit_t", _c_d), ("dx", _c_d),
+        ("n_lin", ctypes.c_int32), ("lin_i32", _pi32), ("lin_f64", _pd),
+        ("n_aero", ctypes.c_int32), ("aero_i32", _pi32), ("aero_i64", _pi64), ("aero_f64", _pd), ("rc_aero", _pu8),
+        ("n_evt", ctypes.c_int32), ("evt_i32", _pi32), ("evt_i64", _pi64), ("evt_f64", _pd),
+        ("vals_template", _pd),
+    ]
+
+
+class ScenarioDesc(ctypes.Structure):
+    """GelatoScenarioDesc (include/gelato_b200.h)."""
+
+    _fields_ = [("n_scen", ctypes.c_int32), ("sec_f64", _pd), ("wind", _pd), ("unit_mass", _pd), ("lin_const", _pd),
+                ("vals_template", _pd)]
+
+
+def _ptr(arr, typ):
+    if arr is None or arr.size == 0:
+        return ctypes.cast(None, typ)
+    return arr.ctypes.data_as(typ)
+
+
+def make_desc(plan):
+    """CompiledPlan -> (PlanDesc, keepalive list of the arrays it points into)."""
+    keep = []
+
+    def c(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    d = PlanDesc()
+    d.n_sections, d.n_nodes, d.n_rows, d.n_vals = plan.S, plan.N, plan.n_rows, plan.n_vals
+    d.payload_mode = plan.payload_mode
+    d.sec_i32 = _ptr(c(plan.sec_i32, np.int32), _pi32)
+    d.sec_i64 = _ptr(c(plan.sec_i64, np.int64), _pi64)
+    d.sec_f64 = _ptr(c(plan.sec_f64, np.float64), _pd)
+    d.d_pool = _ptr(c(plan.d_pool, np.float64), _pd)
+    d.d_pool_len = plan.d_pool.size
+    d.tau_pool = _ptr(c(plan.tau_pool, np.float64), _pd)
+    d.tau_pool_len = plan.tau_pool.size
+    d.wind = _ptr(c(plan.wind, np.float64), _pd)
+    d.n_wind = plan.wind.shape[0]
+    d.ca = _ptr(c(plan.ca, np.float64), _pd)
+    d.n_ca = plan.ca.shape[0]
+    d.unit_mass, d.unit_pos, d.unit_vel, d.unit_u, d.unit_t, d.dx = plan.units
+    d.n_lin = plan.n_lin
+    d.lin_i32 = _ptr(c(plan.lin_i32, np.int32), _pi32)
+    d.lin_f64 = _ptr(c(plan.lin_f64, np.float64), _pd)
+    d.n_aero = plan.n_aero
+    d.aero_i32 = _ptr(c(plan.aero_i32, np.int32), _pi32)
+    d.aero_i64 = _ptr(c(plan.aero_i64, np.int64), _pi64)
+    d.aero_f64 = _ptr(c(plan.aero_f64, np.float64), _pd)
+    d.rc_aero = _ptr(c(plan.rc_aero, np.uint8), _pu8)
+    d.n_evt = plan.n_evt
+    d.evt_i32 = _ptr(c(plan.evt_i32, np.int32), _pi32)
+    d.evt_i64 = _ptr(c(plan.evt_i64, np.int64), _pi64)
+    d.evt_f64 = _ptr(c(plan.evt_f64, np.float64), _pd)
+    d.vals_template = _ptr(c(plan.vals_template, np.float64), _pd)
+    return d, keep
+
+
+def make_scenario_desc(plans):
+    """Per-scenario blocks from a list of CompiledPlans that share one structure
+    (same mesh, same constraint rows) and differ in section parameters, wind
+    table, mass unit and the constants derived from them."""
+    base = plans[0]
+    for p in plans[1:]:
+        if (p.n_rows, p.n_vals, p.n_lin, p.n_evt, p.n_aero, p.wind.shape) != (
+                base.n_rows, base.n_vals, base.n_lin, base.n_evt, base.n_aero, base.wind.shape):
+            raise ValueError("scenario plans must share the problem structure")
+    keep = []
+
+    def stack(get):
+        a = np.ascontiguousarray(np.stack([np.asarray(get(p), dtype=np.float64) for p in plans]))
+        keep.append(a)
+        return a
+
+    sc = ScenarioDesc()
+    sc.n_scen = len(plans)
+    sc.sec_f64 = _ptr(stack(lambda p: p.sec_f64), _pd)
+    sc.wind = _ptr(stack(lambda p: p.wind), _pd)
+    sc.unit_mass = _ptr(stack(lambda p: p.units[0]), _pd)
+    sc.lin_const = _ptr(stack(lambda p: p.lin_f64[:, 2]), _pd)
+    sc.vals_template = _ptr(stack(lambda p: p.vals_template), _pd)
+    return sc, keep
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/gelato_b200.cu for sm_100a into csrc/libgelato_b200.so (in tree)."""
+    src = os.path.join(CSRC, "gelato_b200.cu")
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".inc"))]
+    deps.append(os.path.join(INCLUDE, "gelato_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(f) for f in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine and declare the prototypes of include/gelato_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GelatoError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the callback evaluations)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    L.gelato_last_error.restype = ctypes.c_char_p
+    L.gelato_device_count.restype = ctypes.c_int
+    L.gelato_plan_create.argtypes = [ctypes.POINTER(PlanDesc), ctypes.c_int, ctypes.POINTER(vp)]
+    L.gelato_plan_set_scenarios.argtypes = [vp, ctypes.POINTER(ScenarioDesc)]
+    L.gelato_plan_destroy.argtypes = [vp]
+    L.gelato_plan_n_vars.argtypes = [vp]
+    L.gelato_plan_n_vars.restype = ctypes.c_int32
+    L.gelato_plan_n_rows.argtypes = [vp]
+    L.gelato_plan_n_rows.restype = ctypes.c_int32
+    L.gelato_plan_n_vals.argtypes = [vp]
+    L.gelato_plan_n_vals.restype = ctypes.c_int64
+    L.gelato_plan_launch_count.argtypes = [vp]
+    L.gelato_plan_launch_count.restype = ctypes.c_int64
+    L.gelato_eval_residuals.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_jacobian.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_residuals_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_eval_jacobian_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_time_kernel.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_float)]
+    L.gelato_selftest_unfused.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.gelato_fp64_peak.argtypes = [ctypes.c_int, _pd, _pd]
+    _lib = L
+    return L
+
+
+EXPORTS = (
+    "gelato_last_error gelato_device_count gelato_plan_create gelato_plan_set_scenarios gelato_plan_destroy "
+    "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
+    "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
+    "gelato_selftest_unfused gelato_fp64_peak"
+).split()
+
+
+def _check(L, rc, what):
+    if rc != 0:
+        raise GelatoError("%s failed (%d): %s" % (what, rc, L.gelato_last_error().decode()))
+
+
+class Engine:
+    """One plan handle on one GPU.  Not thread-safe (one CUDA stream per handle)."""
+
+    def __init__(self, plan, device=0, scenario_plans=None):
+        self.L = L = load_library()
+        self.plan = plan
+        self.device = device
+        desc, self._keep = make_desc(plan)
+        h = ctypes.c_void_p()
+        _check(L, L.gelato_plan_create(ctypes.byref(desc), device, ctypes.byref(h)), "gelato_plan_create")
+        self.h = h
+        self.n_scen_cfg = 1
+        if scenario_plans is not None:
+            sc, keep = make_scenario_desc(scenario_plans)
+            _check(L, L.gelato_plan_set_scenarios(self.h, ctypes.byref(sc)), "gelato_plan_set_scenarios")
+            self.n_scen_cfg = len(scenario_plans)
+        self.n_vars = L.gelato_plan_n_vars(h)
+        self.n_rows = L.gelato_plan_n_rows(h)
+        self.n_vals = L.gelato_plan_n_vals(h)
+        assert self.n_vars == plan.n_vars and self.n_rows == plan.n_rows and self.n_vals == plan.n_vals
+        ok = ctypes.c_int(0)
+        _check(L, L.gelato_selftest_unfused(device, ctypes.byref(ok)), "gelato_selftest_unfused")
+        if not ok.value:
+            raise GelatoError("libgelato_b200.so was built with fused multiply-add; rebuild with -fmad=false")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gelato_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.L.gelato_plan_launch_count(self.h))
+
+    # ---- host-buffer calls (what objfunc / sens use) --------------------
+    def _x(self, x, n_scen):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != n_scen * self.n_vars:
+            raise ValueError("x has %d entries, expected %d x %d" % (x.size, n_scen, self.n_vars))
+        return x
+
+    def eval_residuals(self, x, n_scen=1, out=None):
+        x = self._x(x, n_scen)
+        g = out if out is not None else np.empty(n_scen * self.n_rows)
+        _check(self.L, self.L.gelato_eval_residuals(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen), "gelato_eval_residuals")
+        return g if n_scen == 1 else g.reshape(n_scen, self.n_rows)
+
+    def eval_jacobian(self, x, n_scen=1, out=None):
+        x = self._x(x, n_scen)
+        v = out if out is not None else np.empty(n_scen * self.n_vals)
+        _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
+        return v if n_scen == 1 else v.reshape(n_scen, self.n_vals)
+
+    # ---- device-resident calls (raw device pointers, e.g. torch .data_ptr()) ----
+    def eval_residuals_dev(self, x_ptr, g_ptr, n_scen=1, stream=None):
+        _check(self.L, self.L.gelato_eval_residuals_dev(self.h, x_ptr, g_ptr, n_scen, stream), "gelato_eval_residuals_dev")
+
+    def eval_jacobian_dev(self, x_ptr, vals_ptr, n_scen=1, stream=None):
+        _check(self.L, self.L.gelato_eval_jacobian_dev(self.h, x_ptr, vals_ptr, n_scen, stream), "gelato_eval_jacobian_dev")
+
+    def time_kernel(self, which, x_ptr, out_ptr, n_scen=1, reps=10):
+        """Average duration [ms] of `reps` back-to-back launches of one kernel
+        (0 residuals, 1 Jacobian), CUDA events on the launch stream."""
+        ms = ctypes.c_float(0)
+        _check(self.L, self.L.gelato_time_kernel(self.h, which, x_ptr, out_ptr, n_scen, reps, ctypes.byref(ms)),
+               "gelato_time_kernel")
+        return float(ms.value)
+
+
+def fp64_peak(device=0):
+    """(TFLOP/s with DFMA, TFLOP/s with separate DMUL+DADD) measured on the device."""
+    L = load_library()
+    a, b = ctypes.c_double(0), ctypes.c_double(0)
+    _check(L, L.gelato_fp64_peak(device, ctypes.byref(a), ctypes.byref(b)), "gelato_fp64_peak")
+    return a.value, b.value

@@ -85,3 +85,21 @@ def quat_from_euler(az_deg, el_deg, ro_deg):
     qy = np.array([math.cos(el / 2), 0.0, math.sin(el / 2), 0.0])
     qx = np.array([math.cos(ro / 2), math.sin(ro / 2), 0.0, 0.0])
     return quatmult(quatmult(qz, qy), qx)
+
+
+def angular_momentum_from_altitude(ha, hp):
+    """Target angular momentum of the terminal orbit (reference:
+    src/wrapper_coordinate.hpp:252-258); only + - * / sqrt."""
+    ra = RA + ha
+    rp = RA + hp
+    a = (ra + rp) / 2.0
+    vp = math.sqrt(MU * (2.0 / rp - 1.0 / a))
+    return rp * vp
+
+
+def orbit_energy_from_altitude(ha, hp):
+    """Target specific orbital energy (reference: src/wrapper_coordinate.hpp:260-265)."""
+    ra = RA + ha
+    rp = RA + hp
+    a = (ra + rp) / 2.0
+    return -MU / 2.0 / a

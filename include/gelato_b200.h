@@ -1,0 +1,201 @@
+/* gelato_b200.h -- C ABI of the B200 NLP-callback engine.
+ *
+ * This is the boundary that replaces the reference's five pybind11 extension
+ * modules (/root/reference/src/pybind_dynamics.cpp:108-114, pybind_utils.cpp:28-48,
+ * pybind_coordinate.cpp:28-78, pybind_IIP.cpp:53-57,
+ * pybind_USStandardAtmosphere.cpp:28-35) AND the Python loops around them
+ * (/root/reference/lib/con_*.py): instead of ~230 by-value leaf calls per
+ * Jacobian, the host describes the whole transcribed problem once (a "plan") and
+ * then makes ONE call per `objfunc` (/root/reference/Trajectory_Optimization.py:194-242)
+ * and ONE per `sens` (:245-312).
+ *
+ * Plain pointers and sizes only; no torch / numpy / Eigen types.  All functions
+ * return 0 on success and a negative code on failure (gelato_last_error() gives
+ * the text).  There is no CPU fallback: without a CUDA device every evaluation
+ * entry point fails with GELATO_ERR_CUDA.
+ *
+ * Decision vector x (length n_vars), reference order
+ * (/root/reference/Trajectory_Optimization.py:318-352):
+ *     mass[M] | position[3M] | velocity[3M] | quaternion[4M] | u[2N] | t[S+1]
+ * Residual vector g (length n_rows): g[0] = objective, then the constraint
+ * groups in the order the plan's row offsets define (the reference's funcs order).
+ * Jacobian value vector vals (length n_vals): the reference's COO `data` arrays
+ * concatenated group by group, variable by variable, followed by a small
+ * auxiliary tail (user-constraint finite differences).
+ */
+#ifndef GELATO_B200_H_
+#define GELATO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GELATO_OK 0
+#define GELATO_ERR_ARG (-1)
+#define GELATO_ERR_CUDA (-2)
+#define GELATO_ERR_ALLOC (-3)
+
+/* ---- section table columns (one row per collocation section) ------------- */
+enum {
+  GS_N = 0,    /* LGR nodes in the section */
+  GS_UA,       /* first control row (reference PSparams.get_index: ua) */
+  GS_XA,       /* first state row (xa); rows xa .. xa+n */
+  GS_FLAGS,    /* GSF_* */
+  GS_D_OFF,    /* offset (doubles) of D[n][n+1] in the D pool */
+  GS_TAU_OFF,  /* offset of tau[n] in the tau pool */
+  GS_R_MASS,   /* first residual row of eqcon_dyn_mass for this section */
+  GS_R_POS,
+  GS_R_VEL,
+  GS_R_QUAT,
+  GS_I32_COLS
+};
+enum {
+  GSF_ENGINE_ON = 1, /* params[i]["engineOn"] (con_dynamics.py:53) */
+  GSF_AIR = 2,       /* reference_area != 0.0 (con_dynamics.py:257) */
+  GSF_AIR_FD = 4,    /* reference_area > 0.0  (con_dynamics.py:403,454) */
+  GSF_HOLD = 8       /* attitude in {hold, vertical} (con_dynamics.py:520) */
+};
+/* offsets into vals of the x-dependent Jacobian blocks of a section (-1: absent) */
+enum {
+  GS_JP_VEL = 0, /* eqcon_dyn_pos / velocity : 3n           (con_dynamics.py:180-183) */
+  GS_JP_T,       /* eqcon_dyn_pos / t        : 3n to + 3n tf (:186-195) */
+  GS_JV_MASS,    /* eqcon_dyn_vel / mass     : 3n           (:372-380) */
+  GS_JV_POS,     /* eqcon_dyn_vel / position : 3 x 3n       (:383-400) */
+  GS_JV_VEL,     /* eqcon_dyn_vel / velocity : 9 x n(n+1)   (:418-428) */
+  GS_JV_QUAT,    /* eqcon_dyn_vel / quaternion: 4 x 3n      (:431-449) */
+  GS_JV_T,       /* eqcon_dyn_vel / t        : 3n to + 3n tf (:482-489) */
+  GS_JQ_QUAT,    /* eqcon_dyn_quat / quaternion: 4n x 4(n+1) (:591-597) */
+  GS_JQ_U,       /* eqcon_dyn_quat / u       : 2 x 4n       (:600-613) */
+  GS_JQ_T,       /* eqcon_dyn_quat / t       : 4n to + 4n tf (:616-625) */
+  GS_I64_COLS
+};
+enum { GS_THRUST = 0, GS_MASSFLOW, GS_REF_AREA, GS_NOZZLE_AREA, GS_F64_COLS };
+
+/* ---- linear rows: g[row] = (sp*x[ip] - sm*x[im]) + c  (index -1 = absent) -- */
+enum { GL_ROW = 0, GL_IDX_PLUS, GL_IDX_MINUS, GL_I32_COLS };
+enum { GL_SCALE_PLUS = 0, GL_SCALE_MINUS, GL_CONST, GL_F64_COLS };
+
+/* ---- aero inequality jobs (con_aero.py) ----------------------------------- */
+enum { GA_KIND = 0 /* 0 alpha, 1 q, 2 q-alpha */, GA_SECTION, GA_NK, GA_ROW0, GA_I32_COLS };
+enum { GA_J_POS = 0, GA_J_VEL, GA_J_QUAT, GA_J_T, GA_I64_COLS };
+enum { GA_LIMIT = 0, GA_F64_COLS };
+
+/* ---- event-point jobs (con_waypoint.py, con_init_terminal_knot.py:329-405,
+ *      user constraint built-ins) ------------------------------------------- */
+enum { GE_LLH = 0, GE_IIP = 1, GE_ANT = 2, GE_TERM = 3, GE_USER_PERIGEE = 4 };
+enum {
+  GE_TYPE = 0,
+  GE_TIDX,    /* index into t (section number), -1 if unused */
+  GE_SROW,    /* state row (position/velocity row index) */
+  GE_COMP,    /* component of the leaf's output used by this row */
+  GE_FORM,    /* GEF_* value formula */
+  GE_ROW,     /* residual row (first row for GE_TERM) */
+  GE_NROW,    /* rows produced (GE_TERM: 2 or 3; others 1) */
+  GE_RC0,     /* 7 residue counts: pos[3], vel[3], t  (see DESIGN.md "H3") */
+  GE_I32_COLS = GE_RC0 + 7
+};
+enum {
+  GEF_DIFF_OVER_DEN = 0, /*  (v - ref)/den                */
+  GEF_NEG_DIFF_OVER_DEN, /* -(v - ref)/den                */
+  GEF_RATIO_M1,          /*  v/ref - 1                    */
+  GEF_NEG_RATIO_P1,      /* -(v/ref) + 1                  */
+  GEF_REF_MINUS_OVER_DEN,/*  (ref - v)/den                */
+  GEF_MINUS_REF          /*  v - ref                      */
+};
+enum { GE_J_POS = 0, GE_J_VEL, GE_J_T, GE_I64_COLS };
+enum { GE_REF = 0, GE_DEN, GE_A0, GE_A1, GE_A2, GE_F64_COLS };
+
+typedef struct GelatoPlanDesc {
+  /* sizes */
+  int32_t n_sections, n_nodes; /* S, N;  M = N + S */
+  int32_t n_rows;              /* length of g (objective included) */
+  int64_t n_vals;              /* length of vals (aux tail included) */
+  int32_t payload_mode;        /* 1: objective = -mass[0]; 0: objective = t[S] */
+  /* sections */
+  const int32_t* sec_i32; /* [S][GS_I32_COLS] */
+  const int64_t* sec_i64; /* [S][GS_I64_COLS] */
+  const double* sec_f64;  /* [S][GS_F64_COLS] */
+  const double* d_pool;   /* concatenated row-major D blocks */
+  int64_t d_pool_len;
+  const double* tau_pool;
+  int64_t tau_pool_len;
+  /* tables */
+  const double* wind; /* [n_wind][3] altitude, wind_n, wind_e */
+  int32_t n_wind;
+  const double* ca; /* [n_ca][2] mach, CA */
+  int32_t n_ca;
+  /* units (/root/reference/Trajectory_Optimization.py:153-167) */
+  double unit_mass, unit_pos, unit_vel, unit_u, unit_t, dx;
+  /* linear rows */
+  int32_t n_lin;
+  const int32_t* lin_i32;
+  const double* lin_f64;
+  /* aero jobs */
+  int32_t n_aero;
+  const int32_t* aero_i32;
+  const int64_t* aero_i64;
+  const double* aero_f64;
+  const uint8_t* rc_aero; /* [n_vars] residue counts seen by the aero groups (may be NULL) */
+  /* event jobs */
+  int32_t n_evt;
+  const int32_t* evt_i32;
+  const int64_t* evt_i64;
+  const double* evt_f64;
+  /* Jacobian template: constants and D entries, length n_vals */
+  const double* vals_template;
+} GelatoPlanDesc;
+
+/* per-scenario overrides for batched evaluation (NULL members = shared) */
+typedef struct GelatoScenarioDesc {
+  int32_t n_scen;
+  const double* sec_f64;       /* [n_scen][S][GS_F64_COLS] */
+  const double* wind;          /* [n_scen][n_wind][3] */
+  const double* unit_mass;     /* [n_scen] */
+  const double* lin_const;     /* [n_scen][n_lin] */
+  const double* vals_template; /* [n_scen][n_vals] */
+} GelatoScenarioDesc;
+
+typedef struct GelatoPlan GelatoPlan;
+
+const char* gelato_last_error(void);
+int gelato_device_count(void);
+
+int gelato_plan_create(const GelatoPlanDesc* desc, int device, GelatoPlan** out);
+int gelato_plan_set_scenarios(GelatoPlan* plan, const GelatoScenarioDesc* sc);
+int gelato_plan_destroy(GelatoPlan* plan);
+int32_t gelato_plan_n_vars(const GelatoPlan* plan);
+int32_t gelato_plan_n_rows(const GelatoPlan* plan);
+int64_t gelato_plan_n_vals(const GelatoPlan* plan);
+/* kernels launched by this plan so far (bench.py's gpu_launches) */
+int64_t gelato_plan_launch_count(const GelatoPlan* plan);
+
+/* Host-buffer entry points (what the drop-in objfunc / sens call): copy x to the
+ * device, run ONE fused kernel, copy the result back.  n_scen = 1 for a single NLP;
+ * x is [n_scen][n_vars], g [n_scen][n_rows], vals [n_scen][n_vals]. */
+int gelato_eval_residuals(GelatoPlan* plan, const double* x, double* g, int32_t n_scen);
+int gelato_eval_jacobian(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
+
+/* Device-resident entry points: pointers are device memory, work is enqueued on
+ * `stream` (a cudaStream_t, NULL = the plan's own stream) and NOT synchronised. */
+int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
+int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
+
+/* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen
+ * kernel (0 residuals, 1 jacobian) on device-resident buffers and returns the
+ * average duration in milliseconds measured with CUDA events on the launch stream. */
+int gelato_time_kernel(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
+                       float* avg_ms);
+
+/* 1 if the library was compiled with unfused multiply-add on the device (the
+ * build contract, checked by running a probe kernel); 0 otherwise. */
+int gelato_selftest_unfused(int device, int* ok);
+
+/* FP64 issue-rate probe: measured DFMA and DADD+DMUL TFLOP/s. */
+int gelato_fp64_peak(int device, double* tflops_fma, double* tflops_nofma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GELATO_B200_H_ */

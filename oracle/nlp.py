@@ -911,7 +911,7 @@ class OracleNLP:
         p_ecef = self.crd.eci2ecef(pos, to)
         direction = self.crd.normalize(p_ecef - p_ant)
         vertical = self.crd.quatrot(self.crd.quat_nedg2ecef(p_ant), np.array([0, 0, -1.0]))
-        return np.dot(direction, vertical)
+        return float(self._dot(np.asarray(direction).reshape(1, 3), np.asarray(vertical).reshape(3, 1)).ravel()[0])
 
     def ineq_antenna(self, x):
         rows = self._antenna_rows()

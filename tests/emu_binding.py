@@ -1,0 +1,60 @@
+"""ctypes front-end of tests/emu (the host emulator of the CUDA kernels).
+
+TEST HARNESS ONLY: lets the CPU test tier run the kernels' per-thread code
+(gelato_b200/csrc/jobs.h) through the same GelatoPlanDesc the GPU library gets.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from gelato_b200 import engine
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+BUILD = os.path.join(_HERE, "_build")
+LIB = os.path.join(BUILD, "libgelato_emu.so")
+_pd = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "emu", "emu.cpp")
+    csrc = os.path.join(ROOT, "gelato_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "include", "gelato_b200.h")] + [
+        os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".inc"))]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(f) for f in deps):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-o", LIB, src])
+    return LIB
+
+
+class Emulator:
+    def __init__(self, plan, scenario_plans=None):
+        build()
+        self.L = ctypes.CDLL(LIB)
+        assert self.L.emu_unfused_check() == 1
+        self.plan = plan
+        self.desc, self._keep = engine.make_desc(plan)
+        self.sc = None
+        if scenario_plans is not None:
+            self.sc, keep = engine.make_scenario_desc(scenario_plans)
+            self._keep += keep
+        for fn in (self.L.emu_eval_residuals, self.L.emu_eval_jacobian):
+            fn.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, ctypes.c_int]
+
+    def _sc(self):
+        return ctypes.byref(self.sc) if self.sc is not None else None
+
+    def eval_residuals(self, x, n_scen=1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.full(n_scen * self.plan.n_rows, np.nan)
+        self.L.emu_eval_residuals(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd), n_scen)
+        return g if n_scen == 1 else g.reshape(n_scen, -1)
+
+    def eval_jacobian(self, x, n_scen=1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.full(n_scen * self.plan.n_vals, np.nan)
+        self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen)
+        return v if n_scen == 1 else v.reshape(n_scen, -1)
