@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the NLP-callback hot path (BASELINE.json metric: FD-Jacobian +
+residual leaf evaluations per second).
+
+Workload (BASELINE.json configs[1]): the shipped example refined to ~1 000 LGR
+nodes (x15 -> N = 990 in 53 sections of <= 20 nodes).  One STEP = one `objfunc`
++ one `sens` (residual kernel + FD-Jacobian kernel) over a batch of dispersed
+launch scenarios of that problem (mass / thrust / wind perturbations, each
+scenario its own decision vector).  An "eval" is one physics-leaf evaluation at
+one (node x perturbation column): see CompiledPlan.eval_counts / DESIGN.md.
+
+  value   device-resident: x already in HBM, outputs stay in HBM, CUDA events.
+  e2e     the same step through the host-buffer C-ABI calls the drop-in
+          objfunc / sens use: x from page-locked host memory -> device, both
+          kernels, residual vector and the FULL Jacobian value vector back to the
+          host, wall clock.
+Multi-GPU: scenarios are independent NLPs; each rank owns `--scenarios` of them
+(weak scaling), no data-path collective (DESIGN.md "multi-GPU").
+
+`--impl reference` times the CPU path instead (the oracle port of the
+reference's callbacks: the reference's pybind11/Eigen modules cannot be built in
+this image), one scenario per host core in parallel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "fd_jacobian_plus_residual_evals_per_s"
+UNIT = "evals/s"
+INPUTS = os.path.join(ROOT, "tests", "golden", "example_inputs.json")
+USER_EVENT = "IIP_END"
+
+# algorithmic FP64 work per leaf evaluation (DESIGN.md "roofline"): elementary ops (+ - * / sqrt)
+# counted 1 each, sin/cos/exp = 40, atan2/acos/asin = 60, pow = 120
+FLOPS = {"air": 1000.0, "noair": 70.0, "quat": 20.0, "aero": 800.0, "evt": 400.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gelato", choices=["gelato", "reference"])
+    ap.add_argument("--scenarios", type=int, default=64, help="dispersed scenarios per GPU in one step")
+    ap.add_argument("--factor", type=int, default=15, help="mesh refinement of the example (15 -> 990 nodes)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_workload(factor, n_scen_total, first, count, coord=None):
+    """Plans and decision vectors of scenarios [first, first+count)."""
+    from gelato_b200 import plan as gplan
+    from gelato_b200 import problem, scenarios
+
+    inp = problem.load_inputs_json(INPUTS)
+    scen = scenarios.disperse(inp, n_scen_total, seed=20260117)
+    plans, xs, probs = [], [], []
+    for k in range(first, first + count):
+        p, u, c, x0 = problem.problem_from_inputs(scen[k], coord=coord, factor=factor, max_nodes=20)
+        rng = np.random.default_rng(1000 + k)
+        x = {key: v + (0.0 if key == "t" else 1e-3) * rng.uniform(-1.0, 1.0, v.shape) for key, v in x0.items()}
+        plans.append(gplan.CompiledPlan(p, u, c, user_eq=gplan.PerigeeAtEvent(USER_EVENT), coord=coord))
+        xs.append(problem.xdict_to_vector(x))
+        probs.append((p, u, c, x))
+    return plans, np.stack(xs), probs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (oracle port of the reference's callbacks)
+# ---------------------------------------------------------------------------
+def _cpu_worker(args):
+    factor, n_total, k, reps = args
+    from oracle import leaves, nlp, user_builtin
+
+    plans, X, probs = load_workload(factor, n_total, k, 1)
+    p, u, c, x = probs[0]
+    L = leaves.get("libm")
+    O = nlp.OracleNLP(p, u, c, "libm", "numpy", user_eq=user_builtin.perigee_ratio_at(L, USER_EVENT))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        xa = {key: v.copy() for key, v in x.items()}
+        f, _ = O.objfunc(xa)
+        O.sens(xa)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(factor, evals_per_scen, budget_s):
+    """One host core, one scenario of the workload, objfunc+sens repeated for ~budget_s."""
+    t1 = _cpu_worker((factor, 1, 0, 1))  # also warms imports / builds
+    reps = int(max(2, min(50, budget_s / max(t1, 1e-3))))
+    dt = _cpu_worker((factor, 1, 0, reps))
+    return {"value": evals_per_scen * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d x (objfunc+sens) of 1 scenario of the workload (N=%d nodes), oracle/nlp.py on libm leaves, "
+                      "%.2f s per pair" % (reps, 66 * factor, dt / reps)}
+
+
+def run_reference(args):
+    """The reference's CPU path on all host cores: one scenario per core per step."""
+    import multiprocessing as mp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gelato_b200 import plan as gplan  # counts only; nothing is evaluated by the engine here
+
+    cores = os.cpu_count() or 1
+    plans, _, _ = load_workload(args.factor, 1, 0, 1)
+    ec = plans[0].eval_counts()
+    evals_per_scen = ec["objfunc"] + ec["sens"]
+    del gplan
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(max(1, min(args.warmup, 1))):
+            pool.map(_cpu_worker, [(args.factor, cores, k, 1) for k in range(cores)])
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_worker, [(args.factor, cores, k, 1) for k in range(cores)])
+        dt = time.perf_counter() - t0
+    value = evals_per_scen * cores * steps / dt
+    sample = ("each step = objfunc+sens of %d dispersed scenarios of the workload (one per host core, spawn pool), "
+              "oracle/nlp.py port on libm leaves; %d timed steps" % (cores, steps))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "example_x%d_N%d_split20" % (args.factor, 66 * args.factor),
+                   "scenarios_per_step": cores, "evals_per_scenario_step": evals_per_scen},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gelato(args):
+    import torch
+    import torch.distributed as dist
+
+    from gelato_b200 import engine
+    from gelato_b200 import scenarios as gscen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.scenarios
+    own = gscen.partition(B * world, world, rank)
+    plans, X, probs = load_workload(args.factor, B * world, own.start, len(own))
+    P = plans[0]
+    E = engine.Engine(P, device=local, scenario_plans=plans)
+    ec = P.eval_counts()
+    evals_step_rank = (ec["objfunc"] + ec["sens"]) * B
+    st = torch.cuda.current_stream().cuda_stream
+
+    xd = torch.from_numpy(X).cuda()
+    gd = torch.empty((B, P.n_rows), dtype=torch.float64, device="cuda")
+    vd = torch.empty((B, P.n_vals), dtype=torch.float64, device="cuda")
+    E.fill_template(vd.data_ptr(), B, st)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev(evs=None):
+        if evs:
+            evs[0].record()
+        E.eval_residuals_dev(xd.data_ptr(), gd.data_ptr(), B, st)
+        if evs:
+            evs[1].record()
+        E.eval_jacobian_dev(xd.data_ptr(), vd.data_ptr(), B, st)
+        if evs:
+            evs[2].record()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+        flush.zero_()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = E.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    for k in range(args.steps):
+        step_dev(evs[k])
+        flush.zero_()  # L2 flush between timed steps (outside the per-step event brackets)
+    barrier()
+    dev_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
+    res_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    jac_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    launches = E.launches - launches0
+
+    # ---- end to end through the host-buffer C ABI (what objfunc / sens call) ----
+    px, pg, pv = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * P.n_vals)
+    px.array[:] = X.ravel()
+
+    def step_e2e():
+        E.eval_residuals(px.array, B, out=pg.array)
+        E.eval_jacobian(px.array, B, out=pv.array)
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.array_equal(pg.array.reshape(B, -1), gd.cpu().numpy()), "host and device paths disagree"
+    assert np.array_equal(pv.array.reshape(B, -1), vd.cpu().numpy()), "host and device paths disagree"
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, jac_ms, res_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, jac_ms, res_ms = [float(v) for v in t.cpu()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        n_xdep = int(P.n_xdep)
+        jac_bytes = B * (P.n_vars + n_xdep) * 8.0
+        n_hold = P.N - ec["free_nodes"]
+        del n_hold
+        flops_jac = B * (FLOPS["air"] * 14 * ec["air_fd_nodes"] + FLOPS["noair"] * 9 * (P.N - ec["air_fd_nodes"])
+                         + FLOPS["quat"] * 7 * ec["free_nodes"] + FLOPS["aero"] * ec["aero_jac_evals"]
+                         + FLOPS["evt"] * ec["evt_jac_evals"])
+        try:
+            fma_tf, nofma_tf = engine.fp64_peak(local)
+        except Exception:
+            fma_tf = nofma_tf = None
+        line = {
+            "metric": METRIC, "value": evals_step_rank * world * args.steps / (dev_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "example_x%d_N%d_split20" % (args.factor, P.N), "scenarios_per_gpu": B,
+                       "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows, "n_vals": int(P.n_vals),
+                       "evals_per_scenario_step": ec["objfunc"] + ec["sens"], "parallelism": "scenarios x%d" % world,
+                       "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launch stream"},
+            "clocks": clocks,
+            "e2e": {"value": evals_step_rank * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(2 * X.size * 8),
+                    "d2h_bytes_per_step": int(B * (P.n_rows + P.n_vals) * 8)},
+            "gpu_launches": int(launches),
+            "kernels": {"k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms},
+            "roofline": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": jac_bytes,
+                         "note": "FP64-ALU-bound kernel: see fp64 (DESIGN.md roofline)",
+                         "fp64": {"achieved_tflops": flops_jac / (jac_ms * 1e-3) / 1e12,
+                                  "peak_tflops_dfma": fma_tf, "peak_tflops_dmul_dadd": nofma_tf,
+                                  "frac_of_unfused_peak": (flops_jac / (jac_ms * 1e-3) / 1e12 / nofma_tf) if nofma_tf else None,
+                                  "algorithmic_flops_per_launch": flops_jac}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.factor, ec["objfunc"] + ec["sens"], args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gelato(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""Drop-in `objfunc` / `sens` callbacks backed by the CUDA engine.
+
+Same signatures and return structures as the reference's callbacks
+(/root/reference/Trajectory_Optimization.py:194-242 `objfunc(xdict) -> (funcs,
+fail)`, :245-312 `sens(xdict, funcs) -> (funcsSens, fail)`), so pyoptsparse /
+IPOPT consume them unchanged:
+
+    prob = GelatoProblem(pdict, unitdict, condition, user_eq=PerigeeAtEvent("IIP_END"))
+    optProb = Optimization("Rocket trajectory optimization", prob.objfunc)
+    ... addVarGroup / addConGroup(jac=prob.sens(x0, prob.objfunc(x0)[0])[0][key]) ...
+    IPOPT(options)(optProb, sens=prob.sens)
+
+One call = one host->device copy of x, ONE kernel launch, one device->host copy
+of the whole result, sliced into the reference's dictionaries as views.
+`fail` is always False, like the reference (:240,311); CUDA errors raise.
+"""
+import numpy as np
+
+from . import engine as _engine
+from .plan import GROUPS, VAR_ORDER, CompiledPlan, PerigeeAtEvent  # noqa: F401
+
+
+class GelatoProblem:
+    def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None):
+        self.plan = CompiledPlan(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, coord=coord)
+        self.engine = _engine.Engine(self.plan, device=device)
+        self._x = np.empty(self.plan.n_vars)
+
+    # -- helpers ---------------------------------------------------------
+    def pack(self, xdict):
+        """xdict -> flat decision vector in the engine's order (mass | position |
+        velocity | quaternion | u | t), independent of the dict's key order."""
+        o = 0
+        for k in VAR_ORDER:
+            n = self.plan.sizes[k]
+            v = np.asarray(xdict[k], dtype=np.float64).ravel()
+            if v.size != n:
+                raise ValueError("xdict[%r] has %d entries, expected %d" % (k, v.size, n))
+            self._x[o: o + n] = v
+            o += n
+        return self._x
+
+    # -- the two callbacks -------------------------------------------------
+    def objfunc(self, xdict):
+        g = self.engine.eval_residuals(self.pack(xdict))
+        return self.plan.split_residuals(g), False
+
+    def sens(self, xdict, funcs=None):
+        vals = self.engine.eval_jacobian(self.pack(xdict))
+        return self.plan.split_jacobian(vals, key_order=[k for k in xdict.keys() if k in VAR_ORDER]), False
+
+    # -- flat-vector variants (no dictionaries), used by benchmarks / batched drivers
+    def residuals(self, x, n_scen=1):
+        return self.engine.eval_residuals(x, n_scen)
+
+    def jacobian_values(self, x, n_scen=1):
+        return self.engine.eval_jacobian(x, n_scen)
+
+    def close(self):
+        self.engine.close()
+
+
+def make_callbacks(pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0):
+    """(objfunc, sens) closures with the reference's signatures."""
+    prob = GelatoProblem(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, device=device)
+    return prob.objfunc, prob.sens

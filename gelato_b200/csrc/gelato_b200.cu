@@ -264,13 +264,11 @@ int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev,
   return GELATO_OK;
 }
 
-int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream) {
+int gelato_fill_template(GelatoPlan* p, double* vals_dev, int32_t n_scen, void* stream) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  // constants and D entries: device-to-device copy of the template, then the kernel
-  // overwrites every x-dependent slot
   if (p->vals_template_sstride) {
     CU(cudaMemcpyAsync(vals_dev, p->vals_template, (size_t)n_scen * p->view.n_vals * sizeof(double),
                        cudaMemcpyDeviceToDevice, st));
@@ -279,6 +277,16 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
       CU(cudaMemcpyAsync(vals_dev + (size_t)s * p->view.n_vals, p->vals_template,
                          (size_t)p->view.n_vals * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
+  return GELATO_OK;
+}
+
+int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  // the constants and D entries of vals_dev were put there once by gelato_fill_template;
+  // the kernel rewrites every x-dependent slot and never touches the rest
   dim3 grid(p->n_jac_blocks, n_scen);
   k_jacobian<<<grid, GB_THREADS, 0, st>>>(p->view, p->jac_blocks, x_dev, vals_dev);
   p->launches++;
@@ -304,38 +312,69 @@ static int ensure_staging(GelatoPlan* p, size_t n_scen) {
   CU(cudaMallocHost(&p->h_x, n_scen * v.n_vars * sizeof(double)));
   CU(cudaMallocHost(&p->h_out, n_scen * nout * sizeof(double)));
   p->cap_scen = n_scen;
+  // constants of the Jacobian: written once, the kernel only rewrites x-dependent slots
+  const int chunk = 65535;
+  for (size_t s0 = 0; s0 < n_scen; s0 += chunk) {
+    const int ns = (int)std::min<size_t>(chunk, n_scen - s0);
+    const bool per_scen = p->vals_template_sstride != 0;
+    if (per_scen && s0 > 0) return fail(GELATO_ERR_ARG, "too many scenarios");
+    int rc = gelato_fill_template(p, p->d_vals + s0 * (size_t)v.n_vals, ns, p->stream);
+    if (rc) return rc;
+  }
+  return GELATO_OK;
+}
+
+// page-locked host memory can be DMA'd directly; pageable memory goes through the plan's staging buffers
+static bool is_pinned(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int32_t n_scen) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!x || !out) return fail(GELATO_ERR_ARG, "null buffer");
+  if ((rc = ensure_staging(p, n_scen))) return rc;
+  const PlanView& v = p->view;
+  const size_t nx = (size_t)n_scen * v.n_vars;
+  const size_t no = (size_t)n_scen * (which == 0 ? (size_t)v.n_rows : (size_t)v.n_vals);
+  double* d_out = which == 0 ? p->d_g : p->d_vals;
+  const double* hx = x;
+  if (!is_pinned(x)) {
+    memcpy(p->h_x, x, nx * sizeof(double));
+    hx = p->h_x;
+  }
+  CU(cudaMemcpyAsync(p->d_x, hx, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  if (which == 0) rc = gelato_eval_residuals_dev(p, p->d_x, p->d_g, n_scen, p->stream);
+  else rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream);
+  if (rc) return rc;
+  const bool direct = is_pinned(out);
+  CU(cudaMemcpyAsync(direct ? out : p->h_out, d_out, no * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  if (!direct) memcpy(out, p->h_out, no * sizeof(double));
   return GELATO_OK;
 }
 
 int gelato_eval_residuals(GelatoPlan* p, const double* x, double* g, int32_t n_scen) {
-  int rc = check_scen(p, n_scen);
-  if (rc) return rc;
-  if (!x || !g) return fail(GELATO_ERR_ARG, "null buffer");
-  if ((rc = ensure_staging(p, n_scen))) return rc;
-  const PlanView& v = p->view;
-  const size_t nx = (size_t)n_scen * v.n_vars, ng = (size_t)n_scen * v.n_rows;
-  memcpy(p->h_x, x, nx * sizeof(double));
-  CU(cudaMemcpyAsync(p->d_x, p->h_x, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-  if ((rc = gelato_eval_residuals_dev(p, p->d_x, p->d_g, n_scen, p->stream))) return rc;
-  CU(cudaMemcpyAsync(p->h_out, p->d_g, ng * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  CU(cudaStreamSynchronize(p->stream));
-  memcpy(g, p->h_out, ng * sizeof(double));
-  return GELATO_OK;
+  return eval_host(p, 0, x, g, n_scen);
 }
 
 int gelato_eval_jacobian(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
-  int rc = check_scen(p, n_scen);
-  if (rc) return rc;
-  if (!x || !vals) return fail(GELATO_ERR_ARG, "null buffer");
-  if ((rc = ensure_staging(p, n_scen))) return rc;
-  const PlanView& v = p->view;
-  const size_t nx = (size_t)n_scen * v.n_vars, nv = (size_t)n_scen * (size_t)v.n_vals;
-  memcpy(p->h_x, x, nx * sizeof(double));
-  CU(cudaMemcpyAsync(p->d_x, p->h_x, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-  if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
-  CU(cudaMemcpyAsync(p->h_out, p->d_vals, nv * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  CU(cudaStreamSynchronize(p->stream));
-  memcpy(vals, p->h_out, nv * sizeof(double));
+  return eval_host(p, 1, x, vals, n_scen);
+}
+
+int gelato_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(GELATO_ERR_ARG, "null");
+  CU(cudaMallocHost(out, bytes));
+  return GELATO_OK;
+}
+
+int gelato_host_free(void* ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
   return GELATO_OK;
 }
 
@@ -345,9 +384,6 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
   if (rc) return rc;
   if (reps <= 0 || !avg_ms) return fail(GELATO_ERR_ARG, "bad reps");
   CU(cudaSetDevice(p->device));
-  if (which == 1) {  // template once; the timed region is the kernel alone
-    if ((rc = gelato_eval_jacobian_dev(p, x_dev, out_dev, n_scen, p->stream))) return rc;
-  }
   CU(cudaStreamSynchronize(p->stream));
   CU(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < reps; i++) {

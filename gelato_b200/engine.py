@@ -174,6 +174,9 @@ def load_library():
     L.gelato_eval_jacobian.argtypes = [vp, _pd, _pd, ctypes.c_int32]
     L.gelato_eval_residuals_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_eval_jacobian_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_fill_template.argtypes = [vp, vp, ctypes.c_int32, vp]
+    L.gelato_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.gelato_host_free.argtypes = [vp]
     L.gelato_time_kernel.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_float)]
     L.gelato_selftest_unfused.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
@@ -186,7 +189,7 @@ EXPORTS = (
     "gelato_last_error gelato_device_count gelato_plan_create gelato_plan_set_scenarios gelato_plan_destroy "
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
-    "gelato_selftest_unfused gelato_fp64_peak"
+    "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free"
 ).split()
 
 
@@ -258,6 +261,10 @@ class Engine:
     def eval_residuals_dev(self, x_ptr, g_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_residuals_dev(self.h, x_ptr, g_ptr, n_scen, stream), "gelato_eval_residuals_dev")
 
+    def fill_template(self, vals_ptr, n_scen=1, stream=None):
+        """Write the constant Jacobian entries into a device buffer (once per buffer)."""
+        _check(self.L, self.L.gelato_fill_template(self.h, vals_ptr, n_scen, stream), "gelato_fill_template")
+
     def eval_jacobian_dev(self, x_ptr, vals_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_jacobian_dev(self.h, x_ptr, vals_ptr, n_scen, stream), "gelato_eval_jacobian_dev")
 
@@ -268,6 +275,22 @@ class Engine:
         _check(self.L, self.L.gelato_time_kernel(self.h, which, x_ptr, out_ptr, n_scen, reps, ctypes.byref(ms)),
                "gelato_time_kernel")
         return float(ms.value)
+
+
+class PinnedArray:
+    """A page-locked float64 host array (gelato_host_alloc) the engine DMAs directly."""
+
+    def __init__(self, n):
+        self.L = load_library()
+        self.ptr = ctypes.c_void_p()
+        _check(self.L, self.L.gelato_host_alloc(max(8, int(n) * 8), ctypes.byref(self.ptr)), "gelato_host_alloc")
+        self.array = np.frombuffer((ctypes.c_double * int(n)).from_address(self.ptr.value), dtype=np.float64)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.L.gelato_host_free(self.ptr)
+            self.ptr = None
 
 
 def fp64_peak(device=0):

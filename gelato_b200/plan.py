@@ -840,28 +840,43 @@ class CompiledPlan:
     # ------------------------------------------------------------------
     # host-side views of the kernels' outputs
     def eval_counts(self):
-        """Leaf evaluations per objfunc and per sens call."""
-        n_air = n_noair = n_free = 0
+        """Physics-leaf evaluations per objfunc and per sens call, one per
+        (node x perturbation column), centre points included."""
+        n_air = n_air_fd = n_free = 0
         for i in range(self.S):
             n = self._sec[i][4]
             fl = int(self.sec_i32[i, GS_FLAGS])
-            if fl & GSF_AIR:
-                n_air += n
-            else:
-                n_noair += n
-            if not fl & GSF_HOLD:
-                n_free += n
-        n_air_fd = sum(self._sec[i][4] for i in range(self.S) if self.sec_i32[i, GS_FLAGS] & GSF_AIR_FD)
-        n_vel_nofd = self.N - n_air_fd
+            n_air += n if fl & GSF_AIR else 0
+            n_air_fd += n if fl & GSF_AIR_FD else 0
+            n_free += 0 if fl & GSF_HOLD else n
         aero_rows = {0: 0, 1: 0, 2: 0}
         for j in self._aero:
             aero_rows[j["i32"][0]] += j["i32"][2]
         lanes = {GE_LLH: 5, GE_IIP: 8, GE_ANT: 5, GE_TERM: 7, GE_USER_PERIGEE: 13}
         evt_jac = sum(lanes[j["i32"][0]] for j in self._evt)
+        aero_jac = 13 * aero_rows[0] + 9 * aero_rows[1] + 13 * aero_rows[2]
         obj = self.N + n_free + sum(aero_rows.values()) + len(self._evt)
-        sens = 14 * n_air_fd + 9 * n_vel_nofd + 7 * n_free + 13 * aero_rows[0] + 9 * aero_rows[1] + 13 * aero_rows[2]
-        sens += evt_jac
-        return {"objfunc": obj, "sens": sens, "air_nodes": n_air, "noair_nodes": n_noair, "free_nodes": n_free}
+        sens = 14 * n_air_fd + 9 * (self.N - n_air_fd) + 7 * n_free + aero_jac + evt_jac
+        return {"objfunc": obj, "sens": sens, "air_nodes": n_air, "air_fd_nodes": n_air_fd,
+                "noair_nodes": self.N - n_air, "free_nodes": n_free, "aero_rows": sum(aero_rows.values()),
+                "aero_jac_evals": aero_jac, "evt_jobs": len(self._evt), "evt_jac_evals": evt_jac}
+
+    @property
+    def n_xdep(self):
+        """Jacobian slots that depend on x (what the Jacobian kernel writes each call);
+        the other n_vals - n_xdep slots are constants / D entries set once."""
+        cnt = 0
+        for i in range(self.S):
+            n = self._sec[i][4]
+            fl = int(self.sec_i32[i, GS_FLAGS])
+            cnt += 9 * n + 30 * n + (9 * n if fl & GSF_AIR_FD else 0)
+            cnt += 0 if fl & GSF_HOLD else 32 * n
+        for j in self._aero:
+            cnt += j["i32"][2] * (12 if j["i32"][0] != 1 else 8)
+        per = {GE_LLH: 4, GE_IIP: 7, GE_ANT: 4, GE_USER_PERIGEE: AUX_PER_USER}
+        for j in self._evt:
+            cnt += 6 * j["i32"][GE_NROW] if j["i32"][0] == GE_TERM else per[j["i32"][0]]
+        return cnt
 
     def split_residuals(self, g):
         """g[n_rows] -> the reference's `funcs` dict (views into g)."""

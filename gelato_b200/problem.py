@@ -171,6 +171,78 @@ def load_problem(settings_path, coord=None):
     return pdict, unitdict, condition, xdict
 
 
+TRAJ_COLUMNS = (
+    "time mass pos_ECI_X pos_ECI_Y pos_ECI_Z vel_ECI_X vel_ECI_Y vel_ECI_Z quat_ECI2BODY_0 quat_ECI2BODY_1 "
+    "quat_ECI2BODY_2 quat_ECI2BODY_3 rate_BODY_Y rate_BODY_Z"
+).split()
+
+
+def read_inputs(settings_path):
+    """All inputs of a reference-format problem as one plain dictionary
+    {"settings", "events", "wind_table", "ca_table", "trajectory"}."""
+    base = os.path.dirname(os.path.abspath(settings_path))
+    with open(settings_path) as f:
+        settings = json.load(f)
+    inp = {
+        "settings": settings,
+        "events": read_events(os.path.join(base, settings["Event setting file"])),
+        "wind_table": read_wind_table(os.path.join(base, settings["Wind file"])),
+        "ca_table": read_ca_table(os.path.join(base, settings["CA file"])),
+        "trajectory": None,
+    }
+    if settings.get("Initial trajectory file") is not None:
+        traj = read_trajectory(os.path.join(base, settings["Initial trajectory file"]))
+        inp["trajectory"] = {k: np.asarray(traj[k], dtype=np.float64) for k in TRAJ_COLUMNS}
+    return inp
+
+
+def dump_inputs_json(inp, path):
+    """Freeze `read_inputs` output into one JSON file (floats round-trip exactly)."""
+    def ev(e):
+        e = dict(e)
+        if isinstance(e["time_ref"], float):  # NaN = free event time
+            e["time_ref"] = None
+        return e
+
+    doc = {
+        "settings": inp["settings"],
+        "events": [ev(e) for e in inp["events"]],
+        "wind_table": np.asarray(inp["wind_table"]).tolist(),
+        "ca_table": np.asarray(inp["ca_table"]).tolist(),
+        "trajectory": None if inp["trajectory"] is None else {k: np.asarray(v).tolist() for k, v in inp["trajectory"].items()},
+    }
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=0, sort_keys=False)
+
+
+def load_inputs_json(path):
+    with open(path) as f:
+        doc = json.load(f)
+    for e in doc["events"]:
+        if e["time_ref"] is None:
+            e["time_ref"] = float("nan")
+    doc["wind_table"] = np.array(doc["wind_table"], dtype=np.float64)
+    doc["ca_table"] = np.array(doc["ca_table"], dtype=np.float64)
+    if doc["trajectory"] is not None:
+        doc["trajectory"] = {k: np.array(v, dtype=np.float64) for k, v in doc["trajectory"].items()}
+    return doc
+
+
+def problem_from_inputs(inp, coord=None, factor=1, max_nodes=20):
+    """(pdict, unitdict, condition, xdict0) from a `read_inputs` dictionary;
+    factor > 1 refines the mesh with `refine_events` (C2)."""
+    settings = copy.deepcopy(inp["settings"])
+    events = copy.deepcopy(inp["events"])
+    if factor != 1:
+        events, fc = refine_events(events, settings["FlightConstraint"], factor, max_nodes)
+        settings["FlightConstraint"] = fc
+    pdict, unitdict, condition = build_problem(settings, events, inp["wind_table"], inp["ca_table"], coord)
+    xdict = None
+    if inp.get("trajectory") is not None:
+        xdict = initial_guess_from_table(inp["trajectory"], pdict, unitdict)
+    return pdict, unitdict, condition, xdict
+
+
 def _interp_extrap(tq, t, y):
     """Piecewise-linear interpolation with linear extrapolation (the behaviour of
     scipy interp1d(fill_value="extrapolate") the reference uses)."""

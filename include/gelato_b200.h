@@ -26,6 +26,7 @@
 #ifndef GELATO_B200_H_
 #define GELATO_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,13 +174,22 @@ int64_t gelato_plan_launch_count(const GelatoPlan* plan);
 
 /* Host-buffer entry points (what the drop-in objfunc / sens call): copy x to the
  * device, run ONE fused kernel, copy the result back.  n_scen = 1 for a single NLP;
- * x is [n_scen][n_vars], g [n_scen][n_rows], vals [n_scen][n_vals]. */
+ * x is [n_scen][n_vars], g [n_scen][n_rows], vals [n_scen][n_vals].  Buffers obtained
+ * from gelato_host_alloc (page-locked) are DMA'd directly; any other host memory is
+ * staged through the plan's own page-locked buffers. */
 int gelato_eval_residuals(GelatoPlan* plan, const double* x, double* g, int32_t n_scen);
 int gelato_eval_jacobian(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
 
+int gelato_host_alloc(size_t bytes, void** out);
+int gelato_host_free(void* ptr);
+
 /* Device-resident entry points: pointers are device memory, work is enqueued on
- * `stream` (a cudaStream_t, NULL = the plan's own stream) and NOT synchronised. */
+ * `stream` (a cudaStream_t, NULL = the plan's own stream) and NOT synchronised.
+ * A vals_dev buffer must be initialised ONCE with gelato_fill_template (constants and
+ * D entries, which never change); gelato_eval_jacobian_dev then rewrites every
+ * x-dependent slot on each call and leaves the constants alone. */
 int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
+int gelato_fill_template(GelatoPlan* plan, double* vals_dev, int32_t n_scen, void* stream);
 int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
 
 /* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen

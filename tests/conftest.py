@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_test_libs():
+    """Build the CPU-side checkers once: the oracle (both flavours) and the host
+    emulator of the kernels.  The product library is built by __graft_entry__.build()."""
+    from oracle import leaves
+
+    leaves.build()
+    import emu_binding
+
+    emu_binding.build()

@@ -1,0 +1,98 @@
+"""Regenerates the golden fixtures in this folder.  Run ONLY in the container
+that holds the reference at /root/reference (it is not available on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What it writes
+  example_inputs.json   the shipped example's inputs (settings JSON, events / wind /
+                        CA tables, the columns of the initial-trajectory table the
+                        initial guess reads) re-serialised by gelato_b200.problem.
+  example_reference.npz decision vectors x0 (initial guess) and x1 (x0 + 1e-3 noise) and,
+                        for each, every `funcs` entry and every Jacobian block returned by
+                        the REFERENCE'S OWN Python layer (/root/reference/lib/con_*.py and the
+                        objfunc / sens bodies of Trajectory_Optimization.py, imported where
+                        they lie) running on the oracle's libm physics leaves, because the
+                        reference's pybind11/Eigen modules cannot be built here
+                        (/root/reference/CMakeLists.txt:13, no Eigen3).
+  example_gmath.npz     the same quantities from oracle/nlp.py with the gmath leaves and
+                        sequential-FMA D.X -- the flavour the CUDA kernels must match
+                        bit for bit on any machine.
+  psparams.npz          tau and D of the reference's PSparams for n = 2..24.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import helpers  # noqa: E402
+import refharness  # noqa: E402
+from gelato_b200 import problem  # noqa: E402
+from oracle import leaves  # noqa: E402
+
+
+def pack(prefix, f, s, out):
+    for k, v in helpers.flatten_funcs(f).items():
+        out["%s/f/%s" % (prefix, k)] = v
+    for k, (r, c, d, shape) in helpers.flatten_sens(s).items():
+        out["%s/j/%s/data" % (prefix, k)] = d
+        out["%s/j/%s/shape" % (prefix, k)] = np.array(shape, dtype=np.int64)
+        if r is not None:
+            out["%s/j/%s/rows" % (prefix, k)] = r
+            out["%s/j/%s/cols" % (prefix, k)] = c
+    out["%s/none_f" % prefix] = np.array([k for k, v in f.items() if v is None])
+    out["%s/none_j" % prefix] = np.array([k for k, v in s.items() if v is None])
+
+
+def main():
+    assert refharness.available(), "/root/reference is required"
+    inp = problem.read_inputs(os.path.join(refharness.REF, "example", "example-settings.json"))
+    problem.dump_inputs_json(inp, helpers.INPUTS)
+
+    # ---- the reference's own Python layer on libm leaves -----------------
+    L = leaves.get("libm")
+    pdict, unitdict, condition = refharness.reference_setup(L)
+    objfunc, sens = refharness.reference_callbacks(L, pdict, unitdict, condition)
+    p, u, c, x0 = helpers.example_problem()
+    x1 = helpers.perturbed(x0)
+    out = {}
+    for name, x in (("x0", x0), ("x1", x1)):
+        out["%s/x" % name] = problem.xdict_to_vector(x)
+        xa = helpers.copy_x(x)
+        f, fail = objfunc(xa)
+        assert fail is False
+        s, fail = sens(xa, f)
+        pack(name, f, s, out)
+    np.savez_compressed(os.path.join(HERE, "example_reference.npz"), **out)
+
+    # ---- gmath / sequential-FMA flavour of the oracle ---------------------
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+    out = {}
+    for name, x in (("x0", x0), ("x1", helpers.perturbed(x0))):
+        out["%s/x" % name] = problem.xdict_to_vector(x)
+        xa = helpers.copy_x(x)
+        f, _ = O.objfunc(xa)
+        s, _ = O.sens(xa)
+        pack(name, f, s, out)
+    np.savez_compressed(os.path.join(HERE, "example_gmath.npz"), **out)
+
+    # ---- reference PSparams ------------------------------------------------
+    ns = refharness.load(L)
+    ps_out = {}
+    for n in range(2, 25):
+        ps = ns["PSparams"]([n])
+        ps_out["tau_%d" % n] = ps.tau(0)
+        ps_out["D_%d" % n] = ps.D(0)
+    np.savez_compressed(os.path.join(HERE, "psparams.npz"), **ps_out)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

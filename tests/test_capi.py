@@ -1,0 +1,91 @@
+"""The C-ABI library: loads, exports every symbol include/gelato_b200.h declares,
+matches the ctypes struct layout, and refuses to evaluate without a CUDA device
+(there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+from gelato_b200 import engine
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gelato_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"\b(gelato_[a-z0-9_]+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(engine.LIB_PATH), "run __graft_entry__.build() first"
+    L = engine.load_library()
+    declared = _declared_functions()
+    assert len(declared) >= 16
+    assert sorted(set(declared)) == sorted(engine.EXPORTS)
+    for name in declared:
+        assert getattr(L, name) is not None, name
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    """No C++ / torch types at the boundary: the header is valid C99."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "gelato_b200.h"\nint main(void){GelatoPlanDesc d; GelatoScenarioDesc s; (void)d; (void)s; '
+                   "return sizeof(d) > 0 ? 0 : 1;}\n")
+    import subprocess
+
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(HEADER), "-c", str(src), "-o",
+                           str(tmp_path / "t.o")])
+
+
+def test_struct_layout_matches_header(tmp_path):
+    import subprocess
+
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gelato_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", '
+                   "sizeof(GelatoPlanDesc), offsetof(GelatoPlanDesc, vals_template), offsetof(GelatoPlanDesc, unit_mass), "
+                   "sizeof(GelatoScenarioDesc), offsetof(GelatoPlanDesc, rc_aero)); return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(engine.PlanDesc)
+    assert out[1] == engine.PlanDesc.vals_template.offset
+    assert out[2] == engine.PlanDesc.unit_mass.offset
+    assert out[3] == ctypes.sizeof(engine.ScenarioDesc)
+    assert out[4] == engine.PlanDesc.rc_aero.offset
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU plan creation must fail loudly, not fall back to the host."""
+    L = engine.load_library()
+    if L.gelato_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p, u, c, x0 = helpers.example_problem()
+    P = helpers.compiled_plan(p, u, c)
+    with pytest.raises(engine.GelatoError, match="no CUDA device"):
+        engine.Engine(P)
+
+
+def test_enum_constants_match_header():
+    """gelato_b200/plan.py mirrors the header's table-column enums."""
+    from gelato_b200 import plan as gp
+
+    src = open(HEADER).read()
+    for name, val in (("GS_I32_COLS", gp.GS_I32_COLS), ("GS_I64_COLS", gp.GS_I64_COLS), ("GS_F64_COLS", gp.GS_F64_COLS),
+                      ("GL_I32_COLS", gp.GL_I32_COLS), ("GL_F64_COLS", gp.GL_F64_COLS), ("GA_I32_COLS", gp.GA_I32_COLS),
+                      ("GA_I64_COLS", gp.GA_I64_COLS), ("GE_I64_COLS", gp.GE_I64_COLS), ("GE_F64_COLS", gp.GE_F64_COLS)):
+        assert name in src
+    prog = '#include <stdio.h>\n#include "gelato_b200.h"\nint main(void){printf("%d %d %d %d %d %d %d %d %d %d\\n", GS_I32_COLS, GS_I64_COLS, GS_F64_COLS, GL_I32_COLS, GL_F64_COLS, GA_I32_COLS, GA_I64_COLS, GE_I32_COLS, GE_I64_COLS, GE_F64_COLS); return 0;}\n'
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "e.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), os.path.join(d, "e.c"), "-o", os.path.join(d, "e")])
+        got = [int(v) for v in subprocess.check_output([os.path.join(d, "e")]).split()]
+    assert got == [gp.GS_I32_COLS, gp.GS_I64_COLS, gp.GS_F64_COLS, gp.GL_I32_COLS, gp.GL_F64_COLS, gp.GA_I32_COLS,
+                   gp.GA_I64_COLS, gp.GE_I32_COLS, gp.GE_I64_COLS, gp.GE_F64_COLS]
+    assert np.dtype("i4").itemsize == 4

@@ -1,0 +1,125 @@
+"""CPU tier: the kernels' per-thread code (gelato_b200/csrc/jobs.h + physics.h),
+stepped through by the host emulator in tests/emu with the plan the problem
+compiler emits, must equal the oracle (gmath leaves, sequential-FMA D.X) BIT FOR
+BIT: residual rows, Jacobian sparsity (row/col arrays, dtype, order, explicit
+zeros) and Jacobian values -- including the fl(fl(x+dx)-dx) residue the
+reference's in-place finite differences leave for later columns and groups.
+The same assertions run against the real GPU in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+import emu_binding
+import helpers
+from gelato_b200 import plan as gplan
+from gelato_b200 import problem
+from oracle import leaves
+
+
+def _setup(variant, factor, max_nodes=12, user=True):
+    Lg = leaves.get("gmath")
+    inp = helpers.variant_inputs(variant)
+    p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c, factor=factor, max_nodes=max_nodes)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma", user=user)
+    P = helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c, user=user)
+    return p, u, c, x0, O, P
+
+
+@pytest.mark.parametrize("variant,factor,user", [
+    ("example", 1, True), ("example", 3, True), ("fuel_inclination", 1, True), ("all_aero", 2, True),
+    ("waypoints", 1, True), ("waypoints", 2, False), ("bare", 1, False),
+])
+def test_emulated_kernels_match_oracle_bitwise(variant, factor, user):
+    p, u, c, x0, O, P = _setup(variant, factor, user=user)
+    E = emu_binding.Emulator(P)
+    for x in (x0, helpers.perturbed(x0)):
+        xv = problem.xdict_to_vector(x)
+        xa = helpers.copy_x(x)
+        f, _ = O.objfunc(xa)
+        helpers.assert_funcs_equal(f, P.split_residuals(E.eval_residuals(xv)))
+        s, _ = O.sens(xa)
+        vals = E.eval_jacobian(xv)
+        assert not np.isnan(vals).any(), "a Jacobian slot was left unwritten"
+        helpers.assert_sens_equal(s, P.split_jacobian(vals, key_order=list(x.keys())))
+
+
+def test_large_section_counts():
+    """A section larger than one residual block (n = 40 > 32 nodes) and the minimum n = 2."""
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    inp["events"][2]["num_nodes"] = 40
+    p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+    P = helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c)
+    E = emu_binding.Emulator(P)
+    x = helpers.perturbed(x0)
+    xa = helpers.copy_x(x)
+    f, _ = O.objfunc(xa)
+    helpers.assert_funcs_equal(f, P.split_residuals(E.eval_residuals(problem.xdict_to_vector(x))))
+    s, _ = O.sens(xa)
+    helpers.assert_sens_equal(s, P.split_jacobian(E.eval_jacobian(problem.xdict_to_vector(x)), key_order=list(x.keys())))
+
+
+def test_residue_sensitive_inputs():
+    """Values for which (x + dx) - dx != x (binade crossings, |x| <~ dx)
+    planted in every perturbed variable group."""
+    p, u, c, x0, O, P = _setup("waypoints", 1)
+    E = emu_binding.Emulator(P)
+    x = helpers.copy_x(x0)
+    specials = np.array([0.9999999999, 0.249999995, 3e-9, 1e-12, 0.0, 0.499999999, -3e-9, 1.0 - 1e-9])
+    rng = np.random.default_rng(3)
+    for k in ("velocity", "quaternion", "u"):
+        idx = rng.choice(x[k].size, size=24, replace=False)
+        x[k][idx] = rng.choice(specials, size=24)
+    xv = problem.xdict_to_vector(x)
+    xa = helpers.copy_x(x)
+    s, _ = O.sens(xa)
+    assert any(not np.array_equal(xa[k], x[k]) for k in x), "test inputs left no residue"
+    helpers.assert_sens_equal(s, P.split_jacobian(E.eval_jacobian(xv), key_order=list(x.keys())))
+
+
+def test_key_order_of_dense_user_blocks():
+    """jac_fd walks xdict in insertion order (jac_fd.py:54); the set-up call of the
+    reference uses a different order than pyoptsparse does at run time."""
+    p, u, c, x0, O, P = _setup("example", 1)
+    E = emu_binding.Emulator(P)
+    order = ["t", "u", "mass", "position", "velocity", "quaternion"]
+    x = {k: helpers.perturbed(x0)[k] for k in order}
+    xa = helpers.copy_x(x)
+    s, _ = O.sens(xa)
+    got = P.split_jacobian(E.eval_jacobian(problem.xdict_to_vector(x)), key_order=order)
+    assert list(got["eqcon_user"].keys()) == order
+    for k in order:
+        assert np.array_equal(got["eqcon_user"][k], s["eqcon_user"][k]), k
+
+
+def test_plan_rejects_arbitrary_python_user_constraints():
+    p, u, c, x0 = helpers.example_problem()
+    with pytest.raises(TypeError):
+        gplan.CompiledPlan(p, u, c, user_eq=lambda *a: 0.0)
+
+
+def test_batched_scenarios_match_per_scenario_oracle():
+    """Dispersed scenarios (mass / thrust / wind) evaluated as one batch."""
+    from gelato_b200 import scenarios
+
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    scen = scenarios.disperse(inp, 3, seed=20260117)
+    plans, oracles, xs = [], [], []
+    for si in scen:
+        p, u, c, x0 = problem.problem_from_inputs(si, coord=Lg.coordinate_c)
+        plans.append(helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c))
+        oracles.append(helpers.oracle_nlp(p, u, c, "gmath", "seqfma"))
+        xs.append(helpers.perturbed(x0, seed=len(xs)))
+    E = emu_binding.Emulator(plans[0], scenario_plans=plans)
+    X = np.stack([problem.xdict_to_vector(x) for x in xs])
+    G = E.eval_residuals(X, n_scen=3)
+    V = E.eval_jacobian(X, n_scen=3)
+    for k in range(3):
+        xa = helpers.copy_x(xs[k])
+        f, _ = oracles[k].objfunc(xa)
+        helpers.assert_funcs_equal(f, plans[k].split_residuals(G[k]))
+        s, _ = oracles[k].sens(xa)
+        helpers.assert_sens_equal(s, plans[k].split_jacobian(V[k], key_order=list(xs[k].keys())))
+    assert not np.array_equal(G[0], G[1])

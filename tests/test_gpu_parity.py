@@ -1,0 +1,224 @@
+"""GPU tier (run with -m gpu on the B200 box): the CUDA engine, called through
+the C ABI exactly as the drop-in objfunc / sens call it, against
+
+  * the oracle (gmath leaves, sequential-FMA D.X): BIT-EXACT residual rows,
+    Jacobian sparsity and Jacobian values, on the shipped example, refined meshes
+    and constraint variants;
+  * the committed golden fixtures: bit-exact for the gmath flavour; for the
+    fixture produced by the reference's own Python layer on libm leaves the
+    north-star tolerance 1e-10 relative (to the term scale for residuals; FD
+    slots get the finite-difference noise allowance of DESIGN.md H1);
+  * size-independent properties at the full benchmark sizes (1e4 .. 1e5 nodes).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from gelato_b200 import callbacks, engine, problem, scenarios
+from oracle import leaves
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(variant="example", factor=1, max_nodes=12, user=True):
+    Lg = leaves.get("gmath")
+    inp = helpers.variant_inputs(variant)
+    p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c, factor=factor, max_nodes=max_nodes)
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT) if user else None,
+                                   coord=Lg.coordinate_c)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma", user=user)
+    return prob, O, x0
+
+
+def test_library_is_the_cuda_build():
+    L = engine.load_library()
+    assert L.gelato_device_count() >= 1
+    prob, O, x0 = _problem()
+    assert prob.engine.launches == 0
+    prob.objfunc(x0)
+    prob.sens(x0)
+    assert prob.engine.launches == 2  # ONE kernel per callback
+
+
+@pytest.mark.parametrize("variant,factor,user", [
+    ("example", 1, True), ("example", 4, True), ("example", 15, True), ("fuel_inclination", 1, True),
+    ("all_aero", 2, True), ("waypoints", 1, True), ("waypoints", 3, False), ("bare", 1, False),
+])
+def test_gpu_matches_oracle_bitwise(variant, factor, user):
+    prob, O, x0 = _problem(variant, factor, max_nodes=20 if factor == 15 else 12, user=user)
+    for x in (x0, helpers.perturbed(x0)):
+        xa = helpers.copy_x(x)
+        f, fail = prob.objfunc(x)
+        assert fail is False
+        fo, _ = O.objfunc(xa)
+        helpers.assert_funcs_equal(fo, f)
+        s, fail = prob.sens(x, f)
+        so, _ = O.sens(xa)
+        helpers.assert_sens_equal(so, s)
+        for k in x:  # the drop-in never mutates the caller's xdict
+            assert np.array_equal(x[k], (x0 if x is x0 else x)[k])
+    prob.close()
+
+
+@pytest.mark.parametrize("name", ["x0", "x1"])
+def test_gpu_matches_gmath_golden_bitwise(name):
+    npz = np.load(os.path.join(helpers.GOLDEN, "example_gmath.npz"))
+    prob, O, x0 = _problem()
+    P = prob.plan
+    x = problem.vector_to_xdict(npz["%s/x" % name].copy(), P.M, P.N, P.S)
+    f, _ = prob.objfunc(x)
+    for k, v in helpers.flatten_funcs(f).items():
+        assert np.array_equal(v, npz["%s/f/%s" % (name, k)]), k
+    s, _ = prob.sens(x, f)
+    for k, (r, c, d, shape) in helpers.flatten_sens(s).items():
+        assert np.array_equal(d, npz["%s/j/%s/data" % (name, k)]), k
+        if r is not None:
+            assert np.array_equal(r, npz["%s/j/%s/rows" % (name, k)]), k
+            assert np.array_equal(c, npz["%s/j/%s/cols" % (name, k)]), k
+    prob.close()
+
+
+@pytest.mark.parametrize("name", ["x0", "x1"])
+def test_gpu_matches_reference_golden_within_tolerance(name):
+    """Against the fixture produced by the reference's own Python layer (libm physics,
+    BLAS D.X).  Residuals: 1e-10 relative to the term scale (the defect itself tends to
+    0 at convergence).  Jacobian: identical sparsity; analytic slots to 1e-10 relative;
+    finite-difference slots 1e-10 relative + the FD noise floor eps*|f|/dx*scale
+    (a 1-ulp difference in ANY elementary function moves an FD quotient by ~1e-8 |f|)."""
+    npz = np.load(os.path.join(helpers.GOLDEN, "example_reference.npz"))
+    p, u, c, x0 = helpers.example_problem()  # host set-up through libm, like the reference
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT))
+    P = prob.plan
+    x = problem.vector_to_xdict(npz["%s/x" % name].copy(), P.M, P.N, P.S)
+    f, _ = prob.objfunc(x)
+    for k, v in helpers.flatten_funcs(f).items():
+        ref = npz["%s/f/%s" % (name, k)]
+        atol = 1e-11 if "alpha" in k else 1e-13  # acos near 1 for the angle-of-attack rows; terms are O(1e-3..1)
+        np.testing.assert_allclose(v, ref, rtol=1e-10, atol=atol, err_msg=k)
+    s, _ = prob.sens(x, f)
+    worst = 0.0
+    for k, (r, c_, d, shape) in helpers.flatten_sens(s).items():
+        ref = npz["%s/j/%s/data" % (name, k)]
+        if r is not None:
+            assert np.array_equal(r, npz["%s/j/%s/rows" % (name, k)]), k
+            assert np.array_equal(c_, npz["%s/j/%s/cols" % (name, k)]), k
+        assert tuple(shape) == tuple(npz["%s/j/%s/shape" % (name, k)].tolist())
+        np.testing.assert_allclose(d, ref, rtol=1e-10, atol=2e-6, err_msg=k)
+        worst = max(worst, float(np.max(np.abs(d - ref))) if d.size else 0.0)
+    assert worst < 2e-6
+    prob.close()
+
+
+def test_batched_scenarios_bitwise_and_independent_of_batching():
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    scen = scenarios.disperse(inp, 5, seed=20260117)
+    plans, oracles, xs = [], [], []
+    for si in scen:
+        p, u, c, x0 = problem.problem_from_inputs(si, coord=Lg.coordinate_c)
+        plans.append(helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c))
+        oracles.append(helpers.oracle_nlp(p, u, c, "gmath", "seqfma"))
+        xs.append(helpers.perturbed(x0, seed=len(xs)))
+    E = engine.Engine(plans[0], scenario_plans=plans)
+    X = np.stack([problem.xdict_to_vector(x) for x in xs])
+    G = E.eval_residuals(X, n_scen=5)
+    V = E.eval_jacobian(X, n_scen=5)
+    for k in range(5):
+        xa = helpers.copy_x(xs[k])
+        f, _ = oracles[k].objfunc(xa)
+        helpers.assert_funcs_equal(f, plans[k].split_residuals(G[k]))
+        s, _ = oracles[k].sens(xa)
+        helpers.assert_sens_equal(s, plans[k].split_jacobian(V[k], key_order=list(xs[k].keys())))
+    # a smaller batch gives the same bits for the scenarios it contains
+    assert np.array_equal(E.eval_jacobian(X[:2], n_scen=2), V[:2])
+    E.close()
+
+
+def test_device_resident_entry_points_and_pinned_buffers():
+    import torch
+
+    prob, O, x0 = _problem("example", 4)
+    E, P = prob.engine, prob.plan
+    xv = problem.xdict_to_vector(helpers.perturbed(x0))
+    g_host = E.eval_residuals(xv).copy()
+    v_host = E.eval_jacobian(xv).copy()
+    xd = torch.from_numpy(xv).cuda()
+    gd = torch.full((P.n_rows,), float("nan"), dtype=torch.float64, device="cuda")
+    vd = torch.full((P.n_vals,), float("nan"), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    E.fill_template(vd.data_ptr(), 1, st)
+    E.eval_residuals_dev(xd.data_ptr(), gd.data_ptr(), 1, st)
+    E.eval_jacobian_dev(xd.data_ptr(), vd.data_ptr(), 1, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(gd.cpu().numpy(), g_host)
+    assert np.array_equal(vd.cpu().numpy(), v_host)
+    # page-locked caller buffers take the direct-DMA path
+    px, pv = engine.PinnedArray(P.n_vars), engine.PinnedArray(P.n_vals)
+    px.array[:] = xv
+    E.eval_jacobian(px.array, out=pv.array)
+    assert np.array_equal(pv.array, v_host)
+    px.free()
+    pv.free()
+    prob.close()
+
+
+def test_repeated_calls_are_deterministic_and_template_survives():
+    prob, O, x0 = _problem("example", 2)
+    E = prob.engine
+    xa = problem.xdict_to_vector(x0)
+    xb = problem.xdict_to_vector(helpers.perturbed(x0))
+    va = E.eval_jacobian(xa).copy()
+    vb = E.eval_jacobian(xb).copy()
+    assert not np.array_equal(va, vb)
+    assert np.array_equal(E.eval_jacobian(xa), va)  # x-dependent slots fully rewritten, constants untouched
+    assert np.array_equal(E.eval_jacobian(xb), vb)
+    prob.close()
+
+
+@pytest.mark.parametrize("factor", [150, 1500])
+def test_full_size_properties(factor):
+    """C5 sizes (N = 9 900 and 99 000 nodes): the oracle is too slow there, so check
+    properties that do not depend on the size:
+      * section locality: every section's rows equal the rows of the same section
+        evaluated inside a small problem (sampled sections vs the oracle);
+      * linear groups satisfy g = J x + c with the emitted COO blocks;
+      * the Jacobian of a batch equals the Jacobian of each member."""
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c, factor=factor, max_nodes=20)
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
+    P = prob.plan
+    assert P.N == 66 * factor
+    x = helpers.perturbed(x0)
+    f, _ = prob.objfunc(x)
+    s, _ = prob.sens(x, f)
+    # (1) oracle on the dynamics rows of sampled sections (the oracle's leaves evaluate any row subset)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+    rng = np.random.default_rng(5)
+    ps = p["ps_params"]
+    mass, pos = x["mass"], x["position"].reshape(-1, 3)
+    vel, quat = x["velocity"].reshape(-1, 3), x["quaternion"].reshape(-1, 4)
+    units = O._units3()
+    for i in rng.choice(P.S, size=40, replace=False):
+        ua, ub, xa, xb, n = ps.get_index(i)
+        to, tf = x["t"][i], x["t"][i + 1]
+        tn = ps.time_nodes(i, to, tf)
+        lh = O._dot(ps.D(i), vel[xa:xb])
+        rhs = O._rhs_vel(i, mass[xa + 1:xb], pos[xa + 1:xb], vel[xa + 1:xb], quat[xa + 1:xb], tn[1:], units)
+        want = (lh - rhs * (tf - to) * u["t"] / 2.0).ravel()
+        assert np.array_equal(f["eqcon_dyn_vel"][3 * ua:3 * ub], want), int(i)
+    # (2) linear groups: g = J x + c, where c = g(0)
+    zero = {k: np.zeros_like(v) for k, v in x.items()}
+    f0, _ = prob.objfunc(zero)
+    for key in ("eqcon_knot", "eqcon_rate", "ineqcon_time", "ineqcon_kick", "eqcon_time"):
+        acc = np.array(f0[key], dtype=np.float64, copy=True)
+        for var, blk in s[key].items():
+            r, cidx, d = blk["coo"]
+            np.add.at(acc, r, d * x[var][cidx])
+        np.testing.assert_allclose(acc, f[key], rtol=0, atol=1e-12, err_msg=key)
+    # (3) every value finite, every slot written
+    v = prob.engine.eval_jacobian(problem.xdict_to_vector(x))
+    assert np.isfinite(v).all()
+    prob.close()
