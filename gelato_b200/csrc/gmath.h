@@ -30,8 +30,14 @@
 
 #if defined(__CUDACC__)
 #define GM_HD static __host__ __device__ inline
+/* The large elementary functions are real calls on the device: a right-hand side
+ * evaluates ~20 of them, and with every copy inlined the Jacobian kernel was 365 KB
+ * of SASS -- far beyond the SM instruction cache (ncu round 1: stall_no_instruction
+ * 8.3 per issue).  Called, each exists once. */
+#define GM_HD_CALL static __host__ __device__ __noinline__
 #else
 #define GM_HD static inline
+#define GM_HD_CALL static inline
 #endif
 
 /* ---- primitives ------------------------------------------------------- */
@@ -140,7 +146,7 @@ GM_HD double gm_kcos(double x, double y) {
   return w + (((1.0 - w) - hz) + (z * (z * p) - x * y));
 }
 
-GM_HD void gm_sincos(double x, double* s, double* c) {
+GM_HD_CALL void gm_sincos(double x, double* s, double* c) {
   uint64_t ax = gm_d2u(x) & GM_ABS_MASK;
   if (ax >= GM_INF_BITS) { /* inf or nan */
     *s = gm_nan();
@@ -173,7 +179,7 @@ GM_HD double gm_cos(double x) {
   return c;
 }
 
-GM_HD double gm_tan(double x) {
+GM_HD_CALL double gm_tan(double x) {
   uint64_t ax = gm_d2u(x) & GM_ABS_MASK;
   if (ax >= GM_INF_BITS) return gm_nan();
   double r = x, rl = 0.0;
@@ -240,7 +246,7 @@ GM_HD double gm_atan(double x) {
   return (ux & GM_SIGN_MASK) ? -res : res;
 }
 
-GM_HD double gm_atan2(double y, double x) {
+GM_HD_CALL double gm_atan2(double y, double x) {
   if (gm_isnan(x) || gm_isnan(y)) return x + y;
   uint64_t ux = gm_d2u(x), uy = gm_d2u(y);
   uint64_t ax = ux & GM_ABS_MASK, ay = uy & GM_ABS_MASK;
@@ -323,7 +329,7 @@ GM_HD double gm_scale2(double y, int k) {
 }
 
 /* exp(x + xl), |xl| << |x| */
-GM_HD double gm_exp_dd(double x, double xl) {
+GM_HD_CALL double gm_exp_dd(double x, double xl) {
   if (gm_isnan(x)) return x + x;
   if (x > 709.782712893384) return gm_inf();
   if (x < -745.2) return 0.0;
@@ -439,7 +445,7 @@ GM_HD int gm_is_odd_int(double y) {
   return !gm_is_int(h);
 }
 
-GM_HD double gm_pow(double x, double y) {
+GM_HD_CALL double gm_pow(double x, double y) {
   if (y == 0.0) return 1.0;
   if (x == 1.0) return 1.0;
   if (gm_isnan(x) || gm_isnan(y)) return x + y;

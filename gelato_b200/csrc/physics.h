@@ -24,6 +24,7 @@
 #include "gmath.h"
 
 #define P_HD GM_HD
+#define P_HD_CALL GM_HD_CALL
 
 #define P_PI 3.14159265358979323846
 #define P_MU 3.986004418e14
@@ -205,9 +206,8 @@ P_HD void us76_layer(double h, double* Hb, double* Lmb, double* Tmb, double* Pb,
   *Hb = hb; *Lmb = l; *Tmb = t; *Pb = p; *R = Rstar / m;
 }
 
-/* WANT: bit0 pressure+density, bit1 speed of sound */
-template <int WANT>
-P_HD AirState us76(double h) {
+/* want: bit0 pressure+density, bit1 speed of sound */
+P_HD AirState us76(double h, int want) {
   const double g0 = 9.80665, r0 = 6356766.0;
   double Hb, Lmb, Tmb, Pb, R;
   us76_layer(h, &Hb, &Lmb, &Tmb, &Pb, &R);
@@ -227,14 +227,14 @@ P_HD AirState us76(double h) {
   s.P = 0.0;
   s.rho = 0.0;
   s.a = 0.0;
-  if (WANT & 1) {
+  if (want & 1) {
     if (gm_fabs(Lmb) > 1.0e-6)
       s.P = Pb * gm_pow((Tmb + Lmb * (h - Hb)) / Tmb, -g0 / Lmb / R);
     else
       s.P = Pb * gm_exp(g0 / R * (Hb - h) / Tmb);
     s.rho = s.P / R / s.T;
   }
-  if (WANT & 2) s.a = gm_sqrt(1.4 * R * s.T);
+  if (want & 2) s.a = gm_sqrt(1.4 * R * s.T);
   return s;
 }
 
@@ -245,17 +245,10 @@ P_HD AirState us76(double h) {
 P_HD double interp_table(double x, const double* xp, const double* yp, int n, int stride) {
   if (x < xp[0]) return yp[0];
   if (x > xp[(n - 1) * stride]) return yp[(n - 1) * stride];
-  int lo = 0, cnt = n;
-  while (cnt > 0) {
-    int step = cnt >> 1;
-    int it = lo + step;
-    if (xp[it * stride] < x) {
-      lo = it + 1;
-      cnt -= step + 1;
-    } else {
-      cnt = step;
-    }
-  }
+  /* lower_bound over a sorted table = number of entries below x; the tables have a
+   * handful of rows, so a branch-free count beats a divergent binary search */
+  int lo = 0;
+  for (int i = 0; i < n; i++) lo += (xp[i * stride] < x) ? 1 : 0;
   int idx = lo - 1;
   if (idx < 0) idx = 0;
   double x_lower = xp[idx * stride], x_upper = xp[(idx + 1) * stride];
@@ -264,7 +257,17 @@ P_HD double interp_table(double x, const double* xp, const double* yp, int n, in
   return y_lower + alpha * (y_upper - y_lower);
 }
 
-/* ---- air-relative velocity shared by dynamics and the aero constraints ---- */
+/* ---- the air right-hand side in three parts -------------------------------
+ * The finite-difference columns of one node share most of their work: the
+ * position-only part (geodetic altitude, atmosphere, wind lookup, gravity) takes
+ * only 5 distinct inputs over the 14 columns, the position+time part (NED frame,
+ * wind in ECI axes) 7.  The kernels therefore evaluate
+ *     pos_part(pos)            once per distinct position,
+ *     rot_part(pos, t, wind)   once per distinct (position, time),
+ *     a cheap per-column remainder,
+ * with exactly the operations (and operation order) of the single-pass formulas in
+ * pybind_dynamics.cpp:42-68 / wrapper_utils.hpp:89-193, so every column's bits
+ * are what a full evaluation of that column gives. */
 struct Tables {
   const double* wind; /* [n_wind][3]: altitude, wind_n, wind_e */
   int n_wind;
@@ -272,27 +275,49 @@ struct Tables {
   int n_ca;
 };
 
-struct AirRel {
-  Vec3 va;        /* air-relative velocity, ECI axes */
-  double alt_gp;  /* geopotential altitude */
-};
+enum { PP_WIND_N = 0, PP_WIND_E, PP_RHO, PP_PRESS, PP_SOUND, PP_GX, PP_GY, PP_GZ, PP_COLS };
+enum { RP_COS = 0, RP_SIN, RP_WX, RP_WY, RP_WZ, RP_COLS };
+enum { PW_GRAVITY = 1, PW_SOUND = 2 };
 
-/* pybind_dynamics.cpp:43-53 / wrapper_utils.hpp:93-101: pos/vel dimensional, t as
- * the caller passes it (the dynamics pass NON-dimensional node times -- reference
- * quirk A.5-1 -- the aero constraints pass seconds). */
-P_HD AirRel air_relative(Vec3 pos, Vec3 vel, double t, const Tables& tb) {
-  AirRel o;
-  Geodetic g = ecef2geodetic<1>(pos); /* ECI fed to ecef2geodetic: quirk A.5-2 */
-  o.alt_gp = geopotential_altitude(g.alt);
+/* position-only part; pos dimensional (ECI fed to ecef2geodetic: quirk A.5-2).
+ * pybind_dynamics.cpp:43-46,49,55,66 / wrapper_utils.hpp:93-95,164-172 */
+P_HD_CALL void pos_part(double px, double py, double pz, const double* wind, int n_wind, int want, double* out) {
+  Vec3 pos = v3(px, py, pz);
+  Geodetic g = ecef2geodetic<1>(pos);
+  double alt_gp = geopotential_altitude(g.alt);
+  out[PP_WIND_N] = interp_table(alt_gp, wind, wind + 1, n_wind, 3);
+  out[PP_WIND_E] = interp_table(alt_gp, wind, wind + 2, n_wind, 3);
+  AirState as = us76(alt_gp, 1 | (want & PW_SOUND));
+  out[PP_RHO] = as.rho;
+  out[PP_PRESS] = as.P;
+  out[PP_SOUND] = as.a;
+  Vec3 gr = v3(0.0, 0.0, 0.0);
+  if (want & PW_GRAVITY) gr = gravity_eci(pos);
+  out[PP_GX] = gr.x;
+  out[PP_GY] = gr.y;
+  out[PP_GZ] = gr.z;
+}
+
+/* position+time part: cos/sin of the Earth-rotation angle and the wind in ECI axes.
+ * t as the caller passes it (the dynamics pass NON-dimensional node times -- quirk
+ * A.5-1 -- the aero constraints pass seconds).  pybind_dynamics.cpp:48-52 */
+P_HD_CALL void rot_part(double px, double py, double pz, double t, double wind_n, double wind_e, double* out) {
+  Vec3 pos = v3(px, py, pz);
   double wt = P_OMEGA * t;
   double s, c;
   gm_sincos(wt, &s, &c);
-  Vec3 vel_ecef = vel_eci2ecef_cs(vel, pos, c, s);
-  Vec3 wind_ned = v3(interp_table(o.alt_gp, tb.wind, tb.wind + 1, tb.n_wind, 3),
-                     interp_table(o.alt_gp, tb.wind, tb.wind + 2, tb.n_wind, 3), 0.0);
-  Vec3 wind_eci = quatrot(quat_ned2eci_cs(pos, wt, c, s), wind_ned);
-  o.va = sub3(rot_ecef2eci(vel_ecef, c, s), wind_eci);
-  return o;
+  Vec3 wind_eci = quatrot(quat_ned2eci_cs(pos, wt, c, s), v3(wind_n, wind_e, 0.0));
+  out[RP_COS] = c;
+  out[RP_SIN] = s;
+  out[RP_WX] = wind_eci.x;
+  out[RP_WY] = wind_eci.y;
+  out[RP_WZ] = wind_eci.z;
+}
+
+/* air-relative velocity in ECI axes: pybind_dynamics.cpp:47,53 */
+P_HD Vec3 air_velocity(Vec3 pos, Vec3 vel, const double* rp) {
+  Vec3 vel_ecef = vel_eci2ecef_cs(vel, pos, rp[RP_COS], rp[RP_SIN]);
+  return sub3(rot_ecef2eci(vel_ecef, rp[RP_COS], rp[RP_SIN]), v3(rp[RP_WX], rp[RP_WY], rp[RP_WZ]));
 }
 
 /* ---- dynamics right-hand sides (pybind_dynamics.cpp:30-106) -------------- */
@@ -303,35 +328,46 @@ struct Units {
   double mass, pos, vel, u, t, dx;
 };
 
-/* dynamics_velocity: acceleration / unit_vel */
-P_HD Vec3 rhs_velocity_air(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, double t, const SecParam& sp,
-                           const Units& un, const Tables& tb) {
+/* dynamics_velocity, per-column remainder: acceleration / unit_vel.  mass_e / pos_e /
+ * vel_e non-dimensional; pp = pos_part(pos_e*unit_pos), rp = rot_part(the same pos, t). */
+P_HD Vec3 rhs_velocity_air_col(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, const double* pp, const double* rp,
+                               const SecParam& sp, const Units& un, const Tables& tb) {
   double mass = mass_e * un.mass;
   Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
   Vec3 vel = v3(vel_e.x * un.vel, vel_e.y * un.vel, vel_e.z * un.vel);
-  AirRel ar = air_relative(pos, vel, t, tb);
-  AirState as = us76<3>(ar.alt_gp);
-  double vn = norm3(ar.va);
-  double mach = vn / as.a;
+  Vec3 va = air_velocity(pos, vel, rp);
+  double vn = norm3(va);
+  double mach = vn / pp[PP_SOUND];
   double ca = interp_table(mach, tb.ca, tb.ca + 1, tb.n_ca, 2);
-  double k = 0.5 * as.rho * sp.ref_area * ca * vn;
-  Vec3 aero = v3(k * -ar.va.x, k * -ar.va.y, k * -ar.va.z);
-  double thrust = sp.thrust - sp.nozzle_area * as.P;
+  double k = 0.5 * pp[PP_RHO] * sp.ref_area * ca * vn;
+  Vec3 aero = v3(k * -va.x, k * -va.y, k * -va.z);
+  double thrust = sp.thrust - sp.nozzle_area * pp[PP_PRESS];
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(thrust, tdir);
-  Vec3 g = gravity_eci(pos);
-  return v3(((thr.x + aero.x) / mass + g.x) / un.vel, ((thr.y + aero.y) / mass + g.y) / un.vel,
-            ((thr.z + aero.z) / mass + g.z) / un.vel);
+  return v3(((thr.x + aero.x) / mass + pp[PP_GX]) / un.vel, ((thr.y + aero.y) / mass + pp[PP_GY]) / un.vel,
+            ((thr.z + aero.z) / mass + pp[PP_GZ]) / un.vel);
 }
 
-/* dynamics_velocity_NoAir */
-P_HD Vec3 rhs_velocity_noair(double mass_e, Vec3 pos_e, Quat q, const SecParam& sp, const Units& un) {
+/* dynamics_velocity in one pass (residual kernel: one evaluation per node) */
+P_HD Vec3 rhs_velocity_air(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, double t, const SecParam& sp,
+                           const Units& un, const Tables& tb) {
+  double pp[PP_COLS], rp[RP_COLS];
+  double px = pos_e.x * un.pos, py = pos_e.y * un.pos, pz = pos_e.z * un.pos;
+  pos_part(px, py, pz, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND, pp);
+  rot_part(px, py, pz, t, pp[PP_WIND_N], pp[PP_WIND_E], rp);
+  return rhs_velocity_air_col(mass_e, pos_e, vel_e, q, pp, rp, sp, un, tb);
+}
+
+/* dynamics_velocity_NoAir; g = gravity_eci(pos_e*unit_pos) */
+P_HD Vec3 rhs_velocity_noair_col(double mass_e, Quat q, Vec3 g, const SecParam& sp, const Units& un) {
   double mass = mass_e * un.mass;
-  Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(sp.thrust, tdir);
-  Vec3 g = gravity_eci(pos);
   return v3((thr.x / mass + g.x) / un.vel, (thr.y / mass + g.y) / un.vel, (thr.z / mass + g.z) / un.vel);
+}
+P_HD Vec3 rhs_velocity_noair(double mass_e, Vec3 pos_e, Quat q, const SecParam& sp, const Units& un) {
+  Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
+  return rhs_velocity_noair_col(mass_e, q, gravity_eci(pos), sp, un);
 }
 
 /* dynamics_quaternion: 0.5 * q (x) (0, 0, u0, u1) * pi/180 */
@@ -344,26 +380,29 @@ P_HD Quat rhs_quaternion(Quat q, double u0_e, double u1_e, double unit_u) {
 
 /* ---- aero constraint leaves (wrapper_utils.hpp:89-111,163-193) ----------- */
 /* kind: 0 angle of attack [rad], 1 dynamic pressure [Pa], 2 q*alpha [Pa rad].
- * pos/vel dimensional, t in seconds. */
-P_HD double aero_quantity(int kind, Vec3 pos, Vec3 vel, Quat q, double t, const Tables& tb) {
-  AirRel ar = air_relative(pos, vel, t, tb);
+ * pos / vel dimensional; pp / rp from pos_part / rot_part of the same position (t in seconds). */
+P_HD double aero_quantity_col(int kind, Vec3 pos, Vec3 vel, Quat q, const double* pp, const double* rp) {
+  Vec3 va = air_velocity(pos, vel, rp);
   double alpha = 0.0, dynp = 0.0;
   if (kind != 1) {
     Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
-    Vec3 a = div3(ar.va, norm3(ar.va)); /* normalize(): v / v.norm() */
+    Vec3 a = div3(va, norm3(va)); /* normalize(): v / v.norm() */
     Vec3 b = div3(tdir, norm3(tdir));
     double c_alpha = dot3(a, b);
     if (c_alpha > 1.0) alpha = 0.0;
-    else if (norm3(ar.va) < 1e-6) alpha = 0.0;
+    else if (norm3(va) < 1e-6) alpha = 0.0;
     else alpha = gm_acos(c_alpha);
   }
-  if (kind != 0) {
-    AirState as = us76<1>(ar.alt_gp);
-    dynp = 0.5 * as.rho * norm3(ar.va) * norm3(ar.va);
-  }
+  if (kind != 0) dynp = 0.5 * pp[PP_RHO] * norm3(va) * norm3(va);
   if (kind == 0) return alpha;
   if (kind == 1) return dynp;
   return dynp * alpha;
+}
+P_HD double aero_quantity(int kind, Vec3 pos, Vec3 vel, Quat q, double t, const Tables& tb) {
+  double pp[PP_COLS], rp[RP_COLS];
+  pos_part(pos.x, pos.y, pos.z, tb.wind, tb.n_wind, 0, pp);
+  rot_part(pos.x, pos.y, pos.z, t, pp[PP_WIND_N], pp[PP_WIND_E], rp);
+  return aero_quantity_col(kind, pos, vel, q, pp, rp);
 }
 
 /* ---- event-point leaves --------------------------------------------------- */

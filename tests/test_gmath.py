@@ -1,0 +1,84 @@
+"""gmath.h (the deterministic FP64 elementary functions shared by the CUDA
+kernels and the gmath flavour of the oracle) against mpmath at 50 digits.
+Accuracy target: within 2 ulp (the reference's glibc is < 1 ulp; the parity
+budget of DESIGN.md H1 is written for <= 2 ulp)."""
+import ctypes
+import os
+import subprocess
+
+import mpmath
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libgmath_shim.so")
+_pd = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    src = os.path.join(HERE, "gmath_host_shim.c")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", LIB, src, "-lm"])
+    return ctypes.CDLL(LIB)
+
+
+def _ulps(got, want_mp):
+    out = []
+    for g, w in zip(got, want_mp):
+        wf = float(w)
+        ulp = np.spacing(abs(wf)) if wf != 0 else 5e-324
+        out.append(abs(mpmath.mpf(float(g)) - w) / mpmath.mpf(float(ulp)))
+    return float(max(out))
+
+
+def _call1(L, name, x):
+    y = np.empty_like(x)
+    getattr(L, name)(x.ctypes.data_as(_pd), y.ctypes.data_as(_pd), x.size)
+    return y
+
+
+def _call2(L, name, a, b):
+    y = np.empty_like(a)
+    getattr(L, name)(a.ctypes.data_as(_pd), b.ctypes.data_as(_pd), y.ctypes.data_as(_pd), a.size)
+    return y
+
+
+CASES1 = [
+    ("gmt_sin", mpmath.sin, (-7.0, 7.0)), ("gmt_cos", mpmath.cos, (-7.0, 7.0)), ("gmt_sin", mpmath.sin, (-1e-3, 1e-3)),
+    ("gmt_cos", mpmath.cos, (-0.05, 0.05)), ("gmt_tan", mpmath.tan, (-1.5, 1.5)), ("gmt_atan", mpmath.atan, (-50.0, 50.0)),
+    ("gmt_asin", mpmath.asin, (-1.0, 1.0)), ("gmt_acos", mpmath.acos, (-1.0, 1.0)), ("gmt_exp", mpmath.exp, (-30.0, 5.0)),
+    ("gmt_log", mpmath.log, (1e-6, 1e6)),
+]
+
+
+@pytest.mark.parametrize("name,ref,rng_", CASES1)
+def test_unary_accuracy(shim, name, ref, rng_):
+    mpmath.mp.dps = 50
+    rng = np.random.default_rng(abs(hash(name)) % 2**32)
+    x = rng.uniform(rng_[0], rng_[1], 1500)
+    y = _call1(shim, name, x)
+    assert _ulps(y, [ref(mpmath.mpf(float(v))) for v in x]) <= 2.0
+
+
+def test_atan2_and_pow_accuracy(shim):
+    mpmath.mp.dps = 50
+    rng = np.random.default_rng(11)
+    a, b = rng.uniform(-7e6, 7e6, 1500), rng.uniform(-7e6, 7e6, 1500)
+    y = _call2(shim, "gmt_atan2", a, b)
+    assert _ulps(y, [mpmath.atan2(mpmath.mpf(float(p)), mpmath.mpf(float(q))) for p, q in zip(a, b)]) <= 2.0
+    # the US-76 pressure law: base in (0.7, 1.3), exponent up to +-35 (Air.cpp:92-96)
+    base, ex = rng.uniform(0.7, 1.3, 1500), rng.uniform(-35.0, 35.0, 1500)
+    y = _call2(shim, "gmt_pow", base, ex)
+    assert _ulps(y, [mpmath.power(mpmath.mpf(float(p)), mpmath.mpf(float(q))) for p, q in zip(base, ex)]) <= 2.0
+
+
+def test_special_values(shim):
+    x = np.array([0.0, -0.0, 1.0, -1.0])
+    assert np.array_equal(_call1(shim, "gmt_sin", x[:2]), x[:2])
+    assert _call1(shim, "gmt_cos", x[:1])[0] == 1.0
+    assert _call1(shim, "gmt_acos", x[2:3])[0] == 0.0
+    assert abs(_call1(shim, "gmt_acos", x[3:4])[0] - np.pi) < 1e-15
+    assert _call2(shim, "gmt_atan2", np.array([0.0]), np.array([1.0]))[0] == 0.0
+    assert abs(_call2(shim, "gmt_atan2", np.array([1.0]), np.array([0.0]))[0] - np.pi / 2) < 1e-15
+    assert _call1(shim, "gmt_exp", x[:1])[0] == 1.0
