@@ -216,7 +216,12 @@ def run_gelato(args):
     E = engine.Engine(P, device=local, scenario_plans=plans)
     ec = P.eval_counts()
     evals_step_rank = (ec["objfunc"] + ec["sens"]) * B
-    st = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the C ABI reads stream 0 as "the plan's own stream", and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    st = tstream.cuda_stream
+    assert st != 0
 
     xd = torch.from_numpy(X).cuda()
     gd = torch.empty((B, P.n_rows), dtype=torch.float64, device="cuda")

@@ -13,7 +13,9 @@ What it writes
                         objfunc / sens bodies of Trajectory_Optimization.py, imported where
                         they lie) running on the oracle's libm physics leaves, because the
                         reference's pybind11/Eigen modules cannot be built here
-                        (/root/reference/CMakeLists.txt:13, no Eigen3).
+                        (/root/reference/CMakeLists.txt:13, no Eigen3).  Also `jn/...`: per Jacobian
+                        slot, how far the reference's own value moves when every input is nudged
+                        by one ulp (8 random draws) -- its finite-difference noise floor.
   example_gmath.npz     the same quantities from oracle/nlp.py with the gmath leaves and
                         sequential-FMA D.X -- the flavour the CUDA kernels must match
                         bit for bit on any machine.
@@ -33,6 +35,9 @@ import helpers  # noqa: E402
 import refharness  # noqa: E402
 from gelato_b200 import problem  # noqa: E402
 from oracle import leaves  # noqa: E402
+
+
+NOISE_DRAWS = 8
 
 
 def pack(prefix, f, s, out):
@@ -67,6 +72,19 @@ def main():
         assert fail is False
         s, fail = sens(xa, f)
         pack(name, f, s, out)
+        # FD noise floor of the reference itself: its Jacobian re-evaluated with every input moved
+        # by one ulp in a random direction; per slot, the largest change over the draws
+        base = helpers.flatten_sens(s)
+        noise = {k: np.zeros_like(v[2], dtype=np.float64) for k, v in base.items()}
+        rng = np.random.default_rng(11)
+        for _ in range(NOISE_DRAWS):
+            xn = {k: np.nextafter(v, np.where(rng.random(v.shape) < 0.5, -np.inf, np.inf)) for k, v in x.items()}
+            fn, _ = objfunc(xn)
+            sn, _ = sens(xn, fn)
+            for k, v in helpers.flatten_sens(sn).items():
+                noise[k] = np.maximum(noise[k], np.abs(v[2] - base[k][2]))
+        for k, v in noise.items():
+            out["%s/jn/%s" % (name, k)] = v
     np.savez_compressed(os.path.join(HERE, "example_reference.npz"), **out)
 
     # ---- gmath / sequential-FMA flavour of the oracle ---------------------

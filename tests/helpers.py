@@ -111,6 +111,22 @@ def assert_sens_equal(sa, sb):
                 assert np.array_equal(av, bv), (k, var, float(np.max(np.abs(np.asarray(av) - np.asarray(bv)))))
 
 
+def assert_sens_within_noise(s, npz, name, floor_factor=2.0):
+    """funcsSens `s` against the reference fixture: identical sparsity; values within
+    1e-10 relative + floor_factor x the block's finite-difference noise floor
+    (`jn` arrays of tests/golden/example_reference.npz)."""
+    for k, (r, c, d, shape) in flatten_sens(s).items():
+        ref = npz["%s/j/%s/data" % (name, k)]
+        if r is not None:
+            assert r.dtype == np.int32 and c.dtype == np.int32, k
+            assert np.array_equal(r, npz["%s/j/%s/rows" % (name, k)]), k
+            assert np.array_equal(c, npz["%s/j/%s/cols" % (name, k)]), k
+        assert tuple(shape) == tuple(npz["%s/j/%s/shape" % (name, k)].tolist()), k
+        jn = npz["%s/jn/%s" % (name, k)]
+        floor = floor_factor * float(jn.max()) if jn.size else 0.0
+        np.testing.assert_allclose(d, ref, rtol=1e-10, atol=floor, err_msg=k)
+
+
 def variant_inputs(name):
     """Problem variants exercising the constraint branches the shipped example leaves cold."""
     inp = copy.deepcopy(example_inputs())

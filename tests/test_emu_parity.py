@@ -123,3 +123,25 @@ def test_batched_scenarios_match_per_scenario_oracle():
         s, _ = oracles[k].sens(xa)
         helpers.assert_sens_equal(s, plans[k].split_jacobian(V[k], key_order=list(xs[k].keys())))
     assert not np.array_equal(G[0], G[1])
+
+
+@pytest.mark.parametrize("name", ["x0", "x1"])
+def test_emulated_kernels_match_reference_golden_within_fd_noise(name):
+    """The kernels' code (stepped on the host) against the fixture made by the
+    reference's own Python layer on libm leaves: same sparsity, values within 1e-10
+    relative + the reference's own finite-difference noise floor.  The same check runs
+    on the GPU (test_gpu_parity.py)."""
+    import os
+
+    npz = np.load(os.path.join(helpers.GOLDEN, "example_reference.npz"))
+    p, u, c, x0 = helpers.example_problem()
+    P = helpers.compiled_plan(p, u, c)
+    E = emu_binding.Emulator(P)
+    xv = npz["%s/x" % name].copy()
+    x = problem.vector_to_xdict(xv, P.M, P.N, P.S)
+    f = P.split_residuals(E.eval_residuals(xv))
+    for k, v in helpers.flatten_funcs(f).items():
+        atol = 1e-11 if "alpha" in k else 1e-13
+        np.testing.assert_allclose(v, npz["%s/f/%s" % (name, k)], rtol=1e-10, atol=atol, err_msg=k)
+    s = P.split_jacobian(E.eval_jacobian(xv), key_order=list(x.keys()))
+    helpers.assert_sens_within_noise(s, npz, name)
