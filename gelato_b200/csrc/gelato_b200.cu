@@ -23,30 +23,37 @@
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GB_THREADS)
+__global__ void __launch_bounds__(GJ_THREADS, 2)
 k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
            double* __restrict__ vals_all) {
-  __shared__ BlockScratch sm;
+  __shared__ JacScratch sm;
   const int scen = blockIdx.y;
   const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* vals = vals_all + (size_t)scen * P.n_vals;
-  jac_block_phase1(P, scen, bt, x, threadIdx.x, sm);
+  const bool two_phase = jac_role_two_phase(bt[BT_ROLE]);
+  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 0, sm);
   __syncthreads();
-  jac_block_phase2(P, scen, bt, x, vals, threadIdx.x, sm);
+  if (!two_phase) {
+    jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 1, sm);
+    __syncthreads();
+    jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 2, sm);
+    __syncthreads();
+  }
+  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
 }
 
-__global__ void __launch_bounds__(GB_THREADS)
+__global__ void __launch_bounds__(GR_THREADS)
 k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
             double* __restrict__ g_all) {
-  __shared__ BlockScratch sm;
+  __shared__ ResScratch sm;
   const int scen = blockIdx.y;
   const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* g = g_all + (size_t)scen * P.n_rows;
   res_block_phase1(P, scen, bt, x, g, threadIdx.x, sm);
   __syncthreads();
-  res_block_phase2(P, scen, bt, x, g, threadIdx.x, GB_THREADS, sm);
+  res_block_phase2(P, scen, bt, x, g, threadIdx.x, GR_THREADS, sm);
 }
 
 // probe: is a*b+c left unfused?  (1 + 2^-30)(1 - 2^-30) - 1 is 0 unfused, -2^-60 fused
@@ -170,15 +177,19 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
 #undef UP
 
   // block tables
-  std::vector<int32_t> jb, rb;
-  build_block_tables(d, jb, rb);
-  p->n_jac_blocks = (int)(jb.size() / BT_COLS);
-  p->n_res_blocks = (int)(rb.size() / BT_COLS);
+  HostTables ht;
+  build_host_tables(d, ht);
+  p->n_jac_blocks = (int)(ht.jac_blocks.size() / BT_COLS);
+  p->n_res_blocks = (int)(ht.res_blocks.size() / BT_COLS);
   const int32_t* tb = nullptr;
-  if ((rc = upload(p, jb.data(), jb.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.jac_blocks.data(), ht.jac_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->jac_blocks = const_cast<int32_t*>(tb);
-  if ((rc = upload(p, rb.data(), rb.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.res_blocks.data(), ht.res_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->res_blocks = const_cast<int32_t*>(tb);
+  if ((rc = upload(p, ht.node_sec.data(), ht.node_sec.size(), &v.node_sec)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.jac_nodes.data(), ht.jac_nodes.size(), &v.jac_nodes)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.aero_rows.data(), ht.aero_rows.size(), &v.aero_rows)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  v.n_aero_rows = (int)ht.aero_rows.size() / 2;
 
   CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&p->ev0));
@@ -258,7 +269,7 @@ int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev,
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   dim3 grid(p->n_res_blocks, n_scen);
-  k_residuals<<<grid, GB_THREADS, 0, st>>>(p->view, p->res_blocks, x_dev, g_dev);
+  k_residuals<<<grid, GR_THREADS, 0, st>>>(p->view, p->res_blocks, x_dev, g_dev);
   p->launches++;
   CU(cudaGetLastError());
   return GELATO_OK;
@@ -288,7 +299,7 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
   // the kernel rewrites every x-dependent slot and never touches the rest
   dim3 grid(p->n_jac_blocks, n_scen);
-  k_jacobian<<<grid, GB_THREADS, 0, st>>>(p->view, p->jac_blocks, x_dev, vals_dev);
+  k_jacobian<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, x_dev, vals_dev);
   p->launches++;
   CU(cudaGetLastError());
   return GELATO_OK;
@@ -389,10 +400,10 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
   for (int i = 0; i < reps; i++) {
     if (which == 0) {
       dim3 grid(p->n_res_blocks, n_scen);
-      k_residuals<<<grid, GB_THREADS, 0, p->stream>>>(p->view, p->res_blocks, x_dev, out_dev);
+      k_residuals<<<grid, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, x_dev, out_dev);
     } else {
       dim3 grid(p->n_jac_blocks, n_scen);
-      k_jacobian<<<grid, GB_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, x_dev, out_dev);
+      k_jacobian<<<grid, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, x_dev, out_dev);
     }
     p->launches++;
   }

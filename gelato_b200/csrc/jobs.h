@@ -22,15 +22,26 @@
 #include "../../include/gelato_b200.h"
 #include "physics.h"
 
-#define GB_THREADS 128
-#define GB_DYN_JAC_NODES 8   /* 16 lanes per node */
-#define GB_DYN_RES_NODES 32  /* warp 0 = one thread per node */
-#define GB_ROWS16 8          /* 16-lane jobs per block (aero / event Jacobian) */
+/* ---- launch geometry ------------------------------------------------------ */
+#define GJ_THREADS 256 /* Jacobian kernel block */
+#define GR_THREADS 128 /* residual kernel block */
+#define GJ_NODES 18    /* air nodes (or aero rows) per Jacobian block */
+#define GN_NODES 28    /* no-air nodes per Jacobian block */
+#define GG_NODES 8     /* nodes per block of the one-lane-per-column fallback */
+#define GJ_EVT 16      /* event jobs per Jacobian block (16 lanes each) */
+#define GR_NODES 64    /* nodes per residual block */
+#define NPV 5          /* distinct positions over the columns of one node */
+#define NRV 7          /* distinct (position, time) pairs */
+#define GJ_A_THREADS 96  /* threads [0, 96): position items (>= GJ_NODES*NPV, whole warps) */
+#define GJ_B_THREADS 128 /* threads [96, 224): rotation items (>= GJ_NODES*NRV) */
+#define GJ_Q_BASE 224    /* threads [224, 256): quaternion kinematics, one node each */
+#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
 
 /* block roles */
-enum { BR_DYN = 0, BR_AERO = 1, BR_EVT = 2, BR_LIN = 3 };
+enum { BR_DYN_AIR = 0, BR_DYN_NOAIR, BR_DYN_GEN, BR_AERO, BR_EVT, BR_LIN, BR_DYN /* residual kernel */ };
 /* block table columns */
 enum { BT_ROLE = 0, BT_JOB, BT_START, BT_COUNT, BT_COLS };
+#define GJ_PHASES 4
 
 struct PlanView {
   int S, N, M, n_vars, n_rows;
@@ -63,12 +74,25 @@ struct PlanView {
   const int32_t* evt_i32;
   const int64_t* evt_i64;
   const double* evt_f64;
+  /* built by plan_host.h at plan creation */
+  const int32_t* node_sec;  /* [N] section of collocation node g (natural order) */
+  const int32_t* jac_nodes; /* [N] node ids grouped by Jacobian block role */
+  const int32_t* aero_rows; /* [n_aero_rows][2] (aero job, row inside the job) */
+  int n_aero_rows;
 };
 
-/* scratch shared by the threads of one block */
-struct BlockScratch {
-  double f[GB_THREADS][4];
-  double q[GB_THREADS][4];
+/* shared memory of one Jacobian block (30.5 KB) */
+struct JacScratch {
+  double pp[GJ_NODES * NPV * PP_COLS]; /* pos_part per (node, position variant); no-air: gravity[3] */
+  double rq[GJ_NODES * NRV * RQ_COLS]; /* rotq_part per (node, rotation variant) */
+  double rp[GJ_NODES * NRV * RP_COLS]; /* rot_wind of the same */
+  double f[GN_NODES * 14 * 3];         /* leaf value per (node, column lane); events: per thread */
+  double q[GN_NODES * 7 * 4];          /* quaternion kinematics per (node, variant) */
+};
+/* shared memory of one residual block */
+struct ResScratch {
+  double f[GR_NODES][3];
+  double q[GR_NODES][4];
 };
 
 /* fl(fl(x + dx) - dx): what a perturb/restore cycle leaves behind */
@@ -111,108 +135,114 @@ P_HD double time_node(const double* tau, int r, double to, double tf) {
 }
 
 /* ========================================================================= */
-/* Jacobian kernel, DYN role: 16 lanes per node                              */
-/*   lane 0 centre | 1 mass | 2-4 position | 5-7 velocity | 8-11 quaternion | */
-/*   12 to | 13 tf | 14 dyn_pos entries | 15 idle                             */
-/*   lanes 0-6 also evaluate the quaternion kinematics (centre, q x4, u x2)   */
+/* Dynamics: what each finite-difference column of a node sees                */
+/*   column lanes: 0 centre | 1 mass | 2-4 position | 5-7 velocity |          */
+/*                 8-11 quaternion | 12 to | 13 tf | 14 dyn_pos entries       */
+/*   lanes 0-6 also name the quaternion-kinematics variants (centre, q x4,    */
+/*   u x2)                                                                    */
 /* reference: con_dynamics.py:292-496 (velocity), :536-632 (quaternion),      */
 /*            :155-213 (position)                                             */
 /* ========================================================================= */
-P_HD void dyn_jac_phase1(const PlanView& P, int scen, const double* x, int sec, int node0, int count, int tid,
-                         BlockScratch& sm) {
-  const int nl = tid >> 4, lane = tid & 15;
-  if (nl >= count) return;
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
-  const int n = si[GS_N], ua = si[GS_UA], xa = si[GS_XA], flags = si[GS_FLAGS];
-  const int j = node0 + nl;   /* LGR node index inside the section */
-  const int row = xa + 1 + j; /* state row */
-  const Units un = scen_units(P, scen);
-  const double dx = un.dx;
-  const bool air = flags & GSF_AIR, air_fd = flags & GSF_AIR_FD, hold = flags & GSF_HOLD;
-  (void)n;
+struct NodeRef {
+  int sec, j, row, ua, n, flags;
+  const int32_t* si;
+};
+P_HD NodeRef node_ref(const PlanView& P, int g) {
+  NodeRef r;
+  r.sec = P.node_sec[g];
+  r.si = P.sec_i32 + r.sec * GS_I32_COLS;
+  r.ua = r.si[GS_UA];
+  r.n = r.si[GS_N];
+  r.flags = r.si[GS_FLAGS];
+  r.j = g - r.ua;                 /* LGR node index inside the section */
+  r.row = r.si[GS_XA] + 1 + r.j;  /* state row */
+  return r;
+}
 
-  /* velocity dynamics */
-  bool active = (lane <= 4) || (lane >= 8 && lane <= 11) || ((lane >= 5 && lane <= 7) && air_fd) ||
-                ((lane == 12 || lane == 13) && air_fd);
-  if (active) {
-    double v[11]; /* mass, pos[3], vel[3], quat[4] */
-    v[0] = x[row];
-    for (int k = 0; k < 3; k++) v[1 + k] = x[P.off_pos + 3 * row + k];
-    for (int k = 0; k < 3; k++) v[4 + k] = x[P.off_vel + 3 * row + k];
-    for (int k = 0; k < 4; k++) v[7 + k] = x[P.off_quat + 4 * row + k];
-    if (lane != 0) {
-      const int pidx = (lane <= 11) ? lane - 1 : 11;
+/* mass, pos[3], vel[3], quat[4] of state row `row` as column `lane` evaluates them: the
+ * reference perturbs views of xdict in place, so variables visited before this column
+ * carry fl(fl(x+dx)-dx) and the column's own variable carries x+dx */
+P_HD void dyn_col_state(const PlanView& P, const double* x, int row, int lane, bool air_fd, double dx, double* v) {
+  v[0] = x[row];
+  for (int k = 0; k < 3; k++) v[1 + k] = x[P.off_pos + 3 * row + k];
+  for (int k = 0; k < 3; k++) v[4 + k] = x[P.off_vel + 3 * row + k];
+  for (int k = 0; k < 4; k++) v[7 + k] = x[P.off_quat + 4 * row + k];
+  if (lane == 0) return;
+  const int pidx = (lane <= 11) ? lane - 1 : 11;
 #pragma unroll
-      for (int w = 0; w < 11; w++) {
-        const bool in_protocol = (w < 4) || (w >= 7) || air_fd;
-        if (!in_protocol) continue;
-        if (w < pidx) v[w] = residue(v[w], dx);
-        else if (w == pidx) v[w] = v[w] + dx;
-      }
-    }
-    const double to0 = x[P.off_t + sec], tf0 = x[P.off_t + sec + 1];
-    const double to = (lane == 12) ? to0 + dx : to0;
-    const double tf = (lane == 13) ? tf0 + dx : tf0;
-    const SecParam sp = sec_param(P, scen, sec);
-    Vec3 f;
-    Quat q = q4(v[7], v[8], v[9], v[10]);
-    if (air) {
-      const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], j + 1, to, tf);
-      f = rhs_velocity_air(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q, tn, sp, un, scen_tables(P, scen));
-    } else {
-      f = rhs_velocity_noair(v[0], v3(v[1], v[2], v[3]), q, sp, un);
-    }
-    sm.f[tid][0] = f.x;
-    sm.f[tid][1] = f.y;
-    sm.f[tid][2] = f.z;
+  for (int w = 0; w < 11; w++) {
+    const bool in_protocol = (w < 4) || (w >= 7) || air_fd; /* velocity columns exist for air sections only */
+    if (!in_protocol) continue;
+    if (w < pidx) v[w] = residue(v[w], dx);
+    else if (w == pidx) v[w] = v[w] + dx;
   }
+}
 
-  /* quaternion kinematics: state already carries one residue from the velocity pass */
-  if (!hold && lane <= 6) {
-    double qv[4], uv[2];
-    for (int k = 0; k < 4; k++) qv[k] = residue(x[P.off_quat + 4 * row + k], dx);
-    for (int k = 0; k < 2; k++) uv[k] = x[P.off_u + 2 * (ua + j) + k];
-    if (lane >= 1 && lane <= 4) {
-      const int k = lane - 1;
+/* The 14 columns see only NPV = 5 distinct positions and NRV = 7 distinct (position,
+ * node time) pairs:
+ *   pv 0 pristine (lanes 0,1) | 1-3 axis pv-1 perturbed (lanes 2-4) | 4 all restored (lanes 5-13)
+ *   rv 0-4 = pv 0-4 at the nominal node time | 5 = pv 4, to+dx (lane 12) | 6 = pv 4, tf+dx (lane 13) */
+P_HD int lane_pv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : 4); }
+P_HD int lane_rv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : (lane <= 11 ? 4 : lane - 7)); }
+P_HD int rv_pv(int rv) { return rv < 4 ? rv : 4; }
+
+/* non-dimensional position variant pv of a base position b[3] */
+P_HD void pos_variant(const double* b, int pv, double dx, double* out) {
+  for (int k = 0; k < 3; k++) {
+    double p = b[k];
+    if (pv == 4 || (pv >= 1 && k < pv - 1)) p = residue(p, dx);
+    else if (pv >= 1 && k == pv - 1) p = p + dx;
+    out[k] = p;
+  }
+}
+
+/* quaternion kinematics (con_dynamics.py:580-613): the state already carries one residue from
+ * the velocity pass; variants 0 centre | 1-4 quaternion component | 5-6 control */
+P_HD void dyn_quat_variants(const PlanView& P, const double* x, const NodeRef& nr, const Units& un, double* out) {
+  const double dx = un.dx;
+  double q0[4], u0[2];
+  for (int k = 0; k < 4; k++) q0[k] = residue(x[P.off_quat + 4 * nr.row + k], dx);
+  for (int k = 0; k < 2; k++) u0[k] = x[P.off_u + 2 * (nr.ua + nr.j) + k];
+  for (int var = 0; var < 7; var++) {
+    double qv[4] = {q0[0], q0[1], q0[2], q0[3]}, uv[2] = {u0[0], u0[1]};
+    if (var >= 1 && var <= 4) {
+      const int k = var - 1;
       for (int w = 0; w < k; w++) qv[w] = residue(qv[w], dx);
       qv[k] = qv[k] + dx;
-    } else if (lane >= 5) {
-      const int k = lane - 5;
+    } else if (var >= 5) {
+      const int k = var - 5;
       for (int w = 0; w < 4; w++) qv[w] = residue(qv[w], dx);
       for (int w = 0; w < k; w++) uv[w] = residue(uv[w], dx);
       uv[k] = uv[k] + dx;
     }
     Quat d = rhs_quaternion(q4(qv[0], qv[1], qv[2], qv[3]), uv[0], uv[1], un.u);
-    sm.q[tid][0] = d.w;
-    sm.q[tid][1] = d.x;
-    sm.q[tid][2] = d.y;
-    sm.q[tid][3] = d.z;
+    out[4 * var + 0] = d.w;
+    out[4 * var + 1] = d.x;
+    out[4 * var + 2] = d.y;
+    out[4 * var + 3] = d.z;
   }
 }
 
-P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* vals, int sec, int node0, int count,
-                         int tid, const BlockScratch& sm) {
-  const int nl = tid >> 4, lane = tid & 15;
-  if (nl >= count) return;
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
-  const int64_t* sj = P.sec_i64 + sec * GS_I64_COLS;
-  const int n = si[GS_N], xa = si[GS_XA], flags = si[GS_FLAGS];
-  const int j = node0 + nl;
-  const int row = xa + 1 + j;
+/* finite-difference quotients of one (node, lane) and their COO slots.
+ * fc / fl: velocity right-hand side at the centre / in this lane; qc / ql: quaternion
+ * kinematics at the centre / in variant `lane`. */
+P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals, const NodeRef& nr, int lane,
+                      const double* fc, const double* fl, const double* qc, const double* ql) {
+  const int64_t* sj = P.sec_i64 + nr.sec * GS_I64_COLS;
+  const int n = nr.n, j = nr.j, row = nr.row;
   const Units un = scen_units(P, scen);
   const double dx = un.dx, ut = un.t;
-  const bool air_fd = flags & GSF_AIR_FD, hold = flags & GSF_HOLD;
-  const double to = x[P.off_t + sec], tf = x[P.off_t + sec + 1];
+  const bool air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
+  const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double dt = tf - to;
-  const int c = tid & ~15; /* centre lane of this node */
-  const double* D = P.d_pool + si[GS_D_OFF];
+  const double* D = P.d_pool + nr.si[GS_D_OFF];
   const double d_diag = D[(long long)j * (n + 1) + (j + 1)];
   const long long n3 = 3LL * n, n4 = 4LL * n, nn1 = (long long)n * (n + 1);
 
   /* ---- velocity dynamics: -(f_p - f_c)/dx*(tf-to)*unit_t/2 (con_dynamics.py:372) ---- */
   if (lane >= 1 && lane <= 11 && !(lane >= 5 && lane <= 7 && !air_fd)) {
     double rh[3];
-    for (int k = 0; k < 3; k++) rh[k] = -(sm.f[tid][k] - sm.f[c][k]) / dx * dt * ut / 2.0;
+    for (int k = 0; k < 3; k++) rh[k] = -(fl[k] - fc[k]) / dx * dt * ut / 2.0;
     if (lane == 1) {
       for (int k = 0; k < 3; k++) vals[sj[GS_JV_MASS] + 3LL * j + k] = rh[k];
     } else if (lane <= 4) {
@@ -233,10 +263,10 @@ P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* v
     if (air_fd) { /* :454-465 */
       const double to_p = to + dx;
       for (int k = 0; k < 3; k++)
-        vals[sj[GS_JV_T] + 3LL * j + k] = -(sm.f[tid][k] * (tf - to_p) - sm.f[c][k] * dt) / dx * ut / 2.0;
+        vals[sj[GS_JV_T] + 3LL * j + k] = -(fl[k] * (tf - to_p) - fc[k] * dt) / dx * ut / 2.0;
     } else { /* :478-480 */
       for (int k = 0; k < 3; k++) {
-        const double rh_to = sm.f[c][k] * ut / 2.0;
+        const double rh_to = fc[k] * ut / 2.0;
         vals[sj[GS_JV_T] + 3LL * j + k] = rh_to;
         vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -rh_to;
       }
@@ -245,7 +275,7 @@ P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* v
   if (lane == 13 && air_fd) { /* :466-477 */
     const double tf_p = tf + dx;
     for (int k = 0; k < 3; k++)
-      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -(sm.f[tid][k] * (tf_p - to) - sm.f[c][k] * dt) / dx * ut / 2.0;
+      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -(fl[k] * (tf_p - to) - fc[k] * dt) / dx * ut / 2.0;
   }
   /* ---- position dynamics (analytic, depends on x through vel and t): :180-195 ---- */
   if (lane == 14) {
@@ -261,7 +291,7 @@ P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* v
   if (!hold) {
     if (lane >= 1 && lane <= 6) {
       double rh[4];
-      for (int a = 0; a < 4; a++) rh[a] = -(sm.q[tid][a] - sm.q[c][a]) / dx * dt * ut / 2.0;
+      for (int a = 0; a < 4; a++) rh[a] = -(ql[a] - qc[a]) / dx * dt * ut / 2.0;
       if (lane <= 4) {
         const int kk = lane - 1; /* submat_quat[4j+a, 4(j+1)+kk] += rh[a] */
         for (int a = 0; a < 4; a++) {
@@ -274,7 +304,7 @@ P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* v
       }
     } else if (lane == 0) {
       for (int a = 0; a < 4; a++) {
-        const double rh_to = sm.q[c][a] * ut / 2.0;
+        const double rh_to = qc[a] * ut / 2.0;
         vals[sj[GS_JQ_T] + 4LL * j + a] = rh_to;
         vals[sj[GS_JQ_T] + n4 + 4LL * j + a] = -rh_to;
       }
@@ -282,29 +312,197 @@ P_HD void dyn_jac_phase2(const PlanView& P, int scen, const double* x, double* v
   }
 }
 
+/* all 16 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*7 + var)*4] */
+P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+                            int nthreads, const JacScratch& sm) {
+  for (int item = tid; item < count * 16; item += nthreads) {
+    const int nl = item >> 4, lane = item & 15;
+    if (lane == 15) continue;
+    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    const double* fc = sm.f + (nl * 14) * 3;
+    const double* qc = sm.q + (nl * 7) * 4;
+    dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
+  }
+}
+
 /* ========================================================================= */
-/* Residual kernel, DYN role: up to 32 nodes of one section per block.        */
-/*   phase 1: threads 0..count-1 evaluate the right-hand sides of their node  */
+/* Jacobian kernel, DYN_AIR role: GJ_NODES air nodes per block, four phases   */
+/*   0  position items (node, pv) -> pos_part | rotation items (node, rv) ->  */
+/*      rotq_part | one thread per node: the 7 quaternion-kinematics variants */
+/*   1  rotation items: wind of (node, pv) into ECI axes                      */
+/*   2  column items (node, lane 0-13): the per-column remainder              */
+/*   3  finite-difference quotients -> COO slots                              */
+/* ========================================================================= */
+P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+                        int phase, JacScratch& sm) {
+  const Units un = scen_units(P, scen);
+  const double dx = un.dx;
+  if (phase == 0) {
+    if (tid < GJ_A_THREADS) {
+      if (tid >= count * NPV) return;
+      const int nl = tid / NPV, pv = tid - nl * NPV;
+      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      double p[3];
+      pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+      const Tables tb = scen_tables(P, scen);
+      pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
+               sm.pp + (nl * NPV + pv) * PP_COLS);
+    } else if (tid < GJ_A_THREADS + GJ_B_THREADS) {
+      const int item = tid - GJ_A_THREADS;
+      if (item >= count * NRV) return;
+      const int nl = item / NRV, rv = item - nl * NRV;
+      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      double p[3];
+      pos_variant(x + P.off_pos + 3 * nr.row, rv_pv(rv), dx, p);
+      const double to0 = x[P.off_t + nr.sec], tf0 = x[P.off_t + nr.sec + 1];
+      const double to = (rv == 5) ? to0 + dx : to0;
+      const double tf = (rv == 6) ? tf0 + dx : tf0;
+      const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
+      rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
+    } else {
+      const int nl = tid - GJ_Q_BASE;
+      if (nl < 0 || nl >= count) return;
+      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
+    }
+  } else if (phase == 1) {
+    if (tid >= count * NRV) return;
+    const int nl = tid / NRV, rv = tid - nl * NRV;
+    const double* pp = sm.pp + (nl * NPV + rv_pv(rv)) * PP_COLS;
+    rot_wind(sm.rq + (nl * NRV + rv) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], sm.rp + (nl * NRV + rv) * RP_COLS);
+  } else if (phase == 2) {
+    if (tid >= count * 14) return;
+    const int nl = tid / 14, lane = tid - nl * 14;
+    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    double v[11];
+    dyn_col_state(P, x, nr.row, lane, true, dx, v);
+    const Vec3 f = rhs_velocity_air_col(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q4(v[7], v[8], v[9], v[10]),
+                                        sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS,
+                                        sm.rp + (nl * NRV + lane_rv(lane)) * RP_COLS, sec_param(P, scen, nr.sec), un,
+                                        scen_tables(P, scen));
+    double* o = sm.f + (nl * 14 + lane) * 3;
+    o[0] = f.x;
+    o[1] = f.y;
+    o[2] = f.z;
+  } else {
+    dyn_scatter_block(P, scen, x, vals, start, count, tid, GJ_THREADS, sm);
+  }
+}
+
+/* ========================================================================= */
+/* Jacobian kernel, DYN_NOAIR role: GN_NODES vacuum nodes per block           */
+/*   0  gravity items (node, pv) | quaternion kinematics                      */
+/*   2  column items (node, 9 lanes: centre, mass, position x3, quaternion x4)*/
+/*   3  quotients -> COO slots                                                */
+/* ========================================================================= */
+P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+                          int phase, JacScratch& sm) {
+  const Units un = scen_units(P, scen);
+  const double dx = un.dx;
+  if (phase == 0) {
+    if (tid < GN_A_THREADS) {
+      if (tid >= count * NPV) return;
+      const int nl = tid / NPV, pv = tid - nl * NPV;
+      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      double p[3];
+      pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+      const Vec3 g = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+      double* o = sm.pp + (nl * NPV + pv) * 3;
+      o[0] = g.x;
+      o[1] = g.y;
+      o[2] = g.z;
+    } else {
+      const int nl = tid - GJ_Q_BASE;
+      if (nl < 0 || nl >= count) return;
+      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
+    }
+  } else if (phase == 2) {
+    if (tid >= count * 9) return;
+    const int nl = tid / 9, c9 = tid - nl * 9;
+    const int lane = c9 < 5 ? c9 : c9 + 3;
+    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    double v[11];
+    dyn_col_state(P, x, nr.row, lane, false, dx, v);
+    const double* g = sm.pp + (nl * NPV + lane_pv(lane)) * 3;
+    const Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), v3(g[0], g[1], g[2]),
+                                          sec_param(P, scen, nr.sec), un);
+    double* o = sm.f + (nl * 14 + lane) * 3;
+    o[0] = f.x;
+    o[1] = f.y;
+    o[2] = f.z;
+  } else if (phase == 3) {
+    dyn_scatter_block(P, scen, x, vals, start, count, tid, GJ_THREADS, sm);
+  }
+}
+
+/* ========================================================================= */
+/* Jacobian kernel, DYN_GEN role (fallback): 16 lanes per node, every lane a  */
+/* full right-hand side.  Used for sections whose reference_area is negative  */
+/* (air formula, but no velocity / time finite differences: con_dynamics.py:  */
+/* 257 vs :403,454).                                                          */
+/* ========================================================================= */
+P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+                        int phase, JacScratch& sm) {
+  const int nl = tid >> 4, lane = tid & 15;
+  if (nl >= count) return;
+  const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+  const Units un = scen_units(P, scen);
+  const double dx = un.dx;
+  const bool air = nr.flags & GSF_AIR, air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
+  if (phase == 0) {
+    const bool active = (lane <= 4) || (lane >= 8 && lane <= 11) || ((lane >= 5 && lane <= 7) && air_fd) ||
+                        ((lane == 12 || lane == 13) && air_fd);
+    if (active) {
+      double v[11];
+      dyn_col_state(P, x, nr.row, lane, air_fd, dx, v);
+      const double to0 = x[P.off_t + nr.sec], tf0 = x[P.off_t + nr.sec + 1];
+      const double to = (lane == 12) ? to0 + dx : to0;
+      const double tf = (lane == 13) ? tf0 + dx : tf0;
+      const SecParam sp = sec_param(P, scen, nr.sec);
+      const Quat q = q4(v[7], v[8], v[9], v[10]);
+      Vec3 f;
+      if (air) {
+        const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
+        f = rhs_velocity_air(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q, tn, sp, un, scen_tables(P, scen));
+      } else {
+        f = rhs_velocity_noair(v[0], v3(v[1], v[2], v[3]), q, sp, un);
+      }
+      double* o = sm.f + (nl * 14 + (lane < 14 ? lane : 0)) * 3;
+      o[0] = f.x;
+      o[1] = f.y;
+      o[2] = f.z;
+    }
+    if (lane == 15 && !hold) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
+  } else if (phase == 3) {
+    if (lane == 15) return;
+    const double* fc = sm.f + (nl * 14) * 3;
+    const double* qc = sm.q + (nl * 7) * 4;
+    dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
+  }
+}
+
+/* ========================================================================= */
+/* Residual kernel, DYN role: GR_NODES consecutive nodes per block.           */
+/*   phase 1: thread nl evaluates the right-hand sides of its node            */
 /*   phase 2: all threads sweep the (node, state column) items: D.X - rhs     */
 /* reference: con_dynamics.py:34-63, 116-152, 216-289, 499-533                */
 /* ========================================================================= */
-P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int sec, int node0, int count, int tid,
-                         BlockScratch& sm) {
+P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, int count, int tid, ResScratch& sm) {
   if (tid >= count) return;
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
-  const int ua = si[GS_UA], xa = si[GS_XA], flags = si[GS_FLAGS];
-  const int j = node0 + tid, row = xa + 1 + j;
+  const NodeRef nr = node_ref(P, g0 + tid);
+  const int row = nr.row;
   const Units un = scen_units(P, scen);
-  const SecParam sp = sec_param(P, scen, sec);
-  const double to = x[P.off_t + sec], tf = x[P.off_t + sec + 1];
+  const SecParam sp = sec_param(P, scen, nr.sec);
+  const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double m = x[row];
   const Vec3 p = v3(x[P.off_pos + 3 * row], x[P.off_pos + 3 * row + 1], x[P.off_pos + 3 * row + 2]);
   const Vec3 v = v3(x[P.off_vel + 3 * row], x[P.off_vel + 3 * row + 1], x[P.off_vel + 3 * row + 2]);
   const Quat q = q4(x[P.off_quat + 4 * row], x[P.off_quat + 4 * row + 1], x[P.off_quat + 4 * row + 2],
                     x[P.off_quat + 4 * row + 3]);
   Vec3 f;
-  if (flags & GSF_AIR) {
-    const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], j + 1, to, tf);
+  if (nr.flags & GSF_AIR) {
+    const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
     f = rhs_velocity_air(m, p, v, q, tn, sp, un, scen_tables(P, scen));
   } else {
     f = rhs_velocity_noair(m, p, q, sp, un);
@@ -312,8 +510,8 @@ P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int sec, 
   sm.f[tid][0] = f.x;
   sm.f[tid][1] = f.y;
   sm.f[tid][2] = f.z;
-  if (!(flags & GSF_HOLD)) {
-    Quat d = rhs_quaternion(q, x[P.off_u + 2 * (ua + j)], x[P.off_u + 2 * (ua + j) + 1], un.u);
+  if (!(nr.flags & GSF_HOLD)) {
+    Quat d = rhs_quaternion(q, x[P.off_u + 2 * (nr.ua + nr.j)], x[P.off_u + 2 * (nr.ua + nr.j) + 1], un.u);
     sm.q[tid][0] = d.w;
     sm.q[tid][1] = d.x;
     sm.q[tid][2] = d.y;
@@ -328,24 +526,23 @@ P_HD double dx_dot(const double* Drow, const double* xcol, int stride, int n1) {
   return acc;
 }
 
-P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g, int sec, int node0, int count,
-                         int tid, int nthreads, const BlockScratch& sm) {
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
-  const int n = si[GS_N], xa = si[GS_XA], flags = si[GS_FLAGS];
+P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g, int g0, int count, int tid,
+                         int nthreads, const ResScratch& sm) {
   const Units un = scen_units(P, scen);
   const double ut = un.t;
-  const double to = x[P.off_t + sec], tf = x[P.off_t + sec + 1];
-  const double dt = tf - to;
-  const double* D = P.d_pool + si[GS_D_OFF];
   for (int item = tid; item < count * 11; item += nthreads) {
     const int nl = item / 11, col = item - nl * 11;
-    const int j = node0 + nl, row = xa + 1 + j;
-    const double* Drow = D + (long long)j * (n + 1);
+    const NodeRef nr = node_ref(P, g0 + nl);
+    const int32_t* si = nr.si;
+    const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
+    const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
+    const double dt = tf - to;
+    const double* Drow = P.d_pool + si[GS_D_OFF] + (long long)j * (n + 1);
     if (col == 0) { /* mass: con_dynamics.py:53-61 */
       double r;
       if (flags & GSF_ENGINE_ON) {
         const double lh = dx_dot(Drow, x + xa, 1, n + 1);
-        const double rh = -sec_param(P, scen, sec).massflow / un.mass * dt * ut / 2.0;
+        const double rh = -sec_param(P, scen, nr.sec).massflow / un.mass * dt * ut / 2.0;
         r = lh - rh;
       } else {
         r = x[row] - x[xa];
@@ -378,9 +575,14 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
 
 /* ========================================================================= */
 /* Aero inequality jobs (con_aero.py:48-248, 311-756)                         */
-/*   Jacobian: 16 lanes per constraint row                                    */
-/*   lane 0 centre | 1-3 position | 4-6 velocity | 7-10 quaternion | 11 to | 12 tf */
+/*   Jacobian lanes per constraint row:                                       */
+/*   0 centre | 1-3 position | 4-6 velocity | 7-10 quaternion | 11 to | 12 tf */
+/*   Same sharing as the dynamics: pv 0 base | 1-3 axis perturbed | 4 all     */
+/*   restored; rv 0-4 nominal time | 5 to+dx | 6 tf+dx.                       */
 /* ========================================================================= */
+P_HD int aero_lane_pv(int lane) { return lane == 0 ? 0 : (lane <= 3 ? lane : 4); }
+P_HD int aero_lane_rv(int lane) { return lane == 0 ? 0 : (lane <= 3 ? lane : (lane <= 10 ? 4 : lane - 6)); }
+
 P_HD double aero_value(const PlanView& P, int scen, int kind, const double* v /*pos3 vel3 quat4*/, double t_e,
                        double limit) {
   const Units un = scen_units(P, scen);
@@ -396,58 +598,95 @@ P_HD void aero_load(const PlanView& P, const double* x, int row, double* v) {
   for (int k = 0; k < 4; k++) v[6 + k] = x[P.off_quat + 4 * row + k];
 }
 
-P_HD void aero_jac_phase1(const PlanView& P, int scen, const double* x, int job, int r0, int count, int tid,
-                          BlockScratch& sm) {
-  const int rl = tid >> 4, lane = tid & 15;
-  if (rl >= count) return;
-  const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
-  const int kind = ai[GA_KIND], sec = ai[GA_SECTION];
-  const bool has_quat = kind != 1;
-  if (lane > 12 || (!has_quat && lane >= 7 && lane <= 10)) return;
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
-  const int r = r0 + rl, row = si[GS_XA] + r;
+/* state row + section times as the aero gradient finds them: residue left by the groups
+ * that ran before it in `sens` */
+P_HD void aero_base(const PlanView& P, const double* x, int sec, int row, double* v, double* to, double* tf) {
   const double dx = P.un.dx;
-  double v[10];
   aero_load(P, x, row, v);
-  double to = x[P.off_t + sec], tf = x[P.off_t + sec + 1];
-  if (P.rc_aero) { /* residue left by the groups that ran before */
+  *to = x[P.off_t + sec];
+  *tf = x[P.off_t + sec + 1];
+  if (P.rc_aero) {
     for (int k = 0; k < 3; k++) v[k] = residue_n(v[k], dx, P.rc_aero[P.off_pos + 3 * row + k]);
     for (int k = 0; k < 3; k++) v[3 + k] = residue_n(v[3 + k], dx, P.rc_aero[P.off_vel + 3 * row + k]);
     for (int k = 0; k < 4; k++) v[6 + k] = residue_n(v[6 + k], dx, P.rc_aero[P.off_quat + 4 * row + k]);
-    to = residue_n(to, dx, P.rc_aero[P.off_t + sec]);
-    tf = residue_n(tf, dx, P.rc_aero[P.off_t + sec + 1]);
+    *to = residue_n(*to, dx, P.rc_aero[P.off_t + sec]);
+    *tf = residue_n(*tf, dx, P.rc_aero[P.off_t + sec + 1]);
   }
-  if (lane != 0) { /* gradient works on a copy: columns leave residue inside the copy only */
-    const int pidx = (lane <= 10) ? lane - 1 : 10;
-    for (int w = 0; w < 10; w++) {
-      if (!has_quat && w >= 6) continue;
-      if (w < pidx) v[w] = residue(v[w], dx);
-      else if (w == pidx) v[w] = v[w] + dx;
-    }
-  }
-  if (lane == 11) to = to + dx;
-  if (lane == 12) tf = tf + dx;
-  const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], r, to, tf);
-  sm.f[tid][0] = aero_value(P, scen, kind, v, tn, P.aero_f64[job * GA_F64_COLS + GA_LIMIT]);
 }
 
-P_HD void aero_jac_phase2(const PlanView& P, int scen, double* vals, int job, int r0, int count, int tid,
-                          const BlockScratch& sm) {
-  (void)scen;
-  const int rl = tid >> 4, lane = tid & 15;
-  if (rl >= count || lane == 0 || lane > 12) return;
-  const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
-  const int64_t* aj = P.aero_i64 + job * GA_I64_COLS;
-  const int kind = ai[GA_KIND], nk = ai[GA_NK];
-  if (kind == 1 && lane >= 7 && lane <= 10) return;
-  const int r = r0 + rl;
+P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+                     int phase, JacScratch& sm) {
+  const Units un = scen_units(P, scen);
   const double dx = P.un.dx;
-  const double gval = -((sm.f[tid][0] - sm.f[tid & ~15][0]) / dx); /* -dfdx (con_aero.py:439-461) */
-  if (lane <= 3) vals[aj[GA_J_POS] + (long long)(lane - 1) * nk + r] = gval;
-  else if (lane <= 6) vals[aj[GA_J_VEL] + (long long)(lane - 4) * nk + r] = gval;
-  else if (lane <= 10) vals[aj[GA_J_QUAT] + (long long)(lane - 7) * nk + r] = gval;
-  else if (lane == 11) vals[aj[GA_J_T] + r] = gval;
-  else vals[aj[GA_J_T] + nk + r] = gval;
+  if (phase == 0) {
+    const bool is_a = tid < GJ_A_THREADS;
+    const int item = is_a ? tid : tid - GJ_A_THREADS;
+    const int per = is_a ? NPV : NRV;
+    if (tid >= GJ_A_THREADS + GJ_B_THREADS || item >= count * per) return;
+    const int nl = item / per, var = item - nl * per;
+    const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
+    const int sec = P.aero_i32[job * GA_I32_COLS + GA_SECTION];
+    const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
+    double v[10], to, tf, p[3];
+    aero_base(P, x, sec, si[GS_XA] + r, v, &to, &tf);
+    if (is_a) {
+      pos_variant(v, var, dx, p);
+      const Tables tb = scen_tables(P, scen);
+      pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, 0, sm.pp + (nl * NPV + var) * PP_COLS);
+    } else {
+      pos_variant(v, rv_pv(var), dx, p);
+      if (var == 5) to = to + dx;
+      if (var == 6) tf = tf + dx;
+      const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], r, to, tf);
+      rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
+    }
+  } else if (phase == 1) {
+    if (tid >= count * NRV) return;
+    const int nl = tid / NRV, rv = tid - nl * NRV;
+    const double* pp = sm.pp + (nl * NPV + rv_pv(rv)) * PP_COLS;
+    rot_wind(sm.rq + (nl * NRV + rv) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], sm.rp + (nl * NRV + rv) * RP_COLS);
+  } else if (phase == 2) {
+    if (tid >= count * 13) return;
+    const int nl = tid / 13, lane = tid - nl * 13;
+    const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
+    const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
+    const int kind = ai[GA_KIND], sec = ai[GA_SECTION];
+    const bool has_quat = kind != 1;
+    if (!has_quat && lane >= 7 && lane <= 10) return;
+    double v[10], to, tf;
+    aero_base(P, x, sec, P.sec_i32[sec * GS_I32_COLS + GS_XA] + r, v, &to, &tf);
+    if (lane != 0) { /* the gradient works on a copy: columns leave residue inside the copy only */
+      const int pidx = (lane <= 10) ? lane - 1 : 10;
+      for (int w = 0; w < 10; w++) {
+        if (!has_quat && w >= 6) continue;
+        if (w < pidx) v[w] = residue(v[w], dx);
+        else if (w == pidx) v[w] = v[w] + dx;
+      }
+    }
+    const Vec3 pos = v3(v[0] * un.pos, v[1] * un.pos, v[2] * un.pos);
+    const Vec3 vel = v3(v[3] * un.vel, v[4] * un.vel, v[5] * un.vel);
+    const double val = aero_quantity_col(kind, pos, vel, q4(v[6], v[7], v[8], v[9]),
+                                         sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS,
+                                         sm.rp + (nl * NRV + aero_lane_rv(lane)) * RP_COLS) /
+                       P.aero_f64[job * GA_F64_COLS + GA_LIMIT];
+    sm.f[(nl * 14 + lane) * 3] = val;
+  } else {
+    for (int item = tid; item < count * 16; item += GJ_THREADS) {
+      const int nl = item >> 4, lane = item & 15;
+      if (lane == 0 || lane > 12) continue;
+      const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
+      const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
+      const int64_t* aj = P.aero_i64 + job * GA_I64_COLS;
+      const int kind = ai[GA_KIND], nk = ai[GA_NK];
+      if (kind == 1 && lane >= 7 && lane <= 10) continue;
+      const double gval = -((sm.f[(nl * 14 + lane) * 3] - sm.f[(nl * 14) * 3]) / dx); /* -dfdx (con_aero.py:439-461) */
+      if (lane <= 3) vals[aj[GA_J_POS] + (long long)(lane - 1) * nk + r] = gval;
+      else if (lane <= 6) vals[aj[GA_J_VEL] + (long long)(lane - 4) * nk + r] = gval;
+      else if (lane <= 10) vals[aj[GA_J_QUAT] + (long long)(lane - 7) * nk + r] = gval;
+      else if (lane == 11) vals[aj[GA_J_T] + r] = gval;
+      else vals[aj[GA_J_T] + nk + r] = gval;
+    }
+  }
 }
 
 /* residual kernel: one thread per aero row, pristine inputs: 1 - f (con_aero.py:89-248) */
@@ -544,7 +783,7 @@ P_HD int evt_n_lanes(int type) {
   return type == GE_IIP ? 8 : (type == GE_TERM ? 7 : (type == GE_USER_PERIGEE ? 13 : 5));
 }
 
-P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, BlockScratch& sm) {
+P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
@@ -582,12 +821,12 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
     if (perturbed >= 0) s[perturbed] = s[perturbed] + dx;
   }
   EvtOut o = evt_leaf(P, scen, type, ef, s, s + 3, t_e);
-  sm.f[tid][0] = o.v[0];
-  sm.f[tid][1] = o.v[1];
-  sm.f[tid][2] = o.v[2];
+  sm.f[3 * tid + 0] = o.v[0];
+  sm.f[3 * tid + 1] = o.v[1];
+  sm.f[3 * tid + 2] = o.v[2];
 }
 
-P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, const BlockScratch& sm) {
+P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, const JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
   const int64_t* ej = P.evt_i64 + job * GE_I64_COLS;
@@ -600,15 +839,15 @@ P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, cons
     const int nrow = ei[GE_NROW];
     const int64_t base = (lane <= 3) ? ej[GE_J_POS] + (long long)(lane - 1) * nrow
                                      : ej[GE_J_VEL] + (long long)(lane - 4) * nrow;
-    for (int r = 0; r < nrow; r++) vals[base + r] = (sm.f[tid][r] - sm.f[c][r]) / dx;
+    for (int r = 0; r < nrow; r++) vals[base + r] = (sm.f[3 * tid + r] - sm.f[3 * c + r]) / dx;
     return;
   }
   if (type == GE_USER_PERIGEE) { /* aux tail: fd[6] then background[6] */
-    vals[ej[GE_J_POS] + (lane - 1)] = (sm.f[tid][0] - sm.f[c][0]) / dx;
+    vals[ej[GE_J_POS] + (lane - 1)] = (sm.f[3 * tid] - sm.f[3 * c]) / dx;
     return;
   }
   const int comp = ei[GE_COMP], form = ei[GE_FORM];
-  const double gfd = (sm.f[tid][comp] - sm.f[c][comp]) / dx;
+  const double gfd = (sm.f[3 * tid + comp] - sm.f[3 * c + comp]) / dx;
   const double val = evt_form_grad(form, gfd, ef[GE_REF], ef[GE_DEN]);
   if (type == GE_IIP) {
     if (lane == 7) vals[ej[GE_J_T]] = val;
@@ -633,36 +872,38 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 }
 
 /* ========================================================================= */
-/* Block dispatch: one function per kernel and phase                          */
+/* Block dispatch.  Jacobian blocks run GJ_PHASES phases with a block barrier  */
+/* between them; residual blocks run two.                                      */
 /* ========================================================================= */
-P_HD void jac_block_phase1(const PlanView& P, int scen, const int32_t* bt, const double* x, int tid,
-                           BlockScratch& sm) {
+P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, int tid,
+                          int phase, JacScratch& sm) {
+  const int start = bt[BT_START], count = bt[BT_COUNT];
   switch (bt[BT_ROLE]) {
-    case BR_DYN: dyn_jac_phase1(P, scen, x, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, sm); break;
-    case BR_AERO: aero_jac_phase1(P, scen, x, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, sm); break;
+    case BR_DYN_AIR: dyn_air_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
+    case BR_DYN_NOAIR: dyn_noair_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
+    case BR_DYN_GEN: dyn_gen_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
+    case BR_AERO: aero_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
     case BR_EVT:
-      if ((tid >> 4) < bt[BT_COUNT]) evt_jac_phase1(P, scen, x, bt[BT_START] + (tid >> 4), tid, sm);
+      if ((tid >> 4) < count) {
+        if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, sm);
+        else if (phase == 3) evt_jac_phase2(P, vals, start + (tid >> 4), tid, sm);
+      }
       break;
     default: break;
   }
 }
-P_HD void jac_block_phase2(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, int tid,
-                           const BlockScratch& sm) {
-  switch (bt[BT_ROLE]) {
-    case BR_DYN: dyn_jac_phase2(P, scen, x, vals, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, sm); break;
-    case BR_AERO: aero_jac_phase2(P, scen, vals, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, sm); break;
-    case BR_EVT:
-      if ((tid >> 4) < bt[BT_COUNT]) evt_jac_phase2(P, vals, bt[BT_START] + (tid >> 4), tid, sm);
-      break;
-    default: break;
-  }
-}
+/* roles whose phases 1 and 2 are empty (the kernel skips those barriers) */
+P_HD bool jac_role_two_phase(int role) { return role == BR_EVT || role == BR_DYN_GEN; }
+
 P_HD void res_block_phase1(const PlanView& P, int scen, const int32_t* bt, const double* x, double* g, int tid,
-                           BlockScratch& sm) {
+                           ResScratch& sm) {
   switch (bt[BT_ROLE]) {
-    case BR_DYN: dyn_res_phase1(P, scen, x, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, sm); break;
+    case BR_DYN: dyn_res_phase1(P, scen, x, bt[BT_START], bt[BT_COUNT], tid, sm); break;
     case BR_AERO:
-      if (tid < bt[BT_COUNT]) aero_res(P, scen, x, g, bt[BT_JOB], bt[BT_START] + tid);
+      if (tid < bt[BT_COUNT]) {
+        const int32_t* ar = P.aero_rows + 2 * (bt[BT_START] + tid);
+        aero_res(P, scen, x, g, ar[0], ar[1]);
+      }
       break;
     case BR_EVT:
       if (tid < bt[BT_COUNT]) evt_res(P, scen, x, g, bt[BT_START] + tid);
@@ -676,8 +917,8 @@ P_HD void res_block_phase1(const PlanView& P, int scen, const int32_t* bt, const
   }
 }
 P_HD void res_block_phase2(const PlanView& P, int scen, const int32_t* bt, const double* x, double* g, int tid,
-                           int nthreads, const BlockScratch& sm) {
-  if (bt[BT_ROLE] == BR_DYN) dyn_res_phase2(P, scen, x, g, bt[BT_JOB], bt[BT_START], bt[BT_COUNT], tid, nthreads, sm);
+                           int nthreads, const ResScratch& sm) {
+  if (bt[BT_ROLE] == BR_DYN) dyn_res_phase2(P, scen, x, g, bt[BT_START], bt[BT_COUNT], tid, nthreads, sm);
 }
 
 #endif /* GELATO_B200_JOBS_H_ */

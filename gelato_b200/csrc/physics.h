@@ -263,7 +263,7 @@ P_HD double interp_table(double x, const double* xp, const double* yp, int n, in
  * only 5 distinct inputs over the 14 columns, the position+time part (NED frame,
  * wind in ECI axes) 7.  The kernels therefore evaluate
  *     pos_part(pos)            once per distinct position,
- *     rot_part(pos, t, wind)   once per distinct (position, time),
+ *     rotq_part(pos, t)        once per distinct (position, time), then rot_wind,
  *     a cheap per-column remainder,
  * with exactly the operations (and operation order) of the single-pass formulas in
  * pybind_dynamics.cpp:42-68 / wrapper_utils.hpp:89-193, so every column's bits
@@ -298,20 +298,36 @@ P_HD_CALL void pos_part(double px, double py, double pz, const double* wind, int
   out[PP_GZ] = gr.z;
 }
 
-/* position+time part: cos/sin of the Earth-rotation angle and the wind in ECI axes.
- * t as the caller passes it (the dynamics pass NON-dimensional node times -- quirk
- * A.5-1 -- the aero constraints pass seconds).  pybind_dynamics.cpp:48-52 */
-P_HD_CALL void rot_part(double px, double py, double pz, double t, double wind_n, double wind_e, double* out) {
-  Vec3 pos = v3(px, py, pz);
+/* position+time part, first half: cos/sin of the Earth-rotation angle and the
+ * NED->ECI quaternion at that position and time.  t as the caller passes it (the
+ * dynamics pass NON-dimensional node times -- quirk A.5-1 -- the aero constraints
+ * pass seconds).  pybind_dynamics.cpp:48-51 */
+enum { RQ_COS = 0, RQ_SIN, RQ_W, RQ_X, RQ_Y, RQ_Z, RQ_COLS };
+P_HD_CALL void rotq_part(double px, double py, double pz, double t, double* out) {
   double wt = P_OMEGA * t;
   double s, c;
   gm_sincos(wt, &s, &c);
-  Vec3 wind_eci = quatrot(quat_ned2eci_cs(pos, wt, c, s), v3(wind_n, wind_e, 0.0));
-  out[RP_COS] = c;
-  out[RP_SIN] = s;
+  Quat q = quat_ned2eci_cs(v3(px, py, pz), wt, c, s);
+  out[RQ_COS] = c;
+  out[RQ_SIN] = s;
+  out[RQ_W] = q.w;
+  out[RQ_X] = q.x;
+  out[RQ_Y] = q.y;
+  out[RQ_Z] = q.z;
+}
+/* second half: the wind of that altitude turned into ECI axes (pybind_dynamics.cpp:52) */
+P_HD void rot_wind(const double* rq, double wind_n, double wind_e, double* out) {
+  Vec3 wind_eci = quatrot(q4(rq[RQ_W], rq[RQ_X], rq[RQ_Y], rq[RQ_Z]), v3(wind_n, wind_e, 0.0));
+  out[RP_COS] = rq[RQ_COS];
+  out[RP_SIN] = rq[RQ_SIN];
   out[RP_WX] = wind_eci.x;
   out[RP_WY] = wind_eci.y;
   out[RP_WZ] = wind_eci.z;
+}
+P_HD void rot_part(double px, double py, double pz, double t, double wind_n, double wind_e, double* out) {
+  double rq[RQ_COLS];
+  rotq_part(px, py, pz, t, rq);
+  rot_wind(rq, wind_n, wind_e, out);
 }
 
 /* air-relative velocity in ECI axes: pybind_dynamics.cpp:47,53 */

@@ -1,5 +1,6 @@
 /* plan_host.h -- host-side helpers shared by the CUDA library and the test
- * emulator: PlanView scalar fields from a GelatoPlanDesc and the block tables. */
+ * emulator: PlanView scalar fields from a GelatoPlanDesc, the node / row lists
+ * and the block tables of the two kernels. */
 #ifndef GELATO_B200_PLAN_HOST_H_
 #define GELATO_B200_PLAN_HOST_H_
 
@@ -23,28 +24,60 @@ static inline void planview_scalars(const GelatoPlanDesc* d, PlanView& v) {
   v.n_lin = d->n_lin; v.n_aero = d->n_aero; v.n_evt = d->n_evt;
 }
 
+struct HostTables {
+  std::vector<int32_t> jac_blocks, res_blocks; /* BT_COLS ints per block */
+  std::vector<int32_t> node_sec;               /* [N] */
+  std::vector<int32_t> jac_nodes;              /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
+  std::vector<int32_t> aero_rows;              /* [rows][2] */
+};
+
 static inline void push_block(std::vector<int32_t>& t, int role, int job, int start, int count) {
   t.push_back(role);
   t.push_back(job);
   t.push_back(start);
   t.push_back(count);
 }
+static inline void push_chunks(std::vector<int32_t>& t, int role, int first, int total, int per_block) {
+  for (int a = 0; a < total; a += per_block) push_block(t, role, 0, first + a, std::min(per_block, total - a));
+}
 
-/* jb: Jacobian kernel blocks, rb: residual kernel blocks (BT_COLS ints each) */
-static inline void build_block_tables(const GelatoPlanDesc* d, std::vector<int32_t>& jb, std::vector<int32_t>& rb) {
-  for (int s = 0; s < d->n_sections; s++) {
-    const int n = d->sec_i32[s * GS_I32_COLS + GS_N];
-    for (int a = 0; a < n; a += GB_DYN_JAC_NODES) push_block(jb, BR_DYN, s, a, std::min(GB_DYN_JAC_NODES, n - a));
-    for (int a = 0; a < n; a += GB_DYN_RES_NODES) push_block(rb, BR_DYN, s, a, std::min(GB_DYN_RES_NODES, n - a));
+static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
+  const int S = d->n_sections, N = d->n_nodes;
+  h.node_sec.assign(N, 0);
+  std::vector<int32_t> air, vac, gen;
+  for (int s = 0; s < S; s++) {
+    const int32_t* si = d->sec_i32 + s * GS_I32_COLS;
+    const int flags = si[GS_FLAGS];
+    for (int j = 0; j < si[GS_N]; j++) {
+      const int g = si[GS_UA] + j;
+      h.node_sec[g] = s;
+      if (flags & GSF_AIR_FD) air.push_back(g);
+      else if (!(flags & GSF_AIR)) vac.push_back(g);
+      else gen.push_back(g);
+    }
   }
-  for (int k = 0; k < d->n_aero; k++) {
-    const int nk = d->aero_i32[k * GA_I32_COLS + GA_NK];
-    for (int a = 0; a < nk; a += GB_ROWS16) push_block(jb, BR_AERO, k, a, std::min(GB_ROWS16, nk - a));
-    for (int a = 0; a < nk; a += GB_THREADS) push_block(rb, BR_AERO, k, a, std::min(GB_THREADS, nk - a));
-  }
-  for (int a = 0; a < d->n_evt; a += GB_ROWS16) push_block(jb, BR_EVT, 0, a, std::min(GB_ROWS16, d->n_evt - a));
-  for (int a = 0; a < d->n_evt; a += GB_THREADS) push_block(rb, BR_EVT, 0, a, std::min(GB_THREADS, d->n_evt - a));
-  for (int a = 0; a < d->n_lin; a += GB_THREADS) push_block(rb, BR_LIN, 0, a, std::min(GB_THREADS, d->n_lin - a));
+  h.jac_nodes = air;
+  h.jac_nodes.insert(h.jac_nodes.end(), vac.begin(), vac.end());
+  h.jac_nodes.insert(h.jac_nodes.end(), gen.begin(), gen.end());
+  for (int k = 0; k < d->n_aero; k++)
+    for (int r = 0; r < d->aero_i32[k * GA_I32_COLS + GA_NK]; r++) {
+      h.aero_rows.push_back(k);
+      h.aero_rows.push_back(r);
+    }
+  const int n_aero_rows = (int)h.aero_rows.size() / 2;
+
+  std::vector<int32_t>& jb = h.jac_blocks;
+  push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GJ_NODES);
+  push_chunks(jb, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
+  push_chunks(jb, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
+  push_chunks(jb, BR_AERO, 0, n_aero_rows, GJ_NODES);
+  push_chunks(jb, BR_EVT, 0, d->n_evt, GJ_EVT);
+
+  std::vector<int32_t>& rb = h.res_blocks;
+  push_chunks(rb, BR_DYN, 0, N, GR_NODES);
+  push_chunks(rb, BR_AERO, 0, n_aero_rows, GR_THREADS);
+  push_chunks(rb, BR_EVT, 0, d->n_evt, GR_THREADS);
+  push_chunks(rb, BR_LIN, 0, d->n_lin, GR_THREADS);
 }
 
 #endif

@@ -3,7 +3,7 @@
 // Compiles gelato_b200/csrc/jobs.h (the per-thread job functions the kernels
 // run) with g++ and steps through every block and thread serially: phase 1 for
 // all threads of a block, then phase 2 -- the same order the block barrier
-// enforces on the GPU.  It lets the CPU-only test tier check the plan compiler
+// enforces on the GPU (the Jacobian kernel has GJ_PHASES phases, the residual kernel two).  It lets the CPU-only test tier check the plan compiler
 // and the kernels' index arithmetic against the oracle bit for bit.  It is not
 // part of the product: libgelato_b200.so has no CPU path and bench.py never
 // loads this file.
@@ -25,6 +25,13 @@ static PlanView host_view(const GelatoPlanDesc* d) {
   return v;
 }
 
+static void attach_tables(PlanView& v, const HostTables& h) {
+  v.node_sec = h.node_sec.data();
+  v.jac_nodes = h.jac_nodes.data();
+  v.aero_rows = h.aero_rows.data();
+  v.n_aero_rows = (int)h.aero_rows.size() / 2;
+}
+
 static void apply_scen(PlanView& v, const GelatoScenarioDesc* sc) {
   if (!sc) return;
   if (sc->sec_f64) { v.sec_f64 = sc->sec_f64; v.sec_f64_sstride = (long long)v.S * GS_F64_COLS; }
@@ -43,16 +50,18 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
                                   double* g_all, int n_scen) {
   PlanView P = host_view(d);
   apply_scen(P, sc);
-  std::vector<int32_t> jb, rb;
-  build_block_tables(d, jb, rb);
-  BlockScratch sm;
+  HostTables h;
+  build_host_tables(d, h);
+  attach_tables(P, h);
+  const std::vector<int32_t>& rb = h.res_blocks;
+  ResScratch sm;
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
     double* g = g_all + (size_t)scen * P.n_rows;
     for (size_t b = 0; b < rb.size() / BT_COLS; b++) {
       const int32_t* bt = rb.data() + b * BT_COLS;
-      for (int tid = 0; tid < GB_THREADS; tid++) res_block_phase1(P, scen, bt, x, g, tid, sm);
-      for (int tid = 0; tid < GB_THREADS; tid++) res_block_phase2(P, scen, bt, x, g, tid, GB_THREADS, sm);
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, scen, bt, x, g, tid, sm);
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase2(P, scen, bt, x, g, tid, GR_THREADS, sm);
     }
   }
   return 0;
@@ -62,9 +71,11 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
                                  double* vals_all, int n_scen) {
   PlanView P = host_view(d);
   apply_scen(P, sc);
-  std::vector<int32_t> jb, rb;
-  build_block_tables(d, jb, rb);
-  BlockScratch sm;
+  HostTables h;
+  build_host_tables(d, h);
+  attach_tables(P, h);
+  const std::vector<int32_t>& jb = h.jac_blocks;
+  JacScratch sm;
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
     double* vals = vals_all + (size_t)scen * P.n_vals;
@@ -72,8 +83,10 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
     memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
     for (size_t b = 0; b < jb.size() / BT_COLS; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
-      for (int tid = 0; tid < GB_THREADS; tid++) jac_block_phase1(P, scen, bt, x, tid, sm);
-      for (int tid = 0; tid < GB_THREADS; tid++) jac_block_phase2(P, scen, bt, x, vals, tid, sm);
+      /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
+      memset(&sm, 0xff, sizeof sm);
+      for (int phase = 0; phase < GJ_PHASES; phase++)
+        for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase(P, scen, bt, x, vals, tid, phase, sm);
     }
   }
   return 0;

@@ -153,6 +153,9 @@ def variant_inputs(name):
         }
         fc["antenna"]["ANT2"] = {"lon": 145.0, "lat": 40.0, "altitude": 10.0,
                                  "elevation_min": {"SEIG": 2.0, "FAIRING": 1.0, "SECO": 0.5}}
+    elif name == "neg_area":  # stage 2 with a NEGATIVE reference area: the reference takes the air formula
+        # (reference_area != 0.0, con_dynamics.py:257) but the vacuum Jacobian branches (> 0.0, :403,454)
+        s["RocketStage"]["2"]["reference_area"] = -0.5
     elif name == "bare":  # no waypoint / antenna blocks, no aero rows, no user constraint rows
         fc.pop("waypoint")
         fc.pop("antenna")
