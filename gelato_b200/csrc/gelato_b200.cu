@@ -6,7 +6,7 @@
 //   k_jacobian  : every x-dependent Jacobian value `sens` produces (:245-312)
 // Each is ONE launch per call; blocks take their role from a block table built
 // at plan creation (dynamics sections in chunks of nodes, aero rows, event
-// rows, linear rows).  blockIdx.y is the scenario index for batched solves.
+// rows, linear rows), one copy of the block list per scenario of a batched solve.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see DESIGN.md H1;
 // gelato_selftest_unfused() verifies the flag at run time).
@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "plan_host.h"
@@ -23,12 +24,17 @@
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GJ_THREADS, 2)
-k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
-           double* __restrict__ vals_all) {
+#ifndef GJ_MIN_BLOCKS
+#define GJ_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
+k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+           const double* __restrict__ x_all, double* __restrict__ vals_all) {
   __shared__ JacScratch sm;
-  const int scen = blockIdx.y;
-  const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
+  // role-major launch order: block b of every scenario before block b+1 of any, so the blocks
+  // resident on an SM at one time mostly run the same role's code (instruction-cache locality)
+  const int scen = blockIdx.x % n_scen;
+  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* vals = vals_all + (size_t)scen * P.n_vals;
   const bool two_phase = jac_role_two_phase(bt[BT_ROLE]);
@@ -44,16 +50,26 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const doub
 }
 
 __global__ void __launch_bounds__(GR_THREADS)
-k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const double* __restrict__ x_all,
-            double* __restrict__ g_all) {
+k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+            const double* __restrict__ x_all, double* __restrict__ g_all) {
   __shared__ ResScratch sm;
-  const int scen = blockIdx.y;
-  const int32_t* bt = block_table + (size_t)blockIdx.x * BT_COLS;
+  const int scen = blockIdx.x % n_scen;
+  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* g = g_all + (size_t)scen * P.n_rows;
   res_block_phase1(P, scen, bt, x, g, threadIdx.x, sm);
   __syncthreads();
   res_block_phase2(P, scen, bt, x, g, threadIdx.x, GR_THREADS, sm);
+}
+
+// packed[scen][i] = vals[scen][idx[i]]: the x-dependent slots, gathered for the PCIe copy of update mode
+__global__ void k_pack_xdep(const double* __restrict__ vals_all, const int64_t* __restrict__ idx, long long n_xdep,
+                            long long n_vals, double* __restrict__ packed_all) {
+  const int scen = blockIdx.y;
+  const double* vals = vals_all + (size_t)scen * n_vals;
+  double* packed = packed_all + (size_t)scen * n_xdep;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_xdep; i += (long long)gridDim.x * blockDim.x)
+    packed[i] = vals[idx[i]];
 }
 
 // probe: is a*b+c left unfused?  (1 + 2^-30)(1 - 2^-30) - 1 is 0 unfused, -2^-60 fused
@@ -114,6 +130,14 @@ struct GelatoPlan {
   double *d_x = nullptr, *d_g = nullptr, *d_vals = nullptr;
   double *h_x = nullptr, *h_out = nullptr;  // pinned
   size_t cap_scen = 0;
+  // update mode
+  const int64_t* d_xdep = nullptr;
+  std::vector<int64_t> h_xdep;
+  long long n_xdep = 0;
+  double *d_pack = nullptr, *h_pack = nullptr;  // [cap_pack][n_xdep], h_pack pinned
+  size_t cap_pack = 0;
+  int host_threads = 0;
+  std::vector<cudaEvent_t> chunk_ev;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -143,6 +167,7 @@ int gelato_device_count(void) {
 int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   if (!d || !out) return fail(GELATO_ERR_ARG, "null argument");
   if (d->n_sections <= 0 || d->n_nodes <= 0) return fail(GELATO_ERR_ARG, "empty problem");
+  if (!(d->dx > 0.0)) return fail(GELATO_ERR_ARG, "dx must be positive");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -171,6 +196,18 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   UP(evt_i32, d->evt_i32, (size_t)d->n_evt * GE_I32_COLS)
   UP(evt_i64, d->evt_i64, (size_t)d->n_evt * GE_I64_COLS)
   UP(evt_f64, d->evt_f64, (size_t)d->n_evt * GE_F64_COLS)
+  if (d->xdep_idx && d->n_xdep > 0) {
+    for (int64_t i = 0; i < d->n_xdep; i++)
+      if (d->xdep_idx[i] < 0 || d->xdep_idx[i] >= d->n_vals || (i > 0 && d->xdep_idx[i] <= d->xdep_idx[i - 1])) {
+        gelato_plan_destroy(p);
+        return fail(GELATO_ERR_ARG, "xdep_idx must be strictly ascending and inside [0, n_vals)");
+      }
+    p->h_xdep.assign(d->xdep_idx, d->xdep_idx + d->n_xdep);
+    p->n_xdep = d->n_xdep;
+    const int64_t* dx = nullptr;
+    if ((rc = upload(p, d->xdep_idx, (size_t)d->n_xdep, &dx)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+    p->d_xdep = dx;
+  }
   const double* tmpl = nullptr;
   if ((rc = upload(p, d->vals_template, (size_t)d->n_vals, &tmpl)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->vals_template = const_cast<double*>(tmpl);
@@ -240,6 +277,9 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->d_vals) cudaFree(p->d_vals);
   if (p->h_x) cudaFreeHost(p->h_x);
   if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->d_pack) cudaFree(p->d_pack);
+  if (p->h_pack) cudaFreeHost(p->h_pack);
+  for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -251,6 +291,7 @@ int32_t gelato_plan_n_vars(const GelatoPlan* p) { return p ? p->view.n_vars : 0;
 int32_t gelato_plan_n_rows(const GelatoPlan* p) { return p ? p->view.n_rows : 0; }
 int64_t gelato_plan_n_vals(const GelatoPlan* p) { return p ? p->view.n_vals : 0; }
 int64_t gelato_plan_launch_count(const GelatoPlan* p) { return p ? p->launches : 0; }
+int64_t gelato_plan_n_xdep(const GelatoPlan* p) { return p ? p->n_xdep : 0; }
 
 static int check_scen(GelatoPlan* p, int n_scen) {
   if (!p) return fail(GELATO_ERR_ARG, "null plan");
@@ -259,7 +300,8 @@ static int check_scen(GelatoPlan* p, int n_scen) {
                         p->view.lin_const_scen || p->vals_template_sstride;
   if (per_scen && n_scen > p->n_scen_cfg)
     return fail(GELATO_ERR_ARG, "n_scen exceeds the configured scenario blocks");
-  if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 (gridDim.y)");
+  const long long most = std::max(p->n_jac_blocks, p->n_res_blocks);
+  if (most * n_scen > 0x7fffffffLL) return fail(GELATO_ERR_ARG, "blocks x n_scen exceeds the grid limit");
   return GELATO_OK;
 }
 
@@ -268,8 +310,7 @@ int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev,
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  dim3 grid(p->n_res_blocks, n_scen);
-  k_residuals<<<grid, GR_THREADS, 0, st>>>(p->view, p->res_blocks, x_dev, g_dev);
+  k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(p->view, p->res_blocks, n_scen, x_dev, g_dev);
   p->launches++;
   CU(cudaGetLastError());
   return GELATO_OK;
@@ -298,8 +339,7 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
   // the kernel rewrites every x-dependent slot and never touches the rest
-  dim3 grid(p->n_jac_blocks, n_scen);
-  k_jacobian<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, x_dev, vals_dev);
+  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
   p->launches++;
   CU(cudaGetLastError());
   return GELATO_OK;
@@ -324,15 +364,7 @@ static int ensure_staging(GelatoPlan* p, size_t n_scen) {
   CU(cudaMallocHost(&p->h_out, n_scen * nout * sizeof(double)));
   p->cap_scen = n_scen;
   // constants of the Jacobian: written once, the kernel only rewrites x-dependent slots
-  const int chunk = 65535;
-  for (size_t s0 = 0; s0 < n_scen; s0 += chunk) {
-    const int ns = (int)std::min<size_t>(chunk, n_scen - s0);
-    const bool per_scen = p->vals_template_sstride != 0;
-    if (per_scen && s0 > 0) return fail(GELATO_ERR_ARG, "too many scenarios");
-    int rc = gelato_fill_template(p, p->d_vals + s0 * (size_t)v.n_vals, ns, p->stream);
-    if (rc) return rc;
-  }
-  return GELATO_OK;
+  return gelato_fill_template(p, p->d_vals, (int)n_scen, p->stream);
 }
 
 // page-locked host memory can be DMA'd directly; pageable memory goes through the plan's staging buffers
@@ -378,6 +410,113 @@ int gelato_eval_jacobian(GelatoPlan* p, const double* x, double* vals, int32_t n
   return eval_host(p, 1, x, vals, n_scen);
 }
 
+int gelato_pack_xdep_dev(GelatoPlan* p, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!p->d_xdep) return fail(GELATO_ERR_ARG, "the plan was created without xdep_idx");
+  if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 in update mode (gridDim.y)");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  const int threads = 256;
+  const int bx = (int)std::min<long long>((p->n_xdep + threads - 1) / threads, 4096);
+  k_pack_xdep<<<dim3(bx, n_scen), threads, 0, st>>>(vals_dev, p->d_xdep, p->n_xdep, p->view.n_vals, packed_dev);
+  p->launches++;
+  CU(cudaGetLastError());
+  return GELATO_OK;
+}
+
+int gelato_jacobian_template(GelatoPlan* p, double* vals, int32_t n_scen) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!vals) return fail(GELATO_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(p->device));
+  const size_t nv = (size_t)p->view.n_vals;
+  if (p->vals_template_sstride) {
+    CU(cudaMemcpy(vals, p->vals_template, (size_t)n_scen * nv * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    CU(cudaMemcpy(vals, p->vals_template, nv * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int s = 1; s < n_scen; s++) memcpy(vals + (size_t)s * nv, vals, nv * sizeof(double));
+  }
+  return GELATO_OK;
+}
+
+int gelato_set_host_threads(GelatoPlan* p, int32_t n) {
+  if (!p || n < 0) return fail(GELATO_ERR_ARG, "bad thread count");
+  p->host_threads = n;
+  return GELATO_OK;
+}
+
+static void scatter_scenarios(const int64_t* idx, long long n_xdep, const double* packed, double* vals,
+                              long long n_vals, int s0, int s1) {
+  for (int s = s0; s < s1; s++) {
+    const double* src = packed + (size_t)s * n_xdep;
+    double* dst = vals + (size_t)s * n_vals;
+    for (long long i = 0; i < n_xdep; i++) dst[idx[i]] = src[i];
+  }
+}
+
+int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!x || !vals) return fail(GELATO_ERR_ARG, "null buffer");
+  if (!p->d_xdep) return fail(GELATO_ERR_ARG, "the plan was created without xdep_idx");
+  if ((rc = ensure_staging(p, n_scen))) return rc;
+  const PlanView& v = p->view;
+  const long long nx = p->n_xdep;
+  if ((size_t)n_scen > p->cap_pack) {
+    if (p->d_pack) cudaFree(p->d_pack);
+    if (p->h_pack) cudaFreeHost(p->h_pack);
+    p->d_pack = p->h_pack = nullptr;
+    p->cap_pack = 0;
+    CU(cudaMalloc(&p->d_pack, (size_t)n_scen * nx * sizeof(double)));
+    CU(cudaMallocHost(&p->h_pack, (size_t)n_scen * nx * sizeof(double)));
+    p->cap_pack = n_scen;
+  }
+  const size_t nxin = (size_t)n_scen * v.n_vars;
+  const double* hx = x;
+  if (!is_pinned(x)) {
+    memcpy(p->h_x, x, nxin * sizeof(double));
+    hx = p->h_x;
+  }
+  CU(cudaMemcpyAsync(p->d_x, hx, nxin * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
+  if ((rc = gelato_pack_xdep_dev(p, p->d_vals, p->d_pack, n_scen, p->stream))) return rc;
+  // device->host in chunks of scenarios, so the host scatter of chunk k overlaps the copy of chunk k+1
+  int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  const long long total = (long long)n_scen * nx;
+  if (total < (1LL << 18)) threads = 1;
+  threads = std::min(threads, (int)n_scen);
+  const int n_chunks = (n_scen >= 4 * threads && threads > 1) ? 4 : 1;
+  while ((int)p->chunk_ev.size() < n_chunks) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->chunk_ev.push_back(e);
+  }
+  std::vector<int> bounds(n_chunks + 1);
+  for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n_scen * c / n_chunks);
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t off = (size_t)bounds[c] * nx, cnt = (size_t)(bounds[c + 1] - bounds[c]) * nx;
+    CU(cudaMemcpyAsync(p->h_pack + off, p->d_pack + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaEventRecord(p->chunk_ev[c], p->stream));
+  }
+  const int64_t* idx = p->h_xdep.data();
+  for (int c = 0; c < n_chunks; c++) {
+    CU(cudaEventSynchronize(p->chunk_ev[c]));
+    const int s0 = bounds[c], s1 = bounds[c + 1];
+    if (threads == 1) {
+      scatter_scenarios(idx, nx, p->h_pack, vals, v.n_vals, s0, s1);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; t++) {
+        const int a = s0 + (int)((long long)(s1 - s0) * t / threads), b = s0 + (int)((long long)(s1 - s0) * (t + 1) / threads);
+        if (a < b) pool.emplace_back(scatter_scenarios, idx, nx, p->h_pack, vals, v.n_vals, a, b);
+      }
+      for (auto& th : pool) th.join();
+    }
+  }
+  return GELATO_OK;
+}
+
 int gelato_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(GELATO_ERR_ARG, "null");
   CU(cudaMallocHost(out, bytes));
@@ -399,11 +538,9 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
   CU(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < reps; i++) {
     if (which == 0) {
-      dim3 grid(p->n_res_blocks, n_scen);
-      k_residuals<<<grid, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, x_dev, out_dev);
+      k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, x_dev, out_dev);
     } else {
-      dim3 grid(p->n_jac_blocks, n_scen);
-      k_jacobian<<<grid, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, x_dev, out_dev);
+      k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, n_scen, x_dev, out_dev);
     }
     p->launches++;
   }

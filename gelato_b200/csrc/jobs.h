@@ -105,6 +105,12 @@ P_HD double residue_n(double x, double dx, int n) {
   return x;
 }
 
+/* num / dx for the finite-difference quotients (dx > 0, checked at plan creation).  Many
+ * quotients have an exactly zero numerator (a column that does not move an output); IEEE gives
+ * 0/dx = 0 with the numerator's sign, and saying so skips the division's slow path, which the
+ * GPU's software FP64 division takes for zero numerators (ncu r01b: 8 % of all instructions). */
+P_HD double fd_div(double num, double dx) { return num == 0.0 ? num : num / dx; }
+
 P_HD Units scen_units(const PlanView& P, int scen) {
   Units u = P.un;
   if (P.unit_mass_scen) u.mass = P.unit_mass_scen[scen];
@@ -242,7 +248,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   /* ---- velocity dynamics: -(f_p - f_c)/dx*(tf-to)*unit_t/2 (con_dynamics.py:372) ---- */
   if (lane >= 1 && lane <= 11 && !(lane >= 5 && lane <= 7 && !air_fd)) {
     double rh[3];
-    for (int k = 0; k < 3; k++) rh[k] = -(fl[k] - fc[k]) / dx * dt * ut / 2.0;
+    for (int k = 0; k < 3; k++) rh[k] = fd_div(-(fl[k] - fc[k]), dx) * dt * ut / 2.0;
     if (lane == 1) {
       for (int k = 0; k < 3; k++) vals[sj[GS_JV_MASS] + 3LL * j + k] = rh[k];
     } else if (lane <= 4) {
@@ -263,7 +269,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
     if (air_fd) { /* :454-465 */
       const double to_p = to + dx;
       for (int k = 0; k < 3; k++)
-        vals[sj[GS_JV_T] + 3LL * j + k] = -(fl[k] * (tf - to_p) - fc[k] * dt) / dx * ut / 2.0;
+        vals[sj[GS_JV_T] + 3LL * j + k] = fd_div(-(fl[k] * (tf - to_p) - fc[k] * dt), dx) * ut / 2.0;
     } else { /* :478-480 */
       for (int k = 0; k < 3; k++) {
         const double rh_to = fc[k] * ut / 2.0;
@@ -275,7 +281,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   if (lane == 13 && air_fd) { /* :466-477 */
     const double tf_p = tf + dx;
     for (int k = 0; k < 3; k++)
-      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -(fl[k] * (tf_p - to) - fc[k] * dt) / dx * ut / 2.0;
+      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = fd_div(-(fl[k] * (tf_p - to) - fc[k] * dt), dx) * ut / 2.0;
   }
   /* ---- position dynamics (analytic, depends on x through vel and t): :180-195 ---- */
   if (lane == 14) {
@@ -291,7 +297,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   if (!hold) {
     if (lane >= 1 && lane <= 6) {
       double rh[4];
-      for (int a = 0; a < 4; a++) rh[a] = -(ql[a] - qc[a]) / dx * dt * ut / 2.0;
+      for (int a = 0; a < 4; a++) rh[a] = fd_div(-(ql[a] - qc[a]), dx) * dt * ut / 2.0;
       if (lane <= 4) {
         const int kk = lane - 1; /* submat_quat[4j+a, 4(j+1)+kk] += rh[a] */
         for (int a = 0; a < 4; a++) {
@@ -315,9 +321,9 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
 /* all 16 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*7 + var)*4] */
 P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
                             int nthreads, const JacScratch& sm) {
-  for (int item = tid; item < count * 16; item += nthreads) {
-    const int nl = item >> 4, lane = item & 15;
-    if (lane == 15) continue;
+  /* lane-major items: neighbouring threads run the same column's formula on neighbouring nodes */
+  for (int item = tid; item < count * 15; item += nthreads) {
+    const int lane = item / count, nl = item - lane * count;
     const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
     const double* fc = sm.f + (nl * 14) * 3;
     const double* qc = sm.q + (nl * 7) * 4;
@@ -671,15 +677,14 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
                        P.aero_f64[job * GA_F64_COLS + GA_LIMIT];
     sm.f[(nl * 14 + lane) * 3] = val;
   } else {
-    for (int item = tid; item < count * 16; item += GJ_THREADS) {
-      const int nl = item >> 4, lane = item & 15;
-      if (lane == 0 || lane > 12) continue;
+    for (int item = tid; item < count * 12; item += GJ_THREADS) {
+      const int lane = 1 + item / count, nl = item % count;
       const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
       const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
       const int64_t* aj = P.aero_i64 + job * GA_I64_COLS;
       const int kind = ai[GA_KIND], nk = ai[GA_NK];
       if (kind == 1 && lane >= 7 && lane <= 10) continue;
-      const double gval = -((sm.f[(nl * 14 + lane) * 3] - sm.f[(nl * 14) * 3]) / dx); /* -dfdx (con_aero.py:439-461) */
+      const double gval = -fd_div(sm.f[(nl * 14 + lane) * 3] - sm.f[(nl * 14) * 3], dx); /* -dfdx (con_aero.py:439-461) */
       if (lane <= 3) vals[aj[GA_J_POS] + (long long)(lane - 1) * nk + r] = gval;
       else if (lane <= 6) vals[aj[GA_J_VEL] + (long long)(lane - 4) * nk + r] = gval;
       else if (lane <= 10) vals[aj[GA_J_QUAT] + (long long)(lane - 7) * nk + r] = gval;
@@ -839,15 +844,15 @@ P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, cons
     const int nrow = ei[GE_NROW];
     const int64_t base = (lane <= 3) ? ej[GE_J_POS] + (long long)(lane - 1) * nrow
                                      : ej[GE_J_VEL] + (long long)(lane - 4) * nrow;
-    for (int r = 0; r < nrow; r++) vals[base + r] = (sm.f[3 * tid + r] - sm.f[3 * c + r]) / dx;
+    for (int r = 0; r < nrow; r++) vals[base + r] = fd_div(sm.f[3 * tid + r] - sm.f[3 * c + r], dx);
     return;
   }
   if (type == GE_USER_PERIGEE) { /* aux tail: fd[6] then background[6] */
-    vals[ej[GE_J_POS] + (lane - 1)] = (sm.f[3 * tid] - sm.f[3 * c]) / dx;
+    vals[ej[GE_J_POS] + (lane - 1)] = fd_div(sm.f[3 * tid] - sm.f[3 * c], dx);
     return;
   }
   const int comp = ei[GE_COMP], form = ei[GE_FORM];
-  const double gfd = (sm.f[3 * tid + comp] - sm.f[3 * c + comp]) / dx;
+  const double gfd = fd_div(sm.f[3 * tid + comp] - sm.f[3 * c + comp], dx);
   const double val = evt_form_grad(form, gfd, ef[GE_REF], ef[GE_DEN]);
   if (type == GE_IIP) {
     if (lane == 7) vals[ej[GE_J_T]] = val;

@@ -16,7 +16,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libgelato_b200.so")
+# GELATO_B200_LIB: an alternative build of the same library (kernel tuning experiments, tools/ab_bench.sh)
+LIB_PATH = os.environ.get("GELATO_B200_LIB") or os.path.join(CSRC, "libgelato_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [
@@ -49,6 +50,7 @@ class PlanDesc(ctypes.Structure):
         ("n_aero", ctypes.c_int32), ("aero_i32", _pi32), ("aero_i64", _pi64), ("aero_f64", _pd), ("rc_aero", _pu8),
         ("n_evt", ctypes.c_int32), ("evt_i32", _pi32), ("evt_i64", _pi64), ("evt_f64", _pd),
         ("vals_template", _pd),
+        ("xdep_idx", _pi64), ("n_xdep", ctypes.c_int64),
     ]
 
 
@@ -102,6 +104,9 @@ def make_desc(plan):
     d.evt_i64 = _ptr(c(plan.evt_i64, np.int64), _pi64)
     d.evt_f64 = _ptr(c(plan.evt_f64, np.float64), _pd)
     d.vals_template = _ptr(c(plan.vals_template, np.float64), _pd)
+    xdep = c(plan.xdep_index(), np.int64)
+    d.xdep_idx = _ptr(xdep, _pi64)
+    d.n_xdep = xdep.size
     return d, keep
 
 
@@ -131,9 +136,13 @@ def make_scenario_desc(plans):
     return sc, keep
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/gelato_b200.cu for sm_100a into csrc/libgelato_b200.so (in tree)."""
+def build_library(force=False, verbose=False, out=None, extra=()):
+    """Compile csrc/gelato_b200.cu for sm_100a into csrc/libgelato_b200.so (in tree).
+    `out` / `extra`: another output path and extra nvcc flags (tuning variants)."""
     src = os.path.join(CSRC, "gelato_b200.cu")
+    if out is not None:
+        subprocess.check_call(["nvcc"] + NVCC_FLAGS + list(extra) + ["-o", out, src])
+        return out
     deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".inc"))]
     deps.append(os.path.join(INCLUDE, "gelato_b200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(f) for f in deps):
@@ -175,6 +184,12 @@ def load_library():
     L.gelato_eval_residuals_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_eval_jacobian_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_fill_template.argtypes = [vp, vp, ctypes.c_int32, vp]
+    L.gelato_plan_n_xdep.argtypes = [vp]
+    L.gelato_plan_n_xdep.restype = ctypes.c_int64
+    L.gelato_jacobian_template.argtypes = [vp, _pd, ctypes.c_int32]
+    L.gelato_eval_jacobian_update.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_set_host_threads.argtypes = [vp, ctypes.c_int32]
+    L.gelato_pack_xdep_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.gelato_host_free.argtypes = [vp]
     L.gelato_time_kernel.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int,
@@ -189,7 +204,9 @@ EXPORTS = (
     "gelato_last_error gelato_device_count gelato_plan_create gelato_plan_set_scenarios gelato_plan_destroy "
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
-    "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free"
+    "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
+    "gelato_plan_n_xdep gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_pack_xdep_dev"
 ).split()
 
 
@@ -257,6 +274,25 @@ class Engine:
         _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
         return v if n_scen == 1 else v.reshape(n_scen, self.n_vals)
 
+    # ---- update mode: one persistent host buffer per batch, only x-dependent slots cross PCIe ----
+    def jacobian_template(self, out, n_scen=1):
+        """Fill out[n_scen * n_vals] with the constant Jacobian slots (once per buffer)."""
+        _check(self.L, self.L.gelato_jacobian_template(self.h, _ptr(out, _pd), n_scen), "gelato_jacobian_template")
+        return out
+
+    def eval_jacobian_update(self, x, out, n_scen=1):
+        """Rewrite the x-dependent slots of `out` (a buffer initialised by jacobian_template or
+        holding an earlier result); afterwards `out` equals what eval_jacobian returns."""
+        x = self._x(x, n_scen)
+        if out.size != n_scen * self.n_vals:
+            raise ValueError("out has %d entries, expected %d x %d" % (out.size, n_scen, self.n_vals))
+        _check(self.L, self.L.gelato_eval_jacobian_update(self.h, _ptr(x, _pd), _ptr(out, _pd), n_scen),
+               "gelato_eval_jacobian_update")
+        return out if n_scen == 1 else out.reshape(n_scen, self.n_vals)
+
+    def set_host_threads(self, n):
+        _check(self.L, self.L.gelato_set_host_threads(self.h, int(n)), "gelato_set_host_threads")
+
     # ---- device-resident calls (raw device pointers, e.g. torch .data_ptr()) ----
     def eval_residuals_dev(self, x_ptr, g_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_residuals_dev(self.h, x_ptr, g_ptr, n_scen, stream), "gelato_eval_residuals_dev")
@@ -267,6 +303,9 @@ class Engine:
 
     def eval_jacobian_dev(self, x_ptr, vals_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_jacobian_dev(self.h, x_ptr, vals_ptr, n_scen, stream), "gelato_eval_jacobian_dev")
+
+    def pack_xdep_dev(self, vals_ptr, packed_ptr, n_scen=1, stream=None):
+        _check(self.L, self.L.gelato_pack_xdep_dev(self.h, vals_ptr, packed_ptr, n_scen, stream), "gelato_pack_xdep_dev")
 
     def time_kernel(self, which, x_ptr, out_ptr, n_scen=1, reps=10):
         """Average duration [ms] of `reps` back-to-back launches of one kernel

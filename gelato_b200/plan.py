@@ -861,22 +861,67 @@ class CompiledPlan:
                 "noair_nodes": self.N - n_air, "free_nodes": n_free, "aero_rows": sum(aero_rows.values()),
                 "aero_jac_evals": aero_jac, "evt_jobs": len(self._evt), "evt_jac_evals": evt_jac}
 
+    def xdep_index(self):
+        """Sorted positions in `vals` of the slots that depend on x -- exactly what the
+        Jacobian kernel rewrites on every call (jobs.h: dyn_scatter, aero_phase, evt_jac_phase2);
+        the other slots are constants / D entries written once from `vals_template`.
+        Lets a batched driver move only these values over PCIe (engine: update mode)."""
+        if getattr(self, "_xdep", None) is not None:
+            return self._xdep
+        parts = []
+
+        def run(start, length):
+            parts.append(np.arange(start, start + length, dtype=np.int64))
+
+        for i in range(self.S):
+            n = int(self.sec_i32[i, GS_N])
+            fl = int(self.sec_i32[i, GS_FLAGS])
+            sj = self.sec_i64[i]
+            j = np.arange(n, dtype=np.int64)
+            run(sj[GS_JP_VEL], 3 * n)
+            run(sj[GS_JP_T], 6 * n)
+            run(sj[GS_JV_MASS], 3 * n)
+            run(sj[GS_JV_POS], 9 * n)
+            run(sj[GS_JV_QUAT], 12 * n)
+            run(sj[GS_JV_T], 6 * n)
+            if fl & GSF_AIR_FD:  # node-diagonal of the 9 dense n x (n+1) sub-blocks
+                for b in range(9):
+                    parts.append(sj[GS_JV_VEL] + b * n * (n + 1) + j * (n + 1) + (j + 1))
+            if not fl & GSF_HOLD:
+                for a in range(4):
+                    for kk in range(4):
+                        parts.append(sj[GS_JQ_QUAT] + (4 * j + a) * (4 * (n + 1)) + 4 * (j + 1) + kk)
+                run(sj[GS_JQ_U], 8 * n)
+                run(sj[GS_JQ_T], 8 * n)
+        for job in self._aero:
+            kind, nk = job["i32"][GA_KIND], job["i32"][GA_NK]
+            run(job["i64"][GA_J_POS], 3 * nk)
+            run(job["i64"][GA_J_VEL], 3 * nk)
+            if kind != 1:
+                run(job["i64"][GA_J_QUAT], 4 * nk)
+            run(job["i64"][GA_J_T], 2 * nk)
+        for job in self._evt:
+            typ, nrow = job["i32"][GE_TYPE], job["i32"][GE_NROW]
+            if typ == GE_TERM:
+                run(job["i64"][GE_J_POS], 3 * nrow)
+                run(job["i64"][GE_J_VEL], 3 * nrow)
+            elif typ == GE_USER_PERIGEE:
+                run(job["i64"][GE_J_POS], AUX_PER_USER)
+            else:
+                run(job["i64"][GE_J_POS], 3)
+                if typ == GE_IIP:
+                    run(job["i64"][GE_J_VEL], 3)
+                run(job["i64"][GE_J_T], 1)
+        idx = np.sort(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.int64)
+        assert idx.size == np.unique(idx).size, "an x-dependent Jacobian slot is listed twice"
+        self._xdep = idx
+        return idx
+
     @property
     def n_xdep(self):
         """Jacobian slots that depend on x (what the Jacobian kernel writes each call);
         the other n_vals - n_xdep slots are constants / D entries set once."""
-        cnt = 0
-        for i in range(self.S):
-            n = self._sec[i][4]
-            fl = int(self.sec_i32[i, GS_FLAGS])
-            cnt += 9 * n + 30 * n + (9 * n if fl & GSF_AIR_FD else 0)
-            cnt += 0 if fl & GSF_HOLD else 32 * n
-        for j in self._aero:
-            cnt += j["i32"][2] * (12 if j["i32"][0] != 1 else 8)
-        per = {GE_LLH: 4, GE_IIP: 7, GE_ANT: 4, GE_USER_PERIGEE: AUX_PER_USER}
-        for j in self._evt:
-            cnt += 6 * j["i32"][GE_NROW] if j["i32"][0] == GE_TERM else per[j["i32"][0]]
-        return cnt
+        return int(self.xdep_index().size)
 
     def split_residuals(self, g):
         """g[n_rows] -> the reference's `funcs` dict (views into g)."""

@@ -146,6 +146,10 @@ typedef struct GelatoPlanDesc {
   const double* evt_f64;
   /* Jacobian template: constants and D entries, length n_vals */
   const double* vals_template;
+  /* sorted positions in vals of the x-dependent slots (what the Jacobian kernel rewrites on
+   * every call); may be NULL, then the update-mode entry points are unavailable */
+  const int64_t* xdep_idx;
+  int64_t n_xdep;
 } GelatoPlanDesc;
 
 /* per-scenario overrides for batched evaluation (NULL members = shared) */
@@ -180,6 +184,20 @@ int64_t gelato_plan_launch_count(const GelatoPlan* plan);
 int gelato_eval_residuals(GelatoPlan* plan, const double* x, double* g, int32_t n_scen);
 int gelato_eval_jacobian(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
 
+/* Update mode for drivers that keep one host Jacobian buffer per scenario batch alive across
+ * calls (a batched solve): most of vals never changes (D entries, +-1, unit constants -- 87 % of
+ * the slots at 1 000 nodes), so only the x-dependent slots cross PCIe.
+ *   gelato_jacobian_template     fills vals[n_scen][n_vals] with the constant slots (once per buffer);
+ *   gelato_eval_jacobian_update  runs the Jacobian kernel, packs the x-dependent slots on the
+ *                                device, copies the packed values back and scatters them into
+ *                                vals; every other slot of vals is left as it was.
+ * After the two calls vals holds exactly what gelato_eval_jacobian returns. */
+int64_t gelato_plan_n_xdep(const GelatoPlan* plan);
+int gelato_jacobian_template(GelatoPlan* plan, double* vals, int32_t n_scen);
+int gelato_eval_jacobian_update(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
+/* host threads used by the scatter of update mode (default: min(16, hardware threads)) */
+int gelato_set_host_threads(GelatoPlan* plan, int32_t n_threads);
+
 int gelato_host_alloc(size_t bytes, void** out);
 int gelato_host_free(void* ptr);
 
@@ -191,6 +209,8 @@ int gelato_host_free(void* ptr);
 int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
 int gelato_fill_template(GelatoPlan* plan, double* vals_dev, int32_t n_scen, void* stream);
 int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
+/* packed_dev[n_scen][n_xdep] = the x-dependent slots of vals_dev[n_scen][n_vals], in ascending slot order */
+int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream);
 
 /* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen
  * kernel (0 residuals, 1 jacobian) on device-resident buffers and returns the

@@ -145,3 +145,21 @@ def test_emulated_kernels_match_reference_golden_within_fd_noise(name):
         np.testing.assert_allclose(v, npz["%s/f/%s" % (name, k)], rtol=1e-10, atol=atol, err_msg=k)
     s = P.split_jacobian(E.eval_jacobian(xv), key_order=list(x.keys()))
     helpers.assert_sens_within_noise(s, npz, name)
+
+
+@pytest.mark.parametrize("variant,user", [("example", True), ("all_aero", True), ("waypoints", True), ("neg_area", True),
+                                          ("fuel_inclination", True), ("bare", False)])
+def test_xdep_index_is_exactly_what_the_jacobian_kernel_writes(variant, user):
+    """CompiledPlan.xdep_index() drives the sparse device->host update of the batched
+    path: it must list exactly the slots the kernel code writes (the emulator starts
+    from the template; a template of NaN exposes every slot it touches)."""
+    p, u, c, x0, O, P = _setup(variant, 2, user=user)
+    keep = P.vals_template
+    try:
+        P.vals_template = np.full_like(keep, np.nan)
+        vals = emu_binding.Emulator(P).eval_jacobian(problem.xdict_to_vector(helpers.perturbed(x0)))
+    finally:
+        P.vals_template = keep
+    written = np.flatnonzero(~np.isnan(vals))
+    assert np.array_equal(written, P.xdep_index())
+    assert P.n_xdep == written.size

@@ -159,6 +159,41 @@ def test_device_resident_entry_points_and_pinned_buffers():
     prob.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_update_mode_equals_full_jacobian(pinned):
+    """gelato_jacobian_template + gelato_eval_jacobian_update (only the x-dependent slots cross
+    PCIe) leave the host buffer bit-identical to the full-copy call, call after call."""
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    scen = scenarios.disperse(inp, 6, seed=3)
+    plans, xs = [], []
+    for si in scen:
+        p, u, c, x0 = problem.problem_from_inputs(si, coord=Lg.coordinate_c, factor=2)
+        plans.append(helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c))
+        xs.append(x0)
+    E = engine.Engine(plans[0], scenario_plans=plans)
+    E.set_host_threads(3)
+    P = plans[0]
+    assert E.L.gelato_plan_n_xdep(E.h) == P.n_xdep and 0 < P.n_xdep < P.n_vals
+    holder = engine.PinnedArray(6 * P.n_vals) if pinned else None
+    buf = holder.array if pinned else np.empty(6 * P.n_vals)
+    buf[:] = np.nan
+    E.jacobian_template(buf, 6)
+    assert np.array_equal(buf.reshape(6, -1), np.stack([pl.vals_template for pl in plans]))
+    for seed in (1, 2, 3):
+        X = np.stack([problem.xdict_to_vector(helpers.perturbed(x, seed=seed + 10 * k)) for k, x in enumerate(xs)])
+        want = E.eval_jacobian(X, n_scen=6).copy()
+        got = E.eval_jacobian_update(X, buf, n_scen=6)
+        assert np.array_equal(got, want)
+    # a smaller batch through the same plan, and the single-scenario path
+    one = np.empty(P.n_vals)
+    E.jacobian_template(one, 1)
+    assert np.array_equal(E.eval_jacobian_update(X[0], one, 1), want[0])
+    if holder is not None:
+        holder.free()
+    E.close()
+
+
 def test_repeated_calls_are_deterministic_and_template_survives():
     prob, O, x0 = _problem("example", 2)
     E = prob.engine
