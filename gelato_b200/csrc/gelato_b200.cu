@@ -25,7 +25,7 @@
 // kernels
 // ---------------------------------------------------------------------------
 #ifndef GJ_MIN_BLOCKS
-#define GJ_MIN_BLOCKS 2
+#define GJ_MIN_BLOCKS 4 /* 64 registers: 32 warps per SM; measured best of 2..5 (profiles/r01d_ab.txt) */
 #endif
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Where the end-to-end time of one batched step goes (run on the GPU box)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+from gelato_b200 import engine  # noqa: E402
+
+
+def t(fn, reps=10):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    plans, X, _ = bench.load_workload(15, B, 0, B)
+    P = plans[0]
+    E = engine.Engine(P, scenario_plans=plans)
+    px, pg, pv = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * P.n_vals)
+    px.array[:] = X.ravel()
+    E.jacobian_template(pv.array, B)
+    print("B=%d n_vals=%d n_xdep=%d cores=%d" % (B, P.n_vals, P.n_xdep, os.cpu_count()))
+    print("residuals host call      %.3f ms" % t(lambda: E.eval_residuals(px.array, B, out=pg.array)))
+    print("jacobian full copy       %.3f ms" % t(lambda: E.eval_jacobian(px.array, B, out=pv.array)))
+    for th in (1, 2, 4, 8, 16, 32):
+        E.set_host_threads(th)
+        print("jacobian update, %2d thr   %.3f ms" % (th, t(lambda: E.eval_jacobian_update(px.array, pv.array, B))))
+    idx = P.xdep_index()
+    packed = np.random.rand(B, idx.size)
+    big = pv.array.reshape(B, -1)
+
+    def np_scatter():
+        big[:, idx] = packed
+    print("numpy fancy scatter      %.3f ms" % t(np_scatter, 3))
+
+
+if __name__ == "__main__":
+    main()
