@@ -57,9 +57,16 @@ k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const int
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* g = g_all + (size_t)scen * P.n_rows;
+  const bool dyn = bt[BT_ROLE] == BR_DYN;
+  if (dyn) {
+    res_block_phase0(P, scen, bt, x, threadIdx.x, sm);
+    __syncthreads();
+  }
   res_block_phase1(P, scen, bt, x, g, threadIdx.x, sm);
-  __syncthreads();
-  res_block_phase2(P, scen, bt, x, g, threadIdx.x, GR_THREADS, sm);
+  if (dyn) {
+    __syncthreads();
+    res_block_phase2(P, scen, bt, x, g, threadIdx.x, GR_THREADS, sm);
+  }
 }
 
 // packed[scen][i] = vals[scen][idx[i]]: the x-dependent slots, gathered for the PCIe copy of update mode

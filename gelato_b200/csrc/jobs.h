@@ -37,6 +37,13 @@
 #define GJ_Q_BASE 224    /* threads [224, 256): quaternion kinematics, one node each */
 #define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
 
+static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS >= GJ_NODES * NPV, "position items need whole warps");
+static_assert(GJ_B_THREADS % 32 == 0 && GJ_B_THREADS >= GJ_NODES * NRV, "rotation items need whole warps");
+static_assert(GJ_A_THREADS + GJ_B_THREADS == GJ_Q_BASE && GJ_THREADS - GJ_Q_BASE >= GN_NODES, "phase-0 thread map");
+static_assert(GJ_NODES * 14 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS && GN_NODES * NPV <= GN_A_THREADS, "one pass");
+static_assert(GN_A_THREADS <= GJ_Q_BASE && GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS, "lane maps");
+static_assert(GR_THREADS == 2 * GR_NODES, "residual phase 0 uses two threads per node");
+
 /* block roles */
 enum { BR_DYN_AIR = 0, BR_DYN_NOAIR, BR_DYN_GEN, BR_AERO, BR_EVT, BR_LIN, BR_DYN /* residual kernel */ };
 /* block table columns */
@@ -93,6 +100,8 @@ struct JacScratch {
 struct ResScratch {
   double f[GR_NODES][3];
   double q[GR_NODES][4];
+  double pp[GR_NODES][PP_COLS];
+  double rq[GR_NODES][RQ_COLS];
 };
 
 /* fl(fl(x + dx) - dx): what a perturb/restore cycle leaves behind */
@@ -490,17 +499,39 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
 
 /* ========================================================================= */
 /* Residual kernel, DYN role: GR_NODES consecutive nodes per block.           */
-/*   phase 1: thread nl evaluates the right-hand sides of its node            */
+/*   phase 0: two threads per node: position part | rotation part             */
+/*   phase 1: thread nl finishes the right-hand sides of its node             */
 /*   phase 2: all threads sweep the (node, state column) items: D.X - rhs     */
 /* reference: con_dynamics.py:34-63, 116-152, 216-289, 499-533                */
 /* ========================================================================= */
+/* phase 0: two threads per air node -- the position part and the rotation part of the
+ * right-hand side do not depend on each other (the kernel is latency bound: one right-hand
+ * side is a ~5 000-instruction dependent chain, splitting it halves the chain);
+ * phase 1: one thread per node finishes its right-hand sides. */
+P_HD void dyn_res_phase0(const PlanView& P, int scen, const double* x, int g0, int count, int tid, ResScratch& sm) {
+  const int nl = tid >> 1, half = tid & 1;
+  if (nl >= count) return;
+  const NodeRef nr = node_ref(P, g0 + nl);
+  if (!(nr.flags & GSF_AIR)) return;
+  const Units un = scen_units(P, scen);
+  const int row = nr.row;
+  const double px = x[P.off_pos + 3 * row] * un.pos, py = x[P.off_pos + 3 * row + 1] * un.pos,
+               pz = x[P.off_pos + 3 * row + 2] * un.pos;
+  if (half == 0) {
+    const Tables tb = scen_tables(P, scen);
+    pos_part(px, py, pz, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND, sm.pp[nl]);
+  } else {
+    const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
+    rotq_part(px, py, pz, time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf), sm.rq[nl]);
+  }
+}
+
 P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, int count, int tid, ResScratch& sm) {
   if (tid >= count) return;
   const NodeRef nr = node_ref(P, g0 + tid);
   const int row = nr.row;
   const Units un = scen_units(P, scen);
   const SecParam sp = sec_param(P, scen, nr.sec);
-  const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double m = x[row];
   const Vec3 p = v3(x[P.off_pos + 3 * row], x[P.off_pos + 3 * row + 1], x[P.off_pos + 3 * row + 2]);
   const Vec3 v = v3(x[P.off_vel + 3 * row], x[P.off_vel + 3 * row + 1], x[P.off_vel + 3 * row + 2]);
@@ -508,8 +539,9 @@ P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, i
                     x[P.off_quat + 4 * row + 3]);
   Vec3 f;
   if (nr.flags & GSF_AIR) {
-    const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
-    f = rhs_velocity_air(m, p, v, q, tn, sp, un, scen_tables(P, scen));
+    double rp[RP_COLS];
+    rot_wind(sm.rq[tid], sm.pp[tid][PP_WIND_N], sm.pp[tid][PP_WIND_E], rp);
+    f = rhs_velocity_air_col(m, p, v, q, sm.pp[tid], rp, sp, un, scen_tables(P, scen));
   } else {
     f = rhs_velocity_noair(m, p, q, sp, un);
   }
@@ -878,7 +910,7 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 
 /* ========================================================================= */
 /* Block dispatch.  Jacobian blocks run GJ_PHASES phases with a block barrier  */
-/* between them; residual blocks run two.                                      */
+/* between them; residual blocks run three (only the dynamics role uses 0, 2).  */
 /* ========================================================================= */
 P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, int tid,
                           int phase, JacScratch& sm) {
@@ -900,6 +932,9 @@ P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const 
 /* roles whose phases 1 and 2 are empty (the kernel skips those barriers) */
 P_HD bool jac_role_two_phase(int role) { return role == BR_EVT || role == BR_DYN_GEN; }
 
+P_HD void res_block_phase0(const PlanView& P, int scen, const int32_t* bt, const double* x, int tid, ResScratch& sm) {
+  if (bt[BT_ROLE] == BR_DYN) dyn_res_phase0(P, scen, x, bt[BT_START], bt[BT_COUNT], tid, sm);
+}
 P_HD void res_block_phase1(const PlanView& P, int scen, const int32_t* bt, const double* x, double* g, int tid,
                            ResScratch& sm) {
   switch (bt[BT_ROLE]) {

@@ -25,12 +25,26 @@ _I = ctypes.c_int
 _P = ctypes.POINTER(ctypes.c_double)
 
 
+_REF_DIR = os.path.join(_HERE, "_ref")
+REF_LIB = os.path.join(_REF_DIR, "libref_leaves.so")
+REF_SRC = os.environ.get("GELATO_REFERENCE_SRC", "/root/reference/src")
+
+
 def build(force=False):
-    """Compile both oracle flavours with the committed Makefile."""
+    """Compile both oracle flavours with the committed Makefile and, where the reference
+    tree is present (the build container; never the GPU box), the reference's own C++
+    sources against oracle/ref_shim into oracle/_ref/ (flavour "ref")."""
     libs = [os.path.join(_BUILD, "liboracle_%s.so" % f) for f in ("libm", "gmath")]
     if force or not all(os.path.exists(p) for p in libs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    if os.path.isdir(REF_SRC) and (force or not os.path.exists(REF_LIB)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REF_SRC=" + REF_SRC] + (["-B"] if force else []))
     return libs
+
+
+def ref_available():
+    """True when oracle/_ref/libref_leaves.so (the shim-compiled reference C++) exists."""
+    return os.path.exists(REF_LIB)
 
 
 def _a(x, shape=None):
@@ -45,13 +59,20 @@ def _p(arr):
 
 
 class OracleLeaves:
-    """One flavour ("libm" or "gmath") of the leaf library."""
+    """One flavour of the leaf library: "libm" / "gmath" = the hand-written restatement
+    (oracle_leaves.cpp) on glibc / gmath elementary functions; "ref" = the reference's own
+    C++ sources compiled against oracle/ref_shim (oracle/_ref/, glibc)."""
 
     def __init__(self, flavour="libm"):
-        assert flavour in ("libm", "gmath")
+        assert flavour in ("libm", "gmath", "ref")
         build()
         self.flavour = flavour
-        self.lib = ctypes.CDLL(os.path.join(_BUILD, "liboracle_%s.so" % flavour))
+        if flavour == "ref":
+            if not ref_available():
+                raise FileNotFoundError("%s: build it where /root/reference exists (make -C oracle ref)" % REF_LIB)
+            self.lib = ctypes.CDLL(REF_LIB)
+        else:
+            self.lib = ctypes.CDLL(os.path.join(_BUILD, "liboracle_%s.so" % flavour))
         L = self.lib
         for name in (
             "o_geopotential_altitude o_airtemperature_at o_airpressure_at o_airdensity_at "
@@ -69,7 +90,7 @@ class OracleLeaves:
         L.o_distance_vincenty.argtypes = [_D, _D, _D, _D]
         L.o_interp.restype = _D
         L.o_interp.argtypes = [_D, _P, _P, _I]
-        assert L.oracle_flavour() == (1 if flavour == "gmath" else 0)
+        assert L.oracle_flavour() == {"libm": 0, "gmath": 1, "ref": 2}[flavour]
         assert L.oracle_unfused_check() == 1, "oracle built with FP contraction"
         self._make_modules()
 

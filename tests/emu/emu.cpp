@@ -60,6 +60,8 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
     double* g = g_all + (size_t)scen * P.n_rows;
     for (size_t b = 0; b < rb.size() / BT_COLS; b++) {
       const int32_t* bt = rb.data() + b * BT_COLS;
+      memset(&sm, 0xff, sizeof sm);
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase0(P, scen, bt, x, tid, sm);
       for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, scen, bt, x, g, tid, sm);
       for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase2(P, scen, bt, x, g, tid, GR_THREADS, sm);
     }
