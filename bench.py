@@ -19,9 +19,12 @@ one (node x perturbation column): see CompiledPlan.eval_counts / DESIGN.md.
 Multi-GPU: scenarios are independent NLPs; each rank owns `--scenarios` of them
 (weak scaling), no data-path collective (DESIGN.md "multi-GPU").
 
-`--impl reference` times the CPU path instead (the oracle port of the
-reference's callbacks: the reference's pybind11/Eigen modules cannot be built in
-this image), one scenario per host core in parallel.
+`--impl reference` times the CPU path instead: the reference's own C++ physics
+(oracle/_ref: /root/reference/src compiled against oracle/ref_shim in the build
+container; falls back to the bit-identical oracle restatement if that file is
+absent) under oracle/nlp.py, the numpy port of the reference's lib/con_*.py
+(the reference's Python files themselves do not travel to the GPU box), one
+scenario per host core in parallel.
 """
 import argparse
 import json
@@ -136,8 +139,9 @@ def _cpu_worker(args):
 
     plans, X, probs = load_workload(factor, n_total, k, 1)
     p, u, c, x = probs[0]
-    L = leaves.get("libm")
-    O = nlp.OracleNLP(p, u, c, "libm", "numpy", user_eq=user_builtin.perigee_ratio_at(L, USER_EVENT))
+    flav = cpu_flavour()
+    L = leaves.get(flav)
+    O = nlp.OracleNLP(p, u, c, flav, "numpy", user_eq=user_builtin.perigee_ratio_at(L, USER_EVENT))
     t0 = time.perf_counter()
     for _ in range(reps):
         xa = {key: v.copy() for key, v in x.items()}
@@ -146,14 +150,27 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def cpu_flavour():
+    """Physics leaves of the CPU arm: the reference's own C++ (oracle/_ref, built where the
+    reference tree is mounted and shipped with the snapshot) when present, else the
+    bit-identical hand-written restatement on glibc."""
+    from oracle import leaves
+
+    return "ref" if leaves.ref_available() else "libm"
+
+
+CPU_DESC = {"ref": "the reference's own C++ leaves (oracle/_ref) under oracle/nlp.py, the numpy port of lib/con_*.py",
+            "libm": "oracle/nlp.py port on the oracle's libm leaves"}
+
+
 def cpu_baseline(factor, evals_per_scen, budget_s):
     """One host core, one scenario of the workload, objfunc+sens repeated for ~budget_s."""
     t1 = _cpu_worker((factor, 1, 0, 1))  # also warms imports / builds
     reps = int(max(2, min(50, budget_s / max(t1, 1e-3))))
     dt = _cpu_worker((factor, 1, 0, reps))
     return {"value": evals_per_scen * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d x (objfunc+sens) of 1 scenario of the workload (N=%d nodes), oracle/nlp.py on libm leaves, "
-                      "%.2f s per pair" % (reps, 66 * factor, dt / reps)}
+            "sample": "%d x (objfunc+sens) of 1 scenario of the workload (N=%d nodes), %s, "
+                      "%.2f s per pair" % (reps, 66 * factor, CPU_DESC[cpu_flavour()], dt / reps)}
 
 
 def run_reference(args):
@@ -180,7 +197,7 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = evals_per_scen * cores * steps / dt
     sample = ("each step = objfunc+sens of %d dispersed scenarios of the workload (one per host core, spawn pool), "
-              "oracle/nlp.py port on libm leaves; %d timed steps" % (cores, steps))
+              "%s; %d timed steps" % (cores, CPU_DESC[cpu_flavour()], steps))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

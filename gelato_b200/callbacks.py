@@ -21,9 +21,13 @@ from .plan import GROUPS, VAR_ORDER, CompiledPlan, PerigeeAtEvent  # noqa: F401
 
 
 class GelatoProblem:
-    def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None):
+    def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None,
+                 engine_factory=None):
+        """engine_factory(plan) -> object with eval_residuals / eval_jacobian / close / launches;
+        default: the CUDA engine on `device` (the CPU test tier passes the host emulator of the
+        kernels, tests/emu_binding.py, to exercise this host logic without a GPU)."""
         self.plan = CompiledPlan(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, coord=coord)
-        self.engine = _engine.Engine(self.plan, device=device)
+        self.engine = engine_factory(self.plan) if engine_factory else _engine.Engine(self.plan, device=device)
         self._x = np.empty(self.plan.n_vars)
 
     # -- helpers ---------------------------------------------------------

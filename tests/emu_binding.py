@@ -58,3 +58,22 @@ class Emulator:
         v = np.full(n_scen * self.plan.n_vals, np.nan)
         self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen)
         return v if n_scen == 1 else v.reshape(n_scen, -1)
+
+
+class EmuEngine(Emulator):
+    """The emulator behind the Engine interface GelatoProblem uses (CPU test tier only)."""
+
+    def __init__(self, plan):
+        super().__init__(plan)
+        self.launches = 0
+
+    def eval_residuals(self, x, n_scen=1, out=None):
+        self.launches += 1
+        return super().eval_residuals(x, n_scen)
+
+    def eval_jacobian(self, x, n_scen=1, out=None):
+        self.launches += 1
+        return super().eval_jacobian(x, n_scen)
+
+    def close(self):
+        pass

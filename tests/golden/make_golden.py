@@ -11,9 +11,10 @@ What it writes
                         for each, every `funcs` entry and every Jacobian block returned by
                         the REFERENCE'S OWN Python layer (/root/reference/lib/con_*.py and the
                         objfunc / sens bodies of Trajectory_Optimization.py, imported where
-                        they lie) running on the oracle's libm physics leaves, because the
-                        reference's pybind11/Eigen modules cannot be built here
-                        (/root/reference/CMakeLists.txt:13, no Eigen3).  Also `jn/...`: per Jacobian
+                        they lie) running on the reference's own C++ physics
+                        (/root/reference/src/*.cpp|hpp compiled where they lie against the minimal
+                        Eigen / pybind11 stand-in of oracle/ref_shim -- the image has no Eigen3,
+                        /root/reference/CMakeLists.txt:13 -- and loaded through oracle/leaves.py).  Also `jn/...`: per Jacobian
                         slot, how far the reference's own value moves when every input is nudged
                         by one ulp (8 random draws) -- its finite-difference noise floor.
   example_gmath.npz     the same quantities from oracle/nlp.py with the gmath leaves and
@@ -58,8 +59,10 @@ def main():
     inp = problem.read_inputs(os.path.join(refharness.REF, "example", "example-settings.json"))
     problem.dump_inputs_json(inp, helpers.INPUTS)
 
-    # ---- the reference's own Python layer on libm leaves -----------------
-    L = leaves.get("libm")
+    # ---- the reference's own Python layer on the reference's own C++ leaves (oracle/_ref:
+    #      /root/reference/src compiled against oracle/ref_shim; bit-identical to the oracle's
+    #      libm flavour, tests/test_oracle_vs_refcpp.py) -----------------------------------
+    L = leaves.get("ref")
     pdict, unitdict, condition = refharness.reference_setup(L)
     objfunc, sens = refharness.reference_callbacks(L, pdict, unitdict, condition)
     p, u, c, x0 = helpers.example_problem()
