@@ -164,6 +164,7 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
 extern "C" {
 
 const char* gelato_last_error(void) { return g_err.c_str(); }
+void gelato_set_error_(const char* msg) { g_err = msg ? msg : ""; }  // for leaf_api.cu
 
 int gelato_device_count(void) {
   int n = 0;

@@ -557,10 +557,22 @@ P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, i
   }
 }
 
-/* D.X for one (row of D, state column): acc = fma(D[j][m], X[xa+m], acc), m ascending */
+/* D.X for one (row of D, state column): acc = fma(D[j][m], X[xa+m], acc), m ascending.
+ * The accumulation order is part of the numerical contract; the loads of four
+ * steps are issued together so their latency overlaps. */
 P_HD double dx_dot(const double* Drow, const double* xcol, int stride, int n1) {
   double acc = 0.0;
-  for (int m = 0; m < n1; m++) acc = gm_fma(Drow[m], xcol[(long long)m * stride], acc);
+  int m = 0;
+  for (; m + 4 <= n1; m += 4) {
+    const double d0 = Drow[m], d1 = Drow[m + 1], d2 = Drow[m + 2], d3 = Drow[m + 3];
+    const double x0 = xcol[(long long)m * stride], x1 = xcol[(long long)(m + 1) * stride],
+                 x2 = xcol[(long long)(m + 2) * stride], x3 = xcol[(long long)(m + 3) * stride];
+    acc = gm_fma(d0, x0, acc);
+    acc = gm_fma(d1, x1, acc);
+    acc = gm_fma(d2, x2, acc);
+    acc = gm_fma(d3, x3, acc);
+  }
+  for (; m < n1; m++) acc = gm_fma(Drow[m], xcol[(long long)m * stride], acc);
   return acc;
 }
 
@@ -568,8 +580,9 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
                          int nthreads, const ResScratch& sm) {
   const Units un = scen_units(P, scen);
   const double ut = un.t;
+  /* column-major items: neighbouring threads run the same state column on neighbouring nodes */
   for (int item = tid; item < count * 11; item += nthreads) {
-    const int nl = item / 11, col = item - nl * 11;
+    const int col = item / count, nl = item - col * count;
     const NodeRef nr = node_ref(P, g0 + nl);
     const int32_t* si = nr.si;
     const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;

@@ -1,0 +1,231 @@
+// leaf_api.cu -- batch versions of the reference's pybind11 leaf functions
+// (/root/reference/src/pybind_dynamics.cpp:108-114, pybind_utils.cpp:28-48, pybind_coordinate.cpp:28-78,
+// pybind_IIP.cpp:53-57, pybind_USStandardAtmosphere.cpp:28-35): one kernel launch evaluates a leaf for n
+// nodes, one thread per node, with the device functions the fused kernels use (physics.h).  They serve the
+// callers AROUND the NLP loop that evaluate leaves over whole trajectories (initial guess, result tables)
+// and let tests compare every leaf with the oracle on its own.  Host buffers in, host buffers out.
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gelato_b200.h"
+#include "physics.h"
+
+extern "C" void gelato_set_error_(const char* msg);  // gelato_b200.cu
+
+namespace {
+
+struct DevBuf {
+  std::vector<void*> ptrs;
+  ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  T* in(const T* host, size_t count, cudaError_t& err) {
+    T* d = nullptr;
+    if (err != cudaSuccess || count == 0) return d;
+    err = cudaMalloc(&d, count * sizeof(T));
+    if (err != cudaSuccess) return nullptr;
+    ptrs.push_back(d);
+    err = cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+  }
+  double* out(size_t count, cudaError_t& err) {
+    double* d = nullptr;
+    if (err != cudaSuccess || count == 0) return d;
+    err = cudaMalloc(&d, count * sizeof(double));
+    if (err == cudaSuccess) ptrs.push_back(d);
+    return d;
+  }
+};
+
+int finish(cudaError_t err, double* host_out, const double* dev_out, size_t count) {
+  if (err == cudaSuccess) err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpy(host_out, dev_out, count * sizeof(double), cudaMemcpyDeviceToHost);
+  if (err != cudaSuccess) {
+    gelato_set_error_(cudaGetErrorString(err));
+    return GELATO_ERR_CUDA;
+  }
+  return GELATO_OK;
+}
+
+inline int blocks_for(int n) { return (n + 127) / 128; }
+
+__global__ void k_leaf_dynamics_velocity(int n, const double* mass_e, const double* pos_e, const double* vel_e,
+                                         const double* quat, const double* t, SecParam sp, Units un, Tables tb,
+                                         double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec3 f = rhs_velocity_air(mass_e[i], v3(pos_e[3 * i], pos_e[3 * i + 1], pos_e[3 * i + 2]),
+                            v3(vel_e[3 * i], vel_e[3 * i + 1], vel_e[3 * i + 2]),
+                            q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), t[i], sp, un, tb);
+  out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
+}
+
+__global__ void k_leaf_dynamics_velocity_noair(int n, const double* mass_e, const double* pos_e, const double* quat,
+                                               SecParam sp, Units un, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec3 f = rhs_velocity_noair(mass_e[i], v3(pos_e[3 * i], pos_e[3 * i + 1], pos_e[3 * i + 2]),
+                              q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), sp, un);
+  out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
+}
+
+__global__ void k_leaf_dynamics_quaternion(int n, const double* quat, const double* u_e, double unit_u, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Quat d = rhs_quaternion(q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), u_e[2 * i],
+                          u_e[2 * i + 1], unit_u);
+  out[4 * i] = d.w; out[4 * i + 1] = d.x; out[4 * i + 2] = d.y; out[4 * i + 3] = d.z;
+}
+
+__global__ void k_leaf_aero(int kind, int n, const double* pos, const double* vel, const double* quat,
+                            const double* t, Tables tb, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Quat q = q4(1.0, 0.0, 0.0, 0.0);
+  if (quat) q = q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]);
+  out[i] = aero_quantity(kind, v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]),
+                         v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]), q, t[i], tb);
+}
+
+__global__ void k_leaf_eci2geodetic(int n, const double* pos, const double* t, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec3 g = eci2geodetic_deg(v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), t[i]);
+  out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
+}
+
+__global__ void k_leaf_iip(int n, const double* pos_ecef, const double* vel_ecef, int fill_na, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec3 g = iip_faa_deg(v3(pos_ecef[3 * i], pos_ecef[3 * i + 1], pos_ecef[3 * i + 2]),
+                       v3(vel_ecef[3 * i], vel_ecef[3 * i + 1], vel_ecef[3 * i + 2]));
+  /* pybind_IIP.cpp:38-45: with fill_na = false an all-zero "no solution" becomes NaN */
+  if (!fill_na && g.x == 0.0 && g.y == 0.0 && g.z == 0.0) g.x = g.y = g.z = gm_nan();
+  out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
+}
+
+__global__ void k_leaf_gravity(int n, const double* pos, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec3 g = gravity_eci(v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+  out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
+}
+
+/* out[i][5] = geopotential_altitude(z), airtemperature_at(z), airpressure_at(z), airdensity_at(z),
+ * speed_of_sound(z), each applied to z as given (pybind_USStandardAtmosphere.cpp:28-35) */
+__global__ void k_leaf_atmosphere(int n, const double* z, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  AirState s = us76(z[i], 3);
+  out[5 * i] = geopotential_altitude(z[i]);
+  out[5 * i + 1] = s.T;
+  out[5 * i + 2] = s.P;
+  out[5 * i + 3] = s.rho;
+  out[5 * i + 4] = s.a;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define LEAF_PROLOGUE                                                          \
+  if (n <= 0) { gelato_set_error_("n must be positive"); return GELATO_ERR_ARG; } \
+  cudaError_t err = cudaSetDevice(device);                                     \
+  DevBuf buf;
+
+int gelato_leaf_dynamics_velocity(int device, int32_t n, const double* mass_e, const double* pos_e,
+                                  const double* vel_e, const double* quat, const double* t, const double* param5,
+                                  const double* wind, int32_t n_wind, const double* ca, int32_t n_ca,
+                                  const double* units3, double* out) {
+  LEAF_PROLOGUE
+  SecParam sp{param5[0], param5[1], param5[2], param5[4]};
+  Units un{units3[0], units3[1], units3[2], 1.0, 1.0, 0.0};
+  Tables tb;
+  tb.wind = buf.in(wind, (size_t)n_wind * 3, err); tb.n_wind = n_wind;
+  tb.ca = buf.in(ca, (size_t)n_ca * 2, err); tb.n_ca = n_ca;
+  const double* dm = buf.in(mass_e, n, err);
+  const double* dp = buf.in(pos_e, (size_t)3 * n, err);
+  const double* dv = buf.in(vel_e, (size_t)3 * n, err);
+  const double* dq = buf.in(quat, (size_t)4 * n, err);
+  const double* dt = buf.in(t, n, err);
+  double* d_out = buf.out((size_t)3 * n, err);
+  if (err == cudaSuccess) k_leaf_dynamics_velocity<<<blocks_for(n), 128>>>(n, dm, dp, dv, dq, dt, sp, un, tb, d_out);
+  return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_dynamics_velocity_noair(int device, int32_t n, const double* mass_e, const double* pos_e,
+                                        const double* quat, const double* param5, const double* units3, double* out) {
+  LEAF_PROLOGUE
+  SecParam sp{param5[0], param5[1], param5[2], param5[4]};
+  Units un{units3[0], units3[1], units3[2], 1.0, 1.0, 0.0};
+  const double* dm = buf.in(mass_e, n, err);
+  const double* dp = buf.in(pos_e, (size_t)3 * n, err);
+  const double* dq = buf.in(quat, (size_t)4 * n, err);
+  double* d_out = buf.out((size_t)3 * n, err);
+  if (err == cudaSuccess) k_leaf_dynamics_velocity_noair<<<blocks_for(n), 128>>>(n, dm, dp, dq, sp, un, d_out);
+  return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_dynamics_quaternion(int device, int32_t n, const double* quat, const double* u_e, double unit_u,
+                                    double* out) {
+  LEAF_PROLOGUE
+  const double* dq = buf.in(quat, (size_t)4 * n, err);
+  const double* du = buf.in(u_e, (size_t)2 * n, err);
+  double* d_out = buf.out((size_t)4 * n, err);
+  if (err == cudaSuccess) k_leaf_dynamics_quaternion<<<blocks_for(n), 128>>>(n, dq, du, unit_u, d_out);
+  return finish(err, out, d_out, (size_t)4 * n);
+}
+
+int gelato_leaf_aero(int device, int32_t kind, int32_t n, const double* pos, const double* vel, const double* quat,
+                     const double* t, const double* wind, int32_t n_wind, double* out) {
+  LEAF_PROLOGUE
+  if (kind < 0 || kind > 2 || (kind != 1 && !quat)) { gelato_set_error_("bad kind / missing quaternion"); return GELATO_ERR_ARG; }
+  Tables tb;
+  tb.wind = buf.in(wind, (size_t)n_wind * 3, err); tb.n_wind = n_wind;
+  tb.ca = nullptr; tb.n_ca = 0;
+  const double* dp = buf.in(pos, (size_t)3 * n, err);
+  const double* dv = buf.in(vel, (size_t)3 * n, err);
+  const double* dq = quat ? buf.in(quat, (size_t)4 * n, err) : nullptr;
+  const double* dt = buf.in(t, n, err);
+  double* d_out = buf.out(n, err);
+  if (err == cudaSuccess) k_leaf_aero<<<blocks_for(n), 128>>>(kind, n, dp, dv, dq, dt, tb, d_out);
+  return finish(err, out, d_out, n);
+}
+
+int gelato_leaf_eci2geodetic(int device, int32_t n, const double* pos_eci, const double* t, double* out) {
+  LEAF_PROLOGUE
+  const double* dp = buf.in(pos_eci, (size_t)3 * n, err);
+  const double* dt = buf.in(t, n, err);
+  double* d_out = buf.out((size_t)3 * n, err);
+  if (err == cudaSuccess) k_leaf_eci2geodetic<<<blocks_for(n), 128>>>(n, dp, dt, d_out);
+  return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_iip(int device, int32_t n, const double* pos_ecef, const double* vel_ecef, int32_t fill_na,
+                    double* out) {
+  LEAF_PROLOGUE
+  const double* dp = buf.in(pos_ecef, (size_t)3 * n, err);
+  const double* dv = buf.in(vel_ecef, (size_t)3 * n, err);
+  double* d_out = buf.out((size_t)3 * n, err);
+  if (err == cudaSuccess) k_leaf_iip<<<blocks_for(n), 128>>>(n, dp, dv, fill_na, d_out);
+  return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_gravity(int device, int32_t n, const double* pos_eci, double* out) {
+  LEAF_PROLOGUE
+  const double* dp = buf.in(pos_eci, (size_t)3 * n, err);
+  double* d_out = buf.out((size_t)3 * n, err);
+  if (err == cudaSuccess) k_leaf_gravity<<<blocks_for(n), 128>>>(n, dp, d_out);
+  return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_atmosphere(int device, int32_t n, const double* altitude, double* out) {
+  LEAF_PROLOGUE
+  const double* dz = buf.in(altitude, n, err);
+  double* d_out = buf.out((size_t)5 * n, err);
+  if (err == cudaSuccess) k_leaf_atmosphere<<<blocks_for(n), 128>>>(n, dz, d_out);
+  return finish(err, out, d_out, (size_t)5 * n);
+}
+
+}  // extern "C"

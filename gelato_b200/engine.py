@@ -140,14 +140,15 @@ def build_library(force=False, verbose=False, out=None, extra=()):
     """Compile csrc/gelato_b200.cu for sm_100a into csrc/libgelato_b200.so (in tree).
     `out` / `extra`: another output path and extra nvcc flags (tuning variants)."""
     src = os.path.join(CSRC, "gelato_b200.cu")
+    srcs = [src, os.path.join(CSRC, "leaf_api.cu")]
     if out is not None:
-        subprocess.check_call(["nvcc"] + NVCC_FLAGS + list(extra) + ["-o", out, src])
+        subprocess.check_call(["nvcc"] + NVCC_FLAGS + list(extra) + ["-o", out] + srcs)
         return out
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".inc"))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".inc"))]
     deps.append(os.path.join(INCLUDE, "gelato_b200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(f) for f in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
     subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -196,6 +197,15 @@ def load_library():
                                      ctypes.POINTER(ctypes.c_float)]
     L.gelato_selftest_unfused.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.gelato_fp64_peak.argtypes = [ctypes.c_int, _pd, _pd]
+    i32 = ctypes.c_int32
+    L.gelato_leaf_dynamics_velocity.argtypes = [ctypes.c_int, i32, _pd, _pd, _pd, _pd, _pd, _pd, _pd, i32, _pd, i32, _pd, _pd]
+    L.gelato_leaf_dynamics_velocity_noair.argtypes = [ctypes.c_int, i32, _pd, _pd, _pd, _pd, _pd, _pd]
+    L.gelato_leaf_dynamics_quaternion.argtypes = [ctypes.c_int, i32, _pd, _pd, _c_d, _pd]
+    L.gelato_leaf_aero.argtypes = [ctypes.c_int, i32, i32, _pd, _pd, _pd, _pd, _pd, i32, _pd]
+    L.gelato_leaf_eci2geodetic.argtypes = [ctypes.c_int, i32, _pd, _pd, _pd]
+    L.gelato_leaf_gravity.argtypes = [ctypes.c_int, i32, _pd, _pd]
+    L.gelato_leaf_iip.argtypes = [ctypes.c_int, i32, _pd, _pd, i32, _pd]
+    L.gelato_leaf_atmosphere.argtypes = [ctypes.c_int, i32, _pd, _pd]
     _lib = L
     return L
 
@@ -206,7 +216,9 @@ EXPORTS = (
     "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
     "gelato_plan_n_xdep gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
-    "gelato_pack_xdep_dev"
+    "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
+    "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
+    "gelato_leaf_atmosphere"
 ).split()
 
 

@@ -225,6 +225,39 @@ int gelato_selftest_unfused(int device, int* ok);
 /* FP64 issue-rate probe: measured DFMA and DADD+DMUL TFLOP/s. */
 int gelato_fp64_peak(int device, double* tflops_fma, double* tflops_nofma);
 
+/* ---- leaf batch entry points ------------------------------------------------------------
+ * The reference's pybind11 leaf functions evaluated for n nodes by one kernel launch (one thread per
+ * node; same device functions as the fused kernels).  Host buffers in and out, row-major, synchronous.
+ * They replace, argument for argument:
+ *   gelato_leaf_dynamics_velocity        dynamics_c.dynamics_velocity(mass_e, pos, vel, quat, t, param, wind, CA, units)
+ *                                         (/root/reference/src/pybind_dynamics.cpp:30-71; param[5], units[3]; out n x 3)
+ *   gelato_leaf_dynamics_velocity_noair  dynamics_c.dynamics_velocity_NoAir (:73-92)
+ *   gelato_leaf_dynamics_quaternion      dynamics_c.dynamics_quaternion (:94-106; out n x 4)
+ *   gelato_leaf_aero                     utils_c.angle_of_attack_all_array_rad (kind 0), dynamic_pressure_array_pa
+ *                                         (kind 1, quat may be NULL), q_alpha_array_pa_rad (kind 2)
+ *                                         (/root/reference/src/wrapper_utils.hpp:113-206; dimensional inputs, t in seconds)
+ *   gelato_leaf_eci2geodetic             coordinate_c.eci2geodetic (wrapper_coordinate.hpp:193-199; lat deg, lon deg, alt m)
+ *   gelato_leaf_gravity                  coordinate_c.gravity (gravity.cpp:11-57)
+ *   gelato_leaf_iip                      IIP_c.posLLH_IIP_FAA(posECEF, velECEF, fill_na) (pybind_IIP.cpp:34-51)
+ *   gelato_leaf_atmosphere               USStandardAtmosphere_c: out[i] = geopotential_altitude, airtemperature_at,
+ *                                         airpressure_at, airdensity_at, speed_of_sound of altitude[i] (n x 5)
+ */
+int gelato_leaf_dynamics_velocity(int device, int32_t n, const double* mass_e, const double* pos_e,
+                                  const double* vel_e, const double* quat, const double* t, const double* param5,
+                                  const double* wind, int32_t n_wind, const double* ca, int32_t n_ca,
+                                  const double* units3, double* out);
+int gelato_leaf_dynamics_velocity_noair(int device, int32_t n, const double* mass_e, const double* pos_e,
+                                        const double* quat, const double* param5, const double* units3, double* out);
+int gelato_leaf_dynamics_quaternion(int device, int32_t n, const double* quat, const double* u_e, double unit_u,
+                                    double* out);
+int gelato_leaf_aero(int device, int32_t kind, int32_t n, const double* pos, const double* vel, const double* quat,
+                     const double* t, const double* wind, int32_t n_wind, double* out);
+int gelato_leaf_eci2geodetic(int device, int32_t n, const double* pos_eci, const double* t, double* out);
+int gelato_leaf_gravity(int device, int32_t n, const double* pos_eci, double* out);
+int gelato_leaf_iip(int device, int32_t n, const double* pos_ecef, const double* vel_ecef, int32_t fill_na,
+                    double* out);
+int gelato_leaf_atmosphere(int device, int32_t n, const double* altitude, double* out);
+
 #ifdef __cplusplus
 }
 #endif
