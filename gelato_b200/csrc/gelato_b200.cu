@@ -41,15 +41,16 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
   jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 0, sm);
   __syncthreads();
   if (!two_phase) {
-    jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 1, sm);
-    __syncthreads();
     jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 2, sm);
     __syncthreads();
   }
   jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
 }
 
-__global__ void __launch_bounds__(GR_THREADS)
+#ifndef GR_MIN_BLOCKS
+#define GR_MIN_BLOCKS 8 /* 64 registers; measured best of 5, 8, 10 (profiles/r01g_ab.txt) */
+#endif
+__global__ void __launch_bounds__(GR_THREADS, GR_MIN_BLOCKS)
 k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
             const double* __restrict__ x_all, double* __restrict__ g_all) {
   __shared__ ResScratch sm;

@@ -88,11 +88,10 @@ struct PlanView {
   int n_aero_rows;
 };
 
-/* shared memory of one Jacobian block (30.5 KB) */
+/* shared memory of one Jacobian block (25.5 KB) */
 struct JacScratch {
   double pp[GJ_NODES * NPV * PP_COLS]; /* pos_part per (node, position variant); no-air: gravity[3] */
   double rq[GJ_NODES * NRV * RQ_COLS]; /* rotq_part per (node, rotation variant) */
-  double rp[GJ_NODES * NRV * RP_COLS]; /* rot_wind of the same */
   double f[GN_NODES * 14 * 3];         /* leaf value per (node, column lane); events: per thread */
   double q[GN_NODES * 7 * 4];          /* quaternion kinematics per (node, variant) */
 };
@@ -344,9 +343,10 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
 /* Jacobian kernel, DYN_AIR role: GJ_NODES air nodes per block, four phases   */
 /*   0  position items (node, pv) -> pos_part | rotation items (node, rv) ->  */
 /*      rotq_part | one thread per node: the 7 quaternion-kinematics variants */
-/*   1  rotation items: wind of (node, pv) into ECI axes                      */
-/*   2  column items (node, lane 0-13): the per-column remainder              */
+/*   2  column items (node, lane 0-13): wind into ECI axes, per-column        */
+/*      remainder                                                             */
 /*   3  finite-difference quotients -> COO slots                              */
+/*   (phase 1 is unused: the numbering is shared with the other roles)        */
 /* ========================================================================= */
 P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
                         int phase, JacScratch& sm) {
@@ -380,21 +380,18 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
       if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
     }
-  } else if (phase == 1) {
-    if (tid >= count * NRV) return;
-    const int nl = tid / NRV, rv = tid - nl * NRV;
-    const double* pp = sm.pp + (nl * NPV + rv_pv(rv)) * PP_COLS;
-    rot_wind(sm.rq + (nl * NRV + rv) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], sm.rp + (nl * NRV + rv) * RP_COLS);
   } else if (phase == 2) {
     if (tid >= count * 14) return;
     const int nl = tid / 14, lane = tid - nl * 14;
     const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
-    double v[11];
+    double v[11], rp[RP_COLS];
     dyn_col_state(P, x, nr.row, lane, true, dx, v);
+    const double* pp = sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS;
+    /* the wind of this column's position, turned into ECI axes with this column's (position, time)
+     * quaternion: 56 flops, cheaper to repeat per column than a block barrier for 7 items per node */
+    rot_wind(sm.rq + (nl * NRV + lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
     const Vec3 f = rhs_velocity_air_col(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q4(v[7], v[8], v[9], v[10]),
-                                        sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS,
-                                        sm.rp + (nl * NRV + lane_rv(lane)) * RP_COLS, sec_param(P, scen, nr.sec), un,
-                                        scen_tables(P, scen));
+                                        pp, rp, sec_param(P, scen, nr.sec), un, scen_tables(P, scen));
     double* o = sm.f + (nl * 14 + lane) * 3;
     o[0] = f.x;
     o[1] = f.y;
@@ -691,11 +688,6 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
       const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], r, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
     }
-  } else if (phase == 1) {
-    if (tid >= count * NRV) return;
-    const int nl = tid / NRV, rv = tid - nl * NRV;
-    const double* pp = sm.pp + (nl * NPV + rv_pv(rv)) * PP_COLS;
-    rot_wind(sm.rq + (nl * NRV + rv) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], sm.rp + (nl * NRV + rv) * RP_COLS);
   } else if (phase == 2) {
     if (tid >= count * 13) return;
     const int nl = tid / 13, lane = tid - nl * 13;
@@ -714,11 +706,13 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
         else if (w == pidx) v[w] = v[w] + dx;
       }
     }
+    double rp[RP_COLS];
+    const double* pp = sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS;
+    rot_wind(sm.rq + (nl * NRV + aero_lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
     const Vec3 pos = v3(v[0] * un.pos, v[1] * un.pos, v[2] * un.pos);
     const Vec3 vel = v3(v[3] * un.vel, v[4] * un.vel, v[5] * un.vel);
     const double val = aero_quantity_col(kind, pos, vel, q4(v[6], v[7], v[8], v[9]),
-                                         sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS,
-                                         sm.rp + (nl * NRV + aero_lane_rv(lane)) * RP_COLS) /
+                                         pp, rp) /
                        P.aero_f64[job * GA_F64_COLS + GA_LIMIT];
     sm.f[(nl * 14 + lane) * 3] = val;
   } else {
@@ -942,7 +936,7 @@ P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const 
     default: break;
   }
 }
-/* roles whose phases 1 and 2 are empty (the kernel skips those barriers) */
+/* roles whose phase 2 is empty (the kernel skips that barrier); phase 1 is empty for every role */
 P_HD bool jac_role_two_phase(int role) { return role == BR_EVT || role == BR_DYN_GEN; }
 
 P_HD void res_block_phase0(const PlanView& P, int scen, const int32_t* bt, const double* x, int tid, ResScratch& sm) {

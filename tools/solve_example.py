@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""End-to-end solve of the shipped example with the pyoptsparse stand-in (gelato_b200/nlpshim.py; the
+solver is scipy trust-constr, NOT IPOPT), once on the CPU oracle's callbacks and once on the CUDA
+callbacks: same solver, same problem, same start.  Prints converged payload, event times, iteration
+counts and the time spent inside the callbacks.
+
+    python tools/solve_example.py --arm cpu|gpu|both [--maxiter 200] [--factor 1]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+from gelato_b200 import nlpshim, problem  # noqa: E402
+
+
+def run(arm, factor, maxiter):
+    from oracle import leaves
+
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c, factor=factor)
+    if arm == "cpu":
+        O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+
+        def objfunc(x):
+            return O.objfunc(x)
+
+        def sens(x, f=None):
+            return O.sens(x)
+    else:
+        from gelato_b200 import callbacks
+
+        prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
+        objfunc, sens = prob.objfunc, prob.sens
+    opt = nlpshim.register(objfunc, sens, x0, c)
+    sol = nlpshim.TrustConstr({"maxiter": maxiter})(opt, sens=sens)
+    t_events = sol.xStar["t"] * u["t"]
+    out = {
+        "arm": arm, "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status, "obj": float(sol.fStar),
+        "constr_violation": sol.constr_violation,
+        "payload_kg": float(sol.xStar["mass"][0] * u["mass"]) if c["OptimizationMode"] == "Payload" else None,
+        "event_times_s": [float(v) for v in t_events],
+        "optTime": sol.optTime, "userObjTime": sol.userObjTime, "userObjCalls": sol.userObjCalls,
+        "userSensTime": sol.userSensTime, "userSensCalls": sol.userSensCalls,
+    }
+    return out, problem.xdict_to_vector(sol.xStar)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
+    ap.add_argument("--maxiter", type=int, default=200)
+    ap.add_argument("--factor", type=int, default=1)
+    a = ap.parse_args()
+    res = {}
+    for arm in (["cpu", "gpu"] if a.arm == "both" else [a.arm]):
+        res[arm] = run(arm, a.factor, a.maxiter)
+        print(json.dumps(res[arm][0]))
+    if len(res) == 2:
+        xa, xb = res["cpu"][1], res["gpu"][1]
+        print(json.dumps({"max_abs_diff_x": float(np.max(np.abs(xa - xb))), "identical_iterates": bool(np.array_equal(xa, xb))}))
+
+
+if __name__ == "__main__":
+    main()
