@@ -44,7 +44,7 @@ def test_library_is_the_cuda_build():
 
 @pytest.mark.parametrize("variant,factor,user", [
     ("example", 1, True), ("example", 4, True), ("example", 15, True), ("fuel_inclination", 1, True),
-    ("all_aero", 2, True), ("waypoints", 1, True), ("neg_area", 1, True), ("waypoints", 3, False), ("bare", 1, False),
+    ("all_aero", 2, True), ("waypoints", 1, True), ("neg_area", 1, True), ("three_stage", 2, True), ("waypoints", 3, False), ("bare", 1, False),
 ])
 def test_gpu_matches_oracle_bitwise(variant, factor, user):
     prob, O, x0 = _problem(variant, factor, max_nodes=20 if factor == 15 else 12, user=user)
@@ -207,20 +207,21 @@ def test_repeated_calls_are_deterministic_and_template_survives():
     prob.close()
 
 
-@pytest.mark.parametrize("factor", [150, 1500])
-def test_full_size_properties(factor):
-    """C5 sizes (N = 9 900 and 99 000 nodes): the oracle is too slow there, so check
+@pytest.mark.parametrize("variant,factor", [("example", 150), ("example", 1500), ("three_stage", 62)])
+def test_full_size_properties(variant, factor):
+    """BASELINE.json configs[4] sizes (N = 9 900 and 99 000 nodes) and configs[2] (three stages, 250
+    sections, N = 4 836): the oracle is too slow there, so check
     properties that do not depend on the size:
       * section locality: every section's rows equal the rows of the same section
         evaluated inside a small problem (sampled sections vs the oracle);
       * linear groups satisfy g = J x + c with the emitted COO blocks;
       * the Jacobian of a batch equals the Jacobian of each member."""
     Lg = leaves.get("gmath")
-    inp = helpers.example_inputs()
+    inp = helpers.variant_inputs(variant)
     p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c, factor=factor, max_nodes=20)
     prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
     P = prob.plan
-    assert P.N == 66 * factor
+    assert P.N == sum(e["num_nodes"] for e in inp["events"][:-1]) * factor
     x = helpers.perturbed(x0)
     f, _ = prob.objfunc(x)
     s, _ = prob.sens(x, f)
