@@ -22,12 +22,18 @@ from .plan import GROUPS, VAR_ORDER, CompiledPlan, PerigeeAtEvent  # noqa: F401
 
 class GelatoProblem:
     def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None,
-                 engine_factory=None):
+                 engine_factory=None, reuse_output=False):
         """engine_factory(plan) -> object with eval_residuals / eval_jacobian / close / launches;
         default: the CUDA engine on `device` (the CPU test tier passes the host emulator of the
         kernels, tests/emu_binding.py, to exercise this host logic without a GPU)."""
         self.plan = CompiledPlan(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, coord=coord)
         self.engine = engine_factory(self.plan) if engine_factory else _engine.Engine(self.plan, device=device)
+        # reuse_output=True: `sens` writes into ONE page-locked buffer kept across calls and only the
+        # x-dependent Jacobian values cross PCIe (update mode); the returned COO data arrays are views of
+        # that buffer, valid until the next `sens` call -- what pyoptsparse needs (it converts them at
+        # once), and ~10x less traffic on fine meshes.  Default False: fresh arrays, like the reference.
+        self.reuse_output = bool(reuse_output) and hasattr(self.engine, "eval_jacobian_update")
+        self._vals = None
         self._x = np.empty(self.plan.n_vars)
 
     # -- helpers ---------------------------------------------------------
@@ -50,7 +56,13 @@ class GelatoProblem:
         return self.plan.split_residuals(g), False
 
     def sens(self, xdict, funcs=None):
-        vals = self.engine.eval_jacobian(self.pack(xdict))
+        if self.reuse_output:
+            if self._vals is None:
+                self._vals = _engine.PinnedArray(self.plan.n_vals)
+                self.engine.jacobian_template(self._vals.array, 1)
+            vals = self.engine.eval_jacobian_update(self.pack(xdict), self._vals.array, 1)
+        else:
+            vals = self.engine.eval_jacobian(self.pack(xdict))
         return self.plan.split_jacobian(vals, key_order=[k for k in xdict.keys() if k in VAR_ORDER]), False
 
     # -- flat-vector variants (no dictionaries), used by benchmarks / batched drivers
@@ -61,6 +73,9 @@ class GelatoProblem:
         return self.engine.eval_jacobian(x, n_scen)
 
     def close(self):
+        if self._vals is not None:
+            self._vals.free()
+            self._vals = None
         self.engine.close()
 
 

@@ -301,6 +301,7 @@ int32_t gelato_plan_n_rows(const GelatoPlan* p) { return p ? p->view.n_rows : 0;
 int64_t gelato_plan_n_vals(const GelatoPlan* p) { return p ? p->view.n_vals : 0; }
 int64_t gelato_plan_launch_count(const GelatoPlan* p) { return p ? p->launches : 0; }
 int64_t gelato_plan_n_xdep(const GelatoPlan* p) { return p ? p->n_xdep : 0; }
+int32_t gelato_plan_n_blocks(const GelatoPlan* p, int which) { return !p ? 0 : (which ? p->n_jac_blocks : p->n_res_blocks); }
 
 static int check_scen(GelatoPlan* p, int n_scen) {
   if (!p) return fail(GELATO_ERR_ARG, "null plan");

@@ -185,6 +185,8 @@ def load_library():
     L.gelato_eval_residuals_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_eval_jacobian_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_fill_template.argtypes = [vp, vp, ctypes.c_int32, vp]
+    L.gelato_plan_n_blocks.argtypes = [vp, ctypes.c_int]
+    L.gelato_plan_n_blocks.restype = ctypes.c_int32
     L.gelato_plan_n_xdep.argtypes = [vp]
     L.gelato_plan_n_xdep.restype = ctypes.c_int64
     L.gelato_jacobian_template.argtypes = [vp, _pd, ctypes.c_int32]
@@ -215,7 +217,7 @@ EXPORTS = (
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
-    "gelato_plan_n_xdep gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_plan_n_blocks gelato_plan_n_xdep gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
     "gelato_leaf_atmosphere"
@@ -243,6 +245,8 @@ class Engine:
             sc, keep = make_scenario_desc(scenario_plans)
             _check(L, L.gelato_plan_set_scenarios(self.h, ctypes.byref(sc)), "gelato_plan_set_scenarios")
             self.n_scen_cfg = len(scenario_plans)
+        self.n_jac_blocks = L.gelato_plan_n_blocks(h, 1)
+        self.n_res_blocks = L.gelato_plan_n_blocks(h, 0)
         self.n_vars = L.gelato_plan_n_vars(h)
         self.n_rows = L.gelato_plan_n_rows(h)
         self.n_vals = L.gelato_plan_n_vals(h)

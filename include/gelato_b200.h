@@ -173,6 +173,8 @@ int gelato_plan_destroy(GelatoPlan* plan);
 int32_t gelato_plan_n_vars(const GelatoPlan* plan);
 int32_t gelato_plan_n_rows(const GelatoPlan* plan);
 int64_t gelato_plan_n_vals(const GelatoPlan* plan);
+/* thread blocks per scenario of the residual (which = 0) / Jacobian (which = 1) kernel */
+int32_t gelato_plan_n_blocks(const GelatoPlan* plan, int which);
 /* kernels launched by this plan so far (bench.py's gpu_launches) */
 int64_t gelato_plan_launch_count(const GelatoPlan* plan);
 

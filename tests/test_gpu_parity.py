@@ -194,6 +194,17 @@ def test_update_mode_equals_full_jacobian(pinned):
     E.close()
 
 
+def test_reuse_output_sens_equals_fresh_sens():
+    prob, O, x0 = _problem("example", 3)
+    p2 = callbacks.GelatoProblem(prob.plan.p, prob.plan.u, prob.plan.c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT),
+                                 coord=leaves.get("gmath").coordinate_c, reuse_output=True)
+    for seed in (1, 2):
+        x = helpers.perturbed(x0, seed=seed)
+        helpers.assert_sens_equal(prob.sens(x)[0], p2.sens(x)[0])
+    prob.close()
+    p2.close()
+
+
 def test_repeated_calls_are_deterministic_and_template_survives():
     prob, O, x0 = _problem("example", 2)
     E = prob.engine

@@ -48,6 +48,20 @@ def main():
         lines.append("  stall reasons (warps stalled per issue-active cycle), top 8:")
         for v, k in stalls[:8]:
             lines.append("    %-40s %.3f" % (k[len(STALL):-len("_per_issue_active.ratio")], v))
+    # machine-readable DRAM traffic of the profiled launch, read by bench.py (roofline.traffic)
+    import json, os, re
+    tj = os.path.join(os.path.dirname(os.path.abspath(out)), "traffic.json")
+    db = json.load(open(tj)) if os.path.exists(tj) else {}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        d, u = dict(zip(hdr, r)), dict(zip(hdr, units))
+        name = re.match(r"\w+", d.get("Kernel Name", "?")).group(0)
+        try:
+            tot = sum(float(d[k]) * mult[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except (KeyError, ValueError):
+            continue
+        db[name] = {"dram_bytes_per_launch": tot, "grid": d.get("Grid Size"), "source": os.path.basename(out)}
+    json.dump(db, open(tj, "w"), indent=1, sort_keys=True)
     open(out, "w").write("source: %s (ncu --set full --clock-control none, one launch inside bench.py)\n" % rep
                          + "\n".join(lines) + "\n")
     print("\n".join(lines))

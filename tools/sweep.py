@@ -52,11 +52,14 @@ def main():
         reps = 20 if P.N < 20000 else 5
         obj_ms = timed(lambda: prob.objfunc(x), reps)
         sens_ms = timed(lambda: prob.sens(x), reps)
+        prob2 = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), reuse_output=True)
+        sens_reuse_ms = timed(lambda: prob2.sens(x), reps)
+        prob2.close()
         row = {"variant": variant, "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows,
                "n_vals": int(P.n_vals), "n_xdep": P.n_xdep, "evals_objfunc": ec["objfunc"], "evals_sens": ec["sens"],
                "plan_compile_s": t_plan, "k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms,
                "device_evals_per_s": (ec["objfunc"] + ec["sens"]) / ((res_ms + jac_ms) * 1e-3),
-               "objfunc_call_ms": obj_ms, "sens_call_ms": sens_ms,
+               "objfunc_call_ms": obj_ms, "sens_call_ms": sens_ms, "sens_call_reuse_output_ms": sens_reuse_ms,
                "callback_pairs_per_s": 1e3 / (obj_ms + sens_ms)}
         if P.N <= 1000:
             from oracle import leaves
