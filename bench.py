@@ -246,6 +246,8 @@ def run_gelato(args):
     plans, X, probs = load_workload(args.factor, B * world, own.start, len(own))
     P = plans[0]
     E = engine.Engine(P, device=local, scenario_plans=plans)
+    # scatter threads of update mode: the ranks of one node share the host cores (and its memory bandwidth)
+    E.set_host_threads(max(1, min(16, (os.cpu_count() or 1) // world)))
     ec = P.eval_counts()
     evals_step_rank = (ec["objfunc"] + ec["sens"]) * B
     # a dedicated non-default stream: the C ABI reads stream 0 as "the plan's own stream", and the

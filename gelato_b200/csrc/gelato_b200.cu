@@ -30,7 +30,8 @@
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
            const double* __restrict__ x_all, double* __restrict__ vals_all) {
-  __shared__ JacScratch sm;
+  __shared__ JacStore store;
+  const JacScratch sm = jac_scratch(store);
   // role-major launch order: block b of every scenario before block b+1 of any, so the blocks
   // resident on an SM at one time mostly run the same role's code (instruction-cache locality)
   const int scen = blockIdx.x % n_scen;
@@ -44,6 +45,33 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
     jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 2, sm);
     __syncthreads();
   }
+  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
+}
+
+// Two-launch variant of the same job (GJ_SPLIT): launch 1 runs phase 0 of every block without any
+// barrier (position / rotation / quaternion items are independent) and parks pp | rq | q in a global
+// staging buffer that stays in L2; launch 2 runs phases 2 and 3.  Blocks whose role has no phase 2
+// (event rows, fallback nodes) run entirely in launch 2.
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
+k_jacobian_stage0(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+                  const double* __restrict__ x_all, double* __restrict__ stage_all) {
+  const int scen = blockIdx.x % n_scen;
+  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
+  if (jac_role_two_phase(bt[BT_ROLE])) return;
+  const JacScratch sm = jac_scratch_staged(stage_all + (size_t)blockIdx.x * GJ_STAGE_LEN, nullptr);
+  jac_block_phase(P, scen, bt, x_all + (size_t)scen * P.n_vars, nullptr, threadIdx.x, 0, sm);
+}
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
+k_jacobian_stage23(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+                   const double* __restrict__ x_all, double* __restrict__ vals_all, double* __restrict__ stage_all) {
+  __shared__ double f[GJ_F_LEN];
+  const int scen = blockIdx.x % n_scen;
+  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
+  const double* x = x_all + (size_t)scen * P.n_vars;
+  double* vals = vals_all + (size_t)scen * P.n_vals;
+  const JacScratch sm = jac_scratch_staged(stage_all + (size_t)blockIdx.x * GJ_STAGE_LEN, f);
+  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, jac_role_two_phase(bt[BT_ROLE]) ? 0 : 2, sm);
+  __syncthreads();
   jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
 }
 
@@ -122,6 +150,10 @@ static int fail(int code, const std::string& msg) {
       return fail(GELATO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
+#ifndef GJ_SPLIT
+#define GJ_SPLIT 0
+#endif
+
 struct GelatoPlan {
   int device = 0;
   PlanView view{};  // device pointers
@@ -146,6 +178,8 @@ struct GelatoPlan {
   size_t cap_pack = 0;
   int host_threads = 0;
   std::vector<cudaEvent_t> chunk_ev;
+  double* d_stage = nullptr;  // two-launch Jacobian: [n_jac_blocks x cap_stage][GJ_STAGE_LEN]
+  size_t cap_stage = 0;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -159,6 +193,28 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
   p->owned.push_back(d);
   CU(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
   *dst = static_cast<const T*>(d);
+  return GELATO_OK;
+}
+
+// one Jacobian evaluation on `st`: the fused kernel, or the two-launch variant
+static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* vals_dev, int n_scen, cudaStream_t st) {
+  const unsigned grid = (unsigned)p->n_jac_blocks * n_scen;
+#if GJ_SPLIT
+  if ((size_t)n_scen > p->cap_stage) {
+    CU(cudaStreamSynchronize(st));
+    if (p->d_stage) cudaFree(p->d_stage);
+    p->d_stage = nullptr;
+    p->cap_stage = 0;
+    CU(cudaMalloc(&p->d_stage, (size_t)grid * GJ_STAGE_LEN * sizeof(double)));
+    p->cap_stage = n_scen;
+  }
+  k_jacobian_stage0<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, p->d_stage);
+  k_jacobian_stage23<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev, p->d_stage);
+  p->launches += 2;
+#else
+  k_jacobian<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
+  p->launches++;
+#endif
   return GELATO_OK;
 }
 
@@ -286,6 +342,7 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->d_vals) cudaFree(p->d_vals);
   if (p->h_x) cudaFreeHost(p->h_x);
   if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->d_stage) cudaFree(p->d_stage);
   if (p->d_pack) cudaFree(p->d_pack);
   if (p->h_pack) cudaFreeHost(p->h_pack);
   for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
@@ -349,8 +406,7 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
   // the kernel rewrites every x-dependent slot and never touches the rest
-  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
-  p->launches++;
+  if ((rc = launch_jacobian(p, x_dev, vals_dev, n_scen, st))) return rc;
   CU(cudaGetLastError());
   return GELATO_OK;
 }
@@ -461,7 +517,15 @@ static void scatter_scenarios(const int64_t* idx, long long n_xdep, const double
   for (int s = s0; s < s1; s++) {
     const double* src = packed + (size_t)s * n_xdep;
     double* dst = vals + (size_t)s * n_vals;
-    for (long long i = 0; i < n_xdep; i++) dst[idx[i]] = src[i];
+    // isolated slots (the node-diagonals of the dense D blocks) cost one cache-line fill each: ask for
+    // the lines a few dozen writes ahead so the fills overlap
+    const long long ahead = 48;
+    long long i = 0;
+    for (; i + ahead < n_xdep; i++) {
+      __builtin_prefetch(dst + idx[i + ahead], 1, 0);
+      dst[idx[i]] = src[i];
+    }
+    for (; i < n_xdep; i++) dst[idx[i]] = src[i];
   }
 }
 
@@ -474,7 +538,8 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
   const PlanView& v = p->view;
   const long long nx = p->n_xdep;
   if ((size_t)n_scen > p->cap_pack) {
-    if (p->d_pack) cudaFree(p->d_pack);
+    if (p->d_stage) cudaFree(p->d_stage);
+  if (p->d_pack) cudaFree(p->d_pack);
     if (p->h_pack) cudaFreeHost(p->h_pack);
     p->d_pack = p->h_pack = nullptr;
     p->cap_pack = 0;
@@ -550,7 +615,8 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
     if (which == 0) {
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, x_dev, out_dev);
     } else {
-      k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, n_scen, x_dev, out_dev);
+      if ((rc = launch_jacobian(p, x_dev, out_dev, n_scen, p->stream))) return rc;
+      continue;
     }
     p->launches++;
   }

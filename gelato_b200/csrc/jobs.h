@@ -88,13 +88,37 @@ struct PlanView {
   int n_aero_rows;
 };
 
-/* shared memory of one Jacobian block (25.5 KB) */
-struct JacScratch {
-  double pp[GJ_NODES * NPV * PP_COLS]; /* pos_part per (node, position variant); no-air: gravity[3] */
-  double rq[GJ_NODES * NRV * RQ_COLS]; /* rotq_part per (node, rotation variant) */
-  double f[GN_NODES * 14 * 3];         /* leaf value per (node, column lane); events: per thread */
-  double q[GN_NODES * 7 * 4];          /* quaternion kinematics per (node, variant) */
+/* working arrays of one Jacobian block.  The fused kernel keeps all four in shared memory (JacStore,
+ * 25.5 KB); the two-launch variant keeps pp / rq / q in a global staging buffer between its launches. */
+#define GJ_PP_LEN (GJ_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
+#define GJ_RQ_LEN (GJ_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
+#define GJ_F_LEN (GN_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
+#define GJ_Q_LEN (GN_NODES * 7 * 4)          /* quaternion kinematics per (node, variant) */
+#define GJ_STAGE_LEN (GJ_PP_LEN + GJ_RQ_LEN + GJ_Q_LEN)
+struct JacStore {
+  double pp[GJ_PP_LEN];
+  double rq[GJ_RQ_LEN];
+  double q[GJ_Q_LEN];
+  double f[GJ_F_LEN];
 };
+struct JacScratch {
+  double* pp;
+  double* rq;
+  double* q;
+  double* f;
+};
+P_HD JacScratch jac_scratch(JacStore& st) {
+  JacScratch sm;
+  sm.pp = st.pp; sm.rq = st.rq; sm.q = st.q; sm.f = st.f;
+  return sm;
+}
+/* staging buffer of the two-launch variant: pp | rq | q of one (block, scenario) */
+P_HD JacScratch jac_scratch_staged(double* stage, double* f) {
+  JacScratch sm;
+  sm.pp = stage; sm.rq = stage + GJ_PP_LEN; sm.q = stage + GJ_PP_LEN + GJ_RQ_LEN; sm.f = f;
+  return sm;
+}
+
 /* shared memory of one residual block */
 struct ResScratch {
   double f[GR_NODES][3];
@@ -349,7 +373,7 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
 /*   (phase 1 is unused: the numbering is shared with the other roles)        */
 /* ========================================================================= */
 P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                        int phase, JacScratch& sm) {
+                        int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
@@ -408,7 +432,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
 /*   3  quotients -> COO slots                                                */
 /* ========================================================================= */
 P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                          int phase, JacScratch& sm) {
+                          int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
@@ -455,7 +479,7 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
 /* 257 vs :403,454).                                                          */
 /* ========================================================================= */
 P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                        int phase, JacScratch& sm) {
+                        int phase, const JacScratch& sm) {
   const int nl = tid >> 4, lane = tid & 15;
   if (nl >= count) return;
   const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
@@ -663,7 +687,7 @@ P_HD void aero_base(const PlanView& P, const double* x, int sec, int row, double
 }
 
 P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                     int phase, JacScratch& sm) {
+                     int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = P.un.dx;
   if (phase == 0) {
@@ -827,7 +851,7 @@ P_HD int evt_n_lanes(int type) {
   return type == GE_IIP ? 8 : (type == GE_TERM ? 7 : (type == GE_USER_PERIGEE ? 13 : 5));
 }
 
-P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, JacScratch& sm) {
+P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, const JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
@@ -920,7 +944,7 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 /* between them; residual blocks run three (only the dynamics role uses 0, 2).  */
 /* ========================================================================= */
 P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, int tid,
-                          int phase, JacScratch& sm) {
+                          int phase, const JacScratch& sm) {
   const int start = bt[BT_START], count = bt[BT_COUNT];
   switch (bt[BT_ROLE]) {
     case BR_DYN_AIR: dyn_air_phase(P, scen, x, vals, start, count, tid, phase, sm); break;

@@ -77,7 +77,8 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
   build_host_tables(d, h);
   attach_tables(P, h);
   const std::vector<int32_t>& jb = h.jac_blocks;
-  JacScratch sm;
+  JacStore store;
+  const JacScratch sm = jac_scratch(store);
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
     double* vals = vals_all + (size_t)scen * P.n_vals;
@@ -86,7 +87,7 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
     for (size_t b = 0; b < jb.size() / BT_COLS; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
       /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
-      memset(&sm, 0xff, sizeof sm);
+      memset(&store, 0xff, sizeof store);
       for (int phase = 0; phase < GJ_PHASES; phase++)
         for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase(P, scen, bt, x, vals, tid, phase, sm);
     }
