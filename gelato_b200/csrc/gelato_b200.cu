@@ -538,8 +538,7 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
   const PlanView& v = p->view;
   const long long nx = p->n_xdep;
   if ((size_t)n_scen > p->cap_pack) {
-    if (p->d_stage) cudaFree(p->d_stage);
-  if (p->d_pack) cudaFree(p->d_pack);
+    if (p->d_pack) cudaFree(p->d_pack);
     if (p->h_pack) cudaFreeHost(p->h_pack);
     p->d_pack = p->h_pack = nullptr;
     p->cap_pack = 0;
