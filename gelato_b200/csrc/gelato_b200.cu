@@ -48,33 +48,6 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
   jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
 }
 
-// Two-launch variant of the same job (GJ_SPLIT): launch 1 runs phase 0 of every block without any
-// barrier (position / rotation / quaternion items are independent) and parks pp | rq | q in a global
-// staging buffer that stays in L2; launch 2 runs phases 2 and 3.  Blocks whose role has no phase 2
-// (event rows, fallback nodes) run entirely in launch 2.
-__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian_stage0(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
-                  const double* __restrict__ x_all, double* __restrict__ stage_all) {
-  const int scen = blockIdx.x % n_scen;
-  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
-  if (jac_role_two_phase(bt[BT_ROLE])) return;
-  const JacScratch sm = jac_scratch_staged(stage_all + (size_t)blockIdx.x * GJ_STAGE_LEN, nullptr);
-  jac_block_phase(P, scen, bt, x_all + (size_t)scen * P.n_vars, nullptr, threadIdx.x, 0, sm);
-}
-__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian_stage23(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
-                   const double* __restrict__ x_all, double* __restrict__ vals_all, double* __restrict__ stage_all) {
-  __shared__ double f[GJ_F_LEN];
-  const int scen = blockIdx.x % n_scen;
-  const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
-  const double* x = x_all + (size_t)scen * P.n_vars;
-  double* vals = vals_all + (size_t)scen * P.n_vals;
-  const JacScratch sm = jac_scratch_staged(stage_all + (size_t)blockIdx.x * GJ_STAGE_LEN, f);
-  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, jac_role_two_phase(bt[BT_ROLE]) ? 0 : 2, sm);
-  __syncthreads();
-  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
-}
-
 #ifndef GR_MIN_BLOCKS
 #define GR_MIN_BLOCKS 8 /* 64 registers; measured best of 5, 8, 10 (profiles/r01g_ab.txt) */
 #endif
@@ -150,10 +123,6 @@ static int fail(int code, const std::string& msg) {
       return fail(GELATO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
-#ifndef GJ_SPLIT
-#define GJ_SPLIT 0
-#endif
-
 struct GelatoPlan {
   int device = 0;
   PlanView view{};  // device pointers
@@ -178,8 +147,6 @@ struct GelatoPlan {
   size_t cap_pack = 0;
   int host_threads = 0;
   std::vector<cudaEvent_t> chunk_ev;
-  double* d_stage = nullptr;  // two-launch Jacobian: [n_jac_blocks x cap_stage][GJ_STAGE_LEN]
-  size_t cap_stage = 0;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -196,25 +163,11 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
   return GELATO_OK;
 }
 
-// one Jacobian evaluation on `st`: the fused kernel, or the two-launch variant
+// one Jacobian evaluation on `st`.  (A two-launch variant -- phase 0 barrier-free with pp | rq | q staged
+// through L2 -- was measured 38 % slower than this fused kernel: profiles/r01i_split_ab.txt.)
 static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* vals_dev, int n_scen, cudaStream_t st) {
-  const unsigned grid = (unsigned)p->n_jac_blocks * n_scen;
-#if GJ_SPLIT
-  if ((size_t)n_scen > p->cap_stage) {
-    CU(cudaStreamSynchronize(st));
-    if (p->d_stage) cudaFree(p->d_stage);
-    p->d_stage = nullptr;
-    p->cap_stage = 0;
-    CU(cudaMalloc(&p->d_stage, (size_t)grid * GJ_STAGE_LEN * sizeof(double)));
-    p->cap_stage = n_scen;
-  }
-  k_jacobian_stage0<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, p->d_stage);
-  k_jacobian_stage23<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev, p->d_stage);
-  p->launches += 2;
-#else
-  k_jacobian<<<grid, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
+  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
   p->launches++;
-#endif
   return GELATO_OK;
 }
 
@@ -342,7 +295,6 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->d_vals) cudaFree(p->d_vals);
   if (p->h_x) cudaFreeHost(p->h_x);
   if (p->h_out) cudaFreeHost(p->h_out);
-  if (p->d_stage) cudaFree(p->d_stage);
   if (p->d_pack) cudaFree(p->d_pack);
   if (p->h_pack) cudaFreeHost(p->h_pack);
   for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);

@@ -88,13 +88,12 @@ struct PlanView {
   int n_aero_rows;
 };
 
-/* working arrays of one Jacobian block.  The fused kernel keeps all four in shared memory (JacStore,
- * 25.5 KB); the two-launch variant keeps pp / rq / q in a global staging buffer between its launches. */
+/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 25.5 KB), a plain struct
+ * in the host emulator; the jobs reach them through the pointers of JacScratch. */
 #define GJ_PP_LEN (GJ_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
 #define GJ_RQ_LEN (GJ_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
 #define GJ_F_LEN (GN_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
 #define GJ_Q_LEN (GN_NODES * 7 * 4)          /* quaternion kinematics per (node, variant) */
-#define GJ_STAGE_LEN (GJ_PP_LEN + GJ_RQ_LEN + GJ_Q_LEN)
 struct JacStore {
   double pp[GJ_PP_LEN];
   double rq[GJ_RQ_LEN];
@@ -112,13 +111,6 @@ P_HD JacScratch jac_scratch(JacStore& st) {
   sm.pp = st.pp; sm.rq = st.rq; sm.q = st.q; sm.f = st.f;
   return sm;
 }
-/* staging buffer of the two-launch variant: pp | rq | q of one (block, scenario) */
-P_HD JacScratch jac_scratch_staged(double* stage, double* f) {
-  JacScratch sm;
-  sm.pp = stage; sm.rq = stage + GJ_PP_LEN; sm.q = stage + GJ_PP_LEN + GJ_RQ_LEN; sm.f = f;
-  return sm;
-}
-
 /* shared memory of one residual block */
 struct ResScratch {
   double f[GR_NODES][3];
