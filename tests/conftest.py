@@ -16,9 +16,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _native_test_libs():
     """Build the CPU-side checkers once: the oracle (both flavours) and the host
-    emulator of the kernels.  The product library is built by __graft_entry__.build()."""
+    emulator of the kernels, and the product library if it is missing or stale (the same
+    nvcc command as __graft_entry__.build())."""
+    import shutil
+
+    from gelato_b200 import engine
     from oracle import leaves
 
+    if shutil.which("nvcc"):  # the product library (cross-compiles without a GPU); a no-op when up to date
+        engine.build_library()
     leaves.build()
     import emu_binding
 
