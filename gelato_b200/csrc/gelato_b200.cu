@@ -81,6 +81,19 @@ __global__ void k_pack_xdep(const double* __restrict__ vals_all, const int64_t* 
     packed[i] = vals[idx[i]];
 }
 
+// update mode, zero-copy flavour: the x-dependent slots written straight into the caller's page-locked
+// (device-mapped) host buffer over PCIe; runs of consecutive slots coalesce into full-width writes
+__global__ void k_scatter_xdep_host(const double* __restrict__ vals_all, const int64_t* __restrict__ idx,
+                                    long long n_xdep, long long n_vals, double* __restrict__ host_vals_all) {
+  const int scen = blockIdx.y;
+  const double* vals = vals_all + (size_t)scen * n_vals;
+  double* host = host_vals_all + (size_t)scen * n_vals;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_xdep; i += (long long)gridDim.x * blockDim.x) {
+    const long long k = idx[i];
+    host[k] = vals[k];
+  }
+}
+
 // probe: is a*b+c left unfused?  (1 + 2^-30)(1 - 2^-30) - 1 is 0 unfused, -2^-60 fused
 __global__ void k_unfused_probe(double a, double b, double c, double* out) { *out = a * b + c; }
 
@@ -146,6 +159,7 @@ struct GelatoPlan {
   double *d_pack = nullptr, *h_pack = nullptr;  // [cap_pack][n_xdep], h_pack pinned
   size_t cap_pack = 0;
   int host_threads = 0;
+  int update_zero_copy = 1;  // page-locked caller buffers are written from the device (profiles/r01k_e2e.txt)
   std::vector<cudaEvent_t> chunk_ev;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -458,6 +472,12 @@ int gelato_jacobian_template(GelatoPlan* p, double* vals, int32_t n_scen) {
   return GELATO_OK;
 }
 
+int gelato_set_update_zero_copy(GelatoPlan* p, int32_t on) {
+  if (!p) return fail(GELATO_ERR_ARG, "null plan");
+  p->update_zero_copy = on ? 1 : 0;
+  return GELATO_OK;
+}
+
 int gelato_set_host_threads(GelatoPlan* p, int32_t n) {
   if (!p || n < 0) return fail(GELATO_ERR_ARG, "bad thread count");
   p->host_threads = n;
@@ -506,6 +526,18 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
   }
   CU(cudaMemcpyAsync(p->d_x, hx, nxin * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
+  if (p->update_zero_copy && is_pinned(vals)) {
+    if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 in update mode (gridDim.y)");
+    double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
+    CU(cudaHostGetDevicePointer((void**)&dev_view, vals, 0));
+    const int threads = 256;
+    const int bx = (int)std::min<long long>((nx + threads - 1) / threads, 4096);
+    k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, p->d_xdep, nx, v.n_vals, dev_view);
+    p->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(p->stream));
+    return GELATO_OK;
+  }
   if ((rc = gelato_pack_xdep_dev(p, p->d_vals, p->d_pack, n_scen, p->stream))) return rc;
   // device->host in chunks of scenarios, so the host scatter of chunk k overlaps the copy of chunk k+1
   int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));

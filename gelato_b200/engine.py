@@ -192,6 +192,7 @@ def load_library():
     L.gelato_jacobian_template.argtypes = [vp, _pd, ctypes.c_int32]
     L.gelato_eval_jacobian_update.argtypes = [vp, _pd, _pd, ctypes.c_int32]
     L.gelato_set_host_threads.argtypes = [vp, ctypes.c_int32]
+    L.gelato_set_update_zero_copy.argtypes = [vp, ctypes.c_int32]
     L.gelato_pack_xdep_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.gelato_host_free.argtypes = [vp]
@@ -217,7 +218,7 @@ EXPORTS = (
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
-    "gelato_plan_n_blocks gelato_plan_n_xdep gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
     "gelato_leaf_atmosphere"
@@ -305,6 +306,9 @@ class Engine:
         _check(self.L, self.L.gelato_eval_jacobian_update(self.h, _ptr(x, _pd), _ptr(out, _pd), n_scen),
                "gelato_eval_jacobian_update")
         return out if n_scen == 1 else out.reshape(n_scen, self.n_vals)
+
+    def set_update_zero_copy(self, on=True):
+        _check(self.L, self.L.gelato_set_update_zero_copy(self.h, 1 if on else 0), "gelato_set_update_zero_copy")
 
     def set_host_threads(self, n):
         _check(self.L, self.L.gelato_set_host_threads(self.h, int(n)), "gelato_set_host_threads")

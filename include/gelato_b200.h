@@ -190,13 +190,18 @@ int gelato_eval_jacobian(GelatoPlan* plan, const double* x, double* vals, int32_
  * calls (a batched solve): most of vals never changes (D entries, +-1, unit constants -- 87 % of
  * the slots at 1 000 nodes), so only the x-dependent slots cross PCIe.
  *   gelato_jacobian_template     fills vals[n_scen][n_vals] with the constant slots (once per buffer);
- *   gelato_eval_jacobian_update  runs the Jacobian kernel, packs the x-dependent slots on the
- *                                device, copies the packed values back and scatters them into
- *                                vals; every other slot of vals is left as it was.
+ *   gelato_eval_jacobian_update  runs the Jacobian kernel and moves only the x-dependent slots into
+ *                                vals (page-locked vals: written from the device; pageable vals:
+ *                                packed, copied and scattered by host threads); every other slot
+ *                                of vals is left as it was.
  * After the two calls vals holds exactly what gelato_eval_jacobian returns. */
 int64_t gelato_plan_n_xdep(const GelatoPlan* plan);
 int gelato_jacobian_template(GelatoPlan* plan, double* vals, int32_t n_scen);
 int gelato_eval_jacobian_update(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
+/* on != 0 (default): when `vals` is page-locked (gelato_host_alloc), update mode writes the x-dependent
+ * slots straight into it from the device (zero-copy over PCIe, no host thread touches the buffer); pageable
+ * buffers, or on == 0, take pack + copy + host scatter */
+int gelato_set_update_zero_copy(GelatoPlan* plan, int32_t on);
 /* host threads used by the scatter of update mode (default: min(16, hardware threads)) */
 int gelato_set_host_threads(GelatoPlan* plan, int32_t n_threads);
 

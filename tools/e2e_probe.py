@@ -35,6 +35,11 @@ def main():
     for th in (1, 2, 4, 8, 16, 32):
         E.set_host_threads(th)
         print("jacobian update, %2d thr   %.3f ms" % (th, t(lambda: E.eval_jacobian_update(px.array, pv.array, B))))
+    E.set_update_zero_copy(True)
+    print("jacobian update, zero-copy %.3f ms" % t(lambda: E.eval_jacobian_update(px.array, pv.array, B)))
+    want = E.eval_jacobian(px.array, B).copy()
+    assert np.array_equal(pv.array.reshape(B, -1), want), "zero-copy update differs from the full copy"
+    E.set_update_zero_copy(False)
     idx = P.xdep_index()
     packed = np.random.rand(B, idx.size)
     big = pv.array.reshape(B, -1)
