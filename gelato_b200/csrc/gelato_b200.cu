@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "plan_host.h"
@@ -160,6 +161,12 @@ struct GelatoPlan {
   size_t cap_pack = 0;
   int host_threads = 0;
   int update_zero_copy = 1;  // page-locked caller buffers are written from the device (profiles/r01k_e2e.txt)
+  std::vector<std::pair<int64_t, int64_t>> big_runs;  // (first slot, length) of the long runs in xdep_idx
+  const int64_t* d_xdep_small = nullptr;              // the slots outside those runs
+  std::vector<int64_t> h_small;
+  long long n_small = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_kernel = nullptr, ev_copy = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -239,6 +246,20 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
     const int64_t* dx = nullptr;
     if ((rc = upload(p, d->xdep_idx, (size_t)d->n_xdep, &dx)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
     p->d_xdep = dx;
+    // split for the zero-copy route: long runs of consecutive slots go through the copy engine (one strided
+    // 2-D copy per run covers every scenario), the scattered rest is written by a kernel
+    std::vector<int64_t> small;
+    for (int64_t i = 0; i < d->n_xdep;) {
+      int64_t j = i + 1;
+      while (j < d->n_xdep && d->xdep_idx[j] == d->xdep_idx[j - 1] + 1) j++;
+      if (j - i >= 512) p->big_runs.push_back({d->xdep_idx[i], j - i});
+      else small.insert(small.end(), d->xdep_idx + i, d->xdep_idx + j);
+      i = j;
+    }
+    p->n_small = (long long)small.size();
+    p->h_small = small;
+    if ((rc = upload(p, small.data(), small.size(), &dx)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+    p->d_xdep_small = dx;
   }
   const double* tmpl = nullptr;
   if ((rc = upload(p, d->vals_template, (size_t)d->n_vals, &tmpl)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
@@ -261,6 +282,9 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   v.n_aero_rows = (int)ht.aero_rows.size() / 2;
 
   CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&p->ev_kernel, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming));
   CU(cudaEventCreate(&p->ev0));
   CU(cudaEventCreate(&p->ev1));
   *out = p;
@@ -314,6 +338,9 @@ int gelato_plan_destroy(GelatoPlan* p) {
   for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->ev_kernel) cudaEventDestroy(p->ev_kernel);
+  if (p->ev_copy) cudaEventDestroy(p->ev_copy);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   return GELATO_OK;
@@ -501,21 +528,36 @@ static void scatter_scenarios(const int64_t* idx, long long n_xdep, const double
   }
 }
 
+// packed -> vals for scenarios [s0, s1) on `threads` host threads
+static void scatter_parallel(const int64_t* idx, long long n_idx, const double* packed, double* vals, long long n_vals,
+                             int s0, int s1, int threads) {
+  if (threads <= 1 || s1 - s0 < 2) {
+    scatter_scenarios(idx, n_idx, packed, vals, n_vals, s0, s1);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) {
+    const int a = s0 + (int)((long long)(s1 - s0) * t / threads), b = s0 + (int)((long long)(s1 - s0) * (t + 1) / threads);
+    if (a < b) pool.emplace_back(scatter_scenarios, idx, n_idx, packed, vals, n_vals, a, b);
+  }
+  for (auto& th : pool) th.join();
+}
+
 int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
   if (!x || !vals) return fail(GELATO_ERR_ARG, "null buffer");
   if (!p->d_xdep) return fail(GELATO_ERR_ARG, "the plan was created without xdep_idx");
+  if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 in update mode (gridDim.y)");
   if ((rc = ensure_staging(p, n_scen))) return rc;
   const PlanView& v = p->view;
-  const long long nx = p->n_xdep;
   if ((size_t)n_scen > p->cap_pack) {
     if (p->d_pack) cudaFree(p->d_pack);
     if (p->h_pack) cudaFreeHost(p->h_pack);
     p->d_pack = p->h_pack = nullptr;
     p->cap_pack = 0;
-    CU(cudaMalloc(&p->d_pack, (size_t)n_scen * nx * sizeof(double)));
-    CU(cudaMallocHost(&p->h_pack, (size_t)n_scen * nx * sizeof(double)));
+    CU(cudaMalloc(&p->d_pack, (size_t)n_scen * p->n_xdep * sizeof(double)));
+    CU(cudaMallocHost(&p->h_pack, (size_t)n_scen * p->n_xdep * sizeof(double)));
     p->cap_pack = n_scen;
   }
   const size_t nxin = (size_t)n_scen * v.n_vars;
@@ -526,52 +568,64 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
   }
   CU(cudaMemcpyAsync(p->d_x, hx, nxin * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
-  if (p->update_zero_copy && is_pinned(vals)) {
-    if (n_scen > 65535) return fail(GELATO_ERR_ARG, "n_scen > 65535 in update mode (gridDim.y)");
-    double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
-    CU(cudaHostGetDevicePointer((void**)&dev_view, vals, 0));
-    const int threads = 256;
-    const int bx = (int)std::min<long long>((nx + threads - 1) / threads, 4096);
-    k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, p->d_xdep, nx, v.n_vals, dev_view);
-    p->launches++;
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(p->stream));
-    return GELATO_OK;
-  }
-  if ((rc = gelato_pack_xdep_dev(p, p->d_vals, p->d_pack, n_scen, p->stream))) return rc;
-  // device->host in chunks of scenarios, so the host scatter of chunk k overlaps the copy of chunk k+1
-  int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-  const long long total = (long long)n_scen * nx;
-  if (total < (1LL << 18)) threads = 1;
-  threads = std::min(threads, (int)n_scen);
-  const int n_chunks = (n_scen >= 4 * threads && threads > 1) ? 4 : 1;
-  while ((int)p->chunk_ev.size() < n_chunks) {
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    p->chunk_ev.push_back(e);
-  }
-  std::vector<int> bounds(n_chunks + 1);
-  for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n_scen * c / n_chunks);
-  for (int c = 0; c < n_chunks; c++) {
-    const size_t off = (size_t)bounds[c] * nx, cnt = (size_t)(bounds[c + 1] - bounds[c]) * nx;
-    CU(cudaMemcpyAsync(p->h_pack + off, p->d_pack + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaEventRecord(p->chunk_ev[c], p->stream));
-  }
-  const int64_t* idx = p->h_xdep.data();
-  for (int c = 0; c < n_chunks; c++) {
-    CU(cudaEventSynchronize(p->chunk_ev[c]));
-    const int s0 = bounds[c], s1 = bounds[c + 1];
-    if (threads == 1) {
-      scatter_scenarios(idx, nx, p->h_pack, vals, v.n_vals, s0, s1);
-    } else {
-      std::vector<std::thread> pool;
-      for (int t = 0; t < threads; t++) {
-        const int a = s0 + (int)((long long)(s1 - s0) * t / threads), b = s0 + (int)((long long)(s1 - s0) * (t + 1) / threads);
-        if (a < b) pool.emplace_back(scatter_scenarios, idx, nx, p->h_pack, vals, v.n_vals, a, b);
-      }
-      for (auto& th : pool) th.join();
+
+  // Which slots travel packed (gathered on the device, copied, scattered by host threads) and which go
+  // straight to their place: a page-locked `vals` takes the long runs of consecutive slots through the copy
+  // engine (one strided 2-D copy per run covers every scenario; second stream) and, in zero-copy mode, the
+  // scattered rest through a kernel that stores into the buffer's device mapping.
+  const bool direct = is_pinned(vals);
+  const int64_t* pack_idx_dev = direct ? p->d_xdep_small : p->d_xdep;
+  const int64_t* pack_idx_host = direct ? p->h_small.data() : p->h_xdep.data();
+  long long n_pack = direct ? p->n_small : p->n_xdep;
+  if (direct) {
+    CU(cudaEventRecord(p->ev_kernel, p->stream));
+    CU(cudaStreamWaitEvent(p->copy_stream, p->ev_kernel, 0));
+    const size_t pitch = (size_t)v.n_vals * sizeof(double);
+    for (const auto& run : p->big_runs)
+      CU(cudaMemcpy2DAsync(vals + run.first, pitch, p->d_vals + run.first, pitch, (size_t)run.second * sizeof(double),
+                           (size_t)n_scen, cudaMemcpyDeviceToHost, p->copy_stream));
+    CU(cudaEventRecord(p->ev_copy, p->copy_stream));
+    if (p->update_zero_copy && n_pack > 0) {
+      double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
+      CU(cudaHostGetDevicePointer((void**)&dev_view, vals, 0));
+      const int threads = 256;
+      const int bx = (int)std::min<long long>((n_pack + threads - 1) / threads, 4096);
+      k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, pack_idx_dev, n_pack, v.n_vals, dev_view);
+      p->launches++;
+      CU(cudaGetLastError());
+      n_pack = 0;
     }
   }
+  if (n_pack > 0) {
+    const int threads_gpu = 256;
+    const int bx = (int)std::min<long long>((n_pack + threads_gpu - 1) / threads_gpu, 4096);
+    k_pack_xdep<<<dim3(bx, n_scen), threads_gpu, 0, p->stream>>>(p->d_vals, pack_idx_dev, n_pack, v.n_vals, p->d_pack);
+    p->launches++;
+    CU(cudaGetLastError());
+    // device->host in chunks of scenarios, so the host scatter of chunk k overlaps the copy of chunk k+1
+    int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if ((long long)n_scen * n_pack < (1LL << 18)) threads = 1;
+    threads = std::min(threads, (int)n_scen);
+    const int n_chunks = (n_scen >= 4 * threads && threads > 1) ? 4 : 1;
+    while ((int)p->chunk_ev.size() < n_chunks) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->chunk_ev.push_back(e);
+    }
+    std::vector<int> bounds(n_chunks + 1);
+    for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n_scen * c / n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+      const size_t off = (size_t)bounds[c] * n_pack, cnt = (size_t)(bounds[c + 1] - bounds[c]) * n_pack;
+      CU(cudaMemcpyAsync(p->h_pack + off, p->d_pack + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      CU(cudaEventRecord(p->chunk_ev[c], p->stream));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+      CU(cudaEventSynchronize(p->chunk_ev[c]));
+      scatter_parallel(pack_idx_host, n_pack, p->h_pack, vals, v.n_vals, bounds[c], bounds[c + 1], threads);
+    }
+  }
+  if (direct) CU(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
+  CU(cudaStreamSynchronize(p->stream));
   return GELATO_OK;
 }
 

@@ -32,11 +32,20 @@ def main():
     print("B=%d n_vals=%d n_xdep=%d cores=%d" % (B, P.n_vals, P.n_xdep, os.cpu_count()))
     print("residuals host call      %.3f ms" % t(lambda: E.eval_residuals(px.array, B, out=pg.array)))
     print("jacobian full copy       %.3f ms" % t(lambda: E.eval_jacobian(px.array, B, out=pv.array)))
-    for th in (1, 2, 4, 8, 16, 32):
+    pageable = np.empty(B * P.n_vals)
+    E.jacobian_template(pageable, B)
+    for th in (4, 16):
         E.set_host_threads(th)
-        print("jacobian update, %2d thr   %.3f ms" % (th, t(lambda: E.eval_jacobian_update(px.array, pv.array, B))))
+        print("update, pageable buffer (pack all + host scatter), %2d thr   %.3f ms"
+              % (th, t(lambda: E.eval_jacobian_update(px.array, pageable, B))))
+    E.set_update_zero_copy(False)
+    for th in (1, 4, 8, 16):
+        E.set_host_threads(th)
+        print("update, pinned: 2-D copies + packed scattered slots, %2d thr  %.3f ms"
+              % (th, t(lambda: E.eval_jacobian_update(px.array, pv.array, B))))
     E.set_update_zero_copy(True)
-    print("jacobian update, zero-copy %.3f ms" % t(lambda: E.eval_jacobian_update(px.array, pv.array, B)))
+    print("update, pinned: 2-D copies + zero-copy scattered slots       %.3f ms"
+          % t(lambda: E.eval_jacobian_update(px.array, pv.array, B)))
     want = E.eval_jacobian(px.array, B).copy()
     assert np.array_equal(pv.array.reshape(B, -1), want), "zero-copy update differs from the full copy"
     E.set_update_zero_copy(False)
