@@ -4,7 +4,7 @@ solver is scipy trust-constr, NOT IPOPT), once on the CPU oracle's callbacks and
 callbacks: same solver, same problem, same start.  Prints converged payload, event times, iteration
 counts and the time spent inside the callbacks.
 
-    python tools/solve_example.py --arm cpu|gpu|both [--maxiter 200] [--factor 1]
+    python tests/scripts/solve_example.py --arm cpu|gpu|both [--maxiter 200] [--factor 1]
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers  # noqa: E402
