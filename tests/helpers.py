@@ -173,6 +173,11 @@ def variant_inputs(name):
                event("TECO", 700.0, float("nan"), False, 0.0, "hold", 3),
                event("SEP3", 720.0, "TECO", False, 0.0, "hold", 2),
                event("SIMEND", 725.0, "SEP3", False, 0.0, "hold", 2)]
+    elif name == "iip_orbital":  # IIP rows where there is no impact point (orbital speed): the leaf returns
+        # zeros (iip.cpp:49-128), the rows become constants and their finite differences exact zeros
+        fc["waypoint"] = {"SECO": {"lat_IIP": {"min": -10.0}, "lon_IIP": {"exact": 150.0}},
+                          "SEP2": {"lon_IIP": {"max": 190.0}},
+                          "KICKTURN": {"lat_IIP": {"max": 60.0}, "lon_IIP": {"min": 100.0}}}
     elif name == "bare":  # no waypoint / antenna blocks, no aero rows, no user constraint rows
         fc.pop("waypoint")
         fc.pop("antenna")

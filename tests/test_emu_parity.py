@@ -27,7 +27,7 @@ def _setup(variant, factor, max_nodes=12, user=True):
 
 @pytest.mark.parametrize("variant,factor,user", [
     ("example", 1, True), ("example", 3, True), ("fuel_inclination", 1, True), ("all_aero", 2, True),
-    ("waypoints", 1, True), ("neg_area", 1, True), ("three_stage", 1, True), ("waypoints", 2, False), ("bare", 1, False),
+    ("waypoints", 1, True), ("neg_area", 1, True), ("three_stage", 1, True), ("iip_orbital", 1, True), ("waypoints", 2, False), ("bare", 1, False),
 ])
 def test_emulated_kernels_match_oracle_bitwise(variant, factor, user):
     p, u, c, x0, O, P = _setup(variant, factor, user=user)

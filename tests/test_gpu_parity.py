@@ -44,7 +44,7 @@ def test_library_is_the_cuda_build():
 
 @pytest.mark.parametrize("variant,factor,user", [
     ("example", 1, True), ("example", 4, True), ("example", 15, True), ("fuel_inclination", 1, True),
-    ("all_aero", 2, True), ("waypoints", 1, True), ("neg_area", 1, True), ("three_stage", 2, True), ("waypoints", 3, False), ("bare", 1, False),
+    ("all_aero", 2, True), ("waypoints", 1, True), ("neg_area", 1, True), ("three_stage", 2, True), ("iip_orbital", 1, True), ("waypoints", 3, False), ("bare", 1, False),
 ])
 def test_gpu_matches_oracle_bitwise(variant, factor, user):
     prob, O, x0 = _problem(variant, factor, max_nodes=20 if factor == 15 else 12, user=user)
