@@ -276,10 +276,10 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   p->jac_blocks = const_cast<int32_t*>(tb);
   if ((rc = upload(p, ht.res_blocks.data(), ht.res_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->res_blocks = const_cast<int32_t*>(tb);
-  if ((rc = upload(p, ht.node_sec.data(), ht.node_sec.size(), &v.node_sec)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
-  if ((rc = upload(p, ht.jac_nodes.data(), ht.jac_nodes.size(), &v.jac_nodes)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.node_rec.data(), ht.node_rec.size(), &v.node_rec)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  if ((rc = upload(p, ht.jac_rec.data(), ht.jac_rec.size(), &v.jac_rec)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   if ((rc = upload(p, ht.aero_rows.data(), ht.aero_rows.size(), &v.aero_rows)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
-  v.n_aero_rows = (int)ht.aero_rows.size() / 2;
+  v.n_aero_rows = (int)ht.aero_rows.size();
 
   CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));

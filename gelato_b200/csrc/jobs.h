@@ -82,9 +82,9 @@ struct PlanView {
   const int64_t* evt_i64;
   const double* evt_f64;
   /* built by plan_host.h at plan creation */
-  const int32_t* node_sec;  /* [N] section of collocation node g (natural order) */
-  const int32_t* jac_nodes; /* [N] node ids grouped by Jacobian block role */
-  const int32_t* aero_rows; /* [n_aero_rows][2] (aero job, row inside the job) */
+  const struct NodeRec* node_rec; /* [N] collocation nodes in natural order */
+  const struct NodeRec* jac_rec;  /* [N] the same records grouped by Jacobian block role */
+  const struct AeroRec* aero_rows; /* [n_aero_rows] one record per aero constraint row */
   int n_aero_rows;
 };
 
@@ -124,8 +124,16 @@ P_HD double residue(double x, double dx) {
   double y = x + dx;
   return y - dx;
 }
+/* n perturb/restore cycles.  n is a small per-variable count compiled into the plan (how many earlier
+ * groups of `sens` touched the variable); four predicated steps cover it without a data-dependent
+ * branch (ncu r01j: the loop form was 16 % of the instruction-fetch stalls), a loop takes any excess. */
 P_HD double residue_n(double x, double dx, int n) {
-  for (int i = 0; i < n; i++) x = residue(x, dx);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double y = residue(x, dx);
+    x = (i < n) ? y : x;
+  }
+  for (int i = 4; i < n; i++) x = residue(x, dx);
   return x;
 }
 
@@ -173,21 +181,32 @@ P_HD double time_node(const double* tau, int r, double to, double tf) {
 /* reference: con_dynamics.py:292-496 (velocity), :536-632 (quaternion),      */
 /*            :155-213 (position)                                             */
 /* ========================================================================= */
-struct NodeRef {
-  int sec, j, row, ua, n, flags;
-  const int32_t* si;
+/* everything a job needs to know about one collocation node, in one 32-byte record (two 16-byte loads)
+ * instead of a chain of dependent table look-ups; built by plan_host.h */
+struct alignas(16) NodeRec {
+  int32_t sec, j, row, ua; /* section, LGR node index inside it, state row, first control row of the section */
+  int32_t n, flags, d_off, tau_off; /* nodes in the section, GSF_*, offsets of its D block and tau */
 };
-P_HD NodeRef node_ref(const PlanView& P, int g) {
+struct NodeRef {
+  int sec, j, row, ua, n, flags, d_off, tau_off;
+  const int32_t* si; /* the section's row of sec_i32 (address only: no load) */
+};
+P_HD NodeRef node_from_rec(const PlanView& P, const NodeRec& q) {
   NodeRef r;
-  r.sec = P.node_sec[g];
-  r.si = P.sec_i32 + r.sec * GS_I32_COLS;
-  r.ua = r.si[GS_UA];
-  r.n = r.si[GS_N];
-  r.flags = r.si[GS_FLAGS];
-  r.j = g - r.ua;                 /* LGR node index inside the section */
-  r.row = r.si[GS_XA] + 1 + r.j;  /* state row */
+  r.sec = q.sec; r.j = q.j; r.row = q.row; r.ua = q.ua;
+  r.n = q.n; r.flags = q.flags; r.d_off = q.d_off; r.tau_off = q.tau_off;
+  r.si = P.sec_i32 + q.sec * GS_I32_COLS;
   return r;
 }
+/* the same for one aero constraint row */
+struct alignas(16) AeroRec {
+  int32_t job, r, sec, row;        /* aero job, row inside it, section, state row */
+  int32_t kind, nk, tau_off, row0; /* 0 alpha / 1 q / 2 q-alpha, rows of the job, tau offset, first residual row */
+};
+
+/* node k of the Jacobian kernel's role-grouped order / node g of the natural order */
+P_HD NodeRef jac_node(const PlanView& P, int k) { return node_from_rec(P, P.jac_rec[k]); }
+P_HD NodeRef res_node(const PlanView& P, int g) { return node_from_rec(P, P.node_rec[g]); }
 
 /* mass, pos[3], vel[3], quat[4] of state row `row` as column `lane` evaluates them: the
  * reference perturbs views of xdict in place, so variables visited before this column
@@ -265,7 +284,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   const bool air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
   const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double dt = tf - to;
-  const double* D = P.d_pool + nr.si[GS_D_OFF];
+  const double* D = P.d_pool + nr.d_off;
   const double d_diag = D[(long long)j * (n + 1) + (j + 1)];
   const long long n3 = 3LL * n, n4 = 4LL * n, nn1 = (long long)n * (n + 1);
 
@@ -348,7 +367,7 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
   /* lane-major items: neighbouring threads run the same column's formula on neighbouring nodes */
   for (int item = tid; item < count * 15; item += nthreads) {
     const int lane = item / count, nl = item - lane * count;
-    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    const NodeRef nr = jac_node(P, start + nl);
     const double* fc = sm.f + (nl * 14) * 3;
     const double* qc = sm.q + (nl * 7) * 4;
     dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
@@ -372,7 +391,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
     if (tid < GJ_A_THREADS) {
       if (tid >= count * NPV) return;
       const int nl = tid / NPV, pv = tid - nl * NPV;
-      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      const NodeRef nr = jac_node(P, start + nl);
       double p[3];
       pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
       const Tables tb = scen_tables(P, scen);
@@ -382,24 +401,24 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const int item = tid - GJ_A_THREADS;
       if (item >= count * NRV) return;
       const int nl = item / NRV, rv = item - nl * NRV;
-      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      const NodeRef nr = jac_node(P, start + nl);
       double p[3];
       pos_variant(x + P.off_pos + 3 * nr.row, rv_pv(rv), dx, p);
       const double to0 = x[P.off_t + nr.sec], tf0 = x[P.off_t + nr.sec + 1];
       const double to = (rv == 5) ? to0 + dx : to0;
       const double tf = (rv == 6) ? tf0 + dx : tf0;
-      const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
+      const double tn = time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
     } else {
       const int nl = tid - GJ_Q_BASE;
       if (nl < 0 || nl >= count) return;
-      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      const NodeRef nr = jac_node(P, start + nl);
       if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
     }
   } else if (phase == 2) {
     if (tid >= count * 14) return;
     const int nl = tid / 14, lane = tid - nl * 14;
-    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    const NodeRef nr = jac_node(P, start + nl);
     double v[11], rp[RP_COLS];
     dyn_col_state(P, x, nr.row, lane, true, dx, v);
     const double* pp = sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS;
@@ -431,7 +450,7 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
     if (tid < GN_A_THREADS) {
       if (tid >= count * NPV) return;
       const int nl = tid / NPV, pv = tid - nl * NPV;
-      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      const NodeRef nr = jac_node(P, start + nl);
       double p[3];
       pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
       const Vec3 g = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
@@ -442,14 +461,14 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
     } else {
       const int nl = tid - GJ_Q_BASE;
       if (nl < 0 || nl >= count) return;
-      const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+      const NodeRef nr = jac_node(P, start + nl);
       if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
     }
   } else if (phase == 2) {
     if (tid >= count * 9) return;
     const int nl = tid / 9, c9 = tid - nl * 9;
     const int lane = c9 < 5 ? c9 : c9 + 3;
-    const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+    const NodeRef nr = jac_node(P, start + nl);
     double v[11];
     dyn_col_state(P, x, nr.row, lane, false, dx, v);
     const double* g = sm.pp + (nl * NPV + lane_pv(lane)) * 3;
@@ -474,7 +493,7 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
                         int phase, const JacScratch& sm) {
   const int nl = tid >> 4, lane = tid & 15;
   if (nl >= count) return;
-  const NodeRef nr = node_ref(P, P.jac_nodes[start + nl]);
+  const NodeRef nr = jac_node(P, start + nl);
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   const bool air = nr.flags & GSF_AIR, air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
@@ -491,7 +510,7 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
       const Quat q = q4(v[7], v[8], v[9], v[10]);
       Vec3 f;
       if (air) {
-        const double tn = time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf);
+        const double tn = time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf);
         f = rhs_velocity_air(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q, tn, sp, un, scen_tables(P, scen));
       } else {
         f = rhs_velocity_noair(v[0], v3(v[1], v[2], v[3]), q, sp, un);
@@ -524,7 +543,7 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
 P_HD void dyn_res_phase0(const PlanView& P, int scen, const double* x, int g0, int count, int tid, ResScratch& sm) {
   const int nl = tid >> 1, half = tid & 1;
   if (nl >= count) return;
-  const NodeRef nr = node_ref(P, g0 + nl);
+  const NodeRef nr = res_node(P, g0 + nl);
   if (!(nr.flags & GSF_AIR)) return;
   const Units un = scen_units(P, scen);
   const int row = nr.row;
@@ -535,13 +554,13 @@ P_HD void dyn_res_phase0(const PlanView& P, int scen, const double* x, int g0, i
     pos_part(px, py, pz, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND, sm.pp[nl]);
   } else {
     const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
-    rotq_part(px, py, pz, time_node(P.tau_pool + nr.si[GS_TAU_OFF], nr.j + 1, to, tf), sm.rq[nl]);
+    rotq_part(px, py, pz, time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf), sm.rq[nl]);
   }
 }
 
 P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, int count, int tid, ResScratch& sm) {
   if (tid >= count) return;
-  const NodeRef nr = node_ref(P, g0 + tid);
+  const NodeRef nr = res_node(P, g0 + tid);
   const int row = nr.row;
   const Units un = scen_units(P, scen);
   const SecParam sp = sec_param(P, scen, nr.sec);
@@ -596,12 +615,12 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
   /* column-major items: neighbouring threads run the same state column on neighbouring nodes */
   for (int item = tid; item < count * 11; item += nthreads) {
     const int col = item / count, nl = item - col * count;
-    const NodeRef nr = node_ref(P, g0 + nl);
+    const NodeRef nr = res_node(P, g0 + nl);
     const int32_t* si = nr.si;
     const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
     const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
     const double dt = tf - to;
-    const double* Drow = P.d_pool + si[GS_D_OFF] + (long long)j * (n + 1);
+    const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
     if (col == 0) { /* mass: con_dynamics.py:53-61 */
       double r;
       if (flags & GSF_ENGINE_ON) {
@@ -688,11 +707,9 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
     const int per = is_a ? NPV : NRV;
     if (tid >= GJ_A_THREADS + GJ_B_THREADS || item >= count * per) return;
     const int nl = item / per, var = item - nl * per;
-    const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
-    const int sec = P.aero_i32[job * GA_I32_COLS + GA_SECTION];
-    const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
+    const AeroRec ar = P.aero_rows[start + nl];
     double v[10], to, tf, p[3];
-    aero_base(P, x, sec, si[GS_XA] + r, v, &to, &tf);
+    aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
     if (is_a) {
       pos_variant(v, var, dx, p);
       const Tables tb = scen_tables(P, scen);
@@ -701,19 +718,18 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
       pos_variant(v, rv_pv(var), dx, p);
       if (var == 5) to = to + dx;
       if (var == 6) tf = tf + dx;
-      const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], r, to, tf);
+      const double tn = time_node(P.tau_pool + ar.tau_off, ar.r, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
     }
   } else if (phase == 2) {
     if (tid >= count * 13) return;
     const int nl = tid / 13, lane = tid - nl * 13;
-    const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
-    const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
-    const int kind = ai[GA_KIND], sec = ai[GA_SECTION];
+    const AeroRec ar = P.aero_rows[start + nl];
+    const int kind = ar.kind, job = ar.job;
     const bool has_quat = kind != 1;
     if (!has_quat && lane >= 7 && lane <= 10) return;
     double v[10], to, tf;
-    aero_base(P, x, sec, P.sec_i32[sec * GS_I32_COLS + GS_XA] + r, v, &to, &tf);
+    aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
     if (lane != 0) { /* the gradient works on a copy: columns leave residue inside the copy only */
       const int pidx = (lane <= 10) ? lane - 1 : 10;
       for (int w = 0; w < 10; w++) {
@@ -734,10 +750,9 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
   } else {
     for (int item = tid; item < count * 12; item += GJ_THREADS) {
       const int lane = 1 + item / count, nl = item % count;
-      const int job = P.aero_rows[2 * (start + nl)], r = P.aero_rows[2 * (start + nl) + 1];
-      const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
-      const int64_t* aj = P.aero_i64 + job * GA_I64_COLS;
-      const int kind = ai[GA_KIND], nk = ai[GA_NK];
+      const AeroRec ar = P.aero_rows[start + nl];
+      const int64_t* aj = P.aero_i64 + ar.job * GA_I64_COLS;
+      const int kind = ar.kind, nk = ar.nk, r = ar.r;
       if (kind == 1 && lane >= 7 && lane <= 10) continue;
       const double gval = -fd_div(sm.f[(nl * 14 + lane) * 3] - sm.f[(nl * 14) * 3], dx); /* -dfdx (con_aero.py:439-461) */
       if (lane <= 3) vals[aj[GA_J_POS] + (long long)(lane - 1) * nk + r] = gval;
@@ -750,14 +765,11 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
 }
 
 /* residual kernel: one thread per aero row, pristine inputs: 1 - f (con_aero.py:89-248) */
-P_HD void aero_res(const PlanView& P, int scen, const double* x, double* g, int job, int r) {
-  const int32_t* ai = P.aero_i32 + job * GA_I32_COLS;
-  const int sec = ai[GA_SECTION];
-  const int32_t* si = P.sec_i32 + sec * GS_I32_COLS;
+P_HD void aero_res(const PlanView& P, int scen, const double* x, double* g, const AeroRec& ar) {
   double v[10];
-  aero_load(P, x, si[GS_XA] + r, v);
-  const double tn = time_node(P.tau_pool + si[GS_TAU_OFF], r, x[P.off_t + sec], x[P.off_t + sec + 1]);
-  g[ai[GA_ROW0] + r] = 1.0 - aero_value(P, scen, ai[GA_KIND], v, tn, P.aero_f64[job * GA_F64_COLS + GA_LIMIT]);
+  aero_load(P, x, ar.row, v);
+  const double tn = time_node(P.tau_pool + ar.tau_off, ar.r, x[P.off_t + ar.sec], x[P.off_t + ar.sec + 1]);
+  g[ar.row0 + ar.r] = 1.0 - aero_value(P, scen, ar.kind, v, tn, P.aero_f64[ar.job * GA_F64_COLS + GA_LIMIT]);
 }
 
 /* ========================================================================= */
@@ -964,8 +976,7 @@ P_HD void res_block_phase1(const PlanView& P, int scen, const int32_t* bt, const
     case BR_DYN: dyn_res_phase1(P, scen, x, bt[BT_START], bt[BT_COUNT], tid, sm); break;
     case BR_AERO:
       if (tid < bt[BT_COUNT]) {
-        const int32_t* ar = P.aero_rows + 2 * (bt[BT_START] + tid);
-        aero_res(P, scen, x, g, ar[0], ar[1]);
+        aero_res(P, scen, x, g, P.aero_rows[bt[BT_START] + tid]);
       }
       break;
     case BR_EVT:

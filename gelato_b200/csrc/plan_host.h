@@ -26,9 +26,9 @@ static inline void planview_scalars(const GelatoPlanDesc* d, PlanView& v) {
 
 struct HostTables {
   std::vector<int32_t> jac_blocks, res_blocks; /* BT_COLS ints per block */
-  std::vector<int32_t> node_sec;               /* [N] */
-  std::vector<int32_t> jac_nodes;              /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
-  std::vector<int32_t> aero_rows;              /* [rows][2] */
+  std::vector<NodeRec> node_rec;               /* [N] natural order */
+  std::vector<NodeRec> jac_rec;                /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
+  std::vector<AeroRec> aero_rows;              /* one per aero constraint row */
 };
 
 static inline void push_block(std::vector<int32_t>& t, int role, int job, int start, int count) {
@@ -43,28 +43,34 @@ static inline void push_chunks(std::vector<int32_t>& t, int role, int first, int
 
 static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
   const int S = d->n_sections, N = d->n_nodes;
-  h.node_sec.assign(N, 0);
+  h.node_rec.assign(N, NodeRec());
   std::vector<int32_t> air, vac, gen;
   for (int s = 0; s < S; s++) {
     const int32_t* si = d->sec_i32 + s * GS_I32_COLS;
     const int flags = si[GS_FLAGS];
     for (int j = 0; j < si[GS_N]; j++) {
       const int g = si[GS_UA] + j;
-      h.node_sec[g] = s;
+      NodeRec& q = h.node_rec[g];
+      q.sec = s; q.j = j; q.row = si[GS_XA] + 1 + j; q.ua = si[GS_UA];
+      q.n = si[GS_N]; q.flags = flags; q.d_off = si[GS_D_OFF]; q.tau_off = si[GS_TAU_OFF];
       if (flags & GSF_AIR_FD) air.push_back(g);
       else if (!(flags & GSF_AIR)) vac.push_back(g);
       else gen.push_back(g);
     }
   }
-  h.jac_nodes = air;
-  h.jac_nodes.insert(h.jac_nodes.end(), vac.begin(), vac.end());
-  h.jac_nodes.insert(h.jac_nodes.end(), gen.begin(), gen.end());
-  for (int k = 0; k < d->n_aero; k++)
-    for (int r = 0; r < d->aero_i32[k * GA_I32_COLS + GA_NK]; r++) {
-      h.aero_rows.push_back(k);
-      h.aero_rows.push_back(r);
+  for (const std::vector<int32_t>* list : {&air, &vac, &gen})
+    for (int32_t g : *list) h.jac_rec.push_back(h.node_rec[g]);
+  for (int k = 0; k < d->n_aero; k++) {
+    const int32_t* ai = d->aero_i32 + k * GA_I32_COLS;
+    const int32_t* si = d->sec_i32 + ai[GA_SECTION] * GS_I32_COLS;
+    for (int r = 0; r < ai[GA_NK]; r++) {
+      AeroRec q;
+      q.job = k; q.r = r; q.sec = ai[GA_SECTION]; q.row = si[GS_XA] + r;
+      q.kind = ai[GA_KIND]; q.nk = ai[GA_NK]; q.tau_off = si[GS_TAU_OFF]; q.row0 = ai[GA_ROW0];
+      h.aero_rows.push_back(q);
     }
-  const int n_aero_rows = (int)h.aero_rows.size() / 2;
+  }
+  const int n_aero_rows = (int)h.aero_rows.size();
 
   std::vector<int32_t>& jb = h.jac_blocks;
   push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GJ_NODES);

@@ -26,10 +26,10 @@ static PlanView host_view(const GelatoPlanDesc* d) {
 }
 
 static void attach_tables(PlanView& v, const HostTables& h) {
-  v.node_sec = h.node_sec.data();
-  v.jac_nodes = h.jac_nodes.data();
+  v.node_rec = h.node_rec.data();
+  v.jac_rec = h.jac_rec.data();
   v.aero_rows = h.aero_rows.data();
-  v.n_aero_rows = (int)h.aero_rows.size() / 2;
+  v.n_aero_rows = (int)h.aero_rows.size();
 }
 
 static void apply_scen(PlanView& v, const GelatoScenarioDesc* sc) {
