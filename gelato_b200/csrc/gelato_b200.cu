@@ -205,8 +205,7 @@ int gelato_device_count(void) {
 
 int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   if (!d || !out) return fail(GELATO_ERR_ARG, "null argument");
-  if (d->n_sections <= 0 || d->n_nodes <= 0) return fail(GELATO_ERR_ARG, "empty problem");
-  if (!(d->dx > 0.0)) return fail(GELATO_ERR_ARG, "dx must be positive");
+  if (const char* why = validate_desc(d)) return fail(GELATO_ERR_ARG, why);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -281,12 +280,16 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   if ((rc = upload(p, ht.aero_rows.data(), ht.aero_rows.size(), &v.aero_rows)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   v.n_aero_rows = (int)ht.aero_rows.size();
 
-  CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&p->ev_kernel, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming));
-  CU(cudaEventCreate(&p->ev0));
-  CU(cudaEventCreate(&p->ev1));
+  cudaError_t ce = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_kernel, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&p->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&p->ev1);
+  if (ce != cudaSuccess) {
+    gelato_plan_destroy(p);
+    return fail(GELATO_ERR_CUDA, std::string("stream / event creation: ") + cudaGetErrorString(ce));
+  }
   *out = p;
   return GELATO_OK;
 }

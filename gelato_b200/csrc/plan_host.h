@@ -24,6 +24,59 @@ static inline void planview_scalars(const GelatoPlanDesc* d, PlanView& v) {
   v.n_lin = d->n_lin; v.n_aero = d->n_aero; v.n_evt = d->n_evt;
 }
 
+/* Bounds of every index table of a plan description; returns NULL or what is wrong.  The kernels trust
+ * these tables, so a description that fails here is refused before anything is uploaded. */
+static inline const char* validate_desc(const GelatoPlanDesc* d) {
+  if (!d) return "null description";
+  const long long S = d->n_sections, N = d->n_nodes, M = N + S;
+  if (S <= 0 || N <= 0) return "empty problem";
+  if (!(d->dx > 0.0)) return "dx must be positive";
+  if (d->n_rows <= 0 || d->n_vals < 0) return "bad n_rows / n_vals";
+  if (!d->sec_i32 || !d->sec_i64 || !d->sec_f64 || !d->d_pool || !d->tau_pool) return "missing section tables";
+  if (!d->vals_template && d->n_vals > 0) return "missing vals_template";
+  if (d->n_wind < 2 || !d->wind || d->n_ca < 2 || !d->ca) return "wind / CA tables need at least two rows";
+  const long long n_vars = 11 * M + 2 * N + S + 1;
+  long long nodes = 0;
+  for (long long s = 0; s < S; s++) {
+    const int32_t* si = d->sec_i32 + s * GS_I32_COLS;
+    const long long n = si[GS_N];
+    if (n < 1) return "a section has no nodes";
+    if (si[GS_UA] != nodes) return "sections must tile the control rows in order";
+    if (si[GS_XA] < 0 || si[GS_XA] + n + 1 > M) return "state rows of a section out of range";
+    if (si[GS_D_OFF] < 0 || si[GS_D_OFF] + n * (n + 1) > d->d_pool_len) return "D block outside the pool";
+    if (si[GS_TAU_OFF] < 0 || si[GS_TAU_OFF] + n > d->tau_pool_len) return "tau outside the pool";
+    for (int c = GS_R_MASS; c <= GS_R_QUAT; c++)
+      if (si[c] < 1 || si[c] >= d->n_rows) return "residual row offset of a section out of range";
+    nodes += n;
+  }
+  if (nodes != N) return "section node counts do not add up to n_nodes";
+  if (d->n_lin < 0 || d->n_aero < 0 || d->n_evt < 0) return "negative table length";
+  for (long long k = 0; k < d->n_lin; k++) {
+    const int32_t* li = d->lin_i32 + k * GL_I32_COLS;
+    if (li[GL_ROW] < 1 || li[GL_ROW] >= d->n_rows) return "linear row out of range";
+    if (li[GL_IDX_PLUS] < -1 || li[GL_IDX_PLUS] >= n_vars || li[GL_IDX_MINUS] < -1 || li[GL_IDX_MINUS] >= n_vars)
+      return "linear row reads outside x";
+  }
+  for (long long k = 0; k < d->n_aero; k++) {
+    const int32_t* ai = d->aero_i32 + k * GA_I32_COLS;
+    if (ai[GA_KIND] < 0 || ai[GA_KIND] > 2) return "unknown aero kind";
+    if (ai[GA_SECTION] < 0 || ai[GA_SECTION] >= S) return "aero job section out of range";
+    const long long n = d->sec_i32[ai[GA_SECTION] * GS_I32_COLS + GS_N];
+    if (ai[GA_NK] < 1 || ai[GA_NK] > n + 1) return "aero job has more rows than its section has state nodes";
+    if (ai[GA_ROW0] < 1 || ai[GA_ROW0] + ai[GA_NK] > d->n_rows) return "aero rows out of range";
+  }
+  for (long long k = 0; k < d->n_evt; k++) {
+    const int32_t* ei = d->evt_i32 + k * GE_I32_COLS;
+    if (ei[GE_TYPE] < GE_LLH || ei[GE_TYPE] > GE_USER_PERIGEE) return "unknown event job type";
+    if (ei[GE_SROW] < 0 || ei[GE_SROW] >= M) return "event job state row out of range";
+    if (ei[GE_TIDX] < -1 || ei[GE_TIDX] > S) return "event job time index out of range";
+    if (ei[GE_ROW] < 1 || ei[GE_ROW] + ei[GE_NROW] > d->n_rows || ei[GE_NROW] < 1 || ei[GE_NROW] > 3)
+      return "event job rows out of range";
+    if (ei[GE_COMP] < 0 || ei[GE_COMP] > 2) return "event job component out of range";
+  }
+  return nullptr;
+}
+
 struct HostTables {
   std::vector<int32_t> jac_blocks, res_blocks; /* BT_COLS ints per block */
   std::vector<NodeRec> node_rec;               /* [N] natural order */

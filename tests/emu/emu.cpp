@@ -48,6 +48,7 @@ extern "C" int emu_unfused_check(void) {
 
 extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
                                   double* g_all, int n_scen) {
+  if (validate_desc(d)) return -1;
   PlanView P = host_view(d);
   apply_scen(P, sc);
   HostTables h;
@@ -71,6 +72,7 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
 
 extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
                                  double* vals_all, int n_scen) {
+  if (validate_desc(d)) return -1;
   PlanView P = host_view(d);
   apply_scen(P, sc);
   HostTables h;

@@ -50,13 +50,15 @@ class Emulator:
     def eval_residuals(self, x, n_scen=1):
         x = np.ascontiguousarray(x, dtype=np.float64)
         g = np.full(n_scen * self.plan.n_rows, np.nan)
-        self.L.emu_eval_residuals(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd), n_scen)
+        rc = self.L.emu_eval_residuals(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd), n_scen)
+        assert rc == 0, "the plan description failed validate_desc (plan_host.h)"
         return g if n_scen == 1 else g.reshape(n_scen, -1)
 
     def eval_jacobian(self, x, n_scen=1):
         x = np.ascontiguousarray(x, dtype=np.float64)
         v = np.full(n_scen * self.plan.n_vals, np.nan)
-        self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen)
+        rc = self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen)
+        assert rc == 0, "the plan description failed validate_desc (plan_host.h)"
         return v if n_scen == 1 else v.reshape(n_scen, -1)
 
 

@@ -89,3 +89,48 @@ def test_enum_constants_match_header():
     assert got == [gp.GS_I32_COLS, gp.GS_I64_COLS, gp.GS_F64_COLS, gp.GL_I32_COLS, gp.GL_F64_COLS, gp.GA_I32_COLS,
                    gp.GA_I64_COLS, gp.GE_I32_COLS, gp.GE_I64_COLS, gp.GE_F64_COLS]
     assert np.dtype("i4").itemsize == 4
+
+
+def test_plan_create_refuses_malformed_descriptions():
+    """The kernels trust the plan's index tables, so gelato_plan_create checks their bounds first
+    (before it even looks for a device): a corrupted description is GELATO_ERR_ARG with a reason."""
+    L = engine.load_library()
+    p, u, c, x0 = helpers.example_problem()
+    P = helpers.compiled_plan(p, u, c)
+
+    def create(mutate):
+        desc, keep = engine.make_desc(P)
+        mutate(desc, keep)
+        h = ctypes.c_void_p()
+        rc = L.gelato_plan_create(ctypes.byref(desc), 0, ctypes.byref(h))
+        msg = L.gelato_last_error().decode()
+        if rc == 0:
+            L.gelato_plan_destroy(h)
+        return rc, msg
+
+    def bad_section(desc, keep):
+        a = np.array(P.sec_i32, dtype=np.int32, copy=True)
+        a[3, 2] = 10 ** 6  # GS_XA far outside the state rows
+        keep.append(a)
+        desc.sec_i32 = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    def bad_lin(desc, keep):
+        a = np.array(P.lin_i32, dtype=np.int32, copy=True)
+        a[0, 1] = P.n_vars + 5
+        keep.append(a)
+        desc.lin_i32 = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    def bad_dx(desc, keep):
+        desc.dx = 0.0
+
+    def bad_evt(desc, keep):
+        a = np.array(P.evt_i32, dtype=np.int32, copy=True)
+        a[0, 0] = 99
+        keep.append(a)
+        desc.evt_i32 = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    for mutate, word in ((bad_section, "state rows"), (bad_lin, "outside x"), (bad_dx, "dx"), (bad_evt, "event job type")):
+        rc, msg = create(mutate)
+        assert rc == -1 and word in msg, (rc, msg)
+    rc, msg = create(lambda d, k: None)  # the untouched description passes validation
+    assert rc == 0 or "no CUDA device" in msg, (rc, msg)
