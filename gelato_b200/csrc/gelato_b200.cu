@@ -30,7 +30,7 @@
 #endif
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
-           const double* __restrict__ x_all, double* __restrict__ vals_all) {
+           const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ vals_all) {
   __shared__ JacStore store;
   const JacScratch sm = jac_scratch(store);
   // role-major launch order: block b of every scenario before block b+1 of any, so the blocks
@@ -39,14 +39,16 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* vals = vals_all + (size_t)scen * P.n_vals;
+  // which scenario's parameter blocks this batch slot uses (a coalesced subset of the configured scenarios)
+  const int sid = scen_ids ? scen_ids[scen] : scen;
   const bool two_phase = jac_role_two_phase(bt[BT_ROLE]);
-  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 0, sm);
+  jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 0, sm);
   __syncthreads();
   if (!two_phase) {
-    jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 2, sm);
+    jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 2, sm);
     __syncthreads();
   }
-  jac_block_phase(P, scen, bt, x, vals, threadIdx.x, 3, sm);
+  jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 3, sm);
 }
 
 #ifndef GR_MIN_BLOCKS
@@ -54,21 +56,22 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
 #endif
 __global__ void __launch_bounds__(GR_THREADS, GR_MIN_BLOCKS)
 k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
-            const double* __restrict__ x_all, double* __restrict__ g_all) {
+            const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ g_all) {
   __shared__ ResScratch sm;
   const int scen = blockIdx.x % n_scen;
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* g = g_all + (size_t)scen * P.n_rows;
+  const int sid = scen_ids ? scen_ids[scen] : scen;
   const bool dyn = bt[BT_ROLE] == BR_DYN;
   if (dyn) {
-    res_block_phase0(P, scen, bt, x, threadIdx.x, sm);
+    res_block_phase0(P, sid, bt, x, threadIdx.x, sm);
     __syncthreads();
   }
-  res_block_phase1(P, scen, bt, x, g, threadIdx.x, sm);
+  res_block_phase1(P, sid, bt, x, g, threadIdx.x, sm);
   if (dyn) {
     __syncthreads();
-    res_block_phase2(P, scen, bt, x, g, threadIdx.x, GR_THREADS, sm);
+    res_block_phase2(P, sid, bt, x, g, threadIdx.x, GR_THREADS, sm);
   }
 }
 
@@ -153,6 +156,10 @@ struct GelatoPlan {
   double *d_x = nullptr, *d_g = nullptr, *d_vals = nullptr;
   double *h_x = nullptr, *h_out = nullptr;  // pinned
   size_t cap_scen = 0;
+  // subset batches (gelato_eval_*_ids)
+  int32_t* d_ids = nullptr;
+  double* d_vals_ids = nullptr;
+  size_t cap_ids = 0;
   // update mode
   const int64_t* d_xdep = nullptr;
   std::vector<int64_t> h_xdep;
@@ -186,8 +193,10 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
 
 // one Jacobian evaluation on `st`.  (A two-launch variant -- phase 0 barrier-free with pp | rq | q staged
 // through L2 -- was measured 38 % slower than this fused kernel: profiles/r01i_split_ab.txt.)
-static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* vals_dev, int n_scen, cudaStream_t st) {
-  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, x_dev, vals_dev);
+static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* vals_dev, int n_scen, cudaStream_t st,
+                           const int32_t* ids_dev = nullptr) {
+  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, ids_dev, x_dev,
+                                                                        vals_dev);
   p->launches++;
   return GELATO_OK;
 }
@@ -338,6 +347,8 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->h_out) cudaFreeHost(p->h_out);
   if (p->d_pack) cudaFree(p->d_pack);
   if (p->h_pack) cudaFreeHost(p->h_pack);
+  if (p->d_ids) cudaFree(p->d_ids);
+  if (p->d_vals_ids) cudaFree(p->d_vals_ids);
   for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -373,7 +384,7 @@ int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev,
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(p->view, p->res_blocks, n_scen, x_dev, g_dev);
+  k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, g_dev);
   p->launches++;
   CU(cudaGetLastError());
   return GELATO_OK;
@@ -439,7 +450,8 @@ static bool is_pinned(const void* ptr) {
   return a.type == cudaMemoryTypeHost;
 }
 
-static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int32_t n_scen) {
+static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int32_t n_scen,
+                     const int32_t* ids = nullptr) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
   if (!x || !out) return fail(GELATO_ERR_ARG, "null buffer");
@@ -448,15 +460,47 @@ static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int
   const size_t nx = (size_t)n_scen * v.n_vars;
   const size_t no = (size_t)n_scen * (which == 0 ? (size_t)v.n_rows : (size_t)v.n_vals);
   double* d_out = which == 0 ? p->d_g : p->d_vals;
+  if (ids) {  // batch slot k evaluates configured scenario ids[k]
+    for (int k = 0; k < n_scen; k++)
+      if (ids[k] < 0 || ids[k] >= p->n_scen_cfg) return fail(GELATO_ERR_ARG, "scenario id outside the configured scenarios");
+    if ((size_t)n_scen > p->cap_ids) {
+      if (p->d_ids) cudaFree(p->d_ids);
+      if (p->d_vals_ids) cudaFree(p->d_vals_ids);
+      p->d_ids = nullptr;
+      p->d_vals_ids = nullptr;
+      p->cap_ids = 0;
+      CU(cudaMalloc(&p->d_ids, (size_t)n_scen * sizeof(int32_t)));
+      CU(cudaMalloc(&p->d_vals_ids, (size_t)n_scen * v.n_vals * sizeof(double)));
+      p->cap_ids = n_scen;
+    }
+    CU(cudaMemcpyAsync(p->d_ids, ids, (size_t)n_scen * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
+    if (which == 1) {  // constants of each slot's scenario
+      d_out = p->d_vals_ids;
+      for (int k = 0; k < n_scen; k++)
+        CU(cudaMemcpyAsync(d_out + (size_t)k * v.n_vals, p->vals_template + (size_t)ids[k] * p->vals_template_sstride,
+                           (size_t)v.n_vals * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    }
+  }
   const double* hx = x;
   if (!is_pinned(x)) {
     memcpy(p->h_x, x, nx * sizeof(double));
     hx = p->h_x;
   }
   CU(cudaMemcpyAsync(p->d_x, hx, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-  if (which == 0) rc = gelato_eval_residuals_dev(p, p->d_x, p->d_g, n_scen, p->stream);
-  else rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream);
-  if (rc) return rc;
+  if (!ids) {
+    if (which == 0) rc = gelato_eval_residuals_dev(p, p->d_x, p->d_g, n_scen, p->stream);
+    else rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream);
+    if (rc) return rc;
+  } else {
+    if (which == 0) {
+      k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, p->d_ids,
+                                                                                p->d_x, p->d_g);
+      p->launches++;
+    } else if ((rc = launch_jacobian(p, p->d_x, d_out, n_scen, p->stream, p->d_ids))) {
+      return rc;
+    }
+    CU(cudaGetLastError());
+  }
   const bool direct = is_pinned(out);
   CU(cudaMemcpyAsync(direct ? out : p->h_out, d_out, no * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CU(cudaStreamSynchronize(p->stream));
@@ -470,6 +514,16 @@ int gelato_eval_residuals(GelatoPlan* p, const double* x, double* g, int32_t n_s
 
 int gelato_eval_jacobian(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
   return eval_host(p, 1, x, vals, n_scen);
+}
+
+int gelato_eval_residuals_ids(GelatoPlan* p, const double* x, double* g, int32_t n_scen, const int32_t* scen_ids) {
+  if (!scen_ids) return fail(GELATO_ERR_ARG, "null scen_ids");
+  return eval_host(p, 0, x, g, n_scen, scen_ids);
+}
+
+int gelato_eval_jacobian_ids(GelatoPlan* p, const double* x, double* vals, int32_t n_scen, const int32_t* scen_ids) {
+  if (!scen_ids) return fail(GELATO_ERR_ARG, "null scen_ids");
+  return eval_host(p, 1, x, vals, n_scen, scen_ids);
 }
 
 int gelato_pack_xdep_dev(GelatoPlan* p, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream) {
@@ -653,7 +707,7 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
   CU(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < reps; i++) {
     if (which == 0) {
-      k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, x_dev, out_dev);
+      k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
     } else {
       if ((rc = launch_jacobian(p, x_dev, out_dev, n_scen, p->stream))) return rc;
       continue;

@@ -182,6 +182,8 @@ def load_library():
     L.gelato_plan_launch_count.restype = ctypes.c_int64
     L.gelato_eval_residuals.argtypes = [vp, _pd, _pd, ctypes.c_int32]
     L.gelato_eval_jacobian.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_residuals_ids.argtypes = [vp, _pd, _pd, ctypes.c_int32, _pi32]
+    L.gelato_eval_jacobian_ids.argtypes = [vp, _pd, _pd, ctypes.c_int32, _pi32]
     L.gelato_eval_residuals_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_eval_jacobian_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_fill_template.argtypes = [vp, vp, ctypes.c_int32, vp]
@@ -216,7 +218,7 @@ def load_library():
 EXPORTS = (
     "gelato_last_error gelato_device_count gelato_plan_create gelato_plan_set_scenarios gelato_plan_destroy "
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
-    "gelato_eval_jacobian gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
+    "gelato_eval_jacobian gelato_eval_residuals_ids gelato_eval_jacobian_ids gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
     "gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
@@ -279,16 +281,29 @@ class Engine:
             raise ValueError("x has %d entries, expected %d x %d" % (x.size, n_scen, self.n_vars))
         return x
 
-    def eval_residuals(self, x, n_scen=1, out=None):
+    def eval_residuals(self, x, n_scen=1, out=None, scen_ids=None):
+        """scen_ids: batch slot k uses the parameter blocks of configured scenario scen_ids[k]."""
         x = self._x(x, n_scen)
         g = out if out is not None else np.empty(n_scen * self.n_rows)
-        _check(self.L, self.L.gelato_eval_residuals(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen), "gelato_eval_residuals")
+        if scen_ids is None:
+            _check(self.L, self.L.gelato_eval_residuals(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen), "gelato_eval_residuals")
+        else:
+            ids = np.ascontiguousarray(scen_ids, dtype=np.int32)
+            assert ids.size == n_scen
+            _check(self.L, self.L.gelato_eval_residuals_ids(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen, _ptr(ids, _pi32)),
+                   "gelato_eval_residuals_ids")
         return g if n_scen == 1 else g.reshape(n_scen, self.n_rows)
 
-    def eval_jacobian(self, x, n_scen=1, out=None):
+    def eval_jacobian(self, x, n_scen=1, out=None, scen_ids=None):
         x = self._x(x, n_scen)
         v = out if out is not None else np.empty(n_scen * self.n_vals)
-        _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
+        if scen_ids is None:
+            _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
+        else:
+            ids = np.ascontiguousarray(scen_ids, dtype=np.int32)
+            assert ids.size == n_scen
+            _check(self.L, self.L.gelato_eval_jacobian_ids(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen, _ptr(ids, _pi32)),
+                   "gelato_eval_jacobian_ids")
         return v if n_scen == 1 else v.reshape(n_scen, self.n_vals)
 
     # ---- update mode: one persistent host buffer per batch, only x-dependent slots cross PCIe ----

@@ -186,6 +186,13 @@ int64_t gelato_plan_launch_count(const GelatoPlan* plan);
 int gelato_eval_residuals(GelatoPlan* plan, const double* x, double* g, int32_t n_scen);
 int gelato_eval_jacobian(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
 
+/* Subset batches: batch slot k is evaluated with the parameter blocks of configured scenario
+ * scen_ids[k] (0 <= scen_ids[k] < n_scen of gelato_plan_set_scenarios; repeats allowed).  This is what a
+ * coalescing server needs: of many concurrent solves, those that happen to be waiting for a callback are
+ * evaluated together in one launch (gelato_b200/server.py). */
+int gelato_eval_residuals_ids(GelatoPlan* plan, const double* x, double* g, int32_t n_scen, const int32_t* scen_ids);
+int gelato_eval_jacobian_ids(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen, const int32_t* scen_ids);
+
 /* Update mode for drivers that keep one host Jacobian buffer per scenario batch alive across
  * calls (a batched solve): most of vals never changes (D entries, +-1, unit constants -- 87 % of
  * the slots at 1 000 nodes), so only the x-dependent slots cross PCIe.

@@ -47,7 +47,7 @@ extern "C" int emu_unfused_check(void) {
 }
 
 extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
-                                  double* g_all, int n_scen) {
+                                  double* g_all, int n_scen, const int32_t* ids) {
   if (validate_desc(d)) return -1;
   PlanView P = host_view(d);
   apply_scen(P, sc);
@@ -62,16 +62,17 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
     for (size_t b = 0; b < rb.size() / BT_COLS; b++) {
       const int32_t* bt = rb.data() + b * BT_COLS;
       memset(&sm, 0xff, sizeof sm);
-      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase0(P, scen, bt, x, tid, sm);
-      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, scen, bt, x, g, tid, sm);
-      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase2(P, scen, bt, x, g, tid, GR_THREADS, sm);
+      const int sid = ids ? ids[scen] : scen;
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase0(P, sid, bt, x, tid, sm);
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, sid, bt, x, g, tid, sm);
+      for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase2(P, sid, bt, x, g, tid, GR_THREADS, sm);
     }
   }
   return 0;
 }
 
 extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
-                                 double* vals_all, int n_scen) {
+                                 double* vals_all, int n_scen, const int32_t* ids) {
   if (validate_desc(d)) return -1;
   PlanView P = host_view(d);
   apply_scen(P, sc);
@@ -84,14 +85,15 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
     double* vals = vals_all + (size_t)scen * P.n_vals;
-    const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)scen * P.n_vals : d->vals_template;
+    const int sid = ids ? ids[scen] : scen;
+    const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)sid * P.n_vals : d->vals_template;
     memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
     for (size_t b = 0; b < jb.size() / BT_COLS; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
       /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
       memset(&store, 0xff, sizeof store);
       for (int phase = 0; phase < GJ_PHASES; phase++)
-        for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase(P, scen, bt, x, vals, tid, phase, sm);
+        for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase(P, sid, bt, x, vals, tid, phase, sm);
     }
   }
   return 0;

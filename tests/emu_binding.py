@@ -42,22 +42,32 @@ class Emulator:
             self.sc, keep = engine.make_scenario_desc(scenario_plans)
             self._keep += keep
         for fn in (self.L.emu_eval_residuals, self.L.emu_eval_jacobian):
-            fn.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, ctypes.c_int]
+            fn.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, ctypes.c_int,
+                           ctypes.POINTER(ctypes.c_int32)]
 
     def _sc(self):
         return ctypes.byref(self.sc) if self.sc is not None else None
 
-    def eval_residuals(self, x, n_scen=1):
+    @staticmethod
+    def _ids(scen_ids):
+        if scen_ids is None:
+            return None, None
+        ids = np.ascontiguousarray(scen_ids, dtype=np.int32)
+        return ids, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    def eval_residuals(self, x, n_scen=1, scen_ids=None):
         x = np.ascontiguousarray(x, dtype=np.float64)
         g = np.full(n_scen * self.plan.n_rows, np.nan)
-        rc = self.L.emu_eval_residuals(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd), n_scen)
+        ids, pids = self._ids(scen_ids)
+        rc = self.L.emu_eval_residuals(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd), n_scen, pids)
         assert rc == 0, "the plan description failed validate_desc (plan_host.h)"
         return g if n_scen == 1 else g.reshape(n_scen, -1)
 
-    def eval_jacobian(self, x, n_scen=1):
+    def eval_jacobian(self, x, n_scen=1, scen_ids=None):
         x = np.ascontiguousarray(x, dtype=np.float64)
         v = np.full(n_scen * self.plan.n_vals, np.nan)
-        rc = self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen)
+        ids, pids = self._ids(scen_ids)
+        rc = self.L.emu_eval_jacobian(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), v.ctypes.data_as(_pd), n_scen, pids)
         assert rc == 0, "the plan description failed validate_desc (plan_host.h)"
         return v if n_scen == 1 else v.reshape(n_scen, -1)
 
@@ -65,17 +75,17 @@ class Emulator:
 class EmuEngine(Emulator):
     """The emulator behind the Engine interface GelatoProblem uses (CPU test tier only)."""
 
-    def __init__(self, plan):
-        super().__init__(plan)
+    def __init__(self, plan, scenario_plans=None):
+        super().__init__(plan, scenario_plans=scenario_plans)
         self.launches = 0
 
-    def eval_residuals(self, x, n_scen=1, out=None):
+    def eval_residuals(self, x, n_scen=1, out=None, scen_ids=None):
         self.launches += 1
-        return super().eval_residuals(x, n_scen)
+        return super().eval_residuals(x, n_scen, scen_ids)
 
-    def eval_jacobian(self, x, n_scen=1, out=None):
+    def eval_jacobian(self, x, n_scen=1, out=None, scen_ids=None):
         self.launches += 1
-        return super().eval_jacobian(x, n_scen)
+        return super().eval_jacobian(x, n_scen, scen_ids)
 
     def close(self):
         pass
