@@ -21,6 +21,11 @@ What it writes
                         sequential-FMA D.X -- the flavour the CUDA kernels must match
                         bit for bit on any machine.
   psparams.npz          tau and D of the reference's PSparams for n = 2..24.
+  example_trajectory_kinematics.npz
+                        the 67 rows of /root/reference/example/example-trajectory_init.csv: state (t, position,
+                        velocity, quaternion) and the derived columns a former output_result wrote next to it
+                        (latitude, longitude, altitude, apogee / perigee altitude, inclination, IIP, total angle
+                        of attack) -- the only known answers the reference ships for the physics leaves.
 """
 import os
 import sys
@@ -102,6 +107,23 @@ def main():
         s, _ = O.sens(xa)
         pack(name, f, s, out)
     np.savez_compressed(os.path.join(HERE, "example_gmath.npz"), **out)
+
+    # ---- the known answers the reference ships: kinematic columns of its example trajectory table ----
+    import csv
+
+    with open(os.path.join(refharness.REF, "example", "example-trajectory_init.csv")) as fh:
+        rows = list(csv.DictReader(fh))
+
+    def col(*names):
+        return np.array([[float(r[n]) if r[n] != "" else np.nan for n in names] for r in rows])
+
+    np.savez_compressed(
+        os.path.join(HERE, "example_trajectory_kinematics.npz"),
+        t=col("time")[:, 0], pos=col("pos_ECI_X", "pos_ECI_Y", "pos_ECI_Z"), vel=col("vel_ECI_X", "vel_ECI_Y", "vel_ECI_Z"),
+        quat=col("quat_ECI2BODY_0", "quat_ECI2BODY_1", "quat_ECI2BODY_2", "quat_ECI2BODY_3"),
+        lat=col("lat")[:, 0], lon=col("lon")[:, 0], altitude=col("altitude")[:, 0],
+        apogee=col("altitude_apogee")[:, 0], perigee=col("altitude_perigee")[:, 0], inclination=col("inclination")[:, 0],
+        lat_iip=col("lat_IIP")[:, 0], lon_iip=col("lon_IIP")[:, 0], aoa_deg=col("AOA_total")[:, 0])
 
     # ---- reference PSparams ------------------------------------------------
     ns = refharness.load(L)
