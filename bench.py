@@ -38,7 +38,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "fd_jacobian_plus_residual_evals_per_s"
 UNIT = "evals/s"
