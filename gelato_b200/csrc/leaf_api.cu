@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../include/gelato_b200.h"
-#include "physics.h"
+#include "output.h"
 
 extern "C" void gelato_set_error_(const char* msg);  // gelato_b200.cu
 
@@ -125,6 +125,19 @@ __global__ void k_leaf_atmosphere(int n, const double* z, double* out) {
   out[5 * i + 4] = s.a;
 }
 
+/* one row of the reference's result table per thread (output.h) */
+__global__ void k_leaf_output_table(int n, const double* mass, const double* pos, const double* vel, const double* quat,
+                                    const double* t, const double* thrust_vac, const double* air_area,
+                                    const double* nozzle_area, Tables tb, double lat0, double lon0, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double row[GO_COLS];
+  output_row(mass[i], v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]),
+             q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), t[i], thrust_vac[i], air_area[i],
+             nozzle_area[i], tb, lat0, lon0, row);
+  for (int k = 0; k < GO_COLS; k++) out[(size_t)i * GO_COLS + k] = row[k];
+}
+
 }  // namespace
 
 extern "C" {
@@ -218,6 +231,28 @@ int gelato_leaf_gravity(int device, int32_t n, const double* pos_eci, double* ou
   double* d_out = buf.out((size_t)3 * n, err);
   if (err == cudaSuccess) k_leaf_gravity<<<blocks_for(n), 128>>>(n, dp, d_out);
   return finish(err, out, d_out, (size_t)3 * n);
+}
+
+int gelato_leaf_output_table(int device, int32_t n, const double* mass, const double* pos, const double* vel,
+                             const double* quat, const double* t, const double* thrust_vac, const double* air_area,
+                             const double* nozzle_area, const double* wind, int32_t n_wind, const double* ca, int32_t n_ca,
+                             double launch_lat_deg, double launch_lon_deg, double* out) {
+  LEAF_PROLOGUE
+  Tables tb;
+  tb.wind = buf.in(wind, (size_t)n_wind * 3, err); tb.n_wind = n_wind;
+  tb.ca = buf.in(ca, (size_t)n_ca * 2, err); tb.n_ca = n_ca;
+  const double* dm = buf.in(mass, n, err);
+  const double* dp = buf.in(pos, (size_t)3 * n, err);
+  const double* dv = buf.in(vel, (size_t)3 * n, err);
+  const double* dq = buf.in(quat, (size_t)4 * n, err);
+  const double* dt = buf.in(t, n, err);
+  const double* d1 = buf.in(thrust_vac, n, err);
+  const double* d2 = buf.in(air_area, n, err);
+  const double* d3 = buf.in(nozzle_area, n, err);
+  double* d_out = buf.out((size_t)GO_COLS * n, err);
+  if (err == cudaSuccess)
+    k_leaf_output_table<<<blocks_for(n), 128>>>(n, dm, dp, dv, dq, dt, d1, d2, d3, tb, launch_lat_deg, launch_lon_deg, d_out);
+  return finish(err, out, d_out, (size_t)GO_COLS * n);
 }
 
 int gelato_leaf_atmosphere(int device, int32_t n, const double* altitude, double* out) {

@@ -211,6 +211,7 @@ def load_library():
     L.gelato_leaf_gravity.argtypes = [ctypes.c_int, i32, _pd, _pd]
     L.gelato_leaf_iip.argtypes = [ctypes.c_int, i32, _pd, _pd, i32, _pd]
     L.gelato_leaf_atmosphere.argtypes = [ctypes.c_int, i32, _pd, _pd]
+    L.gelato_leaf_output_table.argtypes = [ctypes.c_int, i32] + [_pd] * 9 + [i32, _pd, i32, _c_d, _c_d, _pd]
     _lib = L
     return L
 
@@ -223,7 +224,7 @@ EXPORTS = (
     "gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
-    "gelato_leaf_atmosphere"
+    "gelato_leaf_atmosphere gelato_leaf_output_table"
 ).split()
 
 

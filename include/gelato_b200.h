@@ -272,6 +272,21 @@ int gelato_leaf_iip(int device, int32_t n, const double* pos_ecef, const double*
                     double* out);
 int gelato_leaf_atmosphere(int device, int32_t n, const double* altitude, double* out);
 
+/* The numeric body of the reference's result table (/root/reference/output_result.py:130-261) for n state
+ * nodes (any number of solved trajectories concatenated): one thread per node computes the 34 derived
+ * quantities the reference obtains through ~30 leaf calls per node.  Inputs dimensional (kg, m, m/s), t in
+ * seconds, quat as stored in the decision vector (normalised inside), per-node thrust_vac / air_area /
+ * nozzle_area of the section the reference attributes the node to.  out is [n][34] in the order
+ *   thrust, lat, lon, lat_IIP, lon_IIP, downrange, altitude, altitude_apogee, altitude_perigee, inclination,
+ *   argument_perigee, lon_ascending_node, true_anomaly, vel_ground_NED_X/Y/Z, accel_BODY_X, aero_BODY_X,
+ *   heading/pitch/roll_NED2BODY, flightpath, azimuth (inertial velocity, geocentric), thrust_direction_ECI_X/Y/Z,
+ *   vel_ground, vel_air, AOA_total, AOA_pitch, AOA_yaw, dynamic_pressure, Q_alpha, M
+ * (gelato_b200/output.py assembles the reference's DataFrame columns from it). */
+int gelato_leaf_output_table(int device, int32_t n, const double* mass, const double* pos, const double* vel,
+                             const double* quat, const double* t, const double* thrust_vac, const double* air_area,
+                             const double* nozzle_area, const double* wind, int32_t n_wind, const double* ca, int32_t n_ca,
+                             double launch_lat_deg, double launch_lon_deg, double* out);
+
 #ifdef __cplusplus
 }
 #endif

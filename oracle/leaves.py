@@ -147,6 +147,8 @@ class OracleLeaves:
             gravity=lambda p: self._v(L.o_gravity, 3, _p(v3(p))),
             eci2geodetic=lambda p, t: self._v(L.o_eci2geodetic, 3, _p(v3(p)), _D(t)),
             orbital_elements=lambda p, v: self._v(L.o_orbital_elements, 6, _p(v3(p)), _p(v3(v))),
+            euler_from_quat=lambda q: self._v(L.o_euler_from_quat, 3, _p(v4(q))),
+            quat_nedg2body=lambda q, p, t: self._v(L.o_quat_nedg2body, 4, _p(v4(q)), _p(v3(p)), _D(t)),
             distance_vincenty=lambda a, b, c, d: L.o_distance_vincenty(_D(a), _D(b), _D(c), _D(d)),
             angular_momentum_vec=lambda p, v: self._v(L.o_angular_momentum_vec, 3, _p(v3(p)), _p(v3(v))),
             angular_momentum=lambda p, v: L.o_angular_momentum(_p(v3(p)), _p(v3(v))),
@@ -192,7 +194,13 @@ class OracleLeaves:
             yp = _a(yp).ravel()
             return L.o_interp(_D(x), _p(xp), _p(yp), _I(xp.size))
 
+        def aoa_ab(pos, vel, quat, t, wind):
+            w = _a(wind)
+            return self._v(L.o_angle_of_attack_ab_rad, 2, _p(_a(pos, (3,))), _p(_a(vel, (3,))), _p(_a(quat, (4,))), _D(t),
+                           _p(w), _I(w.shape[0]))
+
         self.utils_c = ns(
+            angle_of_attack_ab_rad=aoa_ab,
             interp=interp,
             wind_ned=wind_ned,
             angle_of_attack_all_array_rad=aoa_arr,

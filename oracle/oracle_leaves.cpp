@@ -204,6 +204,44 @@ V4 c_quat_from_euler_deg(double az_deg, double el_deg, double ro_deg) {
   return eigen_quat_prod(eigen_quat_prod(qz, qy), qx);
 }
 
+// :127-146 euler_from_quat: Eigen q.toRotationMatrix().eulerAngles(2, 1, 0) + range fix-ups (radians).
+// toRotationMatrix / eulerAngles are restated from Eigen's Quaternion.h / EulerAngles.h (as in ref_shim).
+V3 c_euler_from_quat(const V4& q) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  double m[3][3];
+  m[0][0] = 1.0 - (tyy + tzz); m[0][1] = txy - twz; m[0][2] = txz + twy;
+  m[1][0] = txy + twz; m[1][1] = 1.0 - (txx + tzz); m[1][2] = tyz - twx;
+  m[2][0] = txz - twy; m[2][1] = tyz + twx; m[2][2] = 1.0 - (txx + tyy);
+  // eulerAngles(2, 1, 0): i = 2, odd = 1, j = 1, k = 0
+  const int i = 2, j = 1, k = 0;
+  double res[3];
+  res[0] = O_ATAN2(m[j][k], m[k][k]);
+  const double c2 = O_SQRT(m[i][i] * m[i][i] + m[i][j] * m[i][j]);
+  if (res[0] < 0.0) {  // odd && res[0] < 0
+    if (res[0] > 0.0) res[0] -= M_PI; else res[0] += M_PI;
+    res[1] = O_ATAN2(-m[i][k], -c2);
+  } else {
+    res[1] = O_ATAN2(-m[i][k], c2);
+  }
+  const double s1 = O_SIN(res[0]), c1 = O_COS(res[0]);
+  res[2] = O_ATAN2(s1 * m[k][i] - c1 * m[j][i], c1 * m[j][j] - s1 * m[k][j]);
+  V3 out = mk3(res[0], res[1], res[2]);  // odd: no sign flip
+  if (std::fabs(out[1]) > M_PI / 2.0) {
+    if (out[1] > 0.0) out[1] = M_PI - out[1];
+    else out[1] = -M_PI - out[1];
+    out[0] = M_PI + out[0];
+    out[2] = M_PI + out[2];
+  }
+  out[0] = std::fmod(out[0], 2.0 * M_PI);
+  if (out[0] < 0.0) out[0] += 2.0 * M_PI;
+  out[2] = std::fmod(out[2] + M_PI, 2.0 * M_PI) - M_PI;
+  return out;
+}
+
 // :197-245 (radians)
 void c_orbital_elements(const V3& pos, const V3& vel, double out[6]) {
   V3 nr = normalized3(pos);
@@ -372,6 +410,15 @@ double u_aoa_all_rad(const V3& pos, const V3& vel, const V4& quat, double t, con
   else if (norm3(va) < 1e-6) return 0.0;
   else return O_ACOS(c_alpha);
 }
+void u_aoa_ab_rad(const V3& pos, const V3& vel, const V4& quat, double t, const double* wind, int nw, double out[2]) {  // :125-148
+  V3 llh = w_ecef2geodetic_deg(pos[0], pos[1], pos[2]);
+  double altitude = air_geopotential_altitude(llh[2]);
+  V3 va = u_vel_air_eci(pos, vel, t, altitude, wind, nw);
+  V3 vb = w_quatrot(quat, va);
+  if (vb[0] < 1e-6) { out[0] = 0.0; out[1] = 0.0; return; }
+  out[0] = O_ATAN2(vb[2], vb[0]);
+  out[1] = O_ATAN2(vb[1], vb[0]);
+}
 double u_dynamic_pressure_pa(const V3& pos, const V3& vel, double t, const double* wind, int nw) {  // :163-174
   V3 llh = w_ecef2geodetic_deg(pos[0], pos[1], pos[2]);
   double altitude = air_geopotential_altitude(llh[2]);
@@ -424,6 +471,87 @@ V3 iip_faa(const V3& posECEF, const V3& velECEF) {
   double phi = O_ATAN2(O_TAN(phi_tmp), 1.0 - E_e2);
   double lam = O_ATAN2(Fk, Ek) - E_omega * time_sec;
   return mk3(phi, lam, 0.0);
+}
+
+// ---- output_result.py:130-261: the derived quantities of one state node -------------------------
+// numpy pieces as numpy evaluates them on this kind of input: numpy.linalg.norm of a 3-vector is
+// sqrt(x.dot(x)) with BLAS ddot accumulating by fused multiply-add in index order; numpy.interp uses
+// slope * (x - xp[j]) + fp[j]; math.degrees(x) = x * (180 / pi); x ** 2 = x * x.
+enum { OUT_COLS = 34 };
+inline double np_norm3(const V3& v) { return O_SQRT(__builtin_fma(v[2], v[2], __builtin_fma(v[1], v[1], v[0] * v[0]))); }
+inline double np_degrees(double x) { return x * (180.0 / M_PI); }
+double np_interp(double x, const double* xp, const double* fp, int n, int stride) {
+  if (x <= xp[0]) return fp[0];  // numpy: x < xp[0] -> left = fp[0]; x == xp[0] gives the same value
+  if (x >= xp[(n - 1) * stride]) return fp[(n - 1) * stride];
+  int j = 0;
+  while (j + 1 < n - 1 && xp[(j + 1) * stride] <= x) j++;
+  const double slope = (fp[(j + 1) * stride] - fp[j * stride]) / (xp[(j + 1) * stride] - xp[j * stride]);
+  return slope * (x - xp[j * stride]) + fp[j * stride];
+}
+void output_row(double mass, const V3& pos, const V3& vel, const V4& quat_raw, double t, double thrust_vac,
+                double air_area, double nozzle_area, const double* wind, int nw, const double* ca, int nca,
+                double lat0, double lon0, double* out) {
+  // quat = normalize(quat_[i]): dynamic vector v / v.norm()   (:133)
+  const double qn = O_SQRT(((quat_raw[0] * quat_raw[0] + quat_raw[1] * quat_raw[1]) + quat_raw[2] * quat_raw[2]) +
+                           quat_raw[3] * quat_raw[3]);
+  const V4 quat = mk4(quat_raw[0] / qn, quat_raw[1] / qn, quat_raw[2] / qn, quat_raw[3] / qn);
+  const V3 llh = w_eci2geodetic_deg(pos, t);  // :150
+  const double altitude_m = air_geopotential_altitude(llh[2]);
+  out[1] = llh[0]; out[2] = llh[1]; out[6] = llh[2];
+  out[5] = earth_distance_vincenty(lat0 * M_PI / 180.0, lon0 * M_PI / 180.0, llh[0] * M_PI / 180.0, llh[1] * M_PI / 180.0);
+  double el[6];
+  c_orbital_elements(pos, vel, el);  // wrapper converts elements 2..5 to degrees (:201-210)
+  for (int k = 2; k < 6; k++) el[k] = el[k] * 180.0 / M_PI;
+  out[7] = el[0] * (1.0 + el[1]) - 6378137;
+  out[8] = el[0] * (1.0 - el[1]) - 6378137;
+  out[9] = el[2]; out[11] = el[3]; out[10] = el[4]; out[12] = el[5];
+  const V3 vel_ground_ecef = c_vel_eci2ecef(vel, pos, t);  // :172
+  const V3 vel_ground_ned = w_quatrot(c_quat_ecef2ned(c_eci2ecef(pos, t)), vel_ground_ecef);
+  out[13] = vel_ground_ned[0]; out[14] = vel_ground_ned[1]; out[15] = vel_ground_ned[2];
+  const V3 vel_ned = w_quatrot(c_quat_eci2ned(pos, t), vel);
+  const V3 vel_air_ned = sub3(vel_ground_ned, u_wind_ned(altitude_m, wind, nw));
+  out[26] = np_norm3(vel_ground_ecef);
+  out[22] = np_degrees(O_ATAN2(vel_ned[1], vel_ned[0]));
+  out[21] = np_degrees(O_ASIN(-vel_ned[2] / np_norm3(vel_ned)));
+  const double nva = np_norm3(vel_air_ned);
+  const double q = 0.5 * (nva * nva) * air_density(altitude_m);  // :190
+  out[31] = q;
+  const double aoa_all_deg = u_aoa_all_rad(pos, vel, quat, t, wind, nw) * 180.0 / M_PI;
+  double ab[2];
+  u_aoa_ab_rad(pos, vel, quat, t, wind, nw, ab);
+  out[28] = aoa_all_deg;
+  out[32] = aoa_all_deg * q;
+  out[29] = ab[0] * 180.0 / M_PI;
+  out[30] = ab[1] * 180.0 / M_PI;
+  const V3 thrustdir = w_quatrot(quat_conj(quat), mk3(1.0, 0.0, 0.0));  // :211
+  out[23] = thrustdir[0]; out[24] = thrustdir[1]; out[25] = thrustdir[2];
+  const V3 eul = c_euler_from_quat(w_quatmult(quat_conj(c_quat_eci2ned(pos, t)), quat));
+  out[18] = eul[0] * 180.0 / M_PI; out[19] = eul[1] * 180.0 / M_PI; out[20] = eul[2] * 180.0 / M_PI;
+  const double rho = air_density(altitude_m);  // :223
+  const double p = air_pressure(altitude_m);
+  const V3 pos_ecef = c_eci2ecef(pos, t);
+  const V3 vel_ecef = c_vel_eci2ecef(vel, pos, t);
+  const V3 vel_air_eci = u_vel_air_eci(pos, vel, t, altitude_m, wind, nw);
+  const double nv = np_norm3(vel_air_eci);
+  const double mach = nv / air_speed_of_sound(altitude_m);
+  out[33] = mach;
+  const double coeff = np_interp(mach, ca, ca + 1, nca, 2);
+  out[27] = nv;
+  const double k = 0.5 * rho * nv;  // 0.5 * rho * norm * -v * area * coeff, left to right (:240-247)
+  const V3 aero = mk3(k * -vel_air_eci[0] * air_area * coeff, k * -vel_air_eci[1] * air_area * coeff,
+                      k * -vel_air_eci[2] * air_area * coeff);
+  const V3 aero_body = w_quatrot(quat, aero);
+  const double thrust_n = thrust_vac - nozzle_area * p;
+  out[0] = thrust_n;
+  out[17] = aero_body[0];
+  out[16] = (thrust_n + aero_body[0]) / mass;
+  V3 iip = iip_faa(pos_ecef, vel_ecef);  // posLLH_IIP_FAA(pos_ecef, vel_ecef, False): NaN when there is none
+  if (iip[0] == 0.0 && iip[1] == 0.0 && iip[2] == 0.0) {
+    out[3] = out[4] = std::numeric_limits<double>::quiet_NaN();
+  } else {
+    out[3] = iip[0] * (180.0 / M_PI);
+    out[4] = iip[1] * (180.0 / M_PI);
+  }
 }
 
 inline V3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
@@ -485,6 +613,13 @@ void o_quat_nedg2eci(const double* p, double t, double* out) { st4(out, c_quat_n
 void o_quat_from_euler(double az, double el, double ro, double* out) { st4(out, c_quat_from_euler_deg(az, el, ro)); }
 void o_gravity(const double* p, double* out) { st3(out, gravityECI(ld3(p))); }
 void o_eci2geodetic(const double* p, double t, double* out) { st3(out, w_eci2geodetic_deg(ld3(p), t)); }
+void o_euler_from_quat(const double* q, double* out) {  // wrapper_coordinate.hpp:176-180 (degrees)
+  V3 e = c_euler_from_quat(ld4(q));
+  st3(out, mk3(e[0] * 180.0 / M_PI, e[1] * 180.0 / M_PI, e[2] * 180.0 / M_PI));
+}
+void o_quat_nedg2body(const double* quat, const double* p, double t, double* out) {  // :171-174
+  st4(out, w_quatmult(quat_conj(c_quat_eci2ned(ld3(p), t)), ld4(quat)));
+}
 void o_orbital_elements(const double* p, const double* v, double* out) {  // wrapper_coordinate.hpp:201-210
   c_orbital_elements(ld3(p), ld3(v), out);
   out[2] = out[2] * 180.0 / M_PI;
@@ -524,6 +659,10 @@ void o_wind_ned(double alt, const double* wind, int nw, double* out) { st3(out, 
 void o_angle_of_attack_all_array_rad(const double* pos, const double* vel, const double* quat, const double* t,
                                      int n, const double* wind, int nw, double* out) {
   for (int i = 0; i < n; i++) out[i] = u_aoa_all_rad(ld3(pos + 3 * i), ld3(vel + 3 * i), ld4(quat + 4 * i), t[i], wind, nw);
+}
+void o_angle_of_attack_ab_rad(const double* pos, const double* vel, const double* quat, double t, const double* wind,
+                              int nw, double* out) {
+  u_aoa_ab_rad(ld3(pos), ld3(vel), ld4(quat), t, wind, nw, out);
 }
 void o_dynamic_pressure_array_pa(const double* pos, const double* vel, const double* t, int n, const double* wind,
                                  int nw, double* out) {
@@ -590,6 +729,14 @@ void o_dynamics_velocity_NoAir(const double* mass_e, const double* pos_e, const 
   }
 }
 
+// out[n][OUT_COLS]; per-node section parameters thrust_vac / air_area / nozzle_area as output_result.py:139-143 picks them
+void o_output_rows(int n, const double* mass, const double* pos, const double* vel, const double* quat, const double* t,
+                   const double* thrust_vac, const double* air_area, const double* nozzle_area, const double* wind, int nw,
+                   const double* ca, int nca, double lat0, double lon0, double* out) {
+  for (int i = 0; i < n; i++)
+    output_row(mass[i], ld3(pos + 3 * i), ld3(vel + 3 * i), ld4(quat + 4 * i), t[i], thrust_vac[i], air_area[i],
+               nozzle_area[i], wind, nw, ca, nca, lat0, lon0, out + (size_t)i * OUT_COLS);
+}
 void o_dynamics_quaternion(const double* quat, const double* u_e, double unit_u, int n, double* out) {
   for (int i = 0; i < n; i++) {
     double u0 = u_e[2 * i] * unit_u, u1 = u_e[2 * i + 1] * unit_u;

@@ -65,6 +65,8 @@ void o_quat_nedg2eci(const double* p, double t, double* out) { st(out, quat_nedg
 void o_quat_from_euler(double az, double el, double ro, double* out) { st(out, quat_from_euler(az, el, ro), 4); }
 void o_gravity(const double* p, double* out) { st(out, gravity(ld3(p)), 3); }
 void o_eci2geodetic(const double* p, double t, double* out) { st(out, eci2geodetic(ld3(p), t), 3); }
+void o_euler_from_quat(const double* q, double* out) { st(out, euler_from_quat(ld4(q)), 3); }
+void o_quat_nedg2body(const double* quat, const double* p, double t, double* out) { st(out, quat_nedg2body(ld4(quat), ld3(p), t), 4); }
 void o_orbital_elements(const double* p, const double* v, double* out) { st(out, orbital_elements(ld3(p), ld3(v)), 6); }
 double o_distance_vincenty(double lat0, double lon0, double lat1, double lon1) {
   return distance_vincenty(lat0, lon0, lat1, lon1);
@@ -82,6 +84,10 @@ void o_wind_ned(double alt, const double* wind, int nw, double* out) { st(out, w
 void o_angle_of_attack_all_array_rad(const double* pos, const double* vel, const double* quat, const double* t, int n,
                                      const double* wind, int nw, double* out) {
   st(out, angle_of_attack_all_array_rad(ldm(pos, n, 3), ldm(vel, n, 3), ldm(quat, n, 4), ldv(t, n), ldm(wind, nw, 3)), n);
+}
+void o_angle_of_attack_ab_rad(const double* pos, const double* vel, const double* quat, double t, const double* wind,
+                              int nw, double* out) {
+  st(out, angle_of_attack_ab_rad(ld3(pos), ld3(vel), ld4(quat), t, ldm(wind, nw, 3)), 2);
 }
 void o_dynamic_pressure_array_pa(const double* pos, const double* vel, const double* t, int n, const double* wind,
                                  int nw, double* out) {

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../gelato_b200/csrc/output.h"
 #include "../../gelato_b200/csrc/plan_host.h"
 
 static PlanView host_view(const GelatoPlanDesc* d) {
@@ -97,4 +98,17 @@ extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDe
     }
   }
   return 0;
+}
+
+// the result-table kernel's per-thread function (output.h), one call per node
+extern "C" void emu_output_rows(int n, const double* mass, const double* pos, const double* vel, const double* quat,
+                                const double* t, const double* thrust_vac, const double* air_area,
+                                const double* nozzle_area, const double* wind, int n_wind, const double* ca, int n_ca,
+                                double lat0, double lon0, double* out) {
+  Tables tb;
+  tb.wind = wind; tb.n_wind = n_wind; tb.ca = ca; tb.n_ca = n_ca;
+  for (int i = 0; i < n; i++)
+    output_row(mass[i], v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]),
+               q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), t[i], thrust_vac[i], air_area[i],
+               nozzle_area[i], tb, lat0, lon0, out + (size_t)i * GO_COLS);
 }

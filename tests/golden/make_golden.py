@@ -21,6 +21,10 @@ What it writes
                         sequential-FMA D.X -- the flavour the CUDA kernels must match
                         bit for bit on any machine.
   psparams.npz          tau and D of the reference's PSparams for n = 2..24.
+  example_output_result.npz
+                        every column of the table the reference's own output_result function
+                        (/root/reference/output_result.py:37-263, imported where it lies, on the reference's
+                        C++ leaves) produces for x0 and x1.
   example_trajectory_kinematics.npz
                         the 67 rows of /root/reference/example/example-trajectory_init.csv: state (t, position,
                         velocity, quaternion) and the derived columns a former output_result wrote next to it
@@ -124,6 +128,18 @@ def main():
         lat=col("lat")[:, 0], lon=col("lon")[:, 0], altitude=col("altitude")[:, 0],
         apogee=col("altitude_apogee")[:, 0], perigee=col("altitude_perigee")[:, 0], inclination=col("inclination")[:, 0],
         lat_iip=col("lat_IIP")[:, 0], lon_iip=col("lon_IIP")[:, 0], aoa_deg=col("AOA_total")[:, 0])
+
+    # ---- the reference's own output_result table of the two decision vectors --------------------
+    out_fn = refharness.reference_output_result(L)
+    tab = {}
+    for name, x in (("x0", x0), ("x1", x1)):
+        tx, tu = refharness.result_times(x, pdict, unitdict)
+        df = out_fn(helpers.copy_x(x), unitdict, tx, tu, pdict)
+        tab["%s/columns" % name] = np.array(list(df.columns))
+        for c in df.columns:
+            v = np.asarray(df[c].values)
+            tab["%s/%s" % (name, c)] = v if v.dtype.kind in "fiub" else np.array([str(e) for e in v])
+    np.savez_compressed(os.path.join(HERE, "example_output_result.npz"), **tab)
 
     # ---- reference PSparams ------------------------------------------------
     ns = refharness.load(L)

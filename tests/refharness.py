@@ -90,3 +90,26 @@ def reference_callbacks(leaves, pdict, unitdict, condition):
     g.update(pdict=pdict, unitdict=unitdict, condition=condition)
     exec(_slice_source("def objfunc(xdict):", "optProb = Optimization", include_end=False), g)
     return g["objfunc"], g["sens"]
+
+
+def reference_output_result(leaves):
+    """The reference's own output_result function (/root/reference/output_result.py:37-263), imported
+    where it lies on top of the given leaves."""
+    load(leaves)
+    for k in [k for k in sys.modules if k == "output_result"]:
+        del sys.modules[k]
+    return importlib.import_module("output_result").output_result
+
+
+def result_times(xdict, pdict, unitdict):
+    """tx_res / tu_res as the reference's driver builds them (Trajectory_Optimization.py:477-492)."""
+    import numpy as np
+
+    tu, tx = np.array([]), np.array([])
+    ps = pdict["ps_params"]
+    for i in range(pdict["num_sections"]):
+        to, tf = xdict["t"][i], xdict["t"][i + 1]
+        tau_x = np.hstack((-1.0, ps.tau(i)))
+        tu = np.hstack((tu, (ps.tau(i) * (tf - to) / 2 + (tf + to) / 2) * unitdict["t"]))
+        tx = np.hstack((tx, (tau_x * (tf - to) / 2 + (tf + to) / 2) * unitdict["t"]))
+    return tx, tu

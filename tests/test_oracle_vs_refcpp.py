@@ -68,6 +68,8 @@ def test_coordinate_functions(pair):
             _eq(getattr(ca, name)(p), getattr(cb, name)(p), name)
         for name in ("quat_eci2ecef", "quat_ecef2eci"):
             _eq(getattr(ca, name)(tt), getattr(cb, name)(tt), name)
+        _eq(ca.euler_from_quat(qq), cb.euler_from_quat(qq), "euler_from_quat")
+        _eq(ca.quat_nedg2body(qq, p, tt), cb.quat_nedg2body(qq, p, tt), "quat_nedg2body")
         _eq(ca.quatmult(qq, q[i - 1]), cb.quatmult(qq, q[i - 1]), "quatmult")
         _eq(ca.conj(qq), cb.conj(qq), "conj")
         _eq(ca.quatrot(qq, v), cb.quatrot(qq, v), "quatrot")
@@ -98,6 +100,9 @@ def test_tables_aero_iip_dynamics(pair):
     _eq(ua.angle_of_attack_all_array_rad(pos, vel, q, t, wind), ub.angle_of_attack_all_array_rad(pos, vel, q, t, wind), "aoa")
     _eq(ua.dynamic_pressure_array_pa(pos, vel, t, wind), ub.dynamic_pressure_array_pa(pos, vel, t, wind), "q")
     _eq(ua.q_alpha_array_pa_rad(pos, vel, q, t, wind), ub.q_alpha_array_pa_rad(pos, vel, q, t, wind), "q-alpha")
+    for i in range(0, pos.shape[0], 3):
+        _eq(ua.angle_of_attack_ab_rad(pos[i], vel[i], q[i], t[i], wind), ub.angle_of_attack_ab_rad(pos[i], vel[i], q[i], t[i], wind),
+            "angle_of_attack_ab_rad")
     for i in range(pos.shape[0]):
         pe = A.coordinate_c.eci2ecef(pos[i], t[i])
         ve = A.coordinate_c.vel_eci2ecef(vel[i], pos[i], t[i])
