@@ -22,26 +22,30 @@
 #include "../../include/gelato_b200.h"
 #include "physics.h"
 
-/* ---- launch geometry ------------------------------------------------------ */
-#define GJ_THREADS 256 /* Jacobian kernel block */
-#define GR_THREADS 128 /* residual kernel block */
-#define GJ_NODES 18    /* air nodes (or aero rows) per Jacobian block */
-#define GN_NODES 28    /* no-air nodes per Jacobian block */
+/* ---- launch geometry (overridable with -D for tuning experiments: tools/ab_bench.sh) ------------- */
+#ifndef GJ_THREADS
+#define GJ_THREADS 256   /* Jacobian kernel block */
+#define GJ_NODES 18      /* air nodes (or aero rows) per Jacobian block */
+#define GJ_A_THREADS 96  /* threads [0, 96): position items (>= GJ_NODES*NPV, whole warps) */
+#define GJ_B_THREADS 128 /* threads [96, 224): rotation items (>= GJ_NODES*NRV, whole warps) */
+#define GN_NODES 28      /* no-air nodes per Jacobian block */
+#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
+#define GJ_EVT 16        /* event jobs per Jacobian block (16 lanes each) */
+#endif
 #define GG_NODES 8     /* nodes per block of the one-lane-per-column fallback */
-#define GJ_EVT 16      /* event jobs per Jacobian block (16 lanes each) */
+#define GR_THREADS 128 /* residual kernel block */
 #define GR_NODES 64    /* nodes per residual block */
 #define NPV 5          /* distinct positions over the columns of one node */
 #define NRV 7          /* distinct (position, time) pairs */
-#define GJ_A_THREADS 96  /* threads [0, 96): position items (>= GJ_NODES*NPV, whole warps) */
-#define GJ_B_THREADS 128 /* threads [96, 224): rotation items (>= GJ_NODES*NRV) */
-#define GJ_Q_BASE 224    /* threads [224, 256): quaternion kinematics, one node each */
-#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
 
 static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS >= GJ_NODES * NPV, "position items need whole warps");
 static_assert(GJ_B_THREADS % 32 == 0 && GJ_B_THREADS >= GJ_NODES * NRV, "rotation items need whole warps");
-static_assert(GJ_A_THREADS + GJ_B_THREADS == GJ_Q_BASE && GJ_THREADS - GJ_Q_BASE >= GN_NODES, "phase-0 thread map");
-static_assert(GJ_NODES * 14 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS && GN_NODES * NPV <= GN_A_THREADS, "one pass");
-static_assert(GN_A_THREADS <= GJ_Q_BASE && GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS, "lane maps");
+static_assert(GJ_A_THREADS + GJ_B_THREADS <= GJ_THREADS, "phase-0 thread map");
+static_assert(GJ_THREADS - GJ_NODES * (NPV + NRV) >= GJ_NODES, "one spare phase-0 thread per node for the quaternion items");
+static_assert(GJ_THREADS - GN_NODES * NPV >= GN_NODES && GN_NODES * NPV <= GN_A_THREADS && GN_A_THREADS <= GJ_THREADS, "no-air map");
+static_assert(GJ_NODES * 14 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS, "column items in one pass");
+static_assert(GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS && GG_NODES <= GN_NODES, "lane maps");
+static_assert(GJ_THREADS * 3 <= GN_NODES * 14 * 3, "event jobs keep 3 values per thread in f");
 static_assert(GR_THREADS == 2 * GR_NODES, "residual phase 0 uses two threads per node");
 
 /* block roles */
@@ -235,6 +239,13 @@ P_HD int lane_pv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : 4); }
 P_HD int lane_rv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : (lane <= 11 ? 4 : lane - 7)); }
 P_HD int rv_pv(int rv) { return rv < 4 ? rv : 4; }
 
+/* phase 0 also evaluates the quaternion kinematics, one thread per node: the threads the position /
+ * rotation items leave over, in thread order.  Returns the node a thread takes, or -1. */
+P_HD int spare_item(int tid, int n_a_items, int a_threads, int n_b_items) {
+  if (tid < a_threads) return tid >= n_a_items ? tid - n_a_items : -1;
+  return tid - a_threads >= n_b_items ? (a_threads - n_a_items) + (tid - a_threads - n_b_items) : -1;
+}
+
 /* non-dimensional position variant pv of a base position b[3] */
 P_HD void pos_variant(const double* b, int pv, double dx, double* out) {
   for (int k = 0; k < 3; k++) {
@@ -377,7 +388,8 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
 /* ========================================================================= */
 /* Jacobian kernel, DYN_AIR role: GJ_NODES air nodes per block, four phases   */
 /*   0  position items (node, pv) -> pos_part | rotation items (node, rv) ->  */
-/*      rotq_part | one thread per node: the 7 quaternion-kinematics variants */
+/*      rotq_part | the threads left over: one node each, the 7 quaternion-  */
+/*      kinematics variants                                                   */
 /*   2  column items (node, lane 0-13): wind into ECI axes, per-column        */
 /*      remainder                                                             */
 /*   3  finite-difference quotients -> COO slots                              */
@@ -388,8 +400,12 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    if (tid < GJ_A_THREADS) {
-      if (tid >= count * NPV) return;
+    const int qn = spare_item(tid, count * NPV, GJ_A_THREADS, count * NRV);
+    if (qn >= 0) {
+      if (qn >= count) return;
+      const NodeRef nr = jac_node(P, start + qn);
+      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
+    } else if (tid < GJ_A_THREADS) {
       const int nl = tid / NPV, pv = tid - nl * NPV;
       const NodeRef nr = jac_node(P, start + nl);
       double p[3];
@@ -397,9 +413,8 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const Tables tb = scen_tables(P, scen);
       pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
                sm.pp + (nl * NPV + pv) * PP_COLS);
-    } else if (tid < GJ_A_THREADS + GJ_B_THREADS) {
+    } else {
       const int item = tid - GJ_A_THREADS;
-      if (item >= count * NRV) return;
       const int nl = item / NRV, rv = item - nl * NRV;
       const NodeRef nr = jac_node(P, start + nl);
       double p[3];
@@ -409,11 +424,6 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const double tf = (rv == 6) ? tf0 + dx : tf0;
       const double tn = time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
-    } else {
-      const int nl = tid - GJ_Q_BASE;
-      if (nl < 0 || nl >= count) return;
-      const NodeRef nr = jac_node(P, start + nl);
-      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
     }
   } else if (phase == 2) {
     if (tid >= count * 14) return;
@@ -447,8 +457,12 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    if (tid < GN_A_THREADS) {
-      if (tid >= count * NPV) return;
+    const int qn = spare_item(tid, count * NPV, GN_A_THREADS, 0);
+    if (qn >= 0) {
+      if (qn >= count) return;
+      const NodeRef nr = jac_node(P, start + qn);
+      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
+    } else {
       const int nl = tid / NPV, pv = tid - nl * NPV;
       const NodeRef nr = jac_node(P, start + nl);
       double p[3];
@@ -458,11 +472,6 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
       o[0] = g.x;
       o[1] = g.y;
       o[2] = g.z;
-    } else {
-      const int nl = tid - GJ_Q_BASE;
-      if (nl < 0 || nl >= count) return;
-      const NodeRef nr = jac_node(P, start + nl);
-      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
     }
   } else if (phase == 2) {
     if (tid >= count * 9) return;
