@@ -240,10 +240,12 @@ P_HD int lane_rv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : (lane
 P_HD int rv_pv(int rv) { return rv < 4 ? rv : 4; }
 
 /* phase 0 also evaluates the quaternion kinematics, one thread per node: the threads the position /
- * rotation items leave over, in thread order.  Returns the node a thread takes, or -1. */
-P_HD int spare_item(int tid, int n_a_items, int a_threads, int n_b_items) {
-  if (tid < a_threads) return tid >= n_a_items ? tid - n_a_items : -1;
-  return tid - a_threads >= n_b_items ? (a_threads - n_a_items) + (tid - a_threads - n_b_items) : -1;
+ * rotation items leave over, taken from the END of the block (with the default geometry that is a warp
+ * of its own, so the short quaternion items do not lengthen a warp of long ones).  Returns the node a
+ * thread takes, or -1 when it has a position / rotation item. */
+P_HD int spare_item(int tid, int n_threads, int n_a_items, int a_threads, int n_b_items) {
+  if (tid >= a_threads) return tid - a_threads >= n_b_items ? n_threads - 1 - tid : -1;
+  return tid >= n_a_items ? (n_threads - a_threads - n_b_items) + (a_threads - 1 - tid) : -1;
 }
 
 /* non-dimensional position variant pv of a base position b[3] */
@@ -400,7 +402,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    const int qn = spare_item(tid, count * NPV, GJ_A_THREADS, count * NRV);
+    const int qn = spare_item(tid, GJ_THREADS, count * NPV, GJ_A_THREADS, count * NRV);
     if (qn >= 0) {
       if (qn >= count) return;
       const NodeRef nr = jac_node(P, start + qn);
@@ -457,7 +459,7 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    const int qn = spare_item(tid, count * NPV, GN_A_THREADS, 0);
+    const int qn = spare_item(tid, GJ_THREADS, count * NPV, GN_A_THREADS, 0);
     if (qn >= 0) {
       if (qn >= count) return;
       const NodeRef nr = jac_node(P, start + qn);
