@@ -9,7 +9,8 @@ launch scenarios of that problem (mass / thrust / wind perturbations, each
 scenario its own decision vector).  An "eval" is one physics-leaf evaluation at
 one (node x perturbation column): see CompiledPlan.eval_counts / DESIGN.md.
 
-  value   device-resident: x already in HBM, outputs stay in HBM, CUDA events.
+  value   device-resident: x already in HBM, outputs stay in HBM, CUDA events; the two kernels
+          of a step are launched as one pair (residual kernel on a side stream).
   e2e     the same step through the host-buffer C-ABI calls: x from page-locked
           host memory -> device, both kernels, residual vector and Jacobian values
           back into host buffers, wall clock.  The Jacobian uses update mode
@@ -290,10 +291,33 @@ def run_gelato(args):
         step_dev(evs[k])
         flush.zero_()  # L2 flush between timed steps (outside the per-step event brackets)
     barrier()
-    dev_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
+    serial_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
     res_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     jac_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    # ---- the headline: objfunc + sens of the same decision vectors as ONE pair evaluation (the residual kernel
+    #      on a side stream next to the Jacobian kernel); same work, same results as the two calls above ----
+    def step_pair(ev=None):
+        if ev:
+            ev[0].record()
+        E.eval_pair_dev(xd.data_ptr(), gd.data_ptr(), vd.data_ptr(), B, st)
+        if ev:
+            ev[1].record()
+
+    g_serial, v_serial = gd.clone(), vd.clone()
+    for _ in range(max(args.warmup, 3)):
+        step_pair()
+        flush.zero_()
+    evp = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    barrier()
+    launches0 = E.launches
+    for k in range(args.steps):
+        step_pair(evp[k])
+        flush.zero_()
+    barrier()
+    dev_ms = sum(e[0].elapsed_time(e[1]) for e in evp)
     launches = E.launches - launches0
+    assert torch.equal(g_serial, gd) and torch.equal(v_serial, vd), "pair and separate evaluations disagree"
 
     # ---- end to end through the host-buffer C ABI (what objfunc / sens call) ----
     px, pg, pv = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * P.n_vals)
@@ -303,11 +327,15 @@ def run_gelato(args):
         E.eval_residuals(px.array, B, out=pg.array)
         E.eval_jacobian(px.array, B, out=pv.array)
 
-    def step_e2e():
+    def step_e2e_separate():
         # update mode: the batch's host Jacobian buffer lives across calls (as in a batched solve), so
         # only the x-dependent slots cross PCIe; the buffer ends up identical to the full copy
         E.eval_residuals(px.array, B, out=pg.array)
         E.eval_jacobian_update(px.array, pv.array, B)
+
+    def step_e2e():
+        # the same as one pair call: x uploaded once, the residual kernel and its copy overlap the Jacobian's
+        E.eval_pair_update(px.array, pg.array, pv.array, B)
 
     def timed(step):
         for _ in range(max(args.warmup, 3)):
@@ -323,15 +351,18 @@ def run_gelato(args):
     assert np.array_equal(pv.array.reshape(B, -1), vd.cpu().numpy()), "host and device paths disagree"
     pv.array[:] = np.nan
     E.jacobian_template(pv.array, B)
+    e2e_sep_s = timed(step_e2e_separate)
+    pg.array[:] = np.nan
     e2e_s = timed(step_e2e)
     clocks = sampler.stop()
     assert np.array_equal(pg.array.reshape(B, -1), gd.cpu().numpy()), "host and device paths disagree"
     assert np.array_equal(pv.array.reshape(B, -1), vd.cpu().numpy()), "host and device paths disagree"
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, jac_ms, res_ms, e2e_full_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, jac_ms, res_ms, e2e_full_s * 1e3, serial_ms, e2e_sep_s * 1e3], dtype=torch.float64,
+                     device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, jac_ms, res_ms, e2e_full_ms = [float(v) for v in t.cpu()]
+    dev_ms, e2e_ms, jac_ms, res_ms, e2e_full_ms, serial_ms, e2e_sep_ms = [float(v) for v in t.cpu()]
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -354,6 +385,8 @@ def run_gelato(args):
             "config": {"workload": "example_x%d_N%d_split20" % (args.factor, P.N), "scenarios_per_gpu": B,
                        "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows, "n_vals": int(P.n_vals),
                        "evals_per_scenario_step": ec["objfunc"] + ec["sens"], "parallelism": "scenarios x%d" % world,
+                       "step": "objfunc + sens of one batch as one pair evaluation (gelato_eval_pair_dev: residual "
+                               "kernel on a side stream next to the Jacobian kernel)",
                        "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launch stream"},
             "clocks": clocks,
             "e2e": {"value": evals_step_rank * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
@@ -361,11 +394,16 @@ def run_gelato(args):
                     "d2h_bytes_per_step": int(B * (P.n_rows + n_xdep) * 8),
                     "mode": "page-locked host Jacobian buffer kept across calls; only the %d x-dependent of %d slots per "
                             "scenario cross PCIe, written into it by the device (zero-copy)" % (n_xdep, int(P.n_vals)),
+                    "separate_calls": {"value": evals_step_rank * world * args.steps / (e2e_sep_ms * 1e-3),
+                                       "ms_per_step": e2e_sep_ms / args.steps},
                     "full_copy": {"value": evals_step_rank * world * args.steps / (e2e_full_ms * 1e-3),
                                   "ms_per_step": e2e_full_ms / args.steps,
                                   "d2h_bytes_per_step": int(B * (P.n_rows + P.n_vals) * 8)}},
             "gpu_launches": int(launches),
-            "kernels": {"k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms},
+            "kernels": {"k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms,
+                        "note": "each kernel timed alone, back to back on one stream",
+                        "separate_calls_ms_per_step": serial_ms / args.steps,
+                        "separate_calls_value": evals_step_rank * world * args.steps / (serial_ms * 1e-3)},
             "roofline": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -174,6 +174,8 @@ struct GelatoPlan {
   long long n_small = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_kernel = nullptr, ev_copy = nullptr;
+  cudaStream_t pair_stream = nullptr;  // residual kernel of a pair evaluation, concurrent with the Jacobian kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -293,6 +295,9 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_kernel, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&p->pair_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreate(&p->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&p->ev1);
   if (ce != cudaSuccess) {
@@ -355,6 +360,9 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->ev_kernel) cudaEventDestroy(p->ev_kernel);
   if (p->ev_copy) cudaEventDestroy(p->ev_copy);
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->pair_stream) cudaStreamDestroy(p->pair_stream);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   return GELATO_OK;
@@ -387,6 +395,26 @@ int gelato_eval_residuals_dev(GelatoPlan* p, const double* x_dev, double* g_dev,
   k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, g_dev);
   p->launches++;
   CU(cudaGetLastError());
+  return GELATO_OK;
+}
+
+int gelato_eval_pair_dev(GelatoPlan* p, const double* x_dev, double* g_dev, double* vals_dev, int32_t n_scen, void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  // fork: the residual kernel (one right-hand side per node, latency bound) runs on a side stream next to
+  // the Jacobian kernel and fills the SM time its tail leaves; join: `st` continues when both are done
+  CU(cudaEventRecord(p->ev_fork, st));
+  CU(cudaStreamWaitEvent(p->pair_stream, p->ev_fork, 0));
+  k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->pair_stream>>>(p->view, p->res_blocks, n_scen, nullptr,
+                                                                                  x_dev, g_dev);
+  p->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(p->ev_join, p->pair_stream));
+  if ((rc = launch_jacobian(p, x_dev, vals_dev, n_scen, st))) return rc;
+  CU(cudaGetLastError());
+  CU(cudaStreamWaitEvent(st, p->ev_join, 0));
   return GELATO_OK;
 }
 
@@ -600,7 +628,8 @@ static void scatter_parallel(const int64_t* idx, long long n_idx, const double* 
   for (auto& th : pool) th.join();
 }
 
-int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
+// shared body of gelato_eval_jacobian_update / gelato_eval_pair_update; g == NULL: Jacobian only
+static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, int32_t n_scen) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
   if (!x || !vals) return fail(GELATO_ERR_ARG, "null buffer");
@@ -624,6 +653,18 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
     hx = p->h_x;
   }
   CU(cudaMemcpyAsync(p->d_x, hx, nxin * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  const bool g_direct = g && is_pinned(g);
+  if (g) {  // residuals of the same x on the side stream: kernel and copy overlap the Jacobian's
+    const size_t ng = (size_t)n_scen * v.n_rows;
+    CU(cudaEventRecord(p->ev_fork, p->stream));
+    CU(cudaStreamWaitEvent(p->pair_stream, p->ev_fork, 0));
+    k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->pair_stream>>>(p->view, p->res_blocks, n_scen, nullptr,
+                                                                                    p->d_x, p->d_g);
+    p->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(g_direct ? g : p->h_out, p->d_g, ng * sizeof(double), cudaMemcpyDeviceToHost, p->pair_stream));
+    CU(cudaEventRecord(p->ev_join, p->pair_stream));
+  }
   if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
 
   // Which slots travel packed (gathered on the device, copied, scattered by host threads) and which go
@@ -682,8 +723,19 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
     }
   }
   if (direct) CU(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
+  if (g) CU(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
   CU(cudaStreamSynchronize(p->stream));
+  if (g && !g_direct) memcpy(g, p->h_out, (size_t)n_scen * v.n_rows * sizeof(double));
   return GELATO_OK;
+}
+
+int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, int32_t n_scen) {
+  return eval_update(p, x, nullptr, vals, n_scen);
+}
+
+int gelato_eval_pair_update(GelatoPlan* p, const double* x, double* g, double* vals, int32_t n_scen) {
+  if (!g) return fail(GELATO_ERR_ARG, "null buffer");
+  return eval_update(p, x, g, vals, n_scen);
 }
 
 int gelato_host_alloc(size_t bytes, void** out) {

@@ -193,6 +193,8 @@ def load_library():
     L.gelato_plan_n_xdep.restype = ctypes.c_int64
     L.gelato_jacobian_template.argtypes = [vp, _pd, ctypes.c_int32]
     L.gelato_eval_jacobian_update.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_pair_update.argtypes = [vp, _pd, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_pair_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_set_host_threads.argtypes = [vp, ctypes.c_int32]
     L.gelato_set_update_zero_copy.argtypes = [vp, ctypes.c_int32]
     L.gelato_pack_xdep_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
@@ -221,7 +223,7 @@ EXPORTS = (
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_ids gelato_eval_jacobian_ids gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
-    "gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_eval_pair_update gelato_eval_pair_dev gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
     "gelato_leaf_atmosphere gelato_leaf_output_table"
@@ -322,6 +324,19 @@ class Engine:
         _check(self.L, self.L.gelato_eval_jacobian_update(self.h, _ptr(x, _pd), _ptr(out, _pd), n_scen),
                "gelato_eval_jacobian_update")
         return out if n_scen == 1 else out.reshape(n_scen, self.n_vals)
+
+    def eval_pair_update(self, x, g_out, vals_out, n_scen=1):
+        """objfunc + sens of the same decision vectors in one call (x uploaded once, the two kernels
+        concurrent); g_out is filled whole, vals_out updated as by eval_jacobian_update."""
+        x = self._x(x, n_scen)
+        if g_out.size != n_scen * self.n_rows or vals_out.size != n_scen * self.n_vals:
+            raise ValueError("output buffers have the wrong size")
+        _check(self.L, self.L.gelato_eval_pair_update(self.h, _ptr(x, _pd), _ptr(g_out, _pd), _ptr(vals_out, _pd), n_scen),
+               "gelato_eval_pair_update")
+        return g_out.reshape(n_scen, self.n_rows), vals_out.reshape(n_scen, self.n_vals)
+
+    def eval_pair_dev(self, x_ptr, g_ptr, vals_ptr, n_scen=1, stream=None):
+        _check(self.L, self.L.gelato_eval_pair_dev(self.h, x_ptr, g_ptr, vals_ptr, n_scen, stream), "gelato_eval_pair_dev")
 
     def set_update_zero_copy(self, on=True):
         _check(self.L, self.L.gelato_set_update_zero_copy(self.h, 1 if on else 0), "gelato_set_update_zero_copy")

@@ -202,9 +202,13 @@ int gelato_eval_jacobian_ids(GelatoPlan* plan, const double* x, double* vals, in
  *                                packed, copied and scattered by host threads); every other slot
  *                                of vals is left as it was.
  * After the two calls vals holds exactly what gelato_eval_jacobian returns. */
+/* gelato_eval_pair_update: `objfunc` and `sens` of the same decision vectors in one call -- x is uploaded
+ * once, the residual kernel runs on a side stream next to the Jacobian kernel, g is copied back whole and
+ * vals is updated as by gelato_eval_jacobian_update.  Results are those of the two separate calls. */
 int64_t gelato_plan_n_xdep(const GelatoPlan* plan);
 int gelato_jacobian_template(GelatoPlan* plan, double* vals, int32_t n_scen);
 int gelato_eval_jacobian_update(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
+int gelato_eval_pair_update(GelatoPlan* plan, const double* x, double* g, double* vals, int32_t n_scen);
 /* on != 0 (default): when `vals` is page-locked (gelato_host_alloc), update mode writes the x-dependent
  * slots straight into it from the device (zero-copy over PCIe, no host thread touches the buffer); pageable
  * buffers, or on == 0, take pack + copy + host scatter */
@@ -222,6 +226,10 @@ int gelato_host_free(void* ptr);
  * x-dependent slot on each call and leaves the constants alone. */
 int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
 int gelato_fill_template(GelatoPlan* plan, double* vals_dev, int32_t n_scen, void* stream);
+/* both kernels for the same x_dev: the residual kernel on a side stream forked from and joined back into
+ * `stream`, concurrent with the Jacobian kernel */
+int gelato_eval_pair_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* vals_dev, int32_t n_scen,
+                         void* stream);
 int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
 /* packed_dev[n_scen][n_xdep] = the x-dependent slots of vals_dev[n_scen][n_vals], in ascending slot order */
 int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream);

@@ -194,6 +194,38 @@ def test_update_mode_equals_full_jacobian(pinned):
     E.close()
 
 
+def test_pair_evaluation_equals_the_two_calls():
+    import torch
+
+    prob, O, x0 = _problem("example", 4)
+    E, P = prob.engine, prob.plan
+    X = np.stack([problem.xdict_to_vector(helpers.perturbed(x0, seed=s)) for s in (1, 2, 3)])
+    g_want = E.eval_residuals(X, 3).copy()
+    v_want = E.eval_jacobian(X, 3).copy()
+    for pinned in (True, False):
+        hg = engine.PinnedArray(3 * P.n_rows) if pinned else None
+        hv = engine.PinnedArray(3 * P.n_vals) if pinned else None
+        g = hg.array if pinned else np.empty(3 * P.n_rows)
+        v = hv.array if pinned else np.empty(3 * P.n_vals)
+        g[:] = np.nan
+        E.jacobian_template(v, 3)
+        G, V = E.eval_pair_update(X, g, v, 3)
+        assert np.array_equal(G, g_want) and np.array_equal(V, v_want)
+        if pinned:
+            hg.free()
+            hv.free()
+    xd = torch.from_numpy(X).cuda()
+    gd = torch.full((3, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
+    vd = torch.empty((3, P.n_vals), dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        E.fill_template(vd.data_ptr(), 3, s.cuda_stream)
+        E.eval_pair_dev(xd.data_ptr(), gd.data_ptr(), vd.data_ptr(), 3, s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(gd.cpu().numpy(), g_want) and np.array_equal(vd.cpu().numpy(), v_want)
+    prob.close()
+
+
 def test_reuse_output_sens_equals_fresh_sens():
     prob, O, x0 = _problem("example", 3)
     p2 = callbacks.GelatoProblem(prob.plan.p, prob.plan.u, prob.plan.c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT),
