@@ -683,9 +683,12 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
       CU(cudaMemcpy2DAsync(vals + run.first, pitch, p->d_vals + run.first, pitch, (size_t)run.second * sizeof(double),
                            (size_t)n_scen, cudaMemcpyDeviceToHost, p->copy_stream));
     CU(cudaEventRecord(p->ev_copy, p->copy_stream));
-    if (p->update_zero_copy && n_pack > 0) {
-      double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
-      CU(cudaHostGetDevicePointer((void**)&dev_view, vals, 0));
+    double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
+    if (p->update_zero_copy && n_pack > 0 && cudaHostGetDevicePointer((void**)&dev_view, vals, 0) != cudaSuccess) {
+      cudaGetLastError();  // registered without a device mapping: the scattered slots travel packed instead
+      dev_view = nullptr;
+    }
+    if (dev_view) {
       const int threads = 256;
       const int bx = (int)std::min<long long>((n_pack + threads - 1) / threads, 4096);
       k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, pack_idx_dev, n_pack, v.n_vals, dev_view);
