@@ -41,6 +41,18 @@
 #endif
 
 /* ---- primitives ------------------------------------------------------- */
+/* IEEE division.  On the device a quotient is ~30 instructions inline and the NLP kernels contain a few
+ * hundred of them; as a call each exists once and the kernels' instruction footprint shrinks by a third
+ * (GM_DIV_CALLS=0 restores the inline form; profiles/r01r_div_ab.txt). */
+#ifndef GM_DIV_CALLS
+#define GM_DIV_CALLS 1
+#endif
+#if defined(__CUDACC__) && GM_DIV_CALLS
+static __host__ __device__ __noinline__ double gm_div(double a, double b) { return a / b; }
+#else
+static inline double gm_div(double a, double b) { return a / b; }
+#endif
+
 
 GM_HD double gm_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
@@ -224,19 +236,19 @@ GM_HD double gm_atan(double x) {
     double z = x * x;
     return x - x * (z * gm_atan_poly(z));
   } else if (a < 0.6875) {
-    t = (2.0 * a - 1.0) / (2.0 + a);
+    t = gm_div(2.0 * a - 1.0, 2.0 + a);
     hi = GM_ATAN_05_HI;
     lo = GM_ATAN_05_LO;
   } else if (a < 1.1875) {
-    t = (a - 1.0) / (a + 1.0);
+    t = gm_div(a - 1.0, a + 1.0);
     hi = GM_ATAN_10_HI;
     lo = GM_ATAN_10_LO;
   } else if (a < 2.4375) {
-    t = (a - 1.5) / (1.0 + 1.5 * a);
+    t = gm_div(a - 1.5, 1.0 + 1.5 * a);
     hi = GM_ATAN_15_HI;
     lo = GM_ATAN_15_LO;
   } else {
-    t = -1.0 / a;
+    t = gm_div(-1.0, a);
     hi = GM_ATAN_INF_HI;
     lo = GM_ATAN_INF_LO;
   }
@@ -288,7 +300,7 @@ GM_HD_CALL double gm_atan2(double y, double x) {
   } else if ((m & 2) && k < -64) { /* 0 > |y|/x > -2^-64 */
     z = 0.0;
   } else {
-    z = gm_atan(gm_u2d(ay) / gm_u2d(ax));
+    z = gm_atan(gm_div(gm_u2d(ay), gm_u2d(ax)));
   }
   switch (m) {
     case 0: return z;

@@ -145,7 +145,7 @@ P_HD double residue_n(double x, double dx, int n) {
  * quotients have an exactly zero numerator (a column that does not move an output); IEEE gives
  * 0/dx = 0 with the numerator's sign, and saying so skips the division's slow path, which the
  * GPU's software FP64 division takes for zero numerators (ncu r01b: 8 % of all instructions). */
-P_HD double fd_div(double num, double dx) { return num == 0.0 ? num : num / dx; }
+P_HD double fd_div(double num, double dx) { return num == 0.0 ? num : gm_div(num, dx); }
 
 P_HD Units scen_units(const PlanView& P, int scen) {
   Units u = P.un;
@@ -341,10 +341,10 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   }
   /* ---- position dynamics (analytic, depends on x through vel and t): :180-195 ---- */
   if (lane == 14) {
-    const double rh_vel = -un.vel * dt * ut / 2.0 / un.pos;
+    const double rh_vel = gm_div(-un.vel * dt * ut / 2.0, un.pos);
     for (int k = 0; k < 3; k++) {
       vals[sj[GS_JP_VEL] + 3LL * j + k] = rh_vel;
-      const double rh_to = x[P.off_vel + 3 * row + k] * un.vel * ut / 2.0 / un.pos;
+      const double rh_to = gm_div(x[P.off_vel + 3 * row + k] * un.vel * ut / 2.0, un.pos);
       vals[sj[GS_JP_T] + 3LL * j + k] = rh_to;
       vals[sj[GS_JP_T] + n3 + 3LL * j + k] = -rh_to;
     }
@@ -636,7 +636,7 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
       double r;
       if (flags & GSF_ENGINE_ON) {
         const double lh = dx_dot(Drow, x + xa, 1, n + 1);
-        const double rh = -sec_param(P, scen, nr.sec).massflow / un.mass * dt * ut / 2.0;
+        const double rh = gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
         r = lh - rh;
       } else {
         r = x[row] - x[xa];
@@ -645,7 +645,7 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
     } else if (col <= 3) { /* position: :146-150 */
       const int k = col - 1;
       const double lh = dx_dot(Drow, x + P.off_pos + 3 * xa + k, 3, n + 1);
-      const double rh = x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0 / un.pos;
+      const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
       g[si[GS_R_POS] + 3 * j + k] = lh - rh;
     } else if (col <= 6) { /* velocity: :256-287 */
       const int k = col - 4;

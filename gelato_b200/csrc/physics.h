@@ -62,7 +62,7 @@ P_HD Vec3 cross3(Vec3 a, Vec3 b) {
 P_HD Vec3 sub3(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 P_HD Vec3 add3(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 P_HD Vec3 scale3(double s, Vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-P_HD Vec3 div3(Vec3 a, double s) { return v3(a.x / s, a.y / s, a.z / s); }
+P_HD Vec3 div3(Vec3 a, double s) { return v3(gm_div(a.x, s), gm_div(a.y, s), gm_div(a.z, s)); }
 P_HD Vec3 normalized3(Vec3 a) { /* Eigen normalized() */
   double z = dot3(a, a);
   if (z > 0.0) return div3(a, gm_sqrt(z));
@@ -110,8 +110,8 @@ P_HD Geodetic ecef2geodetic(Vec3 r) {
   if (WANT & 1) {
     double sl, cl;
     gm_sincos(g.lat, &sl, &cl);
-    double N = P_RA / gm_sqrt(1.0 - P_E2 * sl * sl);
-    g.alt = p / cl - N;
+    double N = gm_div(P_RA, gm_sqrt(1.0 - P_E2 * sl * sl));
+    g.alt = gm_div(p, cl) - N;
   }
   return g;
 }
@@ -139,8 +139,8 @@ P_HD Quat quat_ecef2ned_ll(double lat, double lon) {
   gm_sincos(lon / 2.0, &s_hl, &c_hl);
   gm_sincos(lat / 2.0, &s_hp, &c_hp);
   double r2 = gm_sqrt(2.0);
-  return q4(c_hl * (c_hp - s_hp) / r2, s_hl * (c_hp + s_hp) / r2, -c_hl * (c_hp + s_hp) / r2,
-            s_hl * (c_hp - s_hp) / r2);
+  return q4(gm_div(c_hl * (c_hp - s_hp), r2), gm_div(s_hl * (c_hp + s_hp), r2), gm_div(-c_hl * (c_hp + s_hp), r2),
+            gm_div(s_hl * (c_hp - s_hp), r2));
 }
 
 /* Coordinate.cpp:104-110 quat_ned2eci(pos_eci, t); c,s = cos/sin(omega t) */
@@ -165,16 +165,16 @@ P_HD Vec3 gravity_eci(Vec3 pos) {
   if (r == 0.0) {
     irx = iry = irz = 0.0;
   } else {
-    irx = x / r;
-    iry = y / r;
-    irz = z / r;
+    irx = gm_div(x, r);
+    iry = gm_div(y, r);
+    irz = gm_div(z, r);
   }
   double s5 = gm_sqrt(5.0);
   double barP20 = s5 * (3.0 * irz * irz - 1.0) * 0.5;
   double barP20d = s5 * 3.0 * irz;
   if (r < b) r = b;
-  double g_ir = -mu / (r * r) * (1.0 + barC20 * (a / r) * (a / r) * (3.0 * barP20 + irz * barP20d));
-  double g_iz = mu / (r * r) * (a / r) * (a / r) * barC20 * barP20d;
+  double g_ir = gm_div(-mu, r * r) * (1.0 + barC20 * gm_div(a, r) * gm_div(a, r) * (3.0 * barP20 + irz * barP20d));
+  double g_iz = gm_div(mu, r * r) * gm_div(a, r) * gm_div(a, r) * barC20 * barP20d;
   return v3(g_ir * irx, g_ir * iry, g_ir * irz + g_iz);
 }
 
@@ -184,7 +184,7 @@ struct AirState {
 };
 
 P_HD double geopotential_altitude(double z) {
-  if (z < 86000.0) return 1.0 * (6356766.0 * z) / (6356766.0 + z);
+  if (z < 86000.0) return gm_div(1.0 * (6356766.0 * z), 6356766.0 + z);
   return z;
 }
 
@@ -203,7 +203,7 @@ P_HD void us76_layer(double h, double* Hb, double* Lmb, double* Tmb, double* Pb,
   if (h >= 91000.0) { hb = 91000.0; l = 0.0025; t = 186.8673; p = 0.15381; m = 28.89; }
   if (h >= 110000.0) { hb = 110000.0; l = 0.012; t = 240.0; p = 7.1042e-3; m = 27.27; }
   if (h >= 120000.0) { hb = 120000.0; l = 0.012; t = 360.0; p = 2.5382e-3; m = 26.20; }
-  *Hb = hb; *Lmb = l; *Tmb = t; *Pb = p; *R = Rstar / m;
+  *Hb = hb; *Lmb = l; *Tmb = t; *Pb = p; *R = gm_div(Rstar, m);
 }
 
 /* want: bit0 pressure+density, bit1 speed of sound */
@@ -229,10 +229,10 @@ P_HD AirState us76(double h, int want) {
   s.a = 0.0;
   if (want & 1) {
     if (gm_fabs(Lmb) > 1.0e-6)
-      s.P = Pb * gm_pow((Tmb + Lmb * (h - Hb)) / Tmb, -g0 / Lmb / R);
+      s.P = Pb * gm_pow(gm_div(Tmb + Lmb * (h - Hb), Tmb), gm_div(gm_div(-g0, Lmb), R));
     else
-      s.P = Pb * gm_exp(g0 / R * (Hb - h) / Tmb);
-    s.rho = s.P / R / s.T;
+      s.P = Pb * gm_exp(gm_div(gm_div(g0, R) * (Hb - h), Tmb));
+    s.rho = gm_div(gm_div(s.P, R), s.T);
   }
   if (want & 2) s.a = gm_sqrt(1.4 * R * s.T);
   return s;
@@ -253,7 +253,7 @@ P_HD double interp_table(double x, const double* xp, const double* yp, int n, in
   if (idx < 0) idx = 0;
   double x_lower = xp[idx * stride], x_upper = xp[(idx + 1) * stride];
   double y_lower = yp[idx * stride], y_upper = yp[(idx + 1) * stride];
-  double alpha = (x - x_lower) / (x_upper - x_lower);
+  double alpha = gm_div(x - x_lower, x_upper - x_lower);
   return y_lower + alpha * (y_upper - y_lower);
 }
 
@@ -353,15 +353,15 @@ P_HD Vec3 rhs_velocity_air_col(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, co
   Vec3 vel = v3(vel_e.x * un.vel, vel_e.y * un.vel, vel_e.z * un.vel);
   Vec3 va = air_velocity(pos, vel, rp);
   double vn = norm3(va);
-  double mach = vn / pp[PP_SOUND];
+  double mach = gm_div(vn, pp[PP_SOUND]);
   double ca = interp_table(mach, tb.ca, tb.ca + 1, tb.n_ca, 2);
   double k = 0.5 * pp[PP_RHO] * sp.ref_area * ca * vn;
   Vec3 aero = v3(k * -va.x, k * -va.y, k * -va.z);
   double thrust = sp.thrust - sp.nozzle_area * pp[PP_PRESS];
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(thrust, tdir);
-  return v3(((thr.x + aero.x) / mass + pp[PP_GX]) / un.vel, ((thr.y + aero.y) / mass + pp[PP_GY]) / un.vel,
-            ((thr.z + aero.z) / mass + pp[PP_GZ]) / un.vel);
+  return v3(gm_div(gm_div(thr.x + aero.x, mass) + pp[PP_GX], un.vel), gm_div(gm_div(thr.y + aero.y, mass) + pp[PP_GY], un.vel),
+            gm_div(gm_div(thr.z + aero.z, mass) + pp[PP_GZ], un.vel));
 }
 
 /* dynamics_velocity in one pass (residual kernel: one evaluation per node) */
@@ -379,7 +379,8 @@ P_HD Vec3 rhs_velocity_noair_col(double mass_e, Quat q, Vec3 g, const SecParam& 
   double mass = mass_e * un.mass;
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(sp.thrust, tdir);
-  return v3((thr.x / mass + g.x) / un.vel, (thr.y / mass + g.y) / un.vel, (thr.z / mass + g.z) / un.vel);
+  return v3(gm_div(gm_div(thr.x, mass) + g.x, un.vel), gm_div(gm_div(thr.y, mass) + g.y, un.vel),
+            gm_div(gm_div(thr.z, mass) + g.z, un.vel));
 }
 P_HD Vec3 rhs_velocity_noair(double mass_e, Vec3 pos_e, Quat q, const SecParam& sp, const Units& un) {
   Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);
