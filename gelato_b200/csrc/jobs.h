@@ -1,20 +1,24 @@
 /* jobs.h -- the work items of the two fused kernels, as per-thread functions.
  *
- * A kernel block has a role (a row of the block table) and runs its job in two
- * phases separated by one block barrier:
- *   phase 1  every thread evaluates ONE leaf (a right-hand side, an aero
- *            quantity, an event-point function) on its own perturbed copy of
- *            the inputs and parks the result in shared memory;
- *   phase 2  every thread forms its finite-difference quotients against the
- *            centre evaluation of its group and scatters them to their COO
- *            slots (Jacobian kernel), or combines D.X with the right-hand side
- *            into residual rows (residual kernel).
- * The functions are host+device so tests/emu can step through the same code on
- * the CPU; the shipped library only runs them inside CUDA kernels.
+ * A kernel block has a role (a row of the block table) and runs its job in phases separated by
+ * block barriers.  Jacobian kernel (phases numbered 0, 2, 3; each role uses those it needs):
+ *   phase 0  the expensive, shareable parts of the leaves: per air node 5 position items
+ *            (pos_part) and 7 rotation items (rotq_part) cover all 14 finite-difference columns;
+ *            vacuum nodes: 5 gravity items; the quaternion kinematics, one thread per node;
+ *            event rows and fallback nodes: one full leaf per lane;
+ *   phase 2  one thread per (node, column): the cheap per-column remainder on its own perturbed
+ *            copy of the inputs, result parked in shared memory;
+ *   phase 3  finite-difference quotients against the centre column, in the reference's operation
+ *            order, scattered to their COO slots (lane-major: neighbouring threads, same formula).
+ * Residual kernel: phase 0 position | rotation part (two threads per node), phase 1 the
+ * right-hand sides, phase 2 D.X minus right-hand side for the 11 state columns.
  *
- * Reference formulas: see the citations on each function; the perturbation
- * protocol (which inputs carry fl(fl(x+dx)-dx) residue when a given column is
- * evaluated) is DESIGN.md "H3" / SURVEY.md A.4.
+ * The functions are host+device so tests/emu can step through the same code on the CPU; the
+ * shipped library only runs them inside CUDA kernels.
+ *
+ * Reference formulas: see the citations on each function; the perturbation protocol (which
+ * inputs carry fl(fl(x+dx)-dx) residue when a given column is evaluated) is DESIGN.md "H3" /
+ * SURVEY.md A.4.
  */
 #ifndef GELATO_B200_JOBS_H_
 #define GELATO_B200_JOBS_H_

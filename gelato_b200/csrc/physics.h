@@ -1,5 +1,7 @@
-/* physics.h -- the 3-DoF launch-vehicle physics leaves, written for one GPU
- * thread per (node x perturbation column).
+/* physics.h -- the 3-DoF launch-vehicle physics leaves, written for GPU threads
+ * that each evaluate one (node x perturbation column) or a shareable part of it
+ * (pos_part / rotq_part / per-column remainder: see "the air right-hand side in
+ * three parts" below and jobs.h).
  *
  * Each function states which reference routine it replaces.  Values are
  * bit-identical to the reference's formulas evaluated in IEEE binary64 with
