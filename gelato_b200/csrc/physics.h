@@ -175,8 +175,11 @@ P_HD Vec3 gravity_eci(Vec3 pos) {
   double barP20 = s5 * (3.0 * irz * irz - 1.0) * 0.5;
   double barP20d = s5 * 3.0 * irz;
   if (r < b) r = b;
-  double g_ir = gm_div(-mu, r * r) * (1.0 + barC20 * gm_div(a, r) * gm_div(a, r) * (3.0 * barP20 + irz * barP20d));
-  double g_iz = gm_div(mu, r * r) * gm_div(a, r) * gm_div(a, r) * barC20 * barP20d;
+  /* the reference writes a / r four times and mu / (r * r) twice (gravity.cpp:49-53); equal operands give
+   * equal quotients, and (-mu) / d == -(mu / d) exactly, so each is divided once */
+  const double a_r = gm_div(a, r), mu_r2 = gm_div(mu, r * r);
+  double g_ir = -mu_r2 * (1.0 + barC20 * a_r * a_r * (3.0 * barP20 + irz * barP20d));
+  double g_iz = mu_r2 * a_r * a_r * barC20 * barP20d;
   return v3(g_ir * irx, g_ir * iry, g_ir * irz + g_iz);
 }
 
@@ -190,29 +193,43 @@ P_HD double geopotential_altitude(double z) {
   return z;
 }
 
-P_HD void us76_layer(double h, double* Hb, double* Lmb, double* Tmb, double* Pb, double* R) {
+/* One row of the US-76 layer table (Air.cpp:31-45) and what depends on that row only:
+ * R = Rstar / M, the pressure exponent -g0 / Lmb / R (gradient layers) and g0 / R (isothermal layers).
+ * They are constant expressions of the row -- the reference evaluates them again on every call
+ * (Air.cpp:62-67, 93-97); here the compiler folds them with the same IEEE divisions. */
+struct Us76Layer {
+  double Hb, Lmb, Tmb, Pb, R, expo, g0_R;
+};
+#define US76_ROW(hb_, l_, t_, p_, m_)                                                                          \
+  {                                                                                                            \
+    L.Hb = (hb_); L.Lmb = (l_); L.Tmb = (t_); L.Pb = (p_); L.R = 8314.32 / (m_);                               \
+    L.expo = ((l_) != 0.0) ? -9.80665 / (l_) / (8314.32 / (m_)) : 0.0;                                         \
+    L.g0_R = 9.80665 / (8314.32 / (m_));                                                                       \
+  }
+P_HD Us76Layer us76_layer(double h) {
   /* last layer whose base is <= h; layer 0 when h is below every base (Air.cpp:56-60).
    * Branch ladder instead of a table: no local-memory indexing on the GPU. */
-  const double Rstar = 8314.32;
-  double hb = 0.0, l = -0.0065, t = 288.15, p = 101325.0, m = 28.9644;
-  if (h >= 11000.0) { hb = 11000.0; l = 0.0; t = 216.65; p = 22632.0; }
-  if (h >= 20000.0) { hb = 20000.0; l = 0.001; t = 216.65; p = 5474.9; }
-  if (h >= 32000.0) { hb = 32000.0; l = 0.0028; t = 228.65; p = 868.02; }
-  if (h >= 47000.0) { hb = 47000.0; l = 0.0; t = 270.65; p = 110.91; }
-  if (h >= 51000.0) { hb = 51000.0; l = -0.0028; t = 270.65; p = 66.939; }
-  if (h >= 71000.0) { hb = 71000.0; l = -0.002; t = 214.65; p = 3.9564; }
-  if (h >= 86000.0) { hb = 86000.0; l = 0.0; t = 186.8673; p = 0.37338; m = 28.9522; }
-  if (h >= 91000.0) { hb = 91000.0; l = 0.0025; t = 186.8673; p = 0.15381; m = 28.89; }
-  if (h >= 110000.0) { hb = 110000.0; l = 0.012; t = 240.0; p = 7.1042e-3; m = 27.27; }
-  if (h >= 120000.0) { hb = 120000.0; l = 0.012; t = 360.0; p = 2.5382e-3; m = 26.20; }
-  *Hb = hb; *Lmb = l; *Tmb = t; *Pb = p; *R = gm_div(Rstar, m);
+  Us76Layer L;
+  US76_ROW(0.0, -0.0065, 288.15, 101325.0, 28.9644)
+  if (h >= 11000.0) US76_ROW(11000.0, 0.0, 216.65, 22632.0, 28.9644)
+  if (h >= 20000.0) US76_ROW(20000.0, 0.001, 216.65, 5474.9, 28.9644)
+  if (h >= 32000.0) US76_ROW(32000.0, 0.0028, 228.65, 868.02, 28.9644)
+  if (h >= 47000.0) US76_ROW(47000.0, 0.0, 270.65, 110.91, 28.9644)
+  if (h >= 51000.0) US76_ROW(51000.0, -0.0028, 270.65, 66.939, 28.9644)
+  if (h >= 71000.0) US76_ROW(71000.0, -0.002, 214.65, 3.9564, 28.9644)
+  if (h >= 86000.0) US76_ROW(86000.0, 0.0, 186.8673, 0.37338, 28.9522)
+  if (h >= 91000.0) US76_ROW(91000.0, 0.0025, 186.8673, 0.15381, 28.89)
+  if (h >= 110000.0) US76_ROW(110000.0, 0.012, 240.0, 7.1042e-3, 27.27)
+  if (h >= 120000.0) US76_ROW(120000.0, 0.012, 360.0, 2.5382e-3, 26.20)
+  return L;
 }
+#undef US76_ROW
 
 /* want: bit0 pressure+density, bit1 speed of sound */
 P_HD AirState us76(double h, int want) {
-  const double g0 = 9.80665, r0 = 6356766.0;
-  double Hb, Lmb, Tmb, Pb, R;
-  us76_layer(h, &Hb, &Lmb, &Tmb, &Pb, &R);
+  const double r0 = 6356766.0;
+  const Us76Layer L = us76_layer(h);
+  const double Hb = L.Hb, Lmb = L.Lmb, Tmb = L.Tmb, Pb = L.Pb, R = L.R;
   AirState s;
   if (h <= 91000.0) {
     s.T = Tmb + Lmb * (h - Hb);
@@ -231,9 +248,9 @@ P_HD AirState us76(double h, int want) {
   s.a = 0.0;
   if (want & 1) {
     if (gm_fabs(Lmb) > 1.0e-6)
-      s.P = Pb * gm_pow(gm_div(Tmb + Lmb * (h - Hb), Tmb), gm_div(gm_div(-g0, Lmb), R));
+      s.P = Pb * gm_pow(gm_div(Tmb + Lmb * (h - Hb), Tmb), L.expo); /* -g0 / Lmb / R */
     else
-      s.P = Pb * gm_exp(gm_div(gm_div(g0, R) * (Hb - h), Tmb));
+      s.P = Pb * gm_exp(gm_div(L.g0_R * (Hb - h), Tmb)); /* g0 / R * (Hb - h) / Tmb */
     s.rho = gm_div(gm_div(s.P, R), s.T);
   }
   if (want & 2) s.a = gm_sqrt(1.4 * R * s.T);
