@@ -4,8 +4,8 @@ residual leaf evaluations per second).
 
 Workload (BASELINE.json configs[1]): the shipped example refined to ~1 000 LGR
 nodes (x15 -> N = 990 in 53 sections of <= 20 nodes).  One STEP = one `objfunc`
-+ one `sens` (residual kernel + FD-Jacobian kernel) over a batch of dispersed
-launch scenarios of that problem (mass / thrust / wind perturbations, each
++ one `sens` (residual kernel + FD-Jacobian kernel) over a batch of 128 dispersed
+launch scenarios of that problem per GPU (8 GPUs = the 1 024 scenarios of configs[3]) (mass / thrust / wind perturbations, each
 scenario its own decision vector).  An "eval" is one physics-leaf evaluation at
 one (node x perturbation column): see CompiledPlan.eval_counts / DESIGN.md.
 
@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gelato", choices=["gelato", "reference"])
-    ap.add_argument("--scenarios", type=int, default=64, help="dispersed scenarios per GPU in one step")
+    ap.add_argument("--scenarios", type=int, default=128,
+                    help="dispersed scenarios per GPU in one step (128 x 8 GPUs = the 1 024 scenarios of BASELINE.json configs[3])")
     ap.add_argument("--factor", type=int, default=15, help="mesh refinement of the example (15 -> 990 nodes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
