@@ -391,7 +391,7 @@ def run_gelato(args):
                        "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launch stream"},
             "clocks": clocks,
             "e2e": {"value": evals_step_rank * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(2 * X.size * 8),
+                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(X.size * 8),
                     "d2h_bytes_per_step": int(B * (P.n_rows + n_xdep) * 8),
                     "mode": "page-locked host Jacobian buffer kept across calls; only the %d x-dependent of %d slots per "
                             "scenario cross PCIe, written into it by the device (zero-copy)" % (n_xdep, int(P.n_vals)),
