@@ -61,6 +61,10 @@ def parse():
     ap.add_argument("--factor", type=int, default=15, help="mesh refinement of the example (15 -> 990 nodes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "pool", "zero-copy"],
+                    help="scattered Jacobian slots of the end-to-end leg: packed + host thread pool, or written by the "
+                         "device into the mapped buffer; auto = pool when this rank has 8+ host threads to itself")
+    ap.add_argument("--e2e-slices", type=int, default=0, help="pipeline slices of the end-to-end leg (0 = library default)")
     return ap.parse_args()
 
 
@@ -248,7 +252,11 @@ def run_gelato(args):
     P = plans[0]
     E = engine.Engine(P, device=local, scenario_plans=plans)
     # scatter threads of update mode: the ranks of one node share the host cores (and its memory bandwidth)
-    E.set_host_threads(max(1, min(16, (os.cpu_count() or 1) // world)))
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // world))
+    E.set_host_threads(host_threads)
+    zero_copy = args.e2e_mode == "zero-copy" or (args.e2e_mode == "auto" and host_threads < 8)
+    E.set_update_zero_copy(zero_copy)
+    E.set_update_slices(args.e2e_slices)
     ec = P.eval_counts()
     evals_step_rank = (ec["objfunc"] + ec["sens"]) * B
     # a dedicated non-default stream: the C ABI reads stream 0 as "the plan's own stream", and the
@@ -394,7 +402,10 @@ def run_gelato(args):
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(X.size * 8),
                     "d2h_bytes_per_step": int(B * (P.n_rows + n_xdep) * 8),
                     "mode": "page-locked host Jacobian buffer kept across calls; only the %d x-dependent of %d slots per "
-                            "scenario cross PCIe, written into it by the device (zero-copy)" % (n_xdep, int(P.n_vals)),
+                            "scenario cross PCIe (long runs by strided copies into place, scattered slots %s); pipelined "
+                            "over slices of 16 scenarios"
+                            % (n_xdep, int(P.n_vals), "written by the device into the mapped buffer (zero-copy)" if zero_copy
+                               else "packed and scattered by %d pooled host threads" % host_threads),
                     "separate_calls": {"value": evals_step_rank * world * args.steps / (e2e_sep_ms * 1e-3),
                                        "ms_per_step": e2e_sep_ms / args.steps},
                     "full_copy": {"value": evals_step_rank * world * args.steps / (e2e_full_ms * 1e-3),

@@ -20,6 +20,7 @@
 #include <utility>
 #include <vector>
 
+#include "host_pool.h"
 #include "plan_host.h"
 
 // ---------------------------------------------------------------------------
@@ -167,7 +168,9 @@ struct GelatoPlan {
   double *d_pack = nullptr, *h_pack = nullptr;  // [cap_pack][n_xdep], h_pack pinned
   size_t cap_pack = 0;
   int host_threads = 0;
-  int update_zero_copy = 1;  // page-locked caller buffers are written from the device (profiles/r01k_e2e.txt)
+  // scattered slots of a page-locked caller buffer: packed + host pool (0) or written from the device (1).
+  // With 8+ host threads the pool is 1.6x faster end to end (profiles/r01v_e2e.txt); few cores: zero-copy.
+  int update_zero_copy = std::thread::hardware_concurrency() < 8 ? 1 : 0;
   std::vector<std::pair<int64_t, int64_t>> big_runs;  // (first slot, length) of the long runs in xdep_idx
   const int64_t* d_xdep_small = nullptr;              // the slots outside those runs
   std::vector<int64_t> h_small;
@@ -176,7 +179,16 @@ struct GelatoPlan {
   cudaEvent_t ev_kernel = nullptr, ev_copy = nullptr;
   cudaStream_t pair_stream = nullptr;  // residual kernel of a pair evaluation, concurrent with the Jacobian kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  std::vector<cudaEvent_t> chunk_ev;
+  // update mode pipelined over slices of the batch: slice k's upload and kernels overlap slice k-1's copies.
+  // Slice 0 runs on the streams above, the others on lanes created on first use.
+  struct Lane {
+    cudaStream_t stream = nullptr, copy_stream = nullptr, pair_stream = nullptr;
+    cudaEvent_t ev_kernel = nullptr, ev_copy = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+  };
+  std::vector<Lane> lanes;
+  int update_slices = 0;  // 0 = choose from the batch size
+  int32_t* d_iota = nullptr;  // 0, 1, 2 ...: a slice's scenario ids
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -354,7 +366,18 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (p->h_pack) cudaFreeHost(p->h_pack);
   if (p->d_ids) cudaFree(p->d_ids);
   if (p->d_vals_ids) cudaFree(p->d_vals_ids);
-  for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
+  for (size_t k = 0; k < p->lanes.size(); k++) {
+    GelatoPlan::Lane& L = p->lanes[k];
+    for (cudaEvent_t e : L.chunk_ev) cudaEventDestroy(e);
+    if (k == 0) continue;  // lane 0 borrows the plan's own streams and events
+    for (cudaEvent_t e : {L.ev_kernel, L.ev_copy, L.ev_fork, L.ev_join})
+      if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {L.stream, L.copy_stream, L.pair_stream})
+      if (st) cudaStreamDestroy(st);
+  }
+  for (GelatoPlan::Lane& L : p->lanes)
+    if (L.ev_h2d) cudaEventDestroy(L.ev_h2d);
+  if (p->d_iota) cudaFree(p->d_iota);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev_kernel) cudaEventDestroy(p->ev_kernel);
@@ -454,7 +477,9 @@ static int ensure_staging(GelatoPlan* p, size_t n_scen) {
   if (p->d_vals) cudaFree(p->d_vals);
   if (p->h_x) cudaFreeHost(p->h_x);
   if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->d_iota) cudaFree(p->d_iota);
   p->d_x = p->d_g = p->d_vals = p->h_x = p->h_out = nullptr;
+  p->d_iota = nullptr;
   p->cap_scen = 0;
   const PlanView& v = p->view;
   const size_t nout = std::max<size_t>((size_t)v.n_rows, (size_t)v.n_vals);
@@ -463,9 +488,16 @@ static int ensure_staging(GelatoPlan* p, size_t n_scen) {
   CU(cudaMalloc(&p->d_vals, n_scen * (size_t)v.n_vals * sizeof(double)));
   CU(cudaMallocHost(&p->h_x, n_scen * v.n_vars * sizeof(double)));
   CU(cudaMallocHost(&p->h_out, n_scen * nout * sizeof(double)));
+  CU(cudaMalloc(&p->d_iota, n_scen * sizeof(int32_t)));
+  std::vector<int32_t> iota(n_scen);
+  for (size_t k = 0; k < n_scen; k++) iota[k] = (int32_t)k;
+  CU(cudaMemcpy(p->d_iota, iota.data(), n_scen * sizeof(int32_t), cudaMemcpyHostToDevice));
   p->cap_scen = n_scen;
   // constants of the Jacobian: written once, the kernel only rewrites x-dependent slots
-  return gelato_fill_template(p, p->d_vals, (int)n_scen, p->stream);
+  int rc = gelato_fill_template(p, p->d_vals, (int)n_scen, p->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(p->stream));  // the other lanes' kernels write into it too
+  return GELATO_OK;
 }
 
 // page-locked host memory can be DMA'd directly; pageable memory goes through the plan's staging buffers
@@ -596,39 +628,30 @@ int gelato_set_host_threads(GelatoPlan* p, int32_t n) {
   return GELATO_OK;
 }
 
-static void scatter_scenarios(const int64_t* idx, long long n_xdep, const double* packed, double* vals,
-                              long long n_vals, int s0, int s1) {
-  for (int s = s0; s < s1; s++) {
-    const double* src = packed + (size_t)s * n_xdep;
-    double* dst = vals + (size_t)s * n_vals;
-    // isolated slots (the node-diagonals of the dense D blocks) cost one cache-line fill each: ask for
-    // the lines a few dozen writes ahead so the fills overlap
-    const long long ahead = 48;
-    long long i = 0;
-    for (; i + ahead < n_xdep; i++) {
-      __builtin_prefetch(dst + idx[i + ahead], 1, 0);
-      dst[idx[i]] = src[i];
-    }
-    for (; i < n_xdep; i++) dst[idx[i]] = src[i];
+using gelato_host::scatter_parallel;
+
+static int ensure_lanes(GelatoPlan* p, int n) {
+  if (p->lanes.empty()) {
+    GelatoPlan::Lane L;
+    L.stream = p->stream; L.copy_stream = p->copy_stream; L.pair_stream = p->pair_stream;
+    L.ev_kernel = p->ev_kernel; L.ev_copy = p->ev_copy; L.ev_fork = p->ev_fork; L.ev_join = p->ev_join;
+    p->lanes.push_back(L);
   }
+  while ((int)p->lanes.size() < n) {
+    p->lanes.emplace_back();
+    GelatoPlan::Lane& L = p->lanes.back();  // registered first: gelato_plan_destroy releases whatever exists
+    for (cudaStream_t* st : {&L.stream, &L.copy_stream, &L.pair_stream}) CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&L.ev_kernel, &L.ev_copy, &L.ev_fork, &L.ev_join}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  for (GelatoPlan::Lane& L : p->lanes)
+    if (!L.ev_h2d) CU(cudaEventCreateWithFlags(&L.ev_h2d, cudaEventDisableTiming));
+  return GELATO_OK;
 }
 
-// packed -> vals for scenarios [s0, s1) on `threads` host threads
-static void scatter_parallel(const int64_t* idx, long long n_idx, const double* packed, double* vals, long long n_vals,
-                             int s0, int s1, int threads) {
-  if (threads <= 1 || s1 - s0 < 2) {
-    scatter_scenarios(idx, n_idx, packed, vals, n_vals, s0, s1);
-    return;
-  }
-  std::vector<std::thread> pool;
-  for (int t = 0; t < threads; t++) {
-    const int a = s0 + (int)((long long)(s1 - s0) * t / threads), b = s0 + (int)((long long)(s1 - s0) * (t + 1) / threads);
-    if (a < b) pool.emplace_back(scatter_scenarios, idx, n_idx, packed, vals, n_vals, a, b);
-  }
-  for (auto& th : pool) th.join();
-}
-
-// shared body of gelato_eval_jacobian_update / gelato_eval_pair_update; g == NULL: Jacobian only
+// shared body of gelato_eval_jacobian_update / gelato_eval_pair_update; g == NULL: Jacobian only.
+// The batch is cut into slices of scenarios, each on its own lane of streams: slice k's upload and kernels
+// overlap slice k-1's device->host traffic (PCIe is full duplex), and the host threads scatter slice k-1's
+// packed slots meanwhile.  Per slice: upload x -> { residual kernel -> copy g | Jacobian kernel -> transfers }.
 static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, int32_t n_scen) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
@@ -646,89 +669,128 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
     CU(cudaMallocHost(&p->h_pack, (size_t)n_scen * p->n_xdep * sizeof(double)));
     p->cap_pack = n_scen;
   }
-  const size_t nxin = (size_t)n_scen * v.n_vars;
   const double* hx = x;
   if (!is_pinned(x)) {
-    memcpy(p->h_x, x, nxin * sizeof(double));
+    memcpy(p->h_x, x, (size_t)n_scen * v.n_vars * sizeof(double));
     hx = p->h_x;
   }
-  CU(cudaMemcpyAsync(p->d_x, hx, nxin * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   const bool g_direct = g && is_pinned(g);
-  if (g) {  // residuals of the same x on the side stream: kernel and copy overlap the Jacobian's
-    const size_t ng = (size_t)n_scen * v.n_rows;
-    CU(cudaEventRecord(p->ev_fork, p->stream));
-    CU(cudaStreamWaitEvent(p->pair_stream, p->ev_fork, 0));
-    k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->pair_stream>>>(p->view, p->res_blocks, n_scen, nullptr,
-                                                                                    p->d_x, p->d_g);
-    p->launches++;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(g_direct ? g : p->h_out, p->d_g, ng * sizeof(double), cudaMemcpyDeviceToHost, p->pair_stream));
-    CU(cudaEventRecord(p->ev_join, p->pair_stream));
-  }
-  if ((rc = gelato_eval_jacobian_dev(p, p->d_x, p->d_vals, n_scen, p->stream))) return rc;
+  double* const g_dst = g_direct ? g : p->h_out;
 
-  // Which slots travel packed (gathered on the device, copied, scattered by host threads) and which go
+  // Which slots travel packed (gathered on the device, copied, scattered by the host pool) and which go
   // straight to their place: a page-locked `vals` takes the long runs of consecutive slots through the copy
-  // engine (one strided 2-D copy per run covers every scenario; second stream) and, in zero-copy mode, the
-  // scattered rest through a kernel that stores into the buffer's device mapping.
+  // engine (one strided 2-D copy per run covers a slice's scenarios) and, in zero-copy mode, the scattered
+  // rest through a kernel that stores into the buffer's device mapping.
   const bool direct = is_pinned(vals);
   const int64_t* pack_idx_dev = direct ? p->d_xdep_small : p->d_xdep;
   const int64_t* pack_idx_host = direct ? p->h_small.data() : p->h_xdep.data();
   long long n_pack = direct ? p->n_small : p->n_xdep;
-  if (direct) {
-    CU(cudaEventRecord(p->ev_kernel, p->stream));
-    CU(cudaStreamWaitEvent(p->copy_stream, p->ev_kernel, 0));
-    const size_t pitch = (size_t)v.n_vals * sizeof(double);
-    for (const auto& run : p->big_runs)
-      CU(cudaMemcpy2DAsync(vals + run.first, pitch, p->d_vals + run.first, pitch, (size_t)run.second * sizeof(double),
-                           (size_t)n_scen, cudaMemcpyDeviceToHost, p->copy_stream));
-    CU(cudaEventRecord(p->ev_copy, p->copy_stream));
-    double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
-    if (p->update_zero_copy && n_pack > 0 && cudaHostGetDevicePointer((void**)&dev_view, vals, 0) != cudaSuccess) {
+  double* dev_view = nullptr;  // the device's address of the caller's page-locked buffer
+  if (direct && p->update_zero_copy && n_pack > 0) {
+    if (cudaHostGetDevicePointer((void**)&dev_view, vals, 0) != cudaSuccess) {
       cudaGetLastError();  // registered without a device mapping: the scattered slots travel packed instead
       dev_view = nullptr;
     }
-    if (dev_view) {
-      const int threads = 256;
-      const int bx = (int)std::min<long long>((n_pack + threads - 1) / threads, 4096);
-      k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, pack_idx_dev, n_pack, v.n_vals, dev_view);
-      p->launches++;
-      CU(cudaGetLastError());
-      n_pack = 0;
-    }
   }
-  if (n_pack > 0) {
-    const int threads_gpu = 256;
-    const int bx = (int)std::min<long long>((n_pack + threads_gpu - 1) / threads_gpu, 4096);
-    k_pack_xdep<<<dim3(bx, n_scen), threads_gpu, 0, p->stream>>>(p->d_vals, pack_idx_dev, n_pack, v.n_vals, p->d_pack);
-    p->launches++;
-    CU(cudaGetLastError());
-    // device->host in chunks of scenarios, so the host scatter of chunk k overlaps the copy of chunk k+1
-    int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    if ((long long)n_scen * n_pack < (1LL << 18)) threads = 1;
-    threads = std::min(threads, (int)n_scen);
-    const int n_chunks = (n_scen >= 4 * threads && threads > 1) ? 4 : 1;
-    while ((int)p->chunk_ev.size() < n_chunks) {
+  const bool zero_copy = dev_view != nullptr;
+
+  int threads = p->host_threads > 0 ? p->host_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if ((long long)n_scen * n_pack < (1LL << 18)) threads = 1;
+  threads = std::min(threads, (int)n_scen);
+  int n_slices = p->update_slices > 0 ? p->update_slices : n_scen / 16;  // measured: profiles/r01v_e2e.txt
+  n_slices = std::max(1, std::min(n_slices, std::min((int)n_scen, 8)));
+  // one slice: the packed slots come down in chunks so the scatter of chunk k overlaps the copy of chunk k+1
+  const int n_chunks = (n_slices == 1 && n_scen >= 4 * threads && threads > 1) ? 4 : 1;
+  if ((rc = ensure_lanes(p, n_slices))) return rc;
+  for (int k = 0; k < n_slices; k++)
+    while ((int)p->lanes[k].chunk_ev.size() < n_chunks) {
       cudaEvent_t e;
       CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      p->chunk_ev.push_back(e);
+      p->lanes[k].chunk_ev.push_back(e);
     }
-    std::vector<int> bounds(n_chunks + 1);
-    for (int c = 0; c <= n_chunks; c++) bounds[c] = (int)((long long)n_scen * c / n_chunks);
-    for (int c = 0; c < n_chunks; c++) {
-      const size_t off = (size_t)bounds[c] * n_pack, cnt = (size_t)(bounds[c + 1] - bounds[c]) * n_pack;
-      CU(cudaMemcpyAsync(p->h_pack + off, p->d_pack + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-      CU(cudaEventRecord(p->chunk_ev[c], p->stream));
+  auto slice_lo = [&](int k) { return (int)((long long)n_scen * k / n_slices); };
+  auto chunk_lo = [&](int k, int c) {
+    const int s0 = slice_lo(k), s1 = slice_lo(k + 1);
+    return s0 + (int)((long long)(s1 - s0) * c / n_chunks);
+  };
+
+  for (int k = 0; k < n_slices; k++) {
+    GelatoPlan::Lane& L = p->lanes[k];
+    const int s0 = slice_lo(k), ns = slice_lo(k + 1) - s0;
+    const int32_t* ids = n_slices > 1 ? p->d_iota + s0 : nullptr;  // the slice's scenario parameter blocks
+    double* const dx = p->d_x + (size_t)s0 * v.n_vars;
+    double* const dg = p->d_g + (size_t)s0 * v.n_rows;
+    double* const dvals = p->d_vals + (size_t)s0 * v.n_vals;
+    double* const hvals = vals + (size_t)s0 * v.n_vals;
+    if (k > 0) CU(cudaStreamWaitEvent(L.stream, p->lanes[k - 1].ev_h2d, 0));  // uploads one after the other
+    CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+    CU(cudaEventRecord(L.ev_h2d, L.stream));
+    if (g) {  // residuals of the same x on the side stream: kernel and copy overlap the Jacobian's
+      CU(cudaStreamWaitEvent(L.pair_stream, L.ev_h2d, 0));
+      k_residuals<<<(unsigned)p->n_res_blocks * ns, GR_THREADS, 0, L.pair_stream>>>(p->view, p->res_blocks, ns, ids, dx, dg);
+      p->launches++;
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(g_dst + (size_t)s0 * v.n_rows, dg, (size_t)ns * v.n_rows * sizeof(double), cudaMemcpyDeviceToHost,
+                         L.pair_stream));
+      CU(cudaEventRecord(L.ev_join, L.pair_stream));
     }
-    for (int c = 0; c < n_chunks; c++) {
-      CU(cudaEventSynchronize(p->chunk_ev[c]));
-      scatter_parallel(pack_idx_host, n_pack, p->h_pack, vals, v.n_vals, bounds[c], bounds[c + 1], threads);
+    if ((rc = launch_jacobian(p, dx, dvals, ns, L.stream, ids))) return rc;
+    CU(cudaGetLastError());
+
+    // the long runs, on the lane's copy stream once `after` has happened
+    auto issue_runs = [&](cudaEvent_t after) -> int {
+      CU(cudaStreamWaitEvent(L.copy_stream, after, 0));
+      const size_t pitch = (size_t)v.n_vals * sizeof(double);
+      for (const auto& run : p->big_runs)
+        CU(cudaMemcpy2DAsync(hvals + run.first, pitch, dvals + run.first, pitch, (size_t)run.second * sizeof(double),
+                             (size_t)ns, cudaMemcpyDeviceToHost, L.copy_stream));
+      CU(cudaEventRecord(L.ev_copy, L.copy_stream));
+      return GELATO_OK;
+    };
+    const int gpu_threads = 256;
+    const int bx = (int)std::max<long long>(1, std::min<long long>((n_pack + gpu_threads - 1) / gpu_threads, 4096));
+    if (direct && (zero_copy || n_pack == 0)) {
+      CU(cudaEventRecord(L.ev_kernel, L.stream));
+      if (zero_copy) {
+        k_scatter_xdep_host<<<dim3(bx, ns), gpu_threads, 0, L.stream>>>(dvals, pack_idx_dev, n_pack, v.n_vals,
+                                                                       dev_view + (size_t)s0 * v.n_vals);
+        p->launches++;
+        CU(cudaGetLastError());
+      }
+      if ((rc = issue_runs(L.ev_kernel))) return rc;
+    } else if (n_pack > 0) {
+      k_pack_xdep<<<dim3(bx, ns), gpu_threads, 0, L.stream>>>(dvals, pack_idx_dev, n_pack, v.n_vals,
+                                                             p->d_pack + (size_t)s0 * n_pack);
+      p->launches++;
+      CU(cudaGetLastError());
+      for (int c = 0; c < n_chunks; c++) {
+        const size_t off = (size_t)chunk_lo(k, c) * n_pack, cnt = (size_t)(chunk_lo(k, c + 1) - chunk_lo(k, c)) * n_pack;
+        CU(cudaMemcpyAsync(p->h_pack + off, p->d_pack + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+        CU(cudaEventRecord(L.chunk_ev[c], L.stream));
+      }
+      // the packed slots cross PCIe first: the host threads scatter them while the long runs follow
+      if (direct && (rc = issue_runs(L.chunk_ev[n_chunks - 1]))) return rc;
     }
   }
-  if (direct) CU(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
-  if (g) CU(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
-  CU(cudaStreamSynchronize(p->stream));
+  if (!zero_copy && n_pack > 0)
+    for (int k = 0; k < n_slices; k++)
+      for (int c = 0; c < n_chunks; c++) {
+        CU(cudaEventSynchronize(p->lanes[k].chunk_ev[c]));
+        scatter_parallel(pack_idx_host, n_pack, p->h_pack, vals, v.n_vals, chunk_lo(k, c), chunk_lo(k, c + 1), threads);
+      }
+  for (int k = 0; k < n_slices; k++) {
+    GelatoPlan::Lane& L = p->lanes[k];
+    if (direct) CU(cudaStreamWaitEvent(L.stream, L.ev_copy, 0));
+    if (g) CU(cudaStreamWaitEvent(L.stream, L.ev_join, 0));
+    CU(cudaStreamSynchronize(L.stream));
+  }
   if (g && !g_direct) memcpy(g, p->h_out, (size_t)n_scen * v.n_rows * sizeof(double));
+  return GELATO_OK;
+}
+
+int gelato_set_update_slices(GelatoPlan* p, int32_t n) {
+  if (!p || n < 0) return fail(GELATO_ERR_ARG, "bad slice count");
+  p->update_slices = n;
   return GELATO_OK;
 }
 
@@ -739,6 +801,58 @@ int gelato_eval_jacobian_update(GelatoPlan* p, const double* x, double* vals, in
 int gelato_eval_pair_update(GelatoPlan* p, const double* x, double* g, double* vals, int32_t n_scen) {
   if (!g) return fail(GELATO_ERR_ARG, "null buffer");
   return eval_update(p, x, g, vals, n_scen);
+}
+
+// Measurement only: device times (ms) of the transfer pieces of update mode, each alone, for a page-locked
+// `vals` after a gelato_eval_*_update call: [0] the 2-D copies of the long runs, [1] the zero-copy kernel of the
+// scattered slots, [2] both at once, [3] pack kernel + one contiguous copy of the scattered slots (no host
+// scatter), [4] one contiguous copy of as many bytes as all x-dependent slots, [5] the residual copy.
+int gelato_probe_update(GelatoPlan* p, double* vals, int32_t n_scen, int reps, float* out_ms) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!vals || !out_ms || reps <= 0 || !is_pinned(vals)) return fail(GELATO_ERR_ARG, "page-locked vals required");
+  if (!p->d_xdep || (size_t)n_scen > p->cap_pack) return fail(GELATO_ERR_ARG, "call gelato_eval_jacobian_update first");
+  const PlanView& v = p->view;
+  double* dev_view = nullptr;
+  CU(cudaHostGetDevicePointer((void**)&dev_view, vals, 0));
+  const size_t pitch = (size_t)v.n_vals * sizeof(double);
+  const int threads = 256;
+  const int bx = (int)std::min<long long>((p->n_small + threads - 1) / threads, 4096);
+  auto copies = [&]() {
+    for (const auto& run : p->big_runs)
+      cudaMemcpy2DAsync(vals + run.first, pitch, p->d_vals + run.first, pitch, (size_t)run.second * sizeof(double),
+                        (size_t)n_scen, cudaMemcpyDeviceToHost, p->copy_stream);
+  };
+  auto zero_copy = [&]() {
+    if (p->n_small > 0)
+      k_scatter_xdep_host<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, p->d_xdep_small, p->n_small, v.n_vals, dev_view);
+  };
+  for (int piece = 0; piece < 6; piece++) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(p->ev0, p->stream));
+    CU(cudaStreamWaitEvent(p->copy_stream, p->ev0, 0));
+    for (int r = 0; r < reps; r++) {
+      if (piece == 0 || piece == 2) copies();
+      if (piece == 1 || piece == 2) zero_copy();
+      if (piece == 3 && p->n_small > 0) {
+        k_pack_xdep<<<dim3(bx, n_scen), threads, 0, p->stream>>>(p->d_vals, p->d_xdep_small, p->n_small, v.n_vals, p->d_pack);
+        cudaMemcpyAsync(p->h_pack, p->d_pack, (size_t)n_scen * p->n_small * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+      }
+      if (piece == 4)
+        cudaMemcpyAsync(p->h_pack, p->d_pack, (size_t)n_scen * p->n_xdep * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+      if (piece == 5)
+        cudaMemcpyAsync(p->h_out, p->d_g, (size_t)n_scen * v.n_rows * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+    }
+    CU(cudaEventRecord(p->ev_copy, p->copy_stream));
+    CU(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaEventSynchronize(p->ev1));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    out_ms[piece] = ms / reps;
+  }
+  return GELATO_OK;
 }
 
 int gelato_host_alloc(size_t bytes, void** out) {

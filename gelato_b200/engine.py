@@ -197,6 +197,8 @@ def load_library():
     L.gelato_eval_pair_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_set_host_threads.argtypes = [vp, ctypes.c_int32]
     L.gelato_set_update_zero_copy.argtypes = [vp, ctypes.c_int32]
+    L.gelato_set_update_slices.argtypes = [vp, ctypes.c_int32]
+    L.gelato_probe_update.argtypes = [vp, _pd, ctypes.c_int32, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     L.gelato_pack_xdep_dev.argtypes = [vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.gelato_host_free.argtypes = [vp]
@@ -223,7 +225,7 @@ EXPORTS = (
     "gelato_plan_n_vars gelato_plan_n_rows gelato_plan_n_vals gelato_plan_launch_count gelato_eval_residuals "
     "gelato_eval_jacobian gelato_eval_residuals_ids gelato_eval_jacobian_ids gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
-    "gelato_eval_pair_update gelato_eval_pair_dev gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_eval_pair_update gelato_eval_pair_dev gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_set_update_slices gelato_probe_update gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
     "gelato_leaf_atmosphere gelato_leaf_output_table"
@@ -340,6 +342,15 @@ class Engine:
 
     def set_update_zero_copy(self, on=True):
         _check(self.L, self.L.gelato_set_update_zero_copy(self.h, 1 if on else 0), "gelato_set_update_zero_copy")
+
+    def probe_update(self, vals, n_scen, reps=10):
+        """Device times (ms) of the transfer pieces of update mode (measurement only; tools/e2e_probe.py)."""
+        out = (ctypes.c_float * 6)()
+        _check(self.L, self.L.gelato_probe_update(self.h, vals.ctypes.data_as(_pd), n_scen, reps, out), "gelato_probe_update")
+        return dict(zip(("copies_2d", "zero_copy", "both", "pack_and_copy", "contiguous_all", "residual_copy"), list(out)))
+
+    def set_update_slices(self, n):
+        _check(self.L, self.L.gelato_set_update_slices(self.h, int(n)), "gelato_set_update_slices")
 
     def set_host_threads(self, n):
         _check(self.L, self.L.gelato_set_host_threads(self.h, int(n)), "gelato_set_host_threads")

@@ -213,6 +213,13 @@ int gelato_eval_pair_update(GelatoPlan* plan, const double* x, double* g, double
  * slots straight into it from the device (zero-copy over PCIe, no host thread touches the buffer); pageable
  * buffers, or on == 0, take pack + copy + host scatter */
 int gelato_set_update_zero_copy(GelatoPlan* plan, int32_t on);
+/* Update mode is pipelined over `n` slices of the batch (slice k's upload and kernels overlap slice k-1's
+ * device->host traffic and host scatter); 0 = chosen from the batch size (one slice per 16 scenarios, at most 8). */
+int gelato_set_update_slices(GelatoPlan* plan, int32_t n);
+/* Measurement only: device times (ms) of the transfer pieces of update mode, each alone (out_ms[6]: long-run 2-D
+ * copies, zero-copy kernel, both, pack + contiguous copy of the scattered slots, one contiguous copy of all
+ * x-dependent bytes, the residual copy).  `vals` page-locked, after a gelato_eval_*_update call. */
+int gelato_probe_update(GelatoPlan* plan, double* vals, int32_t n_scen, int reps, float* out_ms);
 /* host threads used by the scatter of update mode (default: min(16, hardware threads)) */
 int gelato_set_host_threads(GelatoPlan* plan, int32_t n_threads);
 

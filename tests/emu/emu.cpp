@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../gelato_b200/csrc/host_pool.h"
 #include "../../gelato_b200/csrc/output.h"
 #include "../../gelato_b200/csrc/plan_host.h"
 
@@ -112,3 +113,11 @@ extern "C" void emu_output_rows(int n, const double* mass, const double* pos, co
                q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]), t[i], thrust_vac[i], air_area[i],
                nozzle_area[i], tb, lat0, lon0, out + (size_t)i * GO_COLS);
 }
+
+// update mode's host side (host_pool.h): packed x-dependent slots -> the caller's Jacobian buffers
+extern "C" void emu_scatter_parallel(const int64_t* idx, long long n_idx, const double* packed, double* vals,
+                                     long long n_vals, int s0, int s1, int threads) {
+  gelato_host::scatter_parallel(idx, n_idx, packed, vals, n_vals, s0, s1, threads);
+}
+
+extern "C" int emu_pool_workers(void) { return gelato_host::HostPool::instance().workers(); }

@@ -194,6 +194,50 @@ def test_update_mode_equals_full_jacobian(pinned):
     E.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_sliced_update_pipeline_is_invisible(pinned):
+    """Update mode pipelined over 1, 2, 3, 5 slices of a batch of DISPERSED scenarios (every slice must use its own
+    scenarios' parameter blocks), packed or zero-copy: the host buffers are the same bits as the plain calls."""
+    Lg = leaves.get("gmath")
+    inp = helpers.example_inputs()
+    n = 7
+    scen = scenarios.disperse(inp, n, seed=5)
+    plans, xs = [], []
+    for si in scen:
+        p, u, c, x0 = problem.problem_from_inputs(si, coord=Lg.coordinate_c, factor=2)
+        plans.append(helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c))
+        xs.append(x0)
+    E = engine.Engine(plans[0], scenario_plans=plans)
+    P = plans[0]
+    X = np.stack([problem.xdict_to_vector(helpers.perturbed(x, seed=3 + k)) for k, x in enumerate(xs)])
+    g_want, v_want = E.eval_residuals(X, n).copy(), E.eval_jacobian(X, n).copy()
+    assert len({v_want[k].tobytes() for k in range(n)}) == n  # the scenarios do differ
+    hg = engine.PinnedArray(n * P.n_rows) if pinned else None
+    hv = engine.PinnedArray(n * P.n_vals) if pinned else None
+    g = hg.array if pinned else np.empty(n * P.n_rows)
+    v = hv.array if pinned else np.empty(n * P.n_vals)
+    E.jacobian_template(v, n)
+    for zero_copy in (False, True):
+        E.set_update_zero_copy(zero_copy)
+        for slices, threads in ((1, 1), (2, 3), (3, 2), (5, 4), (0, 0)):
+            E.set_update_slices(slices)
+            E.set_host_threads(threads)
+            g[:] = np.nan
+            v.reshape(n, -1)[:, P.xdep_index()] = np.nan
+            G, V = E.eval_pair_update(X, g, v, n)
+            assert np.array_equal(G, g_want) and np.array_equal(V, v_want), (zero_copy, slices)
+            v.reshape(n, -1)[:, P.xdep_index()] = np.nan
+            assert np.array_equal(E.eval_jacobian_update(X, v, n), v_want), (zero_copy, slices)
+    # fewer scenarios than slices asked for
+    E.set_update_slices(8)
+    v.reshape(n, -1)[:3, P.xdep_index()] = np.nan
+    assert np.array_equal(E.eval_jacobian_update(X[:3], v[:3 * P.n_vals], 3), v_want[:3])
+    if pinned:
+        hg.free()
+        hv.free()
+    E.close()
+
+
 def test_pair_evaluation_equals_the_two_calls():
     import torch
 

@@ -25,6 +25,7 @@ def main():
     plans, X, _ = bench.load_workload(15, B, 0, B)
     P = plans[0]
     E = engine.Engine(P, scenario_plans=plans)
+    E.set_update_slices(1)
     px, pg, pv = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * P.n_vals)
     px.array[:] = X.ravel()
     E.jacobian_template(pv.array, B)
@@ -43,10 +44,34 @@ def main():
         print("update, pinned: 2-D copies + packed scattered slots, %2d thr  %.3f ms"
               % (th, t(lambda: E.eval_jacobian_update(px.array, pv.array, B))))
     E.set_update_zero_copy(True)
+    E.set_update_slices(1)
     print("update, pinned: 2-D copies + zero-copy scattered slots       %.3f ms"
           % t(lambda: E.eval_jacobian_update(px.array, pv.array, B)))
     want = E.eval_jacobian(px.array, B).copy()
     assert np.array_equal(pv.array.reshape(B, -1), want), "zero-copy update differs from the full copy"
+    print("transfer pieces alone (device ms):", {k: round(v, 3) for k, v in E.probe_update(pv.array, B).items()})
+    print("pair update, zero-copy   %.3f ms" % t(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B)))
+    E.set_update_zero_copy(False)
+    E.set_update_slices(1)
+    for th in (4, 8, 16, 32):
+        E.set_host_threads(th)
+        print("pair update, packed + pool of %2d threads, 1 slice   %.3f ms"
+              % (th, t(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B), 20)))
+    for sl in (2, 3, 4, 6, 8):
+        E.set_update_slices(sl)
+        for th in (8, 16):
+            E.set_host_threads(th)
+            print("pair update, packed + pool of %2d threads, %d slices  %.3f ms"
+                  % (th, sl, t(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B), 20)))
+    E.set_update_zero_copy(True)
+    for sl in (1, 2, 4):
+        E.set_update_slices(sl)
+        print("pair update, zero-copy, %d slices  %.3f ms" % (sl, t(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B), 20)))
+    E.set_update_zero_copy(False)
+    E.set_update_slices(0)
+    E.set_host_threads(0)
+    print("pair update, defaults    %.3f ms" % t(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B), 20))
+    assert np.array_equal(pv.array.reshape(B, -1), want), "packed update differs from the full copy"
     E.set_update_zero_copy(False)
     idx = P.xdep_index()
     packed = np.random.rand(B, idx.size)
