@@ -36,6 +36,13 @@
 #define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
 #define GJ_EVT 16        /* event jobs per Jacobian block (16 lanes each) */
 #endif
+#ifndef GD_NODES
+#define GD_NODES 32      /* air dynamics nodes per Jacobian block */
+#define GD_A_THREADS 160 /* air dynamics blocks: threads [0, 160) one position item each (>= GD_NODES*NPV, whole
+                            warps); the other 96 loop over the rotation and quaternion items (3 rounds), and all
+                            256 over the column items (2 rounds).  Measured against 18 / 24 / 28 / 30 / 36 nodes per
+                            block: profiles/r01w_ab.txt */
+#endif
 #define GG_NODES 8     /* nodes per block of the one-lane-per-column fallback */
 #define GR_THREADS 128 /* residual kernel block */
 #define GR_NODES 64    /* nodes per residual block */
@@ -45,11 +52,14 @@
 static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS >= GJ_NODES * NPV, "position items need whole warps");
 static_assert(GJ_B_THREADS % 32 == 0 && GJ_B_THREADS >= GJ_NODES * NRV, "rotation items need whole warps");
 static_assert(GJ_A_THREADS + GJ_B_THREADS <= GJ_THREADS, "phase-0 thread map");
-static_assert(GJ_THREADS - GJ_NODES * (NPV + NRV) >= GJ_NODES, "one spare phase-0 thread per node for the quaternion items");
+static_assert(GD_A_THREADS % 32 == 0 && GD_A_THREADS >= GD_NODES * NPV && GD_A_THREADS < GJ_THREADS, "air dynamics thread map");
 static_assert(GJ_THREADS - GN_NODES * NPV >= GN_NODES && GN_NODES * NPV <= GN_A_THREADS && GN_A_THREADS <= GJ_THREADS, "no-air map");
-static_assert(GJ_NODES * 14 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS, "column items in one pass");
+static_assert(GJ_NODES * 13 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS, "column items in one pass");
 static_assert(GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS && GG_NODES <= GN_NODES, "lane maps");
-static_assert(GJ_THREADS * 3 <= GN_NODES * 14 * 3, "event jobs keep 3 values per thread in f");
+#define GJ_MAX2(a, b) ((a) > (b) ? (a) : (b))
+#define GJ_FQ_NODES GJ_MAX2(GN_NODES, GD_NODES) /* nodes the f and q arrays hold */
+#define GJ_PR_NODES GJ_MAX2(GJ_NODES, GD_NODES) /* nodes (or aero rows) the pp and rq arrays hold */
+static_assert(GJ_THREADS * 3 <= GJ_FQ_NODES * 14 * 3, "event jobs keep 3 values per thread in f");
 static_assert(GR_THREADS == 2 * GR_NODES, "residual phase 0 uses two threads per node");
 
 /* block roles */
@@ -96,12 +106,12 @@ struct PlanView {
   int n_aero_rows;
 };
 
-/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 25.5 KB), a plain struct
+/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 38 KB), a plain struct
  * in the host emulator; the jobs reach them through the pointers of JacScratch. */
-#define GJ_PP_LEN (GJ_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
-#define GJ_RQ_LEN (GJ_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
-#define GJ_F_LEN (GN_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
-#define GJ_Q_LEN (GN_NODES * 7 * 4)          /* quaternion kinematics per (node, variant) */
+#define GJ_PP_LEN (GJ_PR_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
+#define GJ_RQ_LEN (GJ_PR_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
+#define GJ_F_LEN (GJ_FQ_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
+#define GJ_Q_LEN (GJ_FQ_NODES * 7 * 4)          /* quaternion kinematics per (node, variant) */
 struct JacStore {
   double pp[GJ_PP_LEN];
   double rq[GJ_RQ_LEN];
@@ -392,7 +402,7 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
 }
 
 /* ========================================================================= */
-/* Jacobian kernel, DYN_AIR role: GJ_NODES air nodes per block, four phases   */
+/* Jacobian kernel, DYN_AIR role: GD_NODES air nodes per block, four phases   */
 /*   0  position items (node, pv) -> pos_part | rotation items (node, rv) ->  */
 /*      rotq_part | the threads left over: one node each, the 7 quaternion-  */
 /*      kinematics variants                                                   */
@@ -406,12 +416,8 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    const int qn = spare_item(tid, GJ_THREADS, count * NPV, GJ_A_THREADS, count * NRV);
-    if (qn >= 0) {
-      if (qn >= count) return;
-      const NodeRef nr = jac_node(P, start + qn);
-      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
-    } else if (tid < GJ_A_THREADS) {
+    if (tid < GD_A_THREADS) { /* the long items, one per thread */
+      if (tid >= count * NPV) return;
       const int nl = tid / NPV, pv = tid - nl * NPV;
       const NodeRef nr = jac_node(P, start + nl);
       double p[3];
@@ -419,8 +425,16 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const Tables tb = scen_tables(P, scen);
       pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
                sm.pp + (nl * NPV + pv) * PP_COLS);
-    } else {
-      const int item = tid - GJ_A_THREADS;
+      return;
+    }
+    /* the short items share the other threads: rotation items first, then one quaternion item per node */
+    for (int item = tid - GD_A_THREADS; item < count * (NRV + 1); item += GJ_THREADS - GD_A_THREADS) {
+      if (item >= count * NRV) {
+        const int qn = item - count * NRV;
+        const NodeRef nr = jac_node(P, start + qn);
+        if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
+        continue;
+      }
       const int nl = item / NRV, rv = item - nl * NRV;
       const NodeRef nr = jac_node(P, start + nl);
       double p[3];
@@ -432,21 +446,22 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
     }
   } else if (phase == 2) {
-    if (tid >= count * 14) return;
-    const int nl = tid / 14, lane = tid - nl * 14;
-    const NodeRef nr = jac_node(P, start + nl);
-    double v[11], rp[RP_COLS];
-    dyn_col_state(P, x, nr.row, lane, true, dx, v);
-    const double* pp = sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS;
-    /* the wind of this column's position, turned into ECI axes with this column's (position, time)
-     * quaternion: 56 flops, cheaper to repeat per column than a block barrier for 7 items per node */
-    rot_wind(sm.rq + (nl * NRV + lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
-    const Vec3 f = rhs_velocity_air_col(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q4(v[7], v[8], v[9], v[10]),
-                                        pp, rp, sec_param(P, scen, nr.sec), un, scen_tables(P, scen));
-    double* o = sm.f + (nl * 14 + lane) * 3;
-    o[0] = f.x;
-    o[1] = f.y;
-    o[2] = f.z;
+    for (int item = tid; item < count * 14; item += GJ_THREADS) {
+      const int nl = item / 14, lane = item - nl * 14;
+      const NodeRef nr = jac_node(P, start + nl);
+      double v[11], rp[RP_COLS];
+      dyn_col_state(P, x, nr.row, lane, true, dx, v);
+      const double* pp = sm.pp + (nl * NPV + lane_pv(lane)) * PP_COLS;
+      /* the wind of this column's position, turned into ECI axes with this column's (position, time)
+       * quaternion: 56 flops, cheaper to repeat per column than a block barrier for 7 items per node */
+      rot_wind(sm.rq + (nl * NRV + lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
+      const Vec3 f = rhs_velocity_air_col(v[0], v3(v[1], v[2], v[3]), v3(v[4], v[5], v[6]), q4(v[7], v[8], v[9], v[10]),
+                                          pp, rp, sec_param(P, scen, nr.sec), un, scen_tables(P, scen));
+      double* o = sm.f + (nl * 14 + lane) * 3;
+      o[0] = f.x;
+      o[1] = f.y;
+      o[2] = f.z;
+    }
   } else {
     dyn_scatter_block(P, scen, x, vals, start, count, tid, GJ_THREADS, sm);
   }

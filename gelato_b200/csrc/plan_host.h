@@ -126,7 +126,7 @@ static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
   const int n_aero_rows = (int)h.aero_rows.size();
 
   std::vector<int32_t>& jb = h.jac_blocks;
-  push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GJ_NODES);
+  push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GD_NODES);
   push_chunks(jb, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
   push_chunks(jb, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
   push_chunks(jb, BR_AERO, 0, n_aero_rows, GJ_NODES);
