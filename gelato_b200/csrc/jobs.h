@@ -619,69 +619,77 @@ P_HD void dyn_res_phase1(const PlanView& P, int scen, const double* x, int g0, i
   }
 }
 
-/* D.X for one (row of D, state column): acc = fma(D[j][m], X[xa+m], acc), m ascending.
- * The accumulation order is part of the numerical contract; the loads of four
- * steps are issued together so their latency overlaps. */
-P_HD double dx_dot(const double* Drow, const double* xcol, int stride, int n1) {
-  double acc = 0.0;
+/* D.X for one row of D and the W adjacent state columns of one state array (position 3, velocity 3,
+ * quaternion 4, mass 1): acc[w] = fma(D[j][m], X[xa+m][w], acc[w]), m ascending.  The accumulation order
+ * of each column is part of the numerical contract; the W chains are independent, so their
+ * fixed latencies overlap, and one load of D[j][m] serves all of them. */
+template <int W>
+P_HD void dx_dot(const double* Drow, const double* xrows, int n1, double* acc) {
+  for (int w = 0; w < W; w++) acc[w] = 0.0;
   int m = 0;
-  for (; m + 4 <= n1; m += 4) {
-    const double d0 = Drow[m], d1 = Drow[m + 1], d2 = Drow[m + 2], d3 = Drow[m + 3];
-    const double x0 = xcol[(long long)m * stride], x1 = xcol[(long long)(m + 1) * stride],
-                 x2 = xcol[(long long)(m + 2) * stride], x3 = xcol[(long long)(m + 3) * stride];
-    acc = gm_fma(d0, x0, acc);
-    acc = gm_fma(d1, x1, acc);
-    acc = gm_fma(d2, x2, acc);
-    acc = gm_fma(d3, x3, acc);
+  for (; m + 2 <= n1; m += 2) { /* the loads of two steps are issued together */
+    const double d0 = Drow[m], d1 = Drow[m + 1];
+    double x0[W], x1[W];
+    for (int w = 0; w < W; w++) x0[w] = xrows[(long long)m * W + w];
+    for (int w = 0; w < W; w++) x1[w] = xrows[(long long)(m + 1) * W + w];
+    for (int w = 0; w < W; w++) acc[w] = gm_fma(d0, x0[w], acc[w]);
+    for (int w = 0; w < W; w++) acc[w] = gm_fma(d1, x1[w], acc[w]);
   }
-  for (; m < n1; m++) acc = gm_fma(Drow[m], xcol[(long long)m * stride], acc);
-  return acc;
+  for (; m < n1; m++) {
+    const double d0 = Drow[m];
+    for (int w = 0; w < W; w++) acc[w] = gm_fma(d0, xrows[(long long)m * W + w], acc[w]);
+  }
 }
 
+/* phase 2 of the residual kernel: D.X minus right-hand side.  One item per (node, state array), array-major
+ * (neighbouring threads run the same array on neighbouring nodes), ordered position | quaternion | velocity |
+ * mass so that the two items a thread takes (item, item + nthreads) carry 6 and 5 columns. */
 P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g, int g0, int count, int tid,
                          int nthreads, const ResScratch& sm) {
   const Units un = scen_units(P, scen);
   const double ut = un.t;
-  /* column-major items: neighbouring threads run the same state column on neighbouring nodes */
-  for (int item = tid; item < count * 11; item += nthreads) {
-    const int col = item / count, nl = item - col * count;
+  for (int item = tid; item < count * 4; item += nthreads) {
+    const int grp = item / count, nl = item - grp * count;
     const NodeRef nr = res_node(P, g0 + nl);
     const int32_t* si = nr.si;
     const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
     const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
     const double dt = tf - to;
     const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
-    if (col == 0) { /* mass: con_dynamics.py:53-61 */
+    if (grp == 3) { /* mass: con_dynamics.py:53-61 */
       double r;
       if (flags & GSF_ENGINE_ON) {
-        const double lh = dx_dot(Drow, x + xa, 1, n + 1);
+        double lh[1];
+        dx_dot<1>(Drow, x + xa, n + 1, lh);
         const double rh = gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
-        r = lh - rh;
+        r = lh[0] - rh;
       } else {
         r = x[row] - x[xa];
       }
       g[si[GS_R_MASS] + j] = r;
-    } else if (col <= 3) { /* position: :146-150 */
-      const int k = col - 1;
-      const double lh = dx_dot(Drow, x + P.off_pos + 3 * xa + k, 3, n + 1);
-      const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
-      g[si[GS_R_POS] + 3 * j + k] = lh - rh;
-    } else if (col <= 6) { /* velocity: :256-287 */
-      const int k = col - 4;
-      const double lh = dx_dot(Drow, x + P.off_vel + 3 * xa + k, 3, n + 1);
-      const double rh = sm.f[nl][k] * dt * ut / 2.0;
-      g[si[GS_R_VEL] + 3 * j + k] = lh - rh;
-    } else { /* quaternion: :520-531 */
-      const int k = col - 7;
-      double r;
-      if (flags & GSF_HOLD) {
-        r = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
-      } else {
-        const double lh = dx_dot(Drow, x + P.off_quat + 4 * xa + k, 4, n + 1);
-        const double rh = sm.q[nl][k] * dt * ut / 2.0;
-        r = lh - rh;
+    } else if (grp == 0) { /* position: :146-150 */
+      double lh[3];
+      dx_dot<3>(Drow, x + P.off_pos + 3 * xa, n + 1, lh);
+      for (int k = 0; k < 3; k++) {
+        const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
+        g[si[GS_R_POS] + 3 * j + k] = lh[k] - rh;
       }
-      g[si[GS_R_QUAT] + 4 * j + k] = r;
+    } else if (grp == 2) { /* velocity: :256-287 */
+      double lh[3];
+      dx_dot<3>(Drow, x + P.off_vel + 3 * xa, n + 1, lh);
+      for (int k = 0; k < 3; k++) {
+        const double rh = sm.f[nl][k] * dt * ut / 2.0;
+        g[si[GS_R_VEL] + 3 * j + k] = lh[k] - rh;
+      }
+    } else if (flags & GSF_HOLD) { /* quaternion: :520-531 */
+      for (int k = 0; k < 4; k++) g[si[GS_R_QUAT] + 4 * j + k] = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
+    } else {
+      double lh[4];
+      dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh);
+      for (int k = 0; k < 4; k++) {
+        const double rh = sm.q[nl][k] * dt * ut / 2.0;
+        g[si[GS_R_QUAT] + 4 * j + k] = lh[k] - rh;
+      }
     }
   }
 }
