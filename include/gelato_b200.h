@@ -198,9 +198,10 @@ int gelato_eval_jacobian_ids(GelatoPlan* plan, const double* x, double* vals, in
  * the slots at 1 000 nodes), so only the x-dependent slots cross PCIe.
  *   gelato_jacobian_template     fills vals[n_scen][n_vals] with the constant slots (once per buffer);
  *   gelato_eval_jacobian_update  runs the Jacobian kernel and moves only the x-dependent slots into
- *                                vals (page-locked vals: written from the device; pageable vals:
- *                                packed, copied and scattered by host threads); every other slot
- *                                of vals is left as it was.
+ *                                vals (page-locked vals: long runs copied into place, scattered slots
+ *                                packed and scattered by a pool of host threads or written from the
+ *                                device; pageable vals: all packed, copied and scattered by the pool);
+ *                                every other slot of vals is left as it was.
  * After the two calls vals holds exactly what gelato_eval_jacobian returns. */
 /* gelato_eval_pair_update: `objfunc` and `sens` of the same decision vectors in one call -- x is uploaded
  * once, the residual kernel runs on a side stream next to the Jacobian kernel, g is copied back whole and
@@ -209,9 +210,11 @@ int64_t gelato_plan_n_xdep(const GelatoPlan* plan);
 int gelato_jacobian_template(GelatoPlan* plan, double* vals, int32_t n_scen);
 int gelato_eval_jacobian_update(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
 int gelato_eval_pair_update(GelatoPlan* plan, const double* x, double* g, double* vals, int32_t n_scen);
-/* on != 0 (default): when `vals` is page-locked (gelato_host_alloc), update mode writes the x-dependent
- * slots straight into it from the device (zero-copy over PCIe, no host thread touches the buffer); pageable
- * buffers, or on == 0, take pack + copy + host scatter */
+/* Scattered x-dependent slots of a page-locked `vals` (gelato_host_alloc).  on == 0 (default on hosts with 8 or
+ * more hardware threads): packed on the device, copied as one block, scattered by the host thread pool.
+ * on != 0 (default on smaller hosts): written straight into `vals` from the device (zero-copy over PCIe, no
+ * host thread touches the buffer; isolated 8-byte writes reach ~6 GB/s).  Pageable buffers always take the
+ * packed route. */
 int gelato_set_update_zero_copy(GelatoPlan* plan, int32_t on);
 /* Update mode is pipelined over `n` slices of the batch (slice k's upload and kernels overlap slice k-1's
  * device->host traffic and host scatter); 0 = chosen from the batch size (one slice per 16 scenarios, at most 8). */
