@@ -48,6 +48,20 @@ def lgr_diff_matrix(n, tau=None):
     return num / den[None, :]
 
 
+_MESH = {}  # n -> (tau, D), read-only: a study of many scenarios builds the same meshes again and again
+
+
+def mesh_tables(n):
+    """(tau[n], D[n, n+1]) of an n-node section, computed once per process (read-only arrays)."""
+    if n not in _MESH:
+        tau = lgr_nodes(n)
+        D = lgr_diff_matrix(n, tau)
+        tau.setflags(write=False)
+        D.setflags(write=False)
+        _MESH[n] = (tau, D)
+    return _MESH[n]
+
+
 class PSparams:
     """Per-section node counts, LGR points, differentiation matrices and the
     index arithmetic of the decision vector (reference: SectionParameters.py)."""
@@ -55,14 +69,11 @@ class PSparams:
     def __init__(self, num_nodes):
         self._num_nodes = [int(n) for n in num_nodes]
         self._num_sections = len(self._num_nodes)
-        cache = {}
         self._tau, self._D = [], []
         for n in self._num_nodes:
-            if n not in cache:
-                tau = lgr_nodes(n)
-                cache[n] = (tau, lgr_diff_matrix(n, tau))
-            self._tau.append(cache[n][0])
-            self._D.append(cache[n][1])
+            tau, D = mesh_tables(n)
+            self._tau.append(tau)
+            self._D.append(D)
         self._index_start_u = [int(v) for v in np.concatenate(([0], np.cumsum(self._num_nodes)[:-1]))]
         self._N = int(sum(self._num_nodes))
 
