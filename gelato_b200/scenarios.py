@@ -3,8 +3,8 @@
 A scenario is the nominal problem with perturbed stage masses, thrust levels
 and wind profile -- an independent NLP.  The reference can only run such a
 study one settings file after another (/root/reference/run_batch.sh:75-79); here
-a batch of scenarios is ONE kernel launch with the scenario index on
-blockIdx.y, and batches are spread over GPUs without any exchange in the loop.
+a batch of scenarios is ONE kernel launch (scenario = blockIdx.x mod n_scen,
+role-major), and batches are spread over GPUs without any exchange in the loop.
 """
 import copy
 
