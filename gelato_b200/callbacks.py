@@ -34,6 +34,7 @@ class GelatoProblem:
         # once), and ~10x less traffic on fine meshes.  Default False: fresh arrays, like the reference.
         self.reuse_output = bool(reuse_output) and hasattr(self.engine, "eval_jacobian_update")
         self._vals = None
+        self._csr = None
         self._x = np.empty(self.plan.n_vars)
 
     # -- helpers ---------------------------------------------------------
@@ -64,6 +65,22 @@ class GelatoProblem:
         else:
             vals = self.engine.eval_jacobian(self.pack(xdict))
         return self.plan.split_jacobian(vals, key_order=[k for k in xdict.keys() if k in VAR_ORDER]), False
+
+    def jacobian_csr(self, xdict, wrt=None):
+        """The constraint Jacobian of all registered groups as one scipy CSR matrix (rows in registration order,
+        columns in `xdict` key order): the structure is compiled once (`plan.csr_map`), each call is one kernel
+        launch and one gather -- no per-call COO sorting (what pyoptsparse does with the dictionaries of `sens`).
+        `wrt`: {group: [variables]} as in Trajectory_Optimization.py:358-384 (None = every block)."""
+        import scipy.sparse as sp
+
+        order = tuple(k for k in xdict.keys() if k in VAR_ORDER)
+        key = (order, None if wrt is None else tuple(sorted((g, tuple(v)) for g, v in wrt.items())))
+        if self._csr is None or self._csr[0] != key:
+            self._csr = (key, self.plan.csr_map(wrt=wrt, key_order=order))
+        m = self._csr[1]
+        vals = self.engine.eval_jacobian(self.pack(xdict))
+        data = np.append(vals, 0.0)[m["src"]]
+        return sp.csr_matrix((data, m["indices"], m["indptr"]), shape=m["shape"])
 
     # -- flat-vector variants (no dictionaries), used by benchmarks / batched drivers
     def residuals(self, x, n_scen=1):

@@ -973,6 +973,48 @@ class CompiledPlan:
             out[key] = row.reshape(1, -1)
         return out
 
+    def csr_map(self, wrt=None, key_order=VAR_ORDER):
+        """The whole constraint Jacobian as ONE CSR matrix whose data is a gather of the flat value vector
+        (SURVEY.md 8(f)-2): rows = the groups present, stacked in registration order
+        (Trajectory_Optimization.py:358-384), columns = the variables in `key_order`; `wrt[group]`
+        (optional) restricts a group to the variables it is registered against (`:358-384` wrt lists).
+        Returns {"shape", "indptr", "indices", "src", "row0"}: for x-independent structure computed once,
+        `data = np.append(vals, 0.0)[src]` is the CSR data of any later evaluation (`src == n_vals` marks the
+        structural zeros of jac_fd's dense user blocks); entries are sorted by (row, column) and unique."""
+        probe = np.arange(1, self.n_vals + 1, dtype=np.float64)  # value = slot + 1, 0.0 = constant zero
+        s = self.split_jacobian(probe, key_order)
+        col0, o = {}, 0
+        for k in key_order:
+            col0[k] = o
+            o += self.sizes[k]
+        rows, cols, src, row0, r0 = [], [], [], {}, 0
+        for key in GROUPS:
+            gr = self.group_rows.get(key)
+            if gr is None:
+                continue
+            row0[key] = r0
+            for var, blk in s[key].items():
+                if wrt is not None and key in wrt and var not in wrt[key]:
+                    continue
+                if isinstance(blk, dict):
+                    r, c, d = blk["coo"]
+                else:  # dense (1, size) block of a user constraint
+                    d = np.asarray(blk, dtype=np.float64).ravel()
+                    r, c = np.zeros(d.size, dtype=np.int64), np.arange(d.size, dtype=np.int64)
+                rows.append(np.asarray(r, dtype=np.int64) + r0)
+                cols.append(np.asarray(c, dtype=np.int64) + col0[var])
+                src.append(np.asarray(d, dtype=np.float64))
+            r0 += gr[1]
+        rows, cols, src = np.concatenate(rows), np.concatenate(cols), np.concatenate(src)
+        src = np.where(src == 0.0, self.n_vals + 1, src).astype(np.int64) - 1
+        order = np.lexsort((cols, rows))
+        rows, cols, src = rows[order], cols[order], src[order]
+        if rows.size > 1 and np.any((np.diff(rows) == 0) & (np.diff(cols) == 0)):
+            raise ValueError("duplicate (row, column) entries in the constraint Jacobian")
+        indptr = np.zeros(r0 + 1, dtype=np.int64)
+        np.add.at(indptr, rows + 1, 1)
+        return {"shape": (r0, o), "indptr": np.cumsum(indptr), "indices": cols, "src": src, "row0": row0}
+
     def split_jacobian(self, vals, key_order=VAR_ORDER):
         """vals[n_vals] -> the reference's `funcsSens` dict; COO data arrays are
         views into `vals` (no copies)."""
