@@ -67,6 +67,17 @@ def _ptr(arr, typ):
     return arr.ctypes.data_as(typ)
 
 
+def _out(arr, n, what):
+    """A caller-supplied output buffer the C side will write n doubles into: it must be a writeable,
+    C-contiguous float64 array of exactly that size (anything else would be written through a wrong
+    pointer or stride -- memory corruption instead of an exception)."""
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags.c_contiguous or not arr.flags.writeable:
+        raise ValueError("%s must be a writeable C-contiguous float64 numpy array" % what)
+    if arr.size != n:
+        raise ValueError("%s has %d entries, expected %d" % (what, arr.size, n))
+    return arr
+
+
 def make_desc(plan):
     """CompiledPlan -> (PlanDesc, keepalive list of the arrays it points into)."""
     keep = []
@@ -289,7 +300,7 @@ class Engine:
     def eval_residuals(self, x, n_scen=1, out=None, scen_ids=None):
         """scen_ids: batch slot k uses the parameter blocks of configured scenario scen_ids[k]."""
         x = self._x(x, n_scen)
-        g = out if out is not None else np.empty(n_scen * self.n_rows)
+        g = _out(out, n_scen * self.n_rows, "out") if out is not None else np.empty(n_scen * self.n_rows)
         if scen_ids is None:
             _check(self.L, self.L.gelato_eval_residuals(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen), "gelato_eval_residuals")
         else:
@@ -301,7 +312,7 @@ class Engine:
 
     def eval_jacobian(self, x, n_scen=1, out=None, scen_ids=None):
         x = self._x(x, n_scen)
-        v = out if out is not None else np.empty(n_scen * self.n_vals)
+        v = _out(out, n_scen * self.n_vals, "out") if out is not None else np.empty(n_scen * self.n_vals)
         if scen_ids is None:
             _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
         else:
@@ -314,6 +325,7 @@ class Engine:
     # ---- update mode: one persistent host buffer per batch, only x-dependent slots cross PCIe ----
     def jacobian_template(self, out, n_scen=1):
         """Fill out[n_scen * n_vals] with the constant Jacobian slots (once per buffer)."""
+        _out(out, n_scen * self.n_vals, "out")
         _check(self.L, self.L.gelato_jacobian_template(self.h, _ptr(out, _pd), n_scen), "gelato_jacobian_template")
         return out
 
@@ -321,8 +333,7 @@ class Engine:
         """Rewrite the x-dependent slots of `out` (a buffer initialised by jacobian_template or
         holding an earlier result); afterwards `out` equals what eval_jacobian returns."""
         x = self._x(x, n_scen)
-        if out.size != n_scen * self.n_vals:
-            raise ValueError("out has %d entries, expected %d x %d" % (out.size, n_scen, self.n_vals))
+        _out(out, n_scen * self.n_vals, "out")
         _check(self.L, self.L.gelato_eval_jacobian_update(self.h, _ptr(x, _pd), _ptr(out, _pd), n_scen),
                "gelato_eval_jacobian_update")
         return out if n_scen == 1 else out.reshape(n_scen, self.n_vals)
@@ -331,8 +342,8 @@ class Engine:
         """objfunc + sens of the same decision vectors in one call (x uploaded once, the two kernels
         concurrent); g_out is filled whole, vals_out updated as by eval_jacobian_update."""
         x = self._x(x, n_scen)
-        if g_out.size != n_scen * self.n_rows or vals_out.size != n_scen * self.n_vals:
-            raise ValueError("output buffers have the wrong size")
+        _out(g_out, n_scen * self.n_rows, "g_out")
+        _out(vals_out, n_scen * self.n_vals, "vals_out")
         _check(self.L, self.L.gelato_eval_pair_update(self.h, _ptr(x, _pd), _ptr(g_out, _pd), _ptr(vals_out, _pd), n_scen),
                "gelato_eval_pair_update")
         return g_out.reshape(n_scen, self.n_rows), vals_out.reshape(n_scen, self.n_vals)

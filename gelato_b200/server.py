@@ -142,10 +142,17 @@ class CoalescingServer:
                 r.ready.set()
 
     def close(self):
+        """Stop the server: pending requests are served, the thread is joined WITHOUT a timeout (a launch in
+        flight keeps using the plan handle until it returns), then the engine is released."""
         with self._lock:
             self._stop = True
             self._lock.notify_all()
-        self._thread.join(timeout=5)
+        self._thread.join()
+        with self._lock:
+            late, self._pending = self._pending, []
+        for r in late:  # submitted after the stop flag: fail them instead of leaving their solvers waiting
+            r.error = RuntimeError("the coalescing server was closed")
+            r.ready.set()
         self.engine.close()
 
 

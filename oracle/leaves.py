@@ -35,9 +35,9 @@ def build(force=False):
     tree is present (the build container; never the GPU box), the reference's own C++
     sources against oracle/ref_shim into oracle/_ref/ (flavour "ref")."""
     libs = [os.path.join(_BUILD, "liboracle_%s.so" % f) for f in ("libm", "gmath")]
-    if force or not all(os.path.exists(p) for p in libs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
-    if os.path.isdir(REF_SRC) and (force or not os.path.exists(REF_LIB)):
+    # make decides from the time stamps (gmath.h is a dependency of the gmath flavour): a no-op when up to date
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    if os.path.isdir(REF_SRC):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REF_SRC=" + REF_SRC] + (["-B"] if force else []))
     return libs
 

@@ -16,7 +16,10 @@ What it writes
                         Eigen / pybind11 stand-in of oracle/ref_shim -- the image has no Eigen3,
                         /root/reference/CMakeLists.txt:13 -- and loaded through oracle/leaves.py).  Also `jn/...`: per Jacobian
                         slot, how far the reference's own value moves when every input is nudged
-                        by one ulp (8 random draws) -- its finite-difference noise floor.
+                        by one ulp (64 random draws) -- its finite-difference noise floor.
+  bench_reference.npz   the same (x1 only) for the BENCHMARK workload: the example refined x15 into sections
+                        of <= 20 nodes (N = 990, 13 507 variables, 571 254 Jacobian values), so that the
+                        configuration bench.py times is pinned to the reference directly.
   example_gmath.npz     the same quantities from oracle/nlp.py with the gmath leaves and
                         sequential-FMA D.X -- the flavour the CUDA kernels must match
                         bit for bit on any machine.
@@ -47,7 +50,7 @@ from gelato_b200 import problem  # noqa: E402
 from oracle import leaves  # noqa: E402
 
 
-NOISE_DRAWS = 8
+NOISE_DRAWS = 64
 
 
 def pack(prefix, f, s, out):
@@ -61,6 +64,29 @@ def pack(prefix, f, s, out):
             out["%s/j/%s/cols" % (prefix, k)] = c
     out["%s/none_f" % prefix] = np.array([k for k, v in f.items() if v is None])
     out["%s/none_j" % prefix] = np.array([k for k, v in s.items() if v is None])
+
+
+def reference_record(name, x, objfunc, sens, out):
+    """x, every funcs entry, every Jacobian block and the per-slot noise floor of the reference's callbacks."""
+    out["%s/x" % name] = problem.xdict_to_vector(x)
+    xa = helpers.copy_x(x)
+    f, fail = objfunc(xa)
+    assert fail is False
+    s, fail = sens(xa, f)
+    pack(name, f, s, out)
+    # FD noise floor of the reference itself: its Jacobian re-evaluated with every input moved
+    # by one ulp in a random direction; per slot, the largest change over the draws
+    base = helpers.flatten_sens(s)
+    noise = {k: np.zeros_like(v[2], dtype=np.float64) for k, v in base.items()}
+    rng = np.random.default_rng(11)
+    for _ in range(NOISE_DRAWS):
+        xn = {k: np.nextafter(v, np.where(rng.random(v.shape) < 0.5, -np.inf, np.inf)) for k, v in x.items()}
+        fn, _ = objfunc(xn)
+        sn, _ = sens(xn, fn)
+        for k, v in helpers.flatten_sens(sn).items():
+            noise[k] = np.maximum(noise[k], np.abs(v[2] - base[k][2]))
+    for k, v in noise.items():
+        out["%s/jn/%s" % (name, k)] = v
 
 
 def main():
@@ -78,26 +104,15 @@ def main():
     x1 = helpers.perturbed(x0)
     out = {}
     for name, x in (("x0", x0), ("x1", x1)):
-        out["%s/x" % name] = problem.xdict_to_vector(x)
-        xa = helpers.copy_x(x)
-        f, fail = objfunc(xa)
-        assert fail is False
-        s, fail = sens(xa, f)
-        pack(name, f, s, out)
-        # FD noise floor of the reference itself: its Jacobian re-evaluated with every input moved
-        # by one ulp in a random direction; per slot, the largest change over the draws
-        base = helpers.flatten_sens(s)
-        noise = {k: np.zeros_like(v[2], dtype=np.float64) for k, v in base.items()}
-        rng = np.random.default_rng(11)
-        for _ in range(NOISE_DRAWS):
-            xn = {k: np.nextafter(v, np.where(rng.random(v.shape) < 0.5, -np.inf, np.inf)) for k, v in x.items()}
-            fn, _ = objfunc(xn)
-            sn, _ = sens(xn, fn)
-            for k, v in helpers.flatten_sens(sn).items():
-                noise[k] = np.maximum(noise[k], np.abs(v[2] - base[k][2]))
-        for k, v in noise.items():
-            out["%s/jn/%s" % (name, k)] = v
+        reference_record(name, x, objfunc, sens, out)
     np.savez_compressed(os.path.join(HERE, "example_reference.npz"), **out)
+
+    # ---- the same at the benchmark workload (bench.py: factor 15, sections of <= 20 nodes) ----
+    pb, ub, cb, xb0 = problem.problem_from_inputs(helpers.example_inputs(), factor=15, max_nodes=20)
+    objfunc_b, sens_b = refharness.reference_callbacks(L, pb, ub, cb)
+    out = {}
+    reference_record("x1", helpers.perturbed(xb0), objfunc_b, sens_b, out)
+    np.savez_compressed(os.path.join(HERE, "bench_reference.npz"), **out)
 
     # ---- gmath / sequential-FMA flavour of the oracle ---------------------
     Lg = leaves.get("gmath")

@@ -147,6 +147,44 @@ def test_emulated_kernels_match_reference_golden_within_fd_noise(name):
     helpers.assert_sens_within_noise(s, npz, name)
 
 
+def test_emulated_kernels_match_reference_at_the_bench_workload():
+    """The same at the workload bench.py times (example x15 in sections of <= 20 nodes, N = 990): fixture
+    tests/golden/bench_reference.npz, made by the reference's own Python layer on its own C++ leaves."""
+    import os
+
+    npz = np.load(os.path.join(helpers.GOLDEN, "bench_reference.npz"))
+    p, u, c, x0 = helpers.example_problem(factor=15, max_nodes=20)
+    P = helpers.compiled_plan(p, u, c)
+    assert (P.N, P.n_vars, P.n_vals) == (990, 13507, 571254)
+    E = emu_binding.Emulator(P)
+    xv = npz["x1/x"].copy()
+    x = problem.vector_to_xdict(xv, P.M, P.N, P.S)
+    f = P.split_residuals(E.eval_residuals(xv))
+    for k, v in helpers.flatten_funcs(f).items():
+        atol = 1e-11 if "alpha" in k else 1e-13
+        np.testing.assert_allclose(v, npz["x1/f/%s" % k], rtol=1e-10, atol=atol, err_msg=k)
+    s = P.split_jacobian(E.eval_jacobian(xv), key_order=list(x.keys()))
+    helpers.assert_sens_within_noise(s, npz, "x1")
+
+
+def test_emulated_jacobian_is_as_close_to_the_true_derivative_as_the_reference():
+    """Finite differences with dx = 1e-8 carry ~1e-8 |f| of rounding noise, so two correct implementations
+    differ slot by slot; what the solver cares about is the distance to the TRUE derivative.  Per Jacobian
+    block: the kernels' values are no further from a 4th-order central-difference derivative of the
+    (independent, libm-flavoured) oracle residuals than the reference's own values are (x 1.5)."""
+    import os
+
+    npz = np.load(os.path.join(helpers.GOLDEN, "example_reference.npz"))
+    p, u, c, x0 = helpers.example_problem()
+    P = helpers.compiled_plan(p, u, c)
+    xv = npz["x1/x"].copy()
+    x = problem.vector_to_xdict(xv, P.M, P.N, P.S)
+    row0, J, col0 = helpers.true_jacobian(helpers.oracle_nlp(p, u, c, "libm", "numpy").objfunc, x)
+    s = P.split_jacobian(emu_binding.Emulator(P).eval_jacobian(xv), key_order=list(x.keys()))
+    rep = helpers.assert_as_close_to_truth_as_reference(s, npz, "x1", row0, J, col0)
+    assert "eqcon_dyn_vel/position" in rep and "ineqcon_qalpha/position" in rep
+
+
 @pytest.mark.parametrize("variant,user", [("example", True), ("all_aero", True), ("waypoints", True), ("neg_area", True),
                                           ("fuel_inclination", True), ("bare", False)])
 def test_xdep_index_is_exactly_what_the_jacobian_kernel_writes(variant, user):

@@ -106,6 +106,37 @@ def test_gpu_matches_reference_golden_within_tolerance(name):
     prob.close()
 
 
+def test_gpu_matches_reference_at_the_bench_workload():
+    """The configuration bench.py times (example x15, N = 990) against the reference's own result on it
+    (tests/golden/bench_reference.npz): sparsity identical, residuals 1e-10, Jacobian 1e-10 + per-row FD noise."""
+    npz = np.load(os.path.join(helpers.GOLDEN, "bench_reference.npz"))
+    p, u, c, x0 = helpers.example_problem(factor=15, max_nodes=20)
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT))
+    P = prob.plan
+    x = problem.vector_to_xdict(npz["x1/x"].copy(), P.M, P.N, P.S)
+    f, _ = prob.objfunc(x)
+    for k, v in helpers.flatten_funcs(f).items():
+        atol = 1e-11 if "alpha" in k else 1e-13
+        np.testing.assert_allclose(v, npz["x1/f/%s" % k], rtol=1e-10, atol=atol, err_msg=k)
+    s, _ = prob.sens(x, f)
+    helpers.assert_sens_within_noise(s, npz, "x1")
+    prob.close()
+
+
+def test_gpu_jacobian_is_as_close_to_the_true_derivative_as_the_reference():
+    """Per Jacobian block, |J_gpu - J_true| <= 1.5 |J_reference - J_true| (+ the FD noise floor), with J_true a
+    4th-order central-difference derivative of the libm-flavoured oracle residuals (helpers.true_jacobian)."""
+    npz = np.load(os.path.join(helpers.GOLDEN, "example_reference.npz"))
+    p, u, c, x0 = helpers.example_problem()
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT))
+    P = prob.plan
+    x = problem.vector_to_xdict(npz["x1/x"].copy(), P.M, P.N, P.S)
+    row0, J, col0 = helpers.true_jacobian(helpers.oracle_nlp(p, u, c, "libm", "numpy").objfunc, x)
+    s, _ = prob.sens(x, None)
+    helpers.assert_as_close_to_truth_as_reference(s, npz, "x1", row0, J, col0)
+    prob.close()
+
+
 def test_batched_scenarios_bitwise_and_independent_of_batching():
     Lg = leaves.get("gmath")
     inp = helpers.example_inputs()

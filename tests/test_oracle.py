@@ -125,15 +125,21 @@ def test_problem_setup_matches_reference():
         assert (a["time_ref"] == b["time_ref"]) or (a["time_ref"] != a["time_ref"] and b["time_ref"] != b["time_ref"])
 
 
+# every variant the GPU tier is checked on against the oracle (tests/test_gpu_parity.py), plus the
+# benchmark workload itself (the example refined x15 into sections of <= 20 nodes: N = 990)
+LIVE_CASES = [(v, f, 12) for v in ("example", "fuel_inclination", "all_aero", "waypoints") for f in (1, 2)]
+LIVE_CASES += [("neg_area", 1, 12), ("three_stage", 1, 12), ("three_stage", 2, 12), ("iip_orbital", 1, 12),
+               ("bare", 1, 12), ("example", 15, 20), ("waypoints", 3, 12)]
+
+
 @needs_ref
-@pytest.mark.parametrize("variant", ["example", "fuel_inclination", "all_aero", "waypoints"])
-@pytest.mark.parametrize("factor", [1, 2])
-def test_oracle_matches_reference_python_layer(variant, factor):
+@pytest.mark.parametrize("variant,factor,max_nodes", LIVE_CASES)
+def test_oracle_matches_reference_python_layer(variant, factor, max_nodes):
     """oracle/nlp.py == /root/reference/lib/con_*.py + objfunc/sens, bit for bit,
     including the residue the in-place finite differences leave in xdict."""
     L = leaves.get("libm")
     inp = helpers.variant_inputs(variant)
-    p, u, c, x0 = problem.problem_from_inputs(inp, factor=factor, max_nodes=12)
+    p, u, c, x0 = problem.problem_from_inputs(inp, factor=factor, max_nodes=max_nodes)
     objfunc, sens = refharness.reference_callbacks(L, p, u, c)
     O = helpers.oracle_nlp(p, u, c, "libm", "numpy")
     for x in (x0, helpers.perturbed(x0)):
