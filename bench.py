@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the NLP-callback hot path (BASELINE.json metric: FD-Jacobian +
-residual leaf evaluations per second).
+residual leaf evaluations per second; callback pairs per second; batched NLP solves
+per hour).
 
-Workload (BASELINE.json configs[1]): the shipped example refined to ~1 000 LGR
-nodes (x15 -> N = 990 in 53 sections of <= 20 nodes).  One STEP = one `objfunc`
-+ one `sens` (residual kernel + FD-Jacobian kernel) over a batch of 128 dispersed
-launch scenarios of that problem per GPU (8 GPUs = the 1 024 scenarios of configs[3]) (mass / thrust / wind perturbations, each
-scenario its own decision vector).  An "eval" is one physics-leaf evaluation at
-one (node x perturbation column): see CompiledPlan.eval_counts / DESIGN.md.
+Workloads (`--workload`, BASELINE.json `configs`):
+  example_x15      configs[1] (default): the shipped example refined to ~1 000 LGR nodes
+                   (x15 -> N = 990 in 53 sections of <= 20 nodes); one STEP = one `objfunc`
+                   + one `sens` over a batch of 128 dispersed launch scenarios per GPU (mass /
+                   thrust / wind perturbations, each scenario its own decision vector; 8 GPUs =
+                   the 1 024 scenarios of configs[3]).
+  three_stage_250  configs[2]: three stages, 250 sections, N = 4 836; 32 scenarios per GPU.
+  sweep_1e2 .. sweep_1e5
+                   configs[4]: ONE NLP (no batching) of 132 / 990 / 9 900 / 99 000 nodes.
+An "eval" is one physics-leaf evaluation at one (node x perturbation column): see
+CompiledPlan.eval_counts / DESIGN.md.
 
-  value   device-resident: x already in HBM, outputs stay in HBM, CUDA events; the two kernels
-          of a step are launched as one pair (residual kernel on a side stream).
-  e2e     the same step through the host-buffer C-ABI calls: x from page-locked
-          host memory -> device, both kernels, residual vector and Jacobian values
-          back into host buffers, wall clock.  The Jacobian uses update mode
-          (gelato_eval_jacobian_update: the x-dependent slots are packed on the
-          device, copied, and scattered into the batch's persistent host buffer);
-          e2e.full_copy is the same step copying the FULL value vector each call.
+  value   device-resident: x already in HBM, outputs stay in HBM, CUDA events.  A step is ONE pair
+          evaluation (gelato_eval_pair_packed_dev): the heavy Jacobian kernel, next to it the light
+          Jacobian kernel and the residual kernel's non-dynamics blocks; objfunc's dynamics rows come
+          out of the Jacobian blocks' centre columns.
+  e2e     the same step through the host-buffer C-ABI call (gelato_eval_pair_packed): x from
+          page-locked host memory -> device, the kernels, g and the packed Jacobian values back
+          into host buffers as contiguous copies, wall clock.
 Multi-GPU: scenarios are independent NLPs; each rank owns `--scenarios` of them
 (weak scaling), no data-path collective (DESIGN.md "multi-GPU").
 
@@ -24,8 +29,8 @@ Multi-GPU: scenarios are independent NLPs; each rank owns `--scenarios` of them
 (oracle/_ref: /root/reference/src compiled against oracle/ref_shim in the build
 container; falls back to the bit-identical oracle restatement if that file is
 absent) under oracle/nlp.py, the numpy port of the reference's lib/con_*.py
-(the reference's Python files themselves do not travel to the GPU box), one
-scenario per host core in parallel.
+(the reference's Python files themselves do not travel to the GPU box), the
+scenarios of a step spread over all host cores.
 """
 import argparse
 import json
@@ -49,6 +54,17 @@ USER_EVENT = "IIP_END"
 # counted 1 each, sin/cos/exp = 40, atan2/acos/asin = 60, pow = 120
 FLOPS = {"air": 1000.0, "noair": 70.0, "quat": 20.0, "aero": 800.0, "evt": 400.0}
 
+# name -> (variant, mesh factor, default scenarios per GPU)
+WORKLOADS = {
+    "example_x15": ("example", 15, 128),
+    "three_stage_250": ("three_stage", 62, 32),
+    "sweep_1e2": ("example", 2, 1),
+    "sweep_1e3": ("example", 15, 1),
+    "sweep_1e4": ("example", 150, 1),
+    "sweep_1e5": ("example", 1500, 1),
+}
+REFERENCE_SCEN_CAP = 128  # scenarios per step of the CPU arm (a bounded sample of a multi-GPU step)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -56,25 +72,41 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gelato", choices=["gelato", "reference"])
-    ap.add_argument("--scenarios", type=int, default=128,
-                    help="dispersed scenarios per GPU in one step (128 x 8 GPUs = the 1 024 scenarios of BASELINE.json configs[3])")
-    ap.add_argument("--factor", type=int, default=15, help="mesh refinement of the example (15 -> 990 nodes)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--workload", default="example_x15", choices=sorted(WORKLOADS))
+    ap.add_argument("--scenarios", type=int, default=0,
+                    help="dispersed scenarios per GPU in one step (0 = the workload's default; 128 x 8 GPUs = the 1 024 "
+                         "scenarios of BASELINE.json configs[3])")
+    ap.add_argument("--factor", type=int, default=0, help="override the workload's mesh refinement factor")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "pool", "zero-copy"],
-                    help="scattered Jacobian slots of the end-to-end leg: packed + host thread pool, or written by the "
-                         "device into the mapped buffer; auto = pool when this rank has 8+ host threads to itself")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the back-to-back device leg")
     ap.add_argument("--e2e-slices", type=int, default=0, help="pipeline slices of the end-to-end leg (0 = library default)")
-    return ap.parse_args()
+    ap.add_argument("--solve-scenarios", type=int, default=0,
+                    help="also solve this many dispersed scenarios of the shipped example per GPU to convergence "
+                         "(batched NLP solves per hour; 0 = skip)")
+    a = ap.parse_args()
+    variant, factor, scen = WORKLOADS[a.workload]
+    a.variant = variant
+    a.factor = a.factor or factor
+    a.scenarios = a.scenarios or scen
+    return a
 
 
-def load_workload(factor, n_scen_total, first, count, coord=None):
+def workload_inputs(variant):
+    from gelato_b200 import problem
+
+    inp = problem.load_inputs_json(INPUTS)
+    if variant == "three_stage":
+        problem.three_stage_inputs(inp)
+    return inp
+
+
+def load_workload(variant, factor, n_scen_total, first, count, coord=None):
     """Plans and decision vectors of scenarios [first, first+count)."""
     from gelato_b200 import plan as gplan
     from gelato_b200 import problem, scenarios
 
-    inp = problem.load_inputs_json(INPUTS)
-    scen = scenarios.disperse(inp, n_scen_total, seed=20260117)
+    scen = scenarios.disperse(workload_inputs(variant), n_scen_total, seed=20260117)
     plans, xs, probs = [], [], []
     for k in range(first, first + count):
         p, u, c, x0 = problem.problem_from_inputs(scen[k], coord=coord, factor=factor, max_nodes=20)
@@ -84,6 +116,17 @@ def load_workload(factor, n_scen_total, first, count, coord=None):
         xs.append(problem.xdict_to_vector(x))
         probs.append((p, u, c, x))
     return plans, np.stack(xs), probs
+
+
+def config_of(args, P, world):
+    """The `config` object of the JSON line -- identical for both arms."""
+    ec = P.eval_counts()
+    return {"workload": "%s (%s x%d, N=%d, sections of <= 20 nodes)" % (args.workload, args.variant, args.factor, P.N),
+            "scenarios_per_gpu": args.scenarios, "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows,
+            "n_vals": int(P.n_vals), "evals_per_scenario_step": ec["objfunc"] + ec["sens"],
+            "parallelism": "scenarios x%d" % world,
+            "step": "objfunc + sens of every scenario of the batch at its own decision vector",
+            "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launch stream"}
 
 
 class ClockSampler(threading.Thread):
@@ -104,27 +147,33 @@ class ClockSampler(threading.Thread):
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2)
-        sm, smax, reasons = [], 0.0, set()
+    def summary(self, t0=None, t1=None):
+        sm, smax, reasons, power = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in list(self.rows):
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             try:
                 sm.append(float(r[0]))
                 smax = max(smax, float(r[1]))
+                power.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except (ValueError, IndexError):
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(power)) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        return self.summary()
 
 
 def ncu_traffic(kernel, grid_blocks):
@@ -151,20 +200,34 @@ def measured_peaks():
 # ---------------------------------------------------------------------------
 # CPU legs (oracle port of the reference's callbacks)
 # ---------------------------------------------------------------------------
-def _cpu_worker(args):
-    factor, n_total, k, reps = args
-    from oracle import leaves, nlp, user_builtin
+_CPU_CACHE = {}
 
-    plans, X, probs = load_workload(factor, n_total, k, 1)
-    p, u, c, x = probs[0]
-    flav = cpu_flavour()
-    L = leaves.get(flav)
-    O = nlp.OracleNLP(p, u, c, flav, "numpy", user_eq=user_builtin.perigee_ratio_at(L, USER_EVENT))
+
+def _cpu_problem(variant, factor, n_total, k, flav):
+    """The oracle's callbacks and the decision vector of scenario k (built once per worker process)."""
+    key = (variant, factor, n_total, k, flav)
+    if key not in _CPU_CACHE:
+        from oracle import leaves, nlp, user_builtin
+
+        plans, X, probs = load_workload(variant, factor, n_total, k, 1)
+        p, u, c, x = probs[0]
+        L = leaves.get(flav)
+        _CPU_CACHE[key] = (nlp.OracleNLP(p, u, c, flav, "numpy", user_eq=user_builtin.perigee_ratio_at(L, USER_EVENT)), x)
+    return _CPU_CACHE[key]
+
+
+def _cpu_worker(args):
+    """objfunc + sens of the scenarios `ks`, `reps` times; returns the seconds spent in the callbacks."""
+    variant, factor, n_total, ks, reps, flav = args
+    if isinstance(ks, int):
+        ks = [ks]
+    todo = [_cpu_problem(variant, factor, n_total, k, flav) for k in ks]
     t0 = time.perf_counter()
     for _ in range(reps):
-        xa = {key: v.copy() for key, v in x.items()}
-        f, _ = O.objfunc(xa)
-        O.sens(xa)
+        for O, x in todo:
+            xa = {key: v.copy() for key, v in x.items()}
+            f, _ = O.objfunc(xa)
+            O.sens(xa)
     return time.perf_counter() - t0
 
 
@@ -178,51 +241,80 @@ def cpu_flavour():
 
 
 CPU_DESC = {"ref": "the reference's own C++ leaves (oracle/_ref) under oracle/nlp.py, the numpy port of lib/con_*.py",
-            "libm": "oracle/nlp.py port on the oracle's libm leaves"}
+            "libm": "oracle/nlp.py port on the oracle's own libm leaves (bit-identical to the reference's C++, lighter call layer)"}
 
 
-def cpu_baseline(factor, evals_per_scen, budget_s):
-    """One host core, one scenario of the workload, objfunc+sens repeated for ~budget_s."""
-    t1 = _cpu_worker((factor, 1, 0, 1))  # also warms imports / builds
-    reps = int(max(2, min(50, budget_s / max(t1, 1e-3))))
-    dt = _cpu_worker((factor, 1, 0, reps))
-    return {"value": evals_per_scen * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d x (objfunc+sens) of 1 scenario of the workload (N=%d nodes), %s, "
-                      "%.2f s per pair" % (reps, 66 * factor, CPU_DESC[cpu_flavour()], dt / reps)}
+def cpu_baseline(args, evals_per_scen, nodes):
+    """One host core, one scenario of the workload, objfunc+sens repeated for ~budget seconds -- on the reference's own
+    C++ leaves (the headline figure) and on the oracle's restatement of them (4-5x faster per leaf call)."""
+    out = None
+    for flav in ([cpu_flavour()] + (["libm"] if cpu_flavour() == "ref" else [])):
+        t1 = _cpu_worker((args.variant, args.factor, 1, 0, 1, flav))  # also warms imports / builds
+        reps = int(max(2, min(50, args.cpu_seconds / max(t1, 1e-3))))
+        dt = _cpu_worker((args.variant, args.factor, 1, 0, reps, flav))
+        leg = {"value": evals_per_scen * reps / dt, "unit": UNIT, "cores": 1, "kind": "port", "leaves": flav,
+               "pairs_per_s": reps / dt,
+               "sample": "%d x (objfunc+sens) of 1 scenario of the workload (N=%d nodes), %s, %.3f s per pair"
+                         % (reps, nodes, CPU_DESC[flav], dt / reps)}
+        if out is None:
+            out = leg
+        else:
+            out["libm_leaves"] = leg
+    return out
 
 
 def run_reference(args):
-    """The reference's CPU path on all host cores: one scenario per core per step."""
+    """The reference's CPU path on all host cores.  Honours --steps / --warmup / --scenarios: a step is objfunc + sens
+    of the step's scenarios (at most REFERENCE_SCEN_CAP of them: a bounded sample of a multi-GPU step), spread over a
+    pool of one worker per host core."""
     import multiprocessing as mp
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from gelato_b200 import plan as gplan  # counts only; nothing is evaluated by the engine here
-
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    plans, _, _ = load_workload(args.factor, 1, 0, 1)
-    ec = plans[0].eval_counts()
+    plans, _, _ = load_workload(args.variant, args.factor, 1, 0, 1)
+    P = plans[0]
+    ec = P.eval_counts()
     evals_per_scen = ec["objfunc"] + ec["sens"]
-    del gplan
-    with mp.get_context("spawn").Pool(cores) as pool:
-        for _ in range(max(1, min(args.warmup, 1))):
-            pool.map(_cpu_worker, [(args.factor, cores, k, 1) for k in range(cores)])
-        steps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            pool.map(_cpu_worker, [(args.factor, cores, k, 1) for k in range(cores)])
-        dt = time.perf_counter() - t0
-    value = evals_per_scen * cores * steps / dt
-    sample = ("each step = objfunc+sens of %d dispersed scenarios of the workload (one per host core, spawn pool), "
-              "%s; %d timed steps" % (cores, CPU_DESC[cpu_flavour()], steps))
+    n_step = min(args.scenarios * world, REFERENCE_SCEN_CAP)
+    flav = cpu_flavour()
+    nw = min(cores, n_step)
+    # one single-process executor per worker, so that scenario k always lands in the process that has already set its
+    # problem up (the reference sets a problem up once per solve, not once per callback)
+    from concurrent.futures import ProcessPoolExecutor
+
+    ctx = mp.get_context("spawn")
+    workers = [ProcessPoolExecutor(1, mp_context=ctx) for _ in range(nw)]
+    tasks = [(args.variant, args.factor, n_step, list(range(w, n_step, nw)), 1, flav) for w in range(nw)]
+
+    def step():
+        for f in [workers[w].submit(_cpu_worker, tasks[w]) for w in range(nw)]:
+            f.result()
+
+    step()  # problem set-up and imports in every worker (not a timed or counted step)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    for w in workers:
+        w.shutdown()
+    value = evals_per_scen * n_step * args.steps / dt
+    sample = ("each step = objfunc+sens of %d dispersed scenarios of the workload%s, spread over %d worker processes (one per "
+              "host core; every problem set up once, before the warm-up), %s"
+              % (n_step, "" if n_step == args.scenarios * world else " (of the %d of a step of the GPU arm)" % (args.scenarios * world),
+                 nw, CPU_DESC[flav]))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "example_x%d_N%d_split20" % (args.factor, 66 * args.factor),
-                   "scenarios_per_step": cores, "evals_per_scenario_step": evals_per_scen},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(args, P, world),
+        "pairs_per_s": n_step * args.steps / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nw, "kind": "port", "leaves": flav,
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -248,17 +340,13 @@ def run_gelato(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.scenarios
     own = gscen.partition(B * world, world, rank)
-    plans, X, probs = load_workload(args.factor, B * world, own.start, len(own))
+    plans, X, probs = load_workload(args.variant, args.factor, B * world, own.start, len(own))
     P = plans[0]
-    E = engine.Engine(P, device=local, scenario_plans=plans)
-    # scatter threads of update mode: the ranks of one node share the host cores (and its memory bandwidth)
-    host_threads = max(1, min(16, (os.cpu_count() or 1) // world))
-    E.set_host_threads(host_threads)
-    zero_copy = args.e2e_mode == "zero-copy" or (args.e2e_mode == "auto" and host_threads < 8)
-    E.set_update_zero_copy(zero_copy)
+    E = engine.Engine(P, device=local, scenario_plans=plans if B > 1 else None)
     E.set_update_slices(args.e2e_slices)
     ec = P.eval_counts()
     evals_step_rank = (ec["objfunc"] + ec["sens"]) * B
+    n_pack = E.n_pack
     # a dedicated non-default stream: the C ABI reads stream 0 as "the plan's own stream", and the
     # CUDA events below must sit on the stream the kernels are launched on
     tstream = torch.cuda.Stream()
@@ -267,87 +355,85 @@ def run_gelato(args):
     assert st != 0
 
     xd = torch.from_numpy(X).cuda()
-    gd = torch.empty((B, P.n_rows), dtype=torch.float64, device="cuda")
-    vd = torch.empty((B, P.n_vals), dtype=torch.float64, device="cuda")
-    E.fill_template(vd.data_ptr(), B, st)
+    gd = torch.full((B, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
+    pd = torch.full((B, n_pack), float("nan"), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    W = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev(evs=None):
-        if evs:
-            evs[0].record()
-        E.eval_residuals_dev(xd.data_ptr(), gd.data_ptr(), B, st)
-        if evs:
-            evs[1].record()
-        E.eval_jacobian_dev(xd.data_ptr(), vd.data_ptr(), B, st)
-        if evs:
-            evs[2].record()
+    def timed_events(launch, n_ev=2):
+        """W warm-up steps, then args.steps steps bracketed by CUDA events on the launch stream, L2 flushed between
+        steps (outside the brackets); returns the summed milliseconds."""
+        for _ in range(W):
+            launch()
+            flush.zero_()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        barrier()
+        for k in range(args.steps):
+            evs[k][0].record()
+            launch()
+            evs[k][1].record()
+            flush.zero_()
+        barrier()
+        return sum(e[0].elapsed_time(e[1]) for e in evs)
 
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-        flush.zero_()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    launches0 = E.launches
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    barrier()
-    for k in range(args.steps):
-        step_dev(evs[k])
-        flush.zero_()  # L2 flush between timed steps (outside the per-step event brackets)
-    barrier()
-    serial_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
-    res_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    jac_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
 
-    # ---- the headline: objfunc + sens of the same decision vectors as ONE pair evaluation (the residual kernel
-    #      on a side stream next to the Jacobian kernel); same work, same results as the two calls above ----
-    def step_pair(ev=None):
-        if ev:
-            ev[0].record()
-        E.eval_pair_dev(xd.data_ptr(), gd.data_ptr(), vd.data_ptr(), B, st)
-        if ev:
-            ev[1].record()
-
-    g_serial, v_serial = gd.clone(), vd.clone()
-    for _ in range(max(args.warmup, 3)):
-        step_pair()
-        flush.zero_()
-    evp = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    barrier()
+    # ---- the headline: objfunc + sens of the batch as ONE pair evaluation, packed Jacobian output ----
     launches0 = E.launches
-    for k in range(args.steps):
-        step_pair(evp[k])
-        flush.zero_()
+    t_dev0 = time.perf_counter()
+    dev_ms = timed_events(lambda: E.eval_pair_packed_dev(xd.data_ptr(), gd.data_ptr(), pd.data_ptr(), B, st))
+    t_dev1 = time.perf_counter()
+    launches = (E.launches - launches0) * args.steps // (args.steps + W)
+    clocks = sampler.summary(t_dev0, t_dev1)
+
+    # ---- each kernel alone (CUDA events around the single launch, L2 flushed): the roofline's kernel is the heavy one ----
+    vd = torch.empty((B, P.n_vals), dtype=torch.float64, device="cuda")
+    E.fill_template(vd.data_ptr(), B, st)
+    gsep = torch.full((B, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
+    heavy_ms = timed_events(lambda: E.launch_kernel_dev(2, xd.data_ptr(), pd.data_ptr(), B, True, st)) / args.steps \
+        if E.n_jac_heavy else 0.0
+    light_ms = timed_events(lambda: E.launch_kernel_dev(3, xd.data_ptr(), pd.data_ptr(), B, True, st)) / args.steps \
+        if E.n_jac_light else 0.0
+    res_ms = timed_events(lambda: E.launch_kernel_dev(0, xd.data_ptr(), gsep.data_ptr(), B, False, st)) / args.steps
+    # the two callbacks as separate device calls with the reference's COO layout (what a per-callback driver gets)
+    sep_ms = timed_events(lambda: (E.eval_residuals_dev(xd.data_ptr(), gsep.data_ptr(), B, st),
+                                   E.eval_jacobian_dev(xd.data_ptr(), vd.data_ptr(), B, st)))
+    # the pair evaluation must reproduce them bit for bit
+    full, src, sgn = E.packed_map()
+    assert torch.equal(gsep, gd), "pair and separate evaluations disagree (residual rows)"
+    v_host = vd.cpu().numpy()
+    pk_host = pd.cpu().numpy()
+    assert np.array_equal(v_host[:, full], sgn * pk_host[:, src]), "packed and COO Jacobian values disagree"
+
+    # ---- sustained: back-to-back pair evaluations for >= N seconds, no flush, one event pair around all of them ----
+    n_sus = max(args.steps, int(args.sustained_seconds / max(dev_ms / args.steps * 1e-3, 1e-6)))
     barrier()
-    dev_ms = sum(e[0].elapsed_time(e[1]) for e in evp)
-    launches = E.launches - launches0
-    assert torch.equal(g_serial, gd) and torch.equal(v_serial, vd), "pair and separate evaluations disagree"
+    t_s0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_sus):
+        E.eval_pair_packed_dev(xd.data_ptr(), gd.data_ptr(), pd.data_ptr(), B, st)
+    e1.record()
+    barrier()
+    t_s1 = time.perf_counter()
+    sus_ms = e0.elapsed_time(e1)
+    sus_clocks = sampler.summary(t_s0 + 0.2, t_s1)
 
-    # ---- end to end through the host-buffer C ABI (what objfunc / sens call) ----
-    px, pg, pv = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * P.n_vals)
+    # ---- end to end through the host-buffer C ABI (what a batched driver calls) ----
+    px, pg, pp = engine.PinnedArray(X.size), engine.PinnedArray(B * P.n_rows), engine.PinnedArray(B * n_pack)
     px.array[:] = X.ravel()
+    pg.array[:] = np.nan
+    pp.array[:] = np.nan
 
-    def step_e2e_full():
-        E.eval_residuals(px.array, B, out=pg.array)
-        E.eval_jacobian(px.array, B, out=pv.array)
-
-    def step_e2e_separate():
-        # update mode: the batch's host Jacobian buffer lives across calls (as in a batched solve), so
-        # only the x-dependent slots cross PCIe; the buffer ends up identical to the full copy
-        E.eval_residuals(px.array, B, out=pg.array)
-        E.eval_jacobian_update(px.array, pv.array, B)
-
-    def step_e2e():
-        # the same as one pair call: x uploaded once, the residual kernel and its copy overlap the Jacobian's
-        E.eval_pair_update(px.array, pg.array, pv.array, B)
-
-    def timed(step):
-        for _ in range(max(args.warmup, 3)):
+    def timed_wall(step):
+        for _ in range(W):
             step()
         barrier()
         t0 = time.perf_counter()
@@ -356,84 +442,120 @@ def run_gelato(args):
         barrier()
         return time.perf_counter() - t0
 
-    e2e_full_s = timed(step_e2e_full)
-    assert np.array_equal(pv.array.reshape(B, -1), vd.cpu().numpy()), "host and device paths disagree"
-    pv.array[:] = np.nan
-    E.jacobian_template(pv.array, B)
-    e2e_sep_s = timed(step_e2e_separate)
-    pg.array[:] = np.nan
-    e2e_s = timed(step_e2e)
-    clocks = sampler.stop()
+    e2e_s = timed_wall(lambda: E.eval_pair_packed(px.array, B, g_out=pg.array, packed_out=pp.array))
     assert np.array_equal(pg.array.reshape(B, -1), gd.cpu().numpy()), "host and device paths disagree"
-    assert np.array_equal(pv.array.reshape(B, -1), vd.cpu().numpy()), "host and device paths disagree"
+    assert np.array_equal(pp.array.reshape(B, -1), pk_host), "host and device paths disagree"
+    # the reference's layout through the same boundary: COO values in a page-locked buffer kept across calls
+    # (update mode: x-dependent slots scattered into place) and the plain full copy
+    pv = engine.PinnedArray(B * P.n_vals)
+    E.jacobian_template(pv.array, B)
+    e2e_upd_s = timed_wall(lambda: E.eval_pair_update(px.array, pg.array, pv.array, B))
+    assert np.array_equal(pv.array.reshape(B, -1), v_host), "host and device paths disagree"
+    e2e_full_s = timed_wall(lambda: (E.eval_residuals(px.array, B, out=pg.array), E.eval_jacobian(px.array, B, out=pv.array)))
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, jac_ms, res_ms, e2e_full_s * 1e3, serial_ms, e2e_sep_s * 1e3], dtype=torch.float64,
-                     device="cuda")
+    # ---- FP64 issue peaks, with the clocks they were measured at ----
+    t_p0 = time.perf_counter()
+    peaks = [engine.fp64_peak(local) for _ in range(6)]
+    t_p1 = time.perf_counter()
+    fma_tf, nofma_tf = max(p[0] for p in peaks), max(p[1] for p in peaks)
+    peak_clocks = sampler.summary(t_p0, t_p1)
+    sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, heavy_ms, light_ms, res_ms, e2e_full_s * 1e3, sep_ms, e2e_upd_s * 1e3, sus_ms / n_sus],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, jac_ms, res_ms, e2e_full_ms, serial_ms, e2e_sep_ms = [float(v) for v in t.cpu()]
+    dev_ms, e2e_ms, heavy_ms, light_ms, res_ms, e2e_full_ms, sep_ms, e2e_upd_ms, sus_step_ms = [float(v) for v in t.cpu()]
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        n_xdep = int(P.n_xdep)
-        jac_bytes = B * (P.n_vars + n_xdep) * 8.0
-        n_hold = P.N - ec["free_nodes"]
-        del n_hold
-        flops_jac = B * (FLOPS["air"] * 14 * ec["air_fd_nodes"] + FLOPS["noair"] * 9 * (P.N - ec["air_fd_nodes"])
-                         + FLOPS["quat"] * 7 * ec["free_nodes"] + FLOPS["aero"] * ec["aero_jac_evals"]
-                         + FLOPS["evt"] * ec["evt_jac_evals"])
-        traffic, traffic_src = ncu_traffic("k_jacobian", E.n_jac_blocks * B)
-        try:
-            fma_tf, nofma_tf = engine.fp64_peak(local)
-        except Exception:
-            fma_tf = nofma_tf = None
+        peak_hbm, peak_src = measured_peaks()
+        K = args.steps
+        rate = lambda ms_total: evals_step_rank * world * K / (ms_total * 1e-3)  # noqa: E731
+        # the heavy kernel: air dynamics blocks (14 columns + the quaternion variants of their nodes) and aero rows
+        flops_heavy = B * (FLOPS["air"] * 14 * ec["air_fd_nodes"] + FLOPS["quat"] * 7 * ec["air_free_nodes"]
+                           + FLOPS["aero"] * ec["aero_jac_evals"])
+        n_pack_heavy = None
+        bytes_heavy = B * (P.n_vars + n_pack) * 8.0  # reads x once, writes (at most) every packed value once
+        traffic, traffic_src = ncu_traffic("k_jacobian", E.n_jac_heavy * B)
+        ach_tf = flops_heavy / (heavy_ms * 1e-3) / 1e12 if heavy_ms else None
         line = {
-            "metric": METRIC, "value": evals_step_rank * world * args.steps / (dev_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "metric": METRIC, "value": rate(dev_ms), "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "example_x%d_N%d_split20" % (args.factor, P.N), "scenarios_per_gpu": B,
-                       "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows, "n_vals": int(P.n_vals),
-                       "evals_per_scenario_step": ec["objfunc"] + ec["sens"], "parallelism": "scenarios x%d" % world,
-                       "step": "objfunc + sens of one batch as one pair evaluation (gelato_eval_pair_dev: residual "
-                               "kernel on a side stream next to the Jacobian kernel)",
-                       "l2": "flushed between timed steps (256 MiB write); per-step CUDA events on the launch stream"},
+            "config": config_of(args, P, world),
+            "pairs_per_s": B * world * K / (dev_ms * 1e-3),
             "clocks": clocks,
-            "e2e": {"value": evals_step_rank * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(X.size * 8),
-                    "d2h_bytes_per_step": int(B * (P.n_rows + n_xdep) * 8),
-                    "mode": "page-locked host Jacobian buffer kept across calls; only the %d x-dependent of %d slots per "
-                            "scenario cross PCIe (long runs by strided copies into place, scattered slots %s); pipelined "
-                            "over slices of 16 scenarios"
-                            % (n_xdep, int(P.n_vals), "written by the device into the mapped buffer (zero-copy)" if zero_copy
-                               else "packed and scattered by %d pooled host threads" % host_threads),
-                    "separate_calls": {"value": evals_step_rank * world * args.steps / (e2e_sep_ms * 1e-3),
-                                       "ms_per_step": e2e_sep_ms / args.steps},
-                    "full_copy": {"value": evals_step_rank * world * args.steps / (e2e_full_ms * 1e-3),
-                                  "ms_per_step": e2e_full_ms / args.steps,
-                                  "d2h_bytes_per_step": int(B * (P.n_rows + P.n_vals) * 8)}},
+            "e2e": {"value": rate(e2e_ms), "unit": UNIT, "ms_per_step": e2e_ms / K, "pairs_per_s": B * world * K / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": int(X.size * 8), "d2h_bytes_per_step": int(B * (P.n_rows + n_pack) * 8),
+                    "mode": "gelato_eval_pair_packed: page-locked host buffers; x up, one pair evaluation per slice of 16 "
+                            "scenarios, g and the %d independent x-dependent Jacobian values per scenario (of %d x-dependent, "
+                            "%d total COO slots) down as contiguous copies" % (n_pack, int(P.n_xdep), int(P.n_vals)),
+                    "coo_update_mode": {"value": rate(e2e_upd_ms), "ms_per_step": e2e_upd_ms / K,
+                                        "d2h_bytes_per_step": int(B * (P.n_rows + P.n_xdep) * 8),
+                                        "note": "the reference's COO layout in a host buffer kept across calls; x-dependent "
+                                                "slots scattered into place (gelato_eval_pair_update)"},
+                    "coo_full_copy": {"value": rate(e2e_full_ms), "ms_per_step": e2e_full_ms / K,
+                                      "d2h_bytes_per_step": int(B * (P.n_rows + P.n_vals) * 8)}},
             "gpu_launches": int(launches),
-            "kernels": {"k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms,
-                        "note": "each kernel timed alone, back to back on one stream",
-                        "separate_calls_ms_per_step": serial_ms / args.steps,
-                        "separate_calls_value": evals_step_rank * world * args.steps / (serial_ms * 1e-3)},
-            "roofline": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": jac_bytes,
-                         "note": "the kernel is FP64-ALU bound, not HBM bound (DESIGN.md section 5): `fp64` is the "
-                                 "binding roofline, against the measured DMUL+DADD issue peak (fused multiply-add is "
-                                 "off by the bit-parity contract)",
-                         "fp64": {"achieved_tflops": flops_jac / (jac_ms * 1e-3) / 1e12,
-                                  "peak_tflops_dfma": fma_tf, "peak_tflops_dmul_dadd": nofma_tf,
-                                  "frac_of_unfused_peak": (flops_jac / (jac_ms * 1e-3) / 1e12 / nofma_tf) if nofma_tf else None,
-                                  "algorithmic_flops_per_launch": flops_jac}},
+            "sustained": {"value": evals_step_rank * world / (sus_step_ms * 1e-3), "ms_per_step": sus_step_ms, "steps": n_sus,
+                          "seconds": sus_ms * 1e-3, "clocks": sus_clocks,
+                          "note": "back-to-back pair evaluations, no L2 flush, one CUDA-event pair around all of them"},
+            "kernels": {"k_jacobian_ms": heavy_ms, "k_jacobian_light_ms": light_ms, "k_residuals_ms": res_ms,
+                        "note": "each kernel alone (the residual kernel with its dynamics blocks, which a pair evaluation "
+                                "does not launch), CUDA events around the single launch, L2 flushed between launches",
+                        "separate_calls_coo_ms_per_step": sep_ms / K, "separate_calls_coo_value": rate(sep_ms)},
+            "roofline": {"kernel": "k_jacobian (heavy roles: air dynamics nodes + aero rows)", "bound": "fp64",
+                         "achieved": ach_tf, "peak": nofma_tf, "unit": "TFLOP/s",
+                         "frac": (ach_tf / nofma_tf) if (ach_tf and nofma_tf) else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_flops_per_launch": flops_heavy,
+                         "peak_source": "gelato_fp64_peak on this device in this run: unfused DMUL+DADD issue rate (fused "
+                                        "multiply-add is off by the bit-parity contract); best of 6",
+                         "peak_measurement": {"dmul_dadd_tflops": nofma_tf, "dfma_tflops": fma_tf, "clocks": peak_clocks},
+                         "frac_of_dfma_peak": (ach_tf / fma_tf) if (ach_tf and fma_tf) else None,
+                         "hbm": {"bound": "hbm", "achieved": bytes_heavy / (heavy_ms * 1e-3) / 1e9 if heavy_ms else None,
+                                 "peak": peak_hbm, "unit": "GB/s",
+                                 "frac": bytes_heavy / (heavy_ms * 1e-3) / 1e9 / peak_hbm if heavy_ms else None,
+                                 "algorithmic_bytes_per_launch": bytes_heavy, "peak_source": peak_src,
+                                 "note": "upper bound of the kernel's own bytes (x read once, every packed value written "
+                                         "once); the path is FP64-issue bound, ~30 flop per byte"}},
         }
+        del n_pack_heavy
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.factor, ec["objfunc"] + ec["sens"], args.cpu_seconds)
+            line["cpu_baseline"] = cpu_baseline(args, ec["objfunc"] + ec["sens"], P.N)
+        if args.solve_scenarios > 0:
+            line["solves"] = None  # filled below by every rank's solve leg
+    sol = None
+    if args.solve_scenarios > 0:
+        sol = run_solves(args, world, rank, local)
+        if rank == 0:
+            line["solves"] = sol
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_solves(args, world, rank, local):
+    """Batched NLP solves per hour: `--solve-scenarios` dispersed scenarios of the shipped example per GPU, each solved
+    to convergence by the host-side interior-point solver (gelato_b200/ipsolve.py -- NOT IPOPT) on callbacks that the
+    per-GPU coalescing server turns into batched launches."""
+    import torch
+    import torch.distributed as dist
+
+    from gelato_b200 import solve_batch
+
+    res = solve_batch.solve_dispersed(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local)
+    t = torch.tensor([res["wall_s"]], dtype=torch.float64, device="cuda")
+    n_ok = torch.tensor([res["converged"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_ok, op=dist.ReduceOp.SUM)
+    wall = float(t.item())
+    res.update({"scenarios_total": args.solve_scenarios * world, "converged_total": int(n_ok.item()), "wall_s_max_over_ranks": wall,
+                "solves_per_hour": args.solve_scenarios * world / wall * 3600.0})
+    return res
 
 
 def main():

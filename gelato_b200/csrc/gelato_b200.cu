@@ -26,12 +26,20 @@
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-#ifndef GJ_MIN_BLOCKS
-#define GJ_MIN_BLOCKS 4 /* 64 registers: 32 warps per SM; measured best of 2..5 (profiles/r01d_ab.txt) */
+// One Jacobian evaluation = two kernels on two streams: the HEAVY roles (air dynamics nodes, aero rows -- the
+// pos_part / rotq_part code, ~1 kFLOP per column) and the LIGHT ones (vacuum dynamics, fallback, event rows).
+// Each instantiation contains only its own roles' code (instruction-cache footprint: ncu round 1 measured
+// 12 % i-cache misses with everything in one kernel) and its own register budget.
+#ifndef GJ_MIN_BLOCKS_HEAVY
+#define GJ_MIN_BLOCKS_HEAVY 3 /* 288 threads x 3 blocks: 27 warps per SM, up to 72 registers */
 #endif
-__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
-           const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ vals_all) {
+#ifndef GJ_MIN_BLOCKS_LIGHT
+#define GJ_MIN_BLOCKS_LIGHT 3
+#endif
+template <int ROLES>
+__device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* __restrict__ block_table, const int n_scen,
+                                              const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all,
+                                              double* __restrict__ out_all, double* __restrict__ g_all) {
   __shared__ JacStore store;
   const JacScratch sm = jac_scratch(store);
   // role-major launch order: block b of every scenario before block b+1 of any, so the blocks
@@ -39,17 +47,31 @@ k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int 
   const int scen = blockIdx.x % n_scen;
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
-  double* vals = vals_all + (size_t)scen * P.n_vals;
+  // COO output: vals[n_scen][n_vals] (constants pre-filled); packed output: [n_scen][n_pack]
+  double* out = out_all + (size_t)scen * (size_t)(P.packed ? P.n_pack : P.n_vals);
+  // pair evaluation: the dynamics blocks also write their nodes' collocation defects (objfunc's rows)
+  double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
   // which scenario's parameter blocks this batch slot uses (a coalesced subset of the configured scenarios)
   const int sid = scen_ids ? scen_ids[scen] : scen;
   const bool two_phase = jac_role_two_phase(bt[BT_ROLE]);
-  jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 0, sm);
+  jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 0, sm);
   __syncthreads();
   if (!two_phase) {
-    jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 2, sm);
+    jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 2, sm);
     __syncthreads();
   }
-  jac_block_phase(P, sid, bt, x, vals, threadIdx.x, 3, sm);
+  jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 3, sm);
+}
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS_HEAVY)
+k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen, const int32_t* __restrict__ scen_ids,
+           const double* __restrict__ x_all, double* __restrict__ out_all, double* __restrict__ g_all) {
+  jacobian_body<JR_HEAVY>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
+}
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS_LIGHT)
+k_jacobian_light(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+                 const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
+                 double* __restrict__ g_all) {
+  jacobian_body<JR_LIGHT>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
 }
 
 #ifndef GR_MIN_BLOCKS
@@ -145,10 +167,21 @@ struct GelatoPlan {
   int device = 0;
   PlanView view{};  // device pointers
   std::vector<void*> owned;
-  int32_t* jac_blocks = nullptr;
-  int n_jac_blocks = 0;
-  int32_t* res_blocks = nullptr;
-  int n_res_blocks = 0;
+  int32_t* jac_blocks = nullptr;  // heavy roles' blocks, then the light roles'
+  int n_jac_blocks = 0, n_jac_heavy = 0;
+  int32_t* res_blocks = nullptr;  // dynamics blocks, then aero / event / linear rows
+  int n_res_blocks = 0, n_res_dyn = 0;
+  // packed output (plan_host.h: build_packed_layout)
+  long long n_pack = 0;
+  std::vector<int64_t> pk_full, pk_src;
+  std::vector<double> pk_sgn;
+  std::vector<void*> scen_owned;  // uploads of gelato_plan_set_scenarios (replaced by the next call)
+  double *d_packed = nullptr, *h_packed = nullptr;  // staging of the packed host entry points
+  size_t cap_packed = 0;
+  double *d_px = nullptr, *d_pg = nullptr, *h_px = nullptr;
+  int32_t* d_pids = nullptr;
+  bool pids_iota = false;
+  size_t cap_px = 0;
   double* vals_template = nullptr;       // [n_vals] (or [n_scen][n_vals])
   long long vals_template_sstride = 0;
   int n_scen_cfg = 1;
@@ -184,6 +217,7 @@ struct GelatoPlan {
   struct Lane {
     cudaStream_t stream = nullptr, copy_stream = nullptr, pair_stream = nullptr;
     cudaEvent_t ev_kernel = nullptr, ev_copy = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_h2d = nullptr;
+    cudaEvent_t ev_g = nullptr, ev_gdone = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
   };
   std::vector<Lane> lanes;
@@ -205,13 +239,40 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
   return GELATO_OK;
 }
 
-// one Jacobian evaluation on `st`.  (A two-launch variant -- phase 0 barrier-free with pp | rq | q staged
-// through L2 -- was measured 38 % slower than this fused kernel: profiles/r01i_split_ab.txt.)
-static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* vals_dev, int n_scen, cudaStream_t st,
-                           const int32_t* ids_dev = nullptr) {
-  k_jacobian<<<(unsigned)p->n_jac_blocks * n_scen, GJ_THREADS, 0, st>>>(p->view, p->jac_blocks, n_scen, ids_dev, x_dev,
-                                                                        vals_dev);
-  p->launches++;
+// One Jacobian evaluation: the heavy kernel on `st`, the light kernel (and, for a pair evaluation, the residual
+// kernel's aero / event / linear-row blocks) on `aux`, forked from and joined back into `st` with the two events.
+// g_dev != NULL: pair evaluation (the dynamics blocks write the collocation defects too).  packed: output layout.
+// (A two-launch variant of round 1 -- phase 0 barrier-free with pp | rq | q staged through L2 -- was 38 % slower
+// than the fused phases: profiles/r01i_split_ab.txt.)
+static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* out_dev, double* g_dev, int n_scen, cudaStream_t st,
+                           cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, const int32_t* ids_dev, bool packed) {
+  PlanView v = p->view;
+  v.packed = packed ? 1 : 0;
+  const int n_light = p->n_jac_blocks - p->n_jac_heavy, n_rest = p->n_res_blocks - p->n_res_dyn;
+  const bool side = n_light > 0 || (g_dev && n_rest > 0);
+  if (side) {
+    CU(cudaEventRecord(ev_fork, st));
+    CU(cudaStreamWaitEvent(aux, ev_fork, 0));
+  }
+  if (p->n_jac_heavy > 0) {
+    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, ids_dev, x_dev, out_dev, g_dev);
+    p->launches++;
+  }
+  if (n_light > 0) {
+    k_jacobian_light<<<(unsigned)n_light * n_scen, GJ_THREADS, 0, aux>>>(v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS,
+                                                                         n_scen, ids_dev, x_dev, out_dev, g_dev);
+    p->launches++;
+  }
+  if (g_dev && n_rest > 0) {
+    k_residuals<<<(unsigned)n_rest * n_scen, GR_THREADS, 0, aux>>>(v, p->res_blocks + (size_t)p->n_res_dyn * BT_COLS, n_scen,
+                                                                  ids_dev, x_dev, g_dev);
+    p->launches++;
+  }
+  CU(cudaGetLastError());
+  if (side) {
+    CU(cudaEventRecord(ev_join, aux));
+    CU(cudaStreamWaitEvent(st, ev_join, 0));
+  }
   return GELATO_OK;
 }
 
@@ -293,6 +354,25 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   build_host_tables(d, ht);
   p->n_jac_blocks = (int)(ht.jac_blocks.size() / BT_COLS);
   p->n_res_blocks = (int)(ht.res_blocks.size() / BT_COLS);
+  p->n_jac_heavy = ht.n_jac_heavy;
+  p->n_res_dyn = ht.n_res_dyn;
+  {
+    PackedLayout L;
+    build_packed_layout(d, L);
+    if (d->xdep_idx && d->n_xdep > 0 &&
+        ((size_t)d->n_xdep != L.full_slot.size() || !std::equal(L.full_slot.begin(), L.full_slot.end(), d->xdep_idx))) {
+      gelato_plan_destroy(p);
+      return fail(GELATO_ERR_ARG, "xdep_idx is not the set of slots the Jacobian kernel writes for this plan");
+    }
+    p->n_pack = L.n_pack;
+    v.n_pack = L.n_pack;
+    if ((rc = upload(p, L.sec_pk.data(), L.sec_pk.size(), &v.sec_pk)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+    if ((rc = upload(p, L.aero_pk.data(), L.aero_pk.size(), &v.aero_pk)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+    if ((rc = upload(p, L.evt_pk.data(), L.evt_pk.size(), &v.evt_pk)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+    p->pk_full.swap(L.full_slot);
+    p->pk_src.swap(L.src);
+    p->pk_sgn.swap(L.sgn);
+  }
   const int32_t* tb = nullptr;
   if ((rc = upload(p, ht.jac_blocks.data(), ht.jac_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->jac_blocks = const_cast<int32_t*>(tb);
@@ -323,33 +403,48 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
 int gelato_plan_set_scenarios(GelatoPlan* p, const GelatoScenarioDesc* sc) {
   if (!p || !sc || sc->n_scen <= 0) return fail(GELATO_ERR_ARG, "bad scenario descriptor");
   CU(cudaSetDevice(p->device));
+  CU(cudaDeviceSynchronize());  // nothing in flight may still read the blocks being replaced
   PlanView& v = p->view;
+  // the blocks of an earlier call are superseded as a whole
+  for (void* d : p->scen_owned) cudaFree(d);
+  p->scen_owned.clear();
+  auto up = [&](const double* src, size_t count, const double** dst) -> int {
+    void* d = nullptr;
+    CU(cudaMalloc(&d, count * sizeof(double)));
+    p->scen_owned.push_back(d);
+    CU(cudaMemcpy(d, src, count * sizeof(double), cudaMemcpyHostToDevice));
+    *dst = static_cast<const double*>(d);
+    return GELATO_OK;
+  };
   int rc;
   const double* dptr;
   if (sc->sec_f64) {
-    if ((rc = upload(p, sc->sec_f64, (size_t)sc->n_scen * v.S * GS_F64_COLS, &dptr)) != GELATO_OK) return rc;
+    if ((rc = up(sc->sec_f64, (size_t)sc->n_scen * v.S * GS_F64_COLS, &dptr)) != GELATO_OK) return rc;
     v.sec_f64 = dptr;
     v.sec_f64_sstride = (long long)v.S * GS_F64_COLS;
   }
   if (sc->wind) {
-    if ((rc = upload(p, sc->wind, (size_t)sc->n_scen * v.n_wind * 3, &dptr)) != GELATO_OK) return rc;
+    if ((rc = up(sc->wind, (size_t)sc->n_scen * v.n_wind * 3, &dptr)) != GELATO_OK) return rc;
     v.wind = dptr;
     v.wind_sstride = (long long)v.n_wind * 3;
   }
   if (sc->unit_mass) {
-    if ((rc = upload(p, sc->unit_mass, (size_t)sc->n_scen, &dptr)) != GELATO_OK) return rc;
+    if ((rc = up(sc->unit_mass, (size_t)sc->n_scen, &dptr)) != GELATO_OK) return rc;
     v.unit_mass_scen = dptr;
   }
   if (sc->lin_const) {
-    if ((rc = upload(p, sc->lin_const, (size_t)sc->n_scen * v.n_lin, &dptr)) != GELATO_OK) return rc;
+    if ((rc = up(sc->lin_const, (size_t)sc->n_scen * v.n_lin, &dptr)) != GELATO_OK) return rc;
     v.lin_const_scen = dptr;
   }
   if (sc->vals_template) {
-    if ((rc = upload(p, sc->vals_template, (size_t)sc->n_scen * v.n_vals, &dptr)) != GELATO_OK) return rc;
+    if ((rc = up(sc->vals_template, (size_t)sc->n_scen * v.n_vals, &dptr)) != GELATO_OK) return rc;
     p->vals_template = const_cast<double*>(dptr);
     p->vals_template_sstride = v.n_vals;
   }
   p->n_scen_cfg = sc->n_scen;
+  // the staging Jacobian buffer holds the constants of the PREVIOUS scenarios: have it rebuilt on the next call
+  p->cap_scen = 0;
+  p->cap_ids = 0;
   return GELATO_OK;
 }
 
@@ -357,6 +452,13 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (!p) return GELATO_OK;
   cudaSetDevice(p->device);
   for (void* d : p->owned) cudaFree(d);
+  for (void* d : p->scen_owned) cudaFree(d);
+  if (p->d_packed) cudaFree(p->d_packed);
+  if (p->h_packed) cudaFreeHost(p->h_packed);
+  if (p->d_px) cudaFree(p->d_px);
+  if (p->d_pg) cudaFree(p->d_pg);
+  if (p->d_pids) cudaFree(p->d_pids);
+  if (p->h_px) cudaFreeHost(p->h_px);
   if (p->d_x) cudaFree(p->d_x);
   if (p->d_g) cudaFree(p->d_g);
   if (p->d_vals) cudaFree(p->d_vals);
@@ -376,7 +478,8 @@ int gelato_plan_destroy(GelatoPlan* p) {
       if (st) cudaStreamDestroy(st);
   }
   for (GelatoPlan::Lane& L : p->lanes)
-    if (L.ev_h2d) cudaEventDestroy(L.ev_h2d);
+    for (cudaEvent_t e : {L.ev_h2d, L.ev_g, L.ev_gdone})
+      if (e) cudaEventDestroy(e);
   if (p->d_iota) cudaFree(p->d_iota);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -396,7 +499,16 @@ int32_t gelato_plan_n_rows(const GelatoPlan* p) { return p ? p->view.n_rows : 0;
 int64_t gelato_plan_n_vals(const GelatoPlan* p) { return p ? p->view.n_vals : 0; }
 int64_t gelato_plan_launch_count(const GelatoPlan* p) { return p ? p->launches : 0; }
 int64_t gelato_plan_n_xdep(const GelatoPlan* p) { return p ? p->n_xdep : 0; }
-int32_t gelato_plan_n_blocks(const GelatoPlan* p, int which) { return !p ? 0 : (which ? p->n_jac_blocks : p->n_res_blocks); }
+int32_t gelato_plan_n_blocks(const GelatoPlan* p, int which) {
+  if (!p) return 0;
+  switch (which) {
+    case 0: return p->n_res_blocks;
+    case 1: return p->n_jac_blocks;
+    case 2: return p->n_jac_heavy;
+    case 3: return p->n_jac_blocks - p->n_jac_heavy;
+    default: return p->n_res_blocks - p->n_res_dyn;
+  }
+}
 
 static int check_scen(GelatoPlan* p, int n_scen) {
   if (!p) return fail(GELATO_ERR_ARG, "null plan");
@@ -426,19 +538,19 @@ int gelato_eval_pair_dev(GelatoPlan* p, const double* x_dev, double* g_dev, doub
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  // fork: the residual kernel (one right-hand side per node, latency bound) runs on a side stream next to
-  // the Jacobian kernel and fills the SM time its tail leaves; join: `st` continues when both are done
-  CU(cudaEventRecord(p->ev_fork, st));
-  CU(cudaStreamWaitEvent(p->pair_stream, p->ev_fork, 0));
-  k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->pair_stream>>>(p->view, p->res_blocks, n_scen, nullptr,
-                                                                                  x_dev, g_dev);
-  p->launches++;
-  CU(cudaGetLastError());
-  CU(cudaEventRecord(p->ev_join, p->pair_stream));
-  if ((rc = launch_jacobian(p, x_dev, vals_dev, n_scen, st))) return rc;
-  CU(cudaGetLastError());
-  CU(cudaStreamWaitEvent(st, p->ev_join, 0));
-  return GELATO_OK;
+  // objfunc's rows come out of the Jacobian evaluation: the dynamics blocks hold the right-hand side of the
+  // pristine x as their centre column and add the D.X defects; the few aero / event / linear rows run as the
+  // residual kernel's non-dynamics blocks next to the light Jacobian kernel (no second pass over the physics)
+  return launch_jacobian(p, x_dev, vals_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
+}
+
+int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
+                                void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, true);
 }
 
 int gelato_fill_template(GelatoPlan* p, double* vals_dev, int32_t n_scen, void* stream) {
@@ -463,10 +575,8 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
-  // the kernel rewrites every x-dependent slot and never touches the rest
-  if ((rc = launch_jacobian(p, x_dev, vals_dev, n_scen, st))) return rc;
-  CU(cudaGetLastError());
-  return GELATO_OK;
+  // the kernels rewrite every x-dependent slot and never touch the rest
+  return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
 }
 
 static int ensure_staging(GelatoPlan* p, size_t n_scen) {
@@ -556,7 +666,8 @@ static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, p->d_ids,
                                                                                 p->d_x, p->d_g);
       p->launches++;
-    } else if ((rc = launch_jacobian(p, p->d_x, d_out, n_scen, p->stream, p->d_ids))) {
+    } else if ((rc = launch_jacobian(p, p->d_x, d_out, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join,
+                                     p->d_ids, false))) {
       return rc;
     }
     CU(cudaGetLastError());
@@ -644,7 +755,8 @@ static int ensure_lanes(GelatoPlan* p, int n) {
     for (cudaEvent_t* e : {&L.ev_kernel, &L.ev_copy, &L.ev_fork, &L.ev_join}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
   for (GelatoPlan::Lane& L : p->lanes)
-    if (!L.ev_h2d) CU(cudaEventCreateWithFlags(&L.ev_h2d, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&L.ev_h2d, &L.ev_g, &L.ev_gdone})
+      if (!*e) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   return GELATO_OK;
 }
 
@@ -725,17 +837,16 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
     if (k > 0) CU(cudaStreamWaitEvent(L.stream, p->lanes[k - 1].ev_h2d, 0));  // uploads one after the other
     CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     CU(cudaEventRecord(L.ev_h2d, L.stream));
-    if (g) {  // residuals of the same x on the side stream: kernel and copy overlap the Jacobian's
-      CU(cudaStreamWaitEvent(L.pair_stream, L.ev_h2d, 0));
-      k_residuals<<<(unsigned)p->n_res_blocks * ns, GR_THREADS, 0, L.pair_stream>>>(p->view, p->res_blocks, ns, ids, dx, dg);
-      p->launches++;
-      CU(cudaGetLastError());
+    // g != NULL: pair evaluation, the residual rows come out of the same launches
+    if ((rc = launch_jacobian(p, dx, dvals, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join, ids, false)))
+      return rc;
+    if (g) {  // its copy travels on the side stream, next to the Jacobian's transfers
+      CU(cudaEventRecord(L.ev_g, L.stream));
+      CU(cudaStreamWaitEvent(L.pair_stream, L.ev_g, 0));
       CU(cudaMemcpyAsync(g_dst + (size_t)s0 * v.n_rows, dg, (size_t)ns * v.n_rows * sizeof(double), cudaMemcpyDeviceToHost,
                          L.pair_stream));
-      CU(cudaEventRecord(L.ev_join, L.pair_stream));
+      CU(cudaEventRecord(L.ev_gdone, L.pair_stream));
     }
-    if ((rc = launch_jacobian(p, dx, dvals, ns, L.stream, ids))) return rc;
-    CU(cudaGetLastError());
 
     // the long runs, on the lane's copy stream once `after` has happened
     auto issue_runs = [&](cudaEvent_t after) -> int {
@@ -781,10 +892,123 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
   for (int k = 0; k < n_slices; k++) {
     GelatoPlan::Lane& L = p->lanes[k];
     if (direct) CU(cudaStreamWaitEvent(L.stream, L.ev_copy, 0));
-    if (g) CU(cudaStreamWaitEvent(L.stream, L.ev_join, 0));
+    if (g) CU(cudaStreamWaitEvent(L.stream, L.ev_gdone, 0));
     CU(cudaStreamSynchronize(L.stream));
   }
   if (g && !g_direct) memcpy(g, p->h_out, (size_t)n_scen * v.n_rows * sizeof(double));
+  return GELATO_OK;
+}
+
+// Packed host entry points: x[n_scen][n_vars] up, the pair (or Jacobian-only) evaluation, then g[n_scen][n_rows] and
+// packed[n_scen][n_pack] down as CONTIGUOUS copies -- no gather kernel, no host scatter.  Pipelined over slices of
+// the batch like update mode: slice k's upload and kernels overlap slice k-1's device->host copies (PCIe is full
+// duplex).  Page-locked caller buffers (gelato_host_alloc) are DMA'd directly, others staged.
+static int eval_packed(GelatoPlan* p, const double* x, double* g, double* packed, int32_t n_scen, const int32_t* scen_ids) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!x || !packed) return fail(GELATO_ERR_ARG, "null buffer");
+  const PlanView& v = p->view;
+  if (scen_ids)
+    for (int k = 0; k < n_scen; k++)
+      if (scen_ids[k] < 0 || scen_ids[k] >= p->n_scen_cfg) return fail(GELATO_ERR_ARG, "scenario id outside the configured scenarios");
+  CU(cudaSetDevice(p->device));
+  const size_t np = (size_t)p->n_pack;
+  if ((size_t)n_scen > p->cap_packed) {
+    if (p->d_packed) cudaFree(p->d_packed);
+    if (p->h_packed) cudaFreeHost(p->h_packed);
+    p->d_packed = p->h_packed = nullptr;
+    p->cap_packed = 0;
+    CU(cudaMalloc(&p->d_packed, (size_t)n_scen * np * sizeof(double)));
+    CU(cudaMallocHost(&p->h_packed, (size_t)n_scen * np * sizeof(double)));
+    p->cap_packed = n_scen;
+  }
+  // device x / g / ids: shared with the COO entry points when those were used, else allocated here
+  if ((size_t)n_scen > p->cap_px) {
+    for (void* d : {(void*)p->d_px, (void*)p->d_pg, (void*)p->d_pids}) if (d) cudaFree(d);
+    if (p->h_px) cudaFreeHost(p->h_px);
+    p->d_px = p->d_pg = nullptr; p->d_pids = nullptr; p->h_px = nullptr;
+    p->cap_px = 0;
+    CU(cudaMalloc(&p->d_px, (size_t)n_scen * v.n_vars * sizeof(double)));
+    CU(cudaMalloc(&p->d_pg, (size_t)n_scen * v.n_rows * sizeof(double)));
+    CU(cudaMalloc(&p->d_pids, (size_t)n_scen * sizeof(int32_t)));
+    CU(cudaMallocHost(&p->h_px, (size_t)n_scen * ((size_t)v.n_vars + (size_t)v.n_rows) * sizeof(double)));
+    p->cap_px = n_scen;
+    p->pids_iota = false;
+  }
+  const double* hx = x;
+  if (!is_pinned(x)) {
+    memcpy(p->h_px, x, (size_t)n_scen * v.n_vars * sizeof(double));
+    hx = p->h_px;
+  }
+  double* const h_g_stage = p->h_px + (size_t)n_scen * v.n_vars;
+  const bool g_direct = g && is_pinned(g), pk_direct = is_pinned(packed);
+  double* const g_dst = g_direct ? g : h_g_stage;
+  double* const pk_dst = pk_direct ? packed : p->h_packed;
+
+  int n_slices = p->update_slices > 0 ? p->update_slices : n_scen / 16;
+  n_slices = std::max(1, std::min(n_slices, std::min((int)n_scen, 8)));
+  if ((rc = ensure_lanes(p, n_slices))) return rc;
+  // scenario ids of the batch slots: the caller's subset, or 0, 1, 2 ... when the batch is cut into slices
+  const bool need_ids = scen_ids || n_slices > 1;
+  if (scen_ids) {
+    CU(cudaMemcpyAsync(p->d_pids, scen_ids, (size_t)n_scen * sizeof(int32_t), cudaMemcpyHostToDevice, p->lanes[0].stream));
+    p->pids_iota = false;
+  } else if (need_ids && !p->pids_iota) {
+    std::vector<int32_t> iota(p->cap_px);
+    for (size_t k = 0; k < iota.size(); k++) iota[k] = (int32_t)k;
+    CU(cudaMemcpy(p->d_pids, iota.data(), iota.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    p->pids_iota = true;
+  }
+  auto slice_lo = [&](int k) { return (int)((long long)n_scen * k / n_slices); };
+  for (int k = 0; k < n_slices; k++) {
+    GelatoPlan::Lane& L = p->lanes[k];
+    const int s0 = slice_lo(k), ns = slice_lo(k + 1) - s0;
+    double* const dx = p->d_px + (size_t)s0 * v.n_vars;
+    double* const dg = p->d_pg + (size_t)s0 * v.n_rows;
+    double* const dpk = p->d_packed + (size_t)s0 * np;
+    if (k > 0) CU(cudaStreamWaitEvent(L.stream, p->lanes[k - 1].ev_h2d, 0));  // uploads one after the other (and after the ids)
+    CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+    CU(cudaEventRecord(L.ev_h2d, L.stream));
+    if ((rc = launch_jacobian(p, dx, dpk, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join,
+                              need_ids ? p->d_pids + s0 : nullptr, true)))
+      return rc;
+    // both results on the lane's copy stream, after everything of the slice has been computed
+    CU(cudaEventRecord(L.ev_kernel, L.stream));
+    CU(cudaStreamWaitEvent(L.copy_stream, L.ev_kernel, 0));
+    if (g)
+      CU(cudaMemcpyAsync(g_dst + (size_t)s0 * v.n_rows, dg, (size_t)ns * v.n_rows * sizeof(double), cudaMemcpyDeviceToHost,
+                         L.copy_stream));
+    CU(cudaMemcpyAsync(pk_dst + (size_t)s0 * np, dpk, (size_t)ns * np * sizeof(double), cudaMemcpyDeviceToHost, L.copy_stream));
+    CU(cudaEventRecord(L.ev_copy, L.copy_stream));
+  }
+  for (int k = 0; k < n_slices; k++) CU(cudaEventSynchronize(p->lanes[k].ev_copy));
+  if (g && !g_direct) memcpy(g, h_g_stage, (size_t)n_scen * v.n_rows * sizeof(double));
+  if (!pk_direct) memcpy(packed, p->h_packed, (size_t)n_scen * np * sizeof(double));
+  return GELATO_OK;
+}
+
+int gelato_eval_pair_packed(GelatoPlan* p, const double* x, double* g, double* packed, int32_t n_scen) {
+  if (!g) return fail(GELATO_ERR_ARG, "null buffer");
+  return eval_packed(p, x, g, packed, n_scen, nullptr);
+}
+
+int gelato_eval_jacobian_packed(GelatoPlan* p, const double* x, double* packed, int32_t n_scen) {
+  return eval_packed(p, x, nullptr, packed, n_scen, nullptr);
+}
+
+int gelato_eval_pair_packed_ids(GelatoPlan* p, const double* x, double* g, double* packed, int32_t n_scen,
+                                const int32_t* scen_ids) {
+  if (!g || !scen_ids) return fail(GELATO_ERR_ARG, "null buffer");
+  return eval_packed(p, x, g, packed, n_scen, scen_ids);
+}
+
+int64_t gelato_plan_n_pack(const GelatoPlan* p) { return p ? p->n_pack : 0; }
+
+int gelato_plan_packed_map(const GelatoPlan* p, int64_t* full_slot, int64_t* src, double* sgn) {
+  if (!p || !full_slot || !src || !sgn) return fail(GELATO_ERR_ARG, "null argument");
+  std::copy(p->pk_full.begin(), p->pk_full.end(), full_slot);
+  std::copy(p->pk_src.begin(), p->pk_src.end(), src);
+  std::copy(p->pk_sgn.begin(), p->pk_sgn.end(), sgn);
   return GELATO_OK;
 }
 
@@ -866,6 +1090,33 @@ int gelato_host_free(void* ptr) {
   return GELATO_OK;
 }
 
+// Measurement helper: enqueue exactly ONE kernel on `stream` (0 residual kernel | 2 heavy Jacobian kernel |
+// 3 light Jacobian kernel), COO or packed output, so that a benchmark can bracket it with its own CUDA events.
+int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, double* out_dev, int32_t n_scen, int32_t packed,
+                             void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  PlanView v = p->view;
+  v.packed = packed ? 1 : 0;
+  if (which == 0) {
+    k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(v, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
+  } else if (which == 2) {
+    if (p->n_jac_heavy == 0) return fail(GELATO_ERR_ARG, "the plan has no heavy blocks");
+    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, nullptr, x_dev, out_dev, nullptr);
+  } else if (which == 3) {
+    if (p->n_jac_blocks == p->n_jac_heavy) return fail(GELATO_ERR_ARG, "the plan has no light blocks");
+    k_jacobian_light<<<(unsigned)(p->n_jac_blocks - p->n_jac_heavy) * n_scen, GJ_THREADS, 0, st>>>(
+        v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, nullptr);
+  } else {
+    return fail(GELATO_ERR_ARG, "which must be 0, 2 or 3");
+  }
+  p->launches++;
+  CU(cudaGetLastError());
+  return GELATO_OK;
+}
+
 int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
                        float* avg_ms) {
   int rc = check_scen(p, n_scen);
@@ -877,9 +1128,19 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
   for (int i = 0; i < reps; i++) {
     if (which == 0) {
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
-    } else {
-      if ((rc = launch_jacobian(p, x_dev, out_dev, n_scen, p->stream))) return rc;
+    } else if (which == 1) {  // the whole Jacobian evaluation (heavy and light kernels)
+      if ((rc = launch_jacobian(p, x_dev, out_dev, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join, nullptr,
+                                false)))
+        return rc;
       continue;
+    } else if (which == 2) {  // the heavy kernel alone (air dynamics + aero rows): the roofline's kernel
+      if (p->n_jac_heavy > 0)
+        k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, n_scen, nullptr, x_dev,
+                                                                                  out_dev, nullptr);
+    } else {  // the light kernel alone
+      if (p->n_jac_blocks > p->n_jac_heavy)
+        k_jacobian_light<<<(unsigned)(p->n_jac_blocks - p->n_jac_heavy) * n_scen, GJ_THREADS, 0, p->stream>>>(
+            p->view, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, nullptr);
     }
     p->launches++;
   }

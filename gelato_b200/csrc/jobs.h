@@ -26,40 +26,37 @@
 #include "../../include/gelato_b200.h"
 #include "physics.h"
 
-/* ---- launch geometry (overridable with -D for tuning experiments: tools/ab_bench.sh) ------------- */
+/* ---- launch geometry (overridable with -D for tuning experiments: tools/ab_bench.sh) -------------
+ * One block = 9 warps.  A "heavy" block (air dynamics nodes, aero constraint rows) takes 20 nodes: its 100
+ * position items fill warps 0-3 and its 140 rotation + 20 quaternion items warps 4-8, ONE long item per
+ * thread, so no warp waits at the phase barrier for a neighbour that has a second or third item to go
+ * (round 1 ran 32 nodes on 8 warps: 5 warps one position item each, 3 warps three rounds of rotation items;
+ * A/B in profiles/r02a_ab.txt).  Every item loop below strides by its thread-group size, so any geometry
+ * that satisfies the static_asserts is valid. */
 #ifndef GJ_THREADS
-#define GJ_THREADS 256   /* Jacobian kernel block */
-#define GJ_NODES 18      /* air nodes (or aero rows) per Jacobian block */
-#define GJ_A_THREADS 96  /* threads [0, 96): position items (>= GJ_NODES*NPV, whole warps) */
-#define GJ_B_THREADS 128 /* threads [96, 224): rotation items (>= GJ_NODES*NRV, whole warps) */
-#define GN_NODES 28      /* no-air nodes per Jacobian block */
-#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items (>= GN_NODES*NPV) */
-#define GJ_EVT 16        /* event jobs per Jacobian block (16 lanes each) */
+#define GJ_THREADS 288   /* Jacobian kernel block */
+#define GJ_NODES 20      /* aero rows per Jacobian block */
+#define GD_NODES 20      /* air dynamics nodes per Jacobian block */
+#define GJ_A_THREADS 128 /* threads [0, 128): position items; the rest: rotation and quaternion items */
+#define GN_NODES 32      /* no-air nodes per Jacobian block (9 column items each = 288) */
+#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items, the rest quaternion items */
+#define GJ_EVT 18        /* event jobs per Jacobian block (16 lanes each) */
+#define GG_NODES 18      /* nodes per block of the one-lane-per-column fallback (16 lanes each) */
 #endif
-#ifndef GD_NODES
-#define GD_NODES 32      /* air dynamics nodes per Jacobian block */
-#define GD_A_THREADS 160 /* air dynamics blocks: threads [0, 160) one position item each (>= GD_NODES*NPV, whole
-                            warps); the other 96 loop over the rotation and quaternion items (3 rounds), and all
-                            256 over the column items (2 rounds).  Measured against 18 / 24 / 28 / 30 / 36 nodes per
-                            block: profiles/r01w_ab.txt */
-#endif
-#define GG_NODES 8     /* nodes per block of the one-lane-per-column fallback */
 #define GR_THREADS 128 /* residual kernel block */
 #define GR_NODES 64    /* nodes per residual block */
 #define NPV 5          /* distinct positions over the columns of one node */
 #define NRV 7          /* distinct (position, time) pairs */
+#define NQV 8          /* quaternion-kinematics variants: centre, q x4, u x2 (after the velocity pass), pristine */
 
-static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS >= GJ_NODES * NPV, "position items need whole warps");
-static_assert(GJ_B_THREADS % 32 == 0 && GJ_B_THREADS >= GJ_NODES * NRV, "rotation items need whole warps");
-static_assert(GJ_A_THREADS + GJ_B_THREADS <= GJ_THREADS, "phase-0 thread map");
-static_assert(GD_A_THREADS % 32 == 0 && GD_A_THREADS >= GD_NODES * NPV && GD_A_THREADS < GJ_THREADS, "air dynamics thread map");
-static_assert(GJ_THREADS - GN_NODES * NPV >= GN_NODES && GN_NODES * NPV <= GN_A_THREADS && GN_A_THREADS <= GJ_THREADS, "no-air map");
-static_assert(GJ_NODES * 13 <= GJ_THREADS && GN_NODES * 9 <= GJ_THREADS, "column items in one pass");
-static_assert(GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS && GG_NODES <= GN_NODES, "lane maps");
+static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS < GJ_THREADS && GJ_THREADS % 32 == 0, "phase-0 thread groups are whole warps");
+static_assert(GN_A_THREADS % 32 == 0 && GN_A_THREADS < GJ_THREADS, "no-air thread groups are whole warps");
+static_assert(GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS, "lane maps");
 #define GJ_MAX2(a, b) ((a) > (b) ? (a) : (b))
-#define GJ_FQ_NODES GJ_MAX2(GN_NODES, GD_NODES) /* nodes the f and q arrays hold */
-#define GJ_PR_NODES GJ_MAX2(GJ_NODES, GD_NODES) /* nodes (or aero rows) the pp and rq arrays hold */
+#define GJ_FQ_NODES GJ_MAX2(GJ_MAX2(GN_NODES, GD_NODES), GG_NODES) /* nodes the f and q arrays hold */
+#define GJ_PR_NODES GJ_MAX2(GJ_NODES, GD_NODES)                    /* nodes (or aero rows) the pp and rq arrays hold */
 static_assert(GJ_THREADS * 3 <= GJ_FQ_NODES * 14 * 3, "event jobs keep 3 values per thread in f");
+static_assert(GN_NODES * NPV * 3 <= GJ_PR_NODES * NPV * 8, "no-air gravity items fit the pp array");
 static_assert(GR_THREADS == 2 * GR_NODES, "residual phase 0 uses two threads per node");
 
 /* block roles */
@@ -104,14 +101,21 @@ struct PlanView {
   const struct NodeRec* jac_rec;  /* [N] the same records grouped by Jacobian block role */
   const struct AeroRec* aero_rows; /* [n_aero_rows] one record per aero constraint row */
   int n_aero_rows;
+  /* packed output (plan_host.h: build_packed_layout): the Jacobian kernel writes only the INDEPENDENT
+   * x-dependent values, contiguously per section, instead of the reference's COO slots */
+  int packed;             /* 0: vals[n_vals] in COO order | 1: packed[n_pack] */
+  long long n_pack;
+  const int64_t* sec_pk;  /* [S][GS_I64_COLS] offsets into the packed vector */
+  const int64_t* aero_pk; /* [n_aero][GA_I64_COLS] */
+  const int64_t* evt_pk;  /* [n_evt][GE_I64_COLS] */
 };
 
-/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 38 KB), a plain struct
+/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 32 KB), a plain struct
  * in the host emulator; the jobs reach them through the pointers of JacScratch. */
 #define GJ_PP_LEN (GJ_PR_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
 #define GJ_RQ_LEN (GJ_PR_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
 #define GJ_F_LEN (GJ_FQ_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
-#define GJ_Q_LEN (GJ_FQ_NODES * 7 * 4)          /* quaternion kinematics per (node, variant) */
+#define GJ_Q_LEN (GJ_FQ_NODES * NQV * 4)        /* quaternion kinematics per (node, variant) */
 struct JacStore {
   double pp[GJ_PP_LEN];
   double rq[GJ_RQ_LEN];
@@ -253,15 +257,6 @@ P_HD int lane_pv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : 4); }
 P_HD int lane_rv(int lane) { return lane < 2 ? 0 : (lane <= 4 ? lane - 1 : (lane <= 11 ? 4 : lane - 7)); }
 P_HD int rv_pv(int rv) { return rv < 4 ? rv : 4; }
 
-/* phase 0 also evaluates the quaternion kinematics, one thread per node: the threads the position /
- * rotation items leave over, taken from the END of the block (with the default geometry that is a warp
- * of its own, so the short quaternion items do not lengthen a warp of long ones).  Returns the node a
- * thread takes, or -1 when it has a position / rotation item. */
-P_HD int spare_item(int tid, int n_threads, int n_a_items, int a_threads, int n_b_items) {
-  if (tid >= a_threads) return tid - a_threads >= n_b_items ? n_threads - 1 - tid : -1;
-  return tid >= n_a_items ? (n_threads - a_threads - n_b_items) + (a_threads - 1 - tid) : -1;
-}
-
 /* non-dimensional position variant pv of a base position b[3] */
 P_HD void pos_variant(const double* b, int pv, double dx, double* out) {
   for (int k = 0; k < 3; k++) {
@@ -273,23 +268,27 @@ P_HD void pos_variant(const double* b, int pv, double dx, double* out) {
 }
 
 /* quaternion kinematics (con_dynamics.py:580-613): the state already carries one residue from
- * the velocity pass; variants 0 centre | 1-4 quaternion component | 5-6 control */
+ * the velocity pass; variants 0 centre | 1-4 quaternion component | 5-6 control | 7 the PRISTINE state
+ * (what objfunc evaluates, con_dynamics.py:525-530: the residual rows of a pair evaluation) */
 P_HD void dyn_quat_variants(const PlanView& P, const double* x, const NodeRef& nr, const Units& un, double* out) {
   const double dx = un.dx;
-  double q0[4], u0[2];
-  for (int k = 0; k < 4; k++) q0[k] = residue(x[P.off_quat + 4 * nr.row + k], dx);
+  double qp[4], q0[4], u0[2];
+  for (int k = 0; k < 4; k++) qp[k] = x[P.off_quat + 4 * nr.row + k];
+  for (int k = 0; k < 4; k++) q0[k] = residue(qp[k], dx);
   for (int k = 0; k < 2; k++) u0[k] = x[P.off_u + 2 * (nr.ua + nr.j) + k];
-  for (int var = 0; var < 7; var++) {
+  for (int var = 0; var < NQV; var++) {
     double qv[4] = {q0[0], q0[1], q0[2], q0[3]}, uv[2] = {u0[0], u0[1]};
     if (var >= 1 && var <= 4) {
       const int k = var - 1;
       for (int w = 0; w < k; w++) qv[w] = residue(qv[w], dx);
       qv[k] = qv[k] + dx;
-    } else if (var >= 5) {
+    } else if (var == 5 || var == 6) {
       const int k = var - 5;
       for (int w = 0; w < 4; w++) qv[w] = residue(qv[w], dx);
       for (int w = 0; w < k; w++) uv[w] = residue(uv[w], dx);
       uv[k] = uv[k] + dx;
+    } else if (var == 7) {
+      for (int w = 0; w < 4; w++) qv[w] = qp[w];
     }
     Quat d = rhs_quaternion(q4(qv[0], qv[1], qv[2], qv[3]), uv[0], uv[1], un.u);
     out[4 * var + 0] = d.w;
@@ -299,20 +298,24 @@ P_HD void dyn_quat_variants(const PlanView& P, const double* x, const NodeRef& n
   }
 }
 
-/* finite-difference quotients of one (node, lane) and their COO slots.
+/* finite-difference quotients of one (node, lane) and their output slots.
  * fc / fl: velocity right-hand side at the centre / in this lane; qc / ql: quaternion
- * kinematics at the centre / in variant `lane`. */
+ * kinematics at the centre / in variant `lane`.
+ * COO output (P.packed == 0): the reference's slots.  Packed output: the same values, but only the
+ * independent ones, contiguous per section -- the node-diagonal entries of the dense D (x) I blocks become
+ * dense [9][n] / [4n][4] arrays, the `tf` halves that are exact negations of the `to` halves and the 3n
+ * identical entries of eqcon_dyn_pos / velocity are not written (plan_host.h: build_packed_layout lists which
+ * COO slot is which packed value, with what sign). */
 P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals, const NodeRef& nr, int lane,
                       const double* fc, const double* fl, const double* qc, const double* ql) {
-  const int64_t* sj = P.sec_i64 + nr.sec * GS_I64_COLS;
+  const bool pk = P.packed != 0;
+  const int64_t* sj = (pk ? P.sec_pk : P.sec_i64) + nr.sec * GS_I64_COLS;
   const int n = nr.n, j = nr.j, row = nr.row;
   const Units un = scen_units(P, scen);
   const double dx = un.dx, ut = un.t;
   const bool air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
   const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double dt = tf - to;
-  const double* D = P.d_pool + nr.d_off;
-  const double d_diag = D[(long long)j * (n + 1) + (j + 1)];
   const long long n3 = 3LL * n, n4 = 4LL * n, nn1 = (long long)n * (n + 1);
 
   /* ---- velocity dynamics: -(f_p - f_c)/dx*(tf-to)*unit_t/2 (con_dynamics.py:372) ---- */
@@ -326,9 +329,11 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
       for (int k = 0; k < 3; k++) vals[sj[GS_JV_POS] + kk * n3 + 3LL * j + k] = rh[k];
     } else if (lane <= 7) {
       const int kk = lane - 5; /* submat_vel[3j+ki, 3(j+1)+kk] += rh[ki]  (:415-416) */
+      const double d_diag = P.d_pool[nr.d_off + (long long)j * (n + 1) + (j + 1)];
       for (int ki = 0; ki < 3; ki++) {
         const double base = (ki == kk) ? d_diag : 0.0;
-        vals[sj[GS_JV_VEL] + (ki * 3 + kk) * nn1 + (long long)j * (n + 1) + (j + 1)] = base + rh[ki];
+        const long long at = pk ? (long long)(ki * 3 + kk) * n + j : (ki * 3 + kk) * nn1 + (long long)j * (n + 1) + (j + 1);
+        vals[sj[GS_JV_VEL] + at] = base + rh[ki];
       }
     } else {
       const int kk = lane - 8;
@@ -344,7 +349,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
       for (int k = 0; k < 3; k++) {
         const double rh_to = fc[k] * ut / 2.0;
         vals[sj[GS_JV_T] + 3LL * j + k] = rh_to;
-        vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -rh_to;
+        if (!pk) vals[sj[GS_JV_T] + n3 + 3LL * j + k] = -rh_to;
       }
     }
   }
@@ -356,11 +361,15 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   /* ---- position dynamics (analytic, depends on x through vel and t): :180-195 ---- */
   if (lane == 14) {
     const double rh_vel = gm_div(-un.vel * dt * ut / 2.0, un.pos);
+    if (pk) {
+      if (j == 0) vals[sj[GS_JP_VEL]] = rh_vel; /* one value per section */
+    } else {
+      for (int k = 0; k < 3; k++) vals[sj[GS_JP_VEL] + 3LL * j + k] = rh_vel;
+    }
     for (int k = 0; k < 3; k++) {
-      vals[sj[GS_JP_VEL] + 3LL * j + k] = rh_vel;
       const double rh_to = gm_div(x[P.off_vel + 3 * row + k] * un.vel * ut / 2.0, un.pos);
       vals[sj[GS_JP_T] + 3LL * j + k] = rh_to;
-      vals[sj[GS_JP_T] + n3 + 3LL * j + k] = -rh_to;
+      if (!pk) vals[sj[GS_JP_T] + n3 + 3LL * j + k] = -rh_to;
     }
   }
   /* ---- quaternion kinematics: :580-625 ---- */
@@ -370,9 +379,11 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
       for (int a = 0; a < 4; a++) rh[a] = fd_div(-(ql[a] - qc[a]), dx) * dt * ut / 2.0;
       if (lane <= 4) {
         const int kk = lane - 1; /* submat_quat[4j+a, 4(j+1)+kk] += rh[a] */
+        const double d_diag = P.d_pool[nr.d_off + (long long)j * (n + 1) + (j + 1)];
         for (int a = 0; a < 4; a++) {
           const double base = (a == kk) ? d_diag : 0.0;
-          vals[sj[GS_JQ_QUAT] + (4LL * j + a) * (4LL * (n + 1)) + 4LL * (j + 1) + kk] = base + rh[a];
+          const long long at = pk ? (4LL * j + a) * 4 + kk : (4LL * j + a) * (4LL * (n + 1)) + 4LL * (j + 1) + kk;
+          vals[sj[GS_JQ_QUAT] + at] = base + rh[a];
         }
       } else {
         const int kk = lane - 5;
@@ -382,57 +393,72 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
       for (int a = 0; a < 4; a++) {
         const double rh_to = qc[a] * ut / 2.0;
         vals[sj[GS_JQ_T] + 4LL * j + a] = rh_to;
-        vals[sj[GS_JQ_T] + n4 + 4LL * j + a] = -rh_to;
+        if (!pk) vals[sj[GS_JQ_T] + n4 + 4LL * j + a] = -rh_to;
       }
     }
   }
 }
 
-/* all 16 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*7 + var)*4] */
-P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                            int nthreads, const JacScratch& sm) {
+P_HD void dyn_res_item(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
+                       const double* f3, const double* q4v);
+
+/* all 15 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*NQV + var)*4];
+ * with g != NULL (pair evaluation) also the collocation defects of the same nodes, from the centre column's
+ * right-hand side (pristine x) and the pristine quaternion variant -- objfunc's rows without a second pass
+ * over the physics */
+P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+                            int tid, int nthreads, const JacScratch& sm) {
   /* lane-major items: neighbouring threads run the same column's formula on neighbouring nodes */
   for (int item = tid; item < count * 15; item += nthreads) {
     const int lane = item / count, nl = item - lane * count;
     const NodeRef nr = jac_node(P, start + nl);
     const double* fc = sm.f + (nl * 14) * 3;
-    const double* qc = sm.q + (nl * 7) * 4;
+    const double* qc = sm.q + (nl * NQV) * 4;
     dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
+  }
+  if (g) {
+    /* the threads the last scatter round leaves idle go first */
+    for (int item = nthreads - 1 - tid; item < count * 4; item += nthreads) {
+      const int grp = item / count, nl = item - grp * count;
+      const NodeRef nr = jac_node(P, start + nl);
+      dyn_res_item(P, scen, x, g, nr, grp, sm.f + (nl * 14) * 3, sm.q + (nl * NQV + 7) * 4);
+    }
   }
 }
 
 /* ========================================================================= */
-/* Jacobian kernel, DYN_AIR role: GD_NODES air nodes per block, four phases   */
-/*   0  position items (node, pv) -> pos_part | rotation items (node, rv) ->  */
-/*      rotq_part | the threads left over: one node each, the 7 quaternion-  */
-/*      kinematics variants                                                   */
-/*   2  column items (node, lane 0-13): wind into ECI axes, per-column        */
+/* Jacobian kernel, DYN_AIR role: GD_NODES air nodes per block                 */
+/*   0  threads [0, GJ_A_THREADS): position items (node, pv) -> pos_part;      */
+/*      the others: rotation items (node, rv) -> rotq_part, then one           */
+/*      quaternion item per node (the NQV kinematics variants)                 */
+/*   2  column items (node, lane 0-13): wind into ECI axes, per-column         */
 /*      remainder                                                             */
-/*   3  finite-difference quotients -> COO slots                              */
+/*   3  finite-difference quotients -> output slots (+ defects, pair mode)     */
 /*   (phase 1 is unused: the numbering is shared with the other roles)        */
 /* ========================================================================= */
-P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                        int phase, const JacScratch& sm) {
+P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+                        int tid, int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    if (tid < GD_A_THREADS) { /* the long items, one per thread */
-      if (tid >= count * NPV) return;
-      const int nl = tid / NPV, pv = tid - nl * NPV;
-      const NodeRef nr = jac_node(P, start + nl);
-      double p[3];
-      pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+    if (tid < GJ_A_THREADS) {
       const Tables tb = scen_tables(P, scen);
-      pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
-               sm.pp + (nl * NPV + pv) * PP_COLS);
+      for (int item = tid; item < count * NPV; item += GJ_A_THREADS) {
+        const int nl = item / NPV, pv = item - nl * NPV;
+        const NodeRef nr = jac_node(P, start + nl);
+        double p[3];
+        pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
+                 sm.pp + (nl * NPV + pv) * PP_COLS);
+      }
       return;
     }
-    /* the short items share the other threads: rotation items first, then one quaternion item per node */
-    for (int item = tid - GD_A_THREADS; item < count * (NRV + 1); item += GJ_THREADS - GD_A_THREADS) {
+    /* rotation items first (whole warps of them), then one quaternion item per node */
+    for (int item = tid - GJ_A_THREADS; item < count * (NRV + 1); item += GJ_THREADS - GJ_A_THREADS) {
       if (item >= count * NRV) {
         const int qn = item - count * NRV;
         const NodeRef nr = jac_node(P, start + qn);
-        if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
+        if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * NQV * 4);
         continue;
       }
       const int nl = item / NRV, rv = item - nl * NRV;
@@ -463,7 +489,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       o[2] = f.z;
     }
   } else {
-    dyn_scatter_block(P, scen, x, vals, start, count, tid, GJ_THREADS, sm);
+    dyn_scatter_block(P, scen, x, vals, g, start, count, tid, GJ_THREADS, sm);
   }
 }
 
@@ -471,45 +497,48 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
 /* Jacobian kernel, DYN_NOAIR role: GN_NODES vacuum nodes per block           */
 /*   0  gravity items (node, pv) | quaternion kinematics                      */
 /*   2  column items (node, 9 lanes: centre, mass, position x3, quaternion x4)*/
-/*   3  quotients -> COO slots                                                */
+/*   3  quotients -> output slots (+ defects, pair mode)                      */
 /* ========================================================================= */
-P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                          int phase, const JacScratch& sm) {
+P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+                          int tid, int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   if (phase == 0) {
-    const int qn = spare_item(tid, GJ_THREADS, count * NPV, GN_A_THREADS, 0);
-    if (qn >= 0) {
-      if (qn >= count) return;
-      const NodeRef nr = jac_node(P, start + qn);
-      if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * 7 * 4);
+    if (tid < GN_A_THREADS) {
+      for (int item = tid; item < count * NPV; item += GN_A_THREADS) {
+        const int nl = item / NPV, pv = item - nl * NPV;
+        const NodeRef nr = jac_node(P, start + nl);
+        double p[3];
+        pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+        const Vec3 gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+        double* o = sm.pp + (nl * NPV + pv) * 3;
+        o[0] = gr.x;
+        o[1] = gr.y;
+        o[2] = gr.z;
+      }
     } else {
-      const int nl = tid / NPV, pv = tid - nl * NPV;
-      const NodeRef nr = jac_node(P, start + nl);
-      double p[3];
-      pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
-      const Vec3 g = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
-      double* o = sm.pp + (nl * NPV + pv) * 3;
-      o[0] = g.x;
-      o[1] = g.y;
-      o[2] = g.z;
+      for (int qn = tid - GN_A_THREADS; qn < count; qn += GJ_THREADS - GN_A_THREADS) {
+        const NodeRef nr = jac_node(P, start + qn);
+        if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * NQV * 4);
+      }
     }
   } else if (phase == 2) {
-    if (tid >= count * 9) return;
-    const int nl = tid / 9, c9 = tid - nl * 9;
-    const int lane = c9 < 5 ? c9 : c9 + 3;
-    const NodeRef nr = jac_node(P, start + nl);
-    double v[11];
-    dyn_col_state(P, x, nr.row, lane, false, dx, v);
-    const double* g = sm.pp + (nl * NPV + lane_pv(lane)) * 3;
-    const Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), v3(g[0], g[1], g[2]),
-                                          sec_param(P, scen, nr.sec), un);
-    double* o = sm.f + (nl * 14 + lane) * 3;
-    o[0] = f.x;
-    o[1] = f.y;
-    o[2] = f.z;
+    for (int item = tid; item < count * 9; item += GJ_THREADS) {
+      const int nl = item / 9, c9 = item - nl * 9;
+      const int lane = c9 < 5 ? c9 : c9 + 3;
+      const NodeRef nr = jac_node(P, start + nl);
+      double v[11];
+      dyn_col_state(P, x, nr.row, lane, false, dx, v);
+      const double* gr = sm.pp + (nl * NPV + lane_pv(lane)) * 3;
+      const Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), v3(gr[0], gr[1], gr[2]),
+                                            sec_param(P, scen, nr.sec), un);
+      double* o = sm.f + (nl * 14 + lane) * 3;
+      o[0] = f.x;
+      o[1] = f.y;
+      o[2] = f.z;
+    }
   } else if (phase == 3) {
-    dyn_scatter_block(P, scen, x, vals, start, count, tid, GJ_THREADS, sm);
+    dyn_scatter_block(P, scen, x, vals, g, start, count, tid, GJ_THREADS, sm);
   }
 }
 
@@ -519,8 +548,8 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
 /* (air formula, but no velocity / time finite differences: con_dynamics.py:  */
 /* 257 vs :403,454).                                                          */
 /* ========================================================================= */
-P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
-                        int phase, const JacScratch& sm) {
+P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+                        int tid, int phase, const JacScratch& sm) {
   const int nl = tid >> 4, lane = tid & 15;
   if (nl >= count) return;
   const NodeRef nr = jac_node(P, start + nl);
@@ -550,11 +579,15 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
       o[1] = f.y;
       o[2] = f.z;
     }
-    if (lane == 15 && !hold) dyn_quat_variants(P, x, nr, un, sm.q + nl * 7 * 4);
+    if (lane == 15 && !hold) dyn_quat_variants(P, x, nr, un, sm.q + nl * NQV * 4);
   } else if (phase == 3) {
-    if (lane == 15) return;
     const double* fc = sm.f + (nl * 14) * 3;
-    const double* qc = sm.q + (nl * 7) * 4;
+    const double* qc = sm.q + (nl * NQV) * 4;
+    if (lane == 15) {
+      if (g)
+        for (int grp = 0; grp < 4; grp++) dyn_res_item(P, scen, x, g, nr, grp, fc, qc + 7 * 4);
+      return;
+    }
     dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
   }
 }
@@ -641,56 +674,63 @@ P_HD void dx_dot(const double* Drow, const double* xrows, int n1, double* acc) {
   }
 }
 
-/* phase 2 of the residual kernel: D.X minus right-hand side.  One item per (node, state array), array-major
- * (neighbouring threads run the same array on neighbouring nodes), ordered position | quaternion | velocity |
- * mass so that the two items a thread takes (item, item + nthreads) carry 6 and 5 columns. */
-P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g, int g0, int count, int tid,
-                         int nthreads, const ResScratch& sm) {
+/* one (node, state array) item of the collocation defects: D.X minus right-hand side.  grp 0 position |
+ * 1 quaternion | 2 velocity | 3 mass; f3 / q4v: the node's velocity right-hand side and quaternion kinematics
+ * at the pristine x.  Shared by the residual kernel (phase 2) and the Jacobian kernel's pair mode. */
+P_HD void dyn_res_item(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
+                       const double* f3, const double* q4v) {
   const Units un = scen_units(P, scen);
   const double ut = un.t;
+  const int32_t* si = nr.si;
+  const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
+  const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
+  const double dt = tf - to;
+  const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
+  if (grp == 3) { /* mass: con_dynamics.py:53-61 */
+    double r;
+    if (flags & GSF_ENGINE_ON) {
+      double lh[1];
+      dx_dot<1>(Drow, x + xa, n + 1, lh);
+      const double rh = gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
+      r = lh[0] - rh;
+    } else {
+      r = x[row] - x[xa];
+    }
+    g[si[GS_R_MASS] + j] = r;
+  } else if (grp == 0) { /* position: :146-150 */
+    double lh[3];
+    dx_dot<3>(Drow, x + P.off_pos + 3 * xa, n + 1, lh);
+    for (int k = 0; k < 3; k++) {
+      const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
+      g[si[GS_R_POS] + 3 * j + k] = lh[k] - rh;
+    }
+  } else if (grp == 2) { /* velocity: :256-287 */
+    double lh[3];
+    dx_dot<3>(Drow, x + P.off_vel + 3 * xa, n + 1, lh);
+    for (int k = 0; k < 3; k++) {
+      const double rh = f3[k] * dt * ut / 2.0;
+      g[si[GS_R_VEL] + 3 * j + k] = lh[k] - rh;
+    }
+  } else if (flags & GSF_HOLD) { /* quaternion: :520-531 */
+    for (int k = 0; k < 4; k++) g[si[GS_R_QUAT] + 4 * j + k] = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
+  } else {
+    double lh[4];
+    dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh);
+    for (int k = 0; k < 4; k++) {
+      const double rh = q4v[k] * dt * ut / 2.0;
+      g[si[GS_R_QUAT] + 4 * j + k] = lh[k] - rh;
+    }
+  }
+}
+
+/* phase 2 of the residual kernel.  One item per (node, state array), array-major (neighbouring threads run the
+ * same array on neighbouring nodes), ordered position | quaternion | velocity | mass so that the two items a
+ * thread takes (item, item + nthreads) carry 6 and 5 columns. */
+P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g, int g0, int count, int tid,
+                         int nthreads, const ResScratch& sm) {
   for (int item = tid; item < count * 4; item += nthreads) {
     const int grp = item / count, nl = item - grp * count;
-    const NodeRef nr = res_node(P, g0 + nl);
-    const int32_t* si = nr.si;
-    const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
-    const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
-    const double dt = tf - to;
-    const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
-    if (grp == 3) { /* mass: con_dynamics.py:53-61 */
-      double r;
-      if (flags & GSF_ENGINE_ON) {
-        double lh[1];
-        dx_dot<1>(Drow, x + xa, n + 1, lh);
-        const double rh = gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
-        r = lh[0] - rh;
-      } else {
-        r = x[row] - x[xa];
-      }
-      g[si[GS_R_MASS] + j] = r;
-    } else if (grp == 0) { /* position: :146-150 */
-      double lh[3];
-      dx_dot<3>(Drow, x + P.off_pos + 3 * xa, n + 1, lh);
-      for (int k = 0; k < 3; k++) {
-        const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
-        g[si[GS_R_POS] + 3 * j + k] = lh[k] - rh;
-      }
-    } else if (grp == 2) { /* velocity: :256-287 */
-      double lh[3];
-      dx_dot<3>(Drow, x + P.off_vel + 3 * xa, n + 1, lh);
-      for (int k = 0; k < 3; k++) {
-        const double rh = sm.f[nl][k] * dt * ut / 2.0;
-        g[si[GS_R_VEL] + 3 * j + k] = lh[k] - rh;
-      }
-    } else if (flags & GSF_HOLD) { /* quaternion: :520-531 */
-      for (int k = 0; k < 4; k++) g[si[GS_R_QUAT] + 4 * j + k] = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
-    } else {
-      double lh[4];
-      dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh);
-      for (int k = 0; k < 4; k++) {
-        const double rh = sm.q[nl][k] * dt * ut / 2.0;
-        g[si[GS_R_QUAT] + 4 * j + k] = lh[k] - rh;
-      }
-    }
+    dyn_res_item(P, scen, x, g, res_node(P, g0 + nl), grp, sm.f[nl], sm.q[nl]);
   }
 }
 
@@ -741,55 +781,57 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
   const double dx = P.un.dx;
   if (phase == 0) {
     const bool is_a = tid < GJ_A_THREADS;
-    const int item = is_a ? tid : tid - GJ_A_THREADS;
     const int per = is_a ? NPV : NRV;
-    if (tid >= GJ_A_THREADS + GJ_B_THREADS || item >= count * per) return;
-    const int nl = item / per, var = item - nl * per;
-    const AeroRec ar = P.aero_rows[start + nl];
-    double v[10], to, tf, p[3];
-    aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
-    if (is_a) {
-      pos_variant(v, var, dx, p);
-      const Tables tb = scen_tables(P, scen);
-      pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, 0, sm.pp + (nl * NPV + var) * PP_COLS);
-    } else {
-      pos_variant(v, rv_pv(var), dx, p);
-      if (var == 5) to = to + dx;
-      if (var == 6) tf = tf + dx;
-      const double tn = time_node(P.tau_pool + ar.tau_off, ar.r, to, tf);
-      rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
-    }
-  } else if (phase == 2) {
-    if (tid >= count * 13) return;
-    const int nl = tid / 13, lane = tid - nl * 13;
-    const AeroRec ar = P.aero_rows[start + nl];
-    const int kind = ar.kind, job = ar.job;
-    const bool has_quat = kind != 1;
-    if (!has_quat && lane >= 7 && lane <= 10) return;
-    double v[10], to, tf;
-    aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
-    if (lane != 0) { /* the gradient works on a copy: columns leave residue inside the copy only */
-      const int pidx = (lane <= 10) ? lane - 1 : 10;
-      for (int w = 0; w < 10; w++) {
-        if (!has_quat && w >= 6) continue;
-        if (w < pidx) v[w] = residue(v[w], dx);
-        else if (w == pidx) v[w] = v[w] + dx;
+    const int step = is_a ? GJ_A_THREADS : GJ_THREADS - GJ_A_THREADS;
+    for (int item = is_a ? tid : tid - GJ_A_THREADS; item < count * per; item += step) {
+      const int nl = item / per, var = item - nl * per;
+      const AeroRec ar = P.aero_rows[start + nl];
+      double v[10], to, tf, p[3];
+      aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
+      if (is_a) {
+        pos_variant(v, var, dx, p);
+        const Tables tb = scen_tables(P, scen);
+        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, 0, sm.pp + (nl * NPV + var) * PP_COLS);
+      } else {
+        pos_variant(v, rv_pv(var), dx, p);
+        if (var == 5) to = to + dx;
+        if (var == 6) tf = tf + dx;
+        const double tn = time_node(P.tau_pool + ar.tau_off, ar.r, to, tf);
+        rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
       }
     }
-    double rp[RP_COLS];
-    const double* pp = sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS;
-    rot_wind(sm.rq + (nl * NRV + aero_lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
-    const Vec3 pos = v3(v[0] * un.pos, v[1] * un.pos, v[2] * un.pos);
-    const Vec3 vel = v3(v[3] * un.vel, v[4] * un.vel, v[5] * un.vel);
-    const double val = aero_quantity_col(kind, pos, vel, q4(v[6], v[7], v[8], v[9]),
-                                         pp, rp) /
-                       P.aero_f64[job * GA_F64_COLS + GA_LIMIT];
-    sm.f[(nl * 14 + lane) * 3] = val;
+  } else if (phase == 2) {
+    for (int item = tid; item < count * 13; item += GJ_THREADS) {
+      const int nl = item / 13, lane = item - nl * 13;
+      const AeroRec ar = P.aero_rows[start + nl];
+      const int kind = ar.kind, job = ar.job;
+      const bool has_quat = kind != 1;
+      if (!has_quat && lane >= 7 && lane <= 10) continue;
+      double v[10], to, tf;
+      aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
+      if (lane != 0) { /* the gradient works on a copy: columns leave residue inside the copy only */
+        const int pidx = (lane <= 10) ? lane - 1 : 10;
+        for (int w = 0; w < 10; w++) {
+          if (!has_quat && w >= 6) continue;
+          if (w < pidx) v[w] = residue(v[w], dx);
+          else if (w == pidx) v[w] = v[w] + dx;
+        }
+      }
+      double rp[RP_COLS];
+      const double* pp = sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS;
+      rot_wind(sm.rq + (nl * NRV + aero_lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
+      const Vec3 pos = v3(v[0] * un.pos, v[1] * un.pos, v[2] * un.pos);
+      const Vec3 vel = v3(v[3] * un.vel, v[4] * un.vel, v[5] * un.vel);
+      const double val = aero_quantity_col(kind, pos, vel, q4(v[6], v[7], v[8], v[9]),
+                                           pp, rp) /
+                         P.aero_f64[job * GA_F64_COLS + GA_LIMIT];
+      sm.f[(nl * 14 + lane) * 3] = val;
+    }
   } else {
     for (int item = tid; item < count * 12; item += GJ_THREADS) {
       const int lane = 1 + item / count, nl = item % count;
       const AeroRec ar = P.aero_rows[start + nl];
-      const int64_t* aj = P.aero_i64 + ar.job * GA_I64_COLS;
+      const int64_t* aj = (P.packed ? P.aero_pk : P.aero_i64) + ar.job * GA_I64_COLS;
       const int kind = ar.kind, nk = ar.nk, r = ar.r;
       if (kind == 1 && lane >= 7 && lane <= 10) continue;
       const double gval = -fd_div(sm.f[(nl * 14 + lane) * 3] - sm.f[(nl * 14) * 3], dx); /* -dfdx (con_aero.py:439-461) */
@@ -939,7 +981,7 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
 P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, const JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
-  const int64_t* ej = P.evt_i64 + job * GE_I64_COLS;
+  const int64_t* ej = (P.packed ? P.evt_pk : P.evt_i64) + job * GE_I64_COLS;
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
   const int type = ei[GE_TYPE];
   if (lane == 0 || lane >= evt_n_lanes(type)) return;
@@ -984,22 +1026,25 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 /* ========================================================================= */
 /* Block dispatch.  Jacobian blocks run GJ_PHASES phases with a block barrier  */
 /* between them; residual blocks run three (only the dynamics role uses 0, 2).  */
+/* The Jacobian evaluation is two kernels (gelato_b200.cu): the HEAVY roles     */
+/* (air dynamics, aero rows: pos_part / rotq_part code) and the LIGHT ones      */
+/* (vacuum dynamics, fallback, event rows), each compiled with only its own     */
+/* roles' code: ROLES is the mask of roles an instantiation contains.           */
 /* ========================================================================= */
-P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, int tid,
-                          int phase, const JacScratch& sm) {
-  const int start = bt[BT_START], count = bt[BT_COUNT];
-  switch (bt[BT_ROLE]) {
-    case BR_DYN_AIR: dyn_air_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
-    case BR_DYN_NOAIR: dyn_noair_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
-    case BR_DYN_GEN: dyn_gen_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
-    case BR_AERO: aero_phase(P, scen, x, vals, start, count, tid, phase, sm); break;
-    case BR_EVT:
-      if ((tid >> 4) < count) {
-        if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, sm);
-        else if (phase == 3) evt_jac_phase2(P, vals, start + (tid >> 4), tid, sm);
-      }
-      break;
-    default: break;
+#define JR_HEAVY ((1 << BR_DYN_AIR) | (1 << BR_AERO))
+#define JR_LIGHT ((1 << BR_DYN_NOAIR) | (1 << BR_DYN_GEN) | (1 << BR_EVT))
+#define JR_ALL (JR_HEAVY | JR_LIGHT)
+template <int ROLES>
+P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, double* g,
+                          int tid, int phase, const JacScratch& sm) {
+  const int start = bt[BT_START], count = bt[BT_COUNT], role = bt[BT_ROLE];
+  if ((ROLES >> BR_DYN_AIR & 1) && role == BR_DYN_AIR) dyn_air_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
+  if ((ROLES >> BR_AERO & 1) && role == BR_AERO) aero_phase(P, scen, x, vals, start, count, tid, phase, sm);
+  if ((ROLES >> BR_DYN_NOAIR & 1) && role == BR_DYN_NOAIR) dyn_noair_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
+  if ((ROLES >> BR_DYN_GEN & 1) && role == BR_DYN_GEN) dyn_gen_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
+  if ((ROLES >> BR_EVT & 1) && role == BR_EVT && (tid >> 4) < count) {
+    if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, sm);
+    else if (phase == 3) evt_jac_phase2(P, vals, start + (tid >> 4), tid, sm);
   }
 }
 /* roles whose phase 2 is empty (the kernel skips that barrier); phase 1 is empty for every role */

@@ -67,22 +67,174 @@ static inline const char* validate_desc(const GelatoPlanDesc* d) {
   }
   for (long long k = 0; k < d->n_evt; k++) {
     const int32_t* ei = d->evt_i32 + k * GE_I32_COLS;
-    if (ei[GE_TYPE] < GE_LLH || ei[GE_TYPE] > GE_USER_PERIGEE) return "unknown event job type";
+    if (ei[GE_TYPE] < GE_LLH || ei[GE_TYPE] >= GE_N_TYPES) return "unknown event job type";
     if (ei[GE_SROW] < 0 || ei[GE_SROW] >= M) return "event job state row out of range";
     if (ei[GE_TIDX] < -1 || ei[GE_TIDX] > S) return "event job time index out of range";
     if (ei[GE_ROW] < 1 || ei[GE_ROW] + ei[GE_NROW] > d->n_rows || ei[GE_NROW] < 1 || ei[GE_NROW] > 3)
       return "event job rows out of range";
     if (ei[GE_COMP] < 0 || ei[GE_COMP] > 2) return "event job component out of range";
+    for (int c = 0; c < 7; c++)
+      if (ei[GE_RC0 + c] < 0) return "negative residue count of an event job";
   }
+  /* every Jacobian slot offset the kernel writes through, with the extent of its block, inside [0, n_vals) */
+  const long long nv = d->n_vals;
+#define GELATO_RANGE(off, len) ((off) >= 0 && (long long)(off) + (long long)(len) <= nv)
+  for (long long s = 0; s < S; s++) {
+    const int32_t* si = d->sec_i32 + s * GS_I32_COLS;
+    const int64_t* sj = d->sec_i64 + s * GS_I64_COLS;
+    const long long n = si[GS_N];
+    const int fl = si[GS_FLAGS];
+    if (!GELATO_RANGE(sj[GS_JP_VEL], 3 * n) || !GELATO_RANGE(sj[GS_JP_T], 6 * n) || !GELATO_RANGE(sj[GS_JV_MASS], 3 * n) ||
+        !GELATO_RANGE(sj[GS_JV_POS], 9 * n) || !GELATO_RANGE(sj[GS_JV_QUAT], 12 * n) || !GELATO_RANGE(sj[GS_JV_T], 6 * n))
+      return "a section's Jacobian block offset is outside vals";
+    if ((fl & GSF_AIR_FD) && !GELATO_RANGE(sj[GS_JV_VEL], 9 * n * (n + 1))) return "a section's velocity block is outside vals";
+    if (!(fl & GSF_HOLD) && (!GELATO_RANGE(sj[GS_JQ_QUAT], 16 * n * (n + 1)) || !GELATO_RANGE(sj[GS_JQ_U], 8 * n) ||
+                             !GELATO_RANGE(sj[GS_JQ_T], 8 * n)))
+      return "a section's quaternion block is outside vals";
+  }
+  for (long long k = 0; k < d->n_aero; k++) {
+    const int32_t* ai = d->aero_i32 + k * GA_I32_COLS;
+    const int64_t* aj = d->aero_i64 + k * GA_I64_COLS;
+    const long long nk = ai[GA_NK];
+    if (!GELATO_RANGE(aj[GA_J_POS], 3 * nk) || !GELATO_RANGE(aj[GA_J_VEL], 3 * nk) || !GELATO_RANGE(aj[GA_J_T], 2 * nk) ||
+        (ai[GA_KIND] != 1 && !GELATO_RANGE(aj[GA_J_QUAT], 4 * nk)))
+      return "an aero job's Jacobian block is outside vals";
+  }
+  for (long long k = 0; k < d->n_evt; k++) {
+    const int32_t* ei = d->evt_i32 + k * GE_I32_COLS;
+    const int64_t* ej = d->evt_i64 + k * GE_I64_COLS;
+    const int type = ei[GE_TYPE];
+    bool ok;
+    if (type == GE_TERM) ok = GELATO_RANGE(ej[GE_J_POS], 3 * ei[GE_NROW]) && GELATO_RANGE(ej[GE_J_VEL], 3 * ei[GE_NROW]);
+    else if (type >= GE_USER_PERIGEE) ok = GELATO_RANGE(ej[GE_J_POS], GE_USER_AUX);
+    else ok = GELATO_RANGE(ej[GE_J_POS], 3) && GELATO_RANGE(ej[GE_J_T], 1) && (type != GE_IIP || GELATO_RANGE(ej[GE_J_VEL], 3));
+    if (!ok) return "an event job's Jacobian block is outside vals";
+  }
+#undef GELATO_RANGE
   return nullptr;
 }
 
 struct HostTables {
-  std::vector<int32_t> jac_blocks, res_blocks; /* BT_COLS ints per block */
+  /* BT_COLS ints per block.  jac_blocks = the heavy roles' blocks (air dynamics, aero rows: n_jac_heavy of
+   * them) followed by the light roles' (vacuum dynamics, fallback, event rows); res_blocks = the dynamics
+   * blocks (n_res_dyn) followed by the aero / event / linear-row blocks, which are all a pair evaluation
+   * still needs from the residual kernel */
+  std::vector<int32_t> jac_blocks, res_blocks;
+  int n_jac_heavy = 0, n_res_dyn = 0;
   std::vector<NodeRec> node_rec;               /* [N] natural order */
   std::vector<NodeRec> jac_rec;                /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
   std::vector<AeroRec> aero_rows;              /* one per aero constraint row */
 };
+
+/* Packed output of the Jacobian kernel: the INDEPENDENT x-dependent values of one scenario, contiguous per
+ * section / job, n_pack of them (15 % fewer than the x-dependent COO slots, and no scattered stores):
+ *   per section   eqcon_dyn_pos/velocity 1 (all 3n entries are equal) | eqcon_dyn_pos/t 3n (the tf half is the
+ *                 negated to half) | eqcon_dyn_vel: mass 3n, position 9n, velocity node-diagonal [9][n] (air),
+ *                 quaternion 12n, t 6n (air) or 3n (vacuum: tf = -to) | eqcon_dyn_quat (free attitude):
+ *                 node-diagonal [4n][4], u 8n, t 4n (tf = -to)
+ *   per aero job  position 3nk | velocity 3nk | quaternion 4nk (not for max-q) | t 2nk
+ *   per event job as in COO order
+ * `full_slot` (ascending) lists every x-dependent COO slot, `src` / `sgn` say which packed value it holds and
+ * with what sign:  vals[full_slot[i]] = sgn[i] * packed[src[i]]. */
+struct PackedLayout {
+  std::vector<int64_t> sec_pk, aero_pk, evt_pk;
+  long long n_pack = 0;
+  std::vector<int64_t> full_slot, src;
+  std::vector<double> sgn;
+};
+
+static inline void build_packed_layout(const GelatoPlanDesc* d, PackedLayout& L) {
+  const int S = d->n_sections;
+  L.sec_pk.assign((size_t)S * GS_I64_COLS, -1);
+  L.aero_pk.assign((size_t)d->n_aero * GA_I64_COLS, -1);
+  L.evt_pk.assign((size_t)d->n_evt * GE_I64_COLS, -1);
+  struct Ent { int64_t full, src; double sgn; };
+  std::vector<Ent> ents;
+  long long c = 0;
+  auto direct = [&](int64_t full0, long long len) { /* len COO slots in a row = len packed values */
+    const long long at = c;
+    for (long long i = 0; i < len; i++) ents.push_back({full0 + i, at + i, 1.0});
+    c += len;
+    return at;
+  };
+  auto mirrored = [&](int64_t full0, long long half) { /* [half values][their negations] */
+    const long long at = c;
+    for (long long i = 0; i < half; i++) {
+      ents.push_back({full0 + i, at + i, 1.0});
+      ents.push_back({full0 + half + i, at + i, -1.0});
+    }
+    c += half;
+    return at;
+  };
+  for (int s = 0; s < S; s++) {
+    const int32_t* si = d->sec_i32 + (size_t)s * GS_I32_COLS;
+    const int64_t* sj = d->sec_i64 + (size_t)s * GS_I64_COLS;
+    int64_t* pk = L.sec_pk.data() + (size_t)s * GS_I64_COLS;
+    const long long n = si[GS_N];
+    const int fl = si[GS_FLAGS];
+    pk[GS_JP_VEL] = c;
+    for (long long i = 0; i < 3 * n; i++) ents.push_back({sj[GS_JP_VEL] + i, c, 1.0});
+    c += 1;
+    pk[GS_JP_T] = mirrored(sj[GS_JP_T], 3 * n);
+    pk[GS_JV_MASS] = direct(sj[GS_JV_MASS], 3 * n);
+    pk[GS_JV_POS] = direct(sj[GS_JV_POS], 9 * n);
+    if (fl & GSF_AIR_FD) {
+      pk[GS_JV_VEL] = c;
+      for (long long b = 0; b < 9; b++)
+        for (long long j = 0; j < n; j++)
+          ents.push_back({sj[GS_JV_VEL] + b * n * (n + 1) + j * (n + 1) + (j + 1), c + b * n + j, 1.0});
+      c += 9 * n;
+    }
+    pk[GS_JV_QUAT] = direct(sj[GS_JV_QUAT], 12 * n);
+    pk[GS_JV_T] = (fl & GSF_AIR_FD) ? direct(sj[GS_JV_T], 6 * n) : mirrored(sj[GS_JV_T], 3 * n);
+    if (!(fl & GSF_HOLD)) {
+      pk[GS_JQ_QUAT] = c;
+      for (long long j = 0; j < n; j++)
+        for (long long a = 0; a < 4; a++)
+          for (long long kk = 0; kk < 4; kk++)
+            ents.push_back({sj[GS_JQ_QUAT] + (4 * j + a) * (4 * (n + 1)) + 4 * (j + 1) + kk, c + (4 * j + a) * 4 + kk, 1.0});
+      c += 16 * n;
+      pk[GS_JQ_U] = direct(sj[GS_JQ_U], 8 * n);
+      pk[GS_JQ_T] = mirrored(sj[GS_JQ_T], 4 * n);
+    }
+  }
+  for (int k = 0; k < d->n_aero; k++) {
+    const int32_t* ai = d->aero_i32 + (size_t)k * GA_I32_COLS;
+    const int64_t* aj = d->aero_i64 + (size_t)k * GA_I64_COLS;
+    int64_t* pk = L.aero_pk.data() + (size_t)k * GA_I64_COLS;
+    const long long nk = ai[GA_NK];
+    pk[GA_J_POS] = direct(aj[GA_J_POS], 3 * nk);
+    pk[GA_J_VEL] = direct(aj[GA_J_VEL], 3 * nk);
+    if (ai[GA_KIND] != 1) pk[GA_J_QUAT] = direct(aj[GA_J_QUAT], 4 * nk);
+    pk[GA_J_T] = direct(aj[GA_J_T], 2 * nk);
+  }
+  for (int k = 0; k < d->n_evt; k++) {
+    const int32_t* ei = d->evt_i32 + (size_t)k * GE_I32_COLS;
+    const int64_t* ej = d->evt_i64 + (size_t)k * GE_I64_COLS;
+    int64_t* pk = L.evt_pk.data() + (size_t)k * GE_I64_COLS;
+    const int type = ei[GE_TYPE];
+    if (type == GE_TERM) {
+      pk[GE_J_POS] = direct(ej[GE_J_POS], 3 * ei[GE_NROW]);
+      pk[GE_J_VEL] = direct(ej[GE_J_VEL], 3 * ei[GE_NROW]);
+    } else if (type >= GE_USER_PERIGEE) {
+      pk[GE_J_POS] = direct(ej[GE_J_POS], GE_USER_AUX);
+    } else {
+      pk[GE_J_POS] = direct(ej[GE_J_POS], 3);
+      if (type == GE_IIP) pk[GE_J_VEL] = direct(ej[GE_J_VEL], 3);
+      pk[GE_J_T] = direct(ej[GE_J_T], 1);
+    }
+  }
+  L.n_pack = c;
+  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.full < b.full; });
+  L.full_slot.resize(ents.size());
+  L.src.resize(ents.size());
+  L.sgn.resize(ents.size());
+  for (size_t i = 0; i < ents.size(); i++) {
+    L.full_slot[i] = ents[i].full;
+    L.src[i] = ents[i].src;
+    L.sgn[i] = ents[i].sgn;
+  }
+}
 
 static inline void push_block(std::vector<int32_t>& t, int role, int job, int start, int count) {
   t.push_back(role);
@@ -127,13 +279,15 @@ static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
 
   std::vector<int32_t>& jb = h.jac_blocks;
   push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GD_NODES);
+  push_chunks(jb, BR_AERO, 0, n_aero_rows, GJ_NODES);
+  h.n_jac_heavy = (int)(jb.size() / BT_COLS);
   push_chunks(jb, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
   push_chunks(jb, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
-  push_chunks(jb, BR_AERO, 0, n_aero_rows, GJ_NODES);
   push_chunks(jb, BR_EVT, 0, d->n_evt, GJ_EVT);
 
   std::vector<int32_t>& rb = h.res_blocks;
   push_chunks(rb, BR_DYN, 0, N, GR_NODES);
+  h.n_res_dyn = (int)(rb.size() / BT_COLS);
   push_chunks(rb, BR_AERO, 0, n_aero_rows, GR_THREADS);
   push_chunks(rb, BR_EVT, 0, d->n_evt, GR_THREADS);
   push_chunks(rb, BR_LIN, 0, d->n_lin, GR_THREADS);

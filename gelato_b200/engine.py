@@ -206,6 +206,13 @@ def load_library():
     L.gelato_eval_jacobian_update.argtypes = [vp, _pd, _pd, ctypes.c_int32]
     L.gelato_eval_pair_update.argtypes = [vp, _pd, _pd, _pd, ctypes.c_int32]
     L.gelato_eval_pair_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_eval_pair_packed_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_plan_n_pack.argtypes = [vp]
+    L.gelato_plan_n_pack.restype = ctypes.c_int64
+    L.gelato_plan_packed_map.argtypes = [vp, _pi64, _pi64, _pd]
+    L.gelato_eval_pair_packed.argtypes = [vp, _pd, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_jacobian_packed.argtypes = [vp, _pd, _pd, ctypes.c_int32]
+    L.gelato_eval_pair_packed_ids.argtypes = [vp, _pd, _pd, _pd, ctypes.c_int32, _pi32]
     L.gelato_set_host_threads.argtypes = [vp, ctypes.c_int32]
     L.gelato_set_update_zero_copy.argtypes = [vp, ctypes.c_int32]
     L.gelato_set_update_slices.argtypes = [vp, ctypes.c_int32]
@@ -215,6 +222,7 @@ def load_library():
     L.gelato_host_free.argtypes = [vp]
     L.gelato_time_kernel.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_float)]
+    L.gelato_launch_kernel_dev.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
     L.gelato_selftest_unfused.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.gelato_fp64_peak.argtypes = [ctypes.c_int, _pd, _pd]
     i32 = ctypes.c_int32
@@ -237,6 +245,8 @@ EXPORTS = (
     "gelato_eval_jacobian gelato_eval_residuals_ids gelato_eval_jacobian_ids gelato_eval_residuals_dev gelato_eval_jacobian_dev gelato_time_kernel "
     "gelato_selftest_unfused gelato_fp64_peak gelato_fill_template gelato_host_alloc gelato_host_free "
     "gelato_eval_pair_update gelato_eval_pair_dev gelato_plan_n_blocks gelato_plan_n_xdep gelato_set_update_zero_copy gelato_set_update_slices gelato_probe_update gelato_jacobian_template gelato_eval_jacobian_update gelato_set_host_threads "
+    "gelato_eval_pair_packed_dev gelato_plan_n_pack gelato_plan_packed_map gelato_eval_pair_packed gelato_eval_jacobian_packed "
+    "gelato_eval_pair_packed_ids gelato_launch_kernel_dev "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
     "gelato_leaf_atmosphere gelato_leaf_output_table"
@@ -260,12 +270,15 @@ class Engine:
         _check(L, L.gelato_plan_create(ctypes.byref(desc), device, ctypes.byref(h)), "gelato_plan_create")
         self.h = h
         self.n_scen_cfg = 1
+        self.calls = 0  # evaluation calls made through this handle (a call launches one to three kernels)
         if scenario_plans is not None:
             sc, keep = make_scenario_desc(scenario_plans)
             _check(L, L.gelato_plan_set_scenarios(self.h, ctypes.byref(sc)), "gelato_plan_set_scenarios")
             self.n_scen_cfg = len(scenario_plans)
         self.n_jac_blocks = L.gelato_plan_n_blocks(h, 1)
         self.n_res_blocks = L.gelato_plan_n_blocks(h, 0)
+        self.n_jac_heavy = L.gelato_plan_n_blocks(h, 2)
+        self.n_jac_light = L.gelato_plan_n_blocks(h, 3)
         self.n_vars = L.gelato_plan_n_vars(h)
         self.n_rows = L.gelato_plan_n_rows(h)
         self.n_vals = L.gelato_plan_n_vals(h)
@@ -300,6 +313,7 @@ class Engine:
     def eval_residuals(self, x, n_scen=1, out=None, scen_ids=None):
         """scen_ids: batch slot k uses the parameter blocks of configured scenario scen_ids[k]."""
         x = self._x(x, n_scen)
+        self.calls += 1
         g = _out(out, n_scen * self.n_rows, "out") if out is not None else np.empty(n_scen * self.n_rows)
         if scen_ids is None:
             _check(self.L, self.L.gelato_eval_residuals(self.h, _ptr(x, _pd), _ptr(g, _pd), n_scen), "gelato_eval_residuals")
@@ -312,6 +326,7 @@ class Engine:
 
     def eval_jacobian(self, x, n_scen=1, out=None, scen_ids=None):
         x = self._x(x, n_scen)
+        self.calls += 1
         v = _out(out, n_scen * self.n_vals, "out") if out is not None else np.empty(n_scen * self.n_vals)
         if scen_ids is None:
             _check(self.L, self.L.gelato_eval_jacobian(self.h, _ptr(x, _pd), _ptr(v, _pd), n_scen), "gelato_eval_jacobian")
@@ -348,6 +363,47 @@ class Engine:
                "gelato_eval_pair_update")
         return g_out.reshape(n_scen, self.n_rows), vals_out.reshape(n_scen, self.n_vals)
 
+    # ---- packed mode: the independent x-dependent values only, contiguous; the consumer gathers ----
+    @property
+    def n_pack(self):
+        return int(self.L.gelato_plan_n_pack(self.h))
+
+    def packed_map(self):
+        """(full_slot, src, sgn): vals[full_slot] = sgn * packed[src] for the x-dependent COO slots."""
+        n = int(self.L.gelato_plan_n_xdep(self.h))
+        full, src, sgn = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64), np.empty(n)
+        _check(self.L, self.L.gelato_plan_packed_map(self.h, _ptr(full, _pi64), _ptr(src, _pi64), _ptr(sgn, _pd)),
+               "gelato_plan_packed_map")
+        return full, src, sgn
+
+    def eval_pair_packed(self, x, n_scen=1, g_out=None, packed_out=None, scen_ids=None):
+        """objfunc + sens of the same decision vectors: (g[n_scen][n_rows], packed[n_scen][n_pack])."""
+        x = self._x(x, n_scen)
+        g = _out(g_out, n_scen * self.n_rows, "g_out") if g_out is not None else np.empty(n_scen * self.n_rows)
+        pk = _out(packed_out, n_scen * self.n_pack, "packed_out") if packed_out is not None else np.empty(n_scen * self.n_pack)
+        if scen_ids is None:
+            _check(self.L, self.L.gelato_eval_pair_packed(self.h, _ptr(x, _pd), _ptr(g, _pd), _ptr(pk, _pd), n_scen),
+                   "gelato_eval_pair_packed")
+        else:
+            ids = np.ascontiguousarray(scen_ids, dtype=np.int32)
+            assert ids.size == n_scen
+            _check(self.L, self.L.gelato_eval_pair_packed_ids(self.h, _ptr(x, _pd), _ptr(g, _pd), _ptr(pk, _pd), n_scen,
+                                                              _ptr(ids, _pi32)), "gelato_eval_pair_packed_ids")
+        if n_scen == 1:
+            return g, pk
+        return g.reshape(n_scen, self.n_rows), pk.reshape(n_scen, self.n_pack)
+
+    def eval_jacobian_packed(self, x, n_scen=1, packed_out=None):
+        x = self._x(x, n_scen)
+        pk = _out(packed_out, n_scen * self.n_pack, "packed_out") if packed_out is not None else np.empty(n_scen * self.n_pack)
+        _check(self.L, self.L.gelato_eval_jacobian_packed(self.h, _ptr(x, _pd), _ptr(pk, _pd), n_scen),
+               "gelato_eval_jacobian_packed")
+        return pk if n_scen == 1 else pk.reshape(n_scen, self.n_pack)
+
+    def eval_pair_packed_dev(self, x_ptr, g_ptr, packed_ptr, n_scen=1, stream=None):
+        _check(self.L, self.L.gelato_eval_pair_packed_dev(self.h, x_ptr, g_ptr, packed_ptr, n_scen, stream),
+               "gelato_eval_pair_packed_dev")
+
     def eval_pair_dev(self, x_ptr, g_ptr, vals_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_pair_dev(self.h, x_ptr, g_ptr, vals_ptr, n_scen, stream), "gelato_eval_pair_dev")
 
@@ -380,9 +436,14 @@ class Engine:
     def pack_xdep_dev(self, vals_ptr, packed_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_pack_xdep_dev(self.h, vals_ptr, packed_ptr, n_scen, stream), "gelato_pack_xdep_dev")
 
+    def launch_kernel_dev(self, which, x_ptr, out_ptr, n_scen=1, packed=False, stream=None):
+        """Enqueue ONE kernel (0 residual, 2 heavy Jacobian, 3 light Jacobian) on `stream` (measurement helper)."""
+        _check(self.L, self.L.gelato_launch_kernel_dev(self.h, which, x_ptr, out_ptr, n_scen, 1 if packed else 0, stream),
+               "gelato_launch_kernel_dev")
+
     def time_kernel(self, which, x_ptr, out_ptr, n_scen=1, reps=10):
-        """Average duration [ms] of `reps` back-to-back launches of one kernel
-        (0 residuals, 1 Jacobian), CUDA events on the launch stream."""
+        """Average duration [ms] of `reps` back-to-back launches (0 residual kernel, 1 Jacobian evaluation,
+        2 heavy Jacobian kernel alone, 3 light Jacobian kernel alone), CUDA events on the launch stream."""
         ms = ctypes.c_float(0)
         _check(self.L, self.L.gelato_time_kernel(self.h, which, x_ptr, out_ptr, n_scen, reps, ctypes.byref(ms)),
                "gelato_time_kernel")

@@ -842,13 +842,14 @@ class CompiledPlan:
     def eval_counts(self):
         """Physics-leaf evaluations per objfunc and per sens call, one per
         (node x perturbation column), centre points included."""
-        n_air = n_air_fd = n_free = 0
+        n_air = n_air_fd = n_free = n_air_free = 0
         for i in range(self.S):
             n = self._sec[i][4]
             fl = int(self.sec_i32[i, GS_FLAGS])
             n_air += n if fl & GSF_AIR else 0
             n_air_fd += n if fl & GSF_AIR_FD else 0
             n_free += 0 if fl & GSF_HOLD else n
+            n_air_free += n if (fl & GSF_AIR_FD) and not (fl & GSF_HOLD) else 0
         aero_rows = {0: 0, 1: 0, 2: 0}
         for j in self._aero:
             aero_rows[j["i32"][0]] += j["i32"][2]
@@ -858,7 +859,8 @@ class CompiledPlan:
         obj = self.N + n_free + sum(aero_rows.values()) + len(self._evt)
         sens = 14 * n_air_fd + 9 * (self.N - n_air_fd) + 7 * n_free + aero_jac + evt_jac
         return {"objfunc": obj, "sens": sens, "air_nodes": n_air, "air_fd_nodes": n_air_fd,
-                "noair_nodes": self.N - n_air, "free_nodes": n_free, "aero_rows": sum(aero_rows.values()),
+                "noair_nodes": self.N - n_air, "free_nodes": n_free, "air_free_nodes": n_air_free,
+                "aero_rows": sum(aero_rows.values()),
                 "aero_jac_evals": aero_jac, "evt_jobs": len(self._evt), "evt_jac_evals": evt_jac}
 
     def xdep_index(self):

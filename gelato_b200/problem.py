@@ -362,3 +362,28 @@ def vector_to_xdict(x, M, N, S):
 
 
 VAR_ORDER = ("mass", "position", "velocity", "quaternion", "u", "t")
+
+
+def three_stage_inputs(inp):
+    """BASELINE.json configs[2]: the shipped example with a third stage (coast, burn, coast) appended after
+    SEP2.  `inp` is a `read_inputs` dictionary; modified in place and returned."""
+    s = inp["settings"]
+    s["RocketStage"]["3"] = {"mass_dry": 150.0, "mass_propellant": 600.0, "dropMass": {}, "Isp_vac": 320.0,
+                             "reference_area": 0.0, "ignition_at": "TEIG", "cutoff_at": "TECO",
+                             "separation_at": "SEP3"}
+    ev = inp["events"]
+    base = dict(ev[-1])
+    ev[-2]["rocketStage"] = 3  # SEP2 starts the third stage's coast
+    ev.pop()  # SIMEND is re-appended last
+
+    def event(name, time, ref, on, thrust, att, nodes, pr=0.0):
+        e = dict(base)
+        e.update(name=name, time=time, time_ref=ref, rocketStage=3, engineOn=on, thrust=thrust, attitude=att,
+                 pitchrate_init=pr, yawrate_init=0.0, num_nodes=nodes)
+        return e
+
+    ev += [event("TEIG", 640.0, "SEP2", True, 5000.0, "pitch-yaw", 7, -0.02),
+           event("TECO", 700.0, float("nan"), False, 0.0, "hold", 3),
+           event("SEP3", 720.0, "TECO", False, 0.0, "hold", 2),
+           event("SIMEND", 725.0, "SEP3", False, 0.0, "hold", 2)]
+    return inp

@@ -85,7 +85,8 @@ enum { GA_LIMIT = 0, GA_F64_COLS };
 
 /* ---- event-point jobs (con_waypoint.py, con_init_terminal_knot.py:329-405,
  *      user constraint built-ins) ------------------------------------------- */
-enum { GE_LLH = 0, GE_IIP = 1, GE_ANT = 2, GE_TERM = 3, GE_USER_PERIGEE = 4 };
+enum { GE_LLH = 0, GE_IIP = 1, GE_ANT = 2, GE_TERM = 3, GE_USER_PERIGEE = 4, GE_N_TYPES };
+#define GE_USER_AUX 12 /* values a user built-in leaves in the auxiliary tail of vals: 6 FD + 6 background quotients */
 enum {
   GE_TYPE = 0,
   GE_TIDX,    /* index into t (section number), -1 if unused */
@@ -173,7 +174,8 @@ int gelato_plan_destroy(GelatoPlan* plan);
 int32_t gelato_plan_n_vars(const GelatoPlan* plan);
 int32_t gelato_plan_n_rows(const GelatoPlan* plan);
 int64_t gelato_plan_n_vals(const GelatoPlan* plan);
-/* thread blocks per scenario of the residual (which = 0) / Jacobian (which = 1) kernel */
+/* thread blocks per scenario: which = 0 residual kernel | 1 both Jacobian kernels | 2 the heavy Jacobian kernel
+ * | 3 the light one | 4 the residual kernel's non-dynamics blocks (what a pair evaluation launches of it) */
 int32_t gelato_plan_n_blocks(const GelatoPlan* plan, int which);
 /* kernels launched by this plan so far (bench.py's gpu_launches) */
 int64_t gelato_plan_launch_count(const GelatoPlan* plan);
@@ -204,8 +206,8 @@ int gelato_eval_jacobian_ids(GelatoPlan* plan, const double* x, double* vals, in
  *                                every other slot of vals is left as it was.
  * After the two calls vals holds exactly what gelato_eval_jacobian returns. */
 /* gelato_eval_pair_update: `objfunc` and `sens` of the same decision vectors in one call -- x is uploaded
- * once, the residual kernel runs on a side stream next to the Jacobian kernel, g is copied back whole and
- * vals is updated as by gelato_eval_jacobian_update.  Results are those of the two separate calls. */
+ * once, one pair evaluation (see gelato_eval_pair_dev), g is copied back whole and vals is updated as by
+ * gelato_eval_jacobian_update.  Results are those of the two separate calls. */
 int64_t gelato_plan_n_xdep(const GelatoPlan* plan);
 int gelato_jacobian_template(GelatoPlan* plan, double* vals, int32_t n_scen);
 int gelato_eval_jacobian_update(GelatoPlan* plan, const double* x, double* vals, int32_t n_scen);
@@ -226,6 +228,28 @@ int gelato_probe_update(GelatoPlan* plan, double* vals, int32_t n_scen, int reps
 /* host threads used by the scatter of update mode (default: min(16, hardware threads)) */
 int gelato_set_host_threads(GelatoPlan* plan, int32_t n_threads);
 
+/* Packed mode: what a batched driver that assembles its own sparse matrices should call (the consumer gathers,
+ * nobody scatters).  The Jacobian kernels write only the INDEPENDENT x-dependent values of each scenario,
+ * contiguously (n_pack per scenario: the node-diagonal entries of the dense D (x) I blocks as dense arrays, one
+ * value instead of 3n for eqcon_dyn_pos/velocity, no `tf` halves that are exact negations of the `to` halves --
+ * about 15 % fewer values than the x-dependent COO slots), and g and packed come back as contiguous copies.
+ *   gelato_plan_n_pack        n_pack
+ *   gelato_plan_packed_map    for each of the n_xdep x-dependent COO slots, ascending (full_slot == xdep_idx): the
+ *                             packed value it holds and its sign: vals[full_slot[i]] = sgn[i] * packed[src[i]]
+ *                             (sgn = +-1.0; with the constant slots of gelato_jacobian_template this reproduces
+ *                             gelato_eval_jacobian bit for bit -- a CSR / KKT assembly composes this map with its
+ *                             own once and then gathers straight from `packed`)
+ *   gelato_eval_pair_packed   objfunc + sens of the same x: g[n_scen][n_rows] and packed[n_scen][n_pack]
+ *   gelato_eval_jacobian_packed  sens only
+ *   gelato_eval_pair_packed_ids  subset batches (see gelato_eval_residuals_ids)
+ * Host buffers; page-locked ones (gelato_host_alloc) are DMA'd directly; pipelined over slices of the batch. */
+int64_t gelato_plan_n_pack(const GelatoPlan* plan);
+int gelato_plan_packed_map(const GelatoPlan* plan, int64_t* full_slot, int64_t* src, double* sgn);
+int gelato_eval_pair_packed(GelatoPlan* plan, const double* x, double* g, double* packed, int32_t n_scen);
+int gelato_eval_jacobian_packed(GelatoPlan* plan, const double* x, double* packed, int32_t n_scen);
+int gelato_eval_pair_packed_ids(GelatoPlan* plan, const double* x, double* g, double* packed, int32_t n_scen,
+                                const int32_t* scen_ids);
+
 int gelato_host_alloc(size_t bytes, void** out);
 int gelato_host_free(void* ptr);
 
@@ -236,19 +260,29 @@ int gelato_host_free(void* ptr);
  * x-dependent slot on each call and leaves the constants alone. */
 int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
 int gelato_fill_template(GelatoPlan* plan, double* vals_dev, int32_t n_scen, void* stream);
-/* both kernels for the same x_dev: the residual kernel on a side stream forked from and joined back into
- * `stream`, concurrent with the Jacobian kernel */
+/* objfunc + sens of the same x_dev as ONE evaluation: the Jacobian kernels' dynamics blocks already hold the
+ * right-hand side at the pristine x (their centre column) and write the collocation defects next to the
+ * Jacobian values; only the aero / event / linear rows run as (the non-dynamics blocks of) the residual kernel,
+ * on a side stream forked from and joined back into `stream`.  Bit-identical to the two separate calls.
+ * _packed_dev: the same with the packed Jacobian output ([n_scen][n_pack], see gelato_eval_pair_packed). */
 int gelato_eval_pair_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* vals_dev, int32_t n_scen,
                          void* stream);
+int gelato_eval_pair_packed_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
+                                void* stream);
 int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
 /* packed_dev[n_scen][n_xdep] = the x-dependent slots of vals_dev[n_scen][n_vals], in ascending slot order */
 int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream);
 
-/* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen
- * kernel (0 residuals, 1 jacobian) on device-resident buffers and returns the
- * average duration in milliseconds measured with CUDA events on the launch stream. */
+/* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen kernel on device-resident
+ * buffers and returns the average duration in milliseconds measured with CUDA events on the launch stream.
+ * which: 0 residual kernel | 1 the Jacobian evaluation (heavy + light kernels) | 2 the heavy Jacobian kernel
+ * alone (air dynamics + aero rows) | 3 the light Jacobian kernel alone. */
 int gelato_time_kernel(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
                        float* avg_ms);
+/* Measurement helper: enqueue exactly one kernel (which: 0, 2 or 3 as above) on `stream`, COO (packed = 0) or
+ * packed output, not synchronised -- for benchmarks that bracket single kernels with their own CUDA events. */
+int gelato_launch_kernel_dev(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen,
+                             int32_t packed, void* stream);
 
 /* 1 if the library was compiled with unfused multiply-add on the device (the
  * build contract, checked by running a probe kernel); 0 otherwise. */

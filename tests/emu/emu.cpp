@@ -24,6 +24,7 @@ static PlanView host_view(const GelatoPlanDesc* d) {
   v.lin_i32 = d->lin_i32; v.lin_f64 = d->lin_f64;
   v.aero_i32 = d->aero_i32; v.aero_i64 = d->aero_i64; v.aero_f64 = d->aero_f64; v.rc_aero = d->rc_aero;
   v.evt_i32 = d->evt_i32; v.evt_i64 = d->evt_i64; v.evt_f64 = d->evt_f64;
+  v.packed = 0;
   return v;
 }
 
@@ -73,32 +74,84 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
   return 0;
 }
 
-extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
-                                 double* vals_all, int n_scen, const int32_t* ids) {
+// mode bit 0: packed output (out_all is [n_scen][n_pack], nothing is pre-filled);  g_all != NULL: pair
+// evaluation -- the dynamics defects come out of the Jacobian blocks, the other rows from the residual
+// kernel's non-dynamics blocks (what gelato_eval_pair_* launches).
+static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,
+                        double* out_all, int n_scen, const int32_t* ids, int packed) {
   if (validate_desc(d)) return -1;
   PlanView P = host_view(d);
   apply_scen(P, sc);
   HostTables h;
   build_host_tables(d, h);
   attach_tables(P, h);
+  PackedLayout L;
+  build_packed_layout(d, L);
+  P.packed = packed;
+  P.n_pack = L.n_pack;
+  P.sec_pk = L.sec_pk.data(); P.aero_pk = L.aero_pk.data(); P.evt_pk = L.evt_pk.data();
   const std::vector<int32_t>& jb = h.jac_blocks;
+  const std::vector<int32_t>& rb = h.res_blocks;
   JacStore store;
   const JacScratch sm = jac_scratch(store);
+  ResScratch rsm;
+  const size_t stride = packed ? (size_t)L.n_pack : (size_t)P.n_vals;
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
-    double* vals = vals_all + (size_t)scen * P.n_vals;
+    double* vals = out_all + scen * stride;
+    double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
     const int sid = ids ? ids[scen] : scen;
-    const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)sid * P.n_vals : d->vals_template;
-    memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
+    if (!packed) {
+      const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)sid * P.n_vals : d->vals_template;
+      memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
+    }
     for (size_t b = 0; b < jb.size() / BT_COLS; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
       /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
       memset(&store, 0xff, sizeof store);
       for (int phase = 0; phase < GJ_PHASES; phase++)
-        for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase(P, sid, bt, x, vals, tid, phase, sm);
+        for (int tid = 0; tid < GJ_THREADS; tid++) {
+          if ((int)b < h.n_jac_heavy) jac_block_phase<JR_HEAVY>(P, sid, bt, x, vals, g, tid, phase, sm);
+          else jac_block_phase<JR_LIGHT>(P, sid, bt, x, vals, g, tid, phase, sm);
+        }
     }
+    if (g)
+      for (size_t b = (size_t)h.n_res_dyn; b < rb.size() / BT_COLS; b++) {
+        const int32_t* bt = rb.data() + b * BT_COLS;
+        memset(&rsm, 0xff, sizeof rsm);
+        for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, sid, bt, x, g, tid, rsm);
+      }
   }
   return 0;
+}
+
+extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
+                                 double* vals_all, int n_scen, const int32_t* ids) {
+  return emu_jacobian(d, sc, x_all, nullptr, vals_all, n_scen, ids, 0);
+}
+
+extern "C" int emu_eval_pair(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,
+                             double* out_all, int n_scen, const int32_t* ids, int packed) {
+  return emu_jacobian(d, sc, x_all, g_all, out_all, n_scen, ids, packed);
+}
+
+// packed layout of a plan: returns n_pack; with non-NULL arrays also the map of the n_xdep COO slots
+extern "C" long long emu_packed_map(const GelatoPlanDesc* d, int64_t* full_slot, int64_t* src, double* sgn) {
+  if (validate_desc(d)) return -1;
+  PackedLayout L;
+  build_packed_layout(d, L);
+  if (full_slot && src && sgn)
+    for (size_t i = 0; i < L.full_slot.size(); i++) {
+      full_slot[i] = L.full_slot[i];
+      src[i] = L.src[i];
+      sgn[i] = L.sgn[i];
+    }
+  return L.n_pack;
+}
+extern "C" long long emu_n_xdep(const GelatoPlanDesc* d) {
+  PackedLayout L;
+  build_packed_layout(d, L);
+  return (long long)L.full_slot.size();
 }
 
 // the result-table kernel's per-thread function (output.h), one call per node

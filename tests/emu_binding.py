@@ -44,6 +44,14 @@ class Emulator:
         for fn in (self.L.emu_eval_residuals, self.L.emu_eval_jacobian):
             fn.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, ctypes.c_int,
                            ctypes.POINTER(ctypes.c_int32)]
+        self.L.emu_eval_pair.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, _pd,
+                                         ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
+        _pi64 = ctypes.POINTER(ctypes.c_int64)
+        self.L.emu_packed_map.argtypes = [ctypes.POINTER(engine.PlanDesc), _pi64, _pi64, _pd]
+        self.L.emu_packed_map.restype = ctypes.c_longlong
+        self.L.emu_n_xdep.argtypes = [ctypes.POINTER(engine.PlanDesc)]
+        self.L.emu_n_xdep.restype = ctypes.c_longlong
+        self.n_pack = int(self.L.emu_packed_map(ctypes.byref(self.desc), None, None, None))
 
     def _sc(self):
         return ctypes.byref(self.sc) if self.sc is not None else None
@@ -72,19 +80,45 @@ class Emulator:
         return v if n_scen == 1 else v.reshape(n_scen, -1)
 
 
+    def packed_map(self):
+        """(full_slot, src, sgn): vals[full_slot] = sgn * packed[src] (plan_host.h: build_packed_layout)."""
+        n = int(self.L.emu_n_xdep(ctypes.byref(self.desc)))
+        full, src, sgn = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64), np.empty(n)
+        _pi64 = ctypes.POINTER(ctypes.c_int64)
+        self.L.emu_packed_map(ctypes.byref(self.desc), full.ctypes.data_as(_pi64), src.ctypes.data_as(_pi64),
+                              sgn.ctypes.data_as(_pd))
+        return full, src, sgn
+
+    def eval_pair(self, x, n_scen=1, scen_ids=None, packed=False):
+        """(g, vals or packed) of a pair evaluation: defects from the Jacobian blocks' centre columns."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.full(n_scen * self.plan.n_rows, np.nan)
+        width = self.n_pack if packed else self.plan.n_vals
+        v = np.full(n_scen * width, np.nan)
+        ids, pids = self._ids(scen_ids)
+        rc = self.L.emu_eval_pair(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd),
+                                  v.ctypes.data_as(_pd), n_scen, pids, 1 if packed else 0)
+        assert rc == 0
+        if n_scen == 1:
+            return g, v
+        return g.reshape(n_scen, -1), v.reshape(n_scen, -1)
+
+
 class EmuEngine(Emulator):
     """The emulator behind the Engine interface GelatoProblem uses (CPU test tier only)."""
 
     def __init__(self, plan, scenario_plans=None):
         super().__init__(plan, scenario_plans=scenario_plans)
-        self.launches = 0
+        self.launches = self.calls = 0
 
     def eval_residuals(self, x, n_scen=1, out=None, scen_ids=None):
         self.launches += 1
+        self.calls += 1
         return super().eval_residuals(x, n_scen, scen_ids)
 
     def eval_jacobian(self, x, n_scen=1, out=None, scen_ids=None):
         self.launches += 1
+        self.calls += 1
         return super().eval_jacobian(x, n_scen, scen_ids)
 
     def close(self):

@@ -253,22 +253,7 @@ def variant_inputs(name):
         # (reference_area != 0.0, con_dynamics.py:257) but the vacuum Jacobian branches (> 0.0, :403,454)
         s["RocketStage"]["2"]["reference_area"] = -0.5
     elif name == "three_stage":  # BASELINE.json configs[2]: a third stage (coast, burn, coast) after SEP2
-        s["RocketStage"]["3"] = {"mass_dry": 150.0, "mass_propellant": 600.0, "dropMass": {}, "Isp_vac": 320.0,
-                                 "reference_area": 0.0, "ignition_at": "TEIG", "cutoff_at": "TECO",
-                                 "separation_at": "SEP3"}
-        ev = inp["events"]
-        base = dict(ev[-1])
-        ev[-2]["rocketStage"] = 3  # SEP2 starts the third stage's coast
-        ev.pop()  # SIMEND is re-appended last
-        def event(name, time, ref, on, thrust, att, nodes, pr=0.0):
-            e = dict(base)
-            e.update(name=name, time=time, time_ref=ref, rocketStage=3, engineOn=on, thrust=thrust, attitude=att,
-                     pitchrate_init=pr, yawrate_init=0.0, num_nodes=nodes)
-            return e
-        ev += [event("TEIG", 640.0, "SEP2", True, 5000.0, "pitch-yaw", 7, -0.02),
-               event("TECO", 700.0, float("nan"), False, 0.0, "hold", 3),
-               event("SEP3", 720.0, "TECO", False, 0.0, "hold", 2),
-               event("SIMEND", 725.0, "SEP3", False, 0.0, "hold", 2)]
+        problem.three_stage_inputs(inp)
     elif name == "iip_orbital":  # IIP rows where there is no impact point (orbital speed): the leaf returns
         # zeros (iip.cpp:49-128), the rows become constants and their finite differences exact zeros
         fc["waypoint"] = {"SECO": {"lat_IIP": {"min": -10.0}, "lon_IIP": {"exact": 150.0}},

@@ -11,9 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(extra, env=None):
     e = dict(os.environ)
     e.update(env or {})
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--factor", "1"] + extra, cwd=ROOT, env=e, capture_output=True, text=True,
-                         timeout=300)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--factor", "1", "--scenarios", "3"] + extra, cwd=ROOT, env=e, capture_output=True,
+                         text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip().splitlines()
 
@@ -24,14 +24,17 @@ def test_reference_arm_prints_the_contract_line():
     b = json.loads(lines[0])
     assert b["impl"] == "reference" and b["metric"] == "fd_jacobian_plus_residual_evals_per_s"
     assert b["unit"] == "evals/s" and b["higher_is_better"] is True and b["scaling"] == "weak"
-    assert b["n_gpus"] == 1 and b["steps"] == 1 and b["warmup"] == 1 and b["dtype"] == "f64" and b["data"] == "synthetic"
+    # the arm honours the driver's --steps / --warmup / --scenarios
+    assert b["n_gpus"] == 1 and b["steps"] == 2 and b["warmup"] == 1 and b["dtype"] == "f64" and b["data"] == "synthetic"
+    assert b["config"]["scenarios_per_gpu"] == 3
     assert b["value"] > 0 and b["ms_per_step"] > 0 and b["vs_baseline"] is None and b["gpu_launches"] == 0
     assert "workload" in b["config"] and "model" not in b["config"]
     cb = b["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == b["value"] and cb["sample"]
     assert b["e2e"] == {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # value = evaluations of the step / time of the step
-    evals = b["config"]["scenarios_per_step"] * b["config"]["evals_per_scenario_step"]
+    evals = b["config"]["scenarios_per_gpu"] * b["config"]["evals_per_scenario_step"]
+    assert abs(b["pairs_per_s"] - b["config"]["scenarios_per_gpu"] / (b["ms_per_step"] * 1e-3)) <= 1e-6 * b["pairs_per_s"]
     assert abs(b["value"] - evals / (b["ms_per_step"] * 1e-3)) <= 1e-6 * b["value"]
 
 

@@ -43,6 +43,33 @@ def test_emulated_kernels_match_oracle_bitwise(variant, factor, user):
         helpers.assert_sens_equal(s, P.split_jacobian(vals, key_order=list(x.keys())))
 
 
+@pytest.mark.parametrize("variant,factor,user", [
+    ("example", 1, True), ("example", 3, True), ("all_aero", 2, True), ("waypoints", 1, True), ("neg_area", 1, True),
+    ("three_stage", 1, True), ("fuel_inclination", 1, True), ("bare", 1, False),
+])
+def test_pair_and_packed_outputs_equal_the_separate_kernels(variant, factor, user):
+    """A pair evaluation takes objfunc's dynamics rows from the Jacobian blocks (centre column = pristine x);
+    the packed output holds only the independent x-dependent values.  Both must reproduce the separate
+    residual / Jacobian evaluations bit for bit: g == eval_residuals, and template + map(packed) == eval_jacobian."""
+    p, u, c, x0, O, P = _setup(variant, factor, user=user)
+    E = emu_binding.Emulator(P)
+    full, src, sgn = E.packed_map()
+    assert np.array_equal(full, P.xdep_index()), "the C layout and the plan compiler disagree on the x-dependent slots"
+    assert src.min() == 0 and src.max() == E.n_pack - 1 and np.unique(src).size == E.n_pack
+    assert set(np.unique(sgn)) <= {-1.0, 1.0}
+    for x in (x0, helpers.perturbed(x0)):
+        xv = problem.xdict_to_vector(x)
+        g_ref, v_ref = E.eval_residuals(xv), E.eval_jacobian(xv)
+        g, v = E.eval_pair(xv)
+        assert np.array_equal(g, g_ref) and np.array_equal(v, v_ref)
+        g, pk = E.eval_pair(xv, packed=True)
+        assert np.array_equal(g, g_ref) and not np.isnan(pk).any()
+        v = P.vals_template.copy()
+        v[full] = sgn * pk[src]
+        assert np.array_equal(v, v_ref)
+        assert np.array_equal(np.signbit(v[full]), np.signbit(v_ref[full]))
+
+
 def test_large_section_counts():
     """A section larger than one residual block (n = 40 > 32 nodes) and the minimum n = 2."""
     Lg = leaves.get("gmath")

@@ -39,7 +39,7 @@ def test_library_is_the_cuda_build():
     assert prob.engine.launches == 0
     prob.objfunc(x0)
     prob.sens(x0)
-    assert prob.engine.launches == 2  # ONE kernel per callback
+    assert prob.engine.launches == 3  # objfunc: the residual kernel; sens: the heavy and the light Jacobian kernel
 
 
 @pytest.mark.parametrize("variant,factor,user", [
@@ -299,6 +299,73 @@ def test_pair_evaluation_equals_the_two_calls():
     s.synchronize()
     assert np.array_equal(gd.cpu().numpy(), g_want) and np.array_equal(vd.cpu().numpy(), v_want)
     prob.close()
+
+
+@pytest.mark.parametrize("variant,factor,n", [("example", 4, 3), ("all_aero", 2, 40), ("neg_area", 1, 2), ("three_stage", 1, 17)])
+def test_packed_pair_evaluation_reproduces_the_two_calls(variant, factor, n):
+    """gelato_eval_pair_packed: objfunc's rows from the Jacobian kernels' centre columns, and only the independent
+    x-dependent Jacobian values, contiguous.  g must equal gelato_eval_residuals and template + map(packed) must
+    equal gelato_eval_jacobian, bit for bit -- through pageable and page-locked buffers, sliced pipeline included
+    (n = 40 scenarios -> 2 slices), and on the device-resident entry point."""
+    import torch
+
+    prob, O, x0 = _problem(variant, factor)
+    E, P = prob.engine, prob.plan
+    X = np.stack([problem.xdict_to_vector(helpers.perturbed(x0, seed=s)) for s in range(n)])
+    g_want = E.eval_residuals(X, n).reshape(n, -1).copy()
+    v_want = E.eval_jacobian(X, n).reshape(n, -1).copy()
+    full, src, sgn = E.packed_map()
+    assert np.array_equal(full, P.xdep_index()) and E.n_pack == np.unique(src).size < full.size
+
+    def expand(pk):
+        v = np.tile(P.vals_template, (n, 1))
+        v[:, full] = sgn * pk.reshape(n, -1)[:, src]
+        return v
+
+    G, PK = E.eval_pair_packed(X, n)
+    assert np.array_equal(G.reshape(n, -1), g_want) and np.array_equal(expand(PK), v_want)
+    assert np.array_equal(expand(E.eval_jacobian_packed(X, n)), v_want)
+    hx, hg, hp = engine.PinnedArray(X.size), engine.PinnedArray(n * P.n_rows), engine.PinnedArray(n * E.n_pack)
+    hx.array[:] = X.ravel()
+    hg.array[:] = np.nan
+    hp.array[:] = np.nan
+    E.eval_pair_packed(hx.array, n, g_out=hg.array, packed_out=hp.array)
+    assert np.array_equal(hg.array.reshape(n, -1), g_want) and np.array_equal(expand(hp.array), v_want)
+    for a in (hx, hg, hp):
+        a.free()
+    xd = torch.from_numpy(X).cuda()
+    gd = torch.full((n, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
+    pd = torch.full((n, E.n_pack), float("nan"), dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        E.eval_pair_packed_dev(xd.data_ptr(), gd.data_ptr(), pd.data_ptr(), n, s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(gd.cpu().numpy(), g_want) and np.array_equal(expand(pd.cpu().numpy()), v_want)
+    prob.close()
+
+
+def test_replacing_the_scenarios_refreshes_the_staged_constants():
+    """gelato_plan_set_scenarios after an evaluation: the staged Jacobian buffer must not keep the previous
+    scenarios' constant slots."""
+    Lg = leaves.get("gmath")
+    scen = scenarios.disperse(helpers.example_inputs(), 4, seed=3)
+    plans, xs = [], []
+    for si in scen:
+        p, u, c, x0 = problem.problem_from_inputs(si, coord=Lg.coordinate_c)
+        plans.append(helpers.compiled_plan(p, u, c, coord=Lg.coordinate_c))
+        xs.append(problem.xdict_to_vector(helpers.perturbed(x0, seed=len(xs))))
+    X = np.stack(xs)
+    Ea = engine.Engine(plans[0], scenario_plans=plans[:2])
+    va = Ea.eval_jacobian(X[:2], 2).copy()
+    Eb = engine.Engine(plans[0], scenario_plans=plans[2:])
+    want = Eb.eval_jacobian(X[2:], 2).copy()
+    assert not np.array_equal(va, want)
+    import ctypes
+    sc, keep = engine.make_scenario_desc(plans[2:])
+    assert Ea.L.gelato_plan_set_scenarios(Ea.h, ctypes.byref(sc)) == 0
+    assert np.array_equal(Ea.eval_jacobian(X[2:], 2), want)
+    Ea.close()
+    Eb.close()
 
 
 def test_reuse_output_sens_equals_fresh_sens():

@@ -60,7 +60,7 @@ def setup(request):
     glib.reset()
 
 
-def test_every_group_function_matches_the_oracle_with_two_launches(setup):
+def test_every_group_function_matches_the_oracle_with_two_evaluations(setup):
     p, u, c, x, O = setup
     xa = helpers.copy_x(x)
     fo, _ = O.objfunc(xa)
@@ -74,12 +74,12 @@ def test_every_group_function_matches_the_oracle_with_two_launches(setup):
     helpers.assert_funcs_equal(fo, {k: funcs[k] for k in fo})
     helpers.assert_sens_equal(so, {k: sens[k] for k in so})
     eng = glib.problem_for(p, u, c).prob.engine
-    assert eng.launches == 2  # 23 value functions = one residual launch, 23 Jacobian functions = one Jacobian launch
+    assert eng.calls == 2  # 23 value functions = ONE residual evaluation, 23 Jacobian functions = ONE Jacobian evaluation
     # a new decision vector invalidates both caches; results are copies the caller owns
     before = funcs["eqcon_dyn_vel"].copy()
     x2 = helpers.perturbed(x, seed=11)
     r2 = con_dynamics.equality_dynamics_velocity(x2, p, u, c)
-    assert eng.launches == 3 and not np.array_equal(r2, before)
+    assert eng.calls == 3 and not np.array_equal(r2, before)
     assert np.array_equal(funcs["eqcon_dyn_vel"], before)
     assert con_aero.inequality_length_max_qalpha(x, p, u, c) == len(funcs["ineqcon_qalpha"])
     assert con_aero.inequality_length_max_q(x, p, u, c) == 0 and funcs["ineqcon_q"] is None
