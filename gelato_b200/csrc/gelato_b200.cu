@@ -1091,9 +1091,11 @@ int gelato_host_free(void* ptr) {
 }
 
 // Measurement helper: enqueue exactly ONE kernel on `stream` (0 residual kernel | 2 heavy Jacobian kernel |
-// 3 light Jacobian kernel), COO or packed output, so that a benchmark can bracket it with its own CUDA events.
-int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, double* out_dev, int32_t n_scen, int32_t packed,
-                             void* stream) {
+// 3 light Jacobian kernel | 4 the residual kernel's non-dynamics blocks; out_dev = g for 0 and 4), COO or packed
+// output, g_dev != NULL: with the pair evaluation's defect rows -- so that a benchmark can bracket it with its own
+// CUDA events.
+int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, double* out_dev, double* g_dev, int32_t n_scen,
+                             int32_t packed, void* stream) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
@@ -1104,13 +1106,17 @@ int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, doub
     k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(v, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
   } else if (which == 2) {
     if (p->n_jac_heavy == 0) return fail(GELATO_ERR_ARG, "the plan has no heavy blocks");
-    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, nullptr, x_dev, out_dev, nullptr);
+    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else if (which == 3) {
     if (p->n_jac_blocks == p->n_jac_heavy) return fail(GELATO_ERR_ARG, "the plan has no light blocks");
     k_jacobian_light<<<(unsigned)(p->n_jac_blocks - p->n_jac_heavy) * n_scen, GJ_THREADS, 0, st>>>(
-        v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, nullptr);
+        v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, g_dev);
+  } else if (which == 4) {  // the residual kernel's non-dynamics blocks (what a pair evaluation launches of it)
+    if (p->n_res_blocks == p->n_res_dyn) return fail(GELATO_ERR_ARG, "the plan has no non-dynamics residual blocks");
+    k_residuals<<<(unsigned)(p->n_res_blocks - p->n_res_dyn) * n_scen, GR_THREADS, 0, st>>>(
+        v, p->res_blocks + (size_t)p->n_res_dyn * BT_COLS, n_scen, nullptr, x_dev, out_dev);
   } else {
-    return fail(GELATO_ERR_ARG, "which must be 0, 2 or 3");
+    return fail(GELATO_ERR_ARG, "which must be 0, 2, 3 or 4");
   }
   p->launches++;
   CU(cudaGetLastError());

@@ -35,13 +35,27 @@
  * that satisfies the static_asserts is valid. */
 #ifndef GJ_THREADS
 #define GJ_THREADS 288   /* Jacobian kernel block */
+#endif
+#ifndef GJ_NODES
 #define GJ_NODES 20      /* aero rows per Jacobian block */
+#endif
+#ifndef GD_NODES
 #define GD_NODES 20      /* air dynamics nodes per Jacobian block */
+#endif
+#ifndef GJ_A_THREADS
 #define GJ_A_THREADS 128 /* threads [0, 128): position items; the rest: rotation and quaternion items */
+#endif
+#ifndef GN_NODES
 #define GN_NODES 32      /* no-air nodes per Jacobian block (9 column items each = 288) */
+#endif
+#ifndef GN_A_THREADS
 #define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items, the rest quaternion items */
-#define GJ_EVT 18        /* event jobs per Jacobian block (16 lanes each) */
-#define GG_NODES 18      /* nodes per block of the one-lane-per-column fallback (16 lanes each) */
+#endif
+#ifndef GJ_EVT
+#define GJ_EVT (GJ_THREADS / 16) /* event jobs per Jacobian block (16 lanes each) */
+#endif
+#ifndef GG_NODES
+#define GG_NODES (GJ_THREADS / 16) /* nodes per block of the one-lane-per-column fallback (16 lanes each) */
 #endif
 #define GR_THREADS 128 /* residual kernel block */
 #define GR_NODES 64    /* nodes per residual block */

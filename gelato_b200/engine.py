@@ -222,7 +222,7 @@ def load_library():
     L.gelato_host_free.argtypes = [vp]
     L.gelato_time_kernel.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_float)]
-    L.gelato_launch_kernel_dev.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
+    L.gelato_launch_kernel_dev.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
     L.gelato_selftest_unfused.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.gelato_fp64_peak.argtypes = [ctypes.c_int, _pd, _pd]
     i32 = ctypes.c_int32
@@ -436,9 +436,10 @@ class Engine:
     def pack_xdep_dev(self, vals_ptr, packed_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_pack_xdep_dev(self.h, vals_ptr, packed_ptr, n_scen, stream), "gelato_pack_xdep_dev")
 
-    def launch_kernel_dev(self, which, x_ptr, out_ptr, n_scen=1, packed=False, stream=None):
-        """Enqueue ONE kernel (0 residual, 2 heavy Jacobian, 3 light Jacobian) on `stream` (measurement helper)."""
-        _check(self.L, self.L.gelato_launch_kernel_dev(self.h, which, x_ptr, out_ptr, n_scen, 1 if packed else 0, stream),
+    def launch_kernel_dev(self, which, x_ptr, out_ptr, n_scen=1, packed=False, stream=None, g_ptr=None):
+        """Enqueue ONE kernel (0 residual, 2 heavy Jacobian, 3 light Jacobian, 4 non-dynamics residual blocks) on
+        `stream` (measurement helper); g_ptr: a Jacobian kernel also writes the pair evaluation's defect rows."""
+        _check(self.L, self.L.gelato_launch_kernel_dev(self.h, which, x_ptr, out_ptr, g_ptr, n_scen, 1 if packed else 0, stream),
                "gelato_launch_kernel_dev")
 
     def time_kernel(self, which, x_ptr, out_ptr, n_scen=1, reps=10):

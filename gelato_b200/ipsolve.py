@@ -1,0 +1,436 @@
+"""A host-side interior-point NLP solver for the callbacks of this package -- NOT IPOPT.
+
+The reference hands `objfunc` / `sens` to pyoptsparse's IPOPT wrapper
+(/root/reference/Trajectory_Optimization.py:454-458; options `example-settings.json:92-97`: tol 1e-6,
+limited-memory Hessian -- pyoptsparse's default, the callbacks give first derivatives only --, MUMPS for the
+sparse KKT systems).  Neither pyoptsparse nor IPOPT can be installed in this image, so this module restates
+the METHOD (Waechter & Biegler 2006, the algorithm IPOPT implements) in ~500 lines of numpy / scipy for one
+purpose: to drive the very same callbacks, CPU oracle or CUDA, to a converged solution, so that the
+converged payload mass and event times, the callback counts and the time spent in the callbacks can be
+compared and "solves per hour" can be measured.  It is a stand-in and is labelled as such everywhere.
+
+    min f(x)  s.t.  c_E(x) = 0,  c_I(x) >= 0,  x_L <= x <= x_U
+
+* primal-dual log-barrier with slacks for the inequality rows, monotone (Fiacco-McCormick) barrier update,
+  fraction-to-the-boundary rule, gradient-based row scaling (IPOPT's nlp_scaling_max_gradient = 100);
+* Hessian of the Lagrangian: damped limited-memory BFGS in compact form; the KKT matrix
+  [[sigma I + Sigma, J^T], [J, -D]] stays SPARSE (scipy SuperLU) and the 2m rank correction goes through the
+  Woodbury identity -- the sparse KKT solve stays on the host, as the north star prescribes;
+* globalisation: l1 exact-penalty merit function with Armijo backtracking and a second-order correction;
+  when the line search fails the quasi-Newton memory is dropped, then a least-norm feasibility step is tried.
+
+Interface: `IPSolver(options)(optProb, sens=sens) -> Solution`, for `nlpshim.Optimization` problems
+(the same call the reference makes on pyoptsparse's classes).
+"""
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+class Solution:
+    pass
+
+
+class _LBFGS:
+    """Damped limited-memory BFGS approximation B = sigma I - U M^-1 U^T of the Hessian of the Lagrangian
+    (compact form of Byrd, Nocedal & Schnabel 1994), U = [sigma S, Y]."""
+
+    def __init__(self, n, memory):
+        self.n, self.m = n, memory
+        self.reset()
+
+    def reset(self, sigma=1.0):
+        self.S, self.Y = [], []
+        self.sigma = sigma
+        self._U = self._M = None
+
+    def times(self, v):
+        if not self.S:
+            return self.sigma * v
+        U, M = self.factors()
+        return self.sigma * v - U @ np.linalg.solve(M, U.T @ v)
+
+    def update(self, s, y):
+        ss = float(s @ s)
+        if ss < 1e-30:
+            return
+        Bs = self.times(s)
+        sBs = float(s @ Bs)
+        sy = float(s @ y)
+        if sy < 0.2 * sBs:  # Powell damping keeps the approximation positive definite
+            theta = 0.8 * sBs / (sBs - sy)
+            y = theta * y + (1.0 - theta) * Bs
+            sy = float(s @ y)
+        if sy <= 1e-12 * np.sqrt(ss * float(y @ y)):
+            return
+        self.S.append(s.copy())
+        self.Y.append(y.copy())
+        if len(self.S) > self.m:
+            self.S.pop(0)
+            self.Y.pop(0)
+        self.sigma = min(max(float(y @ y) / sy, 1e-6), 1e8)
+        self._U = None
+
+    def factors(self):
+        """(U [n, 2k], M [2k, 2k]) with B = sigma I - U M^-1 U^T."""
+        if self._U is None:
+            S, Y = np.array(self.S).T, np.array(self.Y).T
+            SY = S.T @ Y
+            Lm = np.tril(SY, -1)
+            D = np.diag(np.diag(SY))
+            sg = self.sigma
+            self._U = np.hstack((sg * S, Y))
+            self._M = np.block([[sg * (S.T @ S), Lm], [Lm.T, -D]])
+        return self._U, self._M
+
+
+class IPSolver:
+    """solver = IPSolver({"tol": 1e-6, "max_iter": 2000}); sol = solver(optProb, sens=sens)."""
+
+    DEFAULTS = {"tol": 1e-6, "max_iter": 2000, "mu_init": 0.1, "memory": 12, "bound_push": 1e-2,
+                "scaling_max_gradient": 100.0, "acceptable_tol": 1e-4, "acceptable_iter": 15, "verbose": 0}
+
+    def __init__(self, options=None):
+        self.opt = dict(self.DEFAULTS)
+        for k, v in (options or {}).items():
+            if k in self.opt:
+                self.opt[k] = v  # IPOPT-only options (linear_solver, output_file ...) are ignored
+
+    # ------------------------------------------------------------------
+    def __call__(self, prob, sens=None, **_):
+        o = self.opt
+        t_start = time.perf_counter()
+        names = [v[0] for v in prob.vars]
+        sizes = [v[1] for v in prob.vars]
+        offs = np.concatenate(([0], np.cumsum(sizes))).astype(int)
+        n = int(offs[-1])
+        col0 = dict(zip(names, offs[:-1]))
+        x = np.concatenate([v[2] for v in prob.vars]).astype(float)
+        xl = np.concatenate([np.full(v[1], -np.inf if v[3] is None else v[3]) for v in prob.vars])
+        xu = np.concatenate([np.full(v[1], np.inf if v[4] is None else v[4]) for v in prob.vars])
+        eq = [g for g in prob.cons if g[3] is not None and g[2] == g[3]]
+        ineq = [g for g in prob.cons if g not in eq]
+        for g in ineq:
+            if g[3] is not None or g[2] != 0.0:
+                raise NotImplementedError("inequality groups other than c(x) >= 0")
+        for g in eq:
+            if g[2] != 0.0:
+                raise NotImplementedError("equality groups other than c(x) = 0")
+        mE, mI = sum(g[1] for g in eq), sum(g[1] for g in ineq)
+        stat = {"obj_t": 0.0, "obj_n": 0, "sens_t": 0.0, "sens_n": 0}
+
+        def xdict(xv):
+            return {nm: xv[offs[i]: offs[i + 1]].copy() for i, nm in enumerate(names)}
+
+        def evaluate(xv, want_jac):
+            xd = xdict(xv)
+            t0 = time.perf_counter()
+            f, fail = prob.objfunc(xd)
+            stat["obj_t"] += time.perf_counter() - t0
+            stat["obj_n"] += 1
+            assert not fail
+            cE = np.concatenate([np.atleast_1d(np.asarray(f[g[0]], dtype=float)) for g in eq]) if eq else np.zeros(0)
+            cI = np.concatenate([np.atleast_1d(np.asarray(f[g[0]], dtype=float)) for g in ineq]) if ineq else np.zeros(0)
+            obj = float(np.asarray(f[prob.obj]).ravel()[0])
+            if not want_jac:
+                return obj, cE, cI, None, None, None
+            t0 = time.perf_counter()
+            s, fail = sens(xd, f)
+            stat["sens_t"] += time.perf_counter() - t0
+            stat["sens_n"] += 1
+            assert not fail
+            grad = np.zeros(n)
+            for var, blk in s[prob.obj].items():
+                grad[col0[var]: col0[var] + np.size(blk)] = np.ravel(blk)
+            return obj, cE, cI, grad, self._jac(s, eq, mE, n, col0), self._jac(s, ineq, mI, n, col0)
+
+        # ---- starting point: inside the bounds (IPOPT bound_push / bound_frac) ----
+        span = np.where(np.isfinite(xu - xl), xu - xl, np.inf)
+        pl = np.minimum(o["bound_push"] * np.maximum(1.0, np.abs(np.where(np.isfinite(xl), xl, 0.0))), 0.01 * span)
+        pu = np.minimum(o["bound_push"] * np.maximum(1.0, np.abs(np.where(np.isfinite(xu), xu, 0.0))), 0.01 * span)
+        x = np.minimum(np.maximum(x, xl + pl), xu - pu)
+        hasL, hasU = np.isfinite(xl), np.isfinite(xu)
+
+        f0, cE, cI, g, JE, JI = evaluate(x, True)
+        # gradient-based scaling of the objective and of every constraint row
+        gmax = o["scaling_max_gradient"]
+
+        def row_scale(J):
+            if J.shape[0] == 0:
+                return np.zeros(0)
+            mx = np.abs(J).max(axis=1).toarray().ravel()
+            return np.minimum(1.0, gmax / np.maximum(mx, 1e-300))
+
+        dE, dI = row_scale(JE), row_scale(JI)
+        df = min(1.0, gmax / max(np.abs(g).max(), 1e-300))
+        DE, DI = sp.diags(dE), sp.diags(dI)
+
+        def scaled(ev):
+            ob, ce, ci, gr, je, ji = ev
+            return (df * ob, dE * ce, dI * ci, None if gr is None else df * gr, None if je is None else (DE @ je).tocsr(),
+                    None if ji is None else (DI @ ji).tocsr())
+
+        f0, cE, cI, g, JE, JI = scaled((f0, cE, cI, g, JE, JI))
+        s = np.maximum(cI, o["bound_push"])
+        mu = o["mu_init"]
+        zL = np.where(hasL, mu / np.maximum(x - xl, 1e-300), 0.0)
+        zU = np.where(hasU, mu / np.maximum(xu - x, 1e-300), 0.0)
+        zs = mu / s
+        lamI = -zs.copy()
+        lamE = self._ls_multipliers(g, JE, JI, zL, zU, lamI)
+        B = _LBFGS(n, o["memory"])
+        nu = 1.0  # penalty parameter of the merit function
+        tol = o["tol"]
+        history = []
+        status, message = 1, "maximum number of iterations exceeded"
+        acceptable = 0
+        fails = 0
+        it = 0
+        for it in range(o["max_iter"] + 1):
+            # ---- optimality error of the NLP (mu = 0) and of the barrier problem ----
+            rx = g + JE.T @ lamE + JI.T @ lamI - zL + zU
+            s_d = max(100.0, (np.abs(lamE).sum() + np.abs(lamI).sum() + np.abs(zL).sum() + np.abs(zU).sum() + np.abs(zs).sum())
+                      / max(1, mE + mI + 2 * n + mI)) / 100.0
+            viol = max(np.abs(cE).max(initial=0.0), np.abs(cI - s).max(initial=0.0))
+
+            def compl(m):
+                return max(np.abs(np.where(hasL, (x - xl) * zL - m, 0.0)).max(initial=0.0),
+                           np.abs(np.where(hasU, (xu - x) * zU - m, 0.0)).max(initial=0.0), np.abs(s * zs - m).max(initial=0.0))
+
+            du_inf = max(np.abs(rx).max(), np.abs(lamI + zs).max(initial=0.0)) / s_d
+            E0 = max(du_inf, viol, compl(0.0) / s_d)
+            history.append((f0 / df, viol, du_inf, mu))
+            if o["verbose"] and (it % o["verbose"] == 0):
+                print("it %4d  obj %.8f  viol %.2e  dual %.2e  mu %.1e  nu %.1e  mem %d" % (it, f0 / df, viol, du_inf, mu, nu, len(B.S)))
+            if E0 <= tol:
+                status, message = 0, "converged to tol %g" % tol
+                break
+            acceptable = acceptable + 1 if E0 <= o["acceptable_tol"] else 0
+            if acceptable >= o["acceptable_iter"]:
+                status, message = 0, "converged to acceptable_tol %g" % o["acceptable_tol"]
+                break
+            if it == o["max_iter"]:
+                break
+            while mu > tol / 10.0 and max(du_inf, viol, compl(mu) / s_d) <= 10.0 * mu:
+                mu = max(tol / 10.0, min(0.2 * mu, mu ** 1.5))
+            tau = max(0.99, 1.0 - mu)
+
+            # ---- Newton step of the barrier problem ----
+            SigL = np.where(hasL, zL / np.maximum(x - xl, 1e-300), 0.0)
+            SigU = np.where(hasU, zU / np.maximum(xu - x, 1e-300), 0.0)
+            Sigs = zs / s
+            r_x = g + JE.T @ lamE + JI.T @ lamI - np.where(hasL, mu / np.maximum(x - xl, 1e-300), 0.0) \
+                + np.where(hasU, mu / np.maximum(xu - x, 1e-300), 0.0)
+            r_I = (cI - s) - (lamI + mu / s) / Sigs
+            rhs = -np.concatenate((r_x, cE, r_I))
+            delta_w = 0.0
+            for attempt in range(8):
+                sol_vec = self._kkt_solve(B, SigL + SigU + delta_w, JE, JI, 1.0 / Sigs, rhs, n, mE, mI)
+                if sol_vec is not None and np.all(np.isfinite(sol_vec)):
+                    break
+                delta_w = 1e-4 if delta_w == 0.0 else 10.0 * delta_w
+            else:
+                status, message = 2, "KKT system could not be solved"
+                break
+            dx, dlE, dlI = sol_vec[:n], sol_vec[n: n + mE], sol_vec[n + mE:]
+            ds = (dlI + lamI + mu / s) / Sigs
+            dzL = np.where(hasL, mu / np.maximum(x - xl, 1e-300) - zL - SigL * dx, 0.0)
+            dzU = np.where(hasU, mu / np.maximum(xu - x, 1e-300) - zU + SigU * dx, 0.0)
+            dzs = mu / s - zs - Sigs * ds
+
+            def max_step(v, dv, t):
+                neg = dv < 0
+                return min(1.0, float(np.min(-t * v[neg] / dv[neg]))) if neg.any() else 1.0
+
+            a_max = min(max_step(np.where(hasL, x - xl, 1.0), np.where(hasL, dx, 0.0), tau),
+                        max_step(np.where(hasU, xu - x, 1.0), np.where(hasU, -dx, 0.0), tau), max_step(s, ds, tau))
+            a_z = min(max_step(zL, dzL, tau), max_step(zU, dzU, tau), max_step(zs, dzs, tau))
+
+            # ---- l1 merit function, Armijo backtracking with a second-order correction ----
+            def barrier(xv, sv, fv):
+                return fv - mu * (np.log(np.where(hasL, xv - xl, 1.0)).sum() + np.log(np.where(hasU, xu - xv, 1.0)).sum()
+                                  + np.log(sv).sum())
+
+            gphi_d = float(g @ dx) - mu * (np.where(hasL, dx / np.maximum(x - xl, 1e-300), 0.0).sum()
+                                           - np.where(hasU, dx / np.maximum(xu - x, 1e-300), 0.0).sum() + (ds / s).sum())
+            theta0 = np.abs(cE).sum() + np.abs(cI - s).sum()
+            dWd = float(dx @ B.times(dx)) + float(dx @ ((SigL + SigU) * dx)) + float(ds @ (Sigs * ds))
+            if theta0 > 1e-14:
+                nu_trial = (gphi_d + 0.5 * max(dWd, 0.0)) / (0.7 * theta0)
+                if nu_trial > nu:
+                    nu = nu_trial + 1.0
+            phi0 = barrier(x, s, f0) + nu * theta0
+            Dphi = gphi_d - nu * theta0
+            alpha = a_max
+            accepted = False
+            soc_done = False
+            step_dx, step_ds = dx, ds
+            for ls in range(40):
+                xt = x + alpha * step_dx
+                st = s + alpha * step_ds
+                if np.any(st <= 0) or np.any(xt <= xl) or np.any(xt >= xu):
+                    alpha *= 0.5
+                    continue
+                ft, cEt, cIt, _, _, _ = scaled(evaluate(xt, False))
+                thetat = np.abs(cEt).sum() + np.abs(cIt - st).sum()
+                phit = barrier(xt, st, ft) + nu * thetat
+                if np.isfinite(phit) and phit <= phi0 + 1e-8 * alpha * Dphi + 10.0 * np.finfo(float).eps * abs(phi0):
+                    accepted = True
+                    break
+                if ls == 0 and not soc_done and thetat >= theta0 and np.isfinite(thetat):
+                    # second-order correction: re-solve with the constraint values of the trial point added
+                    soc_done = True
+                    rhs2 = -np.concatenate((r_x, alpha * cE + cEt, alpha * r_I + (cIt - st)))
+                    sv = self._kkt_solve(B, SigL + SigU + delta_w, JE, JI, 1.0 / Sigs, rhs2, n, mE, mI, reuse=True)
+                    if sv is not None and np.all(np.isfinite(sv)):
+                        dx2 = sv[:n]
+                        ds2 = (sv[n + mE:] + lamI + mu / s) / Sigs
+                        a2 = min(max_step(np.where(hasL, x - xl, 1.0), np.where(hasL, dx2, 0.0), tau),
+                                 max_step(np.where(hasU, xu - x, 1.0), np.where(hasU, -dx2, 0.0), tau), max_step(s, ds2, tau))
+                        x2, s2 = x + a2 * dx2, s + a2 * ds2
+                        f2, cE2, cI2, _, _, _ = scaled(evaluate(x2, False))
+                        th2 = np.abs(cE2).sum() + np.abs(cI2 - s2).sum()
+                        phi2 = barrier(x2, s2, f2) + nu * th2
+                        if np.isfinite(phi2) and phi2 <= phi0 + 1e-8 * a2 * Dphi:
+                            step_dx, step_ds, alpha = dx2, ds2, a2
+                            xt, st = x2, s2
+                            accepted = True
+                            break
+                alpha *= 0.5
+                if alpha < 1e-12:
+                    break
+            if not accepted:
+                fails += 1
+                if len(B.S) > 0:  # a poor quasi-Newton model: drop the memory and try again from sigma I
+                    B.reset(B.sigma)
+                    continue
+                # least-norm step towards feasibility (what a restoration phase does first)
+                dxr = self._feasibility_step(JE, JI, cE, cI - s, n, mE, mI)
+                ok = False
+                if dxr is not None:
+                    a = min(max_step(np.where(hasL, x - xl, 1.0), np.where(hasL, dxr, 0.0), tau),
+                            max_step(np.where(hasU, xu - x, 1.0), np.where(hasU, -dxr, 0.0), tau))
+                    for _ in range(30):
+                        xt = x + a * dxr
+                        ft, cEt, cIt, _, _, _ = scaled(evaluate(xt, False))
+                        st = np.maximum(cIt, np.minimum(s, 1e-8 + mu))
+                        if np.abs(cEt).sum() + np.abs(cIt - st).sum() < (1.0 - 1e-4 * a) * theta0:
+                            ok = True
+                            break
+                        a *= 0.5
+                if not ok:
+                    status, message = 3, "line search and feasibility step failed"
+                    break
+                alpha, step_dx, step_ds = 1.0, xt - x, st - s
+                nu = 1.0
+            # ---- accept: primal and equality multipliers with alpha, bound multipliers with their own step ----
+            x_new, s_new = x + alpha * step_dx, s + alpha * step_ds
+            lamE_new = lamE + alpha * dlE
+            lamI_new = lamI + alpha * dlI
+            zL = zL + a_z * dzL
+            zU = zU + a_z * dzU
+            zs = zs + a_z * dzs
+            # keep the bound multipliers within a factor of the primal estimate mu / slack (IPOPT kappa_Sigma = 1e10)
+            ks = 1e10
+            zL = np.where(hasL, np.clip(zL, mu / (ks * np.maximum(x_new - xl, 1e-300)), ks * mu / np.maximum(x_new - xl, 1e-300)), 0.0)
+            zU = np.where(hasU, np.clip(zU, mu / (ks * np.maximum(xu - x_new, 1e-300)), ks * mu / np.maximum(xu - x_new, 1e-300)), 0.0)
+            zs = np.clip(zs, mu / (ks * s_new), ks * mu / s_new)
+            f_new, cE_new, cI_new, g_new, JE_new, JI_new = scaled(evaluate(x_new, True))
+            yk = (g_new + JE_new.T @ lamE_new + JI_new.T @ lamI_new) - (g + JE.T @ lamE_new + JI.T @ lamI_new)
+            B.update(x_new - x, yk)
+            x, s, lamE, lamI = x_new, s_new, lamE_new, lamI_new
+            f0, cE, cI, g, JE, JI = f_new, cE_new, cI_new, g_new, JE_new, JI_new
+
+        sol = Solution()
+        sol.xStar = xdict(x)
+        sol.fStar = f0 / df
+        sol.optTime = time.perf_counter() - t_start
+        sol.userObjTime, sol.userObjCalls = stat["obj_t"], stat["obj_n"]
+        sol.userSensTime, sol.userSensCalls = stat["sens_t"], stat["sens_n"]
+        sol.constr_violation = float(max(np.abs(cE / dE).max(initial=0.0), np.maximum(-(cI / dI), 0.0).max(initial=0.0)))
+        sol.dual_infeasibility = float(history[-1][2]) if history else float("nan")
+        sol.nit, sol.status, sol.message, sol.history = it, status, message, history
+        sol.line_search_failures = fails
+        sol.optInform = {"value": status, "text": message}
+        return sol
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _jac(s, groups, nrow, nvar, col0):
+        rows, cols, data = [], [], []
+        r0 = 0
+        for name, n, _, _, wrt, _ in groups:
+            for var, blk in s[name].items():
+                if wrt is not None and var not in wrt:
+                    continue
+                if isinstance(blk, dict):
+                    r, c, d = blk["coo"]
+                    r, c, d = np.asarray(r), np.asarray(c), np.asarray(d, dtype=float)
+                else:
+                    dense = np.atleast_2d(np.asarray(blk, dtype=float))
+                    r, c = np.nonzero(dense)
+                    d = dense[r, c]
+                rows.append(r + r0)
+                cols.append(c + col0[var])
+                data.append(d)
+            r0 += n
+        if not rows:
+            return sp.csr_matrix((nrow, nvar))
+        return sp.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(nrow, nvar)).tocsr()
+
+    @staticmethod
+    def _ls_multipliers(g, JE, JI, zL, zU, lamI):
+        """Least-squares estimate of the equality multipliers: min || g + JE^T lam + JI^T lamI - zL + zU ||."""
+        mE = JE.shape[0]
+        if mE == 0:
+            return np.zeros(0)
+        n = JE.shape[1]
+        K = sp.bmat([[sp.identity(n), JE.T], [JE, -1e-10 * sp.identity(mE)]], format="csc")
+        rhs = np.concatenate((-(g + JI.T @ lamI - zL + zU), np.zeros(mE)))
+        try:
+            lam = spla.splu(K).solve(rhs)[n:]
+        except RuntimeError:
+            return np.zeros(mE)
+        if not np.all(np.isfinite(lam)) or np.abs(lam).max() > 1e3:
+            return np.zeros(mE)
+        return lam
+
+    def _kkt_solve(self, B, diag_x, JE, JI, inv_sigs, rhs, n, mE, mI, reuse=False):
+        """Solve [[B + diag_x, JE^T, JI^T], [JE, -dc, 0], [JI, 0, -1/Sigma_s - dc]] v = rhs with B = sigma I - U M^-1 U^T:
+        sparse LU of the sigma I part, Woodbury for the rank-2k part."""
+        if not reuse:
+            dc = 1e-9
+            K0 = sp.bmat([[sp.diags(B.sigma + diag_x), JE.T, JI.T],
+                          [JE, -dc * sp.identity(mE), None],
+                          [JI, None, sp.diags(-(inv_sigs + dc))]], format="csc")
+            try:
+                self._lu = spla.splu(K0)
+            except RuntimeError:
+                return None
+            self._W = None
+            if B.S:
+                U, M = B.factors()
+                Ubar = np.vstack((U, np.zeros((mE + mI, U.shape[1]))))
+                KU = self._lu.solve(Ubar)
+                self._W = (Ubar, KU, M - Ubar.T @ KU)
+        v = self._lu.solve(rhs)
+        if self._W is not None:
+            Ubar, KU, C = self._W
+            try:
+                v = v + KU @ np.linalg.solve(C, Ubar.T @ v)
+            except np.linalg.LinAlgError:
+                return None
+        return v
+
+    @staticmethod
+    def _feasibility_step(JE, JI, cE, cIs, n, mE, mI):
+        J = sp.vstack((JE, JI)).tocsr()
+        c = np.concatenate((cE, cIs))
+        K = sp.bmat([[sp.identity(n), J.T], [J, -1e-8 * sp.identity(mE + mI)]], format="csc")
+        try:
+            v = spla.splu(K).solve(np.concatenate((np.zeros(n), -c)))
+        except RuntimeError:
+            return None
+        return v[:n] if np.all(np.isfinite(v)) else None

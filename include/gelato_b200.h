@@ -279,10 +279,12 @@ int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packe
  * alone (air dynamics + aero rows) | 3 the light Jacobian kernel alone. */
 int gelato_time_kernel(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
                        float* avg_ms);
-/* Measurement helper: enqueue exactly one kernel (which: 0, 2 or 3 as above) on `stream`, COO (packed = 0) or
- * packed output, not synchronised -- for benchmarks that bracket single kernels with their own CUDA events. */
-int gelato_launch_kernel_dev(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen,
-                             int32_t packed, void* stream);
+/* Measurement helper: enqueue exactly one kernel on `stream`, not synchronised -- for benchmarks that bracket single
+ * kernels with their own CUDA events.  which: 0, 2, 3 as above, 4 = the residual kernel's non-dynamics blocks
+ * (out_dev is g for 0 and 4); COO (packed = 0) or packed Jacobian output; g_dev != NULL makes a Jacobian kernel
+ * write the pair evaluation's defect rows as well. */
+int gelato_launch_kernel_dev(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, double* g_dev,
+                             int32_t n_scen, int32_t packed, void* stream);
 
 /* 1 if the library was compiled with unfused multiply-add on the device (the
  * build contract, checked by running a probe kernel); 0 otherwise. */
