@@ -16,9 +16,9 @@ An "eval" is one physics-leaf evaluation at one (node x perturbation column): se
 CompiledPlan.eval_counts / DESIGN.md.
 
   value   device-resident: x already in HBM, outputs stay in HBM, CUDA events.  A step is ONE pair
-          evaluation (gelato_eval_pair_packed_dev): the heavy Jacobian kernel, next to it the light
-          Jacobian kernel and the residual kernel's non-dynamics blocks; objfunc's dynamics rows come
-          out of the Jacobian blocks' centre columns.
+          evaluation (gelato_eval_pair_packed_dev) = ONE launch of the Jacobian kernel, whose blocks
+          also write objfunc's rows (dynamics defects from the centre columns, aero / event rows from
+          one more column at the pristine state, linear rows as blocks of their own).
   e2e     the same step through the host-buffer C-ABI call (gelato_eval_pair_packed): x from
           page-locked host memory -> device, the kernels, g and the packed Jacobian values back
           into host buffers as contiguous copies, wall clock.
@@ -397,9 +397,10 @@ def run_gelato(args):
     vd = torch.empty((B, P.n_vals), dtype=torch.float64, device="cuda")
     E.fill_template(vd.data_ptr(), B, st)
     gsep = torch.full((B, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
-    heavy_ms = timed_events(lambda: E.launch_kernel_dev(2, xd.data_ptr(), pd.data_ptr(), B, True, st, gd.data_ptr())) / args.steps \
+    jac_ms = timed_events(lambda: E.launch_kernel_dev(1, xd.data_ptr(), pd.data_ptr(), B, True, st)) / args.steps
+    heavy_ms = timed_events(lambda: E.launch_kernel_dev(2, xd.data_ptr(), pd.data_ptr(), B, True, st)) / args.steps \
         if E.n_jac_heavy else 0.0
-    light_ms = timed_events(lambda: E.launch_kernel_dev(3, xd.data_ptr(), pd.data_ptr(), B, True, st, gd.data_ptr())) / args.steps \
+    light_ms = timed_events(lambda: E.launch_kernel_dev(3, xd.data_ptr(), pd.data_ptr(), B, True, st)) / args.steps \
         if E.n_jac_light else 0.0
     res_ms = timed_events(lambda: E.launch_kernel_dev(0, xd.data_ptr(), gsep.data_ptr(), B, False, st)) / args.steps
     # the two callbacks as separate device calls with the reference's COO layout (what a per-callback driver gets)
@@ -461,23 +462,23 @@ def run_gelato(args):
     peak_clocks = sampler.summary(t_p0, t_p1)
     sampler.stop()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, heavy_ms, light_ms, res_ms, e2e_full_s * 1e3, sep_ms, e2e_upd_s * 1e3, sus_ms / n_sus],
-                     dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, heavy_ms, light_ms, res_ms, e2e_full_s * 1e3, sep_ms, e2e_upd_s * 1e3, sus_ms / n_sus,
+                      jac_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, heavy_ms, light_ms, res_ms, e2e_full_ms, sep_ms, e2e_upd_ms, sus_step_ms = [float(v) for v in t.cpu()]
+    dev_ms, e2e_ms, heavy_ms, light_ms, res_ms, e2e_full_ms, sep_ms, e2e_upd_ms, sus_step_ms, jac_ms = [float(v) for v in t.cpu()]
 
     if rank == 0:
         peak_hbm, peak_src = measured_peaks()
         K = args.steps
         rate = lambda ms_total: evals_step_rank * world * K / (ms_total * 1e-3)  # noqa: E731
-        # the heavy kernel: air dynamics blocks (14 columns + the quaternion variants of their nodes) and aero rows
-        flops_heavy = B * (FLOPS["air"] * 14 * ec["air_fd_nodes"] + FLOPS["quat"] * 7 * ec["air_free_nodes"]
-                           + FLOPS["aero"] * ec["aero_jac_evals"])
-        n_pack_heavy = None
-        bytes_heavy = B * (P.n_vars + n_pack) * 8.0  # reads x once, writes (at most) every packed value once
-        traffic, traffic_src = ncu_traffic("k_jacobian", E.n_jac_heavy * B)
-        ach_tf = flops_heavy / (heavy_ms * 1e-3) / 1e12 if heavy_ms else None
+        # the Jacobian kernel (one launch of `sens`): every finite-difference column of every role
+        flops_jac = B * (FLOPS["air"] * 14 * ec["air_fd_nodes"] + FLOPS["noair"] * 9 * (P.N - ec["air_fd_nodes"])
+                         + FLOPS["quat"] * 7 * ec["free_nodes"] + FLOPS["aero"] * ec["aero_jac_evals"]
+                         + FLOPS["evt"] * ec["evt_jac_evals"])
+        bytes_jac = B * (P.n_vars + n_pack) * 8.0  # reads x once, writes every packed value once
+        traffic, traffic_src = ncu_traffic("k_jacobian", E.n_jac_blocks * B)
+        ach_tf = flops_jac / (jac_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": rate(dev_ms), "unit": UNIT,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
@@ -500,28 +501,28 @@ def run_gelato(args):
             "sustained": {"value": evals_step_rank * world / (sus_step_ms * 1e-3), "ms_per_step": sus_step_ms, "steps": n_sus,
                           "seconds": sus_ms * 1e-3, "clocks": sus_clocks,
                           "note": "back-to-back pair evaluations, no L2 flush, one CUDA-event pair around all of them"},
-            "kernels": {"k_jacobian_ms": heavy_ms, "k_jacobian_light_ms": light_ms, "k_residuals_ms": res_ms,
-                        "note": "each kernel alone, CUDA events around the single launch, L2 flushed between launches; the "
-                                "Jacobian kernels as a pair evaluation runs them (packed output + defect rows); "
-                                "k_residuals with its dynamics blocks, which a pair evaluation does not launch",
+            "kernels": {"k_jacobian_ms": jac_ms, "k_residuals_ms": res_ms, "k_jacobian_pair_ms": dev_ms / K,
+                        "k_jacobian_heavy_roles_ms": heavy_ms, "k_jacobian_light_roles_ms": light_ms,
+                        "note": "each kernel alone, CUDA events around the single launch, L2 flushed between launches: "
+                                "k_jacobian = one `sens` (packed output), k_residuals = one `objfunc`, k_jacobian_pair = the "
+                                "Jacobian kernel of a pair evaluation (objfunc's rows written too: the timed step); heavy / "
+                                "light roles: role-subset builds of the Jacobian kernel on their blocks alone",
                         "separate_calls_coo_ms_per_step": sep_ms / K, "separate_calls_coo_value": rate(sep_ms)},
-            "roofline": {"kernel": "k_jacobian (heavy roles: air dynamics nodes + aero rows)", "bound": "fp64",
+            "roofline": {"kernel": "k_jacobian", "bound": "fp64",
                          "achieved": ach_tf, "peak": nofma_tf, "unit": "TFLOP/s",
-                         "frac": (ach_tf / nofma_tf) if (ach_tf and nofma_tf) else None,
+                         "frac": (ach_tf / nofma_tf) if nofma_tf else None,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_flops_per_launch": flops_heavy,
+                         "algorithmic_flops_per_launch": flops_jac,
                          "peak_source": "gelato_fp64_peak on this device in this run: unfused DMUL+DADD issue rate (fused "
                                         "multiply-add is off by the bit-parity contract); best of 6",
                          "peak_measurement": {"dmul_dadd_tflops": nofma_tf, "dfma_tflops": fma_tf, "clocks": peak_clocks},
-                         "frac_of_dfma_peak": (ach_tf / fma_tf) if (ach_tf and fma_tf) else None,
-                         "hbm": {"bound": "hbm", "achieved": bytes_heavy / (heavy_ms * 1e-3) / 1e9 if heavy_ms else None,
-                                 "peak": peak_hbm, "unit": "GB/s",
-                                 "frac": bytes_heavy / (heavy_ms * 1e-3) / 1e9 / peak_hbm if heavy_ms else None,
-                                 "algorithmic_bytes_per_launch": bytes_heavy, "peak_source": peak_src,
-                                 "note": "upper bound of the kernel's own bytes (x read once, every packed value written "
-                                         "once); the path is FP64-issue bound, ~30 flop per byte"}},
+                         "frac_of_dfma_peak": (ach_tf / fma_tf) if fma_tf else None,
+                         "hbm": {"bound": "hbm", "achieved": bytes_jac / (jac_ms * 1e-3) / 1e9,
+                                 "peak": peak_hbm, "unit": "GB/s", "frac": bytes_jac / (jac_ms * 1e-3) / 1e9 / peak_hbm,
+                                 "algorithmic_bytes_per_launch": bytes_jac, "peak_source": peak_src,
+                                 "note": "the kernel's own bytes (x read once, every packed value written once); the path is "
+                                         "FP64-issue bound, ~20 flop per byte"}},
         }
-        del n_pack_heavy
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, ec["objfunc"] + ec["sens"], P.N)
         if args.solve_scenarios > 0:

@@ -26,15 +26,14 @@
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-// One Jacobian evaluation = two kernels on two streams: the HEAVY roles (air dynamics nodes, aero rows -- the
-// pos_part / rotq_part code, ~1 kFLOP per column) and the LIGHT ones (vacuum dynamics, fallback, event rows).
-// Each instantiation contains only its own roles' code (instruction-cache footprint: ncu round 1 measured
-// 12 % i-cache misses with everything in one kernel) and its own register budget.
-#ifndef GJ_MIN_BLOCKS_HEAVY
-#define GJ_MIN_BLOCKS_HEAVY 3 /* 288 threads x 3 blocks: 27 warps per SM, up to 72 registers */
-#endif
-#ifndef GJ_MIN_BLOCKS_LIGHT
-#define GJ_MIN_BLOCKS_LIGHT 3
+// One Jacobian evaluation = ONE launch: every role's blocks, heavy (air dynamics nodes, aero rows: the pos_part /
+// rotq_part code, ~1 kFLOP per column) and light (vacuum dynamics, fallback, event rows) interleaved in the block
+// table so that FP64-issue-bound and latency-bound blocks share each SM.  (Round 2 first split the roles into two
+// kernels on two streams: they ran one after the other -- the first kernel fills every SM -- and the instruction
+// cache hit rate did not move; profiles/r02a_ab_probe.txt.)  The role-subset instantiations below exist for
+// measurements only (gelato_launch_kernel_dev).
+#ifndef GJ_MIN_BLOCKS
+#define GJ_MIN_BLOCKS 2 /* 448 threads x 2 blocks: 28 warps per SM, up to 72 registers */
 #endif
 template <int ROLES>
 __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* __restrict__ block_table, const int n_scen,
@@ -42,14 +41,13 @@ __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* 
                                               double* __restrict__ out_all, double* __restrict__ g_all) {
   __shared__ JacStore store;
   const JacScratch sm = jac_scratch(store);
-  // role-major launch order: block b of every scenario before block b+1 of any, so the blocks
-  // resident on an SM at one time mostly run the same role's code (instruction-cache locality)
+  // block-major launch order: block b of every scenario before block b+1 of any
   const int scen = blockIdx.x % n_scen;
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
   const double* x = x_all + (size_t)scen * P.n_vars;
   // COO output: vals[n_scen][n_vals] (constants pre-filled); packed output: [n_scen][n_pack]
   double* out = out_all + (size_t)scen * (size_t)(P.packed ? P.n_pack : P.n_vals);
-  // pair evaluation: the dynamics blocks also write their nodes' collocation defects (objfunc's rows)
+  // pair evaluation: every block also writes objfunc's rows of its nodes / constraint rows / events
   double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
   // which scenario's parameter blocks this batch slot uses (a coalesced subset of the configured scenarios)
   const int sid = scen_ids ? scen_ids[scen] : scen;
@@ -62,12 +60,18 @@ __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* 
   }
   jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 3, sm);
 }
-__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS_HEAVY)
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen, const int32_t* __restrict__ scen_ids,
            const double* __restrict__ x_all, double* __restrict__ out_all, double* __restrict__ g_all) {
+  jacobian_body<JR_ALL>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
+}
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
+k_jacobian_heavy(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+                 const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
+                 double* __restrict__ g_all) {
   jacobian_body<JR_HEAVY>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
 }
-__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS_LIGHT)
+__global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian_light(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
                  const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
                  double* __restrict__ g_all) {
@@ -167,10 +171,12 @@ struct GelatoPlan {
   int device = 0;
   PlanView view{};  // device pointers
   std::vector<void*> owned;
-  int32_t* jac_blocks = nullptr;  // heavy roles' blocks, then the light roles'
-  int n_jac_blocks = 0, n_jac_heavy = 0;
-  int32_t* res_blocks = nullptr;  // dynamics blocks, then aero / event / linear rows
-  int n_res_blocks = 0, n_res_dyn = 0;
+  int32_t* jac_blocks = nullptr;  // n_jac_main dynamics / aero / event blocks (roles interleaved), then the linear-row blocks
+  int n_jac_blocks = 0, n_jac_main = 0;
+  int32_t *jac_heavy = nullptr, *jac_light = nullptr;  // the same blocks by role group (measurements)
+  int n_jac_heavy = 0, n_jac_light = 0;
+  int32_t* res_blocks = nullptr;
+  int n_res_blocks = 0;
   // packed output (plan_host.h: build_packed_layout)
   long long n_pack = 0;
   std::vector<int64_t> pk_full, pk_src;
@@ -239,40 +245,21 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
   return GELATO_OK;
 }
 
-// One Jacobian evaluation: the heavy kernel on `st`, the light kernel (and, for a pair evaluation, the residual
-// kernel's aero / event / linear-row blocks) on `aux`, forked from and joined back into `st` with the two events.
-// g_dev != NULL: pair evaluation (the dynamics blocks write the collocation defects too).  packed: output layout.
-// (A two-launch variant of round 1 -- phase 0 barrier-free with pp | rq | q staged through L2 -- was 38 % slower
-// than the fused phases: profiles/r01i_split_ab.txt.)
+// One Jacobian evaluation on `st`.  g_dev != NULL: pair evaluation -- the blocks also write objfunc's rows (the
+// dynamics blocks their nodes' collocation defects, the aero / event blocks their rows at the pristine state) and the
+// linear-row blocks at the end of the table are launched too.  packed: output layout.
+// (Variants measured and dropped: phase 0 as its own launch with pp | rq | q staged through L2, 38 % slower,
+// profiles/r01i_split_ab.txt; role-specialised kernels on two streams, no overlap, profiles/r02a_ab_probe.txt.)
 static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* out_dev, double* g_dev, int n_scen, cudaStream_t st,
-                           cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, const int32_t* ids_dev, bool packed) {
+                           const int32_t* ids_dev, bool packed) {
   PlanView v = p->view;
   v.packed = packed ? 1 : 0;
-  const int n_light = p->n_jac_blocks - p->n_jac_heavy, n_rest = p->n_res_blocks - p->n_res_dyn;
-  const bool side = n_light > 0 || (g_dev && n_rest > 0);
-  if (side) {
-    CU(cudaEventRecord(ev_fork, st));
-    CU(cudaStreamWaitEvent(aux, ev_fork, 0));
-  }
-  if (p->n_jac_heavy > 0) {
-    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, ids_dev, x_dev, out_dev, g_dev);
-    p->launches++;
-  }
-  if (n_light > 0) {
-    k_jacobian_light<<<(unsigned)n_light * n_scen, GJ_THREADS, 0, aux>>>(v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS,
-                                                                         n_scen, ids_dev, x_dev, out_dev, g_dev);
-    p->launches++;
-  }
-  if (g_dev && n_rest > 0) {
-    k_residuals<<<(unsigned)n_rest * n_scen, GR_THREADS, 0, aux>>>(v, p->res_blocks + (size_t)p->n_res_dyn * BT_COLS, n_scen,
-                                                                  ids_dev, x_dev, g_dev);
+  const int nb = g_dev ? p->n_jac_blocks : p->n_jac_main;
+  if (nb > 0) {
+    k_jacobian<<<(unsigned)nb * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, ids_dev, x_dev, out_dev, g_dev);
     p->launches++;
   }
   CU(cudaGetLastError());
-  if (side) {
-    CU(cudaEventRecord(ev_join, aux));
-    CU(cudaStreamWaitEvent(st, ev_join, 0));
-  }
   return GELATO_OK;
 }
 
@@ -352,10 +339,16 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   // block tables
   HostTables ht;
   build_host_tables(d, ht);
+  const int32_t* tb = nullptr;
   p->n_jac_blocks = (int)(ht.jac_blocks.size() / BT_COLS);
   p->n_res_blocks = (int)(ht.res_blocks.size() / BT_COLS);
-  p->n_jac_heavy = ht.n_jac_heavy;
-  p->n_res_dyn = ht.n_res_dyn;
+  p->n_jac_main = ht.n_jac_main;
+  p->n_jac_heavy = (int)(ht.jac_heavy.size() / BT_COLS);
+  p->n_jac_light = (int)(ht.jac_light.size() / BT_COLS);
+  if ((rc = upload(p, ht.jac_heavy.data(), ht.jac_heavy.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  p->jac_heavy = const_cast<int32_t*>(tb);
+  if ((rc = upload(p, ht.jac_light.data(), ht.jac_light.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
+  p->jac_light = const_cast<int32_t*>(tb);
   {
     PackedLayout L;
     build_packed_layout(d, L);
@@ -373,7 +366,6 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
     p->pk_src.swap(L.src);
     p->pk_sgn.swap(L.sgn);
   }
-  const int32_t* tb = nullptr;
   if ((rc = upload(p, ht.jac_blocks.data(), ht.jac_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
   p->jac_blocks = const_cast<int32_t*>(tb);
   if ((rc = upload(p, ht.res_blocks.data(), ht.res_blocks.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
@@ -503,10 +495,10 @@ int32_t gelato_plan_n_blocks(const GelatoPlan* p, int which) {
   if (!p) return 0;
   switch (which) {
     case 0: return p->n_res_blocks;
-    case 1: return p->n_jac_blocks;
+    case 1: return p->n_jac_main;
     case 2: return p->n_jac_heavy;
-    case 3: return p->n_jac_blocks - p->n_jac_heavy;
-    default: return p->n_res_blocks - p->n_res_dyn;
+    case 3: return p->n_jac_light;
+    default: return p->n_jac_blocks;
   }
 }
 
@@ -538,10 +530,10 @@ int gelato_eval_pair_dev(GelatoPlan* p, const double* x_dev, double* g_dev, doub
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  // objfunc's rows come out of the Jacobian evaluation: the dynamics blocks hold the right-hand side of the
-  // pristine x as their centre column and add the D.X defects; the few aero / event / linear rows run as the
-  // residual kernel's non-dynamics blocks next to the light Jacobian kernel (no second pass over the physics)
-  return launch_jacobian(p, x_dev, vals_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
+  // objfunc's rows come out of the Jacobian launch: the dynamics blocks hold the right-hand side of the pristine
+  // x as their centre column and subtract it from the D.X products; aero and event blocks carry one more column
+  // at the pristine state; the linear rows are blocks of their own (no second pass over the physics)
+  return launch_jacobian(p, x_dev, vals_dev, g_dev, n_scen, st, nullptr, false);
 }
 
 int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
@@ -550,7 +542,7 @@ int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_de
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, true);
+  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, nullptr, true);
 }
 
 int gelato_fill_template(GelatoPlan* p, double* vals_dev, int32_t n_scen, void* stream) {
@@ -576,7 +568,7 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
   // the kernels rewrite every x-dependent slot and never touch the rest
-  return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
+  return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, nullptr, false);
 }
 
 static int ensure_staging(GelatoPlan* p, size_t n_scen) {
@@ -666,8 +658,7 @@ static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, p->d_ids,
                                                                                 p->d_x, p->d_g);
       p->launches++;
-    } else if ((rc = launch_jacobian(p, p->d_x, d_out, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join,
-                                     p->d_ids, false))) {
+    } else if ((rc = launch_jacobian(p, p->d_x, d_out, nullptr, n_scen, p->stream, p->d_ids, false))) {
       return rc;
     }
     CU(cudaGetLastError());
@@ -838,8 +829,7 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
     CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     CU(cudaEventRecord(L.ev_h2d, L.stream));
     // g != NULL: pair evaluation, the residual rows come out of the same launches
-    if ((rc = launch_jacobian(p, dx, dvals, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join, ids, false)))
-      return rc;
+    if ((rc = launch_jacobian(p, dx, dvals, g ? dg : nullptr, ns, L.stream, ids, false))) return rc;
     if (g) {  // its copy travels on the side stream, next to the Jacobian's transfers
       CU(cudaEventRecord(L.ev_g, L.stream));
       CU(cudaStreamWaitEvent(L.pair_stream, L.ev_g, 0));
@@ -969,8 +959,7 @@ static int eval_packed(GelatoPlan* p, const double* x, double* g, double* packed
     if (k > 0) CU(cudaStreamWaitEvent(L.stream, p->lanes[k - 1].ev_h2d, 0));  // uploads one after the other (and after the ids)
     CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     CU(cudaEventRecord(L.ev_h2d, L.stream));
-    if ((rc = launch_jacobian(p, dx, dpk, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join,
-                              need_ids ? p->d_pids + s0 : nullptr, true)))
+    if ((rc = launch_jacobian(p, dx, dpk, g ? dg : nullptr, ns, L.stream, need_ids ? p->d_pids + s0 : nullptr, true)))
       return rc;
     // both results on the lane's copy stream, after everything of the slice has been computed
     CU(cudaEventRecord(L.ev_kernel, L.stream));
@@ -1104,19 +1093,16 @@ int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, doub
   v.packed = packed ? 1 : 0;
   if (which == 0) {
     k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(v, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
+  } else if (which == 1) {
+    return launch_jacobian(p, x_dev, out_dev, g_dev, n_scen, st, nullptr, packed != 0);
   } else if (which == 2) {
     if (p->n_jac_heavy == 0) return fail(GELATO_ERR_ARG, "the plan has no heavy blocks");
-    k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, nullptr, x_dev, out_dev, g_dev);
+    k_jacobian_heavy<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_heavy, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else if (which == 3) {
-    if (p->n_jac_blocks == p->n_jac_heavy) return fail(GELATO_ERR_ARG, "the plan has no light blocks");
-    k_jacobian_light<<<(unsigned)(p->n_jac_blocks - p->n_jac_heavy) * n_scen, GJ_THREADS, 0, st>>>(
-        v, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, g_dev);
-  } else if (which == 4) {  // the residual kernel's non-dynamics blocks (what a pair evaluation launches of it)
-    if (p->n_res_blocks == p->n_res_dyn) return fail(GELATO_ERR_ARG, "the plan has no non-dynamics residual blocks");
-    k_residuals<<<(unsigned)(p->n_res_blocks - p->n_res_dyn) * n_scen, GR_THREADS, 0, st>>>(
-        v, p->res_blocks + (size_t)p->n_res_dyn * BT_COLS, n_scen, nullptr, x_dev, out_dev);
+    if (p->n_jac_light == 0) return fail(GELATO_ERR_ARG, "the plan has no light blocks");
+    k_jacobian_light<<<(unsigned)p->n_jac_light * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_light, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else {
-    return fail(GELATO_ERR_ARG, "which must be 0, 2, 3 or 4");
+    return fail(GELATO_ERR_ARG, "which must be 0, 1, 2 or 3");
   }
   p->launches++;
   CU(cudaGetLastError());
@@ -1135,18 +1121,16 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
     if (which == 0) {
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
     } else if (which == 1) {  // the whole Jacobian evaluation (heavy and light kernels)
-      if ((rc = launch_jacobian(p, x_dev, out_dev, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join, nullptr,
-                                false)))
-        return rc;
+      if ((rc = launch_jacobian(p, x_dev, out_dev, nullptr, n_scen, p->stream, nullptr, false))) return rc;
       continue;
-    } else if (which == 2) {  // the heavy kernel alone (air dynamics + aero rows): the roofline's kernel
+    } else if (which == 2) {  // the heavy roles' blocks alone (air dynamics + aero rows)
       if (p->n_jac_heavy > 0)
-        k_jacobian<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_blocks, n_scen, nullptr, x_dev,
-                                                                                  out_dev, nullptr);
-    } else {  // the light kernel alone
-      if (p->n_jac_blocks > p->n_jac_heavy)
-        k_jacobian_light<<<(unsigned)(p->n_jac_blocks - p->n_jac_heavy) * n_scen, GJ_THREADS, 0, p->stream>>>(
-            p->view, p->jac_blocks + (size_t)p->n_jac_heavy * BT_COLS, n_scen, nullptr, x_dev, out_dev, nullptr);
+        k_jacobian_heavy<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_heavy, n_scen, nullptr,
+                                                                                        x_dev, out_dev, nullptr);
+    } else {  // the light roles' blocks alone
+      if (p->n_jac_light > 0)
+        k_jacobian_light<<<(unsigned)p->n_jac_light * n_scen, GJ_THREADS, 0, p->stream>>>(p->view, p->jac_light, n_scen, nullptr,
+                                                                                        x_dev, out_dev, nullptr);
     }
     p->launches++;
   }

@@ -26,30 +26,35 @@
 #include "../../include/gelato_b200.h"
 #include "physics.h"
 
-/* ---- launch geometry (overridable with -D for tuning experiments: tools/ab_bench.sh) -------------
- * One block = 9 warps.  A "heavy" block (air dynamics nodes, aero constraint rows) takes 20 nodes: its 100
- * position items fill warps 0-3 and its 140 rotation + 20 quaternion items warps 4-8, ONE long item per
- * thread, so no warp waits at the phase barrier for a neighbour that has a second or third item to go
- * (round 1 ran 32 nodes on 8 warps: 5 warps one position item each, 3 warps three rounds of rotation items;
- * A/B in profiles/r02a_ab.txt).  Every item loop below strides by its thread-group size, so any geometry
- * that satisfies the static_asserts is valid. */
+/* ---- launch geometry (each overridable with -D for tuning experiments: tools/ab_probe.sh) ---------
+ * One Jacobian block = 14 warps.  A block of 32 air nodes has 160 position items (5 full warps), 224
+ * rotation items (7 full warps) and 32 quaternion items (1 warp): ONE long item per thread, every warp full;
+ * the 14th warp computes the D.X products of a pair evaluation meanwhile.  Its 448 column items are one
+ * round of the whole block.  A block of 32 aero rows in a pair evaluation carries a sixth position / eighth
+ * rotation variant (the pristine state, for objfunc's row): 192 + 256 items = the 14 warps again.
+ * (Measured against 8 warps x 32 nodes -- round 1: three rounds of rotation items on 3 warps --, 9 warps x 20
+ * nodes, 7 warps x 16 nodes, 16 warps x 32 nodes: profiles/r02a_ab_probe.txt.)  Every item loop strides by
+ * its thread-group size, so any geometry that satisfies the static_asserts is valid. */
 #ifndef GJ_THREADS
-#define GJ_THREADS 288   /* Jacobian kernel block */
+#define GJ_THREADS 448   /* Jacobian kernel block */
 #endif
 #ifndef GJ_NODES
-#define GJ_NODES 20      /* aero rows per Jacobian block */
+#define GJ_NODES 32      /* aero rows per Jacobian block */
 #endif
 #ifndef GD_NODES
-#define GD_NODES 20      /* air dynamics nodes per Jacobian block */
+#define GD_NODES 32      /* air dynamics nodes per Jacobian block */
 #endif
 #ifndef GJ_A_THREADS
-#define GJ_A_THREADS 128 /* threads [0, 128): position items; the rest: rotation and quaternion items */
+#define GJ_A_THREADS 160 /* air dynamics blocks: threads [0, 160) position items; the rest rotation / quaternion / D.X items */
+#endif
+#ifndef GJA_A_THREADS
+#define GJA_A_THREADS 192 /* aero blocks: threads [0, 192) position items; the rest rotation items */
 #endif
 #ifndef GN_NODES
-#define GN_NODES 32      /* no-air nodes per Jacobian block (9 column items each = 288) */
+#define GN_NODES 32      /* no-air nodes per Jacobian block */
 #endif
 #ifndef GN_A_THREADS
-#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items, the rest quaternion items */
+#define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items, the rest quaternion and D.X items */
 #endif
 #ifndef GJ_EVT
 #define GJ_EVT (GJ_THREADS / 16) /* event jobs per Jacobian block (16 lanes each) */
@@ -61,16 +66,19 @@
 #define GR_NODES 64    /* nodes per residual block */
 #define NPV 5          /* distinct positions over the columns of one node */
 #define NRV 7          /* distinct (position, time) pairs */
+#define NPVA 6         /* aero rows: + the pristine position (objfunc's row in a pair evaluation) */
+#define NRVA 8         /* aero rows: + the pristine (position, time) */
 #define NQV 8          /* quaternion-kinematics variants: centre, q x4, u x2 (after the velocity pass), pristine */
 
 static_assert(GJ_A_THREADS % 32 == 0 && GJ_A_THREADS < GJ_THREADS && GJ_THREADS % 32 == 0, "phase-0 thread groups are whole warps");
+static_assert(GJA_A_THREADS % 32 == 0 && GJA_A_THREADS < GJ_THREADS, "phase-0 thread groups are whole warps");
 static_assert(GN_A_THREADS % 32 == 0 && GN_A_THREADS < GJ_THREADS, "no-air thread groups are whole warps");
 static_assert(GG_NODES * 16 <= GJ_THREADS && GJ_EVT * 16 <= GJ_THREADS, "lane maps");
 #define GJ_MAX2(a, b) ((a) > (b) ? (a) : (b))
 #define GJ_FQ_NODES GJ_MAX2(GJ_MAX2(GN_NODES, GD_NODES), GG_NODES) /* nodes the f and q arrays hold */
 #define GJ_PR_NODES GJ_MAX2(GJ_NODES, GD_NODES)                    /* nodes (or aero rows) the pp and rq arrays hold */
 static_assert(GJ_THREADS * 3 <= GJ_FQ_NODES * 14 * 3, "event jobs keep 3 values per thread in f");
-static_assert(GN_NODES * NPV * 3 <= GJ_PR_NODES * NPV * 8, "no-air gravity items fit the pp array");
+static_assert(GN_NODES * NPV * 3 <= GJ_PR_NODES * NPVA * 8, "no-air gravity items fit the pp array");
 static_assert(GR_THREADS == 2 * GR_NODES, "residual phase 0 uses two threads per node");
 
 /* block roles */
@@ -124,10 +132,11 @@ struct PlanView {
   const int64_t* evt_pk;  /* [n_evt][GE_I64_COLS] */
 };
 
-/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 32 KB), a plain struct
+/* working arrays of one Jacobian block: shared memory in the kernel (JacStore, 46 KB), a plain struct
  * in the host emulator; the jobs reach them through the pointers of JacScratch. */
-#define GJ_PP_LEN (GJ_PR_NODES * NPV * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
-#define GJ_RQ_LEN (GJ_PR_NODES * NRV * RQ_COLS) /* rotq_part per (node, rotation variant) */
+#define GJ_PP_LEN (GJ_PR_NODES * NPVA * PP_COLS) /* pos_part per (node, position variant); no-air: gravity[3] */
+#define GJ_RQ_LEN (GJ_PR_NODES * NRVA * RQ_COLS) /* rotq_part per (node, rotation variant) */
+#define GJ_LH_LEN (GJ_FQ_NODES * 11)             /* D.X per (node, state column): position 3 | quaternion 4 | velocity 3 | mass */
 #define GJ_F_LEN (GJ_FQ_NODES * 14 * 3)         /* leaf value per (node, column lane); events: per thread */
 #define GJ_Q_LEN (GJ_FQ_NODES * NQV * 4)        /* quaternion kinematics per (node, variant) */
 struct JacStore {
@@ -135,16 +144,18 @@ struct JacStore {
   double rq[GJ_RQ_LEN];
   double q[GJ_Q_LEN];
   double f[GJ_F_LEN];
+  double lh[GJ_LH_LEN];
 };
 struct JacScratch {
   double* pp;
   double* rq;
   double* q;
   double* f;
+  double* lh;
 };
 P_HD JacScratch jac_scratch(JacStore& st) {
   JacScratch sm;
-  sm.pp = st.pp; sm.rq = st.rq; sm.q = st.q; sm.f = st.f;
+  sm.pp = st.pp; sm.rq = st.rq; sm.q = st.q; sm.f = st.f; sm.lh = st.lh;
   return sm;
 }
 /* shared memory of one residual block */
@@ -413,13 +424,31 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   }
 }
 
-P_HD void dyn_res_item(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
-                       const double* f3, const double* q4v);
+P_HD void dyn_lh_item(const PlanView& P, const double* x, const NodeRef& nr, int grp, double* lh);
+P_HD void dyn_res_finish(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
+                         const double* lh, const double* f3, const double* q4v);
+
+/* pair evaluation, phase 0: the D.X products of the block's nodes, by the threads the long items leave idle
+ * (`idx` of `n_group` threads, the first `n_busy` of which have a long item): hidden behind pos_part / rotq_part */
+P_HD void dyn_lh_block(const PlanView& P, const double* x, int start, int count, int idx, int n_group, int n_busy,
+                       const JacScratch& sm) {
+  const int spare = n_group - n_busy;
+  int first = idx, step = n_group;
+  if (spare > 0) {
+    if (idx < n_busy) return;
+    first = idx - n_busy;
+    step = spare;
+  }
+  for (int item = first; item < count * 4; item += step) {
+    const int grp = item / count, nl = item - grp * count;
+    dyn_lh_item(P, x, jac_node(P, start + nl), grp, sm.lh + nl * 11);
+  }
+}
 
 /* all 15 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*NQV + var)*4];
- * with g != NULL (pair evaluation) also the collocation defects of the same nodes, from the centre column's
- * right-hand side (pristine x) and the pristine quaternion variant -- objfunc's rows without a second pass
- * over the physics */
+ * with g != NULL (pair evaluation) also the collocation defects of the same nodes: the D.X of phase 0 minus
+ * the centre column's right-hand side (pristine x) / the pristine quaternion variant -- objfunc's rows without
+ * a second pass over the physics */
 P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
                             int tid, int nthreads, const JacScratch& sm) {
   /* lane-major items: neighbouring threads run the same column's formula on neighbouring nodes */
@@ -435,7 +464,7 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
     for (int item = nthreads - 1 - tid; item < count * 4; item += nthreads) {
       const int grp = item / count, nl = item - grp * count;
       const NodeRef nr = jac_node(P, start + nl);
-      dyn_res_item(P, scen, x, g, nr, grp, sm.f + (nl * 14) * 3, sm.q + (nl * NQV + 7) * 4);
+      dyn_res_finish(P, scen, x, g, nr, grp, sm.lh + nl * 11, sm.f + (nl * 14) * 3, sm.q + (nl * NQV + 7) * 4);
     }
   }
 }
@@ -467,8 +496,10 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       }
       return;
     }
-    /* rotation items first (whole warps of them), then one quaternion item per node */
-    for (int item = tid - GJ_A_THREADS; item < count * (NRV + 1); item += GJ_THREADS - GJ_A_THREADS) {
+    /* rotation items first (whole warps of them), then one quaternion item per node; the threads left over
+     * compute the D.X products of a pair evaluation */
+    const int nb = GJ_THREADS - GJ_A_THREADS, idx = tid - GJ_A_THREADS;
+    for (int item = idx; item < count * (NRV + 1); item += nb) {
       if (item >= count * NRV) {
         const int qn = item - count * NRV;
         const NodeRef nr = jac_node(P, start + qn);
@@ -485,6 +516,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
       const double tn = time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
     }
+    if (g) dyn_lh_block(P, x, start, count, idx, nb, count * (NRV + 1), sm);
   } else if (phase == 2) {
     for (int item = tid; item < count * 14; item += GJ_THREADS) {
       const int nl = item / 14, lane = item - nl * 14;
@@ -531,10 +563,12 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
         o[2] = gr.z;
       }
     } else {
-      for (int qn = tid - GN_A_THREADS; qn < count; qn += GJ_THREADS - GN_A_THREADS) {
+      const int nb = GJ_THREADS - GN_A_THREADS, idx = tid - GN_A_THREADS;
+      for (int qn = idx; qn < count; qn += nb) {
         const NodeRef nr = jac_node(P, start + qn);
         if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * NQV * 4);
       }
+      if (g) dyn_lh_block(P, x, start, count, idx, nb, count, sm);
     }
   } else if (phase == 2) {
     for (int item = tid; item < count * 9; item += GJ_THREADS) {
@@ -594,12 +628,14 @@ P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* va
       o[2] = f.z;
     }
     if (lane == 15 && !hold) dyn_quat_variants(P, x, nr, un, sm.q + nl * NQV * 4);
+    if (lane == 14 && g)
+      for (int grp = 0; grp < 4; grp++) dyn_lh_item(P, x, nr, grp, sm.lh + nl * 11);
   } else if (phase == 3) {
     const double* fc = sm.f + (nl * 14) * 3;
     const double* qc = sm.q + (nl * NQV) * 4;
     if (lane == 15) {
       if (g)
-        for (int grp = 0; grp < 4; grp++) dyn_res_item(P, scen, x, g, nr, grp, fc, qc + 7 * 4);
+        for (int grp = 0; grp < 4; grp++) dyn_res_finish(P, scen, x, g, nr, grp, sm.lh + nl * 11, fc, qc + 7 * 4);
       return;
     }
     dyn_scatter(P, scen, x, vals, nr, lane, fc, fc + (lane < 14 ? lane : 0) * 3, qc, qc + (lane < 7 ? lane : 0) * 4);
@@ -688,51 +724,56 @@ P_HD void dx_dot(const double* Drow, const double* xrows, int n1, double* acc) {
   }
 }
 
-/* one (node, state array) item of the collocation defects: D.X minus right-hand side.  grp 0 position |
- * 1 quaternion | 2 velocity | 3 mass; f3 / q4v: the node's velocity right-hand side and quaternion kinematics
- * at the pristine x.  Shared by the residual kernel (phase 2) and the Jacobian kernel's pair mode. */
-P_HD void dyn_res_item(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
-                       const double* f3, const double* q4v) {
+/* The collocation defects of one (node, state array) item in two steps -- D.X (dyn_lh_item), then minus the
+ * right-hand side (dyn_res_finish) -- so that the Jacobian kernel can compute the products while its long
+ * phase-0 items run.  grp 0 position | 1 quaternion | 2 velocity | 3 mass; lh[11] = the node's products, laid
+ * out position 3 | quaternion 4 | velocity 3 | mass 1; f3 / q4v: the node's velocity right-hand side and
+ * quaternion kinematics at the pristine x.  Rows that are plain differences (engine off, held attitude) take
+ * the difference as their "product".  Shared by the residual kernel (phase 2) and the pair evaluation. */
+P_HD void dyn_lh_item(const PlanView& P, const double* x, const NodeRef& nr, int grp, double* lh) {
+  const int n = nr.n, xa = nr.si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
+  const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
+  if (grp == 3) { /* mass: con_dynamics.py:53-61 */
+    if (flags & GSF_ENGINE_ON) dx_dot<1>(Drow, x + xa, n + 1, lh + 10);
+    else lh[10] = x[row] - x[xa];
+  } else if (grp == 0) { /* position: :146 */
+    dx_dot<3>(Drow, x + P.off_pos + 3 * xa, n + 1, lh);
+  } else if (grp == 2) { /* velocity: :256 */
+    dx_dot<3>(Drow, x + P.off_vel + 3 * xa, n + 1, lh + 7);
+  } else if (flags & GSF_HOLD) { /* quaternion: :520-531 */
+    for (int k = 0; k < 4; k++) lh[3 + k] = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
+  } else {
+    dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh + 3);
+  }
+}
+P_HD void dyn_res_finish(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
+                         const double* lh, const double* f3, const double* q4v) {
   const Units un = scen_units(P, scen);
   const double ut = un.t;
   const int32_t* si = nr.si;
-  const int n = nr.n, xa = si[GS_XA], flags = nr.flags, j = nr.j, row = nr.row;
+  const int flags = nr.flags, j = nr.j, row = nr.row;
   const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double dt = tf - to;
-  const double* Drow = P.d_pool + nr.d_off + (long long)j * (n + 1);
-  if (grp == 3) { /* mass: con_dynamics.py:53-61 */
-    double r;
-    if (flags & GSF_ENGINE_ON) {
-      double lh[1];
-      dx_dot<1>(Drow, x + xa, n + 1, lh);
-      const double rh = gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
-      r = lh[0] - rh;
-    } else {
-      r = x[row] - x[xa];
-    }
+  if (grp == 3) {
+    double r = lh[10];
+    if (flags & GSF_ENGINE_ON) r = r - gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
     g[si[GS_R_MASS] + j] = r;
-  } else if (grp == 0) { /* position: :146-150 */
-    double lh[3];
-    dx_dot<3>(Drow, x + P.off_pos + 3 * xa, n + 1, lh);
+  } else if (grp == 0) { /* :147-150 */
     for (int k = 0; k < 3; k++) {
       const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
       g[si[GS_R_POS] + 3 * j + k] = lh[k] - rh;
     }
-  } else if (grp == 2) { /* velocity: :256-287 */
-    double lh[3];
-    dx_dot<3>(Drow, x + P.off_vel + 3 * xa, n + 1, lh);
+  } else if (grp == 2) { /* :258-287 */
     for (int k = 0; k < 3; k++) {
       const double rh = f3[k] * dt * ut / 2.0;
-      g[si[GS_R_VEL] + 3 * j + k] = lh[k] - rh;
+      g[si[GS_R_VEL] + 3 * j + k] = lh[7 + k] - rh;
     }
-  } else if (flags & GSF_HOLD) { /* quaternion: :520-531 */
-    for (int k = 0; k < 4; k++) g[si[GS_R_QUAT] + 4 * j + k] = x[P.off_quat + 4 * row + k] - x[P.off_quat + 4 * xa + k];
-  } else {
-    double lh[4];
-    dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh);
+  } else if (flags & GSF_HOLD) {
+    for (int k = 0; k < 4; k++) g[si[GS_R_QUAT] + 4 * j + k] = lh[3 + k];
+  } else { /* :525-530 */
     for (int k = 0; k < 4; k++) {
       const double rh = q4v[k] * dt * ut / 2.0;
-      g[si[GS_R_QUAT] + 4 * j + k] = lh[k] - rh;
+      g[si[GS_R_QUAT] + 4 * j + k] = lh[3 + k] - rh;
     }
   }
 }
@@ -744,7 +785,10 @@ P_HD void dyn_res_phase2(const PlanView& P, int scen, const double* x, double* g
                          int nthreads, const ResScratch& sm) {
   for (int item = tid; item < count * 4; item += nthreads) {
     const int grp = item / count, nl = item - grp * count;
-    dyn_res_item(P, scen, x, g, res_node(P, g0 + nl), grp, sm.f[nl], sm.q[nl]);
+    const NodeRef nr = res_node(P, g0 + nl);
+    double lh[11];
+    dyn_lh_item(P, x, nr, grp, lh);
+    dyn_res_finish(P, scen, x, g, nr, grp, lh, sm.f[nl], sm.q[nl]);
   }
 }
 
@@ -789,41 +833,56 @@ P_HD void aero_base(const PlanView& P, const double* x, int sec, int row, double
   }
 }
 
-P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals, int start, int count, int tid,
+P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count, int tid,
                      int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = P.un.dx;
+  /* pair evaluation (g != NULL): one more position / rotation variant and one more column per row, evaluated at
+   * the PRISTINE state -- the value objfunc returns for the row (con_aero.py:89-248), out of the same launch */
+  const int npv = g ? NPVA : NPV, nrv = g ? NRVA : NRV;
   if (phase == 0) {
-    const bool is_a = tid < GJ_A_THREADS;
-    const int per = is_a ? NPV : NRV;
-    const int step = is_a ? GJ_A_THREADS : GJ_THREADS - GJ_A_THREADS;
-    for (int item = is_a ? tid : tid - GJ_A_THREADS; item < count * per; item += step) {
+    const bool is_a = tid < GJA_A_THREADS;
+    const int per = is_a ? npv : nrv;
+    const int step = is_a ? GJA_A_THREADS : GJ_THREADS - GJA_A_THREADS;
+    for (int item = is_a ? tid : tid - GJA_A_THREADS; item < count * per; item += step) {
       const int nl = item / per, var = item - nl * per;
       const AeroRec ar = P.aero_rows[start + nl];
       double v[10], to, tf, p[3];
-      aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
-      if (is_a) {
-        pos_variant(v, var, dx, p);
-        const Tables tb = scen_tables(P, scen);
-        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, 0, sm.pp + (nl * NPV + var) * PP_COLS);
+      const bool pristine = var == (is_a ? NPV : NRV);
+      if (pristine) {
+        aero_load(P, x, ar.row, v);
+        to = x[P.off_t + ar.sec];
+        tf = x[P.off_t + ar.sec + 1];
       } else {
-        pos_variant(v, rv_pv(var), dx, p);
+        aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
+      }
+      if (is_a) {
+        pos_variant(v, pristine ? 0 : var, dx, p);
+        const Tables tb = scen_tables(P, scen);
+        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, 0, sm.pp + (nl * NPVA + var) * PP_COLS);
+      } else {
+        pos_variant(v, pristine ? 0 : rv_pv(var), dx, p);
         if (var == 5) to = to + dx;
         if (var == 6) tf = tf + dx;
         const double tn = time_node(P.tau_pool + ar.tau_off, ar.r, to, tf);
-        rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRV + var) * RQ_COLS);
+        rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn * un.t, sm.rq + (nl * NRVA + var) * RQ_COLS);
       }
     }
   } else if (phase == 2) {
-    for (int item = tid; item < count * 13; item += GJ_THREADS) {
-      const int nl = item / 13, lane = item - nl * 13;
+    const int nlane = g ? 14 : 13;
+    for (int item = tid; item < count * nlane; item += GJ_THREADS) {
+      const int nl = item / nlane, lane = item - nl * nlane;
       const AeroRec ar = P.aero_rows[start + nl];
       const int kind = ar.kind, job = ar.job;
       const bool has_quat = kind != 1;
       if (!has_quat && lane >= 7 && lane <= 10) continue;
       double v[10], to, tf;
-      aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
-      if (lane != 0) { /* the gradient works on a copy: columns leave residue inside the copy only */
+      if (lane == 13) {
+        aero_load(P, x, ar.row, v);
+      } else {
+        aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
+      }
+      if (lane != 0 && lane != 13) { /* the gradient works on a copy: columns leave residue inside the copy only */
         const int pidx = (lane <= 10) ? lane - 1 : 10;
         for (int w = 0; w < 10; w++) {
           if (!has_quat && w >= 6) continue;
@@ -832,8 +891,8 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
         }
       }
       double rp[RP_COLS];
-      const double* pp = sm.pp + (nl * NPV + aero_lane_pv(lane)) * PP_COLS;
-      rot_wind(sm.rq + (nl * NRV + aero_lane_rv(lane)) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
+      const double* pp = sm.pp + (nl * NPVA + (lane == 13 ? NPV : aero_lane_pv(lane))) * PP_COLS;
+      rot_wind(sm.rq + (nl * NRVA + (lane == 13 ? NRV : aero_lane_rv(lane))) * RQ_COLS, pp[PP_WIND_N], pp[PP_WIND_E], rp);
       const Vec3 pos = v3(v[0] * un.pos, v[1] * un.pos, v[2] * un.pos);
       const Vec3 vel = v3(v[3] * un.vel, v[4] * un.vel, v[5] * un.vel);
       const double val = aero_quantity_col(kind, pos, vel, q4(v[6], v[7], v[8], v[9]),
@@ -855,6 +914,11 @@ P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals,
       else if (lane == 11) vals[aj[GA_J_T] + r] = gval;
       else vals[aj[GA_J_T] + nk + r] = gval;
     }
+    if (g)
+      for (int nl = GJ_THREADS - 1 - tid; nl < count; nl += GJ_THREADS) { /* 1 - f: con_aero.py:89-248 */
+        const AeroRec ar = P.aero_rows[start + nl];
+        g[ar.row0 + ar.r] = 1.0 - sm.f[(nl * 14 + 13) * 3];
+      }
   }
 }
 
@@ -932,7 +996,7 @@ P_HD void evt_res(const PlanView& P, int scen, const double* x, double* g, int j
   EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t_e);
   if (type == GE_TERM) {
     for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o.v[r];
-  } else if (type == GE_USER_PERIGEE) {
+  } else if (type >= GE_USER_PERIGEE) {
     g[ei[GE_ROW]] = o.v[0];
   } else {
     g[ei[GE_ROW]] = evt_form_value(ei[GE_FORM], o.v[ei[GE_COMP]], ef[GE_REF], ef[GE_DEN]);
@@ -949,11 +1013,20 @@ P_HD int evt_n_lanes(int type) {
   return type == GE_IIP ? 8 : (type == GE_TERM ? 7 : (type == GE_USER_PERIGEE ? 13 : 5));
 }
 
-P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, const JacScratch& sm) {
+P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, bool pair, const JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
   const int type = ei[GE_TYPE], srow = ei[GE_SROW];
+  if (lane == 15) { /* pair evaluation: the leaf at the PRISTINE state -- objfunc's row (evt_res) */
+    if (!pair) return;
+    const double t0 = (ei[GE_TIDX] >= 0) ? x[P.off_t + ei[GE_TIDX]] : 0.0;
+    EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t0);
+    sm.f[3 * tid + 0] = o.v[0];
+    sm.f[3 * tid + 1] = o.v[1];
+    sm.f[3 * tid + 2] = o.v[2];
+    return;
+  }
   if (lane >= evt_n_lanes(type)) return;
   const double dx = P.un.dx;
   double s[6]; /* pos[3], vel[3] base state = r^rc(x) */
@@ -992,12 +1065,24 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
   sm.f[3 * tid + 2] = o.v[2];
 }
 
-P_HD void evt_jac_phase2(const PlanView& P, double* vals, int job, int tid, const JacScratch& sm) {
+P_HD void evt_jac_phase2(const PlanView& P, double* vals, double* g, int job, int tid, const JacScratch& sm) {
   const int lane = tid & 15;
   const int32_t* ei = P.evt_i32 + job * GE_I32_COLS;
   const int64_t* ej = (P.packed ? P.evt_pk : P.evt_i64) + job * GE_I64_COLS;
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
   const int type = ei[GE_TYPE];
+  if (lane == 15) { /* objfunc's row(s) of this job, as evt_res writes them */
+    if (!g) return;
+    const double* o = sm.f + 3 * tid;
+    if (type == GE_TERM) {
+      for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o[r];
+    } else if (type >= GE_USER_PERIGEE) {
+      g[ei[GE_ROW]] = o[0];
+    } else {
+      g[ei[GE_ROW]] = evt_form_value(ei[GE_FORM], o[ei[GE_COMP]], ef[GE_REF], ef[GE_DEN]);
+    }
+    return;
+  }
   if (lane == 0 || lane >= evt_n_lanes(type)) return;
   const double dx = P.un.dx;
   const int c = tid & ~15;
@@ -1040,29 +1125,33 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 /* ========================================================================= */
 /* Block dispatch.  Jacobian blocks run GJ_PHASES phases with a block barrier  */
 /* between them; residual blocks run three (only the dynamics role uses 0, 2).  */
-/* The Jacobian evaluation is two kernels (gelato_b200.cu): the HEAVY roles     */
-/* (air dynamics, aero rows: pos_part / rotq_part code) and the LIGHT ones      */
-/* (vacuum dynamics, fallback, event rows), each compiled with only its own     */
-/* roles' code: ROLES is the mask of roles an instantiation contains.           */
+/* ROLES is the mask of roles an instantiation of the Jacobian kernel contains  */
+/* (the shipped kernel: all of them; subsets exist for measurements).           */
 /* ========================================================================= */
 #define JR_HEAVY ((1 << BR_DYN_AIR) | (1 << BR_AERO))
-#define JR_LIGHT ((1 << BR_DYN_NOAIR) | (1 << BR_DYN_GEN) | (1 << BR_EVT))
+#define JR_LIGHT ((1 << BR_DYN_NOAIR) | (1 << BR_DYN_GEN) | (1 << BR_EVT) | (1 << BR_LIN))
 #define JR_ALL (JR_HEAVY | JR_LIGHT)
+P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k);
 template <int ROLES>
 P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, double* g,
                           int tid, int phase, const JacScratch& sm) {
   const int start = bt[BT_START], count = bt[BT_COUNT], role = bt[BT_ROLE];
   if ((ROLES >> BR_DYN_AIR & 1) && role == BR_DYN_AIR) dyn_air_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
-  if ((ROLES >> BR_AERO & 1) && role == BR_AERO) aero_phase(P, scen, x, vals, start, count, tid, phase, sm);
+  if ((ROLES >> BR_AERO & 1) && role == BR_AERO) aero_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
   if ((ROLES >> BR_DYN_NOAIR & 1) && role == BR_DYN_NOAIR) dyn_noair_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
   if ((ROLES >> BR_DYN_GEN & 1) && role == BR_DYN_GEN) dyn_gen_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
   if ((ROLES >> BR_EVT & 1) && role == BR_EVT && (tid >> 4) < count) {
-    if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, sm);
-    else if (phase == 3) evt_jac_phase2(P, vals, start + (tid >> 4), tid, sm);
+    if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, g != nullptr, sm);
+    else if (phase == 3) evt_jac_phase2(P, vals, g, start + (tid >> 4), tid, sm);
+  }
+  /* pair evaluation only: the linear rows and the objective (the launch leaves these blocks out otherwise) */
+  if ((ROLES >> BR_LIN & 1) && role == BR_LIN && phase == 3 && g) {
+    if (tid < count) lin_res(P, scen, x, g, start + tid);
+    if (start == 0 && tid == 0) g[0] = P.payload_mode ? -x[0] : x[P.off_t + P.S]; /* cost_gradient.py:29-34 */
   }
 }
 /* roles whose phase 2 is empty (the kernel skips that barrier); phase 1 is empty for every role */
-P_HD bool jac_role_two_phase(int role) { return role == BR_EVT || role == BR_DYN_GEN; }
+P_HD bool jac_role_two_phase(int role) { return role == BR_EVT || role == BR_DYN_GEN || role == BR_LIN; }
 
 P_HD void res_block_phase0(const PlanView& P, int scen, const int32_t* bt, const double* x, int tid, ResScratch& sm) {
   if (bt[BT_ROLE] == BR_DYN) dyn_res_phase0(P, scen, x, bt[BT_START], bt[BT_COUNT], tid, sm);

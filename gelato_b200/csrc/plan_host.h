@@ -115,12 +115,11 @@ static inline const char* validate_desc(const GelatoPlanDesc* d) {
 }
 
 struct HostTables {
-  /* BT_COLS ints per block.  jac_blocks = the heavy roles' blocks (air dynamics, aero rows: n_jac_heavy of
-   * them) followed by the light roles' (vacuum dynamics, fallback, event rows); res_blocks = the dynamics
-   * blocks (n_res_dyn) followed by the aero / event / linear-row blocks, which are all a pair evaluation
-   * still needs from the residual kernel */
-  std::vector<int32_t> jac_blocks, res_blocks;
-  int n_jac_heavy = 0, n_res_dyn = 0;
+  /* BT_COLS ints per block.  jac_blocks: the n_jac_main dynamics / aero / event blocks (heavy and light roles
+   * interleaved), then the linear-row blocks of a pair evaluation; jac_heavy / jac_light: the same blocks by
+   * role group (measurements).  res_blocks: the residual kernel's. */
+  std::vector<int32_t> jac_blocks, jac_heavy, jac_light, res_blocks;
+  int n_jac_main = 0;
   std::vector<NodeRec> node_rec;               /* [N] natural order */
   std::vector<NodeRec> jac_rec;                /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
   std::vector<AeroRec> aero_rows;              /* one per aero constraint row */
@@ -277,17 +276,32 @@ static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
   }
   const int n_aero_rows = (int)h.aero_rows.size();
 
+  /* Jacobian blocks: the heavy roles' (air dynamics, aero rows) and the light roles' (vacuum dynamics, fallback,
+   * event rows) interleaved evenly, so that the blocks resident on an SM at one time mix FP64-issue-bound and
+   * latency-bound work (separate kernels on separate streams ran one after the other: the first fills every SM;
+   * profiles/r02a_ab_probe.txt); then the linear-row blocks, which only a pair evaluation launches */
+  std::vector<int32_t> heavy, light;
+  push_chunks(heavy, BR_DYN_AIR, 0, (int)air.size(), GD_NODES);
+  push_chunks(heavy, BR_AERO, 0, n_aero_rows, GJ_NODES);
+  push_chunks(light, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
+  push_chunks(light, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
+  push_chunks(light, BR_EVT, 0, d->n_evt, GJ_EVT);
+  h.jac_heavy = heavy;
+  h.jac_light = light;
   std::vector<int32_t>& jb = h.jac_blocks;
-  push_chunks(jb, BR_DYN_AIR, 0, (int)air.size(), GD_NODES);
-  push_chunks(jb, BR_AERO, 0, n_aero_rows, GJ_NODES);
-  h.n_jac_heavy = (int)(jb.size() / BT_COLS);
-  push_chunks(jb, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
-  push_chunks(jb, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
-  push_chunks(jb, BR_EVT, 0, d->n_evt, GJ_EVT);
+  const long long nh = (long long)heavy.size() / BT_COLS, nl = (long long)light.size() / BT_COLS;
+  for (long long ih = 0, il = 0; ih < nh || il < nl;) {
+    /* next from the list that is behind its share */
+    const bool take_heavy = il >= nl || (ih < nh && ih * nl <= il * nh);
+    const std::vector<int32_t>& src = take_heavy ? heavy : light;
+    const long long k = take_heavy ? ih++ : il++;
+    jb.insert(jb.end(), src.begin() + k * BT_COLS, src.begin() + (k + 1) * BT_COLS);
+  }
+  h.n_jac_main = (int)(jb.size() / BT_COLS);
+  push_chunks(jb, BR_LIN, 0, d->n_lin, GJ_THREADS);
 
   std::vector<int32_t>& rb = h.res_blocks;
   push_chunks(rb, BR_DYN, 0, N, GR_NODES);
-  h.n_res_dyn = (int)(rb.size() / BT_COLS);
   push_chunks(rb, BR_AERO, 0, n_aero_rows, GR_THREADS);
   push_chunks(rb, BR_EVT, 0, d->n_evt, GR_THREADS);
   push_chunks(rb, BR_LIN, 0, d->n_lin, GR_THREADS);

@@ -16,8 +16,9 @@ compared and "solves per hour" can be measured.  It is a stand-in and is labelle
 * Hessian of the Lagrangian: damped limited-memory BFGS in compact form; the KKT matrix
   [[sigma I + Sigma, J^T], [J, -D]] stays SPARSE (scipy SuperLU) and the 2m rank correction goes through the
   Woodbury identity -- the sparse KKT solve stays on the host, as the north star prescribes;
-* globalisation: l1 exact-penalty merit function with Armijo backtracking and a second-order correction;
-  when the line search fails the quasi-Newton memory is dropped, then a least-norm feasibility step is tried.
+* globalisation: the filter line search of the paper (switching condition, Armijo on the barrier objective,
+  sufficient decrease in violation or objective otherwise) with a second-order correction; when it fails the
+  quasi-Newton memory is dropped, then least-norm steps towards feasibility stand in for the restoration phase.
 
 Interface: `IPSolver(options)(optProb, sens=sens) -> Solution`, for `nlpshim.Optimization` problems
 (the same call the reference makes on pyoptsparse's classes).
@@ -181,7 +182,9 @@ class IPSolver:
         lamI = -zs.copy()
         lamE = self._ls_multipliers(g, JE, JI, zL, zU, lamI)
         B = _LBFGS(n, o["memory"])
-        nu = 1.0  # penalty parameter of the merit function
+        filt = None  # the filter of the current barrier problem
+        theta_max = theta_min = 0.0
+        fails_in_a_row = 0
         tol = o["tol"]
         history = []
         status, message = 1, "maximum number of iterations exceeded"
@@ -203,7 +206,8 @@ class IPSolver:
             E0 = max(du_inf, viol, compl(0.0) / s_d)
             history.append((f0 / df, viol, du_inf, mu))
             if o["verbose"] and (it % o["verbose"] == 0):
-                print("it %4d  obj %.8f  viol %.2e  dual %.2e  mu %.1e  nu %.1e  mem %d" % (it, f0 / df, viol, du_inf, mu, nu, len(B.S)))
+                print("it %4d  obj %.8f  viol %.2e  dual %.2e  mu %.1e  filter %d  mem %d  fails %d"
+                      % (it, f0 / df, viol, du_inf, mu, 0 if filt is None else len(filt), len(B.S), fails))
             if E0 <= tol:
                 status, message = 0, "converged to tol %g" % tol
                 break
@@ -215,6 +219,7 @@ class IPSolver:
                 break
             while mu > tol / 10.0 and max(du_inf, viol, compl(mu) / s_d) <= 10.0 * mu:
                 mu = max(tol / 10.0, min(0.2 * mu, mu ** 1.5))
+                filt = None
             tau = max(0.99, 1.0 - mu)
 
             # ---- Newton step of the barrier problem ----
@@ -248,7 +253,7 @@ class IPSolver:
                         max_step(np.where(hasU, xu - x, 1.0), np.where(hasU, -dx, 0.0), tau), max_step(s, ds, tau))
             a_z = min(max_step(zL, dzL, tau), max_step(zU, dzU, tau), max_step(zs, dzs, tau))
 
-            # ---- l1 merit function, Armijo backtracking with a second-order correction ----
+            # ---- filter line search (Waechter & Biegler, Alg. A) with a second-order correction ----
             def barrier(xv, sv, fv):
                 return fv - mu * (np.log(np.where(hasL, xv - xl, 1.0)).sum() + np.log(np.where(hasU, xu - xv, 1.0)).sum()
                                   + np.log(sv).sum())
@@ -256,30 +261,40 @@ class IPSolver:
             gphi_d = float(g @ dx) - mu * (np.where(hasL, dx / np.maximum(x - xl, 1e-300), 0.0).sum()
                                            - np.where(hasU, dx / np.maximum(xu - x, 1e-300), 0.0).sum() + (ds / s).sum())
             theta0 = np.abs(cE).sum() + np.abs(cI - s).sum()
-            dWd = float(dx @ B.times(dx)) + float(dx @ ((SigL + SigU) * dx)) + float(ds @ (Sigs * ds))
-            if theta0 > 1e-14:
-                nu_trial = (gphi_d + 0.5 * max(dWd, 0.0)) / (0.7 * theta0)
-                if nu_trial > nu:
-                    nu = nu_trial + 1.0
-            phi0 = barrier(x, s, f0) + nu * theta0
-            Dphi = gphi_d - nu * theta0
+            phi0 = barrier(x, s, f0)
+            if filt is None:  # (re)started with every new barrier parameter
+                filt = []
+                theta_max = 1e4 * max(1.0, theta0)
+                theta_min = 1e-4 * max(1.0, theta0)
+            g_th, g_ph, eta = 1e-5, 1e-8, 1e-8
+
+            def in_filter(th, ph):
+                return th >= theta_max or any(th >= (1.0 - g_th) * t_ and ph >= p_ - g_ph * t_ for t_, p_ in filt)
+
             alpha = a_max
             accepted = False
+            armijo_step = False
             soc_done = False
             step_dx, step_ds = dx, ds
-            for ls in range(40):
+            a_min = 1e-10
+            for ls in range(50):
                 xt = x + alpha * step_dx
                 st = s + alpha * step_ds
-                if np.any(st <= 0) or np.any(xt <= xl) or np.any(xt >= xu):
-                    alpha *= 0.5
-                    continue
                 ft, cEt, cIt, _, _, _ = scaled(evaluate(xt, False))
                 thetat = np.abs(cEt).sum() + np.abs(cIt - st).sum()
-                phit = barrier(xt, st, ft) + nu * thetat
-                if np.isfinite(phit) and phit <= phi0 + 1e-8 * alpha * Dphi + 10.0 * np.finfo(float).eps * abs(phi0):
+                phit = barrier(xt, st, ft)
+                ok = np.isfinite(phit) and np.isfinite(thetat) and not in_filter(thetat, phit)
+                if ok:
+                    switching = gphi_d < 0 and theta0 <= theta_min and alpha * (-gphi_d) ** 2.3 > theta0 ** 1.1
+                    if switching:
+                        ok = phit <= phi0 + eta * alpha * gphi_d + 10.0 * np.finfo(float).eps * abs(phi0)
+                        armijo_step = ok
+                    else:
+                        ok = thetat <= (1.0 - g_th) * theta0 or phit <= phi0 - g_ph * theta0
+                if ok:
                     accepted = True
                     break
-                if ls == 0 and not soc_done and thetat >= theta0 and np.isfinite(thetat):
+                if ls == 0 and not soc_done and np.isfinite(thetat) and thetat >= theta0:
                     # second-order correction: re-solve with the constraint values of the trial point added
                     soc_done = True
                     rhs2 = -np.concatenate((r_x, alpha * cE + cEt, alpha * r_I + (cIt - st)))
@@ -292,39 +307,58 @@ class IPSolver:
                         x2, s2 = x + a2 * dx2, s + a2 * ds2
                         f2, cE2, cI2, _, _, _ = scaled(evaluate(x2, False))
                         th2 = np.abs(cE2).sum() + np.abs(cI2 - s2).sum()
-                        phi2 = barrier(x2, s2, f2) + nu * th2
-                        if np.isfinite(phi2) and phi2 <= phi0 + 1e-8 * a2 * Dphi:
+                        phi2 = barrier(x2, s2, f2)
+                        if np.isfinite(phi2) and not in_filter(th2, phi2) and (
+                                th2 <= (1.0 - g_th) * theta0 or phi2 <= phi0 - g_ph * theta0):
                             step_dx, step_ds, alpha = dx2, ds2, a2
-                            xt, st = x2, s2
                             accepted = True
                             break
                 alpha *= 0.5
-                if alpha < 1e-12:
+                if alpha < a_min:
                     break
+            if accepted and not armijo_step:
+                filt.append(((1.0 - g_th) * theta0, phi0 - g_ph * theta0))
             if not accepted:
                 fails += 1
-                if len(B.S) > 0:  # a poor quasi-Newton model: drop the memory and try again from sigma I
+                if len(B.S) > 0 and fails_in_a_row == 0:  # a poor quasi-Newton model: drop the memory and try again from sigma I
                     B.reset(B.sigma)
+                    fails_in_a_row += 1
                     continue
-                # least-norm step towards feasibility (what a restoration phase does first)
-                dxr = self._feasibility_step(JE, JI, cE, cI - s, n, mE, mI)
+                # restoration: least-norm steps towards feasibility until the filter accepts the point
+                filt.append(((1.0 - g_th) * theta0, phi0 - g_ph * theta0))
+                xr, sr, thr = x.copy(), s.copy(), theta0
+                cEr, cIr, JEr, JIr = cE, cI, JE, JI
                 ok = False
-                if dxr is not None:
-                    a = min(max_step(np.where(hasL, x - xl, 1.0), np.where(hasL, dxr, 0.0), tau),
-                            max_step(np.where(hasU, xu - x, 1.0), np.where(hasU, -dxr, 0.0), tau))
+                for _r in range(20):
+                    dxr = self._feasibility_step(JEr, JIr, cEr, cIr - sr, n, mE, mI)
+                    if dxr is None:
+                        break
+                    a = min(max_step(np.where(hasL, xr - xl, 1.0), np.where(hasL, dxr, 0.0), tau),
+                            max_step(np.where(hasU, xu - xr, 1.0), np.where(hasU, -dxr, 0.0), tau))
+                    moved = False
                     for _ in range(30):
-                        xt = x + a * dxr
+                        xt = xr + a * dxr
                         ft, cEt, cIt, _, _, _ = scaled(evaluate(xt, False))
-                        st = np.maximum(cIt, np.minimum(s, 1e-8 + mu))
-                        if np.abs(cEt).sum() + np.abs(cIt - st).sum() < (1.0 - 1e-4 * a) * theta0:
-                            ok = True
+                        st = np.maximum(cIt, np.minimum(sr, mu))
+                        tht = np.abs(cEt).sum() + np.abs(cIt - st).sum()
+                        if np.isfinite(tht) and tht < (1.0 - 1e-4 * a) * thr:
+                            moved = True
                             break
                         a *= 0.5
+                    if not moved:
+                        break
+                    xr, sr, thr = xt, st, tht
+                    if thr <= 0.9 * theta0 and not in_filter(thr, barrier(xr, sr, ft)):
+                        ok = True
+                        break
+                    _, cEr, cIr, _, JEr, JIr = scaled(evaluate(xr, True))
                 if not ok:
-                    status, message = 3, "line search and feasibility step failed"
+                    status, message = 3, "restoration failed"
                     break
-                alpha, step_dx, step_ds = 1.0, xt - x, st - s
-                nu = 1.0
+                alpha, step_dx, step_ds = 1.0, xr - x, sr - s
+                dlE, dlI = np.zeros(mE), np.zeros(mI)
+                B.reset(B.sigma)
+            fails_in_a_row = 0
             # ---- accept: primal and equality multipliers with alpha, bound multipliers with their own step ----
             x_new, s_new = x + alpha * step_dx, s + alpha * step_ds
             lamE_new = lamE + alpha * dlE

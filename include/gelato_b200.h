@@ -6,8 +6,8 @@
  * pybind_USStandardAtmosphere.cpp:28-35) AND the Python loops around them
  * (/root/reference/lib/con_*.py): instead of ~230 by-value leaf calls per
  * Jacobian, the host describes the whole transcribed problem once (a "plan") and
- * then makes ONE call per `objfunc` (/root/reference/Trajectory_Optimization.py:194-242)
- * and ONE per `sens` (:245-312).
+ * then makes ONE call (one kernel launch) per `objfunc` (/root/reference/Trajectory_Optimization.py:194-242)
+ * and ONE per `sens` (:245-312) -- or one for both (gelato_eval_pair_*).
  *
  * Plain pointers and sizes only; no torch / numpy / Eigen types.  All functions
  * return 0 on success and a negative code on failure (gelato_last_error() gives
@@ -174,8 +174,8 @@ int gelato_plan_destroy(GelatoPlan* plan);
 int32_t gelato_plan_n_vars(const GelatoPlan* plan);
 int32_t gelato_plan_n_rows(const GelatoPlan* plan);
 int64_t gelato_plan_n_vals(const GelatoPlan* plan);
-/* thread blocks per scenario: which = 0 residual kernel | 1 both Jacobian kernels | 2 the heavy Jacobian kernel
- * | 3 the light one | 4 the residual kernel's non-dynamics blocks (what a pair evaluation launches of it) */
+/* thread blocks per scenario: which = 0 residual kernel | 1 Jacobian kernel | 2 / 3 its heavy / light roles' blocks
+ * | 4 Jacobian kernel of a pair evaluation (+ the linear-row blocks) */
 int32_t gelato_plan_n_blocks(const GelatoPlan* plan, int which);
 /* kernels launched by this plan so far (bench.py's gpu_launches) */
 int64_t gelato_plan_launch_count(const GelatoPlan* plan);
@@ -260,10 +260,11 @@ int gelato_host_free(void* ptr);
  * x-dependent slot on each call and leaves the constants alone. */
 int gelato_eval_residuals_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, int32_t n_scen, void* stream);
 int gelato_fill_template(GelatoPlan* plan, double* vals_dev, int32_t n_scen, void* stream);
-/* objfunc + sens of the same x_dev as ONE evaluation: the Jacobian kernels' dynamics blocks already hold the
- * right-hand side at the pristine x (their centre column) and write the collocation defects next to the
- * Jacobian values; only the aero / event / linear rows run as (the non-dynamics blocks of) the residual kernel,
- * on a side stream forked from and joined back into `stream`.  Bit-identical to the two separate calls.
+/* objfunc + sens of the same x_dev as ONE launch of the Jacobian kernel: its dynamics blocks already hold the
+ * right-hand side at the pristine x (their centre column) and write the collocation defects (D.X computed by
+ * otherwise idle threads of phase 0) next to the Jacobian values; aero and event blocks carry one more column at
+ * the pristine state; the linear rows and the objective are blocks of their own.  Bit-identical to the two
+ * separate calls.
  * _packed_dev: the same with the packed Jacobian output ([n_scen][n_pack], see gelato_eval_pair_packed). */
 int gelato_eval_pair_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* vals_dev, int32_t n_scen,
                          void* stream);
@@ -275,14 +276,14 @@ int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packe
 
 /* Timing helper for benchmarks: runs `reps` back-to-back launches of the chosen kernel on device-resident
  * buffers and returns the average duration in milliseconds measured with CUDA events on the launch stream.
- * which: 0 residual kernel | 1 the Jacobian evaluation (heavy + light kernels) | 2 the heavy Jacobian kernel
- * alone (air dynamics + aero rows) | 3 the light Jacobian kernel alone. */
+ * which: 0 residual kernel | 1 the Jacobian kernel | 2 the heavy roles' blocks alone (air dynamics + aero rows)
+ * | 3 the light roles' blocks alone (vacuum dynamics, fallback, event rows). */
 int gelato_time_kernel(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, int32_t n_scen, int reps,
                        float* avg_ms);
 /* Measurement helper: enqueue exactly one kernel on `stream`, not synchronised -- for benchmarks that bracket single
- * kernels with their own CUDA events.  which: 0, 2, 3 as above, 4 = the residual kernel's non-dynamics blocks
- * (out_dev is g for 0 and 4); COO (packed = 0) or packed Jacobian output; g_dev != NULL makes a Jacobian kernel
- * write the pair evaluation's defect rows as well. */
+ * kernels with their own CUDA events.  which: 0 the residual kernel (out_dev is g) | 1 the Jacobian kernel | 2 / 3 its
+ * heavy / light roles' blocks alone (role-subset builds of the same kernel); COO (packed = 0) or packed Jacobian
+ * output; g_dev != NULL: as a pair evaluation runs it (objfunc's rows written too). */
 int gelato_launch_kernel_dev(GelatoPlan* plan, int which, const double* x_dev, double* out_dev, double* g_dev,
                              int32_t n_scen, int32_t packed, void* stream);
 

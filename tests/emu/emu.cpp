@@ -74,9 +74,8 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
   return 0;
 }
 
-// mode bit 0: packed output (out_all is [n_scen][n_pack], nothing is pre-filled);  g_all != NULL: pair
-// evaluation -- the dynamics defects come out of the Jacobian blocks, the other rows from the residual
-// kernel's non-dynamics blocks (what gelato_eval_pair_* launches).
+// packed: out_all is [n_scen][n_pack] and nothing is pre-filled;  g_all != NULL: pair evaluation -- objfunc's
+// rows come out of the Jacobian blocks (what gelato_eval_pair_* launches).
 static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,
                         double* out_all, int n_scen, const int32_t* ids, int packed) {
   if (validate_desc(d)) return -1;
@@ -91,10 +90,8 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
   P.n_pack = L.n_pack;
   P.sec_pk = L.sec_pk.data(); P.aero_pk = L.aero_pk.data(); P.evt_pk = L.evt_pk.data();
   const std::vector<int32_t>& jb = h.jac_blocks;
-  const std::vector<int32_t>& rb = h.res_blocks;
   JacStore store;
   const JacScratch sm = jac_scratch(store);
-  ResScratch rsm;
   const size_t stride = packed ? (size_t)L.n_pack : (size_t)P.n_vals;
   for (int scen = 0; scen < n_scen; scen++) {
     const double* x = x_all + (size_t)scen * P.n_vars;
@@ -105,22 +102,14 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
       const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)sid * P.n_vals : d->vals_template;
       memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
     }
-    for (size_t b = 0; b < jb.size() / BT_COLS; b++) {
+    const size_t nb = g ? jb.size() / BT_COLS : (size_t)h.n_jac_main;  /* the linear-row blocks: pair evaluations only */
+    for (size_t b = 0; b < nb; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
       /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
       memset(&store, 0xff, sizeof store);
       for (int phase = 0; phase < GJ_PHASES; phase++)
-        for (int tid = 0; tid < GJ_THREADS; tid++) {
-          if ((int)b < h.n_jac_heavy) jac_block_phase<JR_HEAVY>(P, sid, bt, x, vals, g, tid, phase, sm);
-          else jac_block_phase<JR_LIGHT>(P, sid, bt, x, vals, g, tid, phase, sm);
-        }
+        for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase<JR_ALL>(P, sid, bt, x, vals, g, tid, phase, sm);
     }
-    if (g)
-      for (size_t b = (size_t)h.n_res_dyn; b < rb.size() / BT_COLS; b++) {
-        const int32_t* bt = rb.data() + b * BT_COLS;
-        memset(&rsm, 0xff, sizeof rsm);
-        for (int tid = 0; tid < GR_THREADS; tid++) res_block_phase1(P, sid, bt, x, g, tid, rsm);
-      }
   }
   return 0;
 }

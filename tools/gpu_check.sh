@@ -16,6 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sustained-seconds 0.01 > gpurun_out/ncu_launches.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_jacobian$ -s 3 -c 1 -f -o gpurun_out/prof_jac \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-seconds 0.01 > gpurun_out/ncu_jac.log 2>&1; echo "ncu jac rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_jacobian_light$ -s 3 -c 1 -f -o gpurun_out/prof_light \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-seconds 0.01 > gpurun_out/ncu_light.log 2>&1; echo "ncu light rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_residuals$ -s 3 -c 1 -f -o gpurun_out/prof_res \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-seconds 0.01 > gpurun_out/ncu_res.log 2>&1; echo "ncu res rc=$?"
 ls -la gpurun_out

@@ -54,10 +54,9 @@ def main():
         "heavy_coo": timed(lambda: E.launch_kernel_dev(2, x, v, B, False, st)),
         "light_packed": timed(lambda: E.launch_kernel_dev(3, x, p_, B, True, st)),
         "light_packed_g": timed(lambda: E.launch_kernel_dev(3, x, p_, B, True, st, g)),
-        "res_rest": timed(lambda: E.launch_kernel_dev(4, x, g, B, False, st)),
+        "jac_packed": timed(lambda: E.launch_kernel_dev(1, x, p_, B, True, st)),
         "res_full": timed(lambda: E.launch_kernel_dev(0, x, g, B, False, st)),
-        "serial_heavy_light_rest_g": timed(lambda: (E.launch_kernel_dev(2, x, p_, B, True, st, g), E.launch_kernel_dev(3, x, p_, B, True, st, g),
-                                                    E.launch_kernel_dev(4, x, g, B, False, st))),
+        "serial_heavy_light_g": timed(lambda: (E.launch_kernel_dev(2, x, p_, B, True, st, g), E.launch_kernel_dev(3, x, p_, B, True, st, g))),
         "jacobian_coo": timed(lambda: E.eval_jacobian_dev(x, v, B, st)),
         "pair_packed": timed(lambda: E.eval_pair_packed_dev(x, g, p_, B, st)),
         "pair_coo": timed(lambda: E.eval_pair_dev(x, g, v, B, st)),
