@@ -27,17 +27,35 @@
 #include <string.h>
 
 #include "gmath_coeffs.inc"
+#include "gmath_table.inc"
+
+/* The coefficients as operands.  Host: the literals of gmath_coeffs.inc.  Device: the same literals read from one
+ * table in __constant__ memory (gmath_table.inc) -- identical values, so identical results; what changes is the
+ * instruction count: a 64-bit literal costs two 32-bit immediate moves per use, a constant-bank operand none
+ * (ncu r02a: moves were 27 % of the instructions the Jacobian kernel executed, as many as its FP64 arithmetic). */
+#if defined(__CUDACC__)
+static __constant__ double gm_tab[GM_TAB_N] = GM_TAB_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GMC(name) gm_tab[GMT_##name]
+#else
+#define GMC(name) GM_##name
+#endif
 
 #if defined(__CUDACC__)
 #define GM_HD static __host__ __device__ inline
-/* The large elementary functions are real calls on the device: a right-hand side
- * evaluates ~20 of them, and with every copy inlined the Jacobian kernel was 365 KB
- * of SASS -- far beyond the SM instruction cache (ncu round 1: stall_no_instruction
- * 8.3 per issue).  Called, each exists once. */
+/* The large elementary functions exist in two forms.  `gm_xxx` is a real call on the device (__noinline__): a
+ * right-hand side evaluates ~20 of them, and with every copy inlined the Jacobian kernel was 365 KB of SASS -- far
+ * beyond the SM instruction cache (ncu round 1: stall_no_instruction 8.3 per issue).  `gm_xxx_inl` is the same body
+ * forced inline, for the two functions that ARE the hot path (physics.h: pos_part, rotq_part; themselves called
+ * once per item): there a call costs more in argument moves and spills than the body is worth sharing (ncu r02a:
+ * 18 % of the executed instructions were register moves). */
 #define GM_HD_CALL static __host__ __device__ __noinline__
+#define GM_HD_INL static __host__ __device__ __forceinline__
 #else
 #define GM_HD static inline
 #define GM_HD_CALL static inline
+#define GM_HD_INL static inline
 #endif
 
 /* ---- primitives ------------------------------------------------------- */
@@ -114,15 +132,15 @@ GM_HD double gm_rint(double x) {
  * of pi/2 (159 bits): accurate for |x| up to ~1e6, which is far beyond the
  * O(1) arguments on this path (Earth-rotation angle, latitude, longitude). */
 GM_HD int gm_rem_pio2(double x, double* r, double* rl) {
-  double kd = gm_rint(x * GM_2_OVER_PI);
-  double t = gm_fma(-kd, GM_PIO2_1, x); /* exact (cancellation) */
-  double ph = kd * GM_PIO2_2;
-  double pl = gm_fma(kd, GM_PIO2_2, -ph); /* ph + pl == kd*PIO2_2 */
+  double kd = gm_rint(x * GMC(2_OVER_PI));
+  double t = gm_fma(-kd, GMC(PIO2_1), x); /* exact (cancellation) */
+  double ph = kd * GMC(PIO2_2);
+  double pl = gm_fma(kd, GMC(PIO2_2), -ph); /* ph + pl == kd*PIO2_2 */
   double nph = -ph;
   double rh = t + nph; /* TwoSum(t, -ph) */
   double bb = rh - t;
   double e = (t - (rh - bb)) + (nph - bb);
-  double lo = (e - pl) - kd * GM_PIO2_3;
+  double lo = (e - pl) - kd * GMC(PIO2_3);
   double r0 = rh + lo;
   *rl = (rh - r0) + lo;
   *r = r0;
@@ -133,31 +151,31 @@ GM_HD int gm_rem_pio2(double x, double* r, double* rl) {
 GM_HD double gm_ksin(double x, double y) {
   double z = x * x;
   double v = z * x;
-  double p = GM_SIN_C6;
-  p = gm_fma(p, z, GM_SIN_C5);
-  p = gm_fma(p, z, GM_SIN_C4);
-  p = gm_fma(p, z, GM_SIN_C3);
-  p = gm_fma(p, z, GM_SIN_C2);
-  p = gm_fma(p, z, GM_SIN_C1);
-  return x - ((z * (0.5 * y - v * p) - y) - v * GM_SIN_C0);
+  double p = GMC(SIN_C6);
+  p = gm_fma(p, z, GMC(SIN_C5));
+  p = gm_fma(p, z, GMC(SIN_C4));
+  p = gm_fma(p, z, GMC(SIN_C3));
+  p = gm_fma(p, z, GMC(SIN_C2));
+  p = gm_fma(p, z, GMC(SIN_C1));
+  return x - ((z * (0.5 * y - v * p) - y) - v * GMC(SIN_C0));
 }
 
 /* cos(x + y), |x| <~ pi/4, y a tail */
 GM_HD double gm_kcos(double x, double y) {
   double z = x * x;
-  double p = GM_COS_C6;
-  p = gm_fma(p, z, GM_COS_C5);
-  p = gm_fma(p, z, GM_COS_C4);
-  p = gm_fma(p, z, GM_COS_C3);
-  p = gm_fma(p, z, GM_COS_C2);
-  p = gm_fma(p, z, GM_COS_C1);
-  p = gm_fma(p, z, GM_COS_C0);
+  double p = GMC(COS_C6);
+  p = gm_fma(p, z, GMC(COS_C5));
+  p = gm_fma(p, z, GMC(COS_C4));
+  p = gm_fma(p, z, GMC(COS_C3));
+  p = gm_fma(p, z, GMC(COS_C2));
+  p = gm_fma(p, z, GMC(COS_C1));
+  p = gm_fma(p, z, GMC(COS_C0));
   double hz = 0.5 * z;
   double w = 1.0 - hz;
   return w + (((1.0 - w) - hz) + (z * (z * p) - x * y));
 }
 
-GM_HD_CALL void gm_sincos(double x, double* s, double* c) {
+GM_HD_INL void gm_sincos_inl(double x, double* s, double* c) {
   uint64_t ax = gm_d2u(x) & GM_ABS_MASK;
   if (ax >= GM_INF_BITS) { /* inf or nan */
     *s = gm_nan();
@@ -170,13 +188,13 @@ GM_HD_CALL void gm_sincos(double x, double* s, double* c) {
     q = gm_rem_pio2(x, &r, &rl);
   double ks = gm_ksin(r, rl);
   double kc = gm_kcos(r, rl);
-  switch (q) {
-    case 0: *s = ks; *c = kc; break;
-    case 1: *s = kc; *c = -ks; break;
-    case 2: *s = -ks; *c = -kc; break;
-    default: *s = -kc; *c = ks; break;
-  }
+  /* quadrant: q = 0 (s, c) | 1 (c, -s) | 2 (-s, -c) | 3 (-c, s); selects instead of a four-way branch */
+  double ss = (q & 1) ? kc : ks;
+  double cc = (q & 1) ? ks : kc;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
 }
+GM_HD_CALL void gm_sincos(double x, double* s, double* c) { gm_sincos_inl(x, s, c); }
 
 GM_HD double gm_sin(double x) {
   double s, c;
@@ -204,21 +222,49 @@ GM_HD_CALL double gm_tan(double x) {
 /* ---- atan / atan2 / asin / acos --------------------------------------- */
 
 GM_HD double gm_atan_poly(double z) { /* (t - atan t)/t^3, z = t^2 <= (7/16)^2 */
-  double p = GM_ATAN_C13;
-  p = gm_fma(p, z, GM_ATAN_C12);
-  p = gm_fma(p, z, GM_ATAN_C11);
-  p = gm_fma(p, z, GM_ATAN_C10);
-  p = gm_fma(p, z, GM_ATAN_C9);
-  p = gm_fma(p, z, GM_ATAN_C8);
-  p = gm_fma(p, z, GM_ATAN_C7);
-  p = gm_fma(p, z, GM_ATAN_C6);
-  p = gm_fma(p, z, GM_ATAN_C5);
-  p = gm_fma(p, z, GM_ATAN_C4);
-  p = gm_fma(p, z, GM_ATAN_C3);
-  p = gm_fma(p, z, GM_ATAN_C2);
-  p = gm_fma(p, z, GM_ATAN_C1);
-  p = gm_fma(p, z, GM_ATAN_C0);
+  double p = GMC(ATAN_C13);
+  p = gm_fma(p, z, GMC(ATAN_C12));
+  p = gm_fma(p, z, GMC(ATAN_C11));
+  p = gm_fma(p, z, GMC(ATAN_C10));
+  p = gm_fma(p, z, GMC(ATAN_C9));
+  p = gm_fma(p, z, GMC(ATAN_C8));
+  p = gm_fma(p, z, GMC(ATAN_C7));
+  p = gm_fma(p, z, GMC(ATAN_C6));
+  p = gm_fma(p, z, GMC(ATAN_C5));
+  p = gm_fma(p, z, GMC(ATAN_C4));
+  p = gm_fma(p, z, GMC(ATAN_C3));
+  p = gm_fma(p, z, GMC(ATAN_C2));
+  p = gm_fma(p, z, GMC(ATAN_C1));
+  p = gm_fma(p, z, GMC(ATAN_C0));
   return p;
+}
+
+/* atan(a) for 2^-27 <= a < 2^66 (the range reduction of gm_atan without its special cases) */
+GM_HD double gm_atan_core(double a) {
+  double t, hi, lo;
+  if (a < 0.4375) {
+    double z = a * a;
+    return a - a * (z * gm_atan_poly(z));
+  } else if (a < 0.6875) {
+    t = gm_div(2.0 * a - 1.0, 2.0 + a);
+    hi = GMC(ATAN_05_HI);
+    lo = GMC(ATAN_05_LO);
+  } else if (a < 1.1875) {
+    t = gm_div(a - 1.0, a + 1.0);
+    hi = GMC(ATAN_10_HI);
+    lo = GMC(ATAN_10_LO);
+  } else if (a < 2.4375) {
+    t = gm_div(a - 1.5, 1.0 + 1.5 * a);
+    hi = GMC(ATAN_15_HI);
+    lo = GMC(ATAN_15_LO);
+  } else {
+    t = gm_div(-1.0, a);
+    hi = GMC(ATAN_INF_HI);
+    lo = GMC(ATAN_INF_LO);
+  }
+  double z = t * t;
+  double corr = t * (z * gm_atan_poly(z)); /* t - atan(t) */
+  return hi - ((corr - lo) - t);
 }
 
 GM_HD double gm_atan(double x) {
@@ -227,42 +273,24 @@ GM_HD double gm_atan(double x) {
   if (ax > GM_INF_BITS) return x + x; /* nan */
   double a = gm_u2d(ax);
   if (ax >= 0x4410000000000000ull) /* |x| >= 2^66 */
-    return gm_copysign(GM_ATAN_INF_HI, x);
+    return gm_copysign(GMC(ATAN_INF_HI), x);
   if (ax < 0x3e40000000000000ull) /* |x| < 2^-27 */
     return x;
-  double t, hi, lo;
-  if (a < 0.4375) {
+  if (a < 0.4375) { /* the odd polynomial on the signed argument, as before */
     double z = x * x;
     return x - x * (z * gm_atan_poly(z));
-  } else if (a < 0.6875) {
-    t = gm_div(2.0 * a - 1.0, 2.0 + a);
-    hi = GM_ATAN_05_HI;
-    lo = GM_ATAN_05_LO;
-  } else if (a < 1.1875) {
-    t = gm_div(a - 1.0, a + 1.0);
-    hi = GM_ATAN_10_HI;
-    lo = GM_ATAN_10_LO;
-  } else if (a < 2.4375) {
-    t = gm_div(a - 1.5, 1.0 + 1.5 * a);
-    hi = GM_ATAN_15_HI;
-    lo = GM_ATAN_15_LO;
-  } else {
-    t = gm_div(-1.0, a);
-    hi = GM_ATAN_INF_HI;
-    lo = GM_ATAN_INF_LO;
   }
-  double z = t * t;
-  double corr = t * (z * gm_atan_poly(z)); /* t - atan(t) */
-  double res = hi - ((corr - lo) - t);
+  double res = gm_atan_core(a);
   return (ux & GM_SIGN_MASK) ? -res : res;
 }
 
-GM_HD_CALL double gm_atan2(double y, double x) {
+/* every special case of atan2: zeros, infinities, NaN, extreme quotients */
+GM_HD_CALL double gm_atan2_slow(double y, double x) {
   if (gm_isnan(x) || gm_isnan(y)) return x + y;
   uint64_t ux = gm_d2u(x), uy = gm_d2u(y);
   uint64_t ax = ux & GM_ABS_MASK, ay = uy & GM_ABS_MASK;
   int m = (int)(uy >> 63) | ((int)(ux >> 63) << 1); /* 2*sign(x) + sign(y) */
-  const double pi = GM_PI_HI, pi_lo = GM_PI_LO;
+  const double pi = GMC(PI_HI), pi_lo = GMC(PI_LO);
   if (ay == 0) {
     switch (m) {
       case 0:
@@ -271,14 +299,14 @@ GM_HD_CALL double gm_atan2(double y, double x) {
       default: return -pi;
     }
   }
-  if (ax == 0) return (m & 1) ? -GM_ATAN_INF_HI : GM_ATAN_INF_HI;
+  if (ax == 0) return (m & 1) ? -GMC(ATAN_INF_HI) : GMC(ATAN_INF_HI);
   if (ax == GM_INF_BITS) {
     if (ay == GM_INF_BITS) {
       switch (m) {
-        case 0: return GM_ATAN_10_HI;
-        case 1: return -GM_ATAN_10_HI;
-        case 2: return 3.0 * GM_ATAN_10_HI;
-        default: return -3.0 * GM_ATAN_10_HI;
+        case 0: return GMC(ATAN_10_HI);
+        case 1: return -GMC(ATAN_10_HI);
+        case 2: return 3.0 * GMC(ATAN_10_HI);
+        default: return -3.0 * GMC(ATAN_10_HI);
       }
     } else {
       switch (m) {
@@ -289,12 +317,12 @@ GM_HD_CALL double gm_atan2(double y, double x) {
       }
     }
   }
-  if (ay == GM_INF_BITS) return (m & 1) ? -GM_ATAN_INF_HI : GM_ATAN_INF_HI;
+  if (ay == GM_INF_BITS) return (m & 1) ? -GMC(ATAN_INF_HI) : GMC(ATAN_INF_HI);
 
   int k = (int)(ay >> 52) - (int)(ax >> 52);
   double z;
   if (k > 64) { /* |y/x| > 2^64 */
-    z = GM_ATAN_INF_HI + 0.5 * pi_lo;
+    z = GMC(ATAN_INF_HI) + 0.5 * pi_lo;
     m &= 1;
   } else if ((m & 2) && k < -64) { /* 0 > |y|/x > -2^-64 */
     z = 0.0;
@@ -308,6 +336,24 @@ GM_HD_CALL double gm_atan2(double y, double x) {
     default: return (z - pi_lo) - pi;
   }
 }
+
+/* atan2: the common case -- both arguments normal numbers whose exponents differ by less than 26, so that the
+ * quotient lies in [2^-27, 2^27] -- goes straight to the range reduction (two integer tests instead of the ladder
+ * of special cases, which ncu r02a showed as the kernel's most expensive branches); everything else takes
+ * gm_atan2_slow.  Same operations in the same order on either route. */
+GM_HD_INL double gm_atan2_inl(double y, double x) {
+  const uint64_t ux = gm_d2u(x), uy = gm_d2u(y);
+  const uint32_t ex = (uint32_t)(ux >> 52) & 0x7ffu, ey = (uint32_t)(uy >> 52) & 0x7ffu;
+  const int k = (int)ey - (int)ex;
+  if (ex - 1u < 0x7feu - 1u && ey - 1u < 0x7feu - 1u && k > -26 && k < 26) {
+    const double z = gm_atan_core(gm_div(gm_u2d(uy & GM_ABS_MASK), gm_u2d(ux & GM_ABS_MASK)));
+    const double pi = GMC(PI_HI), pi_lo = GMC(PI_LO);
+    const double zx = (ux >> 63) ? pi - (z - pi_lo) : z; /* x < 0: second / third quadrant */
+    return (uy >> 63) ? -zx : zx;
+  }
+  return gm_atan2_slow(y, x);
+}
+GM_HD_CALL double gm_atan2(double y, double x) { return gm_atan2_inl(y, x); }
 
 GM_HD double gm_acos(double x) {
   if (gm_isnan(x)) return x + x;
@@ -340,35 +386,38 @@ GM_HD double gm_scale2(double y, int k) {
 }
 
 /* exp(x + xl), |xl| << |x| */
-GM_HD_CALL double gm_exp_dd(double x, double xl) {
+GM_HD_INL double gm_exp_dd_inl(double x, double xl) {
   if (gm_isnan(x)) return x + x;
   if (x > 709.782712893384) return gm_inf();
   if (x < -745.2) return 0.0;
-  double kd = gm_rint(x * GM_INV_LN2);
-  double r = gm_fma(-kd, GM_LN2_HI, x); /* exact */
-  double lo = gm_fma(-kd, GM_LN2_LO, xl);
+  double kd = gm_rint(x * GMC(INV_LN2));
+  double r = gm_fma(-kd, GMC(LN2_HI), x); /* exact */
+  double lo = gm_fma(-kd, GMC(LN2_LO), xl);
   double rr = r + lo;
   double rl = (r - rr) + lo;
-  double q = GM_EXP_C12;
-  q = gm_fma(q, rr, GM_EXP_C11);
-  q = gm_fma(q, rr, GM_EXP_C10);
-  q = gm_fma(q, rr, GM_EXP_C9);
-  q = gm_fma(q, rr, GM_EXP_C8);
-  q = gm_fma(q, rr, GM_EXP_C7);
-  q = gm_fma(q, rr, GM_EXP_C6);
-  q = gm_fma(q, rr, GM_EXP_C5);
-  q = gm_fma(q, rr, GM_EXP_C4);
-  q = gm_fma(q, rr, GM_EXP_C3);
-  q = gm_fma(q, rr, GM_EXP_C2);
-  q = gm_fma(q, rr, GM_EXP_C1);
-  q = gm_fma(q, rr, GM_EXP_C0);
+  double q = GMC(EXP_C12);
+  q = gm_fma(q, rr, GMC(EXP_C11));
+  q = gm_fma(q, rr, GMC(EXP_C10));
+  q = gm_fma(q, rr, GMC(EXP_C9));
+  q = gm_fma(q, rr, GMC(EXP_C8));
+  q = gm_fma(q, rr, GMC(EXP_C7));
+  q = gm_fma(q, rr, GMC(EXP_C6));
+  q = gm_fma(q, rr, GMC(EXP_C5));
+  q = gm_fma(q, rr, GMC(EXP_C4));
+  q = gm_fma(q, rr, GMC(EXP_C3));
+  q = gm_fma(q, rr, GMC(EXP_C2));
+  q = gm_fma(q, rr, GMC(EXP_C1));
+  q = gm_fma(q, rr, GMC(EXP_C0));
   double p = (rr * rr) * q;
   double s = rr + (p + gm_fma(rl, rr, rl));
   double y = 1.0 + s;
   return gm_scale2(y, (int)kd);
 }
 
+GM_HD_CALL double gm_exp_dd(double x, double xl) { return gm_exp_dd_inl(x, xl); }
+
 GM_HD double gm_exp(double x) { return gm_exp_dd(x, 0.0); }
+GM_HD_INL double gm_exp_inl(double x) { return gm_exp_dd_inl(x, 0.0); }
 
 /* log(x) as a double-double (hi, lo), x finite > 0 (subnormals handled) */
 GM_HD void gm_log_dd(double x, double* hi, double* lo) {
@@ -396,27 +445,27 @@ GM_HD void gm_log_dd(double x, double* hi, double* lo) {
   rem = gm_fma(-sh, dl, rem);
   double sl = rem / dh;
   double z = sh * sh;
-  double L = GM_LOG_C12;
-  L = gm_fma(L, z, GM_LOG_C11);
-  L = gm_fma(L, z, GM_LOG_C10);
-  L = gm_fma(L, z, GM_LOG_C9);
-  L = gm_fma(L, z, GM_LOG_C8);
-  L = gm_fma(L, z, GM_LOG_C7);
-  L = gm_fma(L, z, GM_LOG_C6);
-  L = gm_fma(L, z, GM_LOG_C5);
-  L = gm_fma(L, z, GM_LOG_C4);
-  L = gm_fma(L, z, GM_LOG_C3);
-  L = gm_fma(L, z, GM_LOG_C2);
-  L = gm_fma(L, z, GM_LOG_C1);
-  L = gm_fma(L, z, GM_LOG_C0);
+  double L = GMC(LOG_C12);
+  L = gm_fma(L, z, GMC(LOG_C11));
+  L = gm_fma(L, z, GMC(LOG_C10));
+  L = gm_fma(L, z, GMC(LOG_C9));
+  L = gm_fma(L, z, GMC(LOG_C8));
+  L = gm_fma(L, z, GMC(LOG_C7));
+  L = gm_fma(L, z, GMC(LOG_C6));
+  L = gm_fma(L, z, GMC(LOG_C5));
+  L = gm_fma(L, z, GMC(LOG_C4));
+  L = gm_fma(L, z, GMC(LOG_C3));
+  L = gm_fma(L, z, GMC(LOG_C2));
+  L = gm_fma(L, z, GMC(LOG_C1));
+  L = gm_fma(L, z, GMC(LOG_C0));
   double T = (sh * z) * L;      /* 2*atanh(sh) - 2*sh */
   T = gm_fma(2.0 * z, sl, T);   /* first-order effect of sl on the tail */
   double A = 2.0 * sh;
   double al = gm_fma(2.0, sl, T);
   double kd = (double)k;
-  double kh = kd * GM_LN2_HI;
-  double kl = gm_fma(kd, GM_LN2_HI, -kh);
-  kl = gm_fma(kd, GM_LN2_LO, kl);
+  double kh = kd * GMC(LN2_HI);
+  double kl = gm_fma(kd, GMC(LN2_HI), -kh);
+  kl = gm_fma(kd, GMC(LN2_LO), kl);
   double h = kh + A; /* TwoSum */
   double bb = h - kh;
   double e = (kh - (h - bb)) + (A - bb);
@@ -456,7 +505,8 @@ GM_HD int gm_is_odd_int(double y) {
   return !gm_is_int(h);
 }
 
-GM_HD_CALL double gm_pow(double x, double y) {
+/* every special case of pow: zero / one / infinite / NaN / negative arguments */
+GM_HD_CALL double gm_pow_slow(double x, double y) {
   if (y == 0.0) return 1.0;
   if (x == 1.0) return 1.0;
   if (gm_isnan(x) || gm_isnan(y)) return x + y;
@@ -486,5 +536,22 @@ GM_HD_CALL double gm_pow(double x, double y) {
   pl = gm_fma(y, ll, pl);
   return sgn * gm_exp_dd(ph, pl);
 }
+
+/* pow: a positive normal base other than 1 and a finite non-zero exponent (two integer tests) go straight to
+ * exp(y log x) in double-double; everything else takes gm_pow_slow.  Same operations on either route. */
+GM_HD_INL double gm_pow_inl(double x, double y) {
+  const uint64_t ux = gm_d2u(x), uy = gm_d2u(y);
+  const uint32_t ex = (uint32_t)(ux >> 52), ey = (uint32_t)(uy >> 52) & 0x7ffu; /* ex includes the sign bit */
+  if (ex - 1u < 0x7feu - 1u && ey != 0x7ffu && (uy << 1) != 0 && ux != 0x3ff0000000000000ull) {
+    double lh, ll;
+    gm_log_dd(x, &lh, &ll);
+    double ph = y * lh;
+    double pl = gm_fma(y, lh, -ph);
+    pl = gm_fma(y, ll, pl);
+    return gm_exp_dd_inl(ph, pl);
+  }
+  return gm_pow_slow(x, y);
+}
+GM_HD_CALL double gm_pow(double x, double y) { return gm_pow_inl(x, y); }
 
 #endif /* GELATO_B200_GMATH_H_ */

@@ -97,21 +97,25 @@ P_HD Vec3 quatrot(Quat q, Vec3 v) {
 struct Geodetic {
   double lat, lon, alt; /* radians, radians, metres */
 };
-/* WANT: bit0 altitude, bit1 longitude (latitude is always produced) */
-template <int WANT>
+/* WANT: bit0 altitude, bit1 longitude (latitude is always produced).  HOT: the elementary functions inlined
+ * (gmath.h: gm_xxx_inl) -- for the two callers that are the Jacobian kernel's long items. */
+template <int WANT, bool HOT = false>
 P_HD Geodetic ecef2geodetic(Vec3 r) {
   Geodetic g;
   double p = gm_sqrt(r.x * r.x + r.y * r.y);
-  double theta = gm_atan2(r.z * P_RA, p * P_RB);
+  double theta = HOT ? gm_atan2_inl(r.z * P_RA, p * P_RB) : gm_atan2(r.z * P_RA, p * P_RB);
   double st, ct;
-  gm_sincos(theta, &st, &ct);
-  g.lat = gm_atan2(r.z + P_EP2 * P_RB * (st * st * st), p - P_E2 * P_RA * (ct * ct * ct));
+  if (HOT) gm_sincos_inl(theta, &st, &ct);
+  else gm_sincos(theta, &st, &ct);
+  const double ny = r.z + P_EP2 * P_RB * (st * st * st), nx = p - P_E2 * P_RA * (ct * ct * ct);
+  g.lat = HOT ? gm_atan2_inl(ny, nx) : gm_atan2(ny, nx);
   g.lon = 0.0;
   g.alt = 0.0;
-  if (WANT & 2) g.lon = gm_atan2(r.y, r.x);
+  if (WANT & 2) g.lon = HOT ? gm_atan2_inl(r.y, r.x) : gm_atan2(r.y, r.x);
   if (WANT & 1) {
     double sl, cl;
-    gm_sincos(g.lat, &sl, &cl);
+    if (HOT) gm_sincos_inl(g.lat, &sl, &cl);
+    else gm_sincos(g.lat, &sl, &cl);
     double N = gm_div(P_RA, gm_sqrt(1.0 - P_E2 * sl * sl));
     g.alt = gm_div(p, cl) - N;
   }
@@ -136,22 +140,30 @@ P_HD Vec3 vel_ecef2eci_cs(Vec3 vel_ecef, Vec3 pos_ecef, double c, double s) {
 }
 
 /* Coordinate.cpp:85-98 quat_ecef2ned from geodetic lat/lon */
+template <bool HOT = false>
 P_HD Quat quat_ecef2ned_ll(double lat, double lon) {
   double s_hl, c_hl, s_hp, c_hp;
-  gm_sincos(lon / 2.0, &s_hl, &c_hl);
-  gm_sincos(lat / 2.0, &s_hp, &c_hp);
+  if (HOT) {
+    gm_sincos_inl(lon / 2.0, &s_hl, &c_hl);
+    gm_sincos_inl(lat / 2.0, &s_hp, &c_hp);
+  } else {
+    gm_sincos(lon / 2.0, &s_hl, &c_hl);
+    gm_sincos(lat / 2.0, &s_hp, &c_hp);
+  }
   double r2 = gm_sqrt(2.0);
   return q4(gm_div(c_hl * (c_hp - s_hp), r2), gm_div(s_hl * (c_hp + s_hp), r2), gm_div(-c_hl * (c_hp + s_hp), r2),
             gm_div(s_hl * (c_hp - s_hp), r2));
 }
 
 /* Coordinate.cpp:104-110 quat_ned2eci(pos_eci, t); c,s = cos/sin(omega t) */
+template <bool HOT = false>
 P_HD Quat quat_ned2eci_cs(Vec3 pos_eci, double wt, double c, double s) {
   double sh, ch;
-  gm_sincos(wt / 2.0, &sh, &ch);
+  if (HOT) gm_sincos_inl(wt / 2.0, &sh, &ch);
+  else gm_sincos(wt / 2.0, &sh, &ch);
   Quat q_eci2ecef = q4(ch, 0.0, 0.0, sh);
-  Geodetic g = ecef2geodetic<2>(rot_eci2ecef(pos_eci, c, s));
-  Quat q = eigen_quat_prod(q_eci2ecef, quat_ecef2ned_ll(g.lat, g.lon));
+  Geodetic g = ecef2geodetic<2, HOT>(rot_eci2ecef(pos_eci, c, s));
+  Quat q = eigen_quat_prod(q_eci2ecef, quat_ecef2ned_ll<HOT>(g.lat, g.lon));
   return quatconj(q);
 }
 
@@ -196,36 +208,42 @@ P_HD double geopotential_altitude(double z) {
 /* One row of the US-76 layer table (Air.cpp:31-45) and what depends on that row only:
  * R = Rstar / M, the pressure exponent -g0 / Lmb / R (gradient layers) and g0 / R (isothermal layers).
  * They are constant expressions of the row -- the reference evaluates them again on every call
- * (Air.cpp:62-67, 93-97); here the compiler folds them with the same IEEE divisions. */
+ * (Air.cpp:62-67, 93-97); here they are folded at compile time with the same IEEE divisions. */
 struct Us76Layer {
   double Hb, Lmb, Tmb, Pb, R, expo, g0_R;
 };
 #define US76_ROW(hb_, l_, t_, p_, m_)                                                                          \
+  { (hb_), (l_), (t_), (p_), 8314.32 / (m_), ((l_) != 0.0) ? -9.80665 / (l_) / (8314.32 / (m_)) : 0.0,         \
+    9.80665 / (8314.32 / (m_)) }
+#define US76_TABLE                                                                                             \
   {                                                                                                            \
-    L.Hb = (hb_); L.Lmb = (l_); L.Tmb = (t_); L.Pb = (p_); L.R = 8314.32 / (m_);                               \
-    L.expo = ((l_) != 0.0) ? -9.80665 / (l_) / (8314.32 / (m_)) : 0.0;                                         \
-    L.g0_R = 9.80665 / (8314.32 / (m_));                                                                       \
+    US76_ROW(0.0, -0.0065, 288.15, 101325.0, 28.9644), US76_ROW(11000.0, 0.0, 216.65, 22632.0, 28.9644),       \
+    US76_ROW(20000.0, 0.001, 216.65, 5474.9, 28.9644), US76_ROW(32000.0, 0.0028, 228.65, 868.02, 28.9644),     \
+    US76_ROW(47000.0, 0.0, 270.65, 110.91, 28.9644), US76_ROW(51000.0, -0.0028, 270.65, 66.939, 28.9644),      \
+    US76_ROW(71000.0, -0.002, 214.65, 3.9564, 28.9644), US76_ROW(86000.0, 0.0, 186.8673, 0.37338, 28.9522),    \
+    US76_ROW(91000.0, 0.0025, 186.8673, 0.15381, 28.89), US76_ROW(110000.0, 0.012, 240.0, 7.1042e-3, 27.27),   \
+    US76_ROW(120000.0, 0.012, 360.0, 2.5382e-3, 26.20)                                                         \
   }
+#if defined(__CUDACC__)
+static __constant__ Us76Layer us76_table_dev[11] = US76_TABLE;
+#endif
 P_HD Us76Layer us76_layer(double h) {
-  /* last layer whose base is <= h; layer 0 when h is below every base (Air.cpp:56-60).
-   * Branch ladder instead of a table: no local-memory indexing on the GPU. */
-  Us76Layer L;
-  US76_ROW(0.0, -0.0065, 288.15, 101325.0, 28.9644)
-  if (h >= 11000.0) US76_ROW(11000.0, 0.0, 216.65, 22632.0, 28.9644)
-  if (h >= 20000.0) US76_ROW(20000.0, 0.001, 216.65, 5474.9, 28.9644)
-  if (h >= 32000.0) US76_ROW(32000.0, 0.0028, 228.65, 868.02, 28.9644)
-  if (h >= 47000.0) US76_ROW(47000.0, 0.0, 270.65, 110.91, 28.9644)
-  if (h >= 51000.0) US76_ROW(51000.0, -0.0028, 270.65, 66.939, 28.9644)
-  if (h >= 71000.0) US76_ROW(71000.0, -0.002, 214.65, 3.9564, 28.9644)
-  if (h >= 86000.0) US76_ROW(86000.0, 0.0, 186.8673, 0.37338, 28.9522)
-  if (h >= 91000.0) US76_ROW(91000.0, 0.0025, 186.8673, 0.15381, 28.89)
-  if (h >= 110000.0) US76_ROW(110000.0, 0.012, 240.0, 7.1042e-3, 27.27)
-  if (h >= 120000.0) US76_ROW(120000.0, 0.012, 360.0, 2.5382e-3, 26.20)
-  return L;
+  /* last layer whose base is <= h; layer 0 when h is below every base (Air.cpp:56-60): the bases ascend, so
+   * that is a count of bases <= h -- ten compares and one indexed read of the row (the table sits in constant
+   * memory on the device) instead of a ladder that rewrote seven doubles per rung */
+  int k = 0;
+  k += (h >= 11000.0); k += (h >= 20000.0); k += (h >= 32000.0); k += (h >= 47000.0); k += (h >= 51000.0);
+  k += (h >= 71000.0); k += (h >= 86000.0); k += (h >= 91000.0); k += (h >= 110000.0); k += (h >= 120000.0);
+#if defined(__CUDA_ARCH__)
+  return us76_table_dev[k];
+#else
+  static const Us76Layer table[11] = US76_TABLE;
+  return table[k];
+#endif
 }
-#undef US76_ROW
 
-/* want: bit0 pressure+density, bit1 speed of sound */
+/* want: bit0 pressure+density, bit1 speed of sound.  HOT: elementary functions inlined (see ecef2geodetic). */
+template <bool HOT = false>
 P_HD AirState us76(double h, int want) {
   const double r0 = 6356766.0;
   const Us76Layer L = us76_layer(h);
@@ -247,10 +265,13 @@ P_HD AirState us76(double h, int want) {
   s.rho = 0.0;
   s.a = 0.0;
   if (want & 1) {
-    if (gm_fabs(Lmb) > 1.0e-6)
-      s.P = Pb * gm_pow(gm_div(Tmb + Lmb * (h - Hb), Tmb), L.expo); /* -g0 / Lmb / R */
-    else
-      s.P = Pb * gm_exp(gm_div(L.g0_R * (Hb - h), Tmb)); /* g0 / R * (Hb - h) / Tmb */
+    if (gm_fabs(Lmb) > 1.0e-6) {
+      const double base = gm_div(Tmb + Lmb * (h - Hb), Tmb);
+      s.P = Pb * (HOT ? gm_pow_inl(base, L.expo) : gm_pow(base, L.expo)); /* -g0 / Lmb / R */
+    } else {
+      const double arg = gm_div(L.g0_R * (Hb - h), Tmb); /* g0 / R * (Hb - h) / Tmb */
+      s.P = Pb * (HOT ? gm_exp_inl(arg) : gm_exp(arg));
+    }
     s.rho = gm_div(gm_div(s.P, R), s.T);
   }
   if (want & 2) s.a = gm_sqrt(1.4 * R * s.T);
@@ -261,19 +282,28 @@ P_HD AirState us76(double h, int want) {
 /* xp[i*stride], yp[i*stride]; lower_bound then idx-1 (x == xp[k] uses the interval
  * below; x == xp[0] would read xp[-1] in the reference -- defined here as interval 0,
  * like the oracle). */
-P_HD double interp_table(double x, const double* xp, const double* yp, int n, int stride) {
-  if (x < xp[0]) return yp[0];
-  if (x > xp[(n - 1) * stride]) return yp[(n - 1) * stride];
+/* interval of the table that x falls into: -1 below the first abscissa, -2 above the last, else idx */
+P_HD int interp_interval(double x, const double* xp, int n, int stride) {
+  if (x < xp[0]) return -1;
+  if (x > xp[(n - 1) * stride]) return -2;
   /* lower_bound over a sorted table = number of entries below x; the tables have a
    * handful of rows, so a branch-free count beats a divergent binary search */
   int lo = 0;
   for (int i = 0; i < n; i++) lo += (xp[i * stride] < x) ? 1 : 0;
   int idx = lo - 1;
   if (idx < 0) idx = 0;
+  return idx;
+}
+P_HD double interp_at(int idx, double x, const double* xp, const double* yp, int n, int stride) {
+  if (idx == -1) return yp[0];
+  if (idx == -2) return yp[(n - 1) * stride];
   double x_lower = xp[idx * stride], x_upper = xp[(idx + 1) * stride];
   double y_lower = yp[idx * stride], y_upper = yp[(idx + 1) * stride];
   double alpha = gm_div(x - x_lower, x_upper - x_lower);
   return y_lower + alpha * (y_upper - y_lower);
+}
+P_HD double interp_table(double x, const double* xp, const double* yp, int n, int stride) {
+  return interp_at(interp_interval(x, xp, n, stride), x, xp, yp, n, stride);
 }
 
 /* ---- the air right-hand side in three parts -------------------------------
@@ -302,11 +332,22 @@ enum { PW_GRAVITY = 1, PW_SOUND = 2 };
  * pybind_dynamics.cpp:43-46,49,55,66 / wrapper_utils.hpp:93-95,164-172 */
 P_HD_CALL void pos_part(double px, double py, double pz, const double* wind, int n_wind, int want, double* out) {
   Vec3 pos = v3(px, py, pz);
-  Geodetic g = ecef2geodetic<1>(pos);
+  Geodetic g = ecef2geodetic<1, true>(pos);
   double alt_gp = geopotential_altitude(g.alt);
-  out[PP_WIND_N] = interp_table(alt_gp, wind, wind + 1, n_wind, 3);
-  out[PP_WIND_E] = interp_table(alt_gp, wind, wind + 2, n_wind, 3);
-  AirState as = us76(alt_gp, 1 | (want & PW_SOUND));
+  /* wind_ned interpolates both components at the same altitude (wrapper_utils.hpp:82-87): one interval search, one
+   * interpolation weight -- the same quotient the two separate calls compute */
+  const int iv = interp_interval(alt_gp, wind, n_wind, 3);
+  if (iv < 0) {
+    const int row = iv == -1 ? 0 : (n_wind - 1) * 3;
+    out[PP_WIND_N] = wind[row + 1];
+    out[PP_WIND_E] = wind[row + 2];
+  } else {
+    const double* w0 = wind + iv * 3;
+    const double alpha = gm_div(alt_gp - w0[0], w0[3] - w0[0]);
+    out[PP_WIND_N] = w0[1] + alpha * (w0[4] - w0[1]);
+    out[PP_WIND_E] = w0[2] + alpha * (w0[5] - w0[2]);
+  }
+  AirState as = us76<true>(alt_gp, 1 | (want & PW_SOUND));
   out[PP_RHO] = as.rho;
   out[PP_PRESS] = as.P;
   out[PP_SOUND] = as.a;
@@ -325,8 +366,8 @@ enum { RQ_COS = 0, RQ_SIN, RQ_W, RQ_X, RQ_Y, RQ_Z, RQ_COLS };
 P_HD_CALL void rotq_part(double px, double py, double pz, double t, double* out) {
   double wt = P_OMEGA * t;
   double s, c;
-  gm_sincos(wt, &s, &c);
-  Quat q = quat_ned2eci_cs(v3(px, py, pz), wt, c, s);
+  gm_sincos_inl(wt, &s, &c);
+  Quat q = quat_ned2eci_cs<true>(v3(px, py, pz), wt, c, s);
   out[RQ_COS] = c;
   out[RQ_SIN] = s;
   out[RQ_W] = q.w;
@@ -507,7 +548,7 @@ P_HD double sin_elevation(Vec3 pos, double t, Vec3 p_ant) {
   Vec3 d = sub3(rot_eci2ecef(pos, c, s), p_ant);
   Vec3 dir = div3(d, norm3(d)); /* normalize(): dynamic vector v / v.norm() */
   Geodetic g = ecef2geodetic<2>(p_ant);
-  Quat q_ned2ecef = quatconj(quat_ecef2ned_ll(g.lat, g.lon));
+  Quat q_ned2ecef = quatconj(quat_ecef2ned_ll<>(g.lat, g.lon));
   Vec3 vert = quatrot(q_ned2ecef, v3(0.0, 0.0, -1.0));
   /* np.dot of two 3-vectors: BLAS ddot accumulates with fused multiply-add, ascending index
    * (the same order the kernels use for D.X) */

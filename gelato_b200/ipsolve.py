@@ -38,8 +38,9 @@ class _LBFGS:
     """Damped limited-memory BFGS approximation B = sigma I - U M^-1 U^T of the Hessian of the Lagrangian
     (compact form of Byrd, Nocedal & Schnabel 1994), U = [sigma S, Y]."""
 
-    def __init__(self, n, memory):
+    def __init__(self, n, memory, sigma_min=1e-8, sigma_max=1e8):
         self.n, self.m = n, memory
+        self.sigma_min, self.sigma_max = sigma_min, sigma_max
         self.reset()
 
     def reset(self, sigma=1.0):
@@ -71,7 +72,7 @@ class _LBFGS:
         if len(self.S) > self.m:
             self.S.pop(0)
             self.Y.pop(0)
-        self.sigma = min(max(float(y @ y) / sy, 1e-6), 1e8)
+        self.sigma = min(max(sy / ss, self.sigma_min), self.sigma_max)  # IPOPT limited_memory_initialization = scalar1
         self._U = None
 
     def factors(self):
@@ -87,11 +88,89 @@ class _LBFGS:
         return self._U, self._M
 
 
+class _ReducedHessian:
+    """W ~ sigma I + Z C Z^T: the EXACT Hessian of the Lagrangian on the null space of the equality Jacobian (Z: an
+    orthonormal basis, n x k with k = n - m_E, a few dozen for a transcribed trajectory problem), sigma I on its
+    complement.  Z^T W Z comes from k directional finite differences of the Lagrangian's gradient (k extra `sens`
+    calls per iteration -- one batched launch for the CUDA callbacks), is symmetrised and its eigenvalues are lifted to
+    stay positive, so the KKT matrix keeps the right inertia without a correction loop.  The cross term Z^T W Y is
+    dropped, as in reduced-Hessian SQP."""
+
+    def __init__(self, n, floor_rel=1e-6):
+        self.n = n
+        self.floor_rel = floor_rel
+        self.sigma = 1.0
+        self.Z = None
+        self.C = None
+        self.S = []  # (interface of _LBFGS, for the log line)
+        self.idx = None
+
+    def reset(self, sigma=None):
+        pass
+
+    def update(self, s, y):
+        pass
+
+    def times(self, v):
+        if self.Z is None:
+            return self.sigma * v
+        return self.sigma * v + self.Z @ (self.C @ (self.Z.T @ v))
+
+    def additive(self):
+        """(U, C^-1) with W = sigma I + U C U^T, or None."""
+        if self.Z is None:
+            return None
+        return self.Z, np.linalg.inv(self.C)
+
+    def choose_basis(self, JE):
+        """Independent variables: the columns a pivoted QR of the equality Jacobian leaves for last."""
+        import scipy.linalg as sla
+
+        if JE.shape[1] > 6000:
+            raise NotImplementedError("dense basis selection is meant for transcriptions of a few thousand variables")
+        R, piv = sla.qr(JE.toarray(), mode="r", pivoting=True)
+        d = np.abs(np.diag(R))
+        rank = int((d > 1e-11 * d[0]).sum())
+        self.idx = np.sort(piv[rank:])
+
+    def build(self, JE, lagr_grad, x, eps):
+        """lagr_grad(x) -> J_E(x)^T lam_E + J_I(x)^T lam_I with the CURRENT multipliers (the objective is linear)."""
+        n, mE = self.n, JE.shape[0]
+        if self.idx is None:
+            self.choose_basis(JE)
+        k = self.idx.size
+        if k == 0:
+            self.Z = None
+            return 0
+        K = sp.bmat([[sp.identity(n), JE.T], [JE, -1e-12 * sp.identity(mE)]], format="csc")
+        E = np.zeros((n + mE, k))
+        E[self.idx, np.arange(k)] = 1.0
+        Zr = spla.splu(K).solve(E)[:n]
+        Z, R = np.linalg.qr(Zr)
+        if np.abs(np.diag(R)).min() < 1e-8 * np.abs(np.diag(R)).max():  # the independent set went stale: choose again
+            self.choose_basis(JE)
+            return self.build(JE, lagr_grad, x, eps)
+        g0 = lagr_grad(x)
+        H = np.empty((k, k))
+        for i in range(k):
+            H[:, i] = Z.T @ ((lagr_grad(x + eps * Z[:, i]) - g0) / eps)
+        H = 0.5 * (H + H.T)
+        w, V = np.linalg.eigh(H)
+        floor = max(1e-8, self.floor_rel * float(np.abs(w).max()))
+        w = np.maximum(np.abs(w), floor)  # |lambda|: a saddle direction is treated as a convex one of the same curvature
+        self.sigma = 0.5 * float(w.min())
+        self.Z = Z
+        self.C = (V * (w - self.sigma)) @ V.T
+        return k
+
+
 class IPSolver:
     """solver = IPSolver({"tol": 1e-6, "max_iter": 2000}); sol = solver(optProb, sens=sens)."""
 
     DEFAULTS = {"tol": 1e-6, "max_iter": 2000, "mu_init": 0.1, "memory": 12, "bound_push": 1e-2,
-                "scaling_max_gradient": 100.0, "acceptable_tol": 1e-4, "acceptable_iter": 15, "verbose": 0}
+                "scaling_max_gradient": 100.0, "acceptable_tol": 1e-4, "acceptable_iter": 15, "verbose": 0,
+                "sigma_max": 1e8, "recalc_y": True, "hessian": "reduced-fd", "fd_eps": 1e-5, "floor_rel": 1e-2, "ignore_bounds": False, "globalization": "filter", "feasible": True, "feasible_iter": 4,
+                "feasible_tol": 1e-9}
 
     def __init__(self, options=None):
         self.opt = dict(self.DEFAULTS)
@@ -111,6 +190,8 @@ class IPSolver:
         x = np.concatenate([v[2] for v in prob.vars]).astype(float)
         xl = np.concatenate([np.full(v[1], -np.inf if v[3] is None else v[3]) for v in prob.vars])
         xu = np.concatenate([np.full(v[1], np.inf if v[4] is None else v[4]) for v in prob.vars])
+        if o["ignore_bounds"]:
+            xl[:], xu[:] = -np.inf, np.inf
         eq = [g for g in prob.cons if g[3] is not None and g[2] == g[3]]
         ineq = [g for g in prob.cons if g not in eq]
         for g in ineq:
@@ -181,7 +262,22 @@ class IPSolver:
         zs = mu / s
         lamI = -zs.copy()
         lamE = self._ls_multipliers(g, JE, JI, zL, zU, lamI)
-        B = _LBFGS(n, o["memory"])
+        exact = o["hessian"] == "reduced-fd"
+        B = _ReducedHessian(n, o["floor_rel"]) if exact else _LBFGS(n, o["memory"], sigma_max=o["sigma_max"])
+
+        def lagr_grad_at(lE, lI):
+            def fn(xv):
+                t0 = time.perf_counter()
+                sj, fail = sens(xdict(xv), None)
+                stat["sens_t"] += time.perf_counter() - t0
+                stat["sens_n"] += 1
+                je = DE @ self._jac(sj, eq, mE, n, col0)
+                ji = DI @ self._jac(sj, ineq, mI, n, col0)
+                return je.T @ lE + ji.T @ lI
+            return fn
+
+        last = (0.0, 0.0, "")
+        nu = 1.0
         filt = None  # the filter of the current barrier problem
         theta_max = theta_min = 0.0
         fails_in_a_row = 0
@@ -206,8 +302,9 @@ class IPSolver:
             E0 = max(du_inf, viol, compl(0.0) / s_d)
             history.append((f0 / df, viol, du_inf, mu))
             if o["verbose"] and (it % o["verbose"] == 0):
-                print("it %4d  obj %.8f  viol %.2e  dual %.2e  mu %.1e  filter %d  mem %d  fails %d"
-                      % (it, f0 / df, viol, du_inf, mu, 0 if filt is None else len(filt), len(B.S), fails))
+                print("it %4d  obj %.8f  viol %.2e  dual %.2e  mu %.1e  filter %d  mem %d  fails %d  |lamE| %.2e  alpha %.2e  |dx| %.2e  sigma %.2e %s"
+                      % (it, f0 / df, viol, du_inf, mu, 0 if filt is None else len(filt), len(B.S), fails,
+                         np.abs(lamE).max(initial=0.0), last[0], last[1], B.sigma, last[2]))
             if E0 <= tol:
                 status, message = 0, "converged to tol %g" % tol
                 break
@@ -222,6 +319,8 @@ class IPSolver:
                 filt = None
             tau = max(0.99, 1.0 - mu)
 
+            if exact:
+                B.build(JE, lagr_grad_at(lamE, lamI), x, o["fd_eps"])
             # ---- Newton step of the barrier problem ----
             SigL = np.where(hasL, zL / np.maximum(x - xl, 1e-300), 0.0)
             SigU = np.where(hasU, zU / np.maximum(xu - x, 1e-300), 0.0)
@@ -271,6 +370,11 @@ class IPSolver:
             def in_filter(th, ph):
                 return th >= theta_max or any(th >= (1.0 - g_th) * t_ and ph >= p_ - g_ph * t_ for t_, p_ in filt)
 
+            use_merit = o["globalization"] == "merit"
+            if use_merit:
+                lam_inf = max(np.abs(lamE + dlE).max(initial=0.0), np.abs(lamI + dlI).max(initial=0.0))
+                nu = max(nu, 1.5 * lam_inf) if nu >= lam_inf else 1.5 * lam_inf + 1.0
+                Dmerit = gphi_d - nu * theta0
             alpha = a_max
             accepted = False
             armijo_step = False
@@ -284,7 +388,11 @@ class IPSolver:
                 thetat = np.abs(cEt).sum() + np.abs(cIt - st).sum()
                 phit = barrier(xt, st, ft)
                 ok = np.isfinite(phit) and np.isfinite(thetat) and not in_filter(thetat, phit)
-                if ok:
+                if use_merit:  # l1 exact-penalty merit function instead of the filter
+                    ok = np.isfinite(phit) and np.isfinite(thetat) and \
+                        phit + nu * thetat <= phi0 + nu * theta0 + 1e-4 * alpha * min(Dmerit, 0.0) + 1e-13 * abs(phi0)
+                    armijo_step = True
+                elif ok:
                     switching = gphi_d < 0 and theta0 <= theta_min and alpha * (-gphi_d) ** 2.3 > theta0 ** 1.1
                     if switching:
                         ok = phit <= phi0 + eta * alpha * gphi_d + 10.0 * np.finfo(float).eps * abs(phi0)
@@ -308,8 +416,11 @@ class IPSolver:
                         f2, cE2, cI2, _, _, _ = scaled(evaluate(x2, False))
                         th2 = np.abs(cE2).sum() + np.abs(cI2 - s2).sum()
                         phi2 = barrier(x2, s2, f2)
-                        if np.isfinite(phi2) and not in_filter(th2, phi2) and (
-                                th2 <= (1.0 - g_th) * theta0 or phi2 <= phi0 - g_ph * theta0):
+                        soc_ok = np.isfinite(phi2) and not in_filter(th2, phi2) and (
+                            th2 <= (1.0 - g_th) * theta0 or phi2 <= phi0 - g_ph * theta0)
+                        if use_merit:
+                            soc_ok = np.isfinite(phi2) and phi2 + nu * th2 <= phi0 + nu * theta0 + 1e-4 * a2 * min(Dmerit, 0.0)
+                        if soc_ok:
                             step_dx, step_ds, alpha = dx2, ds2, a2
                             accepted = True
                             break
@@ -359,6 +470,7 @@ class IPSolver:
                 dlE, dlI = np.zeros(mE), np.zeros(mI)
                 B.reset(B.sigma)
             fails_in_a_row = 0
+            last = (alpha, float(np.abs(alpha * step_dx).max()), "armijo" if armijo_step else ("soc" if step_dx is not dx else "theta"))
             # ---- accept: primal and equality multipliers with alpha, bound multipliers with their own step ----
             x_new, s_new = x + alpha * step_dx, s + alpha * step_ds
             lamE_new = lamE + alpha * dlE
@@ -372,6 +484,27 @@ class IPSolver:
             zU = np.where(hasU, np.clip(zU, mu / (ks * np.maximum(xu - x_new, 1e-300)), ks * mu / np.maximum(xu - x_new, 1e-300)), 0.0)
             zs = np.clip(zs, mu / (ks * s_new), ks * mu / s_new)
             f_new, cE_new, cI_new, g_new, JE_new, JI_new = scaled(evaluate(x_new, True))
+            if o["feasible"]:
+                # back onto the constraint manifold: least-norm Newton steps on the equality rows (quadratic convergence;
+                # each costs one callback pair).  The quasi-Newton pairs are then differences between FEASIBLE points, so the
+                # approximation learns the curvature along the manifold -- the only curvature the tangential step needs.
+                for _r in range(o["feasible_iter"]):
+                    if np.abs(cE_new).max(initial=0.0) <= o["feasible_tol"]:
+                        break
+                    dxr = self._feasibility_step(JE_new, JI_new[:0], cE_new, np.zeros(0), n, mE, 0)
+                    if dxr is None:
+                        break
+                    a = min(1.0, max_step(np.where(hasL, x_new - xl, 1.0), np.where(hasL, dxr, 0.0), tau),
+                            max_step(np.where(hasU, xu - x_new, 1.0), np.where(hasU, -dxr, 0.0), tau))
+                    x_try = x_new + a * dxr
+                    ev_try = scaled(evaluate(x_try, True))
+                    if not np.isfinite(ev_try[1]).all() or np.abs(ev_try[1]).max(initial=0.0) >= np.abs(cE_new).max(initial=0.0):
+                        break
+                    x_new = x_try
+                    f_new, cE_new, cI_new, g_new, JE_new, JI_new = ev_try
+                s_new = np.maximum(cI_new, np.minimum(s_new, mu))
+            if o["recalc_y"]:  # least-squares equality multipliers at the new point (IPOPT recalc_y)
+                lamE_new = self._ls_multipliers(g_new, JE_new, JI_new, zL, zU, lamI_new, fallback=lamE_new)
             yk = (g_new + JE_new.T @ lamE_new + JI_new.T @ lamI_new) - (g + JE.T @ lamE_new + JI.T @ lamI_new)
             B.update(x_new - x, yk)
             x, s, lamE, lamI = x_new, s_new, lamE_new, lamI_new
@@ -415,7 +548,7 @@ class IPSolver:
         return sp.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(nrow, nvar)).tocsr()
 
     @staticmethod
-    def _ls_multipliers(g, JE, JI, zL, zU, lamI):
+    def _ls_multipliers(g, JE, JI, zL, zU, lamI, fallback=None):
         """Least-squares estimate of the equality multipliers: min || g + JE^T lam + JI^T lamI - zL + zU ||."""
         mE = JE.shape[0]
         if mE == 0:
@@ -423,12 +556,13 @@ class IPSolver:
         n = JE.shape[1]
         K = sp.bmat([[sp.identity(n), JE.T], [JE, -1e-10 * sp.identity(mE)]], format="csc")
         rhs = np.concatenate((-(g + JI.T @ lamI - zL + zU), np.zeros(mE)))
+        zero = np.zeros(mE) if fallback is None else fallback
         try:
             lam = spla.splu(K).solve(rhs)[n:]
         except RuntimeError:
-            return np.zeros(mE)
-        if not np.all(np.isfinite(lam)) or np.abs(lam).max() > 1e3:
-            return np.zeros(mE)
+            return zero
+        if not np.all(np.isfinite(lam)) or (fallback is None and np.abs(lam).max() > 1e3):
+            return zero
         return lam
 
     def _kkt_solve(self, B, diag_x, JE, JI, inv_sigs, rhs, n, mE, mI, reuse=False):
@@ -444,7 +578,13 @@ class IPSolver:
             except RuntimeError:
                 return None
             self._W = None
-            if B.S:
+            add = B.additive() if hasattr(B, "additive") else None
+            if add is not None:  # W = sigma I + U C U^T
+                U, Cinv = add
+                Ubar = np.vstack((U, np.zeros((mE + mI, U.shape[1]))))
+                KU = self._lu.solve(Ubar)
+                self._W = (Ubar, -KU, Cinv + Ubar.T @ KU)
+            elif B.S:  # W = sigma I - U M^-1 U^T
                 U, M = B.factors()
                 Ubar = np.vstack((U, np.zeros((mE + mI, U.shape[1]))))
                 KU = self._lu.solve(Ubar)

@@ -13,3 +13,5 @@ V1(gmt_exp, gm_exp)
 V1(gmt_log, gm_log)
 V2(gmt_atan2, gm_atan2)
 V2(gmt_pow, gm_pow)
+V2(gmt_atan2_slow, gm_atan2_slow)
+V2(gmt_pow_slow, gm_pow_slow)

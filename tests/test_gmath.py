@@ -82,3 +82,27 @@ def test_special_values(shim):
     assert _call2(shim, "gmt_atan2", np.array([0.0]), np.array([1.0]))[0] == 0.0
     assert abs(_call2(shim, "gmt_atan2", np.array([1.0]), np.array([0.0]))[0] - np.pi / 2) < 1e-15
     assert _call1(shim, "gmt_exp", x[:1])[0] == 1.0
+
+
+def test_fast_paths_equal_the_complete_functions(shim):
+    """gm_atan2 / gm_pow send the common case (normal operands, moderate exponents) straight to the range reduction
+    and everything else to gm_atan2_slow / gm_pow_slow, which are the complete functions.  Both routes must give the
+    same bits: random operands over the whole exponent range, every pairing of the special values, and operands
+    around the dispatch thresholds."""
+    rng = np.random.default_rng(5)
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308,
+                        1.7976931348623157e308, -1.7976931348623157e308, 2.0 ** -27, 2.0 ** 26, 2.0 ** 25, 2.0 ** -26,
+                        2.0 ** 66, 0.5, 2.0, 3.0, -3.0, 1.0 + 2.0 ** -52, 1.0 - 2.0 ** -53])
+    a = np.concatenate((np.repeat(special, special.size), rng.standard_normal(200000) * 10.0 ** rng.uniform(-320, 308, 200000),
+                        rng.standard_normal(200000) * 2.0 ** rng.integers(-30, 30, 200000)))
+    b = np.concatenate((np.tile(special, special.size), rng.standard_normal(200000) * 10.0 ** rng.uniform(-320, 308, 200000),
+                        rng.standard_normal(200000) * 2.0 ** rng.integers(-30, 30, 200000)))
+    with np.errstate(all="ignore"):
+        for fast, slow in (("gmt_atan2", "gmt_atan2_slow"), ("gmt_pow", "gmt_pow_slow")):
+            x, y = _call2(shim, fast, a, b), _call2(shim, slow, a, b)
+            same = (x.view(np.uint64) == y.view(np.uint64)) | (np.isnan(x) & np.isnan(y))
+            assert same.all(), (fast, a[~same][:5], b[~same][:5], x[~same][:5], y[~same][:5])
+        # pow with the operands the atmosphere uses (base around 1, exponents -35 .. 35)
+        base, ex = rng.uniform(0.2, 1.6, 200000), rng.uniform(-35.0, 35.0, 200000)
+        x, y = _call2(shim, "gmt_pow", base, ex), _call2(shim, "gmt_pow_slow", base, ex)
+        assert np.array_equal(x.view(np.uint64), y.view(np.uint64))
