@@ -61,28 +61,47 @@ __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* 
   jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 3, sm);
 }
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen, const int32_t* __restrict__ scen_ids,
+k_jacobian(const __grid_constant__ PlanView P, const int32_t* __restrict__ block_table, const int n_scen, const int32_t* __restrict__ scen_ids,
            const double* __restrict__ x_all, double* __restrict__ out_all, double* __restrict__ g_all) {
   jacobian_body<JR_ALL>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
 }
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian_heavy(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+k_jacobian_heavy(const __grid_constant__ PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
                  const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
                  double* __restrict__ g_all) {
   jacobian_body<JR_HEAVY>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
 }
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
-k_jacobian_light(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+k_jacobian_light(const __grid_constant__ PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
                  const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
                  double* __restrict__ g_all) {
   jacobian_body<JR_LIGHT>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
+}
+
+// Vacuum dynamics nodes: one thread per node, no shared memory, no barrier (jobs.h: dyn_noair_node).
+#ifndef GV_THREADS
+#define GV_THREADS 128
+#endif
+__global__ void __launch_bounds__(GV_THREADS)
+k_jacobian_noair(const __grid_constant__ PlanView P, const int first, const int count, const int n_scen,
+                 const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
+                 double* __restrict__ g_all) {
+  const int per = (count + GV_THREADS - 1) / GV_THREADS;  // blocks per scenario
+  const int scen = blockIdx.x / per;
+  const int k = (blockIdx.x - scen * per) * GV_THREADS + threadIdx.x;
+  if (k >= count) return;
+  const double* x = x_all + (size_t)scen * P.n_vars;
+  double* out = out_all + (size_t)scen * (size_t)(P.packed ? P.n_pack : P.n_vals);
+  double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
+  const int sid = scen_ids ? scen_ids[scen] : scen;
+  dyn_noair_node(P, sid, x, out, g, jac_node(P, first + k));
 }
 
 #ifndef GR_MIN_BLOCKS
 #define GR_MIN_BLOCKS 8 /* 64 registers; measured best of 5, 8, 10 (profiles/r01g_ab.txt) */
 #endif
 __global__ void __launch_bounds__(GR_THREADS, GR_MIN_BLOCKS)
-k_residuals(const PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
+k_residuals(const __grid_constant__ PlanView P, const int32_t* __restrict__ block_table, const int n_scen,
             const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ g_all) {
   __shared__ ResScratch sm;
   const int scen = blockIdx.x % n_scen;
@@ -175,6 +194,7 @@ struct GelatoPlan {
   int n_jac_blocks = 0, n_jac_main = 0;
   int32_t *jac_heavy = nullptr, *jac_light = nullptr;  // the same blocks by role group (measurements)
   int n_jac_heavy = 0, n_jac_light = 0;
+  int vac_first = 0, n_vac = 0;  // vacuum dynamics nodes: k_jacobian_noair, one thread per node
   int32_t* res_blocks = nullptr;
   int n_res_blocks = 0;
   // packed output (plan_host.h: build_packed_layout)
@@ -245,21 +265,39 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
   return GELATO_OK;
 }
 
-// One Jacobian evaluation on `st`.  g_dev != NULL: pair evaluation -- the blocks also write objfunc's rows (the
-// dynamics blocks their nodes' collocation defects, the aero / event blocks their rows at the pristine state) and the
-// linear-row blocks at the end of the table are launched too.  packed: output layout.
+// One Jacobian evaluation: the block kernel (air dynamics nodes, aero rows, fallback nodes, event rows) on `st` and the
+// one-thread-per-node kernel of the vacuum nodes on `aux`, forked from and joined back into `st` with the two events.
+// g_dev != NULL: pair evaluation -- both also write objfunc's rows (collocation defects of their nodes, aero / event
+// rows at the pristine state) and the linear-row blocks at the end of the block table are launched too.
+// packed: output layout.
 // (Variants measured and dropped: phase 0 as its own launch with pp | rq | q staged through L2, 38 % slower,
-// profiles/r01i_split_ab.txt; role-specialised kernels on two streams, no overlap, profiles/r02a_ab_probe.txt.)
+// profiles/r01i_split_ab.txt; the vacuum nodes as blocks of the block kernel, 0.084 ms instead of 0.03,
+// profiles/r02_probe.txt.)
 static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* out_dev, double* g_dev, int n_scen, cudaStream_t st,
-                           const int32_t* ids_dev, bool packed) {
+                           cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, const int32_t* ids_dev, bool packed) {
   PlanView v = p->view;
   v.packed = packed ? 1 : 0;
   const int nb = g_dev ? p->n_jac_blocks : p->n_jac_main;
+  const bool side = p->n_vac > 0 && nb > 0 && aux != st;
+  if (side) {
+    CU(cudaEventRecord(ev_fork, st));
+    CU(cudaStreamWaitEvent(aux, ev_fork, 0));
+  }
+  if (p->n_vac > 0) {
+    const int per = (p->n_vac + GV_THREADS - 1) / GV_THREADS;
+    k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, side ? aux : st>>>(v, p->vac_first, p->n_vac, n_scen, ids_dev, x_dev,
+                                                                                out_dev, g_dev);
+    p->launches++;
+  }
   if (nb > 0) {
     k_jacobian<<<(unsigned)nb * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, ids_dev, x_dev, out_dev, g_dev);
     p->launches++;
   }
   CU(cudaGetLastError());
+  if (side) {
+    CU(cudaEventRecord(ev_join, aux));
+    CU(cudaStreamWaitEvent(st, ev_join, 0));
+  }
   return GELATO_OK;
 }
 
@@ -343,6 +381,8 @@ int gelato_plan_create(const GelatoPlanDesc* d, int device, GelatoPlan** out) {
   p->n_jac_blocks = (int)(ht.jac_blocks.size() / BT_COLS);
   p->n_res_blocks = (int)(ht.res_blocks.size() / BT_COLS);
   p->n_jac_main = ht.n_jac_main;
+  p->vac_first = ht.vac_first;
+  p->n_vac = ht.n_vac;
   p->n_jac_heavy = (int)(ht.jac_heavy.size() / BT_COLS);
   p->n_jac_light = (int)(ht.jac_light.size() / BT_COLS);
   if ((rc = upload(p, ht.jac_heavy.data(), ht.jac_heavy.size(), &tb)) != GELATO_OK) { gelato_plan_destroy(p); return rc; }
@@ -533,7 +573,7 @@ int gelato_eval_pair_dev(GelatoPlan* p, const double* x_dev, double* g_dev, doub
   // objfunc's rows come out of the Jacobian launch: the dynamics blocks hold the right-hand side of the pristine
   // x as their centre column and subtract it from the D.X products; aero and event blocks carry one more column
   // at the pristine state; the linear rows are blocks of their own (no second pass over the physics)
-  return launch_jacobian(p, x_dev, vals_dev, g_dev, n_scen, st, nullptr, false);
+  return launch_jacobian(p, x_dev, vals_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
 }
 
 int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
@@ -542,7 +582,7 @@ int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_de
   if (rc) return rc;
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, nullptr, true);
+  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, true);
 }
 
 int gelato_fill_template(GelatoPlan* p, double* vals_dev, int32_t n_scen, void* stream) {
@@ -568,7 +608,7 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   // the constants and D entries of vals_dev were put there once by gelato_fill_template;
   // the kernels rewrite every x-dependent slot and never touch the rest
-  return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, nullptr, false);
+  return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
 }
 
 static int ensure_staging(GelatoPlan* p, size_t n_scen) {
@@ -658,7 +698,8 @@ static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, p->d_ids,
                                                                                 p->d_x, p->d_g);
       p->launches++;
-    } else if ((rc = launch_jacobian(p, p->d_x, d_out, nullptr, n_scen, p->stream, p->d_ids, false))) {
+    } else if ((rc = launch_jacobian(p, p->d_x, d_out, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join,
+                                     p->d_ids, false))) {
       return rc;
     }
     CU(cudaGetLastError());
@@ -829,7 +870,8 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
     CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     CU(cudaEventRecord(L.ev_h2d, L.stream));
     // g != NULL: pair evaluation, the residual rows come out of the same launches
-    if ((rc = launch_jacobian(p, dx, dvals, g ? dg : nullptr, ns, L.stream, ids, false))) return rc;
+    if ((rc = launch_jacobian(p, dx, dvals, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join, ids, false)))
+      return rc;
     if (g) {  // its copy travels on the side stream, next to the Jacobian's transfers
       CU(cudaEventRecord(L.ev_g, L.stream));
       CU(cudaStreamWaitEvent(L.pair_stream, L.ev_g, 0));
@@ -959,7 +1001,8 @@ static int eval_packed(GelatoPlan* p, const double* x, double* g, double* packed
     if (k > 0) CU(cudaStreamWaitEvent(L.stream, p->lanes[k - 1].ev_h2d, 0));  // uploads one after the other (and after the ids)
     CU(cudaMemcpyAsync(dx, hx + (size_t)s0 * v.n_vars, (size_t)ns * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, L.stream));
     CU(cudaEventRecord(L.ev_h2d, L.stream));
-    if ((rc = launch_jacobian(p, dx, dpk, g ? dg : nullptr, ns, L.stream, need_ids ? p->d_pids + s0 : nullptr, true)))
+    if ((rc = launch_jacobian(p, dx, dpk, g ? dg : nullptr, ns, L.stream, L.pair_stream, L.ev_fork, L.ev_join,
+                              need_ids ? p->d_pids + s0 : nullptr, true)))
       return rc;
     // both results on the lane's copy stream, after everything of the slice has been computed
     CU(cudaEventRecord(L.ev_kernel, L.stream));
@@ -1094,15 +1137,23 @@ int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, doub
   if (which == 0) {
     k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, st>>>(v, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
   } else if (which == 1) {
-    return launch_jacobian(p, x_dev, out_dev, g_dev, n_scen, st, nullptr, packed != 0);
+    return launch_jacobian(p, x_dev, out_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, packed != 0);
   } else if (which == 2) {
     if (p->n_jac_heavy == 0) return fail(GELATO_ERR_ARG, "the plan has no heavy blocks");
     k_jacobian_heavy<<<(unsigned)p->n_jac_heavy * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_heavy, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else if (which == 3) {
     if (p->n_jac_light == 0) return fail(GELATO_ERR_ARG, "the plan has no light blocks");
     k_jacobian_light<<<(unsigned)p->n_jac_light * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_light, n_scen, nullptr, x_dev, out_dev, g_dev);
+  } else if (which == 5) {
+    if (p->n_vac == 0) return fail(GELATO_ERR_ARG, "the plan has no vacuum nodes");
+    const int per = (p->n_vac + GV_THREADS - 1) / GV_THREADS;
+    k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, st>>>(v, p->vac_first, p->n_vac, n_scen, nullptr, x_dev, out_dev, g_dev);
+  } else if (which == 6) {  // the block kernel alone, as an evaluation launches it
+    const int nb = g_dev ? p->n_jac_blocks : p->n_jac_main;
+    if (nb == 0) return fail(GELATO_ERR_ARG, "the plan has no Jacobian blocks");
+    k_jacobian<<<(unsigned)nb * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else {
-    return fail(GELATO_ERR_ARG, "which must be 0, 1, 2 or 3");
+    return fail(GELATO_ERR_ARG, "which must be 0, 1, 2, 3, 5 or 6");
   }
   p->launches++;
   CU(cudaGetLastError());
@@ -1121,7 +1172,9 @@ int gelato_time_kernel(GelatoPlan* p, int which, const double* x_dev, double* ou
     if (which == 0) {
       k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, nullptr, x_dev, out_dev);
     } else if (which == 1) {  // the whole Jacobian evaluation (heavy and light kernels)
-      if ((rc = launch_jacobian(p, x_dev, out_dev, nullptr, n_scen, p->stream, nullptr, false))) return rc;
+      if ((rc = launch_jacobian(p, x_dev, out_dev, nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork, p->ev_join, nullptr,
+                                false)))
+        return rc;
       continue;
     } else if (which == 2) {  // the heavy roles' blocks alone (air dynamics + aero rows)
       if (p->n_jac_heavy > 0)

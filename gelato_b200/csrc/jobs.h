@@ -295,32 +295,35 @@ P_HD void pos_variant(const double* b, int pv, double dx, double* out) {
 /* quaternion kinematics (con_dynamics.py:580-613): the state already carries one residue from
  * the velocity pass; variants 0 centre | 1-4 quaternion component | 5-6 control | 7 the PRISTINE state
  * (what objfunc evaluates, con_dynamics.py:525-530: the residual rows of a pair evaluation) */
-P_HD void dyn_quat_variants(const PlanView& P, const double* x, const NodeRef& nr, const Units& un, double* out) {
+P_HD void dyn_quat_variant(const PlanView& P, const double* x, const NodeRef& nr, const Units& un, int var, double* out) {
   const double dx = un.dx;
-  double qp[4], q0[4], u0[2];
-  for (int k = 0; k < 4; k++) qp[k] = x[P.off_quat + 4 * nr.row + k];
-  for (int k = 0; k < 4; k++) q0[k] = residue(qp[k], dx);
-  for (int k = 0; k < 2; k++) u0[k] = x[P.off_u + 2 * (nr.ua + nr.j) + k];
-  for (int var = 0; var < NQV; var++) {
-    double qv[4] = {q0[0], q0[1], q0[2], q0[3]}, uv[2] = {u0[0], u0[1]};
-    if (var >= 1 && var <= 4) {
-      const int k = var - 1;
-      for (int w = 0; w < k; w++) qv[w] = residue(qv[w], dx);
-      qv[k] = qv[k] + dx;
-    } else if (var == 5 || var == 6) {
-      const int k = var - 5;
-      for (int w = 0; w < 4; w++) qv[w] = residue(qv[w], dx);
-      for (int w = 0; w < k; w++) uv[w] = residue(uv[w], dx);
-      uv[k] = uv[k] + dx;
-    } else if (var == 7) {
-      for (int w = 0; w < 4; w++) qv[w] = qp[w];
+  double qv[4], uv[2];
+  for (int k = 0; k < 4; k++) qv[k] = x[P.off_quat + 4 * nr.row + k];
+  for (int k = 0; k < 2; k++) uv[k] = x[P.off_u + 2 * (nr.ua + nr.j) + k];
+  if (var != 7)
+    for (int k = 0; k < 4; k++) qv[k] = residue(qv[k], dx);
+  if (var >= 1 && var <= 4) {
+    const int k = var - 1;
+    for (int w = 0; w < 4; w++) {
+      if (w < k) qv[w] = residue(qv[w], dx);
+      else if (w == k) qv[w] = qv[w] + dx;
     }
-    Quat d = rhs_quaternion(q4(qv[0], qv[1], qv[2], qv[3]), uv[0], uv[1], un.u);
-    out[4 * var + 0] = d.w;
-    out[4 * var + 1] = d.x;
-    out[4 * var + 2] = d.y;
-    out[4 * var + 3] = d.z;
+  } else if (var == 5 || var == 6) {
+    const int k = var - 5;
+    for (int w = 0; w < 4; w++) qv[w] = residue(qv[w], dx);
+    for (int w = 0; w < 2; w++) {
+      if (w < k) uv[w] = residue(uv[w], dx);
+      else if (w == k) uv[w] = uv[w] + dx;
+    }
   }
+  Quat d = rhs_quaternion(q4(qv[0], qv[1], qv[2], qv[3]), uv[0], uv[1], un.u);
+  out[0] = d.w;
+  out[1] = d.x;
+  out[2] = d.y;
+  out[3] = d.z;
+}
+P_HD void dyn_quat_variants(const PlanView& P, const double* x, const NodeRef& nr, const Units& un, double* out) {
+  for (int var = 0; var < NQV; var++) dyn_quat_variant(P, x, nr, un, var, out + 4 * var);
 }
 
 /* finite-difference quotients of one (node, lane) and their output slots.
@@ -479,7 +482,7 @@ P_HD void dyn_scatter_block(const PlanView& P, int scen, const double* x, double
 /*   3  finite-difference quotients -> output slots (+ defects, pair mode)     */
 /*   (phase 1 is unused: the numbering is shared with the other roles)        */
 /* ========================================================================= */
-P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+GM_HD_INL void dyn_air_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
                         int tid, int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
@@ -545,7 +548,7 @@ P_HD void dyn_air_phase(const PlanView& P, int scen, const double* x, double* va
 /*   2  column items (node, 9 lanes: centre, mass, position x3, quaternion x4)*/
 /*   3  quotients -> output slots (+ defects, pair mode)                      */
 /* ========================================================================= */
-P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+GM_HD_INL void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
                           int tid, int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
@@ -591,12 +594,63 @@ P_HD void dyn_noair_phase(const PlanView& P, int scen, const double* x, double* 
 }
 
 /* ========================================================================= */
+/* Vacuum nodes, ONE THREAD PER NODE (kernel k_jacobian_noair): a vacuum        */
+/* right-hand side is ~70 flops, so sharing gravity among its columns through   */
+/* shared memory and two block barriers cost more than it saved -- the blocks   */
+/* were latency bound with most threads idle (ncu r02b: 0.084 ms for 2 % of the */
+/* arithmetic).  Here a thread walks its node's columns in registers and stores */
+/* each quotient as soon as it has it; no shared memory, no barrier, and enough */
+/* resident threads to hide the chain.  Same per-(node, lane) functions, same   */
+/* bits.                                                                        */
+/* ========================================================================= */
+P_HD void dyn_noair_node(const PlanView& P, int scen, const double* x, double* vals, double* g, const NodeRef& nr) {
+  const Units un = scen_units(P, scen);
+  const double dx = un.dx;
+  const SecParam sp = sec_param(P, scen, nr.sec);
+  const bool hold = nr.flags & GSF_HOLD;
+  double fc[3], fl[3], qc[4] = {0.0, 0.0, 0.0, 0.0}, ql[4] = {0.0, 0.0, 0.0, 0.0};
+  double v[11], p[3];
+  /* centre column: pristine state, gravity at the pristine position */
+  dyn_col_state(P, x, nr.row, 0, false, dx, v);
+  pos_variant(x + P.off_pos + 3 * nr.row, 0, dx, p);
+  Vec3 gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+  Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), gr, sp, un);
+  fc[0] = f.x; fc[1] = f.y; fc[2] = f.z;
+  if (!hold) dyn_quat_variant(P, x, nr, un, 0, qc);
+  dyn_scatter(P, scen, x, vals, nr, 0, fc, fc, qc, qc);   /* eqcon_dyn_quat / t */
+  dyn_scatter(P, scen, x, vals, nr, 12, fc, fc, qc, qc);  /* eqcon_dyn_vel / t (analytic in vacuum) */
+  dyn_scatter(P, scen, x, vals, nr, 14, fc, fc, qc, qc);  /* eqcon_dyn_pos / velocity, t */
+  for (int lane = 1; lane <= 11; lane++) {
+    const bool vel_lane = lane >= 5 && lane <= 7; /* no velocity columns in vacuum; lanes 5, 6 still carry u columns */
+    if (!vel_lane) {
+      dyn_col_state(P, x, nr.row, lane, false, dx, v);
+      if (lane <= 4 || lane == 8) { /* the position changes with lanes 2-4 and is fully restored from lane 5 on */
+        pos_variant(x + P.off_pos + 3 * nr.row, lane_pv(lane), dx, p);
+        gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+      }
+      f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), gr, sp, un);
+      fl[0] = f.x; fl[1] = f.y; fl[2] = f.z;
+    }
+    if (!hold && lane <= 6) dyn_quat_variant(P, x, nr, un, lane, ql);
+    dyn_scatter(P, scen, x, vals, nr, lane, fc, fl, qc, ql);
+  }
+  if (g) { /* pair evaluation: the node's collocation defects */
+    double lh[11], qp[4] = {0.0, 0.0, 0.0, 0.0};
+    if (!hold) dyn_quat_variant(P, x, nr, un, 7, qp);
+    for (int grp = 0; grp < 4; grp++) {
+      dyn_lh_item(P, x, nr, grp, lh);
+      dyn_res_finish(P, scen, x, g, nr, grp, lh, fc, qp);
+    }
+  }
+}
+
+/* ========================================================================= */
 /* Jacobian kernel, DYN_GEN role (fallback): 16 lanes per node, every lane a  */
 /* full right-hand side.  Used for sections whose reference_area is negative  */
 /* (air formula, but no velocity / time finite differences: con_dynamics.py:  */
 /* 257 vs :403,454).                                                          */
 /* ========================================================================= */
-P_HD void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
+GM_HD_INL void dyn_gen_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count,
                         int tid, int phase, const JacScratch& sm) {
   const int nl = tid >> 4, lane = tid & 15;
   if (nl >= count) return;
@@ -833,7 +887,7 @@ P_HD void aero_base(const PlanView& P, const double* x, int sec, int row, double
   }
 }
 
-P_HD void aero_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count, int tid,
+GM_HD_INL void aero_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count, int tid,
                      int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
   const double dx = P.un.dx;
@@ -1126,14 +1180,18 @@ P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k
 /* Block dispatch.  Jacobian blocks run GJ_PHASES phases with a block barrier  */
 /* between them; residual blocks run three (only the dynamics role uses 0, 2).  */
 /* ROLES is the mask of roles an instantiation of the Jacobian kernel contains  */
-/* (the shipped kernel: all of them; subsets exist for measurements).           */
+/* (the shipped kernel: all of them; subsets exist for measurements).  The      */
+/* dispatch and the role functions are forced inline: the kernel calls them     */
+/* once per phase with a constant phase number, and a copy left as a real call  */
+/* takes the phase at run time and the plan view / scratch through local memory */
+/* (measured: 0.29 -> 0.42 ms, 600 MB of local-memory traffic per launch).      */
 /* ========================================================================= */
 #define JR_HEAVY ((1 << BR_DYN_AIR) | (1 << BR_AERO))
 #define JR_LIGHT ((1 << BR_DYN_NOAIR) | (1 << BR_DYN_GEN) | (1 << BR_EVT) | (1 << BR_LIN))
 #define JR_ALL (JR_HEAVY | JR_LIGHT)
 P_HD void lin_res(const PlanView& P, int scen, const double* x, double* g, int k);
 template <int ROLES>
-P_HD void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, double* g,
+GM_HD_INL void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, const double* x, double* vals, double* g,
                           int tid, int phase, const JacScratch& sm) {
   const int start = bt[BT_START], count = bt[BT_COUNT], role = bt[BT_ROLE];
   if ((ROLES >> BR_DYN_AIR & 1) && role == BR_DYN_AIR) dyn_air_phase(P, scen, x, vals, g, start, count, tid, phase, sm);

@@ -120,6 +120,7 @@ struct HostTables {
    * role group (measurements).  res_blocks: the residual kernel's. */
   std::vector<int32_t> jac_blocks, jac_heavy, jac_light, res_blocks;
   int n_jac_main = 0;
+  int vac_first = 0, n_vac = 0; /* vacuum nodes [vac_first, vac_first + n_vac) of jac_rec: one thread per node */
   std::vector<NodeRec> node_rec;               /* [N] natural order */
   std::vector<NodeRec> jac_rec;                /* [N] air-FD nodes, then vacuum nodes, then fallback nodes */
   std::vector<AeroRec> aero_rows;              /* one per aero constraint row */
@@ -277,17 +278,18 @@ static inline void build_host_tables(const GelatoPlanDesc* d, HostTables& h) {
   const int n_aero_rows = (int)h.aero_rows.size();
 
   /* Jacobian blocks: the heavy roles' (air dynamics, aero rows) and the light roles' (vacuum dynamics, fallback,
-   * event rows) interleaved evenly, so that the blocks resident on an SM at one time mix FP64-issue-bound and
+   * event rows; vacuum dynamics nodes are not blocks at all: k_jacobian_noair, one thread per node) interleaved evenly, so that the blocks resident on an SM at one time mix FP64-issue-bound and
    * latency-bound work (separate kernels on separate streams ran one after the other: the first fills every SM;
    * profiles/r02a_ab_probe.txt); then the linear-row blocks, which only a pair evaluation launches */
   std::vector<int32_t> heavy, light;
   push_chunks(heavy, BR_DYN_AIR, 0, (int)air.size(), GD_NODES);
   push_chunks(heavy, BR_AERO, 0, n_aero_rows, GJ_NODES);
-  push_chunks(light, BR_DYN_NOAIR, (int)air.size(), (int)vac.size(), GN_NODES);
   push_chunks(light, BR_DYN_GEN, (int)(air.size() + vac.size()), (int)gen.size(), GG_NODES);
   push_chunks(light, BR_EVT, 0, d->n_evt, GJ_EVT);
   h.jac_heavy = heavy;
   h.jac_light = light;
+  h.vac_first = (int)air.size(); /* vacuum nodes: one thread each, kernel k_jacobian_noair */
+  h.n_vac = (int)vac.size();
   std::vector<int32_t>& jb = h.jac_blocks;
   const long long nh = (long long)heavy.size() / BT_COLS, nl = (long long)light.size() / BT_COLS;
   for (long long ih = 0, il = 0; ih < nh || il < nl;) {

@@ -110,6 +110,8 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
       for (int phase = 0; phase < GJ_PHASES; phase++)
         for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase<JR_ALL>(P, sid, bt, x, vals, g, tid, phase, sm);
     }
+    /* vacuum dynamics nodes: one thread each (kernel k_jacobian_noair) */
+    for (int k = 0; k < h.n_vac; k++) dyn_noair_node(P, sid, x, vals, g, jac_node(P, h.vac_first + k));
   }
   return 0;
 }

@@ -55,6 +55,10 @@ def main():
         "light_packed": timed(lambda: E.launch_kernel_dev(3, x, p_, B, True, st)),
         "light_packed_g": timed(lambda: E.launch_kernel_dev(3, x, p_, B, True, st, g)),
         "jac_packed": timed(lambda: E.launch_kernel_dev(1, x, p_, B, True, st)),
+        "blocks_only": timed(lambda: E.launch_kernel_dev(6, x, p_, B, True, st)),
+        "blocks_only_g": timed(lambda: E.launch_kernel_dev(6, x, p_, B, True, st, g)),
+        "noair": timed(lambda: E.launch_kernel_dev(5, x, p_, B, True, st)),
+        "noair_g": timed(lambda: E.launch_kernel_dev(5, x, p_, B, True, st, g)),
         "res_full": timed(lambda: E.launch_kernel_dev(0, x, g, B, False, st)),
         "serial_heavy_light_g": timed(lambda: (E.launch_kernel_dev(2, x, p_, B, True, st, g), E.launch_kernel_dev(3, x, p_, B, True, st, g))),
         "jacobian_coo": timed(lambda: E.eval_jacobian_dev(x, v, B, st)),
