@@ -994,7 +994,7 @@ struct EvtOut {
 
 /* evaluate the leaf of an event job: pe/ve non-dimensional state row, t_e non-dimensional */
 P_HD EvtOut evt_leaf(const PlanView& P, int scen, int type, const double* ef, const double* pe, const double* ve,
-                     double t_e) {
+                     double t_e, int ei_comp = 0, int nrow = 1) {
   const Units un = scen_units(P, scen);
   EvtOut o;
   o.v[0] = o.v[1] = o.v[2] = 0.0;
@@ -1012,10 +1012,10 @@ P_HD EvtOut evt_leaf(const PlanView& P, int scen, int type, const double* ef, co
     o.v[0] = (orbit_energy(pos, vel) / ef[GE_A0]) - 1.0;
     o.v[1] = (angular_momentum(pos, vel) / ef[GE_A1]) - 1.0;
     o.v[2] = inclination_rad(pos, vel) - ef[GE_A2];
-  } else { /* GE_USER_PERIGEE: example/user_constraints.py:133-137 */
-    double a, e;
-    orbital_a_e(pos, vel, &a, &e);
-    o.v[0] = (a * (1.0 - e) / 6378137.0) - 1.0;
+  } else { /* GE_USER_ORBIT: rows q / scale - offset (example/user_constraints.py:133-137 is perigee / 6378137 - 1) */
+    const int codes = ei_comp;
+    for (int r = 0; r < nrow && r < 3; r++)
+      o.v[r] = (orbit_quantity((codes >> (8 * r)) & 0xff, pos, vel) / ef[GE_A0 + 2 * r]) - ef[GE_A0 + 2 * r + 1];
   }
   return o;
 }
@@ -1047,11 +1047,11 @@ P_HD void evt_res(const PlanView& P, int scen, const double* x, double* g, int j
   const double* ef = P.evt_f64 + job * GE_F64_COLS;
   const int type = ei[GE_TYPE], srow = ei[GE_SROW];
   const double t_e = (ei[GE_TIDX] >= 0) ? x[P.off_t + ei[GE_TIDX]] : 0.0;
-  EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t_e);
+  EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t_e, ei[GE_COMP], ei[GE_NROW]);
   if (type == GE_TERM) {
     for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o.v[r];
-  } else if (type >= GE_USER_PERIGEE) {
-    g[ei[GE_ROW]] = o.v[0];
+  } else if (type >= GE_USER_ORBIT) {
+    for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o.v[r];
   } else {
     g[ei[GE_ROW]] = evt_form_value(ei[GE_FORM], o.v[ei[GE_COMP]], ef[GE_REF], ef[GE_DEN]);
   }
@@ -1061,10 +1061,10 @@ P_HD void evt_res(const PlanView& P, int scen, const double* x, double* g, int j
  *   LLH / ANT : 0 centre | 1-3 pos j | 4 t                       (con_waypoint.py:54-66, 570-578)
  *   IIP       : 0 centre | 1 p0 2 v0 3 p1 4 v1 5 p2 6 v2 | 7 t   (:225-236, interleaved)
  *   TERM      : 0 centre | 1-3 pos j | 4-6 vel j                  (con_init_terminal_knot.py:391-399)
- *   PERIGEE   : 0 base | 1-6 FD of p0 p1 p2 v0 v1 v2 | 7-12 background after k restores
+ *   USER_ORBIT: 0 base | 1-6 FD of p0 p1 p2 v0 v1 v2 | 7-12 background after k restores
  *               (jac_fd.py:54-60 restricted to the six variables the function reads) */
 P_HD int evt_n_lanes(int type) {
-  return type == GE_IIP ? 8 : (type == GE_TERM ? 7 : (type == GE_USER_PERIGEE ? 13 : 5));
+  return type == GE_IIP ? 8 : (type == GE_TERM ? 7 : (type == GE_USER_ORBIT ? 13 : 5));
 }
 
 P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, int tid, bool pair, const JacScratch& sm) {
@@ -1075,7 +1075,7 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
   if (lane == 15) { /* pair evaluation: the leaf at the PRISTINE state -- objfunc's row (evt_res) */
     if (!pair) return;
     const double t0 = (ei[GE_TIDX] >= 0) ? x[P.off_t + ei[GE_TIDX]] : 0.0;
-    EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t0);
+    EvtOut o = evt_leaf(P, scen, type, ef, x + P.off_pos + 3 * srow, x + P.off_vel + 3 * srow, t0, ei[GE_COMP], ei[GE_NROW]);
     sm.f[3 * tid + 0] = o.v[0];
     sm.f[3 * tid + 1] = o.v[1];
     sm.f[3 * tid + 2] = o.v[2];
@@ -1092,7 +1092,7 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
   if (type == GE_IIP) {
     order[0] = 0; order[1] = 3; order[2] = 1; order[3] = 4; order[4] = 2; order[5] = 5;
     nvar = 6;
-  } else if (type == GE_TERM || type == GE_USER_PERIGEE) {
+  } else if (type == GE_TERM || type == GE_USER_ORBIT) {
     for (int k = 0; k < 6; k++) order[k] = k;
     nvar = 6;
   } else {
@@ -1104,7 +1104,7 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
     if (lane <= nvar) { /* FD lane for variable order[lane-1] */
       n_restored = lane - 1;
       perturbed = order[lane - 1];
-    } else if (type == GE_USER_PERIGEE) { /* background lanes 7..12: k = lane-6 restores done */
+    } else if (type == GE_USER_ORBIT) { /* background lanes 7..12: k = lane-6 restores done */
       n_restored = lane - 6;
     } else { /* the t lane: every variable already restored */
       n_restored = nvar;
@@ -1113,7 +1113,7 @@ P_HD void evt_jac_phase1(const PlanView& P, int scen, const double* x, int job, 
     for (int k = 0; k < n_restored; k++) s[order[k]] = residue(s[order[k]], dx);
     if (perturbed >= 0) s[perturbed] = s[perturbed] + dx;
   }
-  EvtOut o = evt_leaf(P, scen, type, ef, s, s + 3, t_e);
+  EvtOut o = evt_leaf(P, scen, type, ef, s, s + 3, t_e, ei[GE_COMP], ei[GE_NROW]);
   sm.f[3 * tid + 0] = o.v[0];
   sm.f[3 * tid + 1] = o.v[1];
   sm.f[3 * tid + 2] = o.v[2];
@@ -1130,8 +1130,8 @@ P_HD void evt_jac_phase2(const PlanView& P, double* vals, double* g, int job, in
     const double* o = sm.f + 3 * tid;
     if (type == GE_TERM) {
       for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o[r];
-    } else if (type >= GE_USER_PERIGEE) {
-      g[ei[GE_ROW]] = o[0];
+    } else if (type >= GE_USER_ORBIT) {
+      for (int r = 0; r < ei[GE_NROW]; r++) g[ei[GE_ROW] + r] = o[r];
     } else {
       g[ei[GE_ROW]] = evt_form_value(ei[GE_FORM], o[ei[GE_COMP]], ef[GE_REF], ef[GE_DEN]);
     }
@@ -1147,8 +1147,9 @@ P_HD void evt_jac_phase2(const PlanView& P, double* vals, double* g, int job, in
     for (int r = 0; r < nrow; r++) vals[base + r] = fd_div(sm.f[3 * tid + r] - sm.f[3 * c + r], dx);
     return;
   }
-  if (type == GE_USER_PERIGEE) { /* aux tail: fd[6] then background[6] */
-    vals[ej[GE_J_POS] + (lane - 1)] = fd_div(sm.f[3 * tid] - sm.f[3 * c], dx);
+  if (type == GE_USER_ORBIT) { /* aux tail, per row: fd[6] then background[6] */
+    for (int r = 0; r < ei[GE_NROW]; r++)
+      vals[ej[GE_J_POS] + r * GE_USER_AUX + (lane - 1)] = fd_div(sm.f[3 * tid + r] - sm.f[3 * c + r], dx);
     return;
   }
   const int comp = ei[GE_COMP], form = ei[GE_FORM];

@@ -579,4 +579,48 @@ P_HD void orbital_a_e(Vec3 pos, Vec3 vel, double* a_out, double* e_out) {
   *e_out = e;
 }
 
+/* Coordinate.cpp:197-245 orbital_elements: a, e, inclination, ascending node, argument of perigee, true anomaly (radians) */
+P_HD void orbital_elements6(Vec3 pos, Vec3 vel, double* out) {
+  const Vec3 nr = normalized3(pos);
+  const Vec3 c = cross3(pos, vel);
+  const Vec3 f = sub3(cross3(vel, c), scale3(P_MU, nr));
+  const Vec3 c1 = normalized3(c);
+  const Vec3 f1 = normalized3(f);
+  const double inc = gm_acos(c1.z);
+  double asc = 0.0, argp = 0.0;
+  if (inc > 1.0e-10) {
+    asc = gm_atan2(c1.x, -c1.y);
+    double sa, ca;
+    gm_sincos(asc, &sa, &ca);
+    argp = gm_acos(dot3(v3(ca, sa, 0.0), f1));
+    if (f.z < 0.0) argp *= -1.0;
+  } else {
+    if (norm3(f) > 1.0e-10) argp = gm_atan2(f.y, f.x);
+  }
+  const double p = dot3(c, c) / P_MU;
+  const double e = norm3(f) / P_MU;
+  double ta = gm_acos(dot3(f1, nr));
+  if (dot3(vel, pos) < 0.0) ta = 2.0 * P_PI - ta;
+  if (asc < 0.0) asc += 2.0 * P_PI;
+  if (argp < 0.0) argp += 2.0 * P_PI;
+  if (ta < 0.0) ta += 2.0 * P_PI;
+  out[0] = p / (1.0 - e * e); out[1] = e; out[2] = inc; out[3] = asc; out[4] = argp; out[5] = ta;
+}
+
+/* one orbit quantity of a user built-in (include/gelato_b200.h: GEQ_*), from the elements / leaves the reference's
+ * own user constraints would call (example/user_constraints.py:96-139) */
+P_HD double orbit_quantity(int code, Vec3 pos, Vec3 vel) {
+  if (code == 5) return orbit_energy(pos, vel);
+  if (code == 6) return angular_momentum(pos, vel);
+  double el[6];
+  orbital_elements6(pos, vel, el);
+  switch (code) {
+    case 0: return el[0] * (1.0 - el[1]);
+    case 1: return el[0] * (1.0 + el[1]);
+    case 2: return el[0];
+    case 3: return el[1];
+    default: return el[2] * 180.0 / P_PI; /* the wrapper returns degrees: wrapper_coordinate.hpp:204 */
+  }
+}
+
 #endif /* GELATO_B200_PHYSICS_H_ */

@@ -72,7 +72,12 @@ static inline const char* validate_desc(const GelatoPlanDesc* d) {
     if (ei[GE_TIDX] < -1 || ei[GE_TIDX] > S) return "event job time index out of range";
     if (ei[GE_ROW] < 1 || ei[GE_ROW] + ei[GE_NROW] > d->n_rows || ei[GE_NROW] < 1 || ei[GE_NROW] > 3)
       return "event job rows out of range";
-    if (ei[GE_COMP] < 0 || ei[GE_COMP] > 2) return "event job component out of range";
+    if (ei[GE_TYPE] == GE_USER_ORBIT) {
+      for (int r = 0; r < ei[GE_NROW]; r++)
+        if (((ei[GE_COMP] >> (8 * r)) & 0xff) >= GEQ_N) return "unknown quantity code of a user built-in";
+    } else if (ei[GE_COMP] < 0 || ei[GE_COMP] > 2) {
+      return "event job component out of range";
+    }
     for (int c = 0; c < 7; c++)
       if (ei[GE_RC0 + c] < 0) return "negative residue count of an event job";
   }
@@ -106,7 +111,7 @@ static inline const char* validate_desc(const GelatoPlanDesc* d) {
     const int type = ei[GE_TYPE];
     bool ok;
     if (type == GE_TERM) ok = GELATO_RANGE(ej[GE_J_POS], 3 * ei[GE_NROW]) && GELATO_RANGE(ej[GE_J_VEL], 3 * ei[GE_NROW]);
-    else if (type >= GE_USER_PERIGEE) ok = GELATO_RANGE(ej[GE_J_POS], GE_USER_AUX);
+    else if (type >= GE_USER_ORBIT) ok = GELATO_RANGE(ej[GE_J_POS], GE_USER_AUX * ei[GE_NROW]);
     else ok = GELATO_RANGE(ej[GE_J_POS], 3) && GELATO_RANGE(ej[GE_J_T], 1) && (type != GE_IIP || GELATO_RANGE(ej[GE_J_VEL], 3));
     if (!ok) return "an event job's Jacobian block is outside vals";
   }
@@ -216,8 +221,8 @@ static inline void build_packed_layout(const GelatoPlanDesc* d, PackedLayout& L)
     if (type == GE_TERM) {
       pk[GE_J_POS] = direct(ej[GE_J_POS], 3 * ei[GE_NROW]);
       pk[GE_J_VEL] = direct(ej[GE_J_VEL], 3 * ei[GE_NROW]);
-    } else if (type >= GE_USER_PERIGEE) {
-      pk[GE_J_POS] = direct(ej[GE_J_POS], GE_USER_AUX);
+    } else if (type >= GE_USER_ORBIT) {
+      pk[GE_J_POS] = direct(ej[GE_J_POS], (long long)GE_USER_AUX * ei[GE_NROW]);
     } else {
       pk[GE_J_POS] = direct(ej[GE_J_POS], 3);
       if (type == GE_IIP) pk[GE_J_VEL] = direct(ej[GE_J_VEL], 3);

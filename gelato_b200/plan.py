@@ -50,24 +50,51 @@ GL_SCALE_PLUS, GL_SCALE_MINUS, GL_CONST, GL_F64_COLS = range(4)
 GA_KIND, GA_SECTION, GA_NK, GA_ROW0, GA_I32_COLS = range(5)
 GA_J_POS, GA_J_VEL, GA_J_QUAT, GA_J_T, GA_I64_COLS = range(5)
 GA_LIMIT, GA_F64_COLS = range(2)
-GE_LLH, GE_IIP, GE_ANT, GE_TERM, GE_USER_PERIGEE = range(5)
+GE_LLH, GE_IIP, GE_ANT, GE_TERM, GE_USER_ORBIT = range(5)
+GE_USER_PERIGEE = GE_USER_ORBIT
 GE_TYPE, GE_TIDX, GE_SROW, GE_COMP, GE_FORM, GE_ROW, GE_NROW, GE_RC0 = range(8)
 GE_I32_COLS = GE_RC0 + 7
 (GEF_DIFF_OVER_DEN, GEF_NEG_DIFF_OVER_DEN, GEF_RATIO_M1, GEF_NEG_RATIO_P1, GEF_REF_MINUS_OVER_DEN,
  GEF_MINUS_REF) = range(6)
 GE_J_POS, GE_J_VEL, GE_J_T, GE_I64_COLS = range(4)
-GE_REF, GE_DEN, GE_A0, GE_A1, GE_A2, GE_F64_COLS = range(6)
+GE_REF, GE_DEN, GE_A0, GE_A1, GE_A2, GE_A3, GE_A4, GE_A5, GE_F64_COLS = range(9)
 
-AUX_PER_USER = 12  # 6 finite differences + 6 "background" quotients (jobs.h, GE_USER_PERIGEE)
+AUX_PER_USER = 12  # per row: 6 finite differences + 6 "background" quotients (jobs.h, GE_USER_ORBIT)
+
+# quantity codes of the user built-ins (include/gelato_b200.h: GEQ_*)
+ORBIT_QUANTITIES = {"perigee_radius": 0, "apogee_radius": 1, "semi_major_axis": 2, "eccentricity": 3,
+                    "inclination_deg": 4, "orbit_energy": 5, "angular_momentum": 6}
 
 
-class PerigeeAtEvent:
-    """GPU-resident built-in for the shipped example's user constraint
-    (/root/reference/example/user_constraints.py:120-139): perigee radius ratio
-    a(1-e)/6378137 - 1 of the state at the first node of a named event."""
+class OrbitAtEvent:
+    """GPU-resident built-in user constraint (the registry the reference's `user_constraints.py` hook maps onto,
+    /root/reference/lib/con_user.py:33-42): up to three rows
+
+        g_r = quantity_r(position, velocity at the first node of `event_name`) / scale_r - offset_r
+
+    with quantity_r one of ORBIT_QUANTITIES -- the orbital elements and orbit integrals the reference exposes to
+    user constraints (`lib.coordinate_c.orbital_elements`, `orbit_energy`, `angular_momentum`;
+    example/user_constraints.py:96-139 is `perigee_radius / 6378137 - 1`).  One row returns a scalar, like the
+    shipped example; several return a vector, and `jac_fd`'s dense blocks get one line per row."""
+
+    def __init__(self, event_name, rows):
+        self.event_name = event_name
+        self.rows = [(str(q), float(scale), float(offset)) for q, scale, offset in rows]
+        if not 1 <= len(self.rows) <= 3:
+            raise ValueError("a built-in user constraint has one to three rows")
+        for q, scale, _ in self.rows:
+            if q not in ORBIT_QUANTITIES:
+                raise ValueError("unknown quantity %r (known: %s)" % (q, ", ".join(sorted(ORBIT_QUANTITIES))))
+            if scale == 0.0:
+                raise ValueError("scale must be non-zero")
+
+
+class PerigeeAtEvent(OrbitAtEvent):
+    """The shipped example's user constraint (/root/reference/example/user_constraints.py:120-139): perigee radius
+    ratio a(1-e)/6378137 - 1 of the state at the first node of a named event."""
 
     def __init__(self, event_name):
-        self.event_name = event_name
+        super().__init__(event_name, [("perigee_radius", 6378137.0, 1.0)])
 
 
 class Block:
@@ -119,10 +146,10 @@ class CompiledPlan:
             o += self.sizes[k]
         self.n_vars = o
         for fn in (user_eq, user_ineq):
-            if fn is not None and not isinstance(fn, PerigeeAtEvent):
+            if fn is not None and not isinstance(fn, OrbitAtEvent):
                 raise TypeError(
-                    "user constraints evaluated on the GPU must be registered built-ins (PerigeeAtEvent); "
-                    "arbitrary Python callables cannot run inside the CUDA kernels")
+                    "user constraints evaluated on the GPU must be registered built-ins (OrbitAtEvent / "
+                    "PerigeeAtEvent); arbitrary Python callables cannot run inside the CUDA kernels")
         self.user_eq, self.user_ineq = user_eq, user_ineq
 
         self._sec = [self.ps.get_index(i) for i in range(S)]
@@ -658,8 +685,9 @@ class CompiledPlan:
             rc[3 + k] = int(self._rc[self.off["velocity"] + 3 * srow + k])
         if tidx >= 0:
             rc[6] = int(self._rc[self.off["t"] + tidx])
+        a = list(a) + [0.0] * (6 - len(a))
         job = {"i32": [typ, tidx, srow, comp, form, row, nrow] + rc, "i64": [-1, -1, -1],
-               "f64": [float(ref), float(den), float(a[0]), float(a[1]), float(a[2])]}
+               "f64": [float(ref), float(den)] + [float(v) for v in a[:6]]}
         self._evt.append(job)
         for var in perturb:
             self._rc[self.off[var] + 3 * srow: self.off[var] + 3 * srow + 3] += 1
@@ -798,8 +826,13 @@ class CompiledPlan:
             return
         index = self.p["event_index"][fn.event_name]
         srow = self.ps.index_start_u(index) + index
-        g0 = self._begin(key, 1)
-        job = self._evt_job(GE_USER_PERIGEE, -1, srow, 0, 0, g0, 1, 0.0, 1.0)
+        k = len(fn.rows)
+        g0 = self._begin(key, k)
+        codes = sum(ORBIT_QUANTITIES[q] << (8 * r) for r, (q, _, _) in enumerate(fn.rows))
+        a = [1.0, 0.0] * 3
+        for r, (_, scale, offset) in enumerate(fn.rows):
+            a[2 * r], a[2 * r + 1] = scale, offset
+        job = self._evt_job(GE_USER_ORBIT, -1, srow, codes, 0, g0, k, 0.0, 1.0, a=a)
         self.blocks[key] = ("dense-user", job, srow)
         # jac_fd perturbs and restores EVERY variable in place (jac_fd.py:54-60)
         self._rc += 1
@@ -813,7 +846,7 @@ class CompiledPlan:
             b = self.blocks.get(key)
             if isinstance(b, tuple):
                 b[1]["i64"][GE_J_POS] = self._nvals
-                self._nvals += AUX_PER_USER
+                self._nvals += AUX_PER_USER * b[1]["i32"][GE_NROW]
         self.n_vals = self._nvals
         tmpl = np.zeros(self.n_vals, dtype=np.float64)
         for off, vals in self._tmpl:
@@ -853,7 +886,7 @@ class CompiledPlan:
         aero_rows = {0: 0, 1: 0, 2: 0}
         for j in self._aero:
             aero_rows[j["i32"][0]] += j["i32"][2]
-        lanes = {GE_LLH: 5, GE_IIP: 8, GE_ANT: 5, GE_TERM: 7, GE_USER_PERIGEE: 13}
+        lanes = {GE_LLH: 5, GE_IIP: 8, GE_ANT: 5, GE_TERM: 7, GE_USER_ORBIT: 13}
         evt_jac = sum(lanes[j["i32"][0]] for j in self._evt)
         aero_jac = 13 * aero_rows[0] + 9 * aero_rows[1] + 13 * aero_rows[2]
         obj = self.N + n_free + sum(aero_rows.values()) + len(self._evt)
@@ -907,8 +940,8 @@ class CompiledPlan:
             if typ == GE_TERM:
                 run(job["i64"][GE_J_POS], 3 * nrow)
                 run(job["i64"][GE_J_VEL], 3 * nrow)
-            elif typ == GE_USER_PERIGEE:
-                run(job["i64"][GE_J_POS], AUX_PER_USER)
+            elif typ == GE_USER_ORBIT:
+                run(job["i64"][GE_J_POS], AUX_PER_USER * nrow)
             else:
                 run(job["i64"][GE_J_POS], 3)
                 if typ == GE_IIP:
@@ -934,8 +967,8 @@ class CompiledPlan:
                 f[key] = None
             elif key == "ineqcon_mass":  # a Python list in the reference (con_trajectory.py:61)
                 f[key] = [v for v in g[gr[0]: gr[0] + gr[1]]]
-            elif key in ("eqcon_user", "ineqcon_user"):
-                f[key] = g[gr[0]]
+            elif key in ("eqcon_user", "ineqcon_user"):  # one row: a scalar, like the shipped example's function
+                f[key] = g[gr[0]] if gr[1] == 1 else g[gr[0]: gr[0] + gr[1]]
             else:
                 f[key] = g[gr[0]: gr[0] + gr[1]]
         return f
@@ -951,28 +984,29 @@ class CompiledPlan:
         return {"t": gvec}
 
     def _user_dense(self, vals, spec, key_order):
-        """Expand the 12 auxiliary quotients into jac_fd's dense blocks
+        """Expand the 12 auxiliary quotients of every row into jac_fd's dense blocks
         (jac_fd.py:54-60): a variable the function does not read still gets
         (g(x after k restores) - g_base)/dx, k = how many of the six read
         variables were visited before it."""
         _, job, srow = spec
-        a0 = job["i64"][GE_J_POS]
-        fd = vals[a0: a0 + 6]
-        bg = np.concatenate(([0.0], vals[a0 + 6: a0 + 12]))
+        nrow = job["i32"][GE_NROW]
         order = list(key_order)
         if order.index("position") > order.index("velocity"):
             raise NotImplementedError("xdict key order with velocity before position")
-        out = {}
-        k = 0
-        for key in order:
-            row = np.full(self.sizes[key], bg[k])
-            if key in ("position", "velocity"):
-                j0 = 0 if key == "position" else 3
-                row[: 3 * srow] = bg[k]
-                row[3 * srow: 3 * srow + 3] = fd[j0: j0 + 3]
-                k += 3
-                row[3 * srow + 3:] = bg[k]
-            out[key] = row.reshape(1, -1)
+        out = {key: np.empty((nrow, self.sizes[key])) for key in order}
+        for r in range(nrow):
+            a0 = job["i64"][GE_J_POS] + AUX_PER_USER * r
+            fd = vals[a0: a0 + 6]
+            bg = np.concatenate(([0.0], vals[a0 + 6: a0 + 12]))
+            k = 0
+            for key in order:
+                row = out[key][r]
+                row[:] = bg[k]
+                if key in ("position", "velocity"):
+                    j0 = 0 if key == "position" else 3
+                    row[3 * srow: 3 * srow + 3] = fd[j0: j0 + 3]
+                    k += 3
+                    row[3 * srow + 3:] = bg[k]
         return out
 
     def csr_map(self, wrt=None, key_order=VAR_ORDER):
@@ -1000,9 +1034,10 @@ class CompiledPlan:
                     continue
                 if isinstance(blk, dict):
                     r, c, d = blk["coo"]
-                else:  # dense (1, size) block of a user constraint
-                    d = np.asarray(blk, dtype=np.float64).ravel()
-                    r, c = np.zeros(d.size, dtype=np.int64), np.arange(d.size, dtype=np.int64)
+                else:  # dense (rows, size) block of a user constraint
+                    d2 = np.atleast_2d(np.asarray(blk, dtype=np.float64))
+                    r, c = np.divmod(np.arange(d2.size, dtype=np.int64), d2.shape[1])
+                    d = d2.ravel()
                 rows.append(np.asarray(r, dtype=np.int64) + r0)
                 cols.append(np.asarray(c, dtype=np.int64) + col0[var])
                 src.append(np.asarray(d, dtype=np.float64))

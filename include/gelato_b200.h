@@ -85,8 +85,24 @@ enum { GA_LIMIT = 0, GA_F64_COLS };
 
 /* ---- event-point jobs (con_waypoint.py, con_init_terminal_knot.py:329-405,
  *      user constraint built-ins) ------------------------------------------- */
-enum { GE_LLH = 0, GE_IIP = 1, GE_ANT = 2, GE_TERM = 3, GE_USER_PERIGEE = 4, GE_N_TYPES };
-#define GE_USER_AUX 12 /* values a user built-in leaves in the auxiliary tail of vals: 6 FD + 6 background quotients */
+enum { GE_LLH = 0, GE_IIP = 1, GE_ANT = 2, GE_TERM = 3, GE_USER_ORBIT = 4, GE_N_TYPES };
+#define GE_USER_PERIGEE GE_USER_ORBIT /* round-1 name: the one-row perigee-radius case */
+/* GE_USER_ORBIT: a built-in user constraint (/root/reference/lib/con_user.py:33-42 + jac_fd.py:29-62) on orbit
+ * quantities of the state at the first node of a named event, up to three rows: row r = q / scale - offset with the
+ * quantity code in byte r of GE_COMP (GEQ_*) and scale / offset in GE_A0 + 2r, GE_A0 + 2r + 1.  It leaves GE_USER_AUX
+ * values per row in the auxiliary tail of vals: 6 finite-difference quotients (position, velocity) and the 6
+ * "background" quotients jac_fd's perturb / restore protocol gives every variable the function does not read. */
+#define GE_USER_AUX 12
+enum {
+  GEQ_PERIGEE_RADIUS = 0, /* a (1 - e)       Coordinate.cpp:197-245 orbital_elements */
+  GEQ_APOGEE_RADIUS,      /* a (1 + e) */
+  GEQ_SEMI_MAJOR_AXIS,    /* a */
+  GEQ_ECCENTRICITY,       /* e */
+  GEQ_INCLINATION_DEG,    /* acos of the orbit normal's z, in degrees (wrapper_coordinate.hpp:204) */
+  GEQ_ORBIT_ENERGY,       /* v^2 / 2 - mu / r    wrapper_coordinate.hpp:224-250 */
+  GEQ_ANGULAR_MOMENTUM,   /* |r x v| */
+  GEQ_N
+};
 enum {
   GE_TYPE = 0,
   GE_TIDX,    /* index into t (section number), -1 if unused */
@@ -107,7 +123,7 @@ enum {
   GEF_MINUS_REF          /*  v - ref                      */
 };
 enum { GE_J_POS = 0, GE_J_VEL, GE_J_T, GE_I64_COLS };
-enum { GE_REF = 0, GE_DEN, GE_A0, GE_A1, GE_A2, GE_F64_COLS };
+enum { GE_REF = 0, GE_DEN, GE_A0, GE_A1, GE_A2, GE_A3, GE_A4, GE_A5, GE_F64_COLS };
 
 typedef struct GelatoPlanDesc {
   /* sizes */

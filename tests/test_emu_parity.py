@@ -228,3 +228,80 @@ def test_xdep_index_is_exactly_what_the_jacobian_kernel_writes(variant, user):
     written = np.flatnonzero(~np.isnan(vals))
     assert np.array_equal(written, P.xdep_index())
     assert P.n_xdep == written.size
+
+
+USER_CASES = [
+    # (equality built-in, inequality built-in)
+    ([("apogee_radius", 6378137.0, 1.03), ("inclination_deg", 42.2, 1.0)], None),
+    ([("orbit_energy", -3.0e7, 1.0)], [("eccentricity", 0.05, 0.5), ("semi_major_axis", 6578137.0, 1.0), ("angular_momentum", 5.2e10, 1.0)]),
+    (None, [("perigee_radius", 6378137.0, 1.0)]),
+]
+
+
+def _user_setup(eq_rows, ineq_rows, flavour, dot, coord):
+    from oracle import nlp, user_builtin
+
+    L = leaves.get(flavour)
+    p, u, c, x0 = helpers.example_problem(coord=coord, factor=2, max_nodes=12)
+    ue = user_builtin.orbit_rows_at(L, helpers.USER_EVENT, eq_rows) if eq_rows else None
+    ui = user_builtin.orbit_rows_at(L, "SECO", ineq_rows) if ineq_rows else None
+    O = nlp.OracleNLP(p, u, c, flavour, dot, user_eq=ue, user_ineq=ui)
+    P = gplan.CompiledPlan(p, u, c, user_eq=gplan.OrbitAtEvent(helpers.USER_EVENT, eq_rows) if eq_rows else None,
+                           user_ineq=gplan.OrbitAtEvent("SECO", ineq_rows) if ineq_rows else None, coord=coord)
+    return p, u, c, x0, O, P
+
+
+@pytest.mark.parametrize("eq_rows,ineq_rows", USER_CASES)
+def test_user_constraint_registry_matches_jac_fd_on_the_oracle(eq_rows, ineq_rows):
+    """Built-in user constraints (OrbitAtEvent: apogee / perigee radius, inclination, energy, angular momentum,
+    a, e at a named event; scalar or vector valued; equality and inequality group) against `jac_fd` over the
+    same function written in Python on the oracle's leaves: values and the dense per-variable blocks, bit for bit,
+    residue of the perturb / restore protocol included; pair and packed outputs as well."""
+    Lg = leaves.get("gmath")
+    p, u, c, x0, O, P = _user_setup(eq_rows, ineq_rows, "gmath", "seqfma", Lg.coordinate_c)
+    E = emu_binding.Emulator(P)
+    full, src, sgn = E.packed_map()
+    assert np.array_equal(full, P.xdep_index())
+    for x in (x0, helpers.perturbed(x0)):
+        xv = problem.xdict_to_vector(x)
+        xa = helpers.copy_x(x)
+        f, _ = O.objfunc(xa)
+        g = E.eval_residuals(xv)
+        helpers.assert_funcs_equal(f, P.split_residuals(g))
+        s, _ = O.sens(xa)
+        vals = E.eval_jacobian(xv)
+        helpers.assert_sens_equal(s, P.split_jacobian(vals, key_order=list(x.keys())))
+        g2, pk = E.eval_pair(xv, packed=True)
+        v2 = P.vals_template.copy()
+        v2[full] = sgn * pk[src]
+        assert np.array_equal(g2, g) and np.array_equal(v2, vals)
+    for key, rows in (("eqcon_user", eq_rows), ("ineqcon_user", ineq_rows)):
+        if rows:
+            blk = P.split_jacobian(vals, key_order=list(x.keys()))[key]
+            assert all(b.shape == (len(rows), P.sizes[k]) for k, b in blk.items())
+
+
+def test_user_constraint_registry_matches_the_reference_jac_fd():
+    """Live against the reference's own lib/jac_fd.py (where /root/reference exists): its dense forward differences
+    of the Python user function on the reference-faithful (libm) leaves equal the oracle's."""
+    import refharness
+
+    if not refharness.available():
+        pytest.skip("/root/reference not present on this machine")
+    import importlib
+
+    L = leaves.get("libm")
+    refharness.load(L)
+    ref_jac_fd = importlib.import_module("lib.jac_fd").jac_fd
+    for eq_rows, ineq_rows in USER_CASES:
+        p, u, c, x0, O, P = _user_setup(eq_rows, ineq_rows, "libm", "numpy", None)
+        for fn in (O.user_eq, O.user_ineq):
+            if fn is None:
+                continue
+            xa, xb = helpers.copy_x(helpers.perturbed(x0)), helpers.copy_x(helpers.perturbed(x0))
+            ja = ref_jac_fd(fn, xa, p, u, c)
+            jb = O.jac_fd(fn, xb)
+            assert list(ja.keys()) == list(jb.keys())
+            for k in ja:
+                assert np.array_equal(ja[k], jb[k]), k
+                assert np.array_equal(xa[k], xb[k]), k

@@ -368,6 +368,31 @@ def test_replacing_the_scenarios_refreshes_the_staged_constants():
     Eb.close()
 
 
+@pytest.mark.parametrize("eq_rows,ineq_rows", [
+    ([("apogee_radius", 6378137.0, 1.03), ("inclination_deg", 42.2, 1.0)], None),
+    ([("orbit_energy", -3.0e7, 1.0)], [("eccentricity", 0.05, 0.5), ("semi_major_axis", 6578137.0, 1.0), ("angular_momentum", 5.2e10, 1.0)]),
+])
+def test_user_constraint_registry_on_the_gpu(eq_rows, ineq_rows):
+    """Built-in user constraints (callbacks.OrbitAtEvent; scalar and vector valued, equality and inequality group):
+    the CUDA callbacks against `jac_fd` over the same function in Python on the oracle's leaves, bit for bit."""
+    from oracle import nlp, user_builtin
+
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c, factor=2, max_nodes=12)
+    ue = user_builtin.orbit_rows_at(Lg, helpers.USER_EVENT, eq_rows) if eq_rows else None
+    ui = user_builtin.orbit_rows_at(Lg, "SECO", ineq_rows) if ineq_rows else None
+    O = nlp.OracleNLP(p, u, c, "gmath", "seqfma", user_eq=ue, user_ineq=ui)
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.OrbitAtEvent(helpers.USER_EVENT, eq_rows) if eq_rows else None,
+                                   user_ineq=callbacks.OrbitAtEvent("SECO", ineq_rows) if ineq_rows else None, coord=Lg.coordinate_c)
+    for x in (x0, helpers.perturbed(x0)):
+        xa = helpers.copy_x(x)
+        f, _ = O.objfunc(xa)
+        helpers.assert_funcs_equal(f, prob.objfunc(x)[0])
+        s, _ = O.sens(xa)
+        helpers.assert_sens_equal(s, prob.sens(x)[0])
+    prob.close()
+
+
 def test_reuse_output_sens_equals_fresh_sens():
     prob, O, x0 = _problem("example", 3)
     p2 = callbacks.GelatoProblem(prob.plan.p, prob.plan.u, prob.plan.c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT),
