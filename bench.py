@@ -540,9 +540,10 @@ def run_gelato(args):
 
 
 def run_solves(args, world, rank, local):
-    """Batched NLP solves per hour: `--solve-scenarios` dispersed scenarios of the shipped example per GPU, each solved
-    to convergence by the host-side interior-point solver (gelato_b200/ipsolve.py -- NOT IPOPT) on callbacks that the
-    per-GPU coalescing server turns into batched launches."""
+    """Batched solver runs per hour: `--solve-scenarios` dispersed scenarios of the shipped example per GPU, each run by
+    the experimental interior-point stand-in (gelato_b200/ipsolve.py -- NOT IPOPT, fixed iteration budget, does not reach
+    IPOPT's tolerance: see its header) on callbacks that the per-GPU coalescing server turns into batched launches.
+    `solves_per_hour` stays null unless every run converged."""
     import torch
     import torch.distributed as dist
 
@@ -555,8 +556,10 @@ def run_solves(args, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_ok, op=dist.ReduceOp.SUM)
     wall = float(t.item())
-    res.update({"scenarios_total": args.solve_scenarios * world, "converged_total": int(n_ok.item()), "wall_s_max_over_ranks": wall,
-                "solves_per_hour": args.solve_scenarios * world / wall * 3600.0})
+    total = args.solve_scenarios * world
+    res.update({"scenarios_total": total, "converged_total": int(n_ok.item()), "wall_s_max_over_ranks": wall,
+                "runs_per_hour": total / wall * 3600.0,
+                "solves_per_hour": (total / wall * 3600.0) if int(n_ok.item()) == total else None})
     return res
 
 

@@ -1,24 +1,40 @@
-"""A host-side interior-point NLP solver for the callbacks of this package -- NOT IPOPT.
+"""An EXPERIMENTAL host-side interior-point NLP solver for the callbacks of this package -- NOT IPOPT, and on the
+shipped example it does NOT reach IPOPT's tolerance (status below).
 
 The reference hands `objfunc` / `sens` to pyoptsparse's IPOPT wrapper
 (/root/reference/Trajectory_Optimization.py:454-458; options `example-settings.json:92-97`: tol 1e-6,
 limited-memory Hessian -- pyoptsparse's default, the callbacks give first derivatives only --, MUMPS for the
-sparse KKT systems).  Neither pyoptsparse nor IPOPT can be installed in this image, so this module restates
-the METHOD (Waechter & Biegler 2006, the algorithm IPOPT implements) in ~500 lines of numpy / scipy for one
-purpose: to drive the very same callbacks, CPU oracle or CUDA, to a converged solution, so that the
-converged payload mass and event times, the callback counts and the time spent in the callbacks can be
-compared and "solves per hour" can be measured.  It is a stand-in and is labelled as such everywhere.
+sparse KKT systems).  Neither pyoptsparse nor IPOPT can be installed in this image (no wheel, no network), so this
+module restates the METHOD (Waechter & Biegler 2006) in numpy / scipy to drive the very same callbacks, CPU oracle or
+CUDA, through a realistic solve loop: same iterates from both (the callbacks are bit-identical), callback counts
+and times under pyoptsparse's names.
 
     min f(x)  s.t.  c_E(x) = 0,  c_I(x) >= 0,  x_L <= x <= x_U
 
 * primal-dual log-barrier with slacks for the inequality rows, monotone (Fiacco-McCormick) barrier update,
   fraction-to-the-boundary rule, gradient-based row scaling (IPOPT's nlp_scaling_max_gradient = 100);
-* Hessian of the Lagrangian: damped limited-memory BFGS in compact form; the KKT matrix
-  [[sigma I + Sigma, J^T], [J, -D]] stays SPARSE (scipy SuperLU) and the 2m rank correction goes through the
-  Woodbury identity -- the sparse KKT solve stays on the host, as the north star prescribes;
-* globalisation: the filter line search of the paper (switching condition, Armijo on the barrier objective,
-  sufficient decrease in violation or objective otherwise) with a second-order correction; when it fails the
-  quasi-Newton memory is dropped, then least-norm steps towards feasibility stand in for the restoration phase.
+* Hessian of the Lagrangian, three models: `lbfgs` (default; damped limited-memory BFGS in compact form, the KKT matrix
+  [[sigma I + Sigma, J^T], [J, -D]] stays SPARSE -- scipy SuperLU -- and the rank-2m part goes through the Woodbury
+  identity: the sparse KKT solve stays on the host, as the north star prescribes); `sparse-fd` (the exact sparse
+  Hessian from 13 + S + 1 structurally coloured finite differences of the Lagrangian's gradient: cheap with batched
+  CUDA callbacks); `reduced-fd` (the exact Hessian on the null space of the equality Jacobian);
+* globalisation: the filter line search of the paper (or an l1 merit function) with a second-order correction;
+  when it fails the quasi-Newton memory is dropped, then least-norm steps towards feasibility stand in for the
+  restoration phase.
+
+STATUS (round 2, profiles/r02_solver_attempts.txt): on the shipped example (1 003 variables, 964 equality rows, 39
+degrees of freedom) no configuration converges to tol = 1e-6.  The default reaches objective -1.0209 with a constraint
+violation of ~3e-3 in 300 iterations and then creeps; scipy's trust-constr creeps likewise (violation 3.8e-4 after
+3 000 iterations).  What was learnt: (1) the two terminal rows -- orbit energy and angular momentum,
+con_init_terminal_knot.py:362-370 -- have nearly parallel gradients at a near-circular target orbit, so the equality
+Jacobian's smallest singular value is 3e-5 of its largest and their multipliers are ~1e4..1e5: every Newton-type
+step is dominated by them; (2) the loose variable bounds of the reference's registration (position +-10 Earth radii
+...) dominate the barrier function at mu = 0.1 and pull the iterates to the centre of the box, so by default bounds get
+no barrier term here (`ignore_bounds`; the result reports `bound_violation`); (3) with exact curvature the
+tangent-space Hessian has eigenvalues down to 1e-6 of the largest far from the solution, so plain line-search Newton
+steps leave the region where the linearisation means anything.  IPOPT deals with all three (inertia and delta_c
+regularisation, a true restoration phase, adaptive scaling); a converged-solution comparison needs IPOPT itself:
+`nlpshim.register` is the reference's registration block for any pyoptsparse-compatible class.
 
 Interface: `IPSolver(options)(optProb, sens=sens) -> Solution`, for `nlpshim.Optimization` problems
 (the same call the reference makes on pyoptsparse's classes).
@@ -164,12 +180,88 @@ class _ReducedHessian:
         return k
 
 
+class _SparseFDHessian:
+    """The Hessian of the Lagrangian as a SPARSE matrix, from finite differences of the Lagrangian's gradient with a
+    structural colouring.  In a transcribed trajectory problem the only non-linear couplings are inside one
+    collocation node -- its state row (mass, position, velocity, quaternion: 11 variables) and control row (2) --
+    and between a node and the event times (everything else: D.X, knots, rates, are linear).  So perturbing variable
+    c of EVERY node at once gives column c of every node block from one `sens` call (13 calls), and one call per
+    event time gives the time columns: 13 + S + 1 extra Jacobian evaluations per iteration -- one batched launch for
+    the CUDA callbacks -- buy a Newton step instead of a quasi-Newton one."""
+
+    def __init__(self, n, structure, col0, eps):
+        self.n, self.eps = n, eps
+        M, N, S = structure["M"], structure["N"], structure["S"]
+        o = {k: col0[k] for k in ("mass", "position", "velocity", "quaternion", "u", "t")}
+        self.t_idx = o["t"] + np.arange(S + 1)
+        # members[r] = variables of the group of state row r (control row of its node included)
+        node_of_row = np.full(M, -1)
+        for ua, xa, nn in structure["sections"]:
+            node_of_row[xa + 1: xa + 1 + nn] = ua + np.arange(nn)
+        self.colours = []  # (perturbed variables, rows of H, columns of H)
+        members = []
+        for r in range(M):
+            m = [o["mass"] + r] + [o["position"] + 3 * r + k for k in range(3)] + [o["velocity"] + 3 * r + k for k in range(3)] \
+                + [o["quaternion"] + 4 * r + k for k in range(4)]
+            if node_of_row[r] >= 0:
+                m += [o["u"] + 2 * node_of_row[r], o["u"] + 2 * node_of_row[r] + 1]
+            members.append(np.array(m))
+        for c in range(13):
+            pert, rows, cols = [], [], []
+            for r in range(M):
+                if c >= members[r].size:
+                    continue
+                v = members[r][c]
+                pert.append(v)
+                rows.append(members[r])
+                cols.append(np.full(members[r].size, v))
+            self.colours.append((np.array(pert), np.concatenate(rows), np.concatenate(cols)))
+        self.S = []
+        self.sigma = 0.0
+        self.W = sp.csc_matrix((n, n))
+
+    def reset(self, sigma=None):
+        pass
+
+    def update(self, s, y):
+        pass
+
+    def times(self, v):
+        return self.W @ v
+
+    def build(self, lagr_grad, x):
+        n, eps = self.n, self.eps
+        g0 = lagr_grad(x)
+        R, C, V = [], [], []
+        for pert, rows, cols in self.colours:
+            xp = x.copy()
+            xp[pert] += eps
+            v = (lagr_grad(xp) - g0) / eps
+            R.append(rows)
+            C.append(cols)
+            V.append(v[rows])
+        for tk in self.t_idx:
+            xp = x.copy()
+            xp[tk] += eps
+            v = (lagr_grad(xp) - g0) / eps
+            nz = np.flatnonzero(v)
+            R += [nz, np.full(nz.size, tk)]
+            C += [np.full(nz.size, tk), nz]
+            V += [v[nz], v[nz]]
+        H = sp.coo_matrix((np.concatenate(V), (np.concatenate(R), np.concatenate(C))), shape=(n, n)).tocsc()
+        # the time x time block was entered twice (as column and as row)
+        T = sp.csc_matrix((np.ones(self.t_idx.size), (self.t_idx, self.t_idx)), shape=(n, n))
+        H = H - 0.5 * (T @ H @ T)
+        self.W = (0.5 * (H + H.T)).tocsc()
+        return len(self.colours) + self.t_idx.size
+
+
 class IPSolver:
     """solver = IPSolver({"tol": 1e-6, "max_iter": 2000}); sol = solver(optProb, sens=sens)."""
 
     DEFAULTS = {"tol": 1e-6, "max_iter": 2000, "mu_init": 0.1, "memory": 12, "bound_push": 1e-2,
                 "scaling_max_gradient": 100.0, "acceptable_tol": 1e-4, "acceptable_iter": 15, "verbose": 0,
-                "sigma_max": 1e8, "recalc_y": True, "hessian": "reduced-fd", "fd_eps": 1e-5, "floor_rel": 1e-2, "ignore_bounds": False, "globalization": "filter", "feasible": True, "feasible_iter": 4,
+                "sigma_max": 1e8, "recalc_y": False, "hessian": "lbfgs", "fd_eps": 1e-5, "floor_rel": 1e-2, "ignore_bounds": True, "globalization": "filter", "feasible": False, "radius": 0.05, "delta_c": 1e-9, "feasible_iter": 4,
                 "feasible_tol": 1e-9}
 
     def __init__(self, options=None):
@@ -263,7 +355,15 @@ class IPSolver:
         lamI = -zs.copy()
         lamE = self._ls_multipliers(g, JE, JI, zL, zU, lamI)
         exact = o["hessian"] == "reduced-fd"
-        B = _ReducedHessian(n, o["floor_rel"]) if exact else _LBFGS(n, o["memory"], sigma_max=o["sigma_max"])
+        newton = o["hessian"] == "sparse-fd"
+        if newton and getattr(prob, "structure", None) is None:
+            raise ValueError("hessian = sparse-fd needs the problem's structure (nlpshim.register attaches it)")
+        if newton:
+            B = _SparseFDHessian(n, prob.structure, col0, o["fd_eps"])
+        else:
+            B = _ReducedHessian(n, o["floor_rel"]) if exact else _LBFGS(n, o["memory"], sigma_max=o["sigma_max"])
+        delta_last = 0.0
+        radius = o["radius"]
 
         def lagr_grad_at(lE, lI):
             def fn(xv):
@@ -295,8 +395,9 @@ class IPSolver:
             viol = max(np.abs(cE).max(initial=0.0), np.abs(cI - s).max(initial=0.0))
 
             def compl(m):
-                return max(np.abs(np.where(hasL, (x - xl) * zL - m, 0.0)).max(initial=0.0),
-                           np.abs(np.where(hasU, (xu - x) * zU - m, 0.0)).max(initial=0.0), np.abs(s * zs - m).max(initial=0.0))
+                dL, dU = np.where(hasL, x - xl, 1.0), np.where(hasU, xu - x, 1.0)
+                return max(np.abs(np.where(hasL, dL * zL - m, 0.0)).max(initial=0.0),
+                           np.abs(np.where(hasU, dU * zU - m, 0.0)).max(initial=0.0), np.abs(s * zs - m).max(initial=0.0))
 
             du_inf = max(np.abs(rx).max(), np.abs(lamI + zs).max(initial=0.0)) / s_d
             E0 = max(du_inf, viol, compl(0.0) / s_d)
@@ -321,6 +422,8 @@ class IPSolver:
 
             if exact:
                 B.build(JE, lagr_grad_at(lamE, lamI), x, o["fd_eps"])
+            if newton:
+                B.build(lagr_grad_at(lamE, lamI), x)
             # ---- Newton step of the barrier problem ----
             SigL = np.where(hasL, zL / np.maximum(x - xl, 1e-300), 0.0)
             SigU = np.where(hasU, zU / np.maximum(xu - x, 1e-300), 0.0)
@@ -329,15 +432,31 @@ class IPSolver:
                 + np.where(hasU, mu / np.maximum(xu - x, 1e-300), 0.0)
             r_I = (cI - s) - (lamI + mu / s) / Sigs
             rhs = -np.concatenate((r_x, cE, r_I))
-            delta_w = 0.0
-            for attempt in range(8):
+            # inertia control without an inertia: the step must see positive curvature of the regularised Hessian
+            # (Chiang & Zavala 2016); otherwise delta_w grows, as in IPOPT's correction loop
+            delta_w = 0.0 if not newton else (0.0 if delta_last == 0.0 else max(delta_last / 3.0, 1e-8))
+            sol_vec = None
+            for attempt in range(40):
                 sol_vec = self._kkt_solve(B, SigL + SigU + delta_w, JE, JI, 1.0 / Sigs, rhs, n, mE, mI)
-                if sol_vec is not None and np.all(np.isfinite(sol_vec)):
+                ok_step = sol_vec is not None and np.all(np.isfinite(sol_vec))
+                if ok_step and newton:
+                    dxt = sol_vec[:n]
+                    curv = float(dxt @ B.times(dxt)) + float(dxt @ ((SigL + SigU + delta_w) * dxt))
+                    ok_step = curv >= 1e-9 * float(dxt @ dxt)
+                    # trust radius (Levenberg-Marquardt style): a nearly flat tangent-space Hessian must not send the
+                    # iterate where the linearisation means nothing; more regularisation shortens the tangential step
+                    if ok_step and np.abs(dxt).max() > radius and delta_w < 1e8:
+                        ok_step = False
+                if ok_step:
                     break
-                delta_w = 1e-4 if delta_w == 0.0 else 10.0 * delta_w
-            else:
+                delta_w = 1e-4 if delta_w == 0.0 else (8.0 * delta_w if delta_last > 0.0 or attempt > 0 else 100.0 * delta_w)
+                if delta_w > 1e20:
+                    sol_vec = None
+                    break
+            if sol_vec is None or not np.all(np.isfinite(sol_vec)):
                 status, message = 2, "KKT system could not be solved"
                 break
+            delta_last = delta_w
             dx, dlE, dlI = sol_vec[:n], sol_vec[n: n + mE], sol_vec[n + mE:]
             ds = (dlI + lamI + mu / s) / Sigs
             dzL = np.where(hasL, mu / np.maximum(x - xl, 1e-300) - zL - SigL * dx, 0.0)
@@ -470,6 +589,11 @@ class IPSolver:
                 dlE, dlI = np.zeros(mE), np.zeros(mI)
                 B.reset(B.sigma)
             fails_in_a_row = 0
+            if newton:  # the radius follows the line search: full steps widen it, short ones narrow it
+                if alpha >= 0.99:
+                    radius = min(2.0 * radius, 1.0)
+                elif alpha < 0.25:
+                    radius = max(0.5 * radius, 1e-4)
             last = (alpha, float(np.abs(alpha * step_dx).max()), "armijo" if armijo_step else ("soc" if step_dx is not dx else "theta"))
             # ---- accept: primal and equality multipliers with alpha, bound multipliers with their own step ----
             x_new, s_new = x + alpha * step_dx, s + alpha * step_ds
@@ -569,8 +693,11 @@ class IPSolver:
         """Solve [[B + diag_x, JE^T, JI^T], [JE, -dc, 0], [JI, 0, -1/Sigma_s - dc]] v = rhs with B = sigma I - U M^-1 U^T:
         sparse LU of the sigma I part, Woodbury for the rank-2k part."""
         if not reuse:
-            dc = 1e-9
-            K0 = sp.bmat([[sp.diags(B.sigma + diag_x), JE.T, JI.T],
+            dc = self.opt["delta_c"]
+            Wx = sp.diags(B.sigma + diag_x)
+            if getattr(B, "W", None) is not None:
+                Wx = Wx + B.W
+            K0 = sp.bmat([[Wx, JE.T, JI.T],
                           [JE, -dc * sp.identity(mE), None],
                           [JI, None, sp.diags(-(inv_sigs + dc))]], format="csc")
             try:

@@ -184,3 +184,14 @@ def register(objfunc, sens, xdict_init, condition, Opt=Optimization):
             n = len(val) if hasattr(val, "__len__") else 1
             prob.addConGroup(key, n, lower=0.0, upper=None if "ineqcon" in key else 0.0, wrt=wrt[key], jac=jac_init[key])
     return prob
+
+
+def attach_structure(prob, pdict):
+    """Tell a solver of this package where the non-linear couplings of the transcription are (ipsolve.py's sparse
+    finite-difference Hessian): sizes and, per section, (first control row, first state row, nodes).  pyoptsparse has
+    no use for it; the attribute is ignored by anything else."""
+    ps = pdict["ps_params"]
+    S = int(pdict["num_sections"])
+    prob.structure = {"M": int(pdict["M"]), "N": int(pdict["N"]), "S": S,
+                      "sections": [(ps.get_index(i)[0], ps.get_index(i)[2], ps.get_index(i)[4]) for i in range(S)]}
+    return prob

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""End-to-end solve of the shipped example with the pyoptsparse stand-in (gelato_b200/nlpshim.py; the
-solver is scipy trust-constr, NOT IPOPT), once on the CPU oracle's callbacks and once on the CUDA
-callbacks: same solver, same problem, same start.  Prints converged payload, event times, iteration
-counts and the time spent inside the callbacks.
+"""End-to-end solver loop on the shipped example with the pyoptsparse stand-in (gelato_b200/nlpshim.py) and the
+experimental interior-point solver (gelato_b200/ipsolve.py -- NOT IPOPT; it does not reach IPOPT's tolerance on this
+problem, see its header and profiles/r02_solver_attempts.txt), once on the CPU oracle's callbacks and once on the CUDA
+callbacks: same solver, same problem, same start.  Prints the state it reaches (objective, constraint violation,
+payload, event times), iteration counts and the time spent inside the callbacks under pyoptsparse's names
+(userObjTime / userSensTime / calls, Trajectory_Optimization.py:511-517).
 
-    python tests/scripts/solve_example.py --arm cpu|gpu|both [--maxiter 200] [--factor 1]
+    python tests/scripts/solve_example.py --arm cpu|gpu|both [--maxiter 300] [--factor 1] [--solver ip|trust-constr]
 """
 import argparse
 import json
@@ -20,7 +22,7 @@ import helpers  # noqa: E402
 from gelato_b200 import nlpshim, problem  # noqa: E402
 
 
-def run(arm, factor, maxiter):
+def run(arm, factor, maxiter, solver="ip"):
     from oracle import leaves
 
     Lg = leaves.get("gmath")
@@ -38,11 +40,17 @@ def run(arm, factor, maxiter):
 
         prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
         objfunc, sens = prob.objfunc, prob.sens
-    opt = nlpshim.register(objfunc, sens, x0, c)
-    sol = nlpshim.TrustConstr({"maxiter": maxiter})(opt, sens=sens)
+    from gelato_b200 import ipsolve
+
+    opt = nlpshim.attach_structure(nlpshim.register(objfunc, sens, helpers.copy_x(x0), c), p)
+    if solver == "ip":
+        sol = ipsolve.IPSolver({"max_iter": maxiter})(opt, sens=sens)
+    else:
+        sol = nlpshim.TrustConstr({"maxiter": maxiter})(opt, sens=sens)
     t_events = sol.xStar["t"] * u["t"]
     out = {
-        "arm": arm, "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status, "obj": float(sol.fStar),
+        "arm": arm, "solver": solver + " (NOT IPOPT)", "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status,
+        "message": getattr(sol, "message", ""), "obj": float(sol.fStar),
         "constr_violation": sol.constr_violation,
         "payload_kg": float(sol.xStar["mass"][0] * u["mass"]) if c["OptimizationMode"] == "Payload" else None,
         "event_times_s": [float(v) for v in t_events],
@@ -55,12 +63,13 @@ def run(arm, factor, maxiter):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
-    ap.add_argument("--maxiter", type=int, default=200)
+    ap.add_argument("--maxiter", type=int, default=300)
+    ap.add_argument("--solver", default="ip", choices=["ip", "trust-constr"])
     ap.add_argument("--factor", type=int, default=1)
     a = ap.parse_args()
     res = {}
     for arm in (["cpu", "gpu"] if a.arm == "both" else [a.arm]):
-        res[arm] = run(arm, a.factor, a.maxiter)
+        res[arm] = run(arm, a.factor, a.maxiter, a.solver)
         print(json.dumps(res[arm][0]))
     if len(res) == 2:
         xa, xb = res["cpu"][1], res["gpu"][1]
