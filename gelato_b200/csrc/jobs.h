@@ -189,6 +189,8 @@ P_HD double residue_n(double x, double dx, int n) {
  * 0/dx = 0 with the numerator's sign, and saying so skips the division's slow path, which the
  * GPU's software FP64 division takes for zero numerators (ncu r01b: 8 % of all instructions). */
 P_HD double fd_div(double num, double dx) { return num == 0.0 ? num : gm_div(num, dx); }
+/* the same with the reciprocal of dx computed once by the caller (gmath.h: gm_div_by is the IEEE quotient) */
+P_HD double fd_div_by(double num, const GmRcp Rdx) { return num == 0.0 ? num : gm_div_by(num, Rdx); }
 
 P_HD Units scen_units(const PlanView& P, int scen) {
   Units u = P.un;
@@ -341,6 +343,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   const int n = nr.n, j = nr.j, row = nr.row;
   const Units un = scen_units(P, scen);
   const double dx = un.dx, ut = un.t;
+  const GmRcp Rdx = gm_rcp(dx);
   const bool air_fd = nr.flags & GSF_AIR_FD, hold = nr.flags & GSF_HOLD;
   const double to = x[P.off_t + nr.sec], tf = x[P.off_t + nr.sec + 1];
   const double dt = tf - to;
@@ -349,7 +352,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   /* ---- velocity dynamics: -(f_p - f_c)/dx*(tf-to)*unit_t/2 (con_dynamics.py:372) ---- */
   if (lane >= 1 && lane <= 11 && !(lane >= 5 && lane <= 7 && !air_fd)) {
     double rh[3];
-    for (int k = 0; k < 3; k++) rh[k] = fd_div(-(fl[k] - fc[k]), dx) * dt * ut / 2.0;
+    for (int k = 0; k < 3; k++) rh[k] = fd_div_by(-(fl[k] - fc[k]), Rdx) * dt * ut / 2.0;
     if (lane == 1) {
       for (int k = 0; k < 3; k++) vals[sj[GS_JV_MASS] + 3LL * j + k] = rh[k];
     } else if (lane <= 4) {
@@ -372,7 +375,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
     if (air_fd) { /* :454-465 */
       const double to_p = to + dx;
       for (int k = 0; k < 3; k++)
-        vals[sj[GS_JV_T] + 3LL * j + k] = fd_div(-(fl[k] * (tf - to_p) - fc[k] * dt), dx) * ut / 2.0;
+        vals[sj[GS_JV_T] + 3LL * j + k] = fd_div_by(-(fl[k] * (tf - to_p) - fc[k] * dt), Rdx) * ut / 2.0;
     } else { /* :478-480 */
       for (int k = 0; k < 3; k++) {
         const double rh_to = fc[k] * ut / 2.0;
@@ -384,18 +387,19 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   if (lane == 13 && air_fd) { /* :466-477 */
     const double tf_p = tf + dx;
     for (int k = 0; k < 3; k++)
-      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = fd_div(-(fl[k] * (tf_p - to) - fc[k] * dt), dx) * ut / 2.0;
+      vals[sj[GS_JV_T] + n3 + 3LL * j + k] = fd_div_by(-(fl[k] * (tf_p - to) - fc[k] * dt), Rdx) * ut / 2.0;
   }
   /* ---- position dynamics (analytic, depends on x through vel and t): :180-195 ---- */
   if (lane == 14) {
-    const double rh_vel = gm_div(-un.vel * dt * ut / 2.0, un.pos);
+    const GmRcp Rp = gm_rcp(un.pos);
+    const double rh_vel = gm_div_by(-un.vel * dt * ut / 2.0, Rp);
     if (pk) {
       if (j == 0) vals[sj[GS_JP_VEL]] = rh_vel; /* one value per section */
     } else {
       for (int k = 0; k < 3; k++) vals[sj[GS_JP_VEL] + 3LL * j + k] = rh_vel;
     }
     for (int k = 0; k < 3; k++) {
-      const double rh_to = gm_div(x[P.off_vel + 3 * row + k] * un.vel * ut / 2.0, un.pos);
+      const double rh_to = gm_div_by(x[P.off_vel + 3 * row + k] * un.vel * ut / 2.0, Rp);
       vals[sj[GS_JP_T] + 3LL * j + k] = rh_to;
       if (!pk) vals[sj[GS_JP_T] + n3 + 3LL * j + k] = -rh_to;
     }
@@ -404,7 +408,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
   if (!hold) {
     if (lane >= 1 && lane <= 6) {
       double rh[4];
-      for (int a = 0; a < 4; a++) rh[a] = fd_div(-(ql[a] - qc[a]), dx) * dt * ut / 2.0;
+      for (int a = 0; a < 4; a++) rh[a] = fd_div_by(-(ql[a] - qc[a]), Rdx) * dt * ut / 2.0;
       if (lane <= 4) {
         const int kk = lane - 1; /* submat_quat[4j+a, 4(j+1)+kk] += rh[a] */
         const double d_diag = P.d_pool[nr.d_off + (long long)j * (n + 1) + (j + 1)];
@@ -813,8 +817,9 @@ P_HD void dyn_res_finish(const PlanView& P, int scen, const double* x, double* g
     if (flags & GSF_ENGINE_ON) r = r - gm_div(-sec_param(P, scen, nr.sec).massflow, un.mass) * dt * ut / 2.0;
     g[si[GS_R_MASS] + j] = r;
   } else if (grp == 0) { /* :147-150 */
+    const GmRcp Rp = gm_rcp(un.pos);
     for (int k = 0; k < 3; k++) {
-      const double rh = gm_div(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, un.pos);
+      const double rh = gm_div_by(x[P.off_vel + 3 * row + k] * un.vel * dt * ut / 2.0, Rp);
       g[si[GS_R_POS] + 3 * j + k] = lh[k] - rh;
     }
   } else if (grp == 2) { /* :258-287 */

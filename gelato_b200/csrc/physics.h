@@ -64,7 +64,10 @@ P_HD Vec3 cross3(Vec3 a, Vec3 b) {
 P_HD Vec3 sub3(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 P_HD Vec3 add3(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 P_HD Vec3 scale3(double s, Vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-P_HD Vec3 div3(Vec3 a, double s) { return v3(gm_div(a.x, s), gm_div(a.y, s), gm_div(a.z, s)); }
+P_HD Vec3 div3(Vec3 a, double s) {
+  const GmRcp R = gm_rcp(s); /* one reciprocal for the three quotients (gmath.h: gm_div_by is the IEEE quotient) */
+  return v3(gm_div_by(a.x, R), gm_div_by(a.y, R), gm_div_by(a.z, R));
+}
 P_HD Vec3 normalized3(Vec3 a) { /* Eigen normalized() */
   double z = dot3(a, a);
   if (z > 0.0) return div3(a, gm_sqrt(z));
@@ -150,9 +153,9 @@ P_HD Quat quat_ecef2ned_ll(double lat, double lon) {
     gm_sincos(lon / 2.0, &s_hl, &c_hl);
     gm_sincos(lat / 2.0, &s_hp, &c_hp);
   }
-  double r2 = gm_sqrt(2.0);
-  return q4(gm_div(c_hl * (c_hp - s_hp), r2), gm_div(s_hl * (c_hp + s_hp), r2), gm_div(-c_hl * (c_hp + s_hp), r2),
-            gm_div(s_hl * (c_hp - s_hp), r2));
+  const GmRcp r2 = gm_rcp(gm_sqrt(2.0)); /* a compile-time constant and its reciprocal */
+  return q4(gm_div_by(c_hl * (c_hp - s_hp), r2), gm_div_by(s_hl * (c_hp + s_hp), r2), gm_div_by(-c_hl * (c_hp + s_hp), r2),
+            gm_div_by(s_hl * (c_hp - s_hp), r2));
 }
 
 /* Coordinate.cpp:104-110 quat_ned2eci(pos_eci, t); c,s = cos/sin(omega t) */
@@ -179,9 +182,10 @@ P_HD Vec3 gravity_eci(Vec3 pos) {
   if (r == 0.0) {
     irx = iry = irz = 0.0;
   } else {
-    irx = gm_div(x, r);
-    iry = gm_div(y, r);
-    irz = gm_div(z, r);
+    const GmRcp Rr = gm_rcp(r);
+    irx = gm_div_by(x, Rr);
+    iry = gm_div_by(y, Rr);
+    irz = gm_div_by(z, Rr);
   }
   double s5 = gm_sqrt(5.0);
   double barP20 = s5 * (3.0 * irz * irz - 1.0) * 0.5;
@@ -420,8 +424,9 @@ P_HD Vec3 rhs_velocity_air_col(double mass_e, Vec3 pos_e, Vec3 vel_e, Quat q, co
   double thrust = sp.thrust - sp.nozzle_area * pp[PP_PRESS];
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(thrust, tdir);
-  return v3(gm_div(gm_div(thr.x + aero.x, mass) + pp[PP_GX], un.vel), gm_div(gm_div(thr.y + aero.y, mass) + pp[PP_GY], un.vel),
-            gm_div(gm_div(thr.z + aero.z, mass) + pp[PP_GZ], un.vel));
+  const GmRcp Rm = gm_rcp(mass), Rv = gm_rcp(un.vel);
+  return v3(gm_div_by(gm_div_by(thr.x + aero.x, Rm) + pp[PP_GX], Rv), gm_div_by(gm_div_by(thr.y + aero.y, Rm) + pp[PP_GY], Rv),
+            gm_div_by(gm_div_by(thr.z + aero.z, Rm) + pp[PP_GZ], Rv));
 }
 
 /* dynamics_velocity in one pass (residual kernel: one evaluation per node) */
@@ -439,8 +444,9 @@ P_HD Vec3 rhs_velocity_noair_col(double mass_e, Quat q, Vec3 g, const SecParam& 
   double mass = mass_e * un.mass;
   Vec3 tdir = quatrot(quatconj(q), v3(1.0, 0.0, 0.0));
   Vec3 thr = scale3(sp.thrust, tdir);
-  return v3(gm_div(gm_div(thr.x, mass) + g.x, un.vel), gm_div(gm_div(thr.y, mass) + g.y, un.vel),
-            gm_div(gm_div(thr.z, mass) + g.z, un.vel));
+  const GmRcp Rm = gm_rcp(mass), Rv = gm_rcp(un.vel);
+  return v3(gm_div_by(gm_div_by(thr.x, Rm) + g.x, Rv), gm_div_by(gm_div_by(thr.y, Rm) + g.y, Rv),
+            gm_div_by(gm_div_by(thr.z, Rm) + g.z, Rv));
 }
 P_HD Vec3 rhs_velocity_noair(double mass_e, Vec3 pos_e, Quat q, const SecParam& sp, const Units& un) {
   Vec3 pos = v3(pos_e.x * un.pos, pos_e.y * un.pos, pos_e.z * un.pos);

@@ -15,3 +15,5 @@ V2(gmt_atan2, gm_atan2)
 V2(gmt_pow, gm_pow)
 V2(gmt_atan2_slow, gm_atan2_slow)
 V2(gmt_pow_slow, gm_pow_slow)
+double gmt_div_by_one(double a, double d) { return gm_div_by(a, gm_rcp(d)); }
+V2(gmt_div_by, gmt_div_by_one)

@@ -106,3 +106,42 @@ def test_fast_paths_equal_the_complete_functions(shim):
         base, ex = rng.uniform(0.2, 1.6, 200000), rng.uniform(-35.0, 35.0, 200000)
         x, y = _call2(shim, "gmt_pow", base, ex), _call2(shim, "gmt_pow_slow", base, ex)
         assert np.array_equal(x.view(np.uint64), y.view(np.uint64))
+
+
+def test_shared_reciprocal_division_is_the_ieee_quotient(shim):
+    """gm_div_by(a, gm_rcp(d)) -- one reciprocal shared by several quotients, Markstein's correction -- must give the
+    bits of a / d: random operands over the whole exponent range (the guard sends the extreme ones to the plain
+    division), operands with significands next to 1 and next to 2, few-bit significands, zeros, infinities and NaN."""
+    rng = np.random.default_rng(9)
+    n = 2_000_000
+
+    def sig(kind):
+        m = rng.integers(0, 1 << 52, n, dtype=np.uint64)
+        if kind == 1:
+            m = (np.uint64((1 << 52) - 1) - (m & np.uint64(0xff)))
+        elif kind == 2:
+            m = m & np.uint64(0xff)
+        elif kind == 3:
+            m = m & np.uint64(0xfffff00000000)
+        return m
+
+    parts_a, parts_d = [], []
+    for ka in range(4):
+        for kd in range(4):
+            if (ka, kd) not in ((0, 0), (1, 1), (2, 2), (0, 1), (1, 0), (0, 2), (2, 0), (3, 3), (0, 3)):
+                continue
+            ea = rng.integers(1023 - 600, 1023 + 600, n).astype(np.uint64)
+            ed = rng.integers(1023 - 600, 1023 + 600, n).astype(np.uint64)
+            sa = rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63)
+            sd = rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63)
+            parts_a.append((sa | (ea << np.uint64(52)) | sig(ka)).view(np.float64))
+            parts_d.append((sd | (ed << np.uint64(52)) | sig(kd)).view(np.float64))
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                        1e-8, 6378137.0, 1000.0, 3.0, 1.0 / 3.0])
+    parts_a.append(np.repeat(special, special.size))
+    parts_d.append(np.tile(special, special.size))
+    a, d = np.concatenate(parts_a), np.concatenate(parts_d)
+    with np.errstate(all="ignore"):
+        got, want = _call2(shim, "gmt_div_by", a, d), a / d
+    same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (a[~same][:5], d[~same][:5], got[~same][:5], want[~same][:5])
