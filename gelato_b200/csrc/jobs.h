@@ -50,6 +50,10 @@
 #ifndef GJA_A_THREADS
 #define GJA_A_THREADS 192 /* aero blocks: threads [0, 192) position items; the rest rotation items */
 #endif
+#ifndef GD_GRAVITY_IN_POS
+#define GD_GRAVITY_IN_POS 0 /* 1: the position items compute gravity too (round 1); 0: the quaternion items' warp does, which
+                               shortens the longest chain of phase 0 (profiles/r02_ab_probe.txt) */
+#endif
 #ifndef GN_NODES
 #define GN_NODES 32      /* no-air nodes per Jacobian block */
 #endif
@@ -498,7 +502,8 @@ GM_HD_INL void dyn_air_phase(const PlanView& P, int scen, const double* x, doubl
         const NodeRef nr = jac_node(P, start + nl);
         double p[3];
         pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
-        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, PW_GRAVITY | PW_SOUND,
+        /* gravity is independent of the geodetic / atmosphere chain: the quaternion items' warp computes it */
+        pos_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tb.wind, tb.n_wind, GD_GRAVITY_IN_POS ? (PW_GRAVITY | PW_SOUND) : PW_SOUND,
                  sm.pp + (nl * NPV + pv) * PP_COLS);
       }
       return;
@@ -511,6 +516,17 @@ GM_HD_INL void dyn_air_phase(const PlanView& P, int scen, const double* x, doubl
         const int qn = item - count * NRV;
         const NodeRef nr = jac_node(P, start + qn);
         if (!(nr.flags & GSF_HOLD)) dyn_quat_variants(P, x, nr, un, sm.q + qn * NQV * 4);
+        if (!GD_GRAVITY_IN_POS) { /* the node's five gravity vectors: ~300 instructions each, next to ~500 for the variants */
+          for (int pv = 0; pv < NPV; pv++) {
+            double p[3];
+            pos_variant(x + P.off_pos + 3 * nr.row, pv, dx, p);
+            const Vec3 gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+            double* o = sm.pp + (qn * NPV + pv) * PP_COLS;
+            o[PP_GX] = gr.x;
+            o[PP_GY] = gr.y;
+            o[PP_GZ] = gr.z;
+          }
+        }
         continue;
       }
       const int nl = item / NRV, rv = item - nl * NRV;

@@ -355,11 +355,12 @@ P_HD_CALL void pos_part(double px, double py, double pz, const double* wind, int
   out[PP_RHO] = as.rho;
   out[PP_PRESS] = as.P;
   out[PP_SOUND] = as.a;
-  Vec3 gr = v3(0.0, 0.0, 0.0);
-  if (want & PW_GRAVITY) gr = gravity_eci(pos);
-  out[PP_GX] = gr.x;
-  out[PP_GY] = gr.y;
-  out[PP_GZ] = gr.z;
+  if (want & PW_GRAVITY) { /* otherwise the gravity fields are left to whoever computes them (jobs.h: dyn_air_phase) */
+    const Vec3 gr = gravity_eci(pos);
+    out[PP_GX] = gr.x;
+    out[PP_GY] = gr.y;
+    out[PP_GZ] = gr.z;
+  }
 }
 
 /* position+time part, first half: cos/sin of the Earth-rotation angle and the
