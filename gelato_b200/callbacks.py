@@ -22,16 +22,17 @@ from .plan import GROUPS, ORBIT_QUANTITIES, VAR_ORDER, CompiledPlan, OrbitAtEven
 
 class GelatoProblem:
     def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None,
-                 engine_factory=None, reuse_output=False):
+                 engine_factory=None, reuse_output=True):
         """engine_factory(plan) -> object with eval_residuals / eval_jacobian / close / launches;
         default: the CUDA engine on `device` (the CPU test tier passes the host emulator of the
-        kernels, tests/emu_binding.py, to exercise this host logic without a GPU)."""
+        kernels, tests/emu_binding.py, to exercise this host logic without a GPU).
+
+        reuse_output=True (default): `sens` writes into ONE page-locked buffer kept across calls and only the
+        x-dependent Jacobian values cross PCIe (update mode); the returned COO data arrays are views of that
+        buffer, valid until the next `sens` call -- what pyoptsparse needs (it converts them at once), and ~10x
+        less traffic on fine meshes.  reuse_output=False: fresh arrays on every call, like the reference."""
         self.plan = CompiledPlan(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, coord=coord)
         self.engine = engine_factory(self.plan) if engine_factory else _engine.Engine(self.plan, device=device)
-        # reuse_output=True: `sens` writes into ONE page-locked buffer kept across calls and only the
-        # x-dependent Jacobian values cross PCIe (update mode); the returned COO data arrays are views of
-        # that buffer, valid until the next `sens` call -- what pyoptsparse needs (it converts them at
-        # once), and ~10x less traffic on fine meshes.  Default False: fresh arrays, like the reference.
         self.reuse_output = bool(reuse_output) and hasattr(self.engine, "eval_jacobian_update")
         self._vals = None
         self._csr = None

@@ -394,14 +394,26 @@ def test_user_constraint_registry_on_the_gpu(eq_rows, ineq_rows):
 
 
 def test_reuse_output_sens_equals_fresh_sens():
-    prob, O, x0 = _problem("example", 3)
-    p2 = callbacks.GelatoProblem(prob.plan.p, prob.plan.u, prob.plan.c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT),
-                                 coord=leaves.get("gmath").coordinate_c, reuse_output=True)
+    """The drop-in `sens` keeps one page-locked Jacobian buffer across calls by default (only the x-dependent values
+    cross PCIe; the COO arrays are views valid until the next call); reuse_output=False returns fresh arrays like the
+    reference.  Same values either way, and the views do change with the next call."""
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c, factor=3, max_nodes=12)
+    kw = dict(user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
+    fresh = callbacks.GelatoProblem(p, u, c, reuse_output=False, **kw)
+    reuse = callbacks.GelatoProblem(p, u, c, **kw)
+    assert reuse.reuse_output and not fresh.reuse_output
+    first = None
     for seed in (1, 2):
         x = helpers.perturbed(x0, seed=seed)
-        helpers.assert_sens_equal(prob.sens(x)[0], p2.sens(x)[0])
-    prob.close()
-    p2.close()
+        sr = reuse.sens(x)[0]
+        helpers.assert_sens_equal(fresh.sens(x)[0], sr)
+        if first is None:
+            first = sr["eqcon_dyn_vel"]["mass"]["coo"][2]
+            kept = first.copy()
+    assert not np.array_equal(first, kept)  # a view of the reused buffer: the second call rewrote it
+    fresh.close()
+    reuse.close()
 
 
 def test_repeated_calls_are_deterministic_and_template_survives():
