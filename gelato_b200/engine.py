@@ -348,6 +348,7 @@ class Engine:
         """Rewrite the x-dependent slots of `out` (a buffer initialised by jacobian_template or
         holding an earlier result); afterwards `out` equals what eval_jacobian returns."""
         x = self._x(x, n_scen)
+        self.calls += 1
         _out(out, n_scen * self.n_vals, "out")
         _check(self.L, self.L.gelato_eval_jacobian_update(self.h, _ptr(x, _pd), _ptr(out, _pd), n_scen),
                "gelato_eval_jacobian_update")
@@ -357,6 +358,7 @@ class Engine:
         """objfunc + sens of the same decision vectors in one call (x uploaded once, the two kernels
         concurrent); g_out is filled whole, vals_out updated as by eval_jacobian_update."""
         x = self._x(x, n_scen)
+        self.calls += 1
         _out(g_out, n_scen * self.n_rows, "g_out")
         _out(vals_out, n_scen * self.n_vals, "vals_out")
         _check(self.L, self.L.gelato_eval_pair_update(self.h, _ptr(x, _pd), _ptr(g_out, _pd), _ptr(vals_out, _pd), n_scen),
@@ -379,6 +381,7 @@ class Engine:
     def eval_pair_packed(self, x, n_scen=1, g_out=None, packed_out=None, scen_ids=None):
         """objfunc + sens of the same decision vectors: (g[n_scen][n_rows], packed[n_scen][n_pack])."""
         x = self._x(x, n_scen)
+        self.calls += 1
         g = _out(g_out, n_scen * self.n_rows, "g_out") if g_out is not None else np.empty(n_scen * self.n_rows)
         pk = _out(packed_out, n_scen * self.n_pack, "packed_out") if packed_out is not None else np.empty(n_scen * self.n_pack)
         if scen_ids is None:
@@ -395,6 +398,7 @@ class Engine:
 
     def eval_jacobian_packed(self, x, n_scen=1, packed_out=None):
         x = self._x(x, n_scen)
+        self.calls += 1
         pk = _out(packed_out, n_scen * self.n_pack, "packed_out") if packed_out is not None else np.empty(n_scen * self.n_pack)
         _check(self.L, self.L.gelato_eval_jacobian_packed(self.h, _ptr(x, _pd), _ptr(pk, _pd), n_scen),
                "gelato_eval_jacobian_packed")
