@@ -279,6 +279,7 @@ class Engine:
         self.n_res_blocks = L.gelato_plan_n_blocks(h, 0)
         self.n_jac_heavy = L.gelato_plan_n_blocks(h, 2)
         self.n_jac_light = L.gelato_plan_n_blocks(h, 3)
+        self.n_jac_blocks_pair = L.gelato_plan_n_blocks(h, 4)
         self.n_vars = L.gelato_plan_n_vars(h)
         self.n_rows = L.gelato_plan_n_rows(h)
         self.n_vals = L.gelato_plan_n_vals(h)

@@ -113,3 +113,24 @@ def result_times(xdict, pdict, unitdict):
         tu = np.hstack((tu, (ps.tau(i) * (tf - to) / 2 + (tf + to) / 2) * unitdict["t"]))
         tx = np.hstack((tx, (tau_x * (tf - to) / 2 + (tf + to) / 2) * unitdict["t"]))
     return tx, tu
+
+
+def reference_initialize(leaves):
+    """The reference's own initialize.py (forward-simulation initial guess), imported where it lies.  Its plotting
+    imports (tools.plot_output, output_result -> matplotlib / pandas plotting) are replaced by empty stand-ins, and
+    `norm` / `sqrt` -- which initialize.py expects from `from lib.utils_c import *` but the pybind module does not
+    export (the legacy lib/utils.py did) -- are supplied with their legacy meaning (numpy.linalg.norm, math.sqrt)."""
+    import math
+
+    import numpy as np
+
+    load(leaves)
+    sys.modules["lib.utils_c"].__dict__.update(norm=np.linalg.norm, sqrt=math.sqrt)
+    sys.modules["lib.utils_c"].__all__ = list(sys.modules["lib.utils_c"].__dict__.keys())
+    for name in ("tools", "tools.plot_output", "output_result"):
+        mod = types.ModuleType(name)
+        mod.display_6DoF = mod.output_result = lambda *a, **k: None
+        sys.modules[name] = mod
+    for k in [k for k in sys.modules if k == "initialize"]:
+        del sys.modules[k]
+    return importlib.import_module("initialize")
