@@ -35,12 +35,28 @@
 #ifndef GJ_MIN_BLOCKS
 #define GJ_MIN_BLOCKS 2 /* 448 threads x 2 blocks: 28 warps per SM, up to 72 registers */
 #endif
+// The blocks of the first wave ask L2 for the whole decision-vector batch (one 128-byte line per thread, no
+// register, no wait): a block reads ~25 scattered lines of x before it can start, and on an L2 that does not hold
+// them every later wave would pay the DRAM latency again.  0 switches it off.
+#ifndef GJ_PREFETCH_BLOCKS
+#define GJ_PREFETCH_BLOCKS 296
+#endif
+__device__ __forceinline__ void prefetch_batch_l2(const double* x_all, size_t n_doubles, int blocks, int threads) {
+#if GJ_PREFETCH_BLOCKS > 0
+  if ((int)blockIdx.x < blocks) {
+    const size_t lines = (n_doubles * sizeof(double) + 127) / 128;
+    for (size_t l = (size_t)blockIdx.x * threads + threadIdx.x; l < lines; l += (size_t)blocks * threads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(x_all) + l * 128));
+  }
+#endif
+}
 template <int ROLES>
 __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* __restrict__ block_table, const int n_scen,
                                               const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all,
                                               double* __restrict__ out_all, double* __restrict__ g_all) {
   __shared__ JacStore store;
   const JacScratch sm = jac_scratch(store);
+  prefetch_batch_l2(x_all, (size_t)n_scen * P.n_vars, GJ_PREFETCH_BLOCKS, GJ_THREADS);
   // block-major launch order: block b of every scenario before block b+1 of any
   const int scen = blockIdx.x % n_scen;
   const int32_t* bt = block_table + (size_t)(blockIdx.x / n_scen) * BT_COLS;
@@ -78,23 +94,25 @@ k_jacobian_light(const __grid_constant__ PlanView P, const int32_t* __restrict__
   jacobian_body<JR_LIGHT>(P, block_table, n_scen, scen_ids, x_all, out_all, g_all);
 }
 
-// Vacuum dynamics nodes: one thread per node, no shared memory, no barrier (jobs.h: dyn_noair_node).
-#ifndef GV_THREADS
-#define GV_THREADS 128
+// Vacuum dynamics nodes: GV_PARTS threads per node, a warp per part (jobs.h: dyn_noair_part); no shared memory, no
+// barrier.  A block is GV_PARTS warps = 32 nodes.
+#define GV_THREADS (32 * GV_PARTS)
+#ifndef GV_MIN_BLOCKS
+#define GV_MIN_BLOCKS 5 /* the 158 registers ptxas would take leave 12 warps per SM; measured best of 1, 4, 5, 6, 8 */
 #endif
-__global__ void __launch_bounds__(GV_THREADS)
+__global__ void __launch_bounds__(GV_THREADS, GV_MIN_BLOCKS)
 k_jacobian_noair(const __grid_constant__ PlanView P, const int first, const int count, const int n_scen,
                  const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all, double* __restrict__ out_all,
                  double* __restrict__ g_all) {
-  const int per = (count + GV_THREADS - 1) / GV_THREADS;  // blocks per scenario
+  const int per = (count + 31) / 32;  // blocks per scenario
   const int scen = blockIdx.x / per;
-  const int k = (blockIdx.x - scen * per) * GV_THREADS + threadIdx.x;
+  const int k = (blockIdx.x - scen * per) * 32 + (threadIdx.x & 31);
   if (k >= count) return;
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* out = out_all + (size_t)scen * (size_t)(P.packed ? P.n_pack : P.n_vals);
   double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
   const int sid = scen_ids ? scen_ids[scen] : scen;
-  dyn_noair_node(P, sid, x, out, g, jac_node(P, first + k));
+  dyn_noair_part(P, sid, x, out, g, jac_node(P, first + k), threadIdx.x >> 5);
 }
 
 #ifndef GR_MIN_BLOCKS
@@ -284,7 +302,7 @@ static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* out_dev, 
     CU(cudaStreamWaitEvent(aux, ev_fork, 0));
   }
   if (p->n_vac > 0) {
-    const int per = (p->n_vac + GV_THREADS - 1) / GV_THREADS;
+    const int per = (p->n_vac + 31) / 32;
     k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, side ? aux : st>>>(v, p->vac_first, p->n_vac, n_scen, ids_dev, x_dev,
                                                                                 out_dev, g_dev);
     p->launches++;
@@ -1146,7 +1164,7 @@ int gelato_launch_kernel_dev(GelatoPlan* p, int which, const double* x_dev, doub
     k_jacobian_light<<<(unsigned)p->n_jac_light * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_light, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else if (which == 5) {
     if (p->n_vac == 0) return fail(GELATO_ERR_ARG, "the plan has no vacuum nodes");
-    const int per = (p->n_vac + GV_THREADS - 1) / GV_THREADS;
+    const int per = (p->n_vac + 31) / 32;
     k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, st>>>(v, p->vac_first, p->n_vac, n_scen, nullptr, x_dev, out_dev, g_dev);
   } else if (which == 6) {  // the block kernel alone, as an evaluation launches it
     const int nb = g_dev ? p->n_jac_blocks : p->n_jac_main;

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/gelato_b200.h"
+#include "initguess.h"
 #include "output.h"
 
 extern "C" void gelato_set_error_(const char* msg);  // gelato_b200.cu
@@ -138,6 +139,26 @@ __global__ void k_leaf_output_table(int n, const double* mass, const double* pos
   for (int k = 0; k < GO_COLS; k++) out[(size_t)i * GO_COLS + k] = row[k];
 }
 
+
+// forward-simulation initial guess (initguess.h): one thread per scenario walks the whole event schedule.  The
+// scenarios of a dispersed batch differ in their initial state, event rows and tables; the mesh times, the rate
+// table and the zero-lift-turn flags are shared.
+struct InitStrides {
+  long long x_init, events, wind, ca;  // doubles between consecutive scenarios; 0 = one copy shared by all
+};
+__global__ void k_init_rocket_simulation(int n_scen, const double* x_init, const double* ev, const int32_t* zlt, int n_ev,
+                                         const double* u_table, int n_u, const double* wind, int n_wind, const double* ca,
+                                         int n_ca, InitStrides ss, double t_init, const double* t_out, int n_out, double dt,
+                                         double* x_out, double* u_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scen) return;
+  Tables tb;
+  tb.wind = wind + s * ss.wind; tb.n_wind = n_wind;
+  tb.ca = ca + s * ss.ca; tb.n_ca = n_ca;
+  rocket_simulation_thread(x_init + s * ss.x_init, ev + s * ss.events, zlt, n_ev, u_table, n_u, tb, t_init, t_out, n_out, dt,
+                           x_out + (size_t)s * n_out * 11, u_out ? u_out + (size_t)s * n_out * 3 : nullptr);
+}
+
 }  // namespace
 
 extern "C" {
@@ -261,6 +282,50 @@ int gelato_leaf_atmosphere(int device, int32_t n, const double* altitude, double
   double* d_out = buf.out((size_t)5 * n, err);
   if (err == cudaSuccess) k_leaf_atmosphere<<<blocks_for(n), 128>>>(n, dz, d_out);
   return finish(err, out, d_out, (size_t)5 * n);
+}
+
+int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, const double* events, const int32_t* zlt,
+                                  int32_t n_ev, const double* u_table, int32_t n_u, const double* wind, int32_t n_wind,
+                                  const double* ca, int32_t n_ca, const int64_t* scenario_strides, double t_init,
+                                  const double* t_out, int32_t n_out, double dt, double* x_out, double* u_out) {
+  LEAF_PROLOGUE
+  if (n_ev <= 0 || n_u <= 0 || n_wind <= 0 || n_ca <= 0 || n_out <= 0 || !(dt > 0.0) || !scenario_strides) {
+    gelato_set_error_("rocket_simulation: empty table, no output time or non-positive dt");
+    return GELATO_ERR_ARG;
+  }
+  const InitStrides ss = {scenario_strides[0], scenario_strides[1], scenario_strides[2], scenario_strides[3]};
+  const long long need[4] = {11, (long long)n_ev * GI_COLS, (long long)n_wind * 3, (long long)n_ca * 2};
+  const long long have[4] = {ss.x_init, ss.events, ss.wind, ss.ca};
+  size_t count[4];
+  for (int k = 0; k < 4; k++) {
+    if (have[k] != 0 && have[k] < need[k]) {
+      gelato_set_error_("rocket_simulation: a scenario stride is shorter than one scenario's table");
+      return GELATO_ERR_ARG;
+    }
+    count[k] = have[k] ? (size_t)have[k] * (n - 1) + need[k] : (size_t)need[k];
+  }
+  for (int i = 1; i < n_out; i++)
+    if (!(t_out[i] >= t_out[i - 1])) {
+      gelato_set_error_("rocket_simulation: output times must ascend");
+      return GELATO_ERR_ARG;
+    }
+  const double* dx = buf.in(x_init, count[0], err);
+  const double* de = buf.in(events, count[1], err);
+  const double* dw = buf.in(wind, count[2], err);
+  const double* dc = buf.in(ca, count[3], err);
+  const int32_t* dz = buf.in(zlt, (size_t)n_ev, err);
+  const double* du = buf.in(u_table, (size_t)n_u * 4, err);
+  const double* dto = buf.in(t_out, (size_t)n_out, err);
+  double* d_out = buf.out((size_t)n * n_out * 11, err);
+  double* d_uout = u_out ? buf.out((size_t)n * n_out * 3, err) : nullptr;
+  // 32 threads per block: a batch of a few thousand scenarios then covers every SM (each thread is one long serial
+  // integration, so the launch is latency-bound and wants as many SMs as it can touch)
+  if (err == cudaSuccess)
+    k_init_rocket_simulation<<<(n + 31) / 32, 32>>>(n, dx, de, dz, n_ev, du, n_u, dw, n_wind, dc, n_ca, ss, t_init, dto, n_out,
+                                                    dt, d_out, d_uout);
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err == cudaSuccess && u_out) err = cudaMemcpy(u_out, d_uout, (size_t)n * n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost);
+  return finish(err, x_out, d_out, (size_t)n * n_out * 11);
 }
 
 }  // extern "C"

@@ -22,17 +22,7 @@ enum {
   GO_VEL_GROUND, GO_VEL_AIR, GO_AOA_TOTAL, GO_AOA_PITCH, GO_AOA_YAW, GO_DYNP, GO_Q_ALPHA, GO_MACH
 };
 
-P_HD double np_norm3(Vec3 v) { return gm_sqrt(gm_fma(v.z, v.z, gm_fma(v.y, v.y, v.x * v.x))); }
 P_HD double np_degrees(double x) { return x * (180.0 / P_PI); }
-P_HD double np_interp(double x, const double* xp, const double* fp, int n, int stride) {
-  if (x <= xp[0]) return fp[0];
-  if (x >= xp[(n - 1) * stride]) return fp[(n - 1) * stride];
-  int j = 0;
-  while (j + 1 < n - 1 && xp[(j + 1) * stride] <= x) j++;
-  const double slope = (fp[(j + 1) * stride] - fp[j * stride]) / (xp[(j + 1) * stride] - xp[j * stride]);
-  return slope * (x - xp[j * stride]) + fp[j * stride];
-}
-
 /* Earth.cpp:75-154 distance_vincenty (radians in, metres out) */
 P_HD double distance_vincenty(double lat1, double lon1, double lat2, double lon2) {
   if (lat1 == lat2 && lon1 == lon2) return 0.0;

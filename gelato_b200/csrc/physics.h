@@ -310,6 +310,26 @@ P_HD double interp_table(double x, const double* xp, const double* yp, int n, in
   return interp_at(interp_interval(x, xp, n, stride), x, xp, yp, n, stride);
 }
 
+/* ---- numpy's statements of two operations the Python layers around the NLP use (output.h, initguess.h) ---- */
+/* numpy.linalg.norm of a 3-vector: sqrt of a BLAS dot, fused multiply-adds in ascending index */
+P_HD double np_norm3(Vec3 v) { return gm_sqrt(gm_fma(v.z, v.z, gm_fma(v.y, v.y, v.x * v.x))); }
+
+/* numpy.interp for one abscissa (numpy/_core/src/multiarray/compiled_base.c): interval by comparison count (the
+ * tables are short), slope * (x - xp[j]) + fp[j] */
+P_HD double np_interp(double x, const double* xp, const double* fp, int n, int stride) {
+  if (x <= xp[0]) return fp[0];
+  if (x >= xp[(n - 1) * stride]) return fp[(n - 1) * stride];
+  int j = -1;
+  for (int i = 0; i < n; i++) j += (xp[i * stride] <= x) ? 1 : 0;
+  const double slope = (fp[(j + 1) * stride] - fp[j * stride]) / (xp[(j + 1) * stride] - xp[j * stride]);
+  double res = slope * (x - xp[j * stride]) + fp[j * stride];
+  if (res != res) {
+    res = slope * (x - xp[(j + 1) * stride]) + fp[(j + 1) * stride];
+    if (res != res && fp[j * stride] == fp[(j + 1) * stride]) res = fp[j * stride];
+  }
+  return res;
+}
+
 /* ---- the air right-hand side in three parts -------------------------------
  * The finite-difference columns of one node share most of their work: the
  * position-only part (geodetic altitude, atmosphere, wind lookup, gravity) takes

@@ -358,6 +358,27 @@ int gelato_leaf_output_table(int device, int32_t n, const double* mass, const do
                              const double* nozzle_area, const double* wind, int32_t n_wind, const double* ca, int32_t n_ca,
                              double launch_lat_deg, double launch_lon_deg, double* out);
 
+/* The forward-simulation initial guess (/root/reference/initialize.py:114-179 rocket_simulation with :37-111
+ * dynamics_init, :182-221 zerolift_turn_correct and :229-235 integrate_runge_kutta_4d) for n scenarios at once,
+ * ONE THREAD PER SCENARIO: classical Runge-Kutta from t_init to t_out[n_out-1] in steps of dt through the event
+ * schedule, then the states interpolated (numpy.interp) at t_out.  The reference runs it once per settings file in
+ * Python (its dt = 0.005 s: about half a million right-hand sides); a dispersed study needs one per scenario.
+ *   x_init            11 values per scenario: mass, position[3], velocity[3], quaternion[4] (dimensional)
+ *   events            n_ev rows per scenario of {time, thrust, massflow, reference_area, nozzle_area, mass_jettison}
+ *                     (pdict["params"][i]; times ascending)
+ *   zlt               n_ev flags: the event's attitude is "zero-lift-turn" (shared by the scenarios)
+ *   u_table           n_u rows {time, roll, pitch, yaw rate [deg/s]} (shared)
+ *   wind, ca          the tables of gelato_leaf_dynamics_velocity
+ *   scenario_strides  4 values: doubles between consecutive scenarios of x_init, events, wind, ca; 0 = every
+ *                     scenario reads the one copy given
+ *   x_out             [n][n_out][11]
+ *   u_out             [n][n_out][3] or NULL: the reference's second return value (the rate history at t_out)
+ * Same results as the reference's function bit for bit with its libm replaced by gmath.h (tests/test_initguess.py). */
+int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, const double* events, const int32_t* zlt,
+                                  int32_t n_ev, const double* u_table, int32_t n_u, const double* wind, int32_t n_wind,
+                                  const double* ca, int32_t n_ca, const int64_t* scenario_strides, double t_init,
+                                  const double* t_out, int32_t n_out, double dt, double* x_out, double* u_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ import math
 
 import numpy as np
 
+from . import leaves as _leaves
+
 
 def _np_interp(x, xp, fp):
     """numpy.interp for a scalar x (numpy/_core/src/multiarray/compiled_base.c: binary search for the interval,
@@ -40,15 +42,17 @@ def _np_interp(x, xp, fp):
 class ForwardSimulation:
     def __init__(self, leaves, dot="numpy"):
         self.crd, self.utl, self.atm = leaves.coordinate_c, leaves.utils_c, leaves.USStandardAtmosphere_c
-        self.dot = dot
+        self.dot, self.lib = dot, leaves.lib
 
     def norm(self, v):
         if self.dot == "numpy":
             return float(np.sqrt(np.dot(v, v)))
-        acc = v[0] * v[0]
-        for k in range(1, len(v)):
-            acc = math.fma(v[k], v[k], acc)
-        return math.sqrt(acc)
+        # the sequential-FMA statement of the dot product (oracle_leaves.cpp o_seqfma_matmul: product of the first
+        # pair, then fused multiply-adds in ascending index -- what the BLAS ddot kernel does for three elements)
+        vv = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty(1)
+        self.lib.o_seqfma_matmul(_leaves._p(vv), _leaves._p(vv), 1, vv.size, 1, _leaves._p(out))
+        return math.sqrt(out[0])
 
     def air_velocity(self, pos_eci, vel_eci, t, wind):
         c, u, a = self.crd, self.utl, self.atm

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../gelato_b200/csrc/host_pool.h"
+#include "../../gelato_b200/csrc/initguess.h"
 #include "../../gelato_b200/csrc/output.h"
 #include "../../gelato_b200/csrc/plan_host.h"
 
@@ -110,7 +111,7 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
       for (int phase = 0; phase < GJ_PHASES; phase++)
         for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase<JR_ALL>(P, sid, bt, x, vals, g, tid, phase, sm);
     }
-    /* vacuum dynamics nodes: one thread each (kernel k_jacobian_noair) */
+    /* vacuum dynamics nodes: GV_PARTS threads each (kernel k_jacobian_noair), here part after part */
     for (int k = 0; k < h.n_vac; k++) dyn_noair_node(P, sid, x, vals, g, jac_node(P, h.vac_first + k));
   }
   return 0;
@@ -165,3 +166,17 @@ extern "C" void emu_scatter_parallel(const int64_t* idx, long long n_idx, const 
 }
 
 extern "C" int emu_pool_workers(void) { return gelato_host::HostPool::instance().workers(); }
+
+// the forward-simulation kernel's per-thread function (initguess.h), one call per scenario
+extern "C" void emu_rocket_simulation(int n, const double* x_init, const double* events, const int32_t* zlt, int n_ev,
+                                      const double* u_table, int n_u, const double* wind, int n_wind, const double* ca,
+                                      int n_ca, const int64_t* ss, double t_init, const double* t_out, int n_out, double dt,
+                                      double* x_out, double* u_out) {
+  for (int s = 0; s < n; s++) {
+    Tables tb;
+    tb.wind = wind + s * ss[2]; tb.n_wind = n_wind;
+    tb.ca = ca + s * ss[3]; tb.n_ca = n_ca;
+    rocket_simulation_thread(x_init + s * ss[0], events + s * ss[1], zlt, n_ev, u_table, n_u, tb, t_init, t_out, n_out, dt,
+                             x_out + (size_t)s * n_out * 11, u_out ? u_out + (size_t)s * n_out * 3 : nullptr);
+  }
+}
