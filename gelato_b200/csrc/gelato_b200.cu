@@ -50,6 +50,27 @@ __device__ __forceinline__ void prefetch_batch_l2(const double* x_all, size_t n_
   }
 #endif
 }
+// Measurement build only (-DGJ_CLOCKS): cycles every warp spends in each phase and at each barrier, summed per
+// (role, warp) over the launch; read back with gelato_debug_clocks (tools/phase_clocks.py).
+#ifdef GJ_CLOCKS
+__device__ unsigned long long gj_clk_sum[8][16][6];  // [role][warp][phase0, wait0, phase2, wait2, phase3, blocks]
+#define GJ_CLK_DECL long long clk_[6] = {0, 0, 0, 0, 0, 0}
+#define GJ_CLK(i) clk_[i] = clock64()
+#define GJ_CLK_FLUSH(role, two)                                                                         \
+  if ((threadIdx.x & 31) == 0) {                                                                        \
+    unsigned long long* c = gj_clk_sum[(role) & 7][threadIdx.x >> 5];                                   \
+    atomicAdd(c + 0, (unsigned long long)(clk_[1] - clk_[0]));                                              \
+    atomicAdd(c + 1, (unsigned long long)(clk_[2] - clk_[1]));                                              \
+    atomicAdd(c + 2, (unsigned long long)((two) ? 0 : clk_[3] - clk_[2]));                                  \
+    atomicAdd(c + 3, (unsigned long long)((two) ? 0 : clk_[4] - clk_[3]));                                  \
+    atomicAdd(c + 4, (unsigned long long)(clk_[5] - clk_[4]));                                              \
+    atomicAdd(c + 5, 1ull);                                                                             \
+  }
+#else
+#define GJ_CLK_DECL
+#define GJ_CLK(i)
+#define GJ_CLK_FLUSH(role, two)
+#endif
 template <int ROLES>
 __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* __restrict__ block_table, const int n_scen,
                                               const int32_t* __restrict__ scen_ids, const double* __restrict__ x_all,
@@ -68,13 +89,21 @@ __device__ __forceinline__ void jacobian_body(const PlanView& P, const int32_t* 
   // which scenario's parameter blocks this batch slot uses (a coalesced subset of the configured scenarios)
   const int sid = scen_ids ? scen_ids[scen] : scen;
   const bool two_phase = jac_role_two_phase(bt[BT_ROLE]);
+  GJ_CLK_DECL;
+  GJ_CLK(0);
   jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 0, sm);
+  GJ_CLK(1);
   __syncthreads();
+  GJ_CLK(2);
   if (!two_phase) {
     jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 2, sm);
+    GJ_CLK(3);
     __syncthreads();
   }
+  GJ_CLK(4);
   jac_block_phase<ROLES>(P, sid, bt, x, out, g, threadIdx.x, 3, sm);
+  GJ_CLK(5);
+  GJ_CLK_FLUSH(bt[BT_ROLE], two_phase);
 }
 __global__ void __launch_bounds__(GJ_THREADS, GJ_MIN_BLOCKS)
 k_jacobian(const __grid_constant__ PlanView P, const int32_t* __restrict__ block_table, const int n_scen, const int32_t* __restrict__ scen_ids,
@@ -1261,5 +1290,16 @@ int gelato_fp64_peak(int device, double* tflops_fma, double* tflops_nofma) {
   cudaFree(d);
   return GELATO_OK;
 }
+
+#ifdef GJ_CLOCKS
+// measurement build: copy (and clear) the per-(role, warp) phase cycle sums; out[8][16][6]
+int gelato_debug_clocks(unsigned long long* out) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out, gj_clk_sum, sizeof(unsigned long long) * 8 * 16 * 6));
+  static unsigned long long zero[8 * 16 * 6];
+  CU(cudaMemcpyToSymbol(gj_clk_sum, zero, sizeof zero));
+  return GELATO_OK;
+}
+#endif
 
 }  // extern "C"

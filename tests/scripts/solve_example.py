@@ -22,7 +22,7 @@ import helpers  # noqa: E402
 from gelato_b200 import nlpshim, problem  # noqa: E402
 
 
-def run(arm, factor, maxiter, solver="ip"):
+def run(arm, factor, maxiter, solver="redsqp", verbose=0):
     from oracle import leaves
 
     Lg = leaves.get("gmath")
@@ -43,13 +43,17 @@ def run(arm, factor, maxiter, solver="ip"):
     from gelato_b200 import ipsolve
 
     opt = nlpshim.attach_structure(nlpshim.register(objfunc, sens, helpers.copy_x(x0), c), p)
-    if solver == "ip":
+    if solver == "redsqp":
+        from gelato_b200 import redsqp
+        sol = redsqp.ReducedSQP({"max_iter": maxiter, "verbose": verbose})(opt, sens=sens)
+    elif solver == "ip":
         sol = ipsolve.IPSolver({"max_iter": maxiter})(opt, sens=sens)
     else:
         sol = nlpshim.TrustConstr({"maxiter": maxiter})(opt, sens=sens)
     t_events = sol.xStar["t"] * u["t"]
     out = {
-        "arm": arm, "solver": solver + " (NOT IPOPT)", "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status,
+        "arm": arm, "solver": solver + " (NOT IPOPT)", "optimality": getattr(sol, "optimality", None),
+        "reduced_evaluations": getattr(sol, "reduced_evaluations", None), "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status,
         "message": getattr(sol, "message", ""), "obj": float(sol.fStar),
         "constr_violation": sol.constr_violation,
         "payload_kg": float(sol.xStar["mass"][0] * u["mass"]) if c["OptimizationMode"] == "Payload" else None,
@@ -63,13 +67,14 @@ def run(arm, factor, maxiter, solver="ip"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
-    ap.add_argument("--maxiter", type=int, default=300)
-    ap.add_argument("--solver", default="ip", choices=["ip", "trust-constr"])
+    ap.add_argument("--maxiter", type=int, default=600)
+    ap.add_argument("--solver", default="redsqp", choices=["redsqp", "ip", "trust-constr"])
+    ap.add_argument("--verbose", type=int, default=0)
     ap.add_argument("--factor", type=int, default=1)
     a = ap.parse_args()
     res = {}
     for arm in (["cpu", "gpu"] if a.arm == "both" else [a.arm]):
-        res[arm] = run(arm, a.factor, a.maxiter, a.solver)
+        res[arm] = run(arm, a.factor, a.maxiter, a.solver, a.verbose)
         print(json.dumps(res[arm][0]))
     if len(res) == 2:
         xa, xb = res["cpu"][1], res["gpu"][1]
