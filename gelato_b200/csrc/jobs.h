@@ -436,6 +436,7 @@ P_HD void dyn_scatter(const PlanView& P, int scen, const double* x, double* vals
 }
 
 P_HD void dyn_lh_item(const PlanView& P, const double* x, const NodeRef& nr, int grp, double* lh);
+P_HD void dyn_lh_vel_col(const PlanView& P, const double* x, const NodeRef& nr, int k, double* lh);
 P_HD void dyn_res_finish(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
                          const double* lh, const double* f3, const double* q4v);
 
@@ -454,6 +455,27 @@ P_HD void dyn_lh_block(const PlanView& P, const double* x, int start, int count,
     const int grp = item / count, nl = item - grp * count;
     dyn_lh_item(P, x, jac_node(P, start + nl), grp, sm.lh + nl * 11);
   }
+}
+/* The same products for the air-node blocks, spread by measured slack (tools/phase_clocks.py: with all of them on
+ * the one spare warp that warp ended phase 0 last, 17 000 cycles against 15 200 for the position items and 12 800 for
+ * the rotation items): the spare warp takes the position and quaternion products of its lane's node, the first
+ * four rotation warps add ONE column each after their item -- velocity x, y, z and mass.  Needs a whole spare warp
+ * and four busy ones; other geometries keep dyn_lh_block. */
+P_HD void dyn_lh_spread(const PlanView& P, const double* x, int start, int count, int idx, int n_busy, const JacScratch& sm) {
+  if (idx >= n_busy) {
+    const int nl = idx - n_busy;
+    if (nl < count) {
+      const NodeRef nr = jac_node(P, start + nl);
+      dyn_lh_item(P, x, nr, 0, sm.lh + nl * 11);
+      dyn_lh_item(P, x, nr, 1, sm.lh + nl * 11);
+    }
+    return;
+  }
+  const int col = idx >> 5, nl = idx & 31;
+  if (col >= 4 || nl >= count) return;
+  const NodeRef nr = jac_node(P, start + nl);
+  if (col == 3) dyn_lh_item(P, x, nr, 3, sm.lh + nl * 11);
+  else dyn_lh_vel_col(P, x, nr, col, sm.lh + nl * 11);
 }
 
 /* all 15 lanes of the nodes of a block, leaf values laid out f[(nl*14 + lane)*3], q[(nl*NQV + var)*4];
@@ -539,7 +561,10 @@ GM_HD_INL void dyn_air_phase(const PlanView& P, int scen, const double* x, doubl
       const double tn = time_node(P.tau_pool + nr.tau_off, nr.j + 1, to, tf);
       rotq_part(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos, tn, sm.rq + (nl * NRV + rv) * RQ_COLS);
     }
-    if (g) dyn_lh_block(P, x, start, count, idx, nb, count * (NRV + 1), sm);
+    if (g) {
+      if (GD_NODES == 32 && nb - GD_NODES * (NRV + 1) >= 32) dyn_lh_spread(P, x, start, count, idx, GD_NODES * (NRV + 1), sm);
+      else dyn_lh_block(P, x, start, count, idx, nb, count * (NRV + 1), sm);
+    }
   } else if (phase == 2) {
     for (int item = tid; item < count * 14; item += GJ_THREADS) {
       const int nl = item / 14, lane = item - nl * 14;
@@ -817,6 +842,20 @@ P_HD void dx_dot(const double* Drow, const double* xrows, int n1, double* acc) {
   }
 }
 
+/* one column of a W-wide state array: the same chain as column k of dx_dot<W> */
+P_HD double dx_dot_col(const double* Drow, const double* xcol, int stride, int n1) {
+  double acc = 0.0;
+  int m = 0;
+  for (; m + 2 <= n1; m += 2) {
+    const double d0 = Drow[m], d1 = Drow[m + 1];
+    const double x0 = xcol[(long long)m * stride], x1 = xcol[(long long)(m + 1) * stride];
+    acc = gm_fma(d0, x0, acc);
+    acc = gm_fma(d1, x1, acc);
+  }
+  for (; m < n1; m++) acc = gm_fma(Drow[m], xcol[(long long)m * stride], acc);
+  return acc;
+}
+
 /* The collocation defects of one (node, state array) item in two steps -- D.X (dyn_lh_item), then minus the
  * right-hand side (dyn_res_finish) -- so that the Jacobian kernel can compute the products while its long
  * phase-0 items run.  grp 0 position | 1 quaternion | 2 velocity | 3 mass; lh[11] = the node's products, laid
@@ -838,6 +877,11 @@ P_HD void dyn_lh_item(const PlanView& P, const double* x, const NodeRef& nr, int
   } else {
     dx_dot<4>(Drow, x + P.off_quat + 4 * xa, n + 1, lh + 3);
   }
+}
+/* column k of the velocity product alone (dyn_lh_item group 2) */
+P_HD void dyn_lh_vel_col(const PlanView& P, const double* x, const NodeRef& nr, int k, double* lh) {
+  const int n = nr.n, xa = nr.si[GS_XA];
+  lh[7 + k] = dx_dot_col(P.d_pool + nr.d_off + (long long)nr.j * (n + 1), x + P.off_vel + 3 * xa + k, 3, n + 1);
 }
 P_HD void dyn_res_finish(const PlanView& P, int scen, const double* x, double* g, const NodeRef& nr, int grp,
                          const double* lh, const double* f3, const double* q4v) {
