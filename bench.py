@@ -80,6 +80,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the back-to-back device leg")
+    ap.add_argument("--preheat-seconds", type=float, default=0.5,
+                    help="untimed run of the timed launches right before the timed steps (the clocks are sampled over it)")
     ap.add_argument("--e2e-slices", type=int, default=0, help="pipeline slices of the end-to-end leg (0 = library default)")
     ap.add_argument("--solve-scenarios", type=int, default=0,
                     help="also solve this many dispersed scenarios of the shipped example per GPU to convergence "
@@ -389,7 +391,7 @@ def run_gelato(args):
     # K timed steps last a few milliseconds, less than one nvidia-smi sample: the same launches run for 0.5 s right
     # before them (untimed, on top of the W warm-up steps) and the clocks are read over that run plus the timed steps
     t_dev0 = time.perf_counter()
-    while time.perf_counter() - t_dev0 < 0.5:
+    while time.perf_counter() - t_dev0 < args.preheat_seconds:
         for _ in range(50):
             E.eval_pair_packed_dev(xd.data_ptr(), gd.data_ptr(), pd.data_ptr(), B, st)
         torch.cuda.synchronize()
