@@ -130,6 +130,21 @@ def make_scenario_desc(plans):
         if (p.n_rows, p.n_vals, p.n_lin, p.n_evt, p.n_aero, p.wind.shape) != (
                 base.n_rows, base.n_vals, base.n_lin, base.n_evt, base.n_aero, base.wind.shape):
             raise ValueError("scenario plans must share the problem structure")
+        # what is NOT carried per scenario is evaluated with the base plan's copy: it must be the same everywhere
+        shared = ("sec_i32", "sec_i64", "d_pool", "tau_pool", "ca", "lin_i32", "aero_i32", "aero_i64", "aero_f64",
+                  "rc_aero", "evt_i32", "evt_i64", "evt_f64")
+        for name in shared:
+            a, b = getattr(base, name, None), getattr(p, name, None)
+            if a is None and b is None:
+                continue
+            if a is None or b is None or not np.array_equal(np.asarray(a), np.asarray(b)):
+                raise ValueError("scenario plans differ in `%s`, which is shared by every scenario of a batch "
+                                 "(per scenario: section parameters, wind table, mass unit, linear-row constants)" % name)
+        if not np.array_equal(np.asarray(base.units)[1:], np.asarray(p.units)[1:]):
+            raise ValueError("scenario plans differ in a unit other than the mass unit")
+        if not np.array_equal(np.asarray(base.lin_f64)[:, :2], np.asarray(p.lin_f64)[:, :2]) or \
+                not np.array_equal(np.asarray(base.lin_f64)[:, 3:], np.asarray(p.lin_f64)[:, 3:]):
+            raise ValueError("scenario plans differ in linear-row coefficients other than the constant")
     keep = []
 
     def stack(get):

@@ -134,3 +134,24 @@ def test_plan_create_refuses_malformed_descriptions():
         assert rc == -1 and word in msg, (rc, msg)
     rc, msg = create(lambda d, k: None)  # the untouched description passes validation
     assert rc == 0 or "no CUDA device" in msg, (rc, msg)
+
+
+def test_scenario_plans_must_agree_on_everything_that_is_not_carried_per_scenario():
+    """make_scenario_desc refuses a batch whose plans differ in a table every scenario shares (they would silently
+    be evaluated with the base plan's copy)."""
+    import copy
+
+    import pytest
+
+    import bench
+    from gelato_b200 import engine
+    plans, _, _ = bench.load_workload("example", 1, 2, 0, 2)
+    engine.make_scenario_desc(plans)
+    bad = copy.copy(plans[1])
+    bad.ca = plans[1].ca * 1.01
+    with pytest.raises(ValueError, match="`ca`"):
+        engine.make_scenario_desc([plans[0], bad])
+    bad = copy.copy(plans[1])
+    bad.units = (plans[1].units[0],) + (plans[1].units[1] * 2.0,) + tuple(plans[1].units[2:])
+    with pytest.raises(ValueError, match="unit"):
+        engine.make_scenario_desc([plans[0], bad])
