@@ -295,6 +295,7 @@ def test_pair_evaluation_equals_the_two_calls():
     gd = torch.full((3, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
     vd = torch.empty((3, P.n_vals), dtype=torch.float64, device="cuda")
     s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())  # the fills above run on torch's current stream
     with torch.cuda.stream(s):
         E.fill_template(vd.data_ptr(), 3, s.cuda_stream)
         E.eval_pair_dev(xd.data_ptr(), gd.data_ptr(), vd.data_ptr(), 3, s.cuda_stream)
@@ -339,6 +340,7 @@ def test_packed_pair_evaluation_reproduces_the_two_calls(variant, factor, n):
     gd = torch.full((n, P.n_rows), float("nan"), dtype=torch.float64, device="cuda")
     pd = torch.full((n, E.n_pack), float("nan"), dtype=torch.float64, device="cuda")
     s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())  # the fills above run on torch's current stream
     with torch.cuda.stream(s):
         E.eval_pair_packed_dev(xd.data_ptr(), gd.data_ptr(), pd.data_ptr(), n, s.cuda_stream)
     s.synchronize()
