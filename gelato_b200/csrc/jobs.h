@@ -60,8 +60,16 @@
 #ifndef GN_A_THREADS
 #define GN_A_THREADS 160 /* no-air blocks: threads [0, 160) gravity items, the rest quaternion and D.X items */
 #endif
+/* Event jobs per Jacobian block, 16 lanes each.  Two jobs of different types in one warp run one after the other
+ * (phase clocks: 69 000 cycles for the warp with an IIP and an antenna row against 37 000 for its neighbours), so
+ * GJ_EVT_PER_WARP = 1 gives every job a warp of its own: the event block then takes 65 000 instead of 75 000 cycles
+ * and a sens-only launch gains 1.5 %, but the timed pair evaluation (L2 flushed) loses 1 % on the same box
+ * (profiles/r02h_ab_probe.txt) -- off. */
+#ifndef GJ_EVT_PER_WARP
+#define GJ_EVT_PER_WARP 0
+#endif
 #ifndef GJ_EVT
-#define GJ_EVT (GJ_THREADS / 16) /* event jobs per Jacobian block (16 lanes each) */
+#define GJ_EVT (GJ_THREADS / (GJ_EVT_PER_WARP ? 32 : 16))
 #endif
 #ifndef GG_NODES
 #define GG_NODES (GJ_THREADS / 16) /* nodes per block of the one-lane-per-column fallback (16 lanes each) */
@@ -971,6 +979,9 @@ P_HD void aero_base(const PlanView& P, const double* x, int sec, int row, double
   }
 }
 
+#ifndef GJA_SHARE_BASE
+#define GJA_SHARE_BASE 1
+#endif
 GM_HD_INL void aero_phase(const PlanView& P, int scen, const double* x, double* vals, double* g, int start, int count, int tid,
                      int phase, const JacScratch& sm) {
   const Units un = scen_units(P, scen);
@@ -993,6 +1004,10 @@ GM_HD_INL void aero_phase(const PlanView& P, int scen, const double* x, double* 
         tf = x[P.off_t + ar.sec + 1];
       } else {
         aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
+        /* the row's base state (what the gradient finds after the earlier groups' perturb / restore cycles) is the
+         * same for all 13 columns of phase 2: kept in the quaternion scratch, which this role does not use */
+        if (GJA_SHARE_BASE && is_a && var == 0)
+          for (int k = 0; k < 10; k++) sm.q[nl * 10 + k] = v[k];
       }
       if (is_a) {
         pos_variant(v, pristine ? 0 : var, dx, p);
@@ -1014,10 +1029,13 @@ GM_HD_INL void aero_phase(const PlanView& P, int scen, const double* x, double* 
       const int kind = ar.kind, job = ar.job;
       const bool has_quat = kind != 1;
       if (!has_quat && lane >= 7 && lane <= 10) continue;
-      double v[10], to, tf;
+      double v[10];
       if (lane == 13) {
         aero_load(P, x, ar.row, v);
+      } else if (GJA_SHARE_BASE) {
+        for (int k = 0; k < 10; k++) v[k] = sm.q[nl * 10 + k]; /* aero_base of the row, from phase 0 */
       } else {
+        double to, tf;
         aero_base(P, x, ar.sec, ar.row, v, &to, &tf);
       }
       if (lane != 0 && lane != 13) { /* the gradient works on a copy: columns leave residue inside the copy only */
@@ -1283,9 +1301,12 @@ GM_HD_INL void jac_block_phase(const PlanView& P, int scen, const int32_t* bt, c
   if ((ROLES >> BR_AERO & 1) && role == BR_AERO) aero_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
   if ((ROLES >> BR_DYN_NOAIR & 1) && role == BR_DYN_NOAIR) dyn_noair_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
   if ((ROLES >> BR_DYN_GEN & 1) && role == BR_DYN_GEN) dyn_gen_phase(P, scen, x, vals, g, start, count, tid, phase, sm);
-  if ((ROLES >> BR_EVT & 1) && role == BR_EVT && (tid >> 4) < count) {
-    if (phase == 0) evt_jac_phase1(P, scen, x, start + (tid >> 4), tid, g != nullptr, sm);
-    else if (phase == 3) evt_jac_phase2(P, vals, g, start + (tid >> 4), tid, sm);
+  if ((ROLES >> BR_EVT & 1) && role == BR_EVT && (tid >> (GJ_EVT_PER_WARP ? 5 : 4)) < count &&
+      (!GJ_EVT_PER_WARP || (tid & 31) < 16)) {
+    const int job = tid >> (GJ_EVT_PER_WARP ? 5 : 4);
+    const int slot = job * 16 + (tid & (GJ_EVT_PER_WARP ? 31 : 15)); /* the 16-lane numbering the job functions use */
+    if (phase == 0) evt_jac_phase1(P, scen, x, start + job, slot, g != nullptr, sm);
+    else if (phase == 3) evt_jac_phase2(P, vals, g, start + job, slot, sm);
   }
   /* pair evaluation only: the linear rows and the objective (the launch leaves these blocks out otherwise) */
   if ((ROLES >> BR_LIN & 1) && role == BR_LIN && phase == 3 && g) {
