@@ -289,6 +289,10 @@ int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, c
                                   const double* ca, int32_t n_ca, const int64_t* scenario_strides, double t_init,
                                   const double* t_out, int32_t n_out, double dt, double* x_out, double* u_out) {
   LEAF_PROLOGUE
+  if (!x_init || !events || !zlt || !u_table || !wind || !ca || !t_out || !x_out) {
+    gelato_set_error_("rocket_simulation: null buffer");
+    return GELATO_ERR_ARG;
+  }
   if (n_ev <= 0 || n_u <= 0 || n_wind <= 0 || n_ca <= 0 || n_out <= 0 || !(dt > 0.0) || !scenario_strides) {
     gelato_set_error_("rocket_simulation: empty table, no output time or non-positive dt");
     return GELATO_ERR_ARG;

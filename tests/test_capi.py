@@ -155,3 +155,28 @@ def test_scenario_plans_must_agree_on_everything_that_is_not_carried_per_scenari
     bad.units = (plans[1].units[0],) + (plans[1].units[1] * 2.0,) + tuple(plans[1].units[2:])
     with pytest.raises(ValueError, match="unit"):
         engine.make_scenario_desc([plans[0], bad])
+
+
+def test_forward_simulation_entry_point_rejects_bad_arguments():
+    """gelato_init_rocket_simulation checks its arguments before it touches the device: n <= 0, null buffers, empty
+    tables, descending output times, strides shorter than a table (no GPU needed: every case fails first)."""
+    import ctypes
+
+    from gelato_b200 import engine
+    L = engine.load_library()
+    pd, pi32, pi64 = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+    x0, ev, zlt = np.zeros(11), np.zeros((2, 6)), np.zeros(2, dtype=np.int32)
+    ut, wind, ca = np.zeros((3, 4)), np.zeros((2, 3)), np.zeros((2, 2))
+    tout, out, strides = np.array([0.0, 1.0]), np.zeros((1, 2, 11)), np.zeros(4, dtype=np.int64)
+
+    def call(n=1, x0=x0, tout=tout, strides=strides, dt=0.1, n_ev=2):
+        P = lambda a, t=pd: a.ctypes.data_as(t) if a is not None else None  # noqa: E731
+        return L.gelato_init_rocket_simulation(0, n, P(x0), P(ev), P(zlt, pi32), n_ev, P(ut), 3, P(wind), 2, P(ca), 2,
+                                               P(strides, pi64), 0.0, P(tout), tout.size, dt, P(out), None)
+
+    assert call(n=0) == -1
+    assert call(x0=None) == -1 and b"null" in L.gelato_last_error()
+    assert call(dt=0.0) == -1
+    assert call(n_ev=0) == -1
+    assert call(tout=np.array([1.0, 0.5])) == -1 and b"ascend" in L.gelato_last_error()
+    assert call(strides=np.array([5, 0, 0, 0], dtype=np.int64)) == -1 and b"stride" in L.gelato_last_error()
