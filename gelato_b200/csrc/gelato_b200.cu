@@ -263,6 +263,10 @@ struct GelatoPlan {
   double *d_x = nullptr, *d_g = nullptr, *d_vals = nullptr;
   double *h_x = nullptr, *h_out = nullptr;  // pinned
   size_t cap_scen = 0;
+  // small host-buffer objfunc calls: upload, kernel and download as ONE captured graph launch (the staging pointers
+  // and the plan view are baked into it: rebuilt whenever either changes)
+  cudaGraphExec_t res_graph = nullptr;
+  int res_graph_n = 0;
   // subset batches (gelato_eval_*_ids)
   int32_t* d_ids = nullptr;
   double* d_vals_ids = nullptr;
@@ -524,12 +528,16 @@ int gelato_plan_set_scenarios(GelatoPlan* p, const GelatoScenarioDesc* sc) {
   // the staging Jacobian buffer holds the constants of the PREVIOUS scenarios: have it rebuilt on the next call
   p->cap_scen = 0;
   p->cap_ids = 0;
+  if (p->res_graph) cudaGraphExecDestroy(p->res_graph);
+  p->res_graph = nullptr;
+  p->res_graph_n = 0;
   return GELATO_OK;
 }
 
 int gelato_plan_destroy(GelatoPlan* p) {
   if (!p) return GELATO_OK;
   cudaSetDevice(p->device);
+  if (p->res_graph) cudaGraphExecDestroy(p->res_graph);
   for (void* d : p->owned) cudaFree(d);
   for (void* d : p->scen_owned) cudaFree(d);
   if (p->d_packed) cudaFree(p->d_packed);
@@ -658,9 +666,16 @@ int gelato_eval_jacobian_dev(GelatoPlan* p, const double* x_dev, double* vals_de
   return launch_jacobian(p, x_dev, vals_dev, nullptr, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, false);
 }
 
+static void drop_graphs(GelatoPlan* p) {
+  if (p->res_graph) cudaGraphExecDestroy(p->res_graph);
+  p->res_graph = nullptr;
+  p->res_graph_n = 0;
+}
+
 static int ensure_staging(GelatoPlan* p, size_t n_scen) {
   if (n_scen <= p->cap_scen) return GELATO_OK;
   CU(cudaSetDevice(p->device));
+  drop_graphs(p);
   if (p->d_x) cudaFree(p->d_x);
   if (p->d_g) cudaFree(p->d_g);
   if (p->d_vals) cudaFree(p->d_vals);
@@ -729,6 +744,34 @@ static int eval_host(GelatoPlan* p, int which, const double* x, double* out, int
         CU(cudaMemcpyAsync(d_out + (size_t)k * v.n_vals, p->vals_template + (size_t)ids[k] * p->vals_template_sstride,
                            (size_t)v.n_vals * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     }
+  }
+  // a small objfunc call (one NLP, a few scenarios) is launch-latency bound: upload + kernel + download go out as one
+  // graph launch through the pinned staging buffers (GELATO_B200_NO_GRAPH=1 keeps the three separate submissions)
+  static const bool use_graph = !getenv("GELATO_B200_NO_GRAPH");
+  if (which == 0 && !ids && use_graph && (nx + no) * sizeof(double) <= (size_t)64 * 1024) {
+    if (p->res_graph && p->res_graph_n != n_scen) drop_graphs(p);
+    if (!p->res_graph) {
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+      cudaMemcpyAsync(p->d_x, p->h_x, nx * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+      k_residuals<<<(unsigned)p->n_res_blocks * n_scen, GR_THREADS, 0, p->stream>>>(p->view, p->res_blocks, n_scen, nullptr, p->d_x,
+                                                                                p->d_g);
+      cudaMemcpyAsync(p->h_out, p->d_g, no * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+      CU(cudaStreamEndCapture(p->stream, &graph));
+      cudaError_t ge = cudaGraphInstantiate(&p->res_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ge != cudaSuccess) {
+        p->res_graph = nullptr;
+        return fail(GELATO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ge));
+      }
+      p->res_graph_n = n_scen;
+    }
+    memcpy(p->h_x, x, nx * sizeof(double));
+    CU(cudaGraphLaunch(p->res_graph, p->stream));
+    p->launches++;
+    CU(cudaStreamSynchronize(p->stream));
+    memcpy(out, p->h_out, no * sizeof(double));
+    return GELATO_OK;
   }
   const double* hx = x;
   if (!is_pinned(x)) {

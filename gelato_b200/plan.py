@@ -960,17 +960,30 @@ class CompiledPlan:
 
     def split_residuals(self, g):
         """g[n_rows] -> the reference's `funcs` dict (views into g)."""
+        steps = getattr(self, "_split_steps", None)
+        if steps is None:  # (key, mode, first, end) once per plan: this runs on every objfunc call
+            steps = []
+            for key in GROUPS:
+                gr = self.group_rows.get(key)
+                if gr is None:
+                    steps.append((key, 0, 0, 0))
+                elif key == "ineqcon_mass":  # a Python list in the reference (con_trajectory.py:61)
+                    steps.append((key, 2, gr[0], gr[0] + gr[1]))
+                elif key in ("eqcon_user", "ineqcon_user") and gr[1] == 1:  # one row: a scalar, like the shipped example's
+                    steps.append((key, 3, gr[0], gr[0] + 1))
+                else:
+                    steps.append((key, 1, gr[0], gr[0] + gr[1]))
+            self._split_steps = steps
         f = {"obj": g[0]}
-        for key in GROUPS:
-            gr = self.group_rows.get(key)
-            if gr is None:
+        for key, mode, a, b in steps:
+            if mode == 1:
+                f[key] = g[a:b]
+            elif mode == 0:
                 f[key] = None
-            elif key == "ineqcon_mass":  # a Python list in the reference (con_trajectory.py:61)
-                f[key] = [v for v in g[gr[0]: gr[0] + gr[1]]]
-            elif key in ("eqcon_user", "ineqcon_user"):  # one row: a scalar, like the shipped example's function
-                f[key] = g[gr[0]] if gr[1] == 1 else g[gr[0]: gr[0] + gr[1]]
+            elif mode == 2:
+                f[key] = list(g[a:b])
             else:
-                f[key] = g[gr[0]: gr[0] + gr[1]]
+                f[key] = g[a]
         return f
 
     def cost_jac(self):
