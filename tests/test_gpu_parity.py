@@ -479,3 +479,31 @@ def test_full_size_properties(variant, factor):
     v = prob.engine.eval_jacobian(problem.xdict_to_vector(x))
     assert np.isfinite(v).all()
     prob.close()
+
+
+def test_small_objfunc_calls_through_the_captured_graph_stay_exact():
+    """A small host-buffer objfunc call is one captured graph launch (upload, k_residuals, download).  The graph bakes
+    in the batch size and the staging pointers: alternating batch sizes, growing the staging buffers and going back
+    must keep returning the bits of the separate device-pointer path."""
+    import torch
+    prob, O, x0 = _problem()
+    E, P = prob.engine, prob.plan
+    X = np.stack([problem.xdict_to_vector(helpers.perturbed(x0, seed=k)) for k in range(5)])
+
+    def device_path(n):
+        xd = torch.from_numpy(X[:n].copy()).cuda()
+        gd = torch.empty((n, P.n_rows), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        E.eval_residuals_dev(xd.data_ptr(), gd.data_ptr(), n, None)
+        torch.cuda.synchronize()
+        return gd.cpu().numpy()
+
+    launches0 = E.launches
+    for n in (1, 1, 2, 1, 5, 2, 1):
+        g = np.asarray(E.eval_residuals(X[:n].ravel(), n)).reshape(n, -1)
+        assert np.array_equal(g, device_path(n)), n
+    assert E.launches - launches0 == 14  # one kernel per call on either path
+    fo, _ = O.objfunc(helpers.perturbed(x0, seed=0))
+    f, _ = prob.objfunc(helpers.perturbed(x0, seed=0))
+    helpers.assert_funcs_equal(fo, f)
+    prob.close()
