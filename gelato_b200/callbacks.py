@@ -37,11 +37,19 @@ class GelatoProblem:
         self._vals = None
         self._csr = None
         self._x = np.empty(self.plan.n_vars)
+        self._sizes = [self.plan.sizes[k] for k in VAR_ORDER]
 
     # -- helpers ---------------------------------------------------------
     def pack(self, xdict):
         """xdict -> flat decision vector in the engine's order (mass | position |
         velocity | quaternion | u | t), independent of the dict's key order."""
+        try:  # the usual case -- six 1-D arrays of the right sizes -- in one C call
+            parts = [xdict[k] for k in VAR_ORDER]
+            if [len(v) for v in parts] == self._sizes:
+                np.concatenate(parts, out=self._x)
+                return self._x
+        except (ValueError, TypeError):
+            pass
         o = 0
         for k in VAR_ORDER:
             n = self.plan.sizes[k]
