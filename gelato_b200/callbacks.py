@@ -38,6 +38,7 @@ class GelatoProblem:
         self._csr = None
         self._x = np.empty(self.plan.n_vars)
         self._sizes = [self.plan.sizes[k] for k in VAR_ORDER]
+        self._sens_dict = None
 
     # -- helpers ---------------------------------------------------------
     def pack(self, xdict):
@@ -68,11 +69,19 @@ class GelatoProblem:
     def sens(self, xdict, funcs=None):
         if self.reuse_output:
             if self._vals is None:
-                self._vals = _engine.PinnedArray(self.plan.n_vals)
+                alloc = getattr(self.engine, "alloc_output", None)  # the CUDA engine: page-locked memory
+                self._vals = alloc(self.plan.n_vals) if alloc else _engine.PinnedArray(self.plan.n_vals)
                 self.engine.jacobian_template(self._vals.array, 1)
             vals = self.engine.eval_jacobian_update(self.pack(xdict), self._vals.array, 1)
-        else:
-            vals = self.engine.eval_jacobian(self.pack(xdict))
+            # the dictionary is built once per key order: its COO data arrays are views of the one buffer the engine
+            # refreshes in place; only the dense user-constraint blocks are recomputed
+            order = tuple(k for k in xdict.keys() if k in VAR_ORDER)
+            if self._sens_dict is None or self._sens_dict[0] != order or self._sens_dict[2] is not vals:
+                self._sens_dict = (order, self.plan.split_jacobian(vals, key_order=list(order)), vals)
+            else:
+                self.plan.refresh_user_blocks(vals, self._sens_dict[1], order)
+            return self._sens_dict[1], False
+        vals = self.engine.eval_jacobian(self.pack(xdict))
         return self.plan.split_jacobian(vals, key_order=[k for k in xdict.keys() if k in VAR_ORDER]), False
 
     def jacobian_csr(self, xdict, wrt=None):

@@ -66,6 +66,14 @@ ORBIT_QUANTITIES = {"perigee_radius": 0, "apogee_radius": 1, "semi_major_axis": 
                     "inclination_deg": 4, "orbit_energy": 5, "angular_momentum": 6}
 
 
+class _UserBlocks(dict):
+    """{variable: (rows, size) array} of one user-constraint group; the arrays are column slices of `buffer`."""
+
+    def __init__(self, buffer):
+        super().__init__()
+        self.buffer = buffer
+
+
 class OrbitAtEvent:
     """GPU-resident built-in user constraint (the registry the reference's `user_constraints.py` hook maps onto,
     /root/reference/lib/con_user.py:33-42): up to three rows
@@ -996,31 +1004,56 @@ class CompiledPlan:
         gvec[-1] = 1.0
         return {"t": gvec}
 
-    def _user_dense(self, vals, spec, key_order):
+    def _user_dense(self, vals, spec, key_order, out=None):
         """Expand the 12 auxiliary quotients of every row into jac_fd's dense blocks
         (jac_fd.py:54-60): a variable the function does not read still gets
         (g(x after k restores) - g_base)/dx, k = how many of the six read
-        variables were visited before it."""
+        variables were visited before it.  `out`: the dictionary of an earlier call to refill in place (its arrays
+        are column slices of one (rows, n_vars) buffer, filled by one gather per row)."""
         _, job, srow = spec
         nrow = job["i32"][GE_NROW]
-        order = list(key_order)
-        if order.index("position") > order.index("velocity"):
-            raise NotImplementedError("xdict key order with velocity before position")
-        out = {key: np.empty((nrow, self.sizes[key])) for key in order}
-        for r in range(nrow):
-            a0 = job["i64"][GE_J_POS] + AUX_PER_USER * r
-            fd = vals[a0: a0 + 6]
-            bg = np.concatenate(([0.0], vals[a0 + 6: a0 + 12]))
-            k = 0
+        order = tuple(key_order)
+        maps = self.__dict__.setdefault("_user_maps", {})
+        idx = maps.get((order, srow))
+        if idx is None:
+            # every entry of a row is one of 13 values: q = [0, background quotients after 1..6 restores, the six
+            # finite-difference quotients]; which one depends only on the variable's place in the perturbation order
+            if order.index("position") > order.index("velocity"):
+                raise NotImplementedError("xdict key order with velocity before position")
+            parts, k = [], 0
             for key in order:
-                row = out[key][r]
-                row[:] = bg[k]
+                ix = np.full(self.sizes[key], k, dtype=np.intp)
                 if key in ("position", "velocity"):
                     j0 = 0 if key == "position" else 3
-                    row[3 * srow: 3 * srow + 3] = fd[j0: j0 + 3]
+                    ix[3 * srow: 3 * srow + 3] = 7 + j0 + np.arange(3)
                     k += 3
-                    row[3 * srow + 3:] = bg[k]
+                    ix[3 * srow + 3:] = k
+                parts.append(ix)
+            idx = maps[(order, srow)] = np.concatenate(parts)
+        if out is None:
+            buf = np.empty((nrow, idx.size))
+            out, o = _UserBlocks(buf), 0
+            for key in order:
+                out[key] = buf[:, o: o + self.sizes[key]]
+                o += self.sizes[key]
+        buf = out.buffer
+        q = np.empty(13)
+        q[0] = 0.0
+        a0 = job["i64"][GE_J_POS]
+        for r in range(nrow):
+            q[1:7] = vals[a0 + 6: a0 + 12]
+            q[7:13] = vals[a0: a0 + 6]
+            np.take(q, idx, out=buf[r])
+            a0 += AUX_PER_USER
         return out
+
+    def refresh_user_blocks(self, vals, sens_dict, key_order):
+        """Refill the dense user-constraint blocks of a `funcsSens` dictionary made by split_jacobian from the SAME
+        value buffer (its COO data arrays are views and already current; these blocks are computed)."""
+        for key in GROUPS:
+            b = self.blocks.get(key)
+            if isinstance(b, tuple):
+                self._user_dense(vals, b, key_order, out=sens_dict[key])
 
     def csr_map(self, wrt=None, key_order=VAR_ORDER):
         """The whole constraint Jacobian as ONE CSR matrix whose data is a gather of the flat value vector

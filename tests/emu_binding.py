@@ -121,5 +121,30 @@ class EmuEngine(Emulator):
         self.calls += 1
         return super().eval_jacobian(x, n_scen, scen_ids)
 
+    # update mode as the drop-in's default `sens` uses it: one output buffer kept across calls
+    class _HostArray:
+        def __init__(self, n):
+            self.array = np.empty(int(n))
+
+        def free(self):
+            self.array = None
+
+    def alloc_output(self, n):
+        return EmuEngine._HostArray(n)
+
+    def jacobian_template(self, out, n_scen=1):
+        assert n_scen == 1
+        out[:] = self.plan.vals_template
+        return out
+
+    def eval_jacobian_update(self, x, out, n_scen=1):
+        assert n_scen == 1
+        self.launches += 1
+        self.calls += 1
+        v = super().eval_jacobian(x, 1, None)
+        idx = self.plan.xdep_index()
+        out[idx] = v[idx]  # only the x-dependent slots move, as on the device
+        return out
+
     def close(self):
         pass
