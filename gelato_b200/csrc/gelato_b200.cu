@@ -267,6 +267,8 @@ struct GelatoPlan {
   // and the plan view are baked into it: rebuilt whenever either changes)
   cudaGraphExec_t res_graph = nullptr;
   int res_graph_n = 0;
+  double* h_small_out = nullptr;  // pinned staging of the small-problem path of update mode
+  size_t cap_small_out = 0;
   // subset batches (gelato_eval_*_ids)
   int32_t* d_ids = nullptr;
   double* d_vals_ids = nullptr;
@@ -538,6 +540,7 @@ int gelato_plan_destroy(GelatoPlan* p) {
   if (!p) return GELATO_OK;
   cudaSetDevice(p->device);
   if (p->res_graph) cudaGraphExecDestroy(p->res_graph);
+  if (p->h_small_out) cudaFreeHost(p->h_small_out);
   for (void* d : p->owned) cudaFree(d);
   for (void* d : p->scen_owned) cudaFree(d);
   if (p->d_packed) cudaFree(p->d_packed);
@@ -886,6 +889,16 @@ static int ensure_lanes(GelatoPlan* p, int n) {
 // The batch is cut into slices of scenarios, each on its own lane of streams: slice k's upload and kernels
 // overlap slice k-1's device->host traffic (PCIe is full duplex), and the host threads scatter slice k-1's
 // packed slots meanwhile.  Per slice: upload x -> { residual kernel -> copy g | Jacobian kernel -> transfers }.
+static int ensure_small_out(GelatoPlan* p, size_t n_doubles) {
+  if (n_doubles <= p->cap_small_out) return GELATO_OK;
+  if (p->h_small_out) cudaFreeHost(p->h_small_out);
+  p->h_small_out = nullptr;
+  p->cap_small_out = 0;
+  CU(cudaMallocHost(&p->h_small_out, n_doubles * sizeof(double)));
+  p->cap_small_out = n_doubles;
+  return GELATO_OK;
+}
+
 static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, int32_t n_scen) {
   int rc = check_scen(p, n_scen);
   if (rc) return rc;
@@ -907,6 +920,31 @@ static int eval_update(GelatoPlan* p, const double* x, double* g, double* vals, 
   if (!is_pinned(x)) {
     memcpy(p->h_x, x, (size_t)n_scen * v.n_vars * sizeof(double));
     hx = p->h_x;
+  }
+  // A small Jacobian (one NLP of a few hundred nodes) is cheaper to bring down whole than through the gather / strided
+  // copies / host scatter below: the staging copy on the device always holds the complete value vector (constants
+  // filled once, x-dependent slots rewritten by every launch), so one contiguous copy refreshes the caller's buffer
+  // to the same bits.
+  if ((size_t)n_scen * (size_t)v.n_vals * sizeof(double) <= (size_t)512 * 1024) {
+    CU(cudaMemcpyAsync(p->d_x, hx, (size_t)n_scen * v.n_vars * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if ((rc = launch_jacobian(p, p->d_x, p->d_vals, g ? p->d_g : nullptr, n_scen, p->stream, p->pair_stream, p->ev_fork,
+                              p->ev_join, nullptr, false)))
+      return rc;
+    const size_t nv = (size_t)n_scen * (size_t)v.n_vals, ng = (size_t)n_scen * v.n_rows;
+    const bool v_direct = is_pinned(vals), gd = g && is_pinned(g);
+    double* v_dst = vals;
+    double* g_dst = g;
+    if (!v_direct || (g && !gd)) {  // pageable: through one pinned staging block laid out [vals | g]
+      if ((rc = ensure_small_out(p, nv + ng))) return rc;
+      if (!v_direct) v_dst = p->h_small_out;
+      if (g && !gd) g_dst = p->h_small_out + nv;
+    }
+    CU(cudaMemcpyAsync(v_dst, p->d_vals, nv * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (g) CU(cudaMemcpyAsync(g_dst, p->d_g, ng * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    if (v_dst != vals) memcpy(vals, v_dst, nv * sizeof(double));
+    if (g && g_dst != g) memcpy(g, g_dst, ng * sizeof(double));
+    return GELATO_OK;
   }
   const bool g_direct = g && is_pinned(g);
   double* const g_dst = g_direct ? g : p->h_out;
