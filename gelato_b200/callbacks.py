@@ -22,7 +22,7 @@ from .plan import GROUPS, ORBIT_QUANTITIES, VAR_ORDER, CompiledPlan, OrbitAtEven
 
 class GelatoProblem:
     def __init__(self, pdict, unitdict, condition, user_eq=None, user_ineq=None, device=0, coord=None,
-                 engine_factory=None, reuse_output=True):
+                 engine_factory=None, reuse_output=True, fuse_pair=False):
         """engine_factory(plan) -> object with eval_residuals / eval_jacobian / close / launches;
         default: the CUDA engine on `device` (the CPU test tier passes the host emulator of the
         kernels, tests/emu_binding.py, to exercise this host logic without a GPU).
@@ -30,7 +30,13 @@ class GelatoProblem:
         reuse_output=True (default): `sens` writes into ONE page-locked buffer kept across calls and only the
         x-dependent Jacobian values cross PCIe (update mode); the returned COO data arrays are views of that
         buffer, valid until the next `sens` call -- what pyoptsparse needs (it converts them at once), and ~10x
-        less traffic on fine meshes.  reuse_output=False: fresh arrays on every call, like the reference."""
+        less traffic on fine meshes.  reuse_output=False: fresh arrays on every call, like the reference.
+
+        fuse_pair=True (needs reuse_output): every `objfunc` call runs the PAIR evaluation -- the Jacobian launch
+        that also writes objfunc's rows -- and keeps the Jacobian; a `sens` call at the same decision vector (what a
+        solver does after it accepts a point) then returns it without touching the GPU.  Same values bit for bit;
+        one call of ~0.07 ms instead of two for the shipped example, at the price of a Jacobian download for every
+        objfunc call that no sens follows (line-search trial points)."""
         self.plan = CompiledPlan(pdict, unitdict, condition, user_eq=user_eq, user_ineq=user_ineq, coord=coord)
         self.engine = engine_factory(self.plan) if engine_factory else _engine.Engine(self.plan, device=device)
         self.reuse_output = bool(reuse_output) and hasattr(self.engine, "eval_jacobian_update")
@@ -39,6 +45,9 @@ class GelatoProblem:
         self._x = np.empty(self.plan.n_vars)
         self._sizes = [self.plan.sizes[k] for k in VAR_ORDER]
         self._sens_dict = None
+        self.fuse_pair = bool(fuse_pair) and self.reuse_output and hasattr(self.engine, "eval_pair_update")
+        self._x_pair = None  # the decision vector the kept Jacobian belongs to
+        self._pair_fresh = False
 
     # -- helpers ---------------------------------------------------------
     def pack(self, xdict):
@@ -62,17 +71,34 @@ class GelatoProblem:
         return self._x
 
     # -- the two callbacks -------------------------------------------------
+    def _output_buffer(self):
+        if self._vals is None:
+            alloc = getattr(self.engine, "alloc_output", None)  # the CUDA engine: page-locked memory
+            self._vals = alloc(self.plan.n_vals) if alloc else _engine.PinnedArray(self.plan.n_vals)
+            self.engine.jacobian_template(self._vals.array, 1)
+        return self._vals.array
+
     def objfunc(self, xdict):
-        g = self.engine.eval_residuals(self.pack(xdict))
+        x = self.pack(xdict)
+        if self.fuse_pair:
+            g = np.empty(self.plan.n_rows)
+            self.engine.eval_pair_update(x, g, self._output_buffer(), 1)
+            if self._x_pair is None:
+                self._x_pair = np.empty_like(x)
+            self._x_pair[:] = x
+            self._pair_fresh = True
+            return self.plan.split_residuals(g), False
+        g = self.engine.eval_residuals(x)
         return self.plan.split_residuals(g), False
 
     def sens(self, xdict, funcs=None):
         if self.reuse_output:
-            if self._vals is None:
-                alloc = getattr(self.engine, "alloc_output", None)  # the CUDA engine: page-locked memory
-                self._vals = alloc(self.plan.n_vals) if alloc else _engine.PinnedArray(self.plan.n_vals)
-                self.engine.jacobian_template(self._vals.array, 1)
-            vals = self.engine.eval_jacobian_update(self.pack(xdict), self._vals.array, 1)
+            x = self.pack(xdict)
+            if self.fuse_pair and self._x_pair is not None and self._pair_fresh and np.array_equal(x, self._x_pair):
+                vals = self._output_buffer()  # already holds this point's Jacobian
+            else:
+                vals = self.engine.eval_jacobian_update(x, self._output_buffer(), 1)
+                self._pair_fresh = False
             # the dictionary is built once per key order: its COO data arrays are views of the one buffer the engine
             # refreshes in place; only the dense user-constraint blocks are recomputed
             order = tuple(k for k in xdict.keys() if k in VAR_ORDER)

@@ -146,5 +146,15 @@ class EmuEngine(Emulator):
         out[idx] = v[idx]  # only the x-dependent slots move, as on the device
         return out
 
+    def eval_pair_update(self, x, g_out, vals_out, n_scen=1):
+        assert n_scen == 1
+        self.launches += 1
+        self.calls += 1
+        g, v = super().eval_pair(x, 1, None, packed=False)
+        g_out[:] = g
+        idx = self.plan.xdep_index()
+        vals_out[idx] = v[idx]
+        return g_out.reshape(1, -1), vals_out.reshape(1, -1)
+
     def close(self):
         pass

@@ -55,14 +55,19 @@ def main():
         prob2 = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), reuse_output=True)
         sens_reuse_ms = timed(lambda: prob2.sens(x), reps)
         prob2.close()
+        prob3 = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), fuse_pair=True)
+        fused_ms = timed(lambda: (prob3.objfunc(x), prob3.sens(x)), reps)
+        prob3.close()
         row = {"variant": variant, "nodes": P.N, "sections": P.S, "n_vars": P.n_vars, "n_rows": P.n_rows,
                "n_vals": int(P.n_vals), "n_xdep": P.n_xdep, "evals_objfunc": ec["objfunc"], "evals_sens": ec["sens"],
                "plan_compile_s": t_plan, "k_residuals_ms": res_ms, "k_jacobian_ms": jac_ms,
                "device_evals_per_s": (ec["objfunc"] + ec["sens"]) / ((res_ms + jac_ms) * 1e-3),
                "objfunc_call_ms": obj_ms, "sens_call_fresh_arrays_ms": sens_ms, "sens_call_ms": sens_reuse_ms,
                "callback_pairs_per_s": 1e3 / (obj_ms + sens_reuse_ms),
+               "fused_pair_call_ms": fused_ms, "fused_callback_pairs_per_s": 1e3 / fused_ms,
                "note": "sens_call_ms: the drop-in default (reuse_output: one page-locked buffer kept across calls, only the "
-                       "x-dependent values cross PCIe); sens_call_fresh_arrays_ms: reuse_output=False (full copy into a new array)"}
+                       "x-dependent values cross PCIe); sens_call_fresh_arrays_ms: reuse_output=False (full copy into a new array); "
+                       "fused_pair_call_ms: objfunc then sens at the same x with fuse_pair=True (one pair evaluation)"}
         if P.N <= 1000:
             from oracle import leaves
 

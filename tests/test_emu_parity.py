@@ -305,3 +305,33 @@ def test_user_constraint_registry_matches_the_reference_jac_fd():
             for k in ja:
                 assert np.array_equal(ja[k], jb[k]), k
                 assert np.array_equal(xa[k], xb[k]), k
+
+
+def test_fused_pair_callbacks_return_the_same_dictionaries():
+    """GelatoProblem(fuse_pair=True): objfunc runs the pair evaluation and a sens call at the same decision vector is
+    answered from the kept Jacobian; at another vector (or twice in a row) sens evaluates.  Same funcs / funcsSens as
+    the separate callbacks, and the launch counts show which path ran."""
+    from gelato_b200 import callbacks
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c)
+    mk = lambda fuse: callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c,  # noqa: E731
+                                              engine_factory=emu_binding.EmuEngine, fuse_pair=fuse)
+    A, B = mk(False), mk(True)
+    assert B.fuse_pair
+    xa, xb = helpers.perturbed(x0, seed=1), helpers.perturbed(x0, seed=2)
+    fa, _ = A.objfunc(xa)
+    sa, _ = A.sens(xa, fa)
+    n0 = B.engine.calls
+    fb, _ = B.objfunc(xa)
+    sb, _ = B.sens(xa, fb)
+    assert B.engine.calls - n0 == 1  # the pair evaluation only
+    helpers.assert_funcs_equal(fa, fb)
+    helpers.assert_sens_equal(sa, sb)
+    # a sens at another point evaluates; the kept Jacobian is not reused afterwards
+    sa2, _ = A.sens(xb)
+    sb2, _ = B.sens(xb)
+    assert B.engine.calls - n0 == 2
+    helpers.assert_sens_equal(sa2, sb2)
+    sb3, _ = B.sens(xa)  # same x as the pair, but the buffer has moved on
+    assert B.engine.calls - n0 == 3
+    helpers.assert_sens_equal(A.sens(xa)[0], sb3)

@@ -507,3 +507,30 @@ def test_small_objfunc_calls_through_the_captured_graph_stay_exact():
     f, _ = prob.objfunc(helpers.perturbed(x0, seed=0))
     helpers.assert_funcs_equal(fo, f)
     prob.close()
+
+
+def test_fused_pair_callbacks_on_the_gpu():
+    """GelatoProblem(fuse_pair=True) on the device: objfunc runs the pair evaluation, the sens that follows at the
+    same decision vector launches nothing; both equal the oracle bit for bit, also after the buffer has moved on."""
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c,
+                                   fuse_pair=True)
+    assert prob.fuse_pair
+    for seed in (1, 2):
+        x = helpers.perturbed(x0, seed=seed)
+        n0 = prob.engine.calls
+        f, _ = prob.objfunc(x)
+        s, _ = prob.sens(x, f)
+        assert prob.engine.calls - n0 == 1
+        fo, _ = O.objfunc(helpers.copy_x(x))
+        so, _ = O.sens(helpers.copy_x(x))
+        helpers.assert_funcs_equal(fo, f)
+        helpers.assert_sens_equal(so, s)
+    xb = helpers.perturbed(x0, seed=3)
+    s, _ = prob.sens(xb)  # no objfunc before it: evaluates
+    helpers.assert_sens_equal(O.sens(helpers.copy_x(xb))[0], s)
+    s, _ = prob.sens(helpers.perturbed(x0, seed=2))  # the pair's point, but the buffer has moved on: evaluates
+    helpers.assert_sens_equal(O.sens(helpers.copy_x(helpers.perturbed(x0, seed=2)))[0], s)
+    prob.close()
