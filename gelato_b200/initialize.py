@@ -104,6 +104,43 @@ def rate_table(pdict, time_nodes):
     return u_nodes, u_table
 
 
+def _interp1d_extrapolate(x, y, x_new):
+    """scipy.interpolate.interp1d(x, y, axis=0, fill_value="extrapolate")(x_new) for sorted x, linear kind: the
+    two-weight form of scipy >= 1.10 (`_call_linear`: searchsorted, clip(1, n-1),
+    (x_new - x_lo)/(x_hi - x_lo) * y_hi + (x_hi - x_new)/(x_hi - x_lo) * y_lo)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    y2 = y.reshape(y.shape[0], -1)
+    hi = np.searchsorted(x, x_new).clip(1, len(x) - 1).astype(int)
+    lo = hi - 1
+    x_lo, x_hi = x[lo], x[hi]
+    out = ((x_new - x_lo) / (x_hi - x_lo))[:, None] * y2[hi] + ((x_hi - x_new) / (x_hi - x_lo))[:, None] * y2[lo]
+    return out.reshape((len(x_new),) + y.shape[1:])
+
+
+def initialize_xdict_6DoF_from_file(x_ref, pdict, condition, unitdict, mode="LGL", flag_display=False):
+    """initialize.py:322-413: the initial xdict by interpolating a reference trajectory table (a DataFrame or any
+    mapping of the columns time, mass, pos_ECI_X/Y/Z, vel_ECI_X/Y/Z, quat_ECI2BODY_0..3, rate_BODY_Y/Z) onto the
+    mesh.  Host code, as in the reference (it runs once per solve); same values as the reference's function with
+    the SciPy of this image, bit for bit (tests/test_initguess.py)."""
+    time_nodes, time_x_nodes = mesh_times(pdict, mode)
+    t_ref = np.asarray(x_ref["time"], dtype=np.float64)
+
+    def cols(names):
+        return np.column_stack([np.asarray(x_ref[n], dtype=np.float64) for n in names])
+
+    xdict = {"t": (np.array([e["time"] for e in pdict["params"]]) / unitdict["t"]).ravel()}
+    xdict["mass"] = (_interp1d_extrapolate(t_ref, np.asarray(x_ref["mass"], dtype=np.float64), time_x_nodes) / unitdict["mass"]).ravel()
+    xdict["position"] = (_interp1d_extrapolate(t_ref, cols(["pos_ECI_X", "pos_ECI_Y", "pos_ECI_Z"]), time_x_nodes)
+                         / unitdict["position"]).ravel()
+    xdict["velocity"] = (_interp1d_extrapolate(t_ref, cols(["vel_ECI_X", "vel_ECI_Y", "vel_ECI_Z"]), time_x_nodes)
+                         / unitdict["velocity"]).ravel()
+    xdict["quaternion"] = _interp1d_extrapolate(
+        t_ref, cols(["quat_ECI2BODY_0", "quat_ECI2BODY_1", "quat_ECI2BODY_2", "quat_ECI2BODY_3"]), time_x_nodes).ravel()
+    xdict["u"] = (_interp1d_extrapolate(t_ref, cols(["rate_BODY_Y", "rate_BODY_Z"]), time_nodes) / unitdict["u"]).ravel()
+    return xdict
+
+
 def _xdict_from_nodes(pdict, unitdict, u_nodes, x_nodes):
     xdict = {"t": (np.array([e["time"] for e in pdict["params"]]) / unitdict["t"]).ravel(),
              "u": (u_nodes / unitdict["u"]).ravel(),

@@ -126,3 +126,23 @@ def test_forward_simulation_kernel_on_the_gpu():
     assert np.array_equal(one, x_out[9])
     xd = initialize.initialize_xdict_batch(x0, pd, u, dt=dt)
     assert len(xd) == 64 and np.array_equal(xd[9]["mass"], x_out[9][:, 0] / u["mass"])
+
+
+@pytest.mark.skipif(not refharness.available(), reason="/root/reference not present on this machine")
+def test_file_based_initial_guess_matches_the_reference():
+    """initialize_xdict_6DoF_from_file (interpolation of the shipped trajectory table onto the mesh) against the
+    reference's own function, with the SciPy of this image: every array bit for bit, LGR and LGL meshes."""
+    import os
+
+    import pandas as pd
+
+    from gelato_b200 import initialize
+    ini = refharness.reference_initialize(leaves.get("libm"))
+    p, u, c, _ = helpers.example_problem()
+    x_ref = pd.read_csv(os.path.join(refharness.REF, "example", "example-trajectory_init.csv"))
+    for mode in ("LGR", "LGL"):
+        want = ini.initialize_xdict_6DoF_from_file(x_ref, p, c, u, mode, False)
+        got = initialize.initialize_xdict_6DoF_from_file(x_ref, p, c, u, mode, False)
+        assert list(got) == list(want)
+        for k in want:
+            assert np.array_equal(np.asarray(want[k]).ravel(), got[k]), (mode, k)
