@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/gelato_b200.h"
+#include "coord_leaves.h"
 #include "initguess.h"
 #include "output.h"
 
@@ -83,10 +84,20 @@ __global__ void k_leaf_aero(int kind, int n, const double* pos, const double* ve
                             const double* t, Tables tb, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (kind == 4) { /* wind_ned(altitude, table): t[] carries the altitudes (wrapper_utils.hpp:82-87) */
+    out[3 * i] = interp_table(t[i], tb.wind, tb.wind + 1, tb.n_wind, 3);
+    out[3 * i + 1] = interp_table(t[i], tb.wind, tb.wind + 2, tb.n_wind, 3);
+    out[3 * i + 2] = 0.0;
+    return;
+  }
   Quat q = q4(1.0, 0.0, 0.0, 0.0);
   if (quat) q = q4(quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]);
-  out[i] = aero_quantity(kind, v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]),
-                         v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]), q, t[i], tb);
+  const Vec3 p = v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), v = v3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+  if (kind == 3) { /* angle_of_attack_ab_rad -> (pitch-plane, yaw-plane) (wrapper_utils.hpp:125-148) */
+    angle_of_attack_ab(p, v, q, t[i], tb, out + 2 * i);
+    return;
+  }
+  out[i] = aero_quantity(kind, p, v, q, t[i], tb);
 }
 
 __global__ void k_leaf_eci2geodetic(int n, const double* pos, const double* t, double* out) {
@@ -159,6 +170,20 @@ __global__ void k_init_rocket_simulation(int n_scen, const double* x_init, const
                            x_out + (size_t)s * n_out * 11, u_out ? u_out + (size_t)s * n_out * 3 : nullptr);
 }
 
+
+// the coordinate_c / utils_c leaves that are not on the NLP path (coord_leaves.h), one thread per item
+__global__ void k_leaf_coordinate(int fn, int n, const double* a, int sa, const double* b, int sb, const double* t, double* out,
+                                  int so) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double av[GC_IN] = {0.0, 0.0, 0.0, 0.0}, bv[GC_IN] = {0.0, 0.0, 0.0, 0.0}, ov[GC_OUT];
+  for (int k = 0; k < sa; k++) av[k] = a[(size_t)i * sa + k];
+  for (int k = 0; k < sb; k++) bv[k] = b[(size_t)i * sb + k];
+  coord_leaf(fn, av, bv, t ? t[i] : 0.0, ov);
+  for (int k = 0; k < so; k++) out[(size_t)i * so + k] = ov[k];
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -214,17 +239,23 @@ int gelato_leaf_dynamics_quaternion(int device, int32_t n, const double* quat, c
 int gelato_leaf_aero(int device, int32_t kind, int32_t n, const double* pos, const double* vel, const double* quat,
                      const double* t, const double* wind, int32_t n_wind, double* out) {
   LEAF_PROLOGUE
-  if (kind < 0 || kind > 2 || (kind != 1 && !quat)) { gelato_set_error_("bad kind / missing quaternion"); return GELATO_ERR_ARG; }
+  const bool state = kind != 4;  // kind 4 (wind_ned) reads the altitudes in t and the table only
+  if (kind < 0 || kind > 4 || !t || !wind || n_wind <= 0 || !out || (state && (!pos || !vel)) ||
+      ((kind == 0 || kind == 2 || kind == 3) && !quat)) {
+    gelato_set_error_("gelato_leaf_aero: bad kind, missing quaternion or null buffer");
+    return GELATO_ERR_ARG;
+  }
   Tables tb;
   tb.wind = buf.in(wind, (size_t)n_wind * 3, err); tb.n_wind = n_wind;
   tb.ca = nullptr; tb.n_ca = 0;
-  const double* dp = buf.in(pos, (size_t)3 * n, err);
-  const double* dv = buf.in(vel, (size_t)3 * n, err);
-  const double* dq = quat ? buf.in(quat, (size_t)4 * n, err) : nullptr;
+  const double* dp = state ? buf.in(pos, (size_t)3 * n, err) : nullptr;
+  const double* dv = state ? buf.in(vel, (size_t)3 * n, err) : nullptr;
+  const double* dq = (state && quat) ? buf.in(quat, (size_t)4 * n, err) : nullptr;
   const double* dt = buf.in(t, n, err);
-  double* d_out = buf.out(n, err);
+  const size_t width = kind == 3 ? 2 : kind == 4 ? 3 : 1;
+  double* d_out = buf.out(width * n, err);
   if (err == cudaSuccess) k_leaf_aero<<<blocks_for(n), 128>>>(kind, n, dp, dv, dq, dt, tb, d_out);
-  return finish(err, out, d_out, n);
+  return finish(err, out, d_out, width * n);
 }
 
 int gelato_leaf_eci2geodetic(int device, int32_t n, const double* pos_eci, const double* t, double* out) {
@@ -330,6 +361,23 @@ int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, c
   if (err == cudaSuccess) err = cudaDeviceSynchronize();
   if (err == cudaSuccess && u_out) err = cudaMemcpy(u_out, d_uout, (size_t)n * n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost);
   return finish(err, x_out, d_out, (size_t)n * n_out * 11);
+}
+
+int gelato_leaf_coordinate(int device, int32_t fn, int32_t n, const double* a, int32_t a_width, const double* b, int32_t b_width,
+                           const double* t, double* out) {
+  LEAF_PROLOGUE
+  if (fn < 0 || fn >= GC_N_FUNCTIONS || a_width < 0 || a_width > GC_IN || b_width < 0 || b_width > GC_IN || !out ||
+      (a_width > 0 && !a) || (b_width > 0 && !b)) {
+    gelato_set_error_("gelato_leaf_coordinate: unknown function code, width outside 0..4 or null buffer");
+    return GELATO_ERR_ARG;
+  }
+  const int so = coord_leaf_n_out(fn);
+  const double* da = buf.in(a, (size_t)n * a_width, err);
+  const double* db = buf.in(b, (size_t)n * b_width, err);
+  const double* dt = t ? buf.in(t, (size_t)n, err) : nullptr;
+  double* d_out = buf.out((size_t)n * so, err);
+  if (err == cudaSuccess) k_leaf_coordinate<<<blocks_for(n), 128>>>(fn, n, da, a_width, db, b_width, dt, d_out, so);
+  return finish(err, out, d_out, (size_t)n * so);
 }
 
 }  // extern "C"

@@ -250,6 +250,7 @@ def load_library():
     L.gelato_leaf_iip.argtypes = [ctypes.c_int, i32, _pd, _pd, i32, _pd]
     L.gelato_leaf_atmosphere.argtypes = [ctypes.c_int, i32, _pd, _pd]
     L.gelato_leaf_output_table.argtypes = [ctypes.c_int, i32] + [_pd] * 9 + [i32, _pd, i32, _c_d, _c_d, _pd]
+    L.gelato_leaf_coordinate.argtypes = [ctypes.c_int, i32, i32, _pd, i32, _pd, i32, _pd, _pd]
     L.gelato_init_rocket_simulation.argtypes = [ctypes.c_int, i32, _pd, _pd, ctypes.POINTER(ctypes.c_int32), i32, _pd, i32,
                                                 _pd, i32, _pd, i32, ctypes.POINTER(ctypes.c_int64), _c_d, _pd, i32, _c_d, _pd, _pd]
     _lib = L
@@ -266,7 +267,7 @@ EXPORTS = (
     "gelato_eval_pair_packed_ids gelato_launch_kernel_dev "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
-    "gelato_leaf_atmosphere gelato_leaf_output_table gelato_init_rocket_simulation"
+    "gelato_leaf_atmosphere gelato_leaf_output_table gelato_init_rocket_simulation gelato_leaf_coordinate"
 ).split()
 
 

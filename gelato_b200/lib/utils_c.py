@@ -1,5 +1,6 @@
-"""utils_c (/root/reference/src/pybind_utils.cpp:28-48): the aero-constraint leaves on the GPU.
-Dimensional inputs, t in seconds, as in wrapper_utils.hpp:89-206."""
+"""utils_c (/root/reference/src/pybind_utils.cpp:28-48) on the GPU: the aero-constraint leaves, wind_ned and the
+two-plane angle of attack.  Dimensional inputs, t in seconds, as in wrapper_utils.hpp:82-206.  (haversine is not
+offered: no call site in the reference's live code.)"""
 import numpy as np
 
 from ._leaf import arr, call, ptr
@@ -39,3 +40,28 @@ def dynamic_pressure_pa(pos_eci, vel_eci, t, wind):
 
 def q_alpha_pa_rad(pos_eci, vel_eci, quat, t, wind):
     return float(_aero(2, pos_eci, vel_eci, quat, [t], wind)[0])
+
+
+def angle_of_attack_ab_array_rad(pos_eci, vel_eci, quat, t, wind):
+    """wrapper_utils.hpp:150-161 -> (n, 2): pitch-plane and yaw-plane angles of the air-relative velocity in body axes."""
+    pos = arr(pos_eci).reshape(-1, 3)
+    n = pos.shape[0]
+    w = arr(wind)
+    out = np.empty((n, 2))
+    call("gelato_leaf_aero", 3, n, ptr(pos), ptr(arr(vel_eci, (n, 3))), ptr(arr(quat, (n, 4))), ptr(arr(t).ravel()), ptr(w),
+         w.shape[0], ptr(out))
+    return out
+
+
+def angle_of_attack_ab_rad(pos_eci, vel_eci, quat, t, wind):
+    """wrapper_utils.hpp:125-148"""
+    return angle_of_attack_ab_array_rad(pos_eci, vel_eci, quat, [t], wind)[0]
+
+
+def wind_ned(altitude_m, wind):
+    """wrapper_utils.hpp:82-87 -> (north, east, 0) wind at an altitude (or (n, 3) for n altitudes)."""
+    alt = arr(altitude_m).ravel()
+    w = arr(wind)
+    out = np.empty((alt.size, 3))
+    call("gelato_leaf_aero", 4, alt.size, ptr(None), ptr(None), ptr(None), ptr(alt), ptr(w), w.shape[0], ptr(out))
+    return out[0] if np.ndim(altitude_m) == 0 else out

@@ -319,8 +319,10 @@ int gelato_fp64_peak(int device, double* tflops_fma, double* tflops_nofma);
  *   gelato_leaf_dynamics_velocity_noair  dynamics_c.dynamics_velocity_NoAir (:73-92)
  *   gelato_leaf_dynamics_quaternion      dynamics_c.dynamics_quaternion (:94-106; out n x 4)
  *   gelato_leaf_aero                     utils_c.angle_of_attack_all_array_rad (kind 0), dynamic_pressure_array_pa
- *                                         (kind 1, quat may be NULL), q_alpha_array_pa_rad (kind 2)
- *                                         (/root/reference/src/wrapper_utils.hpp:113-206; dimensional inputs, t in seconds)
+ *                                         (kind 1, quat may be NULL), q_alpha_array_pa_rad (kind 2),
+ *                                         angle_of_attack_ab_array_rad (kind 3, out n x 2: pitch-plane, yaw-plane),
+ *                                         wind_ned (kind 4: t[] carries the altitudes, pos / vel / quat unused, out n x 3)
+ *                                         (/root/reference/src/wrapper_utils.hpp:82-206; dimensional inputs, t in seconds)
  *   gelato_leaf_eci2geodetic             coordinate_c.eci2geodetic (wrapper_coordinate.hpp:193-199; lat deg, lon deg, alt m)
  *   gelato_leaf_gravity                  coordinate_c.gravity (gravity.cpp:11-57)
  *   gelato_leaf_iip                      IIP_c.posLLH_IIP_FAA(posECEF, velECEF, fill_na) (pybind_IIP.cpp:34-51)
@@ -378,6 +380,41 @@ int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, c
                                   int32_t n_ev, const double* u_table, int32_t n_u, const double* wind, int32_t n_wind,
                                   const double* ca, int32_t n_ca, const int64_t* scenario_strides, double t_init,
                                   const double* t_out, int32_t n_out, double dt, double* x_out, double* u_out);
+
+/* The coordinate_c leaves that are not on the NLP path (/root/reference/src/pybind_coordinate.cpp:28-78), n items by
+ * one launch, one thread per item.  fn: GC_* below; a / b: per-item input vectors of a_width / b_width doubles (0..4);
+ * t: per-item time or NULL; out: [n][width of the function's result].
+ *   code  function (reference name)            a                      b            t   out
+ *    0    quatmult                             q[4]                   p[4]             4
+ *    1    conj                                 q[4]                                    4
+ *    2/3  normalize (3 / 4 elements)           v                                       3 / 4
+ *    4    quatrot                              q[4]                   v[3]             3
+ *    5    ecef2geodetic                        x, y, z                                 lat deg, lon deg, alt m
+ *    6    geodetic2ecef                        lat deg, lon deg, alt                   3
+ *    7/8  ecef2eci / eci2ecef                  v[3]                                t   3
+ *    9/10 vel_ecef2eci / vel_eci2ecef          vel[3]                 pos[3]       t   3
+ *   11/12 quat_eci2ecef / quat_ecef2eci                                            t   4
+ *   13/14 quat_ecef2nedg / quat_nedg2ecef      pos_ecef[3]                             4
+ *   15/16 quat_eci2nedg / quat_nedg2eci        pos_eci[3]                          t   4
+ *   17    quat_from_euler                      az, el, ro deg                          4
+ *   18    euler_from_quat                      q[4]                                    3 (deg)
+ *   19    quat_nedg2body                       quat_eci2body[4]       pos_eci[3]   t   4
+ *   20    orbital_elements                     pos[3]                 vel[3]           a, e, i, Omega, omega, nu (deg)
+ *   21    distance_vincenty                    lat0, lon0, lat1, lon1 deg              1 (m)
+ *   22-26 angular_momentum_vec, angular_momentum, inclination_rad, inclination_cosine, orbit_energy
+ *                                              pos[3]                 vel[3]           3 / 1 / 1 / 1 / 1
+ *   27/28 angular_momentum_from_altitude / orbit_energy_from_altitude   ha, hp         1
+ * (dcm_from_quat, quat_from_dcm, euler_from_dcm, dcm_from_thrustvector, laplace_vector: not offered -- no call site
+ * in the reference's live code.) */
+enum {
+  GC_QUATMULT = 0, GC_CONJ, GC_NORMALIZE3, GC_NORMALIZE4, GC_QUATROT, GC_ECEF2GEODETIC, GC_GEODETIC2ECEF, GC_ECEF2ECI,
+  GC_ECI2ECEF, GC_VEL_ECEF2ECI, GC_VEL_ECI2ECEF, GC_QUAT_ECI2ECEF, GC_QUAT_ECEF2ECI, GC_QUAT_ECEF2NEDG, GC_QUAT_NEDG2ECEF,
+  GC_QUAT_ECI2NEDG, GC_QUAT_NEDG2ECI, GC_QUAT_FROM_EULER, GC_EULER_FROM_QUAT, GC_QUAT_NEDG2BODY, GC_ORBITAL_ELEMENTS,
+  GC_DISTANCE_VINCENTY, GC_ANGMOM_VEC, GC_ANGMOM, GC_INCLINATION_RAD, GC_INCLINATION_COS, GC_ORBIT_ENERGY,
+  GC_ANGMOM_FROM_ALT, GC_ENERGY_FROM_ALT, GC_N_FUNCTIONS
+};
+int gelato_leaf_coordinate(int device, int32_t fn, int32_t n, const double* a, int32_t a_width, const double* b, int32_t b_width,
+                           const double* t, double* out);
 
 #ifdef __cplusplus
 }

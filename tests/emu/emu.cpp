@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../gelato_b200/csrc/coord_leaves.h"
 #include "../../gelato_b200/csrc/host_pool.h"
 #include "../../gelato_b200/csrc/initguess.h"
 #include "../../gelato_b200/csrc/output.h"
@@ -178,5 +179,17 @@ extern "C" void emu_rocket_simulation(int n, const double* x_init, const double*
     tb.ca = ca + s * ss[3]; tb.n_ca = n_ca;
     rocket_simulation_thread(x_init + s * ss[0], events + s * ss[1], zlt, n_ev, u_table, n_u, tb, t_init, t_out, n_out, dt,
                              x_out + (size_t)s * n_out * 11, u_out ? u_out + (size_t)s * n_out * 3 : nullptr);
+  }
+}
+
+// the coordinate leaf kernel's per-thread function (coord_leaves.h), one call per item
+extern "C" void emu_coord_leaf(int fn, int n, const double* a, int sa, const double* b, int sb, const double* t, double* out) {
+  const int so = coord_leaf_n_out(fn);
+  for (int i = 0; i < n; i++) {
+    double av[GC_IN] = {0.0, 0.0, 0.0, 0.0}, bv[GC_IN] = {0.0, 0.0, 0.0, 0.0}, ov[GC_OUT];
+    for (int k = 0; k < sa; k++) av[k] = a[(size_t)i * sa + k];
+    for (int k = 0; k < sb; k++) bv[k] = b[(size_t)i * sb + k];
+    coord_leaf(fn, av, bv, t ? t[i] : 0.0, ov);
+    for (int k = 0; k < so; k++) out[(size_t)i * so + k] = ov[k];
   }
 }

@@ -59,6 +59,14 @@ def test_utils_c_and_coordinate_c():
     _eq(coordinate_c.eci2geodetic(pos, t), [L.coordinate_c.eci2geodetic(p, tt) for p, tt in zip(pos, t)], "eci2geodetic")
     _eq(coordinate_c.eci2geodetic(pos[0], t[0]), L.coordinate_c.eci2geodetic(pos[0], t[0]), "eci2geodetic one")
     _eq(coordinate_c.gravity(pos), [L.coordinate_c.gravity(p) for p in pos], "gravity")
+    k = 300
+    _eq(utils_c.angle_of_attack_ab_array_rad(pos[:k], vel[:k], q[:k], t[:k], wind),
+        [L.utils_c.angle_of_attack_ab_rad(pos[i], vel[i], q[i], t[i], wind) for i in range(k)], "alpha pitch / yaw")
+    _eq(utils_c.angle_of_attack_ab_rad(pos[5], vel[5], q[5], t[5], wind),
+        L.utils_c.angle_of_attack_ab_rad(pos[5], vel[5], q[5], t[5], wind), "alpha pitch / yaw, one point")
+    alt = np.random.default_rng(8).uniform(-500.0, 60000.0, k)
+    _eq(utils_c.wind_ned(alt, wind), [L.utils_c.wind_ned(a, wind) for a in alt], "wind_ned")
+    _eq(utils_c.wind_ned(1234.5, wind), L.utils_c.wind_ned(1234.5, wind), "wind_ned, one altitude")
 
 
 def test_iip_and_atmosphere():
