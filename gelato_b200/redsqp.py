@@ -31,6 +31,7 @@ multipliers on the active set -- IPOPT's scaled test (`tol`, default 1e-6) -- pl
 original problem.
 """
 import time
+import types
 
 import numpy as np
 import scipy.optimize as so
@@ -280,6 +281,10 @@ class ReducedSQP:
             if hist["it"] >= o["max_iter"]:
                 raise Done()
 
+        # the reduced problem of this call, for diagnostics (tests/scripts): q = w p
+        self.reduced = types.SimpleNamespace(at=at, kkt=kkt, feas=feas, p_cols=p_cols, s_cols=s_cols, w=w, lower=xl[p_cols] * w,
+                                             upper=xu[p_cols] * w, e_rows=e_rows, i_rows=i_rows, state=S, xdict=xdict,
+                                             row_names=[g[0] for g in cons for _ in range(g[1])])
         cons_sq = [{"type": "eq", "fun": ceq, "jac": lambda pv: at(pv, True)["Je"]},
                    {"type": "ineq", "fun": cin, "jac": lambda pv: at(pv, True)["Ji"]}]
         pv = x0[p_cols] * w
@@ -342,6 +347,7 @@ class ReducedSQP:
         sol.constr_violation = float(feas(e["c"]))
         sol.optimality = float(hist["kkt"])
         sol.reduced_evaluations = S["evals"]
+        sol.q = np.array(pv)
         sol.optTime = time.perf_counter() - t_start
         sol.userObjTime, sol.userObjCalls = stat["obj_t"], stat["obj_n"]
         sol.userSensTime, sol.userSensCalls = stat["sens_t"], stat["sens_n"]
