@@ -135,13 +135,21 @@ k_jacobian_noair(const __grid_constant__ PlanView P, const int first, const int 
                  double* __restrict__ g_all) {
   const int per = (count + 31) / 32;  // blocks per scenario
   const int scen = blockIdx.x / per;
-  const int k = (blockIdx.x - scen * per) * 32 + (threadIdx.x & 31);
-  if (k >= count) return;
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int k = (blockIdx.x - scen * per) * 32 + lane;
+  __shared__ double grav[32][NPV * 3];  // the node's five gravity vectors, shared by the four parts
   const double* x = x_all + (size_t)scen * P.n_vars;
   double* out = out_all + (size_t)scen * (size_t)(P.packed ? P.n_pack : P.n_vals);
   double* g = g_all ? g_all + (size_t)scen * P.n_rows : nullptr;
   const int sid = scen_ids ? scen_ids[scen] : scen;
-  dyn_noair_part(P, sid, x, out, g, jac_node(P, first + k), threadIdx.x >> 5);
+  const bool live = k < count;
+  NodeRef nr;
+  if (live) {
+    nr = jac_node(P, first + k);
+    for (int pv = part; pv < NPV; pv += GV_PARTS) dyn_noair_gravity(P, sid, x, nr, pv, grav[lane] + 3 * pv);
+  }
+  __syncthreads();
+  if (live) dyn_noair_part(P, sid, x, out, g, nr, part, grav[lane]);
 }
 
 #ifndef GR_MIN_BLOCKS

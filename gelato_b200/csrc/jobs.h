@@ -658,24 +658,36 @@ GM_HD_INL void dyn_noair_phase(const PlanView& P, int scen, const double* x, dou
 /* ========================================================================= */
 /* One node's columns in GV_PARTS independent parts (a warp per part in k_jacobian_noair: the parts differ in code
  * path, so they must not share a warp).  Every value is a pure function of (node, lane): each part recomputes the
- * centre column it differences against, which costs ~30 % more arithmetic and cuts the dependent chain 3x.
+ * centre column it differences against (cheap once gravity is shared) and the dependent chain is 3x shorter.
  *   part 0: lane 0 (the analytic t columns), lanes 1, 2      part 2: lanes 6, 8, 9
- *   part 1: lanes 3, 4, 5                                    part 3: lanes 10, 11 and, in a pair evaluation, the defects
- * Lanes 5-7 carry no velocity columns in vacuum (5, 6: the u columns of the quaternion rows; 7: nothing).  (The
- * defects as a fifth part, 160-thread blocks, measured slower: 0.075 against 0.062 ms.) */
+ *   part 1: lanes 3, 4, 5                                    part 3: lanes 10, 11
+ * and, in a pair evaluation, the node's defect rows: velocity with part 1, position with part 2, quaternion and mass
+ * with part 3.  Lanes 5-7 carry no velocity columns in vacuum (5, 6: the u columns of the quaternion rows; 7: nothing).
+ * (The defects as a fifth part, 160-thread blocks, measured slower: 0.075 against 0.062 ms.)
+ * The J2 gravity vector -- the expensive piece of a vacuum column -- has only NPV = 5 distinct arguments per node
+ * (pristine, x / y / z perturbed, all restored); the parts would evaluate 10 of them between themselves.  Phase A
+ * (dyn_noair_gravity, one variant per warp, the fourth warp two) puts the five into shared memory, phase B
+ * (dyn_noair_part) reads them. */
 #define GV_PARTS 4
-P_HD void dyn_noair_part(const PlanView& P, int scen, const double* x, double* vals, double* g, const NodeRef& nr, int part) {
+P_HD void dyn_noair_gravity(const PlanView& P, int scen, const double* x, const NodeRef& nr, int pv, double* out3) {
+  const Units un = scen_units(P, scen);
+  double p[3];
+  pos_variant(x + P.off_pos + 3 * nr.row, pv, un.dx, p);
+  const Vec3 gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
+  out3[0] = gr.x; out3[1] = gr.y; out3[2] = gr.z;
+}
+/* grav: the node's NPV gravity vectors, [pv][3] */
+P_HD void dyn_noair_part(const PlanView& P, int scen, const double* x, double* vals, double* g, const NodeRef& nr, int part,
+                         const double* grav) {
   const Units un = scen_units(P, scen);
   const double dx = un.dx;
   const SecParam sp = sec_param(P, scen, nr.sec);
   const bool hold = nr.flags & GSF_HOLD;
   double fc[3], fl[3], qc[4] = {0.0, 0.0, 0.0, 0.0}, ql[4] = {0.0, 0.0, 0.0, 0.0};
-  double v[11], p[3];
+  double v[11];
   /* centre column: pristine state, gravity at the pristine position */
   dyn_col_state(P, x, nr.row, 0, false, dx, v);
-  pos_variant(x + P.off_pos + 3 * nr.row, 0, dx, p);
-  Vec3 gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
-  Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), gr, sp, un);
+  Vec3 f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), v3(grav[0], grav[1], grav[2]), sp, un);
   fc[0] = f.x; fc[1] = f.y; fc[2] = f.z;
   if (!hold && part < 3) dyn_quat_variant(P, x, nr, un, 0, qc);
   if (part == 0) {
@@ -685,35 +697,36 @@ P_HD void dyn_noair_part(const PlanView& P, int scen, const double* x, double* v
   }
   const int first = part == 0 ? 1 : part == 1 ? 3 : part == 2 ? 6 : 10;
   const int last = part == 0 ? 2 : part == 1 ? 5 : part == 2 ? 9 : 11;
-  bool restored = false;
   for (int lane = first; lane <= last; lane++) {
     if (lane == 7) continue;
     const bool vel_lane = lane >= 5 && lane <= 7;
     if (!vel_lane) {
       dyn_col_state(P, x, nr.row, lane, false, dx, v);
-      /* the position changes with lanes 2-4 and is fully restored from lane 5 on: lanes 8-11 share lane 8's */
-      if (lane <= 4 || !restored) {
-        pos_variant(x + P.off_pos + 3 * nr.row, lane_pv(lane <= 4 ? lane : 8), dx, p);
-        gr = gravity_eci(v3(p[0] * un.pos, p[1] * un.pos, p[2] * un.pos));
-        restored = lane > 4;
-      }
-      f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), gr, sp, un);
+      /* the position changes with lanes 2-4 and is fully restored from lane 5 on: lanes 8-11 share variant 4 */
+      const double* gv = grav + 3 * lane_pv(lane);
+      f = rhs_velocity_noair_col(v[0], q4(v[7], v[8], v[9], v[10]), v3(gv[0], gv[1], gv[2]), sp, un);
       fl[0] = f.x; fl[1] = f.y; fl[2] = f.z;
     }
     if (!hold && lane <= 6) dyn_quat_variant(P, x, nr, un, lane, ql);
     dyn_scatter(P, scen, x, vals, nr, lane, fc, fl, qc, ql);
   }
-  if (part == 3 && g) { /* pair evaluation: the node's collocation defects */
+  if (g && part > 0) { /* pair evaluation: the node's collocation defects, spread over the three lighter parts --
+                          position | velocity | quaternion and mass (groups 0 | 2 | 1, 3 of dyn_lh_item) */
     double lh[11], qp[4] = {0.0, 0.0, 0.0, 0.0};
-    if (!hold) dyn_quat_variant(P, x, nr, un, 7, qp);
-    for (int grp = 0; grp < 4; grp++) {
-      dyn_lh_item(P, x, nr, grp, lh);
-      dyn_res_finish(P, scen, x, g, nr, grp, lh, fc, qp);
+    if (part == 3 && !hold) dyn_quat_variant(P, x, nr, un, 7, qp);
+    const int g0 = part == 2 ? 0 : part == 1 ? 2 : 1;
+    dyn_lh_item(P, x, nr, g0, lh);
+    dyn_res_finish(P, scen, x, g, nr, g0, lh, fc, qp);
+    if (part == 3) {
+      dyn_lh_item(P, x, nr, 3, lh);
+      dyn_res_finish(P, scen, x, g, nr, 3, lh, fc, qp);
     }
   }
 }
 P_HD void dyn_noair_node(const PlanView& P, int scen, const double* x, double* vals, double* g, const NodeRef& nr) {
-  for (int part = 0; part < GV_PARTS; part++) dyn_noair_part(P, scen, x, vals, g, nr, part);
+  double grav[NPV * 3];
+  for (int pv = 0; pv < NPV; pv++) dyn_noair_gravity(P, scen, x, nr, pv, grav + 3 * pv);
+  for (int part = 0; part < GV_PARTS; part++) dyn_noair_part(P, scen, x, vals, g, nr, part, grav);
 }
 
 /* ========================================================================= */
