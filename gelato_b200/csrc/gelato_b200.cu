@@ -334,24 +334,34 @@ static int upload(GelatoPlan* p, const T* src, size_t count, const T** dst) {
 // (Variants measured and dropped: phase 0 as its own launch with pp | rq | q staged through L2, 38 % slower,
 // profiles/r01i_split_ab.txt; the vacuum nodes as blocks of the block kernel, 0.084 ms instead of 0.03,
 // profiles/r02_probe.txt.)
+// A sub-range of the evaluation (one problem sharded over GPUs): blocks [b0, b0 + nb) of the block table and vacuum
+// nodes [v0, v0 + nv) of the vacuum list; nb < 0: everything.
+struct JacRange {
+  int b0 = 0, nb = -1, v0 = 0, nv = 0;
+};
 static int launch_jacobian(GelatoPlan* p, const double* x_dev, double* out_dev, double* g_dev, int n_scen, cudaStream_t st,
-                           cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, const int32_t* ids_dev, bool packed) {
+                           cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, const int32_t* ids_dev, bool packed,
+                           JacRange rg = JacRange()) {
   PlanView v = p->view;
   v.packed = packed ? 1 : 0;
-  const int nb = g_dev ? p->n_jac_blocks : p->n_jac_main;
-  const bool side = p->n_vac > 0 && nb > 0 && aux != st;
+  const bool all = rg.nb < 0;
+  const int nb = all ? (g_dev ? p->n_jac_blocks : p->n_jac_main) : rg.nb;
+  const int nv = all ? p->n_vac : rg.nv;
+  const int v_first = p->vac_first + (all ? 0 : rg.v0);
+  const int32_t* table = p->jac_blocks + (size_t)(all ? 0 : rg.b0) * BT_COLS;
+  const bool side = nv > 0 && nb > 0 && aux != st;
   if (side) {
     CU(cudaEventRecord(ev_fork, st));
     CU(cudaStreamWaitEvent(aux, ev_fork, 0));
   }
-  if (p->n_vac > 0) {
-    const int per = (p->n_vac + 31) / 32;
-    k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, side ? aux : st>>>(v, p->vac_first, p->n_vac, n_scen, ids_dev, x_dev,
-                                                                                out_dev, g_dev);
+  if (nv > 0) {
+    const int per = (nv + 31) / 32;
+    k_jacobian_noair<<<(unsigned)per * n_scen, GV_THREADS, 0, side ? aux : st>>>(v, v_first, nv, n_scen, ids_dev, x_dev, out_dev,
+                                                                                g_dev);
     p->launches++;
   }
   if (nb > 0) {
-    k_jacobian<<<(unsigned)nb * n_scen, GJ_THREADS, 0, st>>>(v, p->jac_blocks, n_scen, ids_dev, x_dev, out_dev, g_dev);
+    k_jacobian<<<(unsigned)nb * n_scen, GJ_THREADS, 0, st>>>(v, table, n_scen, ids_dev, x_dev, out_dev, g_dev);
     p->launches++;
   }
   CU(cudaGetLastError());
@@ -604,6 +614,7 @@ int32_t gelato_plan_n_blocks(const GelatoPlan* p, int which) {
     case 1: return p->n_jac_main;
     case 2: return p->n_jac_heavy;
     case 3: return p->n_jac_light;
+    case 5: return p->n_vac;
     default: return p->n_jac_blocks;
   }
 }
@@ -649,6 +660,26 @@ int gelato_eval_pair_packed_dev(GelatoPlan* p, const double* x_dev, double* g_de
   CU(cudaSetDevice(p->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
   return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, true);
+}
+
+// ONE problem sharded over GPUs: the pair evaluation restricted to blocks
+// [block_first, block_first + block_count) of the block table and vacuum nodes [vac_first, vac_first + vac_count).
+// Every output slot and residual row belongs to exactly one block or vacuum node, so ranks with disjoint ranges that
+// cover everything fill disjoint parts of the packed vector and of g.
+int gelato_eval_pair_packed_range_dev(GelatoPlan* p, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
+                                      int32_t block_first, int32_t block_count, int32_t vac_first, int32_t vac_count,
+                                      void* stream) {
+  int rc = check_scen(p, n_scen);
+  if (rc) return rc;
+  if (!g_dev || !packed_dev) return fail(GELATO_ERR_ARG, "null buffer");
+  if (block_first < 0 || block_count < 0 || block_first + block_count > p->n_jac_blocks || vac_first < 0 || vac_count < 0 ||
+      vac_first + vac_count > p->n_vac)
+    return fail(GELATO_ERR_ARG, "block or vacuum-node range outside the plan");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  JacRange rg;
+  rg.b0 = block_first; rg.nb = block_count; rg.v0 = vac_first; rg.nv = vac_count;
+  return launch_jacobian(p, x_dev, packed_dev, g_dev, n_scen, st, p->pair_stream, p->ev_fork, p->ev_join, nullptr, true, rg);
 }
 
 int gelato_fill_template(GelatoPlan* p, double* vals_dev, int32_t n_scen, void* stream) {

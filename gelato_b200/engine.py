@@ -222,6 +222,8 @@ def load_library():
     L.gelato_eval_pair_update.argtypes = [vp, _pd, _pd, _pd, ctypes.c_int32]
     L.gelato_eval_pair_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
     L.gelato_eval_pair_packed_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, vp]
+    L.gelato_eval_pair_packed_range_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_int32, vp]
     L.gelato_plan_n_pack.argtypes = [vp]
     L.gelato_plan_n_pack.restype = ctypes.c_int64
     L.gelato_plan_packed_map.argtypes = [vp, _pi64, _pi64, _pd]
@@ -267,7 +269,8 @@ EXPORTS = (
     "gelato_eval_pair_packed_ids gelato_launch_kernel_dev "
     "gelato_pack_xdep_dev gelato_leaf_dynamics_velocity gelato_leaf_dynamics_velocity_noair "
     "gelato_leaf_dynamics_quaternion gelato_leaf_aero gelato_leaf_eci2geodetic gelato_leaf_gravity gelato_leaf_iip "
-    "gelato_leaf_atmosphere gelato_leaf_output_table gelato_init_rocket_simulation gelato_leaf_coordinate"
+    "gelato_leaf_atmosphere gelato_leaf_output_table gelato_init_rocket_simulation gelato_leaf_coordinate "
+    "gelato_eval_pair_packed_range_dev"
 ).split()
 
 
@@ -298,6 +301,7 @@ class Engine:
         self.n_jac_heavy = L.gelato_plan_n_blocks(h, 2)
         self.n_jac_light = L.gelato_plan_n_blocks(h, 3)
         self.n_jac_blocks_pair = L.gelato_plan_n_blocks(h, 4)
+        self.n_vacuum_nodes = L.gelato_plan_n_blocks(h, 5)
         self.n_vars = L.gelato_plan_n_vars(h)
         self.n_rows = L.gelato_plan_n_rows(h)
         self.n_vals = L.gelato_plan_n_vals(h)
@@ -426,6 +430,13 @@ class Engine:
     def eval_pair_packed_dev(self, x_ptr, g_ptr, packed_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_pair_packed_dev(self.h, x_ptr, g_ptr, packed_ptr, n_scen, stream),
                "gelato_eval_pair_packed_dev")
+
+    def eval_pair_packed_range_dev(self, x_ptr, g_ptr, packed_ptr, blocks, vacuum, n_scen=1, stream=None):
+        """The pair evaluation restricted to blocks [blocks[0], blocks[1]) and vacuum nodes [vacuum[0], vacuum[1])
+        (one problem sharded over GPUs); n_jac_blocks_pair / n_vacuum_nodes give the totals."""
+        _check(self.L, self.L.gelato_eval_pair_packed_range_dev(self.h, x_ptr, g_ptr, packed_ptr, n_scen, blocks[0],
+                                                                blocks[1] - blocks[0], vacuum[0], vacuum[1] - vacuum[0], stream),
+               "gelato_eval_pair_packed_range_dev")
 
     def eval_pair_dev(self, x_ptr, g_ptr, vals_ptr, n_scen=1, stream=None):
         _check(self.L, self.L.gelato_eval_pair_dev(self.h, x_ptr, g_ptr, vals_ptr, n_scen, stream), "gelato_eval_pair_dev")

@@ -286,6 +286,16 @@ int gelato_eval_pair_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, d
                          void* stream);
 int gelato_eval_pair_packed_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
                                 void* stream);
+/* ONE problem sharded over GPUs: the pair evaluation restricted to blocks [block_first, block_first +
+ * block_count) of the plan's block table (gelato_plan_n_blocks(plan, 4) blocks: dynamics, aero rows, event rows,
+ * linear rows) and vacuum dynamics nodes [vac_first, vac_first + vac_count) (gelato_plan_n_blocks(plan, 5) nodes).
+ * Every packed slot and residual row is written by exactly one block or node: ranks with disjoint covering ranges
+ * fill disjoint parts of packed[] and g[] (gelato_b200/batch.py: ShardedProblem finds each rank's part once and
+ * gathers).  Device pointers, caller's stream, not synchronised. */
+int gelato_eval_pair_packed_range_dev(GelatoPlan* plan, const double* x_dev, double* g_dev, double* packed_dev, int32_t n_scen,
+                                      int32_t block_first, int32_t block_count, int32_t vac_first, int32_t vac_count,
+                                      void* stream);
+
 int gelato_eval_jacobian_dev(GelatoPlan* plan, const double* x_dev, double* vals_dev, int32_t n_scen, void* stream);
 /* packed_dev[n_scen][n_xdep] = the x-dependent slots of vals_dev[n_scen][n_vals], in ascending slot order */
 int gelato_pack_xdep_dev(GelatoPlan* plan, const double* vals_dev, double* packed_dev, int32_t n_scen, void* stream);

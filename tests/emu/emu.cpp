@@ -78,6 +78,7 @@ extern "C" int emu_eval_residuals(const GelatoPlanDesc* d, const GelatoScenarioD
 
 // packed: out_all is [n_scen][n_pack] and nothing is pre-filled;  g_all != NULL: pair evaluation -- objfunc's
 // rows come out of the Jacobian blocks (what gelato_eval_pair_* launches).
+static int g_range[4] = {0, -1, 0, 0}; /* block first / count (-1: all), vacuum first / count */
 static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,
                         double* out_all, int n_scen, const int32_t* ids, int packed) {
   if (validate_desc(d)) return -1;
@@ -104,8 +105,10 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
       const double* tmpl = (sc && sc->vals_template) ? sc->vals_template + (size_t)sid * P.n_vals : d->vals_template;
       memcpy(vals, tmpl, (size_t)P.n_vals * sizeof(double));
     }
-    const size_t nb = g ? jb.size() / BT_COLS : (size_t)h.n_jac_main;  /* the linear-row blocks: pair evaluations only */
-    for (size_t b = 0; b < nb; b++) {
+    const size_t nb_all = g ? jb.size() / BT_COLS : (size_t)h.n_jac_main;  /* the linear-row blocks: pair evaluations only */
+    const size_t b_lo = g_range[1] < 0 ? 0 : (size_t)g_range[0], nb = g_range[1] < 0 ? nb_all : (size_t)(g_range[0] + g_range[1]);
+    const int v_lo = g_range[1] < 0 ? 0 : g_range[2], v_hi = g_range[1] < 0 ? h.n_vac : g_range[2] + g_range[3];
+    for (size_t b = b_lo; b < nb; b++) {
       const int32_t* bt = jb.data() + b * BT_COLS;
       /* poison the scratch so a phase that reads what no thread wrote shows up as NaN */
       memset(&store, 0xff, sizeof store);
@@ -113,7 +116,7 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
         for (int tid = 0; tid < GJ_THREADS; tid++) jac_block_phase<JR_ALL>(P, sid, bt, x, vals, g, tid, phase, sm);
     }
     /* vacuum dynamics nodes: GV_PARTS threads each (kernel k_jacobian_noair), here part after part */
-    for (int k = 0; k < h.n_vac; k++) dyn_noair_node(P, sid, x, vals, g, jac_node(P, h.vac_first + k));
+    for (int k = v_lo; k < v_hi; k++) dyn_noair_node(P, sid, x, vals, g, jac_node(P, h.vac_first + k));
   }
   return 0;
 }
@@ -121,6 +124,21 @@ static int emu_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, c
 extern "C" int emu_eval_jacobian(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all,
                                  double* vals_all, int n_scen, const int32_t* ids) {
   return emu_jacobian(d, sc, x_all, nullptr, vals_all, n_scen, ids, 0);
+}
+
+// one problem sharded over ranks: the pair evaluation restricted to a block range and a vacuum-node range
+extern "C" int emu_eval_pair_range(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,
+                                   double* out_all, int n_scen, int b0, int nb, int v0, int nv) {
+  g_range[0] = b0; g_range[1] = nb; g_range[2] = v0; g_range[3] = nv;
+  const int rc = emu_jacobian(d, sc, x_all, g_all, out_all, n_scen, nullptr, 1);
+  g_range[1] = -1;
+  return rc;
+}
+extern "C" void emu_block_counts(const GelatoPlanDesc* d, int* n_blocks_pair, int* n_vac) {
+  HostTables h;
+  build_host_tables(d, h);
+  *n_blocks_pair = (int)(h.jac_blocks.size() / BT_COLS);
+  *n_vac = h.n_vac;
 }
 
 extern "C" int emu_eval_pair(const GelatoPlanDesc* d, const GelatoScenarioDesc* sc, const double* x_all, double* g_all,

@@ -104,6 +104,28 @@ class Emulator:
         return g.reshape(n_scen, -1), v.reshape(n_scen, -1)
 
 
+    # ---- one problem sharded over ranks (gelato_b200/batch.py: ShardedProblem) ----
+    def block_counts(self):
+        """(blocks of a pair evaluation, vacuum dynamics nodes): the two ranges a rank's share is cut from."""
+        nb, nv = ctypes.c_int(0), ctypes.c_int(0)
+        self.L.emu_block_counts.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        self.L.emu_block_counts(ctypes.byref(self.desc), ctypes.byref(nb), ctypes.byref(nv))
+        return nb.value, nv.value
+
+    def eval_pair_range(self, x, g, packed, blocks, vacuum):
+        """The packed pair evaluation restricted to blocks [b0, b1) and vacuum nodes [v0, v1), written into the
+        caller's g[n_rows] / packed[n_pack] (what gelato_eval_pair_packed_range_dev launches)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert g.dtype == np.float64 and g.flags.c_contiguous and g.size == self.plan.n_rows
+        assert packed.dtype == np.float64 and packed.flags.c_contiguous and packed.size == self.n_pack
+        self.L.emu_eval_pair_range.argtypes = [ctypes.POINTER(engine.PlanDesc), ctypes.POINTER(engine.ScenarioDesc), _pd, _pd, _pd,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        rc = self.L.emu_eval_pair_range(ctypes.byref(self.desc), self._sc(), x.ctypes.data_as(_pd), g.ctypes.data_as(_pd),
+                                        packed.ctypes.data_as(_pd), 1, blocks[0], blocks[1] - blocks[0], vacuum[0],
+                                        vacuum[1] - vacuum[0])
+        assert rc == 0
+
+
 class EmuEngine(Emulator):
     """The emulator behind the Engine interface GelatoProblem uses (CPU test tier only)."""
 

@@ -534,3 +534,41 @@ def test_fused_pair_callbacks_on_the_gpu():
     s, _ = prob.sens(helpers.perturbed(x0, seed=2))  # the pair's point, but the buffer has moved on: evaluates
     helpers.assert_sens_equal(O.sens(helpers.copy_x(helpers.perturbed(x0, seed=2)))[0], s)
     prob.close()
+
+
+@pytest.mark.parametrize("variant,factor", [("example", 4), ("three_stage", 2)])
+def test_block_ranges_of_one_problem_on_the_gpu(variant, factor):
+    """SURVEY.md 8(e)-2, one problem sharded over GPUs: gelato_eval_pair_packed_range_dev over disjoint covering
+    ranges of the block table and of the vacuum nodes writes every residual row and packed value exactly once and
+    reproduces gelato_eval_pair_packed bit for bit; batch.ShardedProblem on one rank is that evaluation."""
+    import torch
+
+    from gelato_b200 import batch
+
+    prob, O, x0 = _problem(variant, factor)
+    E = prob.engine
+    x = problem.xdict_to_vector(helpers.perturbed(x0))
+    g_want, pk_want = E.eval_pair_packed(x, 1)
+    ev = batch.EngineRangeEvaluator(E)
+    assert ev.n_blocks > 4
+    xd = torch.from_numpy(x).cuda()
+    for cuts in (1, 2, 5):
+        hits = torch.zeros(E.n_rows + E.n_pack, dtype=torch.int64, device="cuda")
+        out = torch.full((E.n_rows + E.n_pack,), float("nan"), dtype=torch.float64, device="cuda")
+        for r in range(cuts):
+            part = torch.full_like(out, float("nan"))
+            ev.pair_range(xd, part[: E.n_rows], part[E.n_rows:], batch.split_range(ev.n_blocks, cuts, r),
+                          batch.split_range(ev.n_vac, cuts, r))
+            m = ~torch.isnan(part)
+            hits += m
+            out[m] = part[m]
+        torch.cuda.synchronize()
+        assert bool((hits == 1).all())
+        assert np.array_equal(out[: E.n_rows].cpu().numpy(), g_want.ravel())
+        assert np.array_equal(out[E.n_rows:].cpu().numpy(), pk_want.ravel())
+    sp = batch.ShardedProblem(ev, x)
+    g, pk = sp.pair(x)
+    assert np.array_equal(g.cpu().numpy(), g_want.ravel()) and np.array_equal(pk.cpu().numpy(), pk_want.ravel())
+    with pytest.raises(engine.GelatoError):
+        E.eval_pair_packed_range_dev(xd.data_ptr(), out.data_ptr(), out.data_ptr(), (0, ev.n_blocks + 1), (0, 0))
+    prob.close()
