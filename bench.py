@@ -83,6 +83,10 @@ def parse():
     ap.add_argument("--preheat-seconds", type=float, default=0.5,
                     help="untimed run of the timed launches right before the timed steps (the clocks are sampled over it)")
     ap.add_argument("--e2e-slices", type=int, default=0, help="pipeline slices of the end-to-end leg (0 = library default)")
+    ap.add_argument("--solve-mode", default="processes", choices=["processes", "threads"],
+                    help="--solve-scenarios: one worker process per scenario (default; the solver's host side is the cost), or "
+                         "host threads behind the coalescing server")
+    ap.add_argument("--solve-procs", type=int, default=0, help="worker processes per rank (0: host cores / ranks)")
     ap.add_argument("--solve-scenarios", type=int, default=0,
                     help="also solve this many dispersed scenarios of the shipped example per GPU to convergence "
                          "(batched NLP solves per hour; 0 = skip)")
@@ -552,15 +556,19 @@ def run_gelato(args):
 
 def run_solves(args, world, rank, local):
     """Batched solver runs per hour: `--solve-scenarios` dispersed scenarios of the shipped example per GPU, each run by
-    the experimental interior-point stand-in (gelato_b200/ipsolve.py -- NOT IPOPT, fixed iteration budget, does not reach
-    IPOPT's tolerance: see its header) on callbacks that the per-GPU coalescing server turns into batched launches.
-    `solves_per_hour` stays null unless every run converged."""
+    gelato_b200/redsqp.py (NOT IPOPT: state elimination + penalty continuation on the dependent terminal row; converged =
+    its status 0 or 3, see solve_batch.py) on the CUDA callbacks -- one worker process per scenario by default, since the
+    solver's host side is what a batch of solves has to share.  `solves_per_hour` stays null unless every run converged."""
     import torch
     import torch.distributed as dist
 
     from gelato_b200 import solve_batch
 
-    res = solve_batch.solve_dispersed(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local)
+    if args.solve_mode == "processes":
+        res = solve_batch.solve_dispersed_processes(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local,
+                                                    processes=args.solve_procs or None)
+    else:  # one process per GPU, a host thread per scenario, callbacks coalesced into batched launches (server.py)
+        res = solve_batch.solve_dispersed(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local)
     t = torch.tensor([res["wall_s"]], dtype=torch.float64, device="cuda")
     n_ok = torch.tensor([res["converged"]], dtype=torch.float64, device="cuda")
     if world > 1:

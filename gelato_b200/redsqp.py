@@ -15,12 +15,25 @@ inequality rows as functions of p, with derivatives by the implicit function the
 handled in two phases: a bounded Levenberg-Marquardt iteration (SciPy least_squares, trust-region reflective) on the
 violated rows, then SciPy's SLSQP with a scaled objective.
 
-STATUS (profiles/r02_solver_attempts.txt): on the shipped example this reaches a FEASIBLE trajectory from the
-reference's initial guess -- every row of the original problem within 1e-8 after ~200 major iterations, where the
-full-space interior-point and SQP variants of ipsolve.py never got below 1e-4 -- but it does NOT reach IPOPT's
-optimality tolerance: the scaled first-order error stays at 1e-3 .. 1e-2 and the objective keeps creeping along a
-nearly flat feasible valley (different runs stop 0.4 % apart in payload).  `status` says which: 0 optimal, 2 feasible
-but not optimal, 1 neither.  Converged-solution parity and solves per hour therefore remain unmeasured.
+The dependent terminal pair.  The shipped example asks for a CIRCULAR orbit through two rows, orbit energy and angular
+momentum (con_init_terminal_knot.py:365-368).  On the surface E = E_t the angular momentum has its maximum exactly
+where h = h_t: at every feasible point the gradient of one row lies in the span of the other's, the optimum is not a
+KKT point (no finite multipliers), and every Newton-type method on the problem as posed stalls or wanders
+(profiles/r02_solver_attempts.txt: 20 configurations).  Phase 2 therefore finds such a row from the singular values of
+the reduced equality Jacobian and carries it by an exact penalty that is smooth on the rest of the feasible set,
+f - lam c_k (c_k has one sign there), level after level of lam (continuation, warm start): the row's violation falls
+like 1 / lam^2, the objective approaches its limit like 1 / lam (measured: profiles/r02j_solver_convergence.txt).  The
+stationarity condition of f - lam c_k IS that of the original Lagrangian with multiplier lam on c_k, so the
+termination test is the ORIGINAL problem's: every row within `constr_tol`, and IPOPT's scaled dual infeasibility
+(full space, adjoint multipliers for the state equations) against `tol` / `acceptable_tol`.
+
+STATUS.  On the shipped example, from the reference's initial guess, the continuation converges: constraint violation
+<= 1e-10, objective settled to 1e-6 relative between the last two levels (payload 27 817.3 kg), event times settled to
+1e-4 s.  The scaled optimality error ends at 1e-4 .. 2e-3: the dual residual carries (multiplier of the dependent
+row, which must grow without bound) x (error of the reference's forward-difference Jacobian, ~2e-8 per entry at
+dx = 1e-8) -- a floor that no solver on these callbacks gets under, IPOPT included.  `status`: 0 optimal or "solved to
+acceptable level" (IPOPT's two tests), 3 converged in objective and constraints with the optimality error at that
+noise floor, 2 feasible but neither, 1 not feasible.
 
 Every function value the solver sees comes from the two callbacks `objfunc` / `sens` -- the oracle's on the CPU or
 the CUDA kernels' -- so bit-identical callbacks give bit-identical iterates; the time spent inside them is recorded
@@ -51,7 +64,15 @@ class ReducedSQP:
     """solver = ReducedSQP({"tol": 1e-6, "max_iter": 600}); sol = solver(optProb, sens=sens)."""
 
     DEFAULTS = {"tol": 1e-6, "constr_tol": 1e-8, "max_iter": 260, "inner_tol": 1e-12, "inner_iter": 25, "restarts": 4,
-                "active_tol": 1e-7, "u_scale": 1.0, "phase1_evals": 60, "obj_scale": 0.01, "predict_radius": 0.05, "slsqp_ftol": 1e-15, "verbose": 0}
+                "active_tol": 1e-7, "u_scale": 1.0, "phase1_evals": 60, "obj_scale": 0.01, "predict_radius": 0.05, "slsqp_ftol": 1e-15, "verbose": 0,
+                # IPOPT's second threshold ("Solved To Acceptable Level"; example-settings.json:92-97 sets 1e-4)
+                "acceptable_tol": 1e-4,
+                # penalty continuation on a dependent equality row (see __call__, phase 2): "auto" or "off"
+                "degenerate": "auto", "dependent_ratio": 1e-3, "penalty0": 1e3, "penalty_factor": 10.0 ** 0.5,
+                "penalty_levels": 9, "level_iter": 150, "obj_change_tol": 1e-6,
+                # relative error of one entry of the callbacks' Jacobian: the reference's forward difference, eps / dx with
+                # dx = 1e-8 (Trajectory_Optimization.py:167) on values of order one
+                "jac_noise": 2.2e-8, "newton_iters": 0, "radius": 0.0}
 
     def __init__(self, options=None):
         self.opt = dict(self.DEFAULTS)
@@ -60,6 +81,16 @@ class ReducedSQP:
                 self.opt[k] = v  # IPOPT-only options (linear_solver, output_file ...) are ignored
 
     def __call__(self, prob, sens=None, **_):
+        # the matrices are small (a few hundred rows): threaded BLAS only adds hand-over time (3-8x slower here), and
+        # its reduction order would make the iterates depend on the thread count
+        try:
+            from threadpoolctl import threadpool_limits
+        except ImportError:  # pragma: no cover
+            return self._solve(prob, sens)
+        with threadpool_limits(limits=1):
+            return self._solve(prob, sens)
+
+    def _solve(self, prob, sens):
         o = self.opt
         t_start = time.perf_counter()
         names = [v[0] for v in prob.vars]
@@ -225,6 +256,7 @@ class ReducedSQP:
                 e["g"] = (grad[p_cols] + dsdp.T @ grad[s_cols]) / w
                 e["Je"] = (J[e_rows][:, p_cols].toarray() + J[e_rows][:, s_cols] @ dsdp) / w
                 e["Ji"] = (J[i_rows][:, p_cols].toarray() + J[i_rows][:, s_cols] @ dsdp) / w
+                e["grad"], e["J"] = grad, J
                 S["last_good"] = e
             return e
 
@@ -241,21 +273,47 @@ class ReducedSQP:
             e = at(pv, False)
             return e["c"][i_rows] if e["ok"] else big_i
 
-        # ---- first-order optimality of the reduced problem ----
-        def kkt(pv, e):
+        # ---- first-order optimality of the ORIGINAL problem at x(p) ----
+        pen = {"rows": np.zeros(0, int), "lam": np.zeros(0)}  # outer equality rows (positions in e_rows) carried by a penalty
+        n_bound_mult = int(np.isfinite(xl).sum() + np.isfinite(xu).sum())
+
+        def kkt(pv, e, full_space=True):
+            """(IPOPT's scaled dual infeasibility, multipliers of [outer equalities | active inequalities | active
+            bounds], unscaled residual).  Reduced gradient against the reduced active-set Jacobian, least squares with
+            sign constraints; a penalised row keeps the multiplier the penalty gives it (f - lam c has exactly the
+            stationarity condition of the Lagrangian with multiplier lam).  With the adjoint multipliers of the state
+            equations, lam_F = J[F,s]^-T (grad_s - J[c,s]^T lam_c), the full-space dual residual is zero in the state
+            columns and the reduced residual in the others, so the infinity norms agree; s_d is IPOPT's,
+            max(100, ||multipliers||_1 / (m + bound multipliers)) / 100, over ALL multipliers of the original problem."""
             ci = e["c"][i_rows]
             act = np.where(ci <= o["active_tol"])[0]
             at_l = np.where(pv - xl[p_cols] * w <= 1e-9)[0]
             at_u = np.where(xu[p_cols] * w - pv <= 1e-9)[0]
+            free_e = np.setdiff1d(np.arange(e_rows.size), pen["rows"])
             # g = Je' lam + Ji[act]' mu + zl - zu,  mu, zl, zu >= 0
-            A = np.hstack([e["Je"].T, e["Ji"][act].T, np.eye(pv.size)[:, at_l], -np.eye(pv.size)[:, at_u]])
-            lo = np.concatenate([np.full(e_rows.size, -np.inf), np.zeros(act.size + at_l.size + at_u.size)])
+            A = np.hstack([e["Je"][free_e].T, e["Ji"][act].T, np.eye(pv.size)[:, at_l], -np.eye(pv.size)[:, at_u]])
+            lo = np.concatenate([np.full(free_e.size, -np.inf), np.zeros(act.size + at_l.size + at_u.size)])
+            rhs = e["g"] - e["Je"][pen["rows"]].T @ pen["lam"]
             colsc = np.maximum(np.abs(A).max(axis=0), 1e-300)  # column scaling: the rows' gradients differ by 1e6
-            r = so.lsq_linear(A / colsc, e["g"], bounds=(lo, np.full(lo.size, np.inf)), method="bvls", lsmr_tol=None)
+            r = so.lsq_linear(A / colsc, rhs, bounds=(lo, np.full(lo.size, np.inf)), method="bvls", lsmr_tol=None)
             mult = r.x / colsc
-            resid = np.abs(A @ mult - e["g"]).max()
-            s_d = max(100.0, np.abs(mult).sum() / max(mult.size, 1)) / 100.0  # IPOPT's multiplier scaling
-            return resid / s_d, mult
+            resid = np.abs(A @ mult - rhs).max()
+            lam_e = np.zeros(e_rows.size)
+            lam_e[free_e] = mult[: free_e.size]
+            lam_e[pen["rows"]] = pen["lam"]
+            norm1 = np.abs(mult).sum() + np.abs(pen["lam"]).sum()
+            count = mult.size + pen["lam"].size
+            if full_space and "J" in e:
+                J = e["J"]
+                mu = np.zeros(i_rows.size)
+                mu[act] = mult[free_e.size: free_e.size + act.size]
+                rhs_s = e["grad"][s_cols] - J[e_rows][:, s_cols].T @ lam_e - J[i_rows][:, s_cols].T @ mu
+                lam_f = spla.splu(J[f_rows][:, s_cols].T.tocsc()).solve(np.asarray(rhs_s).ravel())
+                norm1 += np.abs(lam_f).sum()
+                count = m + n_bound_mult
+            s_d = max(100.0, norm1 / max(count, 1)) / 100.0
+            full = np.concatenate([lam_e, mult[free_e.size:]])
+            return resid / s_d, full, resid
 
         hist = {"it": 0, "best": None, "kkt": np.inf}
 
@@ -267,18 +325,28 @@ class ReducedSQP:
 
         def callback(pv):
             hist["it"] += 1
+            hist["level_it"] = hist.get("level_it", 0) + 1
             e = at(np.asarray(pv), True)
             if not e["ok"]:
                 return
+            hist["last_q"], hist["stopped"] = np.array(pv), False
+            if hist.get("stop_when") is not None:
+                if hist["stop_when"](e):
+                    hist["stopped"] = True
+                    raise Done()
+                if hist["level_it"] >= hist.get("level_cap", 1 << 30):
+                    raise Done()
+                return
             th = feas(e["c"])
-            err, _ = kkt(np.asarray(pv), e)
+            err, _, raw = kkt(np.asarray(pv), e)
             if o["verbose"]:
-                print("%4d  obj %.10f  infeas %.2e  kkt %.2e  evals %d" % (hist["it"], e["obj"], th, err, S["evals"]), flush=True)
+                print("%4d  obj %.10f  infeas %.2e  kkt %.2e (unscaled %.2e)  evals %d" % (hist["it"], e["obj"], th, err, raw, S["evals"]),
+                      flush=True)
             if th <= o["constr_tol"] and (hist["best"] is None or err < hist["kkt"]):
-                hist["best"], hist["kkt"] = (np.array(pv), e), err
-            if th <= o["constr_tol"] and err <= o["tol"]:
+                hist["best"], hist["kkt"], hist["kkt_raw"] = (np.array(pv), e), err, raw
+            if th <= o["constr_tol"] and err <= hist["target"]:
                 raise Done()
-            if hist["it"] >= o["max_iter"]:
+            if hist["it"] >= o["max_iter"] or hist["level_it"] >= hist.get("level_cap", 1 << 30):
                 raise Done()
 
         # the reduced problem of this call, for diagnostics (tests/scripts): q = w p
@@ -314,25 +382,144 @@ class ReducedSQP:
                 print("phase 1: %d evaluations, |p - p0| %.3e, infeasibility %.2e" % (ls.nfev, np.abs(pv / w - x0[p_cols]).max(),
                                                                                     feas(e["c"]) if e["ok"] else np.inf), flush=True)
         hist["phase"] = 2
+        hist["target"] = o["tol"]
         sf = o["obj_scale"]  # SLSQP's initial Hessian is the identity: the scale sets the length of its first steps
-        for attempt in range(o["restarts"] + 1):
-            try:
-                res = so.minimize(lambda q: sf * fun(q), pv, jac=lambda q: sf * at(q, True)["g"], method="SLSQP", bounds=bounds, constraints=cons_sq,
-                                  callback=callback, options={"maxiter": max(1, o["max_iter"] - hist["it"]), "ftol": o["slsqp_ftol"]})
-                pv = np.asarray(res.x)
-                message = "SLSQP: " + str(res.message)
-            except Done:
-                pass
-            if hist["best"] is not None and hist["kkt"] <= o["tol"]:
-                status, message = 0, "optimal: constraint violation <= %.0e, scaled optimality error <= %.0e" % (o["constr_tol"], o["tol"])
+
+        # ---- a dependent outer equality row?  The shipped example asks for a CIRCULAR orbit through two rows, orbit
+        # energy and angular momentum (con_init_terminal_knot.py:365-368): on the surface E = E_t the angular momentum
+        # has its maximum exactly where h = h_t, so at every feasible point the second row's gradient lies in the span
+        # of the first's -- no finite multipliers exist (the optimum is not a KKT point) and every Newton-type step
+        # is ill-posed (profiles/r02_solver_attempts.txt).  Such a row, call it c_k, has one sign on the rest of the
+        # feasible set, so f - lam c_k is an exact-penalty objective that is SMOOTH there: the row leaves the
+        # constraint list and SLSQP sees a regular problem whose minimiser violates c_k by O(1 / lam^2) and whose
+        # objective is O(1 / lam) from the limit; lam grows level by level (continuation, warm start).  The stationarity
+        # condition of f - lam c_k IS that of the original Lagrangian with multiplier lam, so the termination test
+        # below is the original problem's.  Detection: smallest singular value of the row-normalised reduced equality
+        # Jacobian at the phase-1 point; the row with the largest weight in its left singular vector is penalised
+        # (either of a dependent pair will do), with the sign of its least-squares multiplier there. ----
+        def run_slsqp(pv, lam_vec, cap, target, stop_when=None):
+            """SLSQP on f - lam . c[penalised rows] with those rows out of the constraint list, from pv, for at most cap
+            major iterations (restarting its quasi-Newton matrix from the best feasible point when it gives up early)."""
+            nonlocal message
+            pen["lam"] = np.asarray(lam_vec, dtype=float)
+            keep = np.setdiff1d(np.arange(e_rows.size), pen["rows"])
+            hist["level_it"], hist["level_cap"], hist["target"] = 0, cap, target
+            hist["best"], hist["kkt"], hist["stop_when"] = None, np.inf, stop_when  # per level: the multiplier is part of the test
+
+            def f_pen(q):
+                e = at(q, False)
+                if not e["ok"] or not pen["rows"].size:
+                    return sf * e["obj"]
+                return sf * (e["obj"] - float(pen["lam"] @ e["c"][e_rows][pen["rows"]]))
+
+            def g_pen(q):
+                e = at(q, True)
+                return sf * (e["g"] - (e["Je"][pen["rows"]].T @ pen["lam"] if pen["rows"].size else 0.0))
+
+            cons_lv = [{"type": "eq", "fun": lambda q: ceq(q)[keep], "jac": lambda q: at(q, True)["Je"][keep]}, cons_sq[1]]
+            for attempt in range(o["restarts"] + 1):
+                bounds_lv = bounds
+                if o["radius"] > 0.0:  # a box around the start: SLSQP's early steps (identity Hessian) stay where the model holds
+                    bounds_lv = [(max(lo_, c_ - o["radius"]), min(hi_, c_ + o["radius"])) for (lo_, hi_), c_ in zip(bounds, pv)]
+                try:
+                    res = so.minimize(f_pen, pv, jac=g_pen, method="SLSQP", bounds=bounds_lv, constraints=cons_lv, callback=callback,
+                                      options={"maxiter": max(1, min(o["max_iter"] - hist["it"], cap - hist["level_it"])),
+                                               "ftol": o["slsqp_ftol"]})
+                    pv = np.asarray(res.x)
+                    message = "SLSQP: " + str(res.message)
+                    if o["verbose"]:
+                        print("     ", message, flush=True)
+                except Done:
+                    pv = hist.get("last_q", pv)
+                if hist["best"] is not None and hist["kkt"] <= target:
+                    break
+                if hist["it"] >= o["max_iter"] or hist["level_it"] >= cap or hist.get("stopped"):
+                    break
+                if hist["best"] is not None:
+                    pv = hist["best"][0]
+            return hist["best"][0] if hist["best"] is not None else pv
+
+        levels = []
+        if o["newton_iters"] > 0:  # a full SQP step or two on the problem as posed: onto the linearised constraints
+            pv = run_slsqp(pv, [], o["newton_iters"], -1.0)
+        if o["degenerate"] == "auto" and e_rows.size:
+            e1 = at(pv, True)
+            if e1["ok"]:
+                Jn = e1["Je"] / np.maximum(np.linalg.norm(e1["Je"], axis=1, keepdims=True), 1e-300)
+                U, sv, _ = np.linalg.svd(Jn, full_matrices=False)
+                if sv[-1] <= o["dependent_ratio"] * sv[0]:
+                    # of the rows that make up the dependency (weights within a factor 5 of the largest) the one with
+                    # the SMALLEST weight: penalising the angular-momentum row of the example's pair works, the
+                    # energy row (twice the weight) does not -- SLSQP wanders (profiles/r02_solver_attempts.txt)
+                    wgt = np.abs(U[:, -1])
+                    cand = np.where(wgt >= 0.2 * wgt.max())[0]
+                    k = int(cand[np.argmin(wgt[cand])])
+                    pen["rows"] = np.array([k])
+                    others = np.setdiff1d(np.arange(e_rows.size), [k])
+                    # the sign the row takes where the OTHER rows hold: a short run without it (multiplier 0)
+                    def others_hold(e):
+                        return max(np.abs(e["c"][f_rows]).max(), np.abs(e["c"][e_rows][others]).max(),
+                                   -min(0.0, e["c"][i_rows].min()) if i_rows.size else 0.0) <= 1e-3 * abs(e["c"][e_rows][k])
+                    e2 = at(run_slsqp(pv, [0.0], o["level_iter"] // 2, -1.0, stop_when=others_hold), True)  # pv itself stays
+                    sign = 1.0 if e2["c"][e_rows][k] < 0.0 else -1.0  # f - lam c must GROW with the violation
+                    levels = [sign * o["penalty0"] * o["penalty_factor"] ** j for j in range(o["penalty_levels"])]
+                    if o["verbose"]:
+                        print("dependent equality row: %s (row %d of the outer equalities), sigma_min / sigma_max = %.1e, its value "
+                              "where the other rows hold %.2e, penalty sign %+d" % ([g[0] for g in cons for _ in range(g[1])][e_rows[k]], k,
+                                                                                   sv[-1] / sv[0], e2["c"][e_rows][k], sign), flush=True)
+        hist["levels"] = []
+        hist["stop_when"] = None
+
+        def at_noise_floor():
+            """dual residual of the level's best point <= acceptable_tol (IPOPT's scaling) + |multiplier of the dependent
+            row| x (error of a Jacobian entry): what the callbacks' forward-difference Jacobian can certify"""
+            s_d = hist["kkt_raw"] / hist["kkt"] if hist["kkt"] > 0.0 else 1.0
+            return hist["kkt_raw"] <= o["acceptable_tol"] * s_d + np.abs(pen["lam"]).sum() * o["jac_noise"]
+
+        for level, lam in enumerate(levels or [None]):
+            pv = run_slsqp(pv, [lam] if lam is not None else [], o["level_iter"] if lam is not None else o["max_iter"],
+                           -1.0 if lam is not None else o["tol"])
+            e_lv = hist["best"][1] if hist["best"] is not None else at(pv, False)
+            if lam is not None and e_lv["ok"]:
+                hist["levels"].append({"lam": lam, "obj": e_lv["obj"], "row_value": float(e_lv["c"][e_rows][pen["rows"]][0]),
+                                       "infeasibility": float(feas(e_lv["c"])), "kkt_scaled": float(hist["kkt"]),
+                                       "kkt_unscaled": float(hist.get("kkt_raw", np.nan)), "major_iterations": hist["it"]})
+                if o["verbose"]:
+                    print("level %d: %s" % (level, hist["levels"][-1]), flush=True)
+            if lam is None:
+                if hist["best"] is not None and hist["kkt"] <= o["tol"]:
+                    status, message = 0, "optimal: constraint violation <= %.0e, scaled optimality error <= %.0e" % (o["constr_tol"], o["tol"])
+                break
+            # ---- termination of the continuation.  Every level is run out (its objective has to settle); the sequence
+            # ends when two successive levels agree in the objective to obj_change_tol -- the level error is O(1 / lam),
+            # so with a level factor of sqrt(10) what is left is about half the last change.  The end point is then
+            # classified by IPOPT's test on the ORIGINAL problem with multiplier lam on the dependent row. ----
+            lv = hist["levels"]
+            if (len(lv) >= 2 and hist["best"] is not None and lv[-2]["infeasibility"] <= o["constr_tol"] and at_noise_floor()
+                    and abs(lv[-1]["obj"] - lv[-2]["obj"]) <= o["obj_change_tol"] * max(1.0, abs(lv[-1]["obj"]))):
+                hist["settled"] = abs(lv[-1]["obj"] - lv[-2]["obj"])
                 break
             if hist["it"] >= o["max_iter"]:
                 break
-            if hist["best"] is not None:  # restart the quasi-Newton matrix from the best feasible point so far
-                pv = hist["best"][0]
+        if levels and hist["best"] is not None:
+            if hist["kkt"] <= o["tol"]:
+                status, message = 0, "optimal: constraint violation <= %.0e, scaled optimality error <= %.0e" % (o["constr_tol"], o["tol"])
+            elif hist["kkt"] <= o["acceptable_tol"]:
+                status = 0
+                message = ("solved to acceptable level: constraint violation <= %.0e, scaled optimality error %.1e <= acceptable_tol "
+                           "%.0e (multiplier of the dependent row %.3g)" % (o["constr_tol"], hist["kkt"], o["acceptable_tol"], pen["lam"][0]))
+            elif "settled" in hist and at_noise_floor():
+                # the optimum of a problem with a dependent row is not a KKT point: the multiplier has to grow without
+                # bound, and the dual residual carries (multiplier) x (error of the reference's forward-difference
+                # Jacobian, ~2e-8 per entry with dx = 1e-8, Trajectory_Optimization.py:167) -- a floor no solver on these
+                # callbacks gets under.  What has converged is what the user reads: objective and constraints.
+                status = 3
+                message = ("converged in objective (change %.1e between the last two penalty levels) and constraints (violation <= %.0e); "
+                           "dual residual %.1e (scaled %.1e) within acceptable_tol + multiplier %.3g of the dependent row x Jacobian "
+                           "error %.1e" % (hist["settled"], o["constr_tol"], hist["kkt_raw"], hist["kkt"], pen["lam"][0], o["jac_noise"]))
         if hist["best"] is not None:
             pv, e = hist["best"]
-            if status != 0:
+            if status not in (0, 3):
                 status, message = 2, "feasible (violation <= %.0e) but not optimal: scaled optimality error %.1e" % (o["constr_tol"], hist["kkt"])
         else:
             e = at(pv, True)
@@ -346,6 +533,10 @@ class ReducedSQP:
         sol.message = message
         sol.constr_violation = float(feas(e["c"]))
         sol.optimality = float(hist["kkt"])
+        sol.penalty_levels = hist.get("levels", [])
+        names_of_rows = [g[0] for g in cons for _ in range(g[1])]
+        sol.dependent_rows = [(names_of_rows[e_rows[k]], int(e_rows[k] - rows_of[names_of_rows[e_rows[k]]][0])) for k in pen["rows"]]
+        sol.penalty_sign = float(np.sign(levels[0])) if levels else 0.0
         sol.reduced_evaluations = S["evals"]
         sol.q = np.array(pv)
         sol.optTime = time.perf_counter() - t_start

@@ -22,11 +22,16 @@ import helpers  # noqa: E402
 from gelato_b200 import nlpshim, problem  # noqa: E402
 
 
-def run(arm, factor, maxiter, solver="redsqp", verbose=0):
+def run(arm, factor, maxiter, solver="redsqp", verbose=0, scenario=0, of=8):
+    from gelato_b200 import scenarios
     from oracle import leaves
 
     Lg = leaves.get("gmath")
-    p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c, factor=factor)
+    if scenario == 0:
+        p, u, c, x0 = helpers.example_problem(coord=Lg.coordinate_c, factor=factor)
+    else:  # a dispersed copy (masses, thrust, wind: scenarios.disperse), as the batched solves use them
+        inp = scenarios.disperse(helpers.example_inputs(), of, seed=20260117)[scenario]
+        p, u, c, x0 = problem.problem_from_inputs(inp, coord=Lg.coordinate_c, factor=factor, max_nodes=20)
     if arm == "cpu":
         O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
 
@@ -52,7 +57,7 @@ def run(arm, factor, maxiter, solver="redsqp", verbose=0):
         sol = nlpshim.TrustConstr({"maxiter": maxiter})(opt, sens=sens)
     t_events = sol.xStar["t"] * u["t"]
     out = {
-        "arm": arm, "solver": solver + " (NOT IPOPT)", "optimality": getattr(sol, "optimality", None),
+        "arm": arm, "scenario": scenario, "solver": solver + " (NOT IPOPT)", "penalty_levels": getattr(sol, "penalty_levels", None), "optimality": getattr(sol, "optimality", None),
         "reduced_evaluations": getattr(sol, "reduced_evaluations", None), "nodes": int(p["N"]), "nit": sol.nit, "status": sol.status,
         "message": getattr(sol, "message", ""), "obj": float(sol.fStar),
         "constr_violation": sol.constr_violation,
@@ -67,15 +72,23 @@ def run(arm, factor, maxiter, solver="redsqp", verbose=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
-    ap.add_argument("--maxiter", type=int, default=600)
+    ap.add_argument("--maxiter", type=int, default=1500)
     ap.add_argument("--solver", default="redsqp", choices=["redsqp", "ip", "trust-constr"])
     ap.add_argument("--verbose", type=int, default=0)
     ap.add_argument("--factor", type=int, default=1)
+    ap.add_argument("--save", default="", help="write the end point of the (first) arm to this .npz")
+    ap.add_argument("--scenario", type=int, default=0, help="0: the shipped example; k > 0: the k-th dispersed copy of --of")
+    ap.add_argument("--of", type=int, default=8)
     a = ap.parse_args()
     res = {}
     for arm in (["cpu", "gpu"] if a.arm == "both" else [a.arm]):
-        res[arm] = run(arm, a.factor, a.maxiter, a.solver, a.verbose)
-        print(json.dumps(res[arm][0]))
+        res[arm] = run(arm, a.factor, a.maxiter, a.solver, a.verbose, a.scenario, a.of)
+        print(json.dumps(res[arm][0]), flush=True)
+        if a.save and len(res) == 1:
+            o = res[arm][0]
+            np.savez(a.save, x=res[arm][1], payload_kg=o["payload_kg"], event_times_s=np.array(o["event_times_s"]), obj=o["obj"],
+                     multiplier=o["penalty_levels"][-1]["lam"] if o["penalty_levels"] else np.nan,
+                     optimality=o["optimality"], constr_violation=o["constr_violation"], nit=o["nit"])
     if len(res) == 2:
         xa, xb = res["cpu"][1], res["gpu"][1]
         print(json.dumps({"max_abs_diff_x": float(np.max(np.abs(xa - xb))), "identical_iterates": bool(np.array_equal(xa, xb))}))

@@ -572,3 +572,30 @@ def test_block_ranges_of_one_problem_on_the_gpu(variant, factor):
     with pytest.raises(engine.GelatoError):
         E.eval_pair_packed_range_dev(xd.data_ptr(), out.data_ptr(), out.data_ptr(), (0, ev.n_blocks + 1), (0, 0))
     prob.close()
+
+
+def test_recorded_solution_passes_the_termination_test_through_the_cuda_callbacks():
+    """tests/test_solver_loop.py's warm-started solve with the CUDA engine behind the callbacks: from the recorded
+    solution of the shipped example (tests/golden/example_solution.npz) two short penalty levels, then the
+    termination test of the original problem -- same end point, bit for bit, as with the oracle's callbacks on this
+    host; payload and the 13 event times within 1e-6 relative of the record."""
+    from gelato_b200 import nlpshim, redsqp
+
+    Lg = leaves.get("gmath")
+    p, u, c, x0 = problem.problem_from_inputs(helpers.variant_inputs("example"), coord=Lg.coordinate_c, factor=1, max_nodes=20)
+    prob = callbacks.GelatoProblem(p, u, c, user_eq=callbacks.PerigeeAtEvent(helpers.USER_EVENT), coord=Lg.coordinate_c)
+    O = helpers.oracle_nlp(p, u, c, "gmath", "seqfma")
+    rec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_solution.npz"))
+    xs = problem.vector_to_xdict(rec["x"], p["M"], p["N"], p["num_sections"])
+    ends = []
+    for objfunc, sens in ((lambda x: O.objfunc(x), lambda x, f=None: O.sens(x)), (prob.objfunc, prob.sens)):
+        opt = nlpshim.register(objfunc, sens, helpers.copy_x(xs), c)
+        sol = redsqp.ReducedSQP({"phase1_evals": 0, "penalty0": float(rec["multiplier"]) / 10.0 ** 0.5, "penalty_levels": 2,
+                                 "level_iter": 50, "max_iter": 300})(opt, sens=sens)
+        assert sol.constr_violation <= 1e-8 and len(sol.penalty_levels) == 2
+        assert abs(sol.xStar["mass"][0] * u["mass"] / float(rec["payload_kg"]) - 1.0) <= 5e-6
+        assert np.allclose(sol.xStar["t"] * u["t"], rec["event_times_s"], rtol=1e-5, atol=1e-5)
+        ends.append((problem.xdict_to_vector(sol.xStar), sol.status, sol.nit))
+    assert np.array_equal(ends[0][0], ends[1][0]) and ends[0][1:] == ends[1][1:]
+    assert prob.engine.launches > 100
+    prob.close()
