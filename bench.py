@@ -87,9 +87,9 @@ def parse():
                     help="--solve-scenarios: one worker process per scenario (default; the solver's host side is the cost), or "
                          "host threads behind the coalescing server")
     ap.add_argument("--solve-procs", type=int, default=0, help="worker processes per rank (0: host cores / ranks)")
-    ap.add_argument("--solve-scenarios", type=int, default=0,
+    ap.add_argument("--solve-scenarios", type=int, default=4,
                     help="also solve this many dispersed scenarios of the shipped example per GPU to convergence "
-                         "(batched NLP solves per hour; 0 = skip)")
+                         "(batched NLP solves per hour, BASELINE.json metric iii; 0 = skip)")
     a = ap.parse_args()
     variant, factor, scen = WORKLOADS[a.workload]
     a.variant = variant
@@ -237,6 +237,44 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def _ref_solve_one(args):
+    """One dispersed scenario of the shipped example solved by gelato_b200/redsqp.py on the CPU ORACLE's callbacks (the
+    reference arm of the solves-per-hour figure: same solver, same problems as the GPU arm's solve leg)."""
+    n_total, k, flav, iters = args
+    from gelato_b200 import nlpshim, problem, redsqp, scenarios
+    from oracle import leaves, nlp, user_builtin
+
+    scen = scenarios.disperse(workload_inputs("example"), n_total, seed=20260117)
+    p, u, c, x0 = problem.problem_from_inputs(scen[k])
+    O = nlp.OracleNLP(p, u, c, flav, "numpy", user_eq=user_builtin.perigee_ratio_at(leaves.get(flav), USER_EVENT))
+    sens = lambda x, f=None: O.sens(x)  # noqa: E731
+    s = redsqp.ReducedSQP({"max_iter": iters})(nlpshim.register(lambda x: O.objfunc(x), sens, x0, c), sens=sens)
+    return {"status": int(s.status), "nit": int(s.nit), "payload_kg": float(s.xStar["mass"][0] * u["mass"]),
+            "optTime": float(s.optTime), "userObjTime": float(s.userObjTime), "userSensTime": float(s.userSensTime),
+            "constr_violation": float(s.constr_violation)}
+
+
+def reference_solves(args, world, flav):
+    """Solves per hour of the CPU arm: the scenarios the GPU arm's solve leg solves, on the oracle's callbacks, one
+    worker process per scenario over the host cores."""
+    import multiprocessing as mp
+
+    total = args.solve_scenarios * world
+    nw = max(1, min(total, os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(nw) as pool:
+        res = pool.map(_ref_solve_one, [(total, k, flav, 1500) for k in range(total)], chunksize=1)
+    wall = time.perf_counter() - t0
+    ok = sum(1 for r in res if r["status"] in (0, 3))
+    return {"solver": "gelato_b200/redsqp.py on the CPU oracle's callbacks (%s) -- NOT IPOPT" % CPU_DESC[flav],
+            "scenarios_total": total, "converged_total": ok, "worker_processes": nw, "wall_s": wall,
+            "runs_per_hour": total / wall * 3600.0, "solves_per_hour": (total / wall * 3600.0) if ok == total else None,
+            "statuses": [r["status"] for r in res], "major_iterations": [r["nit"] for r in res],
+            "payload_kg": [r["payload_kg"] for r in res], "optTime_mean_s": float(np.mean([r["optTime"] for r in res])),
+            "userObjTime_mean_s": float(np.mean([r["userObjTime"] for r in res])),
+            "userSensTime_mean_s": float(np.mean([r["userSensTime"] for r in res]))}
+
+
 def cpu_flavour():
     """Physics leaves of the CPU arm: the reference's own C++ (oracle/_ref, built where the
     reference tree is mounted and shipped with the snapshot) when present, else the
@@ -313,7 +351,14 @@ def run_reference(args):
               "host core; every problem set up once, before the warm-up), %s"
               % (n_step, "" if n_step == args.scenarios * world else " (of the %d of a step of the GPU arm)" % (args.scenarios * world),
                  nw, CPU_DESC[flav]))
+    solves = None
+    if args.solve_scenarios > 0:
+        try:
+            solves = reference_solves(args, world, flav)
+        except Exception as exc:
+            solves = {"error": "%s: %s" % (type(exc).__name__, exc), "solves_per_hour": None}
     print(json.dumps({
+        "solves": solves, "solves_per_hour": solves.get("solves_per_hour") if solves else None,
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -547,6 +592,7 @@ def run_gelato(args):
         sol = run_solves(args, world, rank, local)
         if rank == 0:
             line["solves"] = sol
+            line["solves_per_hour"] = sol.get("solves_per_hour")
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -564,11 +610,14 @@ def run_solves(args, world, rank, local):
 
     from gelato_b200 import solve_batch
 
-    if args.solve_mode == "processes":
-        res = solve_batch.solve_dispersed_processes(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local,
-                                                    processes=args.solve_procs or None)
-    else:  # one process per GPU, a host thread per scenario, callbacks coalesced into batched launches (server.py)
-        res = solve_batch.solve_dispersed(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local)
+    try:
+        if args.solve_mode == "processes":
+            res = solve_batch.solve_dispersed_processes(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local,
+                                                        processes=args.solve_procs or None)
+        else:  # one process per GPU, a host thread per scenario, callbacks coalesced into batched launches (server.py)
+            res = solve_batch.solve_dispersed(workload_inputs("example"), args.solve_scenarios * world, world, rank, device=local)
+    except Exception as exc:  # the collectives below still have to be entered by every rank
+        res = {"error": "%s: %s" % (type(exc).__name__, exc), "wall_s": float("inf"), "converged": 0}
     t = torch.tensor([res["wall_s"]], dtype=torch.float64, device="cuda")
     n_ok = torch.tensor([res["converged"]], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -68,11 +68,14 @@ class ReducedSQP:
                 # IPOPT's second threshold ("Solved To Acceptable Level"; example-settings.json:92-97 sets 1e-4)
                 "acceptable_tol": 1e-4,
                 # penalty continuation on a dependent equality row (see __call__, phase 2): "auto" or "off"
-                "degenerate": "auto", "dependent_ratio": 1e-3, "penalty0": 1e3, "penalty_factor": 10.0 ** 0.5,
+                "degenerate": "auto", "dependent_ratio": 1e-2, "dependent_gap": 0.05, "detect_chunks": 4, "detect_iter": 25, "penalty0": 1e3, "penalty_factor": 10.0 ** 0.5,
                 "penalty_levels": 9, "level_iter": 150, "obj_change_tol": 1e-6,
                 # relative error of one entry of the callbacks' Jacobian: the reference's forward difference, eps / dx with
                 # dx = 1e-8 (Trajectory_Optimization.py:167) on values of order one
-                "jac_noise": 2.2e-8, "newton_iters": 0, "radius": 0.0}
+                "jac_noise": 2.2e-8, "newton_iters": 0, "radius": 0.0,
+                # the first penalty level starts inside a box around the phase-1 point, recentred a few times: SLSQP's first
+                # steps (identity Hessian) otherwise leave the region where the linearisations hold on some scenarios
+                "start_radius": 0.0, "start_segments": 4, "start_iter": 25}
 
     def __init__(self, options=None):
         self.opt = dict(self.DEFAULTS)
@@ -365,7 +368,9 @@ class ReducedSQP:
         if o["phase1_evals"] > 0:
             def resid(q):
                 e = at(q, False)
-                if not e["ok"]:
+                if not e["ok"] or not e["converged"]:
+                    # no trajectory for these parameters (the state equations did not converge): a step too long --
+                    # the trust region has to shrink, not move on with the last Newton iterate
                     return np.full(e_rows.size + i_rows.size, 1e3)
                 return np.concatenate([e["c"][e_rows], np.minimum(e["c"][i_rows], 0.0)])
 
@@ -442,18 +447,37 @@ class ReducedSQP:
         levels = []
         if o["newton_iters"] > 0:  # a full SQP step or two on the problem as posed: onto the linearised constraints
             pv = run_slsqp(pv, [], o["newton_iters"], -1.0)
+        def dependent_row(e1):
+            """None, or the position (in e_rows) of an outer equality row to carry by a penalty: the reduced equality
+            Jacobian, rows normalised, has ONE singular value far below the rest (<= dependent_ratio of the largest and
+            <= dependent_gap of the next one).  Of the rows that make up the dependency (weights within a factor 5 of the
+            largest in the left singular vector) the one with the SMALLEST gradient: the angular-momentum row of the
+            example's pair (d(E / E_t) = -2 d(h / h_t), half the energy row's gradient).  Penalising that one works;
+            with the energy row SLSQP wanders (measured, profiles/r02j_solver_convergence.txt)."""
+            norms = np.maximum(np.linalg.norm(e1["Je"], axis=1), 1e-300)
+            U, sv, _ = np.linalg.svd(e1["Je"] / norms[:, None], full_matrices=False)
+            hist["sv"] = (sv[-1] / sv[0], sv[-1] / sv[-2] if sv.size > 1 else 0.0)
+            if sv[-1] > o["dependent_ratio"] * sv[0] or (sv.size > 1 and sv[-1] > o["dependent_gap"] * sv[-2]):
+                return None
+            wgt = np.abs(U[:, -1])
+            cand = np.where(wgt >= 0.2 * wgt.max())[0]
+            return int(cand[np.argmin(norms[cand])])
+
         if o["degenerate"] == "auto" and e_rows.size:
             e1 = at(pv, True)
-            if e1["ok"]:
-                Jn = e1["Je"] / np.maximum(np.linalg.norm(e1["Je"], axis=1, keepdims=True), 1e-300)
-                U, sv, _ = np.linalg.svd(Jn, full_matrices=False)
-                if sv[-1] <= o["dependent_ratio"] * sv[0]:
-                    # of the rows that make up the dependency (weights within a factor 5 of the largest) the one with
-                    # the SMALLEST weight: penalising the angular-momentum row of the example's pair works, the
-                    # energy row (twice the weight) does not -- SLSQP wanders (profiles/r02_solver_attempts.txt)
-                    wgt = np.abs(U[:, -1])
-                    cand = np.where(wgt >= 0.2 * wgt.max())[0]
-                    k = int(cand[np.argmin(wgt[cand])])
+            k = dependent_row(e1) if e1["ok"] else None
+            pv1 = pv
+            for chunk in range(o["detect_chunks"] if k is None else 0):
+                # not visible from here: a few iterations on the problem as posed, towards the feasible set, and look again
+                pv = run_slsqp(pv, [], o["detect_iter"], -1.0)
+                e1 = at(pv, True)
+                k = dependent_row(e1) if e1["ok"] else None
+                if k is not None or hist["it"] >= o["max_iter"]:
+                    break
+            if True:
+                if k is not None:
+                    pv = pv1  # the continuation starts from the phase-1 point
+                    sv = hist["sv"]
                     pen["rows"] = np.array([k])
                     others = np.setdiff1d(np.arange(e_rows.size), [k])
                     # the sign the row takes where the OTHER rows hold: a short run without it (multiplier 0)
@@ -466,7 +490,7 @@ class ReducedSQP:
                     if o["verbose"]:
                         print("dependent equality row: %s (row %d of the outer equalities), sigma_min / sigma_max = %.1e, its value "
                               "where the other rows hold %.2e, penalty sign %+d" % ([g[0] for g in cons for _ in range(g[1])][e_rows[k]], k,
-                                                                                   sv[-1] / sv[0], e2["c"][e_rows][k], sign), flush=True)
+                                                                                   sv[0], e2["c"][e_rows][k], sign), flush=True)
         hist["levels"] = []
         hist["stop_when"] = None
 
@@ -476,6 +500,13 @@ class ReducedSQP:
             s_d = hist["kkt_raw"] / hist["kkt"] if hist["kkt"] > 0.0 else 1.0
             return hist["kkt_raw"] <= o["acceptable_tol"] * s_d + np.abs(pen["lam"]).sum() * o["jac_noise"]
 
+        if levels and o["start_radius"] > 0.0:
+            for seg in range(o["start_segments"]):
+                o["radius"] = o["start_radius"]
+                try:
+                    pv = run_slsqp(pv, [levels[0]], o["start_iter"], -1.0)
+                finally:
+                    o["radius"] = 0.0
         for level, lam in enumerate(levels or [None]):
             pv = run_slsqp(pv, [lam] if lam is not None else [], o["level_iter"] if lam is not None else o["max_iter"],
                            -1.0 if lam is not None else o["tol"])

@@ -50,7 +50,8 @@ def run(arm, factor, maxiter, solver="redsqp", verbose=0, scenario=0, of=8):
     opt = nlpshim.attach_structure(nlpshim.register(objfunc, sens, helpers.copy_x(x0), c), p)
     if solver == "redsqp":
         from gelato_b200 import redsqp
-        sol = redsqp.ReducedSQP({"max_iter": maxiter, "verbose": verbose})(opt, sens=sens)
+        extra = json.loads(os.environ.get("REDSQP_OPTIONS", "{}"))  # experiments: {"start_radius": 0.1} ...
+        sol = redsqp.ReducedSQP(dict({"max_iter": maxiter, "verbose": verbose}, **extra))(opt, sens=sens)
     elif solver == "ip":
         sol = ipsolve.IPSolver({"max_iter": maxiter})(opt, sens=sens)
     else:

@@ -12,7 +12,7 @@ cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 [ "$1" = "quick" ] && exit 0
 timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 cat gpurun_out/bench_ref.json
-NCU_BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sustained-seconds 0.01 --preheat-seconds 0.01"
+NCU_BENCH="python bench.py --steps 3 --warmup 3 --solve-scenarios 0 --no-cpu-baseline --sustained-seconds 0.01 --preheat-seconds 0.01"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
   $NCU_BENCH > gpurun_out/ncu_launches.log 2>&1; echo "ncu list rc=$?"
 for k in k_jacobian k_jacobian_noair k_residuals; do
