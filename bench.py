@@ -263,12 +263,12 @@ def reference_solves(args, world, flav):
     nw = max(1, min(total, os.cpu_count() or 1))
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(nw) as pool:
-        res = pool.map(_ref_solve_one, [(total, k, flav, 1500) for k in range(total)], chunksize=1)
+        res = pool.map(_ref_solve_one, [(total, k, flav, 1800) for k in range(total)], chunksize=1)
     wall = time.perf_counter() - t0
     ok = sum(1 for r in res if r["status"] in (0, 3))
     return {"solver": "gelato_b200/redsqp.py on the CPU oracle's callbacks (%s) -- NOT IPOPT" % CPU_DESC[flav],
             "scenarios_total": total, "converged_total": ok, "worker_processes": nw, "wall_s": wall,
-            "runs_per_hour": total / wall * 3600.0, "solves_per_hour": (total / wall * 3600.0) if ok == total else None,
+            "runs_per_hour": total / wall * 3600.0, "solves_per_hour": ok / wall * 3600.0,
             "statuses": [r["status"] for r in res], "major_iterations": [r["nit"] for r in res],
             "payload_kg": [r["payload_kg"] for r in res], "optTime_mean_s": float(np.mean([r["optTime"] for r in res])),
             "userObjTime_mean_s": float(np.mean([r["userObjTime"] for r in res])),
@@ -627,7 +627,9 @@ def run_solves(args, world, rank, local):
     total = args.solve_scenarios * world
     res.update({"scenarios_total": total, "converged_total": int(n_ok.item()), "wall_s_max_over_ranks": wall,
                 "runs_per_hour": total / wall * 3600.0,
-                "solves_per_hour": (total / wall * 3600.0) if int(n_ok.item()) == total else None})
+                "solves_per_hour": int(n_ok.item()) / wall * 3600.0 if wall > 0 and wall != float("inf") else None,
+                "solves_per_hour_note": "CONVERGED solves (status 0 or 3) of all ranks / wall time (max over ranks); runs that did not "
+                                        "converge cost time and count nothing"})
     return res
 
 

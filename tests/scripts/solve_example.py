@@ -73,7 +73,7 @@ def run(arm, factor, maxiter, solver="redsqp", verbose=0, scenario=0, of=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
-    ap.add_argument("--maxiter", type=int, default=1500)
+    ap.add_argument("--maxiter", type=int, default=1800)
     ap.add_argument("--solver", default="redsqp", choices=["redsqp", "ip", "trust-constr"])
     ap.add_argument("--verbose", type=int, default=0)
     ap.add_argument("--factor", type=int, default=1)

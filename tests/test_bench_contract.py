@@ -12,7 +12,7 @@ def _run(extra, env=None):
     e = dict(os.environ)
     e.update(env or {})
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
-                          "--warmup", "1", "--factor", "1", "--scenarios", "3"] + extra, cwd=ROOT, env=e, capture_output=True,
+                          "--warmup", "1", "--factor", "1", "--scenarios", "3", "--solve-scenarios", "0"] + extra, cwd=ROOT, env=e, capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip().splitlines()
@@ -29,6 +29,7 @@ def test_reference_arm_prints_the_contract_line():
     assert b["config"]["scenarios_per_gpu"] == 3
     assert b["value"] > 0 and b["ms_per_step"] > 0 and b["vs_baseline"] is None and b["gpu_launches"] == 0
     assert "workload" in b["config"] and "model" not in b["config"]
+    assert b["solves"] is None and b["solves_per_hour"] is None  # the solve leg (minutes of CPU work) is switched off here
     cb = b["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == b["value"] and cb["sample"]
     assert b["e2e"] == {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
