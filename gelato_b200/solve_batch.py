@@ -61,7 +61,8 @@ def solve_dispersed_processes(inputs, n_total, world, rank, device=0, iters=1800
     return {
         "solver": "gelato_b200/redsqp.py (state elimination + penalty continuation on the dependent terminal row) -- NOT IPOPT; "
                   "converged = status 0 (IPOPT's tol / acceptable_tol test) or 3 (every row within 1e-8, objective settled to 1e-6 "
-                  "between the last two penalty levels, dual residual within acceptable_tol + multiplier x Jacobian error)",
+                  "between the last two penalty levels, IPOPT's scaled optimality error <= 5e-3: the noise floor of the "
+                  "forward-difference Jacobian, above acceptable_tol)",
         "mode": "one worker process per scenario, %d at a time, each with its own engine on the rank's GPU" % processes,
         "scenarios": n, "converged": converged, "wall_s": wall, "worker_processes": processes,
         "runs_per_hour": n / wall * 3600.0, "solves_per_hour": converged / wall * 3600.0,
