@@ -341,6 +341,10 @@ class ReducedSQP:
                     raise Done()
                 return
             th = feas(e["c"])
+            if th > o["constr_tol"] and not o["verbose"]:  # the optimality test is only read at feasible iterates
+                if hist["it"] >= o["max_iter"] or hist["level_it"] >= hist.get("level_cap", 1 << 30):
+                    raise Done()
+                return
             err, _, raw = kkt(np.asarray(pv), e)
             if o["verbose"]:
                 print("%4d  obj %.10f  infeas %.2e  kkt %.2e (unscaled %.2e)  evals %d" % (hist["it"], e["obj"], th, err, raw, S["evals"]),
@@ -474,23 +478,22 @@ class ReducedSQP:
                 k = dependent_row(e1) if e1["ok"] else None
                 if k is not None or hist["it"] >= o["max_iter"]:
                     break
-            if True:
-                if k is not None:
-                    pv = pv1  # the continuation starts from the phase-1 point
-                    sv = hist["sv"]
-                    pen["rows"] = np.array([k])
-                    others = np.setdiff1d(np.arange(e_rows.size), [k])
-                    # the sign the row takes where the OTHER rows hold: a short run without it (multiplier 0)
-                    def others_hold(e):
-                        return max(np.abs(e["c"][f_rows]).max(), np.abs(e["c"][e_rows][others]).max(),
-                                   -min(0.0, e["c"][i_rows].min()) if i_rows.size else 0.0) <= 1e-3 * abs(e["c"][e_rows][k])
-                    e2 = at(run_slsqp(pv, [0.0], o["level_iter"] // 2, -1.0, stop_when=others_hold), True)  # pv itself stays
-                    sign = 1.0 if e2["c"][e_rows][k] < 0.0 else -1.0  # f - lam c must GROW with the violation
-                    levels = [sign * o["penalty0"] * o["penalty_factor"] ** j for j in range(o["penalty_levels"])]
-                    if o["verbose"]:
-                        print("dependent equality row: %s (row %d of the outer equalities), sigma_min / sigma_max = %.1e, its value "
-                              "where the other rows hold %.2e, penalty sign %+d" % ([g[0] for g in cons for _ in range(g[1])][e_rows[k]], k,
-                                                                                   sv[0], e2["c"][e_rows][k], sign), flush=True)
+            if k is not None:
+                pv = pv1  # the continuation starts from the phase-1 point
+                sv = hist["sv"]
+                pen["rows"] = np.array([k])
+                others = np.setdiff1d(np.arange(e_rows.size), [k])
+                # the sign the row takes where the OTHER rows hold: a short run without it (multiplier 0)
+                def others_hold(e):
+                    return max(np.abs(e["c"][f_rows]).max(), np.abs(e["c"][e_rows][others]).max(),
+                               -min(0.0, e["c"][i_rows].min()) if i_rows.size else 0.0) <= 1e-3 * abs(e["c"][e_rows][k])
+                e2 = at(run_slsqp(pv, [0.0], o["level_iter"] // 2, -1.0, stop_when=others_hold), True)  # pv itself stays
+                sign = 1.0 if e2["c"][e_rows][k] < 0.0 else -1.0  # f - lam c must GROW with the violation
+                levels = [sign * o["penalty0"] * o["penalty_factor"] ** j for j in range(o["penalty_levels"])]
+                if o["verbose"]:
+                    print("dependent equality row: %s (row %d of the outer equalities), sigma_min / sigma_max = %.1e, its value "
+                          "where the other rows hold %.2e, penalty sign %+d" % ([g[0] for g in cons for _ in range(g[1])][e_rows[k]], k,
+                                                                               sv[0], e2["c"][e_rows][k], sign), flush=True)
         hist["levels"] = []
         hist["stop_when"] = None
 
