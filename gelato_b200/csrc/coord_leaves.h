@@ -7,8 +7,8 @@
  * (oracle/oracle_leaves.cpp), built from the device functions the kernels use.  host+device: tests/emu steps it.
  *
  * Item layout: a[GC_IN] and b[GC_IN] input vectors (unused entries ignored), t one scalar, out[GC_OUT].
- * Not offered: dcm_from_quat, quat_from_dcm, euler_from_dcm, dcm_from_thrustvector, laplace_vector (no call site in
- * the reference's live code) and haversine. */
+ * Not offered: dcm_from_quat, quat_from_dcm, euler_from_dcm, dcm_from_thrustvector (3 x 3 matrices, no call site in
+ * the reference's live code). */
 #ifndef GELATO_B200_COORD_LEAVES_H_
 #define GELATO_B200_COORD_LEAVES_H_
 
@@ -28,7 +28,7 @@ P_HD int coord_leaf_n_out(int fn) {
       return 4;
     case GC_ORBITAL_ELEMENTS: return 6;
     case GC_DISTANCE_VINCENTY: case GC_ANGMOM: case GC_INCLINATION_RAD: case GC_INCLINATION_COS: case GC_ORBIT_ENERGY:
-    case GC_ANGMOM_FROM_ALT: case GC_ENERGY_FROM_ALT:
+    case GC_ANGMOM_FROM_ALT: case GC_ENERGY_FROM_ALT: case GC_HAVERSINE:
       return 1;
     default: return 3;
   }
@@ -128,6 +128,19 @@ P_HD void coord_leaf(int fn, const double* a, const double* b, double t, double*
     case GC_ENERGY_FROM_ALT: {
       const double ra = P_RA + a[0], rp = P_RA + a[1];
       out[0] = -P_MU / 2.0 / ((ra + rp) / 2.0);
+      return;
+    }
+    case GC_LAPLACE_VECTOR: { /* wrapper_coordinate.hpp:238-244: v x h - mu r / |r| */
+      const Vec3 h = cross3(a3, b3), vh = cross3(b3, h);
+      const double rn = norm3(a3);
+      r3 = v3(vh.x - P_MU * a3.x / rn, vh.y - P_MU * a3.y / rn, vh.z - P_MU * a3.z / rn);
+      break;
+    }
+    case GC_HAVERSINE: { /* wrapper_utils.hpp:37-49: degrees in, radius t */
+      const double lon1 = a[0] * P_PI / 180.0, lat1 = a[1] * P_PI / 180.0, lon2 = a[2] * P_PI / 180.0, lat2 = a[3] * P_PI / 180.0;
+      const double dlon = lon2 - lon1, dlat = lat2 - lat1;
+      const double h = gm_pow(gm_sin(dlat / 2), 2.0) + gm_cos(lat1) * gm_cos(lat2) * gm_pow(gm_sin(dlon / 2), 2.0);
+      out[0] = 2 * t * gm_asin(gm_sqrt(h));
       return;
     }
     default: return;

@@ -32,13 +32,13 @@ _CODES = {name: k for k, name in enumerate(
     "quatmult conj normalize3 normalize4 quatrot ecef2geodetic geodetic2ecef ecef2eci eci2ecef vel_ecef2eci vel_eci2ecef "
     "quat_eci2ecef quat_ecef2eci quat_ecef2nedg quat_nedg2ecef quat_eci2nedg quat_nedg2eci quat_from_euler euler_from_quat "
     "quat_nedg2body orbital_elements distance_vincenty angular_momentum_vec angular_momentum inclination_rad "
-    "inclination_cosine orbit_energy angular_momentum_from_altitude orbit_energy_from_altitude".split())}
+    "inclination_cosine orbit_energy angular_momentum_from_altitude orbit_energy_from_altitude laplace_vector haversine".split())}
 _N_OUT = {"orbital_elements": 6}
 for _n in ("quatmult conj normalize4 quat_eci2ecef quat_ecef2eci quat_ecef2nedg quat_nedg2ecef quat_eci2nedg quat_nedg2eci "
            "quat_from_euler quat_nedg2body").split():
     _N_OUT[_n] = 4
 for _n in ("distance_vincenty angular_momentum inclination_rad inclination_cosine orbit_energy "
-           "angular_momentum_from_altitude orbit_energy_from_altitude").split():
+           "angular_momentum_from_altitude orbit_energy_from_altitude haversine").split():
     _N_OUT[_n] = 1
 
 
@@ -195,3 +195,15 @@ def angular_momentum_from_altitude(ha, hp, fn=None):
 
 def orbit_energy_from_altitude(ha, hp, fn=None):
     return _leaf("orbit_energy_from_altitude", np.stack(np.broadcast_arrays(ha, hp), axis=-1), 2, fn=fn)
+
+
+def laplace_vector(pos_eci, vel_eci, fn=None):
+    """v x h - mu r / |r| (wrapper_coordinate.hpp:238-244)"""
+    return _leaf("laplace_vector", pos_eci, 3, vel_eci, 3, fn=fn)
+
+
+def _haversine(lon1, lat1, lon2, lat2, r, fn=None):
+    """utils_c.haversine (wrapper_utils.hpp:37-49; exported by lib/utils_c.py): great-circle distance on a sphere of radius
+    r, degrees in.  It shares the batch entry point of this module's functions."""
+    a = np.stack(np.broadcast_arrays(arr(lon1), arr(lat1), arr(lon2), arr(lat2)), axis=-1)
+    return _leaf("haversine", a, 4, t=r, fn=fn)

@@ -65,3 +65,10 @@ def wind_ned(altitude_m, wind):
     out = np.empty((alt.size, 3))
     call("gelato_leaf_aero", 4, alt.size, ptr(None), ptr(None), ptr(None), ptr(alt), ptr(w), w.shape[0], ptr(out))
     return out[0] if np.ndim(altitude_m) == 0 else out
+
+
+def haversine(lon1, lat1, lon2, lat2, r, fn=None):
+    """Great-circle distance on a sphere of radius r, angles in degrees (pybind_utils.cpp:29, wrapper_utils.hpp:37-49)."""
+    from .coordinate_c import _haversine
+
+    return _haversine(lon1, lat1, lon2, lat2, r, fn=fn)

@@ -88,6 +88,8 @@ class OracleLeaves:
             getattr(L, name).argtypes = [_D, _D]
         L.o_distance_vincenty.restype = _D
         L.o_distance_vincenty.argtypes = [_D, _D, _D, _D]
+        L.o_haversine.restype = _D
+        L.o_haversine.argtypes = [_D, _D, _D, _D, _D]
         L.o_interp.restype = _D
         L.o_interp.argtypes = [_D, _P, _P, _I]
         assert L.oracle_flavour() == {"libm": 0, "gmath": 1, "ref": 2}[flavour]
@@ -155,6 +157,7 @@ class OracleLeaves:
             inclination_rad=lambda p, v: L.o_inclination_rad(_p(v3(p)), _p(v3(v))),
             inclination_cosine=lambda p, v: L.o_inclination_cosine(_p(v3(p)), _p(v3(v))),
             orbit_energy=lambda p, v: L.o_orbit_energy(_p(v3(p)), _p(v3(v))),
+            laplace_vector=lambda p, v: self._v(L.o_laplace_vector, 3, _p(v3(p)), _p(v3(v))),
             angular_momentum_from_altitude=lambda ha, hp: L.o_angular_momentum_from_altitude(_D(ha), _D(hp)),
             orbit_energy_from_altitude=lambda ha, hp: L.o_orbit_energy_from_altitude(_D(ha), _D(hp)),
         )
@@ -203,6 +206,7 @@ class OracleLeaves:
             angle_of_attack_ab_rad=aoa_ab,
             interp=interp,
             wind_ned=wind_ned,
+            haversine=lambda lon1, lat1, lon2, lat2, r: L.o_haversine(_D(lon1), _D(lat1), _D(lon2), _D(lat2), _D(r)),
             angle_of_attack_all_array_rad=aoa_arr,
             dynamic_pressure_array_pa=q_arr,
             q_alpha_array_pa_rad=qa_arr,

@@ -641,6 +641,23 @@ double o_orbit_energy(const double* p, const double* v) {  // :246-250
   double vv = norm3(ld3(v));
   return 0.5 * vv * vv - E_mu / r;
 }
+void o_laplace_vector(const double* p, const double* v, double* out) {  // wrapper_coordinate.hpp:238-244
+  V3 r = ld3(p), vel = ld3(v);
+  V3 vh = cross3(vel, cross3(r, vel));
+  double rn = norm3(r);
+  V3 e;
+  for (int i = 0; i < 3; i++) e[i] = vh[i] - E_mu * r[i] / rn;
+  st3(out, e);
+}
+double o_haversine(double lon1, double lat1, double lon2, double lat2, double r) {  // wrapper_utils.hpp:37-49
+  lon1 = lon1 * M_PI / 180.0;
+  lat1 = lat1 * M_PI / 180.0;
+  lon2 = lon2 * M_PI / 180.0;
+  lat2 = lat2 * M_PI / 180.0;
+  double dlon = lon2 - lon1, dlat = lat2 - lat1;
+  double a = O_POW(O_SIN(dlat / 2), 2.0) + O_COS(lat1) * O_COS(lat2) * O_POW(O_SIN(dlon / 2), 2.0);
+  return 2 * r * O_ASIN(O_SQRT(a));
+}
 double o_angular_momentum_from_altitude(double ha, double hp) {  // :252-258
   double ra = E_Ra + ha, rp = E_Ra + hp;
   double a = (ra + rp) / 2.0;

@@ -76,6 +76,8 @@ double o_angular_momentum(const double* p, const double* v) { return angular_mom
 double o_inclination_cosine(const double* p, const double* v) { return inclination_cosine(ld3(p), ld3(v)); }
 double o_inclination_rad(const double* p, const double* v) { return inclination_rad(ld3(p), ld3(v)); }
 double o_orbit_energy(const double* p, const double* v) { return orbit_energy(ld3(p), ld3(v)); }
+void o_laplace_vector(const double* p, const double* v, double* out) { st(out, laplace_vector(ld3(p), ld3(v)), 3); }
+double o_haversine(double lon1, double lat1, double lon2, double lat2, double r) { return haversine(lon1, lat1, lon2, lat2, r); }
 double o_angular_momentum_from_altitude(double ha, double hp) { return angular_momentum_from_altitude(ha, hp); }
 double o_orbit_energy_from_altitude(double ha, double hp) { return orbit_energy_from_altitude(ha, hp); }
 

@@ -41,7 +41,7 @@ CASES = [
     ("distance_vincenty", ("llh0", "llh1", "ang1", "ang2")), ("angular_momentum_vec", ("pos", "vel")),
     ("angular_momentum", ("pos", "vel")), ("inclination_rad", ("pos", "vel")), ("inclination_cosine", ("pos", "vel")),
     ("orbit_energy", ("pos", "vel")), ("angular_momentum_from_altitude", ("alt0", "alt1")),
-    ("orbit_energy_from_altitude", ("alt0", "alt1")),
+    ("orbit_energy_from_altitude", ("alt0", "alt1")), ("laplace_vector", ("pos", "vel")),
 ]
 
 
@@ -64,6 +64,15 @@ def _check(fn):
         assert np.array_equal(got2, want), (name, np.abs(got2 - want).max())
         one = getattr(gc, name)(*[a[3] for a in args], fn=fn)  # a single point, the reference's call shape
         assert np.array_equal(np.atleast_1d(one), want[3]), name
+    # utils_c.haversine rides on the same entry point (function code GC_HAVERSINE)
+    from gelato_b200.lib import utils_c
+
+    U = leaves.get("gmath").utils_c
+    lon1, lat1, lon2, lat2 = d["ang"][:, 0], d["ang"][:, 1], d["ang"][:, 2], d["llh"][:, 0]
+    got = utils_c.haversine(lon1, lat1, lon2, lat2, 6378137.0, fn=fn)
+    want = np.array([U.haversine(lon1[i], lat1[i], lon2[i], lat2[i], 6378137.0) for i in range(n)])
+    assert np.array_equal(got, want) and np.all(want > 0.0)
+    assert utils_c.haversine(lon1[2], lat1[2], lon2[2], lat2[2], 6378137.0, fn=fn) == want[2]
 
 
 def test_coordinate_leaves_match_the_oracle_on_the_host():

@@ -75,7 +75,7 @@ def test_coordinate_functions(pair):
         _eq(ca.quatrot(qq, v), cb.quatrot(qq, v), "quatrot")
         _eq(ca.normalize(v), cb.normalize(v), "normalize")
         for name in ("angular_momentum_vec", "angular_momentum", "inclination_rad", "inclination_cosine",
-                     "orbit_energy", "orbital_elements"):
+                     "orbit_energy", "orbital_elements", "laplace_vector"):
             _eq(getattr(ca, name)(p, v), getattr(cb, name)(p, v), name)
     for az, el, ro in np.random.default_rng(2).uniform(-180.0, 180.0, (50, 3)):
         _eq(ca.quat_from_euler(az, el, ro), cb.quat_from_euler(az, el, ro), "quat_from_euler")
@@ -84,6 +84,7 @@ def test_coordinate_functions(pair):
         _eq(ca.orbit_energy_from_altitude(ha, hp), cb.orbit_energy_from_altitude(ha, hp), "E(alt)")
     for a in np.random.default_rng(3).uniform(-80.0, 80.0, (40, 4)):
         _eq(ca.distance_vincenty(*a), cb.distance_vincenty(*a), "distance_vincenty")
+        _eq(A.utils_c.haversine(*a, 6378137.0), B.utils_c.haversine(*a, 6378137.0), "haversine")
 
 
 def test_tables_aero_iip_dynamics(pair):
