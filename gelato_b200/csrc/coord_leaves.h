@@ -7,8 +7,7 @@
  * (oracle/oracle_leaves.cpp), built from the device functions the kernels use.  host+device: tests/emu steps it.
  *
  * Item layout: a[GC_IN] and b[GC_IN] input vectors (unused entries ignored), t one scalar, out[GC_OUT].
- * Not offered: dcm_from_quat, quat_from_dcm, euler_from_dcm, dcm_from_thrustvector (3 x 3 matrices, no call site in
- * the reference's live code). */
+ * Matrices (the four DCM helpers) travel row-major, nine values. */
 #ifndef GELATO_B200_COORD_LEAVES_H_
 #define GELATO_B200_COORD_LEAVES_H_
 
@@ -16,16 +15,17 @@
 #include "initguess.h"
 #include "output.h"
 
-#define GC_IN 4
-#define GC_OUT 6
+#define GC_IN 9
+#define GC_OUT 9
 /* function codes GC_*: include/gelato_b200.h */
 
 P_HD int coord_leaf_n_out(int fn) {
   switch (fn) {
     case GC_QUATMULT: case GC_CONJ: case GC_NORMALIZE4: case GC_QUAT_ECI2ECEF: case GC_QUAT_ECEF2ECI:
     case GC_QUAT_ECEF2NEDG: case GC_QUAT_NEDG2ECEF: case GC_QUAT_ECI2NEDG: case GC_QUAT_NEDG2ECI:
-    case GC_QUAT_FROM_EULER: case GC_QUAT_NEDG2BODY:
+    case GC_QUAT_FROM_EULER: case GC_QUAT_NEDG2BODY: case GC_QUAT_FROM_DCM:
       return 4;
+    case GC_DCM_FROM_QUAT: case GC_DCM_FROM_THRUSTVECTOR: return 9;
     case GC_ORBITAL_ELEMENTS: return 6;
     case GC_DISTANCE_VINCENTY: case GC_ANGMOM: case GC_INCLINATION_RAD: case GC_INCLINATION_COS: case GC_ORBIT_ENERGY:
     case GC_ANGMOM_FROM_ALT: case GC_ENERGY_FROM_ALT: case GC_HAVERSINE:
@@ -57,6 +57,16 @@ P_HD Quat quat_from_euler_deg(double az_deg, double el_deg, double ro_deg) {
   gm_sincos(0.5 * el, &sy, &cy);
   gm_sincos(0.5 * ro, &sx, &cx);
   return eigen_quat_prod(eigen_quat_prod(q4(cz, 0.0, 0.0, sz), q4(cy, 0.0, sy, 0.0)), q4(cx, sx, 0.0, 0.0));
+}
+
+/* Eigen's normalized(): v / sqrt(squaredNorm) when the squared norm is positive, else v */
+P_HD Vec3 eigen_normalized3(Vec3 a) {
+  const double z = dot3(a, a);
+  if (z > 0.0) {
+    const double n = gm_sqrt(z);
+    return v3(a.x / n, a.y / n, a.z / n);
+  }
+  return a;
 }
 
 P_HD void coord_leaf(int fn, const double* a, const double* b, double t, double* out) {
@@ -128,6 +138,39 @@ P_HD void coord_leaf(int fn, const double* a, const double* b, double t, double*
     case GC_ENERGY_FROM_ALT: {
       const double ra = P_RA + a[0], rp = P_RA + a[1];
       out[0] = -P_MU / 2.0 / ((ra + rp) / 2.0);
+      return;
+    }
+    case GC_DCM_FROM_QUAT: { /* wrapper_coordinate.hpp:80-94 */
+      const double* q = a;
+      out[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3];
+      out[1] = 2 * (q[1] * q[2] + q[0] * q[3]);
+      out[2] = 2 * (q[1] * q[3] - q[0] * q[2]);
+      out[3] = 2 * (q[1] * q[2] - q[0] * q[3]);
+      out[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3];
+      out[5] = 2 * (q[2] * q[3] + q[0] * q[1]);
+      out[6] = 2 * (q[1] * q[3] + q[0] * q[2]);
+      out[7] = 2 * (q[2] * q[3] - q[0] * q[1]);
+      out[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+      return;
+    }
+    case GC_QUAT_FROM_DCM: { /* wrapper_coordinate.hpp:96-103 */
+      const double q0 = 0.5 * gm_sqrt(1 + a[0] + a[4] + a[8]);
+      r4 = q4(q0, (a[5] - a[7]) / (4 * q0), (a[6] - a[2]) / (4 * q0), (a[1] - a[3]) / (4 * q0));
+      break;
+    }
+    case GC_EULER_FROM_DCM: { /* wrapper :182-186, Coordinate.cpp:147-164: the angles of C^T, degrees */
+      const Vec3 e = euler_from_matrix(a[0], a[3], a[6], a[1], a[4], a[7], a[2], a[5], a[8]);
+      r3 = v3(e.x * 180.0 / P_PI, e.y * 180.0 / P_PI, e.z * 180.0 / P_PI);
+      break;
+    }
+    case GC_DCM_FROM_THRUSTVECTOR: { /* wrapper :188-191 (pos_eci, thrustvec_eci), Coordinate.cpp:176-191 */
+      const Vec3 xb = eigen_normalized3(b3), pn = eigen_normalized3(a3);
+      const Vec3 yb = (1.0 - dot3(xb, pn) < 1.0e-10) ? eigen_normalized3(cross3(v3(0.0, 0.0, 1.0), xb))
+                                                     : eigen_normalized3(cross3(xb, pn));
+      const Vec3 zb = cross3(xb, yb);
+      out[0] = xb.x; out[1] = xb.y; out[2] = xb.z;
+      out[3] = yb.x; out[4] = yb.y; out[5] = yb.z;
+      out[6] = zb.x; out[7] = zb.y; out[8] = zb.z;
       return;
     }
     case GC_LAPLACE_VECTOR: { /* wrapper_coordinate.hpp:238-244: v x h - mu r / |r| */

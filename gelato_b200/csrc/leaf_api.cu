@@ -368,7 +368,7 @@ int gelato_leaf_coordinate(int device, int32_t fn, int32_t n, const double* a, i
   LEAF_PROLOGUE
   if (fn < 0 || fn >= GC_N_FUNCTIONS || a_width < 0 || a_width > GC_IN || b_width < 0 || b_width > GC_IN || !out ||
       (a_width > 0 && !a) || (b_width > 0 && !b)) {
-    gelato_set_error_("gelato_leaf_coordinate: unknown function code, width outside 0..4 or null buffer");
+    gelato_set_error_("gelato_leaf_coordinate: unknown function code, width outside 0..9 or null buffer");
     return GELATO_ERR_ARG;
   }
   const int so = coord_leaf_n_out(fn);

@@ -62,16 +62,10 @@ P_HD double distance_vincenty(double lat1, double lon1, double lat2, double lon2
   return P_RB * A * (sigma - delta_sigma);
 }
 
-/* Coordinate.cpp:127-146 euler_from_quat (radians): Eigen toRotationMatrix().eulerAngles(2, 1, 0) + range fix-ups */
-P_HD Vec3 euler_from_quat(Quat q) {
-  const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
-  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
-  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
-  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
-  const double m00 = 1.0 - (tyy + tzz), m10 = txy + twz, m11 = 1.0 - (txx + tzz);
-  const double m01 = txy - twz, m02 = txz + twy, m12 = tyz - twx;
-  const double m20 = txz - twy, m21 = tyz + twx, m22 = 1.0 - (txx + tyy);
-  /* eulerAngles(2, 1, 0): i = 2, j = 1, k = 0, odd */
+/* Eigen's eulerAngles(2, 1, 0) of the rotation matrix m (i = 2, j = 1, k = 0, odd) + the reference's range fix-ups
+ * (Coordinate.cpp:129-145, :149-163), radians */
+P_HD Vec3 euler_from_matrix(double m00, double m01, double m02, double m10, double m11, double m12, double m20, double m21,
+                            double m22) {
   double r0 = gm_atan2(m10, m00), r1;
   const double c2 = gm_sqrt(m22 * m22 + m21 * m21);
   if (r0 < 0.0) {
@@ -92,6 +86,18 @@ P_HD Vec3 euler_from_quat(Quat q) {
   if (r0 < 0.0) r0 += 2.0 * P_PI;
   r2 = fmod(r2 + P_PI, 2.0 * P_PI) - P_PI;
   return v3(r0, r1, r2);
+}
+
+/* Coordinate.cpp:127-146 euler_from_quat (radians): Eigen toRotationMatrix().eulerAngles(2, 1, 0) + range fix-ups */
+P_HD Vec3 euler_from_quat(Quat q) {
+  const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  const double m00 = 1.0 - (tyy + tzz), m10 = txy + twz, m11 = 1.0 - (txx + tzz);
+  const double m01 = txy - twz, m02 = txz + twy, m12 = tyz - twx;
+  const double m20 = txz - twy, m21 = tyz + twx, m22 = 1.0 - (txx + tyy);
+  return euler_from_matrix(m00, m01, m02, m10, m11, m12, m20, m21, m22);
 }
 
 /* Coordinate.cpp:75-106 quat_eci2ned(pos_eci, t) */

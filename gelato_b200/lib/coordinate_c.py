@@ -32,8 +32,9 @@ _CODES = {name: k for k, name in enumerate(
     "quatmult conj normalize3 normalize4 quatrot ecef2geodetic geodetic2ecef ecef2eci eci2ecef vel_ecef2eci vel_eci2ecef "
     "quat_eci2ecef quat_ecef2eci quat_ecef2nedg quat_nedg2ecef quat_eci2nedg quat_nedg2eci quat_from_euler euler_from_quat "
     "quat_nedg2body orbital_elements distance_vincenty angular_momentum_vec angular_momentum inclination_rad "
-    "inclination_cosine orbit_energy angular_momentum_from_altitude orbit_energy_from_altitude laplace_vector haversine".split())}
-_N_OUT = {"orbital_elements": 6}
+    "inclination_cosine orbit_energy angular_momentum_from_altitude orbit_energy_from_altitude laplace_vector haversine "
+    "dcm_from_quat quat_from_dcm euler_from_dcm dcm_from_thrustvector".split())}
+_N_OUT = {"orbital_elements": 6, "dcm_from_quat": 9, "dcm_from_thrustvector": 9, "quat_from_dcm": 4}
 for _n in ("quatmult conj normalize4 quat_eci2ecef quat_ecef2eci quat_ecef2nedg quat_nedg2ecef quat_eci2nedg quat_nedg2eci "
            "quat_from_euler quat_nedg2body").split():
     _N_OUT[_n] = 4
@@ -207,3 +208,28 @@ def _haversine(lon1, lat1, lon2, lat2, r, fn=None):
     r, degrees in.  It shares the batch entry point of this module's functions."""
     a = np.stack(np.broadcast_arrays(arr(lon1), arr(lat1), arr(lon2), arr(lat2)), axis=-1)
     return _leaf("haversine", a, 4, t=r, fn=fn)
+
+
+# ---- the direction-cosine-matrix helpers (pybind_coordinate.cpp:33-36, 53-56); matrices as (3, 3) arrays, C[i][j] = C(i, j)
+def _mat(res):
+    res = np.asarray(res)
+    return res.reshape(3, 3) if res.ndim == 1 else res.reshape(-1, 3, 3)
+
+
+def dcm_from_quat(q, fn=None):
+    return _mat(_leaf("dcm_from_quat", q, 4, fn=fn))
+
+
+def quat_from_dcm(C, fn=None):
+    C = arr(C)
+    return _leaf("quat_from_dcm", C.reshape(9) if C.ndim == 2 else C.reshape(-1, 9), 9, fn=fn)
+
+
+def euler_from_dcm(C, fn=None):
+    """degrees (azimuth, elevation, roll), wrapper_coordinate.hpp:182-186"""
+    C = arr(C)
+    return _leaf("euler_from_dcm", C.reshape(9) if C.ndim == 2 else C.reshape(-1, 9), 9, fn=fn)
+
+
+def dcm_from_thrustvector(pos_eci, thrustvec_eci, fn=None):
+    return _mat(_leaf("dcm_from_thrustvector", pos_eci, 3, thrustvec_eci, 3, fn=fn))

@@ -416,14 +416,17 @@ int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, c
  *   27/28 angular_momentum_from_altitude / orbit_energy_from_altitude   ha, hp         1
  *   29 laplace_vector (pybind_coordinate.cpp:70)  pos[3]                 vel[3]           3
  *   30 haversine (utils_c, pybind_utils.cpp:29)   lon1, lat1, lon2, lat2 (deg)            r         1
- * (dcm_from_quat, quat_from_dcm, euler_from_dcm, dcm_from_thrustvector: not offered -- 3 x 3 matrices in or out and no
- * call site in the reference's live code.) */
+ *   31 dcm_from_quat (:33)                        q[4]                                              9 (row-major C)
+ *   32/33 quat_from_dcm (:35) / euler_from_dcm (:53, degrees)   C[9] row-major                     4 / 3
+ *   34 dcm_from_thrustvector (:55)                pos_eci[3]             thrustvec_eci[3]           9
+ * Widths: a and b up to 9 values per item, up to 9 outputs. */
 enum {
   GC_QUATMULT = 0, GC_CONJ, GC_NORMALIZE3, GC_NORMALIZE4, GC_QUATROT, GC_ECEF2GEODETIC, GC_GEODETIC2ECEF, GC_ECEF2ECI,
   GC_ECI2ECEF, GC_VEL_ECEF2ECI, GC_VEL_ECI2ECEF, GC_QUAT_ECI2ECEF, GC_QUAT_ECEF2ECI, GC_QUAT_ECEF2NEDG, GC_QUAT_NEDG2ECEF,
   GC_QUAT_ECI2NEDG, GC_QUAT_NEDG2ECI, GC_QUAT_FROM_EULER, GC_EULER_FROM_QUAT, GC_QUAT_NEDG2BODY, GC_ORBITAL_ELEMENTS,
   GC_DISTANCE_VINCENTY, GC_ANGMOM_VEC, GC_ANGMOM, GC_INCLINATION_RAD, GC_INCLINATION_COS, GC_ORBIT_ENERGY,
-  GC_ANGMOM_FROM_ALT, GC_ENERGY_FROM_ALT, GC_LAPLACE_VECTOR, GC_HAVERSINE, GC_N_FUNCTIONS
+  GC_ANGMOM_FROM_ALT, GC_ENERGY_FROM_ALT, GC_LAPLACE_VECTOR, GC_HAVERSINE, GC_DCM_FROM_QUAT, GC_QUAT_FROM_DCM,
+  GC_EULER_FROM_DCM, GC_DCM_FROM_THRUSTVECTOR, GC_N_FUNCTIONS
 };
 int gelato_leaf_coordinate(int device, int32_t fn, int32_t n, const double* a, int32_t a_width, const double* b, int32_t b_width,
                            const double* t, double* out);

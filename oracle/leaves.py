@@ -158,6 +158,10 @@ class OracleLeaves:
             inclination_cosine=lambda p, v: L.o_inclination_cosine(_p(v3(p)), _p(v3(v))),
             orbit_energy=lambda p, v: L.o_orbit_energy(_p(v3(p)), _p(v3(v))),
             laplace_vector=lambda p, v: self._v(L.o_laplace_vector, 3, _p(v3(p)), _p(v3(v))),
+            dcm_from_quat=lambda q: self._v(L.o_dcm_from_quat, 9, _p(v4(q))).reshape(3, 3),
+            quat_from_dcm=lambda C: self._v(L.o_quat_from_dcm, 4, _p(_a(C).reshape(9))),
+            euler_from_dcm=lambda C: self._v(L.o_euler_from_dcm, 3, _p(_a(C).reshape(9))),
+            dcm_from_thrustvector=lambda p, th: self._v(L.o_dcm_from_thrustvector, 9, _p(v3(p)), _p(v3(th))).reshape(3, 3),
             angular_momentum_from_altitude=lambda ha, hp: L.o_angular_momentum_from_altitude(_D(ha), _D(hp)),
             orbit_energy_from_altitude=lambda ha, hp: L.o_orbit_energy_from_altitude(_D(ha), _D(hp)),
         )

@@ -206,16 +206,8 @@ V4 c_quat_from_euler_deg(double az_deg, double el_deg, double ro_deg) {
 
 // :127-146 euler_from_quat: Eigen q.toRotationMatrix().eulerAngles(2, 1, 0) + range fix-ups (radians).
 // toRotationMatrix / eulerAngles are restated from Eigen's Quaternion.h / EulerAngles.h (as in ref_shim).
-V3 c_euler_from_quat(const V4& q) {
-  const double w = q[0], x = q[1], y = q[2], z = q[3];
-  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
-  const double twx = tx * w, twy = ty * w, twz = tz * w;
-  const double txx = tx * x, txy = ty * x, txz = tz * x;
-  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-  double m[3][3];
-  m[0][0] = 1.0 - (tyy + tzz); m[0][1] = txy - twz; m[0][2] = txz + twy;
-  m[1][0] = txy + twz; m[1][1] = 1.0 - (txx + tzz); m[1][2] = tyz - twx;
-  m[2][0] = txz - twy; m[2][1] = tyz + twx; m[2][2] = 1.0 - (txx + tyy);
+// eulerAngles(2, 1, 0) of a rotation matrix + the reference's range fix-ups (radians)
+V3 c_euler_from_matrix(const double m[3][3]) {
   // eulerAngles(2, 1, 0): i = 2, odd = 1, j = 1, k = 0
   const int i = 2, j = 1, k = 0;
   double res[3];
@@ -240,6 +232,18 @@ V3 c_euler_from_quat(const V4& q) {
   if (out[0] < 0.0) out[0] += 2.0 * M_PI;
   out[2] = std::fmod(out[2] + M_PI, 2.0 * M_PI) - M_PI;
   return out;
+}
+V3 c_euler_from_quat(const V4& q) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  double m[3][3];
+  m[0][0] = 1.0 - (tyy + tzz); m[0][1] = txy - twz; m[0][2] = txz + twy;
+  m[1][0] = txy + twz; m[1][1] = 1.0 - (txx + tzz); m[1][2] = tyz - twx;
+  m[2][0] = txz - twy; m[2][1] = tyz + twx; m[2][2] = 1.0 - (txx + tyy);
+  return c_euler_from_matrix(m);
 }
 
 // :197-245 (radians)
@@ -640,6 +644,45 @@ double o_orbit_energy(const double* p, const double* v) {  // :246-250
   double r = norm3(ld3(p));
   double vv = norm3(ld3(v));
   return 0.5 * vv * vv - E_mu / r;
+}
+// the four DCM helpers; matrices row-major, C[3 * i + j] = C(i, j)
+void o_dcm_from_quat(const double* q, double* C) {  // wrapper_coordinate.hpp:80-94
+  C[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3];
+  C[1] = 2 * (q[1] * q[2] + q[0] * q[3]);
+  C[2] = 2 * (q[1] * q[3] - q[0] * q[2]);
+  C[3] = 2 * (q[1] * q[2] - q[0] * q[3]);
+  C[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3];
+  C[5] = 2 * (q[2] * q[3] + q[0] * q[1]);
+  C[6] = 2 * (q[1] * q[3] + q[0] * q[2]);
+  C[7] = 2 * (q[2] * q[3] - q[0] * q[1]);
+  C[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+}
+void o_quat_from_dcm(const double* C, double* q) {  // wrapper_coordinate.hpp:96-103
+  q[0] = 0.5 * O_SQRT(1 + C[0] + C[4] + C[8]);
+  q[1] = (C[5] - C[7]) / (4 * q[0]);
+  q[2] = (C[6] - C[2]) / (4 * q[0]);
+  q[3] = (C[1] - C[3]) / (4 * q[0]);
+}
+void o_euler_from_dcm(const double* C, double* out) {  // wrapper :182-186, Coordinate.cpp:147-164: C^T's angles, degrees
+  double m[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) m[i][j] = C[3 * j + i];
+  V3 e = c_euler_from_matrix(m);
+  for (int i = 0; i < 3; i++) out[i] = e[i] * 180.0 / M_PI;
+}
+void o_dcm_from_thrustvector(const double* pos, const double* thrust, double* C) {  // wrapper :188-191, Coordinate.cpp:176-191
+  V3 xb = normalized3(ld3(thrust)), pn = normalized3(ld3(pos)), yb;
+  if (1.0 - dot3(xb, pn) < 1.0e-10) {
+    yb = normalized3(cross3(mk3(0.0, 0.0, 1.0), xb));
+  } else {
+    yb = normalized3(cross3(xb, pn));
+  }
+  V3 zb = cross3(xb, yb);
+  for (int j = 0; j < 3; j++) {  // columns xb | yb | zb, transposed: rows
+    C[j] = xb[j];
+    C[3 + j] = yb[j];
+    C[6 + j] = zb[j];
+  }
 }
 void o_laplace_vector(const double* p, const double* v, double* out) {  // wrapper_coordinate.hpp:238-244
   V3 r = ld3(p), vel = ld3(v);

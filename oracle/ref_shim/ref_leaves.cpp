@@ -76,6 +76,20 @@ double o_angular_momentum(const double* p, const double* v) { return angular_mom
 double o_inclination_cosine(const double* p, const double* v) { return inclination_cosine(ld3(p), ld3(v)); }
 double o_inclination_rad(const double* p, const double* v) { return inclination_rad(ld3(p), ld3(v)); }
 double o_orbit_energy(const double* p, const double* v) { return orbit_energy(ld3(p), ld3(v)); }
+static Eigen::Matrix3d ldc(const double* C) {
+  Eigen::Matrix3d m;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) m(i, j) = C[3 * i + j];
+  return m;
+}
+static void stc(double* C, const Eigen::Matrix3d& m) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = m(i, j);
+}
+void o_dcm_from_quat(const double* q, double* C) { stc(C, dcm_from_quat(ld4(q))); }
+void o_quat_from_dcm(const double* C, double* q) { st(q, quat_from_dcm(ldc(C)), 4); }
+void o_euler_from_dcm(const double* C, double* out) { st(out, euler_from_dcm(ldc(C)), 3); }
+void o_dcm_from_thrustvector(const double* pos, const double* thrust, double* C) { stc(C, dcm_from_thrustvector(ld3(pos), ld3(thrust))); }
 void o_laplace_vector(const double* p, const double* v, double* out) { st(out, laplace_vector(ld3(p), ld3(v)), 3); }
 double o_haversine(double lon1, double lat1, double lon2, double lat2, double r) { return haversine(lon1, lat1, lon2, lat2, r); }
 double o_angular_momentum_from_altitude(double ha, double hp) { return angular_momentum_from_altitude(ha, hp); }

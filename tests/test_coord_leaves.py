@@ -64,6 +64,21 @@ def _check(fn):
         assert np.array_equal(got2, want), (name, np.abs(got2 - want).max())
         one = getattr(gc, name)(*[a[3] for a in args], fn=fn)  # a single point, the reference's call shape
         assert np.array_equal(np.atleast_1d(one), want[3]), name
+    # the four DCM helpers: (3, 3) matrices in / out
+    C = gc.dcm_from_quat(d["q"], fn=fn)
+    assert C.shape == (n, 3, 3)
+    assert np.array_equal(C, np.array([O.dcm_from_quat(d["q"][i]) for i in range(n)]))
+    assert np.array_equal(gc.dcm_from_quat(d["q"][5], fn=fn), O.dcm_from_quat(d["q"][5]))
+    assert np.abs(np.einsum("nij,nkj->nik", C, C) - np.eye(3)).max() < 1e-12  # a rotation matrix (unit quaternions)
+    for name in ("quat_from_dcm", "euler_from_dcm"):
+        got = getattr(gc, name)(C, fn=fn)
+        assert np.array_equal(got, np.array([getattr(O, name)(C[i]) for i in range(n)])), name
+        assert np.array_equal(getattr(gc, name)(C[7], fn=fn), getattr(O, name)(C[7])), name
+    T = gc.dcm_from_thrustvector(d["pos"], d["vel"], fn=fn)
+    assert np.array_equal(T, np.array([O.dcm_from_thrustvector(d["pos"][i], d["vel"][i]) for i in range(n)]))
+    par = gc.dcm_from_thrustvector(d["pos"][:4], 3.0 * d["pos"][:4], fn=fn)  # thrust along the position: the z-axis branch
+    assert np.array_equal(par, np.array([O.dcm_from_thrustvector(d["pos"][i], 3.0 * d["pos"][i]) for i in range(4)]))
+    assert np.all(np.isfinite(par))
     # utils_c.haversine rides on the same entry point (function code GC_HAVERSINE)
     from gelato_b200.lib import utils_c
 

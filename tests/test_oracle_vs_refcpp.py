@@ -74,6 +74,12 @@ def test_coordinate_functions(pair):
         _eq(ca.conj(qq), cb.conj(qq), "conj")
         _eq(ca.quatrot(qq, v), cb.quatrot(qq, v), "quatrot")
         _eq(ca.normalize(v), cb.normalize(v), "normalize")
+        C = ca.dcm_from_quat(qq)
+        _eq(C, cb.dcm_from_quat(qq), "dcm_from_quat")
+        _eq(ca.quat_from_dcm(C), cb.quat_from_dcm(C), "quat_from_dcm")
+        _eq(ca.euler_from_dcm(C), cb.euler_from_dcm(C), "euler_from_dcm")
+        _eq(ca.dcm_from_thrustvector(p, v), cb.dcm_from_thrustvector(p, v), "dcm_from_thrustvector")
+        _eq(ca.dcm_from_thrustvector(p, 2.0 * p), cb.dcm_from_thrustvector(p, 2.0 * p), "dcm_from_thrustvector (parallel)")
         for name in ("angular_momentum_vec", "angular_momentum", "inclination_rad", "inclination_cosine",
                      "orbit_energy", "orbital_elements", "laplace_vector"):
             _eq(getattr(ca, name)(p, v), getattr(cb, name)(p, v), name)
