@@ -529,10 +529,22 @@ class ReducedSQP:
             # so with a level factor of sqrt(10) what is left is about half the last change.  The end point is then
             # classified by IPOPT's test on the ORIGINAL problem with multiplier lam on the dependent row. ----
             lv = hist["levels"]
-            if (len(lv) >= 2 and hist["best"] is not None and lv[-2]["infeasibility"] <= o["constr_tol"] and at_noise_floor()
+            hist.setdefault("level_best", []).append((hist["best"], hist["kkt"], hist.get("kkt_raw", np.nan), lam)
+                                                     if hist["best"] is not None else None)
+            kept = hist["level_best"]
+            if (len(lv) >= 2 and len(kept) >= 2 and kept[-1] is not None and kept[-2] is not None
+                    and lv[-2]["infeasibility"] <= o["constr_tol"]
                     and abs(lv[-1]["obj"] - lv[-2]["obj"]) <= o["obj_change_tol"] * max(1.0, abs(lv[-1]["obj"]))):
-                hist["settled"] = abs(lv[-1]["obj"] - lv[-2]["obj"])
-                break
+                # two levels that agree in the objective: the end point is the later one, unless only the earlier one
+                # passes the optimality test (the best feasible iterate of a level is a noisy sample of it)
+                for cand in (kept[-1], kept[-2]):
+                    if cand[1] <= o["noise_floor_tol"]:
+                        hist["best"], hist["kkt"], hist["kkt_raw"] = cand[0], cand[1], cand[2]
+                        pen["lam"] = np.array([cand[3]])
+                        hist["settled"] = abs(lv[-1]["obj"] - lv[-2]["obj"])
+                        break
+                if "settled" in hist:
+                    break
             if hist["it"] >= o["max_iter"]:
                 break
         if levels and hist["best"] is not None:
