@@ -599,3 +599,15 @@ def test_recorded_solution_passes_the_termination_test_through_the_cuda_callback
     assert np.array_equal(ends[0][0], ends[1][0]) and ends[0][1:] == ends[1][1:]
     assert prob.engine.launches > 100
     prob.close()
+
+
+def test_batched_solves_in_worker_processes_plumbing():
+    """solve_batch.solve_dispersed_processes (the solve leg of bench.py): two dispersed scenarios, a worker process
+    each with its own engine on GPU 0, a handful of solver iterations -- the record a rank reports, not a solve."""
+    from gelato_b200 import solve_batch
+
+    res = solve_batch.solve_dispersed_processes(helpers.example_inputs(), 2, 1, 0, device=0, iters=3, processes=2)
+    assert res["scenarios"] == 2 and res["worker_processes"] == 2 and len(res["statuses"]) == 2
+    assert res["converged"] == 0 and res["solves_per_hour"] == 0.0 and res["runs_per_hour"] > 0.0
+    assert res["launches"] > 20 and res["userObjCalls_mean"] > 10 and res["userSensCalls_mean"] >= 2
+    assert all(27000.0 < p < 29000.0 for p in res["payload_kg"])
