@@ -610,4 +610,4 @@ def test_batched_solves_in_worker_processes_plumbing():
     assert res["scenarios"] == 2 and res["worker_processes"] == 2 and len(res["statuses"]) == 2
     assert res["converged"] == 0 and res["solves_per_hour"] == 0.0 and res["runs_per_hour"] > 0.0
     assert res["launches"] > 20 and res["userObjCalls_mean"] > 10 and res["userSensCalls_mean"] >= 2
-    assert all(27000.0 < p < 29000.0 for p in res["payload_kg"])
+    assert all(2.0e4 < p < 3.5e4 for p in res["payload_kg"]), res["payload_kg"]
