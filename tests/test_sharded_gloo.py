@@ -148,3 +148,20 @@ def test_one_problem_over_two_ranks_equals_one_rank(tmp_path):
         for r in range(2):
             assert np.array_equal(np.load(os.path.join(str(tmp_path), "g%d_%d.npy" % (k, r))), g_want)
             assert np.array_equal(np.load(os.path.join(str(tmp_path), "pk%d_%d.npy" % (k, r))), pk_want)
+
+
+def test_sharded_problem_refuses_parts_that_do_not_cover_the_outputs():
+    """The parts are found by evaluation and CHECKED: an evaluator whose ranges leave output slots unwritten (here:
+    the last block dropped) must be refused at construction, not produce a vector with holes."""
+    from gelato_b200 import batch
+
+    emu, x = _one_problem("example")
+    ev = EmuRangeEvaluator(emu)
+    ev.n_blocks -= 1  # a rank layout that forgets one block
+    with pytest.raises(RuntimeError, match="written by no rank"):
+        batch.ShardedProblem(ev, x)
+    ok = batch.ShardedProblem(EmuRangeEvaluator(emu), x)  # the full range on one rank: the whole evaluation
+    g, pk = ok.pair(x)
+    g_want, pk_want = emu.eval_pair(x, packed=True)
+    assert np.array_equal(g.numpy(), g_want) and np.array_equal(pk.numpy(), pk_want)
+    assert [batch.split_range(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
