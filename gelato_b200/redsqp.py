@@ -48,6 +48,7 @@ import types
 
 import numpy as np
 import scipy.optimize as so
+import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from .ipsolve import IPSolver, Solution
@@ -58,6 +59,31 @@ STATE_ROWS = ("eqcon_init", "eqcon_dyn_mass", "eqcon_dyn_pos", "eqcon_dyn_vel", 
 
 class InnerFailure(Exception):
     pass
+
+
+class _Blocks:
+    """The sub-blocks of the sparse Jacobian that every `sens` needs (state equations x states, outer rows x
+    parameters, ...), cut by index maps that are computed once: fancy indexing of a SciPy sparse matrix costs more
+    than the factorisation that follows it here.  The maps come from the SAME indexing operations applied to a matrix
+    whose values are entry numbers, so a block built from them has the structure, the entry order and the values
+    SciPy's own slicing gives -- bit for bit; a Jacobian whose sparsity pattern differs from the one the maps were
+    made for (a dense block with an exact zero at another place) is sliced the slow way."""
+
+    def __init__(self, J, specs):
+        ids = J.copy()
+        ids.data = np.arange(1, J.nnz + 1, dtype=np.float64)
+        self.indptr, self.indices, self.shape = J.indptr.copy(), J.indices.copy(), J.shape
+        self.specs, self.maps = specs, {}
+        for name, (rows, cols) in specs.items():
+            M = ids[rows][:, cols].tocsc()
+            self.maps[name] = (M.data.astype(np.int64) - 1, M.indices.copy(), M.indptr.copy(), M.shape)
+
+    def cut(self, J):
+        """name -> block of J"""
+        if (J.shape == self.shape and J.nnz == self.indices.size and np.array_equal(J.indptr, self.indptr)
+                and np.array_equal(J.indices, self.indices)):
+            return {name: sp.csc_matrix((J.data[src], ind, ptr), shape=shape) for name, (src, ind, ptr, shape) in self.maps.items()}
+        return {name: J[rows][:, cols].tocsc() for name, (rows, cols) in self.specs.items()}
 
 
 class ReducedSQP:
@@ -171,8 +197,14 @@ class ReducedSQP:
         # ---- the inner solve: states from parameters ----
         S = {"x": x0.copy(), "lu": None, "dsdp": None, "p_lin": None, "x_lin": None, "cache": {}, "evals": 0}
 
+        cutter = _Blocks(J0, {"Fs": (f_rows, s_cols), "Fp": (f_rows, p_cols), "Es": (e_rows, s_cols), "Ep": (e_rows, p_cols),
+                              "Is": (i_rows, s_cols), "Ip": (i_rows, p_cols)})
+
         def factor(J):
-            S["lu"] = spla.splu(J[f_rows][:, s_cols].tocsc())
+            """LU of the state equations' Jacobian with respect to the states; returns the blocks of J"""
+            blk = cutter.cut(J)
+            S["lu"] = spla.splu(blk["Fs"])
+            return blk
 
         factor(J0)
 
@@ -253,13 +285,13 @@ class ReducedSQP:
                 return dict(S["last_good"], ok=False, obj=e["obj"], c=None)
             if want_jac and "Je" not in e:
                 grad, J = jacobian(e["x"], e["f"])
-                factor(J)
-                dsdp = -S["lu"].solve(J[f_rows][:, p_cols].toarray())
+                blk = factor(J)
+                dsdp = -S["lu"].solve(blk["Fp"].toarray())
                 S["dsdp"], S["p_lin"], S["x_lin"] = dsdp, pv.copy(), e["x"].copy()
                 e["g"] = (grad[p_cols] + dsdp.T @ grad[s_cols]) / w
-                e["Je"] = (J[e_rows][:, p_cols].toarray() + J[e_rows][:, s_cols] @ dsdp) / w
-                e["Ji"] = (J[i_rows][:, p_cols].toarray() + J[i_rows][:, s_cols] @ dsdp) / w
-                e["grad"], e["J"] = grad, J
+                e["Je"] = (blk["Ep"].toarray() + blk["Es"] @ dsdp) / w
+                e["Ji"] = (blk["Ip"].toarray() + blk["Is"] @ dsdp) / w
+                e["grad"], e["blk"] = grad, blk
                 S["last_good"] = e
             return e
 
@@ -306,12 +338,12 @@ class ReducedSQP:
             lam_e[pen["rows"]] = pen["lam"]
             norm1 = np.abs(mult).sum() + np.abs(pen["lam"]).sum()
             count = mult.size + pen["lam"].size
-            if full_space and "J" in e:
-                J = e["J"]
+            if full_space and "blk" in e:
+                blk = e["blk"]
                 mu = np.zeros(i_rows.size)
                 mu[act] = mult[free_e.size: free_e.size + act.size]
-                rhs_s = e["grad"][s_cols] - J[e_rows][:, s_cols].T @ lam_e - J[i_rows][:, s_cols].T @ mu
-                lam_f = spla.splu(J[f_rows][:, s_cols].T.tocsc()).solve(np.asarray(rhs_s).ravel())
+                rhs_s = e["grad"][s_cols] - blk["Es"].T @ lam_e - blk["Is"].T @ mu
+                lam_f = spla.splu(blk["Fs"].T.tocsc()).solve(np.asarray(rhs_s).ravel())
                 norm1 += np.abs(lam_f).sum()
                 count = m + n_bound_mult
             s_d = max(100.0, norm1 / max(count, 1)) / 100.0
