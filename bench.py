@@ -22,6 +22,11 @@ CompiledPlan.eval_counts / DESIGN.md.
   e2e     the same step through the host-buffer C-ABI call (gelato_eval_pair_packed): x from
           page-locked host memory -> device, the kernels, g and the packed Jacobian values back
           into host buffers as contiguous copies, wall clock.
+  solves  after the timed steps (not inside them): `--solve-scenarios` dispersed scenarios of the shipped
+          example per GPU (default 4; 0 = skip) solved from the reference's initial guess by the host-side
+          stand-in solver gelato_b200/redsqp.py (NOT IPOPT) on the CUDA callbacks, one worker process each;
+          `solves_per_hour` = converged solves of all ranks / wall time (max over ranks).  The reference arm
+          solves the same scenarios on the CPU oracle's callbacks.
 Multi-GPU: scenarios are independent NLPs; each rank owns `--scenarios` of them
 (weak scaling), no data-path collective (DESIGN.md "multi-GPU").
 
