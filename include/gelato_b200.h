@@ -392,7 +392,7 @@ int gelato_init_rocket_simulation(int device, int32_t n, const double* x_init, c
                                   const double* t_out, int32_t n_out, double dt, double* x_out, double* u_out);
 
 /* The coordinate_c leaves that are not on the NLP path (/root/reference/src/pybind_coordinate.cpp:28-78), n items by
- * one launch, one thread per item.  fn: GC_* below; a / b: per-item input vectors of a_width / b_width doubles (0..4);
+ * one launch, one thread per item.  fn: GC_* below; a / b: per-item input vectors of a_width / b_width doubles (0..9);
  * t: per-item time or NULL; out: [n][width of the function's result].
  *   code  function (reference name)            a                      b            t   out
  *    0    quatmult                             q[4]                   p[4]             4
